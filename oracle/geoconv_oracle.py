@@ -1,0 +1,327 @@
+"""CPU oracle for the ConvIntrinsic + AngularMaxPooling hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``geoconv_b200/`` may import this module; only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
+legs use it, and there only as the checker or as the timed CPU baseline.
+
+It restates, with stock ``torch`` CPU ops and in the reference's own evaluation order
+(materialised gather -> weighted sum -> prior einsum -> one roll + einsum per rotation ->
+stack/permute -> activation; norm -> argmax -> row select), what these reference functions compute:
+
+* ``create_template_matrix``              src/geoconv/preprocessing/barycentric_coordinates.py:91-124
+* ``ConvGeodesic.define_kernel_values``   src/geoconv/pytorch/layers/conv_geodesic.py:52-68 (+ :7-41)
+* ``ConvDirac`` / ``ConvZero`` priors     src/geoconv/pytorch/layers/conv_dirac.py:13-26, conv_zero.py:12-15
+* ``ConvIntrinsic._signal_retrieval``     src/geoconv/pytorch/layers/conv_intrinsic.py:198-240
+* ``ConvIntrinsic._patch_operator``       src/geoconv/pytorch/layers/conv_intrinsic.py:173-196
+* ``ConvIntrinsic.forward``               src/geoconv/pytorch/layers/conv_intrinsic.py:118-171
+* ``AngularMaxPooling.forward``           src/geoconv/pytorch/layers/angular_max_pooling.py:9-29
+
+Parity pinning: the reference ships no tests or golden vectors for this path, so
+the oracle is pinned against outputs of the *executed* reference, generated in the build container
+by ``tests/golden/make_golden.py`` and committed under ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` checks every fixture.  Gradients come from autograd over this
+restatement (exactly how the reference obtains them) and, independently, from the closed-form
+expressions in :func:`conv_amp_backward_closed_form`.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+# --------------------------------------------------------------------------------------------
+# Activations: the six entries of the reference's ACTIVATIONS table (conv_intrinsic.py:10-17),
+# all with torch's default hyper-parameters.  The integer ids are the C-ABI's ``act_id``.
+# --------------------------------------------------------------------------------------------
+ACT_IDS = {"relu": 0, "elu": 1, "leaky_relu": 2, "selu": 3, "sigmoid": 4, "tanh": 5}
+
+_SELU_ALPHA = 1.6732632423543772848170429916717
+_SELU_SCALE = 1.0507009873554804934193349852946
+
+
+def activation(name: str, x: torch.Tensor) -> torch.Tensor:
+    if name == "relu":
+        return torch.clamp_min(x, 0.0)
+    if name == "elu":
+        return torch.where(x > 0, x, torch.expm1(x))
+    if name == "leaky_relu":
+        return torch.where(x > 0, x, 0.01 * x)
+    if name == "selu":
+        return _SELU_SCALE * torch.where(x > 0, x, _SELU_ALPHA * torch.expm1(x))
+    if name == "sigmoid":
+        return torch.sigmoid(x)
+    if name == "tanh":
+        return torch.tanh(x)
+    raise KeyError(name)
+
+
+def activation_grad_from_output(name: str, y: torch.Tensor) -> torch.Tensor:
+    """d act / d pre-activation written in terms of the activation's *output* y."""
+    one = torch.ones_like(y)
+    if name == "relu":
+        return (y > 0).to(y.dtype)
+    if name == "elu":
+        return torch.where(y > 0, one, y + 1.0)
+    if name == "leaky_relu":
+        return torch.where(y > 0, one, 0.01 * one)
+    if name == "selu":
+        return torch.where(y > 0, _SELU_SCALE * one, y + _SELU_SCALE * _SELU_ALPHA)
+    if name == "sigmoid":
+        return y * (1.0 - y)
+    if name == "tanh":
+        return 1.0 - y * y
+    raise KeyError(name)
+
+
+# --------------------------------------------------------------------------------------------
+# Build-time constants
+# --------------------------------------------------------------------------------------------
+def template_matrix(n_radial: int, n_angular: int, radius: float) -> np.ndarray:
+    """Polar template grid (R, A, 2): rho_j = j*radius/R (j=1..R), theta_k = 2*pi*k/A (k=1..A).
+
+    Follows barycentric_coordinates.py:91-124 (polar branch).
+    """
+    rho = (np.arange(1, n_radial + 1, dtype=np.float64) * radius) / n_radial
+    theta = (2 * np.arange(1, n_angular + 1, dtype=np.float64) * np.pi) / n_angular
+    out = np.zeros((n_radial, n_angular, 2), dtype=np.float64)
+    out[:, :, 0] = rho[:, None]
+    out[:, :, 1] = theta[None, :]
+    return out
+
+
+def geodesic_prior(template: np.ndarray) -> np.ndarray:
+    """Gaussian-in-(rho, theta) interpolation coefficients, soft-maxed per (r, a).
+
+    Follows conv_geodesic.py:52-68 with normal_pdf (:11-41) and angle_distance (:7-8):
+    K[r,a,x,y] = softmax_{x,y}( c * exp(-0.5*((rho_x-rho_r)^2/var_rho + dtheta^2/var_theta)) ),
+    dtheta = min(|t1-t2|, 2*pi-|t1-t2|), variances = population variance over the template.
+    """
+    rho = template[:, :, 0]
+    theta = template[:, :, 1]
+    var_rho = rho.var()
+    var_theta = theta.var()
+    coeff = 1.0 / np.sqrt((2 * np.pi) ** 2 * var_rho * var_theta)
+    d_rho = rho[None, None, :, :] - rho[:, :, None, None]
+    hi = np.maximum(theta[:, :, None, None], theta[None, None, :, :])
+    lo = np.minimum(theta[:, :, None, None], theta[None, None, :, :])
+    d_theta = np.minimum(hi - lo, lo + 2.0 * np.pi - hi)
+    pdf = coeff * np.exp(-0.5 * (d_rho * d_rho / var_rho + d_theta * d_theta / var_theta))
+    flat = pdf.reshape(pdf.shape[0], pdf.shape[1], -1)
+    flat = flat - flat.max(axis=-1, keepdims=True)
+    e = np.exp(flat)
+    sm = e / e.sum(axis=-1, keepdims=True)
+    return sm.reshape(pdf.shape)
+
+
+def dirac_prior(template: np.ndarray) -> np.ndarray:
+    """Identity on the (r, a) axis (conv_dirac.py:13-26; visualisation only - Dirac skips the prior)."""
+    r, a = template.shape[:2]
+    return np.eye(r * a, dtype=np.float64).reshape(r, a, r, a)
+
+
+def zero_prior(template: np.ndarray) -> np.ndarray:
+    """All-zero coefficients (conv_zero.py:12-15)."""
+    r, a = template.shape[:2]
+    return np.zeros((r, a, r, a), dtype=np.float64)
+
+
+PRIORS = {"geodesic": geodesic_prior, "dirac": dirac_prior, "zero": zero_prior}
+
+
+def rotation_offsets(n_angular: int, rotation_delta: int) -> list[int]:
+    """arange(0, A, delta) - conv_intrinsic.py:152-154."""
+    return list(range(0, n_angular, rotation_delta))
+
+
+# --------------------------------------------------------------------------------------------
+# Forward, stage by stage
+# --------------------------------------------------------------------------------------------
+def split_bary(bary: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """bary (V,R,A,3,2) -> (idx int64 (V,R,A,3), w float32 (V,R,A,3)).
+
+    conv_intrinsic.py:213-221: cast to float32 first, then ``.long()`` (truncation toward zero).
+    """
+    b = bary.to(torch.float32)
+    return b[..., 0].long(), b[..., 1]
+
+
+def signal_retrieval(signal: torch.Tensor, bary: torch.Tensor) -> torch.Tensor:
+    """I[k,r,a,:] = sum_j w[k,r,a,j] * X[idx[k,r,a,j], :]   (conv_intrinsic.py:198-240)."""
+    x = signal.to(torch.float32) if signal.dtype != torch.float64 else signal
+    idx, w = split_bary(bary)
+    w = w.to(x.dtype)
+    v, r, a, _ = idx.shape
+    rows = x.index_select(0, idx.reshape(-1)).reshape(v, r, a, 3, x.shape[1])
+    return (rows * w.unsqueeze(-1)).sum(dim=-2)
+
+
+def patch_operator(interp: torch.Tensor, prior: torch.Tensor | None) -> torch.Tensor:
+    """P[k,r,a,f] = sum_{x,y} K[r,a,x,y] * I[k,x,y,f]; identity when prior is None (:173-196)."""
+    if prior is None:
+        return interp
+    return torch.einsum("raxy,kxyf->kraf", prior.to(interp.dtype), interp)
+
+
+def conv_forward(signal, bary, w_neighbor, w_self, bias, prior, act="relu", rotation_delta=1,
+                 orientations=None):
+    """ConvIntrinsic.forward (:118-171).  Returns Y (V, n_rot, T).
+
+    ``prior`` is the (R,A,R,A) coefficient tensor or ``None`` for include_prior=False.
+    """
+    a = bary.shape[2]
+    centre = torch.einsum("tef,kf->ket", w_self, signal)
+    patches = patch_operator(signal_retrieval(signal, bary), prior)
+    shifts = rotation_offsets(a, rotation_delta) if orientations is None else [int(o) for o in orientations]
+    per_rot = [
+        torch.einsum("traf,kraf->kt", w_neighbor, torch.roll(patches, shifts=o, dims=2))
+        for o in shifts
+    ]
+    neigh = torch.stack(per_rot).permute(1, 0, 2)
+    return activation(act, centre + neigh + bias)
+
+
+def amp_forward(y: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """AngularMaxPooling.forward (:27-29).  Returns (Z (V,T), argmax int32 (V,)); first max wins."""
+    norms = torch.linalg.vector_norm(y, ord=2, dim=-1)
+    arg = torch.argmax(norms, dim=1)
+    return y[torch.arange(y.shape[0]), arg], arg.to(torch.int32)
+
+
+def conv_amp_forward(signal, bary, w_neighbor, w_self, bias, prior, act="relu", rotation_delta=1):
+    y = conv_forward(signal, bary, w_neighbor, w_self, bias, prior, act, rotation_delta)
+    z, arg = amp_forward(y)
+    return y, z, arg
+
+
+def conv_amp_forward_backward(signal, bary, w_neighbor, w_self, bias, prior, grad_z,
+                              act="relu", rotation_delta=1):
+    """Forward + autograd backward, the way the reference obtains gradients.
+
+    Returns dict with y, z, argmax, d_signal, d_w_neighbor, d_w_self, d_bias.
+    """
+    xs = signal.detach().clone().requires_grad_(True)
+    wn = w_neighbor.detach().clone().requires_grad_(True)
+    ws = w_self.detach().clone().requires_grad_(True)
+    bs = bias.detach().clone().requires_grad_(True)
+    y, z, arg = conv_amp_forward(xs, bary, wn, ws, bs, prior, act, rotation_delta)
+    gx, gwn, gws, gb = torch.autograd.grad(z, [xs, wn, ws, bs], grad_outputs=grad_z, allow_unused=True)
+    if gwn is None:
+        gwn = torch.zeros_like(wn)
+    return {"y": y.detach(), "z": z.detach(), "argmax": arg, "d_signal": gx,
+            "d_w_neighbor": gwn, "d_w_self": gws, "d_bias": gb}
+
+
+# --------------------------------------------------------------------------------------------
+# Closed forms the CUDA kernels implement (SURVEY.md §8a "algebraic restatement"), in any dtype
+# --------------------------------------------------------------------------------------------
+def fold_prior(w_neighbor: torch.Tensor, prior: torch.Tensor | None) -> torch.Tensor:
+    """Weff[t,x,y,f] = sum_{r,a} W[t,r,a,f] * K[r,a,x,y]  (identity when prior is None)."""
+    if prior is None:
+        return w_neighbor
+    return torch.einsum("traf,raxy->txyf", w_neighbor, prior.to(w_neighbor.dtype))
+
+
+def prior_is_rotation_symmetric(prior: np.ndarray, rotation_delta: int = 1, tol: float = 1e-12) -> bool:
+    """K[r,a,x,y] == K[r,(a+s)%A,x,(y+s)%A] for every rotation step s - what makes folding legal."""
+    a = prior.shape[1]
+    for s in range(0, a, rotation_delta):
+        if not np.allclose(prior, np.roll(np.roll(prior, s, axis=1), s, axis=3), atol=tol, rtol=0):
+            return False
+    return True
+
+
+def conv_forward_folded(signal, bary, w_eff, w_self, bias, act="relu", offsets=(0,)):
+    """Y[k,i,t] = act(X[k]·Wself[t] + sum_{x,y,f} Weff[t,x,(y+o_i)%A,f] * I[k,x,y,f] + b[t])."""
+    interp = signal_retrieval(signal, bary).to(w_eff.dtype)
+    centre = signal.to(w_eff.dtype) @ w_self[:, 0, :].T
+    outs = []
+    for o in offsets:
+        outs.append(torch.einsum("txyf,kxyf->kt", torch.roll(w_eff, shifts=-int(o), dims=2), interp))
+    pre = torch.stack(outs, dim=1) + centre[:, None, :] + bias.reshape(1, 1, -1)
+    return activation(act, pre)
+
+
+def conv_amp_backward_closed_form(signal, bary, w_eff, w_self, z, rot_offset, grad_z, act="relu"):
+    """AMP-sparse backward in closed form.
+
+    ``rot_offset[k]`` is the angular shift o of the rotation AMP selected for vertex k.
+    Returns (d_signal, d_w_eff, d_w_self, d_bias).
+    """
+    dt = w_eff.dtype
+    idx, w = split_bary(bary)
+    w = w.to(dt)
+    v, r, a, _ = idx.shape
+    f = signal.shape[1]
+    h = grad_z.to(dt) * activation_grad_from_output(act, z.to(dt))
+    interp = signal_retrieval(signal.to(dt), bary)
+    ar = torch.arange(a)
+    # rotated interpolation seen by the weights: Irot[k,x,y',f] = I[k,x,(y'-o_k)%A,f]
+    src = (ar[None, :] - rot_offset[:, None].long()) % a
+    irot = torch.gather(interp, 2, src[:, None, :, None].expand(v, r, a, f))
+    d_w_eff = torch.einsum("kt,kxyf->txyf", h, irot)
+    # dI[k,x,y,f] = sum_t h[k,t] * Weff[t,x,(y+o_k)%A,f]
+    d_full = torch.einsum("kt,txyf->kxyf", h, w_eff)
+    dst = (ar[None, :] + rot_offset[:, None].long()) % a
+    d_interp = torch.gather(d_full, 2, dst[:, None, :, None].expand(v, r, a, f))
+    d_signal = h @ w_self[:, 0, :]
+    contrib = (d_interp.unsqueeze(3) * w.unsqueeze(-1)).reshape(-1, f)
+    d_signal = d_signal.index_add(0, idx.reshape(-1), contrib)
+    d_w_self = (h.T @ signal.to(dt)).unsqueeze(1)
+    d_bias = h.sum(dim=0, keepdim=True)
+    return d_signal, d_w_eff, d_w_self, d_bias
+
+
+def unfold_prior_grad(d_w_eff: torch.Tensor, prior: torch.Tensor | None) -> torch.Tensor:
+    """dW[t,r,a,f] = sum_{x,y} dWeff[t,x,y,f] * K[r,a,x,y]."""
+    if prior is None:
+        return d_w_eff
+    return torch.einsum("txyf,raxy->traf", d_w_eff, prior.to(d_w_eff.dtype))
+
+
+# --------------------------------------------------------------------------------------------
+# Seeded input generators shared by tests and bench (workload S1)
+# --------------------------------------------------------------------------------------------
+def make_bary(v, r, a, seed=1, fallback_frac=0.02, pool=None, dtype=torch.float32, v_src=None):
+    """Synthetic barycentric tensor (V,R,A,3,2): uniform-random indices stored as floats,
+    weights normalised to sum 1, a fraction of (k,r,a) entries set to the (0,0) fallback
+    (barycentric_coordinates.py:69).  ``pool``: each vertex draws from a private pool of that
+    many random vertices (patch-local reuse)."""
+    g = torch.Generator().manual_seed(seed)
+    v_src = v if v_src is None else v_src
+    if pool is None:
+        idx = torch.randint(0, v_src, (v, r, a, 3), generator=g)
+    else:
+        pools = torch.randint(0, v_src, (v, pool), generator=g)
+        pick = torch.randint(0, pool, (v, r * a * 3), generator=g)
+        idx = torch.gather(pools, 1, pick).reshape(v, r, a, 3)
+    w = torch.rand((v, r, a, 3), generator=g)
+    w = w / w.sum(dim=-1, keepdim=True)
+    if fallback_frac > 0:
+        dead = torch.rand((v, r, a), generator=g) < fallback_frac
+        idx[dead] = 0
+        w[dead] = 0.0
+    return torch.stack([idx.to(dtype), w.to(dtype)], dim=-1)
+
+
+def make_signal(v, f, seed=1, kind="shot"):
+    g = torch.Generator().manual_seed(seed + 7919)
+    if kind == "shot":
+        x = torch.rand((v, f), generator=g)
+        return x / torch.linalg.vector_norm(x, dim=1, keepdim=True)
+    return torch.randn((v, f), generator=g)
+
+
+def xavier_uniform(shape, gen):
+    """nn.init.xavier_uniform_ fan computation for the reference's parameter shapes."""
+    recept = 1
+    for s in shape[2:]:
+        recept *= s
+    fan_in, fan_out = shape[1] * recept, shape[0] * recept
+    bound = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(shape, generator=gen) * 2 - 1) * bound
+
+
+def make_weights(t, r, a, f, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (xavier_uniform((t, r, a, f), g), xavier_uniform((t, 1, f), g), xavier_uniform((1, t), g))
