@@ -1,0 +1,124 @@
+// extern "C" dispatch for the forward / backward entry points (see include/geoconv_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "gcb_common.cuh"
+
+namespace gcb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int make_rot_table(const int32_t* rot_off_host, int n_rot, int A, RotTable* out) {
+  GCB_REQUIRE(rot_off_host, GCB_EINVAL, "rot_off_host is null");
+  GCB_REQUIRE(n_rot > 0 && n_rot <= GCB_MAX_ROT, GCB_EINVAL, "n_rot=%d outside [1,%d]", n_rot, GCB_MAX_ROT);
+  for (int i = 0; i < GCB_MAX_ROT; ++i) {
+    int o = i < n_rot ? rot_off_host[i] : 0;
+    out->off[i] = ((o % A) + A) % A;  // torch.roll accepts any integer shift
+  }
+  return GCB_OK;
+}
+
+static int check_shape(int v_out, int v_src, int R, int A, int F, int T) {
+  GCB_REQUIRE(v_out >= 0 && v_src > 0 && v_out <= v_src, GCB_EINVAL,
+              "need 0 <= v_out (%d) <= v_src (%d)", v_out, v_src);
+  GCB_REQUIRE(R > 0 && A > 0 && F > 0 && T > 0, GCB_EINVAL, "R,A,F,T must be positive");
+  GCB_REQUIRE((int64_t)v_out * R * A * 3 < (1ll << 31), GCB_EUNSUPPORTED, "V*R*A*3 exceeds int32 slot ids");
+  return GCB_OK;
+}
+
+}  // namespace gcb
+
+using namespace gcb;
+
+extern "C" int gcb_abi_version(void) { return GCB_ABI_VERSION; }
+extern "C" const char* gcb_last_error(void) { return g_err; }
+
+extern "C" int gcb_tc_supported(int32_t R, int32_t A, int32_t F, int32_t T, int32_t n_rot) {
+  return tc_supported(R, A, F, T, n_rot) ? 1 : 0;
+}
+
+extern "C" size_t gcb_conv_fwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A,
+                                               int32_t F, int32_t T, int32_t n_rot, int precision) {
+  (void)v_src;
+  size_t y_tmp = align_up((size_t)v_out * n_rot * T * sizeof(float), 256);  // when caller passes y == NULL
+  if (precision == GCB_PREC_FP32) return y_tmp + ffma_fwd_workspace_bytes(v_out, R, A, F) + 256;
+  return y_tmp + tc_fwd_workspace_bytes(v_out, R, A, F, T, n_rot, precision) + 256;
+}
+
+extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
+                            const float* w_self, const float* bias, const int32_t* rot_off_host,
+                            int32_t n_rot, int32_t v_out, int32_t v_src, int32_t R, int32_t A,
+                            int32_t F, int32_t T, int act, int precision, float* y, float* z,
+                            int32_t* argmax, void* workspace, size_t workspace_bytes, void* stream) {
+  GCB_REQUIRE(x && idx && w && w_self && bias, GCB_EINVAL, "gcb_conv_fwd: null input pointer");
+  GCB_REQUIRE(y || z, GCB_EINVAL, "gcb_conv_fwd: need y and/or z");
+  GCB_REQUIRE((z == nullptr) == (argmax == nullptr), GCB_EINVAL, "gcb_conv_fwd: z and argmax go together");
+  GCB_REQUIRE(act >= 0 && act <= GCB_ACT_TANH, GCB_EINVAL, "gcb_conv_fwd: unknown activation %d", act);
+  int rc = check_shape(v_out, v_src, R, A, F, T);
+  if (rc) return rc;
+  RotTable rot;
+  rc = make_rot_table(rot_off_host, n_rot, A, &rot);
+  if (rc) return rc;
+  if (v_out == 0) return GCB_OK;
+  GCB_REQUIRE(workspace && workspace_bytes >= gcb_conv_fwd_workspace_bytes(v_out, v_src, R, A, F, T, n_rot, precision),
+              GCB_EWORKSPACE, "gcb_conv_fwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  size_t y_tmp = align_up((size_t)v_out * n_rot * T * sizeof(float), 256);
+  float* y_out = y ? y : (float*)ws;
+  ws += y_tmp;
+  workspace_bytes -= y_tmp;
+  if (precision == GCB_PREC_FP32 || !w_eff) {  // centre-only (w_eff == NULL) is a tiny GEMM: CUDA cores
+    rc = ffma_conv_fwd(x, idx, w, w_eff, w_self, bias, rot, n_rot, v_out, v_src, R, A, F, T, act, y_out, ws, st);
+  } else if (precision == GCB_PREC_TF32 || precision == GCB_PREC_TF32X3) {
+    GCB_REQUIRE(tc_supported(R, A, F, T, n_rot), GCB_EUNSUPPORTED,
+                "gcb_conv_fwd: tcgen05 path does not support R=%d A=%d F=%d T=%d n_rot=%d", R, A, F, T, n_rot);
+    rc = tc_conv_fwd(x, idx, w, w_eff, w_self, bias, rot, n_rot, v_out, v_src, R, A, F, T, act, precision,
+                     y_out, ws, workspace_bytes, st);
+  } else {
+    GCB_REQUIRE(false, GCB_EINVAL, "gcb_conv_fwd: unknown precision %d", precision);
+  }
+  if (rc) return rc;
+  if (z) rc = amp_fwd(y_out, v_out, n_rot, T, z, argmax, st);
+  return rc;
+}
+
+extern "C" size_t gcb_conv_bwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A,
+                                               int32_t F, int32_t T, int precision) {
+  (void)v_src; (void)T; (void)precision;
+  size_t d_full = align_up((size_t)v_out * R * A * F * sizeof(float), 256);
+  return d_full + ffma_bwd_workspace_bytes(v_out, R, A, F) + 256;
+}
+
+extern "C" int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
+                            const float* w_self, const float* h, const int32_t* rot_sel,
+                            const int32_t* csr_row_ptr, const int32_t* csr_entries, int32_t v_out,
+                            int32_t v_src, int32_t R, int32_t A, int32_t F, int32_t T, int precision,
+                            int accumulate, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  GCB_REQUIRE(x && idx && w && w_self && h && rot_sel, GCB_EINVAL, "gcb_conv_bwd: null input pointer");
+  GCB_REQUIRE(!d_x || !w_eff || (csr_row_ptr && csr_entries), GCB_EINVAL, "gcb_conv_bwd: d_x needs the CSR");
+  GCB_REQUIRE(d_w_eff && d_w_self && d_bias, GCB_EINVAL, "gcb_conv_bwd: null output pointer");
+  int rc = check_shape(v_out, v_src, R, A, F, T);
+  if (rc) return rc;
+  GCB_REQUIRE(v_out > 0, GCB_EINVAL, "gcb_conv_bwd: empty input");
+  GCB_REQUIRE(workspace && workspace_bytes >= gcb_conv_bwd_workspace_bytes(v_out, v_src, R, A, F, T, precision),
+              GCB_EWORKSPACE, "gcb_conv_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  float* d_full = (float*)ws;
+  ws += align_up((size_t)v_out * R * A * F * sizeof(float), 256);
+  // TODO(tc-bwd): precision TF32/TF32X3 currently share the fp32 CUDA-core contraction.
+  rc = ffma_conv_bwd(x, idx, w, w_eff, h, rot_sel, v_out, v_src, R, A, F, T, accumulate, d_w_eff, d_w_self,
+                     d_bias, d_x ? d_full : nullptr, ws, st);
+  if (rc || !d_x) return rc;
+  return csr_reduce_dx(w_eff ? d_full : nullptr, w, h, w_self, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T,
+                       accumulate, d_x, st);
+}

@@ -1,0 +1,170 @@
+// One-time / per-step preparation kernels: bary split, CSR inversion, prior folding, row packing.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "gcb_common.cuh"
+
+namespace gcb {
+
+// ---- bary [n_slots,2] -> idx int32, w fp32  (conv_intrinsic.py:213-221) ---------------------
+template <typename TIn>
+__global__ void k_prep_bary(const TIn* __restrict__ bary, int64_t n_slots, int32_t v_src,
+                            int32_t* __restrict__ idx, float* __restrict__ w,
+                            int32_t* __restrict__ oob_count) {
+  int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  // the reference casts the whole tensor to fp32 first, then truncates toward zero with .long()
+  float fi = (float)bary[2 * s];
+  float fw = (float)bary[2 * s + 1];
+  long long li = (long long)fi;  // cvt.rzi
+  int32_t i32 = (int32_t)li;
+  if (li < 0 || li >= v_src) {
+    atomicAdd(oob_count, 1);
+    i32 = 0;
+    fw = 0.f;
+  }
+  idx[s] = i32;
+  w[s] = fw;
+}
+
+// ---- CSR inversion ---------------------------------------------------------------------------
+__global__ void k_csr_keys(const int32_t* __restrict__ idx, const float* __restrict__ w,
+                           int64_t n_slots, int32_t v_src, int32_t* __restrict__ keys,
+                           int32_t* __restrict__ vals) {
+  int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  keys[s] = (w[s] == 0.f) ? v_src : idx[s];  // zero-weight slots sort to the tail and are dropped
+  vals[s] = (int32_t)s;
+}
+
+__global__ void k_csr_row_ptr(const int32_t* __restrict__ sorted_keys, int64_t n_slots,
+                              int32_t v_src, int32_t* __restrict__ row_ptr) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > v_src) return;
+  // lower_bound(sorted_keys, v)
+  int64_t lo = 0, hi = n_slots;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (sorted_keys[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  row_ptr[v] = (int32_t)lo;
+}
+
+static size_t cub_sort_temp_bytes(int64_t n_slots, int end_bit) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_slots, 0,
+                                  end_bit);
+  return bytes;
+}
+
+static int key_bits(int32_t v_src) {
+  int bits = 1;
+  while ((1ll << bits) <= (long long)v_src) ++bits;
+  return bits;
+}
+
+// ---- prior folding ---------------------------------------------------------------------------
+// out[t,q,f] = sum_p in[t,p,f] * (transpose ? prior[q,p] : prior[p,q]),  p,q in [0, R*A)
+__global__ void k_fold_prior(const float* __restrict__ in, const float* __restrict__ prior,
+                             float* __restrict__ out, int RA, int F, int transpose) {
+  extern __shared__ float s_prior[];  // RA*RA
+  for (int i = threadIdx.x; i < RA * RA; i += blockDim.x) s_prior[i] = prior[i];
+  __syncthreads();
+  int t = blockIdx.y;
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const float* src = in + (size_t)t * RA * F + f;
+  float* dst = out + (size_t)t * RA * F + f;
+  for (int q = 0; q < RA; ++q) {
+    double acc = 0.0;
+    for (int p = 0; p < RA; ++p) {
+      float kv = transpose ? s_prior[q * RA + p] : s_prior[p * RA + q];
+      acc += (double)src[(size_t)p * F] * (double)kv;
+    }
+    dst[(size_t)q * F] = (float)acc;
+  }
+}
+
+__global__ void k_pack_rows(const float* __restrict__ src, const int32_t* __restrict__ rows,
+                            int n_rows, int F, float* __restrict__ out) {
+  int r = blockIdx.x;
+  if (r >= n_rows) return;
+  const float* s = src + (size_t)rows[r] * F;
+  float* d = out + (size_t)r * F;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) d[f] = s[f];
+}
+
+}  // namespace gcb
+
+using namespace gcb;
+
+extern "C" int gcb_prep_bary(const void* bary, int bary_is_f64, int64_t n_slots, int32_t v_src,
+                             int32_t* idx, float* w, int32_t* oob_count, void* stream) {
+  GCB_REQUIRE(bary && idx && w && oob_count, GCB_EINVAL, "gcb_prep_bary: null pointer");
+  GCB_REQUIRE(n_slots >= 0 && v_src > 0, GCB_EINVAL, "gcb_prep_bary: bad sizes");
+  if (n_slots == 0) return GCB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned grid = (unsigned)ceil_div64(n_slots, 256);
+  if (bary_is_f64)
+    k_prep_bary<double><<<grid, 256, 0, st>>>((const double*)bary, n_slots, v_src, idx, w, oob_count);
+  else
+    k_prep_bary<float><<<grid, 256, 0, st>>>((const float*)bary, n_slots, v_src, idx, w, oob_count);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+extern "C" size_t gcb_csr_workspace_bytes(int64_t n_slots, int32_t v_src) {
+  size_t arr = align_up((size_t)n_slots * sizeof(int32_t), 256);
+  return 3 * arr + align_up(cub_sort_temp_bytes(n_slots, key_bits(v_src)), 256) + 256;
+}
+
+extern "C" int gcb_csr_build(const int32_t* idx, const float* w, int64_t n_slots, int32_t v_src,
+                             int32_t* row_ptr, int32_t* entries, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  GCB_REQUIRE(idx && w && row_ptr && entries && workspace, GCB_EINVAL, "gcb_csr_build: null pointer");
+  GCB_REQUIRE(n_slots > 0 && n_slots < (1ll << 31) && v_src > 0, GCB_EINVAL, "gcb_csr_build: bad sizes");
+  GCB_REQUIRE(workspace_bytes >= gcb_csr_workspace_bytes(n_slots, v_src), GCB_EWORKSPACE,
+              "gcb_csr_build: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t arr = align_up((size_t)n_slots * sizeof(int32_t), 256);
+  char* base = (char*)workspace;
+  int32_t* keys_in = (int32_t*)base;
+  int32_t* keys_out = (int32_t*)(base + arr);
+  int32_t* vals_in = (int32_t*)(base + 2 * arr);
+  void* cub_tmp = base + 3 * arr;
+  int bits = key_bits(v_src);
+  size_t cub_bytes = cub_sort_temp_bytes(n_slots, bits);
+  unsigned grid = (unsigned)ceil_div64(n_slots, 256);
+  k_csr_keys<<<grid, 256, 0, st>>>(idx, w, n_slots, v_src, keys_in, vals_in);
+  GCB_LAUNCH_OK();
+  // LSD radix sort is stable: slots of one source vertex stay in ascending slot order.
+  GCB_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, vals_in,
+                                              entries, (int)n_slots, 0, bits, st));
+  k_csr_row_ptr<<<(unsigned)ceil_div64((int64_t)v_src + 1, 256), 256, 0, st>>>(keys_out, n_slots, v_src, row_ptr);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+extern "C" int gcb_fold_prior(const float* in, const float* prior, float* out, int32_t T, int32_t R,
+                              int32_t A, int32_t F, int transpose, void* stream) {
+  GCB_REQUIRE(in && prior && out, GCB_EINVAL, "gcb_fold_prior: null pointer");
+  GCB_REQUIRE(T > 0 && R > 0 && A > 0 && F > 0, GCB_EINVAL, "gcb_fold_prior: bad sizes");
+  int RA = R * A;
+  size_t smem = (size_t)RA * RA * sizeof(float);
+  GCB_REQUIRE(smem <= 160 * 1024, GCB_EUNSUPPORTED, "gcb_fold_prior: R*A=%d too large", RA);
+  if (smem > 48 * 1024)
+    GCB_CUDA_OK(cudaFuncSetAttribute(k_fold_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div64(F, 128), (unsigned)T);
+  k_fold_prior<<<grid, 128, smem, (cudaStream_t)stream>>>(in, prior, out, RA, F, transpose);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+extern "C" int gcb_pack_rows(const float* src, const int32_t* rows, int32_t n_rows, int32_t F,
+                             float* out, void* stream) {
+  GCB_REQUIRE(src && rows && out, GCB_EINVAL, "gcb_pack_rows: null pointer");
+  if (n_rows <= 0) return GCB_OK;
+  k_pack_rows<<<n_rows, 128, 0, (cudaStream_t)stream>>>(src, rows, n_rows, F, out);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}

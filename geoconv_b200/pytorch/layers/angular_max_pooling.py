@@ -1,0 +1,20 @@
+"""Drop-in for ``geoconv.pytorch.layers.angular_max_pooling.AngularMaxPooling``
+(/root/reference/src/geoconv/pytorch/layers/angular_max_pooling.py:6-29)."""
+from torch import nn
+
+from geoconv_b200 import ops
+
+
+class AngularMaxPooling(nn.Module):
+    """Per vertex, keep the rotation whose template-response vector has the largest Euclidean norm
+    (first maximum wins): (V, n_rotations, T) -> (V, T)."""
+
+    def forward(self, inputs):
+        fused = getattr(inputs, "_gcb_pooled", None)
+        if fused is not None and fused[2] == inputs._version:
+            # produced by a geoconv_b200 ConvIntrinsic in the same kernel pass as `inputs`
+            return fused[0]
+        if inputs.dim() != 3:
+            raise ValueError(f"expected (n_vertices, n_rotations, feature_dim), got {tuple(inputs.shape)}")
+        z, _ = ops.AngularMaxPoolFn.apply(inputs)
+        return z

@@ -1,0 +1,149 @@
+/*
+ * geoconv_b200 - C ABI of the B200-native ConvIntrinsic (+AngularMaxPooling) hot path.
+ *
+ * The reference (andreasMazur/geoconv) has NO plugin / FFI seam for this path: the boundary is the
+ * Python class API of geoconv.pytorch.layers.  This header is the seam the
+ * drop-in layers bind to (ctypes); every entry point names the reference code
+ * it replaces.  All paths are relative to /root/reference/src/geoconv/pytorch/layers/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - tensors are dense, row-major, fp32 / int32 unless stated;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is
+ *     enqueued on it and nothing synchronises the host unless stated;
+ *   - the library never allocates device memory: callers pass outputs and a workspace whose
+ *     size the matching *_workspace_bytes() query returns;
+ *   - return value 0 = success; otherwise a GCB_E* code, with text from gcb_last_error().
+ *     There is no CPU fallback anywhere.
+ *
+ * Symbols: V_out rows of the barycentric tensor (output vertices), V_src rows of the signal
+ * (gather source; == V_out for a whole mesh, local+halo rows for a vertex-row shard),
+ * R radial, A angular, F input features, T templates, n_rot rotations, KRA = R*A*F.
+ */
+#ifndef GEOCONV_B200_H_
+#define GEOCONV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCB_ABI_VERSION 1
+#define GCB_MAX_ROT 32
+
+/* error codes */
+#define GCB_OK 0
+#define GCB_EINVAL 1      /* bad argument (shape, null pointer, alignment) */
+#define GCB_ECUDA 2       /* CUDA runtime error; text in gcb_last_error() */
+#define GCB_EUNSUPPORTED 3 /* shape outside what the selected precision path supports */
+#define GCB_EWORKSPACE 4  /* workspace too small */
+
+/* activation ids: the six entries of ACTIVATIONS, conv_intrinsic.py:10-17 */
+#define GCB_ACT_RELU 0
+#define GCB_ACT_ELU 1
+#define GCB_ACT_LEAKY_RELU 2
+#define GCB_ACT_SELU 3
+#define GCB_ACT_SIGMOID 4
+#define GCB_ACT_TANH 5
+
+/* arithmetic of the contraction */
+#define GCB_PREC_FP32 0   /* CUDA-core FFMA, plain fp32 */
+#define GCB_PREC_TF32 1   /* tcgen05 kind::tf32, one pass (<=2e-3 normalised error) */
+#define GCB_PREC_TF32X3 2 /* tcgen05 kind::tf32, 3-term split, fp32-faithful (<=1e-5) */
+
+int gcb_abi_version(void);
+const char* gcb_last_error(void);
+/* 1 if the tcgen05 kernels can serve this shape, else 0 (then use GCB_PREC_FP32). */
+int gcb_tc_supported(int32_t R, int32_t A, int32_t F, int32_t T, int32_t n_rot);
+
+/* ---- bary -> (idx, w) ------------------------------------------------------------------
+ * Replaces conv_intrinsic.py:213-221 (cast to fp32, `[...,0].long()`, `[...,1]`).
+ * bary: [n_slots, 2] fp32 or fp64 (n_slots = V_out*R*A*3).  idx = trunc-toward-zero of the fp32
+ * cast.  *oob_count (int32, device, caller-zeroed) += number of idx outside [0, v_src).        */
+int gcb_prep_bary(const void* bary, int bary_is_f64, int64_t n_slots, int32_t v_src,
+                  int32_t* idx, float* w, int32_t* oob_count, void* stream);
+
+/* ---- CSR inversion (neighbour -> vertex), for the deterministic dSignal reduction -------
+ * Replaces the atomic scatter_add_ that autograd runs for torch.gather (conv_intrinsic.py:237).
+ * row_ptr [v_src+1], entries [n_slots]: slot ids grouped by source vertex, ascending inside a
+ * group (stable => bit-reproducible).  Zero-weight slots (the (0,0,0) fallback,
+ * barycentric_coordinates.py:69) are dropped; row_ptr[v_src] = number kept.                   */
+size_t gcb_csr_workspace_bytes(int64_t n_slots, int32_t v_src);
+int gcb_csr_build(const int32_t* idx, const float* w, int64_t n_slots, int32_t v_src,
+                  int32_t* row_ptr, int32_t* entries, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* ---- prior folding ---------------------------------------------------------------------
+ * Replaces the per-call einsum "raxy,kxyf->kraf" (conv_intrinsic.py:194) by folding the
+ * rotation-symmetric prior into the weights once per step:
+ *   transpose == 0:  out[t,x,y,f] = sum_{r,a} in[t,r,a,f] * prior[r,a,x,y]      (W -> Weff)
+ *   transpose == 1:  out[t,r,a,f] = sum_{x,y} in[t,x,y,f] * prior[r,a,x,y]      (dWeff -> dW) */
+int gcb_fold_prior(const float* in, const float* prior, float* out, int32_t T, int32_t R,
+                   int32_t A, int32_t F, int transpose, void* stream);
+
+/* ---- forward ---------------------------------------------------------------------------
+ * Replaces ConvIntrinsic.forward (conv_intrinsic.py:118-171) incl. _signal_retrieval (:198-240)
+ * and, when z/argmax are given, AngularMaxPooling.forward (angular_max_pooling.py:27-29):
+ *   Y[k,i,t] = act( X[k]·Wself[t] + sum_{x,y,f} Weff[t,x,(y+rot_off[i])%A,f]*I[k,x,y,f] + b[t] )
+ *   I[k,x,y,:] = sum_j w[k,x,y,j] * X[idx[k,x,y,j], :]
+ *   argmax[k] = first i maximising ||Y[k,i,:]||_2 ; Z[k,:] = Y[k,argmax[k],:]
+ * x [V_src,F]; idx,w [V_out,R,A,3]; w_eff [T,R,A,F]; w_self [T,F]; bias [T];
+ * rot_off_host: n_rot ints on the HOST (the rotation list arange(0,A,delta) or `orientations`).
+ * y [V_out,n_rot,T] (may be NULL if z given); z [V_out,T] and argmax [V_out] (both or neither).
+ * w_eff == NULL means an identically-zero prior (ConvZero, conv_zero.py:12-15): the neighbour
+ * term is skipped and only the centre term is computed.                                       */
+size_t gcb_conv_fwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
+                                    int32_t T, int32_t n_rot, int precision);
+int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
+                 const float* w_self, const float* bias, const int32_t* rot_off_host,
+                 int32_t n_rot, int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
+                 int32_t T, int act, int precision, float* y, float* z, int32_t* argmax,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- AngularMaxPooling on a materialised Y -----------------------------------------------
+ * Replaces angular_max_pooling.py:27-29 and its autograd (index_put).                        */
+int gcb_amp_fwd(const float* y, int32_t v, int32_t n_rot, int32_t T, float* z, int32_t* argmax,
+                void* stream);
+int gcb_amp_bwd(const float* grad_z, const int32_t* argmax, int32_t v, int32_t n_rot, int32_t T,
+                float* grad_y, void* stream);
+
+/* h = grad * act'(.) with act' written in terms of the activation OUTPUT `out` (n elements). */
+int gcb_act_grad(const float* grad, const float* out, int64_t n, int act, float* h, void* stream);
+
+/* rot_sel[k] = rot_off_host[argmax[k]]  (int32, device) */
+int gcb_select_rot(const int32_t* argmax, const int32_t* rot_off_host, int32_t n_rot, int32_t v,
+                   int32_t* rot_sel, void* stream);
+
+/* ---- backward --------------------------------------------------------------------------
+ * Replaces autograd of conv_intrinsic.py:144-171/:226-240 for ONE rotation per vertex:
+ * h [V_out,T] = upstream grad times act', rot_sel[k] the angular shift applied for vertex k.
+ *   d_w_eff[t,x,y',f] (+)= sum_k h[k,t] * I[k,x,(y'-rot_sel[k])%A,f]
+ *   d_w_self[t,f]     (+)= sum_k h[k,t] * X[k,f]
+ *   d_bias[t]         (+)= sum_k h[k,t]
+ *   d_x[v,f]          (+)= sum_{slots s->v} w[s]*(sum_t h[k_s,t]*Weff[t,x_s,(y_s+rot_sel[k_s])%A,f])
+ *                          + [v<V_out] sum_t h[v,t]*Wself[t,f]
+ * accumulate != 0 adds into the outputs (used to back-propagate a dense dY one rotation at a
+ * time); == 0 overwrites.  The AMP-sparse backward is a single call with rot_sel from
+ * gcb_select_rot.  d_x uses the CSR from gcb_csr_build: fixed summation order, no atomics.
+ * d_x == NULL skips the dSignal stages (signal does not require grad); w_eff == NULL as above
+ * (then d_w_eff is zero-filled unless accumulating and the CSR pointers may be NULL).          */
+size_t gcb_conv_bwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
+                                    int32_t T, int precision);
+int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
+                 const float* w_self, const float* h, const int32_t* rot_sel,
+                 const int32_t* csr_row_ptr, const int32_t* csr_entries, int32_t v_out,
+                 int32_t v_src, int32_t R, int32_t A, int32_t F, int32_t T, int precision,
+                 int accumulate, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- vertex-row sharding helper (halo exchange) ---------------------------
+ * out[i,:] = src[rows[i],:]  (packs the signal rows a peer asked for into a send buffer). */
+int gcb_pack_rows(const float* src, const int32_t* rows, int32_t n_rows, int32_t F, float* out,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOCONV_B200_H_ */

@@ -1,0 +1,115 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/geoconv_b200.h declares, the
+drop-in layers mirror the reference's construction (seed-for-seed), and there is no CPU path."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from geoconv_b200 import _native
+from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
+from geoconv_b200.pytorch.layers.conv_dirac import ConvDirac
+from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
+from geoconv_b200.pytorch.layers.conv_intrinsic import ConvIntrinsic
+from geoconv_b200.pytorch.layers.conv_zero import ConvZero
+from geoconv_b200.preprocessing.barycentric_coordinates import create_template_matrix
+from tests.helpers import golden_cases, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LAYERS = {"geodesic": ConvGeodesic, "dirac": ConvDirac, "zero": ConvZero}
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "geoconv_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gcb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.load()
+    declared = _header_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/geoconv_b200.h but not exported"
+    assert sorted(_native.SIGNATURES) == declared
+    assert lib.gcb_abi_version() == _native.ABI_VERSION
+
+
+def test_error_reporting_without_gpu():
+    lib = _native.load()
+    # argument validation happens before any CUDA call
+    rc = lib.gcb_prep_bary(None, 0, 10, 5, None, None, None, None)
+    assert rc == 1
+    assert b"null pointer" in lib.gcb_last_error()
+    with pytest.raises(_native.GeoconvNativeError):
+        _native.check(rc, "gcb_prep_bary")
+
+
+def _make(g, **kw):
+    v, r, a = g["bary"].shape[:3]
+    f = g["signal"].shape[1]
+    t = g["w_self"].shape[0]
+    radius = g["template"][-1, 0, 0].item()
+    torch.manual_seed(0)
+    return LAYERS[g["kind"]](input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t,
+                             template_radius=radius, activation=g["act"], rotation_delta=g["delta"], **kw)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_seeded_construction_matches_reference(name):
+    g = load_golden(name)
+    layer = _make(g)
+    sd = layer.state_dict()
+    assert list(sd.keys()) == ["_template_neighbor_weights", "_template_self_weights", "_bias"]
+    assert torch.equal(sd["_template_neighbor_weights"], g["w_neighbor"])
+    assert torch.equal(sd["_template_self_weights"], g["w_self"])
+    assert torch.equal(sd["_bias"], g["bias"])
+    np.testing.assert_allclose(layer._kernel.numpy(), g["prior"].numpy(), rtol=0, atol=1e-7)
+    np.testing.assert_allclose(layer._template_vertices.numpy(), g["template"].numpy(), rtol=0, atol=1e-15)
+    assert layer._template_size == tuple(g["bary"].shape[1:3])
+    assert layer.include_prior == g["include_prior"]
+
+
+def test_public_attributes_and_hook():
+    layer = ConvGeodesic(input_shape=[(None, 6), (None, 2, 4, 3, 2)], amt_templates=3, template_radius=0.1,
+                         activation="elu", rotation_delta=2, initializer="xavier_normal")
+    assert (layer.activation_fn, layer.rotation_delta, layer.amt_templates) == ("elu", 2, 3)
+    assert (layer.template_radius, layer.initializer, layer.include_prior) == (0.1, "xavier_normal", True)
+    assert layer._rotation_offsets(None) == [0, 2]
+    assert layer._rotation_offsets(torch.tensor([3, 1])) == [3, 1]
+    assert ConvDirac(input_shape=[(None, 6), (None, 2, 4, 3, 2)], amt_templates=3, template_radius=0.1).include_prior is False
+    assert ConvZero(input_shape=[(None, 6), (None, 2, 4, 3, 2)], amt_templates=3, template_radius=0.1)._prior_is_zero
+
+    class Lopsided(ConvIntrinsic):
+        def define_kernel_values(self, template_matrix):
+            k = np.zeros(template_matrix.shape[:-1] + template_matrix.shape[:-1])
+            k[0, 0, 0, 1] = 1.0
+            return k
+
+    assert Lopsided(input_shape=[(None, 6), (None, 2, 4, 3, 2)], amt_templates=3, template_radius=0.1)._prior_is_symmetric is False
+    with pytest.raises(TypeError):
+        ConvIntrinsic(input_shape=[(None, 6), (None, 2, 4, 3, 2)], amt_templates=3, template_radius=0.1)
+
+
+def test_template_matrix_cartesian():
+    pol = create_template_matrix(3, 4, 0.3)
+    car = create_template_matrix(3, 4, 0.3, in_cart=True)
+    np.testing.assert_allclose(car[..., 0], pol[..., 0] * np.cos(pol[..., 1]))
+    np.testing.assert_allclose(np.hypot(car[..., 0], car[..., 1]), pol[..., 0])
+
+
+def test_no_cpu_path():
+    layer = ConvDirac(input_shape=[(None, 6), (None, 2, 4, 3, 2)], amt_templates=3, template_radius=0.1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        layer([torch.zeros(5, 6), torch.zeros(5, 2, 4, 3, 2)])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        AngularMaxPooling()(torch.zeros(5, 4, 3))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "geoconv_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, fn)).read(), fn
