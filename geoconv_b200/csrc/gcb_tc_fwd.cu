@@ -1,12 +1,469 @@
-// placeholder until the tcgen05 forward lands
+// tcgen05 forward of ConvIntrinsic (GCB_PREC_TF32 / GCB_PREC_TF32X3).
+//
+// One CTA = 128 output vertices x (a group of g rotations) x (a chunk n_t of templates).
+//   Y[k,i,t] = act( sum_{x,y,f} Weff[t,x,(y+o_i)%A,f] * I[k,x,y,f] + X[k]·Wself[t] + b[t] )
+// is a GEMM with M = vertices, N = (rotation, template), K = (x, y, f) plus one centre slab (f).
+// The rotation never moves data: for a fixed (x, f-chunk) all A angular B tiles (weights) sit in
+// shared memory and rotation i simply pairs the gathered A tile y with B tile (y+o_i)%A, so every
+// operand tile is staged once and used g times.
+//
+// Warp roles (320 threads):
+//   warps 0-7  producers: barycentric 3-neighbour gather of signal rows (float4 loads, L2-resident
+//              signal) + weighted sum in registers, rounded to tf32 (RN) and written straight into
+//              the 128B/64B/32B-swizzled K-major UMMA layout; then the epilogue (tcgen05.ld ->
+//              bias + activation -> global).
+//   warp 8     TMA: weight tiles (cp.async.bulk.tensor, hardware swizzle) into the B ring.
+//   warp 9     MMA: one thread issues tcgen05.mma kind::tf32 into TMEM accumulators (g * n_t columns)
+//              and releases stages with tcgen05.commit.
+// TF32X3 (fp32-faithful): operands are split v = hi + lo (both tf32) and D += Ahi*Bhi + Ahi*Blo +
+// Alo*Bhi - three MMAs per k-step, relative error ~2^-21 per product.
+#include <cuda.h>
+
 #include "gcb_common.cuh"
+#include "gcb_ptx.cuh"
+
 namespace gcb {
-bool tc_supported(int, int, int, int, int) { return false; }
-size_t tc_fwd_workspace_bytes(int, int, int, int, int, int, int) { return 0; }
-int tc_conv_fwd(const float*, const int32_t*, const float*, const float*, const float*, const float*,
-                const RotTable&, int, int, int, int, int, int, int, int, int, float*, void*, size_t,
-                cudaStream_t) {
-  set_error("tcgen05 forward not built");
-  return GCB_EUNSUPPORTED;
+
+constexpr int TC_M = 128;
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+constexpr int TC_BAR_BYTES = 1024;
+
+struct TcFwdParams {
+  const float* x;       // [v_src, F]
+  const uint4* recs;    // [(R*A+1), v_pad, 2]: {i0,i1,i2,-} {w0,w1,w2,-}; slot R*A = centre (self, 1)
+  const float* bias;    // [T]
+  float* y;             // [v_out, n_rot, T]
+  int v_out, v_pad, R, A, F, T, n_rot, act;
+  int nfc;              // F / KC
+  int n_t;              // templates per CTA (MMA N)
+  int g;                // rotations per CTA
+  int ns_a;             // A-tile ring depth
+  int tmem_cols;        // power of two >= g*n_t
+  RotTable rot;         // offsets in [0, A)
+  int8_t last_user[GCB_MAX_ROT][GCB_MAX_ROT];  // [group][yb]: last A tile y (0..A-1) that reads B tile yb
+};
+
+struct TcConfig {
+  int kc, n_t, g, n_groups, ns_a, tmem_cols;
+  size_t smem_bytes;
+  bool ok;
+};
+
+static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3) {
+  TcConfig c{};
+  c.ok = false;
+  if (T % 16 != 0 || F % 8 != 0 || A > GCB_MAX_ROT || n_rot > GCB_MAX_ROT) return c;
+  const int nprod = x3 ? 2 : 1;
+  for (int n_t = (T < 256 ? T : 256); n_t >= 16; n_t -= 16) {
+    if (T % n_t != 0) continue;
+    for (int kc = 32; kc >= 8; kc >>= 1) {
+      if (F % kc != 0) continue;
+      size_t b_bytes = (size_t)A * nprod * n_t * kc * 4;
+      size_t a_stage = (size_t)nprod * TC_M * kc * 4;
+      size_t fixed = b_bytes + TC_BAR_BYTES + 1024 /* alignment slack */;
+      if (fixed + 3 * a_stage > (size_t)TC_SMEM_LIMIT) continue;
+      int ns_a = (int)(((size_t)TC_SMEM_LIMIT - fixed) / a_stage);
+      if (ns_a > 8) ns_a = 8;
+      int g_max = 512 / n_t;
+      if (g_max > n_rot) g_max = n_rot;
+      int n_groups = (n_rot + g_max - 1) / g_max;
+      int g = (n_rot + n_groups - 1) / n_groups;
+      int cols = 32;
+      while (cols < g * n_t) cols <<= 1;
+      c.kc = kc; c.n_t = n_t; c.g = g; c.n_groups = n_groups; c.ns_a = ns_a; c.tmem_cols = cols;
+      c.smem_bytes = fixed + (size_t)ns_a * a_stage;
+      c.ok = true;
+      return c;
+    }
+  }
+  return c;
 }
+
+// ---- preparation kernels ---------------------------------------------------------------------
+// slot-major packed barycentric records, padded to a multiple of 128 vertices
+__global__ void k_tc_pack_recs(const int32_t* __restrict__ idx, const float* __restrict__ w, int v_out,
+                               int v_pad, int RA, uint4* __restrict__ recs) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)(RA + 1) * v_pad;
+  if (e >= total) return;
+  int slot = (int)(e / v_pad), v = (int)(e - (int64_t)slot * v_pad);
+  uint4 ri = make_uint4(0, 0, 0, 0), rw = make_uint4(0, 0, 0, 0);
+  if (v < v_out) {
+    if (slot < RA) {
+      size_t base = ((size_t)v * RA + slot) * 3;
+      ri = make_uint4((uint32_t)idx[base], (uint32_t)idx[base + 1], (uint32_t)idx[base + 2], 0);
+      rw = make_uint4(__float_as_uint(w[base]), __float_as_uint(w[base + 1]), __float_as_uint(w[base + 2]), 0);
+    } else {
+      ri = make_uint4((uint32_t)v, (uint32_t)v, (uint32_t)v, 0);
+      rw = make_uint4(__float_as_uint(1.f), 0, 0, 0);
+    }
+  }
+  recs[e * 2] = ri;
+  recs[e * 2 + 1] = rw;
+}
+
+// Wcat[t, 0:KRA] = Weff[t], Wcat[t, KRA:KRA+F] = Wself[t], split into tf32 hi (+ lo for X3)
+__global__ void k_tc_wcat(const float* __restrict__ w_eff, const float* __restrict__ w_self, int T, int KRA,
+                          int F, float* __restrict__ hi, float* __restrict__ lo) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int kcat = KRA + F;
+  if (e >= (int64_t)T * kcat) return;
+  int t = (int)(e / kcat), k = (int)(e - (int64_t)t * kcat);
+  float v = k < KRA ? w_eff[(size_t)t * KRA + k] : w_self[(size_t)t * F + (k - KRA)];
+  float h = ptx::to_tf32(v);
+  hi[e] = h;
+  if (lo) lo[e] = v - h;
+}
+
+// ---- the kernel --------------------------------------------------------------------------------
+template <int KC>
+__device__ __forceinline__ uint32_t swz_chunk(int row, int c) {
+  if (KC == 32) return (uint32_t)(c ^ (row & 7));
+  if (KC == 16) return (uint32_t)(c ^ ((row >> 1) & 3));
+  return (uint32_t)(c ^ ((row >> 2) & 1));
+}
+
+template <int KC, bool X3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_fwd(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
+         const TcFwdParams p) {
+  constexpr int ROW_BYTES = KC * 4;
+  constexpr int NPROD = X3 ? 2 : 1;
+  constexpr int A_TILE_BYTES = TC_M * ROW_BYTES;
+  constexpr int CPR = KC / 4;          // 16-byte chunks per row
+  constexpr int ROWS_PER_PASS = 32 / CPR;
+  constexpr int ITEMS = 32 / ROWS_PER_PASS;  // float4 items per lane per 32-row sub-tile
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int b_tile_bytes = p.n_t * ROW_BYTES;
+  const uint32_t b_base = smem_base;                                        // [A][NPROD][b_tile]
+  const uint32_t a_base = b_base + (uint32_t)(p.A * NPROD * b_tile_bytes);  // [ns_a][NPROD][A_TILE]
+  const uint32_t bar_base = a_base + (uint32_t)(p.ns_a * NPROD * A_TILE_BYTES);
+  const uint32_t a_full = bar_base;
+  const uint32_t a_empty = a_full + 8u * p.ns_a;
+  const uint32_t b_full = a_empty + 8u * p.ns_a;
+  const uint32_t b_empty = b_full + 8u * p.A;
+  const uint32_t acc_full = b_empty + 8u * p.A;
+  const uint32_t tmem_slot = acc_full + 8u;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));     // generic view of smem_base
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_M;
+  const int grp = blockIdx.y;
+  const int t0 = blockIdx.z * p.n_t;
+  const int rot0 = grp * p.g;
+  const int g_cnt = min(p.g, p.n_rot - rot0);
+  const int RA = p.R * p.A;
+  const int n_ss = (p.R + 1) * p.nfc;  // super-steps: (x, f-chunk) for x < R, then the centre slab
+
+  if (warp == TC_PRODUCER_WARPS && lane == 0) {
+    for (int s = 0; s < p.ns_a; ++s) {
+      ptx::mbar_init(a_full + 8u * s, 4);
+      ptx::mbar_init(a_empty + 8u * s, 1);
+    }
+    for (int s = 0; s < p.A; ++s) {
+      ptx::mbar_init(b_full + 8u * s, 1);
+      ptx::mbar_init(b_empty + 8u * s, 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tensormap(&tmap_hi);
+    if (X3) ptx::prefetch_tensormap(&tmap_lo);
+  }
+  if (warp == TC_PRODUCER_WARPS + 1) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp < TC_PRODUCER_WARPS) {
+    // ===================== producers: gather + interpolate -> swizzled A tiles =====================
+    const int pg = warp >> 2, wq = warp & 3;
+    const int c = lane % CPR;
+    const int row_l = lane / CPR;
+    int n = 0;
+    for (int ss = 0; ss < n_ss; ++ss) {
+      const bool centre = ss >= p.R * p.nfc;
+      const int xr = centre ? 0 : ss / p.nfc;
+      const int fc = centre ? ss - p.R * p.nfc : ss - xr * p.nfc;
+      const int n_y = centre ? 1 : p.A;
+      for (int y = 0; y < n_y; ++y, ++n) {
+        if ((n & 1) != pg) continue;
+        const int slot = centre ? RA : xr * p.A + y;
+        const uint4* rec = p.recs + ((size_t)slot * p.v_pad + m0 + 32 * wq + row_l) * 2;
+        const float* xcol = p.x + fc * KC + c * 4;
+        float4 v[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+          const uint4 ri = __ldg(rec + (size_t)j * ROWS_PER_PASS * 2);
+          const uint4 rw = __ldg(rec + (size_t)j * ROWS_PER_PASS * 2 + 1);
+          const float4 x0 = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.x * p.F));
+          const float4 x1 = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.y * p.F));
+          const float4 x2 = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.z * p.F));
+          const float w0 = __uint_as_float(rw.x), w1 = __uint_as_float(rw.y), w2 = __uint_as_float(rw.z);
+          v[j].x = fmaf(x2.x, w2, fmaf(x1.x, w1, x0.x * w0));
+          v[j].y = fmaf(x2.y, w2, fmaf(x1.y, w1, x0.y * w0));
+          v[j].z = fmaf(x2.z, w2, fmaf(x1.z, w1, x0.z * w0));
+          v[j].w = fmaf(x2.w, w2, fmaf(x1.w, w1, x0.w * w0));
+        }
+        const int stage = n % p.ns_a;
+        ptx::mbar_wait(a_empty + 8u * stage, (((uint32_t)(n / p.ns_a)) & 1u) ^ 1u);
+        uint8_t* a_hi = smem_gen + (a_base - smem_base) + (size_t)stage * NPROD * A_TILE_BYTES;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+          const int row = 32 * wq + row_l + j * ROWS_PER_PASS;
+          const uint32_t off = (uint32_t)row * ROW_BYTES + swz_chunk<KC>(row, c) * 16u;
+          float4 h;
+          h.x = ptx::to_tf32(v[j].x); h.y = ptx::to_tf32(v[j].y);
+          h.z = ptx::to_tf32(v[j].z); h.w = ptx::to_tf32(v[j].w);
+          *reinterpret_cast<float4*>(a_hi + off) = h;
+          if (X3) {
+            float4 l;
+            l.x = v[j].x - h.x; l.y = v[j].y - h.y; l.z = v[j].z - h.z; l.w = v[j].w - h.w;
+            *reinterpret_cast<float4*>(a_hi + A_TILE_BYTES + off) = l;
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a_full + 8u * stage);
+      }
+    }
+    // ===================== epilogue: TMEM -> bias + activation -> Y =====================
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+    const int row = m0 + 32 * wq + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * wq) << 16);
+    for (int il = pg; il < g_cnt; il += 2) {
+      float* yrow = p.y + ((size_t)row * p.n_rot + (rot0 + il)) * p.T + t0;
+      for (int c0 = 0; c0 < p.n_t; c0 += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(lane_addr + (uint32_t)(il * p.n_t + c0), r);
+        ptx::tmem_ld_wait();
+        if (row < p.v_out) {
+#pragma unroll
+          for (int q = 0; q < 16; q += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + t0 + c0 + q));
+            float4 o;
+            o.x = act_apply(p.act, __uint_as_float(r[q + 0]) + b.x);
+            o.y = act_apply(p.act, __uint_as_float(r[q + 1]) + b.y);
+            o.z = act_apply(p.act, __uint_as_float(r[q + 2]) + b.z);
+            o.w = act_apply(p.act, __uint_as_float(r[q + 3]) + b.w);
+            *reinterpret_cast<float4*>(yrow + c0 + q) = o;
+          }
+        }
+      }
+    }
+  } else if (warp == TC_PRODUCER_WARPS) {
+    // ===================== TMA: weight tiles -> B buffer =====================
+    if (lane == 0) {
+      uint32_t loads = 0;  // bit yb = parity of the number of loads issued into slot yb
+      for (int ss = 0; ss < n_ss; ++ss) {
+        const bool centre = ss >= p.R * p.nfc;
+        const int xr = centre ? 0 : ss / p.nfc;
+        const int fc = centre ? ss - p.R * p.nfc : ss - xr * p.nfc;
+        const int n_y = centre ? 1 : p.A;
+        for (int yb = 0; yb < n_y; ++yb) {
+          ptx::mbar_wait(b_empty + 8u * yb, ((loads >> yb) & 1u) ^ 1u);
+          const int col = (centre ? RA * p.F : (xr * p.A + yb) * p.F) + fc * KC;
+          const uint32_t dst = b_base + (uint32_t)(yb * NPROD * b_tile_bytes);
+          ptx::mbar_arrive_expect_tx(b_full + 8u * yb, (uint32_t)(NPROD * b_tile_bytes));
+          ptx::tma_load_2d(dst, &tmap_hi, b_full + 8u * yb, col, t0);
+          if (X3) ptx::tma_load_2d(dst + b_tile_bytes, &tmap_lo, b_full + 8u * yb, col, t0);
+          loads ^= 1u << yb;
+        }
+      }
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_tf32(TC_M, p.n_t);
+      uint32_t uses = 0;   // bit yb = parity of completed uses of B slot yb
+      uint32_t ready = 0;  // bit yb = b_full already observed for the current use
+      int n = 0;
+      for (int ss = 0; ss < n_ss; ++ss) {
+        const bool centre = ss >= p.R * p.nfc;
+        const int n_y = centre ? 1 : p.A;
+        for (int y = 0; y < n_y; ++y, ++n) {
+          const int stage = n % p.ns_a;
+          ptx::mbar_wait(a_full + 8u * stage, ((uint32_t)(n / p.ns_a)) & 1u);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = a_base + (uint32_t)(stage * NPROD * A_TILE_BYTES);
+          for (int il = 0; il < g_cnt; ++il) {
+            int yb = 0;
+            if (!centre) {
+              yb = y + p.rot.off[rot0 + il];
+              yb -= (yb >= p.A) ? p.A : 0;
+            }
+            if (!((ready >> yb) & 1u)) {
+              ptx::mbar_wait(b_full + 8u * yb, (uses >> yb) & 1u);
+              ptx::tc_fence_after();
+              ready |= 1u << yb;
+            }
+            const uint32_t b_hi = b_base + (uint32_t)(yb * NPROD * b_tile_bytes);
+            const uint32_t d = tmem_base + (uint32_t)(il * p.n_t);
+#pragma unroll
+            for (int j = 0; j < KC / 8; ++j) {
+              const uint64_t da = ptx::make_kmajor_desc<ROW_BYTES>(a_hi + 32u * j);
+              const uint64_t db = ptx::make_kmajor_desc<ROW_BYTES>(b_hi + 32u * j);
+              ptx::umma_tf32(d, da, db, idesc, (n > 0 || j > 0) ? 1u : 0u);
+              if (X3) {
+                const uint64_t dal = ptx::make_kmajor_desc<ROW_BYTES>(a_hi + A_TILE_BYTES + 32u * j);
+                const uint64_t dbl = ptx::make_kmajor_desc<ROW_BYTES>(b_hi + b_tile_bytes + 32u * j);
+                ptx::umma_tf32(d, da, dbl, idesc, 1u);
+                ptx::umma_tf32(d, dal, db, idesc, 1u);
+              }
+            }
+          }
+          ptx::umma_commit(a_empty + 8u * stage);
+          for (int yb = 0; yb < n_y; ++yb) {
+            const int last = centre ? 0 : p.last_user[grp][yb];
+            if (last == y) {
+              ptx::umma_commit(b_empty + 8u * yb);
+              uses ^= 1u << yb;
+              ready &= ~(1u << yb);
+            }
+          }
+        }
+      }
+      ptx::umma_commit(acc_full);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == TC_PRODUCER_WARPS + 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)ptr;
+  }
+  return fn;
+}
+
+static int make_weight_tmap(CUtensorMap* out, const float* base, int T, int kcat, int kc, int n_t) {
+  PFN_encodeTiled enc = get_encode_fn();
+  GCB_REQUIRE(enc, GCB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)kcat, (cuuint64_t)T};
+  cuuint64_t strides[1] = {(cuuint64_t)kcat * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_t};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : (kc == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GCB_REQUIRE(r == CUDA_SUCCESS, GCB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return GCB_OK;
+}
+
+bool tc_supported(int R, int A, int F, int T, int n_rot) {
+  (void)R;
+  return tc_pick_config(A, F, T, n_rot, true).ok && tc_pick_config(A, F, T, n_rot, false).ok;
+}
+
+static size_t tc_recs_bytes(int v_out, int R, int A) {
+  size_t v_pad = (size_t)ceil_div64(v_out, TC_M) * TC_M;
+  return align_up((size_t)(R * A + 1) * v_pad * 32, 256);
+}
+static size_t tc_wcat_bytes(int R, int A, int F, int T) {
+  return align_up((size_t)T * ((size_t)R * A * F + F) * sizeof(float), 256);
+}
+
+size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, int precision) {
+  (void)n_rot;
+  return tc_recs_bytes(v_out, R, A) + (precision == GCB_PREC_TF32X3 ? 2 : 1) * tc_wcat_bytes(R, A, F, T) + 1024;
+}
+
+template <int KC, bool X3>
+static int tc_launch(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdParams& p, const TcConfig& cfg,
+                     dim3 grid, cudaStream_t st) {
+  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_fwd<KC, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)cfg.smem_bytes));
+  k_tc_fwd<KC, X3><<<grid, TC_THREADS, cfg.smem_bytes, st>>>(mh, ml, p);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
+                const float* bias, const RotTable& rot, int n_rot, int v_out, int v_src, int R, int A, int F,
+                int T, int act, int precision, float* y, void* workspace, size_t workspace_bytes,
+                cudaStream_t st) {
+  (void)v_src;
+  const bool x3 = precision == GCB_PREC_TF32X3;
+  TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3);
+  GCB_REQUIRE(cfg.ok, GCB_EUNSUPPORTED, "tc_conv_fwd: no tcgen05 tiling for A=%d F=%d T=%d", A, F, T);
+  GCB_REQUIRE(workspace_bytes >= tc_fwd_workspace_bytes(v_out, R, A, F, T, n_rot, precision), GCB_EWORKSPACE,
+              "tc_conv_fwd: workspace too small");
+  GCB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)bias % 16 == 0), GCB_EINVAL,
+              "tc_conv_fwd: x, y and bias must be 16-byte aligned");
+  const int RA = R * A, KRA = RA * F, kcat = KRA + F;
+  const int m_tiles = (int)ceil_div64(v_out, TC_M);
+  const int v_pad = m_tiles * TC_M;
+  char* ws = (char*)workspace;
+  ws = (char*)align_up((size_t)ws, 256);
+  uint4* recs = (uint4*)ws;
+  ws += tc_recs_bytes(v_out, R, A);
+  float* wc_hi = (float*)ws;
+  ws += tc_wcat_bytes(R, A, F, T);
+  float* wc_lo = x3 ? (float*)ws : nullptr;
+
+  {
+    int64_t total = (int64_t)(RA + 1) * v_pad;
+    k_tc_pack_recs<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(idx, w, v_out, v_pad, RA, recs);
+    GCB_LAUNCH_OK();
+    int64_t wt = (int64_t)T * kcat;
+    k_tc_wcat<<<(unsigned)ceil_div64(wt, 256), 256, 0, st>>>(w_eff, w_self, T, KRA, F, wc_hi, wc_lo);
+    GCB_LAUNCH_OK();
+  }
+  CUtensorMap mh, ml;
+  int rc = make_weight_tmap(&mh, wc_hi, T, kcat, cfg.kc, cfg.n_t);
+  if (rc) return rc;
+  rc = make_weight_tmap(&ml, x3 ? wc_lo : wc_hi, T, kcat, cfg.kc, cfg.n_t);
+  if (rc) return rc;
+
+  TcFwdParams p;
+  p.x = x; p.recs = recs; p.bias = bias; p.y = y;
+  p.v_out = v_out; p.v_pad = v_pad; p.R = R; p.A = A; p.F = F; p.T = T; p.n_rot = n_rot; p.act = act;
+  p.nfc = F / cfg.kc; p.n_t = cfg.n_t; p.g = cfg.g; p.ns_a = cfg.ns_a; p.tmem_cols = cfg.tmem_cols;
+  p.rot = rot;
+  for (int grp = 0; grp < GCB_MAX_ROT; ++grp)
+    for (int yb = 0; yb < GCB_MAX_ROT; ++yb) p.last_user[grp][yb] = -1;
+  for (int grp = 0; grp < cfg.n_groups; ++grp) {
+    int r0 = grp * cfg.g, cnt = n_rot - r0 < cfg.g ? n_rot - r0 : cfg.g;
+    for (int yb = 0; yb < A; ++yb) {
+      int last = -1;
+      for (int il = 0; il < cnt; ++il) {
+        int yy = ((yb - rot.off[r0 + il]) % A + A) % A;
+        if (yy > last) last = yy;
+      }
+      p.last_user[grp][yb] = (int8_t)last;
+    }
+  }
+  dim3 grid((unsigned)m_tiles, (unsigned)cfg.n_groups, (unsigned)(T / cfg.n_t));
+  if (cfg.kc == 32) return x3 ? tc_launch<32, true>(mh, ml, p, cfg, grid, st) : tc_launch<32, false>(mh, ml, p, cfg, grid, st);
+  if (cfg.kc == 16) return x3 ? tc_launch<16, true>(mh, ml, p, cfg, grid, st) : tc_launch<16, false>(mh, ml, p, cfg, grid, st);
+  return x3 ? tc_launch<8, true>(mh, ml, p, cfg, grid, st) : tc_launch<8, false>(mh, ml, p, cfg, grid, st);
+}
+
 }  // namespace gcb

@@ -173,7 +173,7 @@ class ConvIntrinsicFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, signal, w_eff, w_self, bias, pack: BaryPack, rot_offsets, act_id, precision):
+    def forward(ctx, signal, w_eff, w_self, bias, pack: BaryPack, rot_offsets, act_id, precision, w_anchor=None):
         lib = N.load()
         _need_cuda(signal, "signal")
         x = signal.contiguous()
@@ -200,6 +200,8 @@ class ConvIntrinsicFn(torch.autograd.Function):
         ctx.act_id = act_id
         ctx.precision = precision
         ctx.has_neighbor = w_eff is not None
+        # all-zero prior: the neighbour weights still receive an all-zeros gradient, like the reference
+        ctx.anchor_shape = None if w_anchor is None else tuple(w_anchor.shape)
         ctx.w_self_shape = tuple(w_self.shape)
         ctx.bias_shape = tuple(bias.shape)
         ctx.save_for_backward(x, w_eff_c if w_eff_c is not None else x.new_empty(0), w_self_c, y, z, arg)
@@ -219,7 +221,7 @@ class ConvIntrinsicFn(torch.autograd.Function):
         n_rot = len(ctx.rot_offsets)
         need_dx = ctx.needs_input_grad[0]
         if grad_y is None and grad_z is None:
-            return (None,) * 8
+            return (None,) * 9
         d_x = torch.empty_like(x) if need_dx else None
         d_w_eff = torch.empty((t, pack.r, pack.a, f), dtype=torch.float32, device=dev)
         d_w_self = torch.empty((t, f), dtype=torch.float32, device=dev)
@@ -261,8 +263,9 @@ class ConvIntrinsicFn(torch.autograd.Function):
                     run(1 if calls else 0)
                     calls += 1
         g_w_eff = d_w_eff if has_nb else None
+        g_anchor = None if ctx.anchor_shape is None else torch.zeros(ctx.anchor_shape, dtype=torch.float32, device=dev)
         return (d_x, g_w_eff, d_w_self.reshape(ctx.w_self_shape), d_bias.reshape(ctx.bias_shape),
-                None, None, None, None)
+                None, None, None, None, g_anchor)
 
 
 # ------------------------------------------------------------------------------------------------

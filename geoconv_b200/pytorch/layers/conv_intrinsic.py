@@ -188,8 +188,9 @@ class ConvIntrinsic(ABC, nn.Module):
         w_eff = self._effective_weights(offsets)
         r, a = self._template_size
         prec = ops.resolve_precision(self.precision, r, a, self._feature_dim, self.amt_templates, len(offsets))
+        anchor = self._template_neighbor_weights if w_eff is None else None
         return ops.ConvIntrinsicFn.apply(signal, w_eff, self._template_self_weights, self._bias, pack,
-                                         tuple(offsets), self._act_id, prec)
+                                         tuple(offsets), self._act_id, prec, anchor)
 
     @abstractmethod
     def define_kernel_values(self, template_matrix):

@@ -1,0 +1,72 @@
+"""tcgen05 forward kernel (TF32 and 3xTF32) against the CPU oracle over the tilings it selects:
+swizzle width KC in {32,16,8}, one or several rotation groups, template chunks, ragged vertex
+counts, rotation_delta > 1."""
+import pytest
+import torch
+
+from oracle import geoconv_oracle as O
+from geoconv_b200 import _native, ops
+from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
+from geoconv_b200.pytorch.layers.conv_dirac import ConvDirac
+from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
+from tests.helpers import TOL_FP32, TOL_TF32, nerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+SHAPES = [
+    # kind, V, F, R, A, T, delta, act
+    ("geodesic", 300, 64, 3, 8, 32, 1, "relu"),
+    ("geodesic", 1000, 96, 5, 8, 96, 1, "relu"),
+    ("dirac", 517, 40, 2, 6, 48, 2, "elu"),
+    ("geodesic", 200, 48, 3, 12, 16, 1, "tanh"),
+    ("dirac", 260, 32, 2, 8, 384, 4, "relu"),
+    ("geodesic", 150, 128, 3, 8, 256, 1, "leaky_relu"),
+    ("geodesic", 129, 64, 1, 3, 64, 1, "sigmoid"),
+]
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "-".join(map(str, s)))
+def test_tc_forward_matches_oracle(shape, precision):
+    kind, v, f, r, a, t, delta, act = shape
+    n_rot = len(range(0, a, delta))
+    assert _native.load().gcb_tc_supported(r, a, f, t, n_rot), "shape should be served by tcgen05"
+    wn, ws, b = O.make_weights(t, r, a, f, seed=0)
+    signal = O.make_signal(v, f, seed=1, kind="randn")
+    bary = O.make_bary(v, r, a, seed=1, fallback_frac=0.05)
+    prior = torch.from_numpy(O.geodesic_prior(O.template_matrix(r, a, 0.03))).float() if kind == "geodesic" else None
+    y_ref = O.conv_forward(signal.double(), bary, wn.double(), ws.double(), b.double(),
+                           None if prior is None else prior.double(), act, delta)
+    cls = ConvGeodesic if kind == "geodesic" else ConvDirac
+    layer = cls(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.03,
+                activation=act, rotation_delta=delta, precision=precision)
+    layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
+    layer = layer.to(DEV)
+    y = layer([signal.to(DEV), bary.to(DEV)])
+    tol = TOL_TF32 if precision == "tf32" else TOL_FP32
+    err = nerr(y, y_ref)
+    assert err < tol, f"normalised error {err:.3e} >= {tol}"
+    # fused pooling outputs are consistent with the Y this kernel produced
+    z, arg, _ = y._gcb_pooled
+    z_ref, arg_ref = O.amp_forward(y.detach().cpu())
+    assert torch.equal(arg.cpu(), arg_ref)
+    assert torch.equal(z.cpu(), z_ref)
+
+
+def test_tc_matches_ffma_on_device_and_is_deterministic():
+    v, f, r, a, t = 2000, 96, 5, 8, 96
+    wn, ws, b = O.make_weights(t, r, a, f, seed=3)
+    signal = O.make_signal(v, f, seed=2, kind="shot").to(DEV)
+    bary = O.make_bary(v, r, a, seed=2).to(DEV)
+    outs = {}
+    for precision in ("ffma", "tf32x3", "tf32"):
+        layer = ConvDirac(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.03,
+                          precision=precision)
+        layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
+        layer = layer.to(DEV)
+        outs[precision] = layer([signal, bary]).detach()
+        again = layer([signal, bary]).detach()
+        assert torch.equal(outs[precision], again)
+    assert nerr(outs["tf32x3"], outs["ffma"]) < TOL_FP32
+    assert nerr(outs["tf32"], outs["ffma"]) < TOL_TF32
