@@ -80,8 +80,9 @@ extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, 
   } else if (precision == GCB_PREC_TF32 || precision == GCB_PREC_TF32X3) {
     GCB_REQUIRE(tc_supported(R, A, F, T, n_rot), GCB_EUNSUPPORTED,
                 "gcb_conv_fwd: tcgen05 path does not support R=%d A=%d F=%d T=%d n_rot=%d", R, A, F, T, n_rot);
-    rc = tc_conv_fwd(x, idx, w, w_eff, w_self, bias, rot, n_rot, v_out, v_src, R, A, F, T, act, precision,
-                     y_out, ws, workspace_bytes, st);
+    // the tensor-core path pools in its own finishing kernel
+    return tc_conv_fwd(x, idx, w, w_eff, w_self, bias, rot, n_rot, v_out, v_src, R, A, F, T, act, precision,
+                       y_out, z, argmax, ws, workspace_bytes, st);
   } else {
     GCB_REQUIRE(false, GCB_EINVAL, "gcb_conv_fwd: unknown precision %d", precision);
   }

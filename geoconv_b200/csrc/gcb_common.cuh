@@ -86,7 +86,8 @@ size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, 
 int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                 const float* w_self, const float* bias, const RotTable& rot, int n_rot, int v_out,
                 int v_src, int R, int A, int F, int T, int act, int precision, float* y,
-                void* workspace, size_t workspace_bytes, cudaStream_t st);
+                float* z /* nullable: fused AngularMaxPooling */, int32_t* argmax, void* workspace,
+                size_t workspace_bytes, cudaStream_t st);
 
 // shared small kernels (gcb_pool.cu)
 int amp_fwd(const float* y, int v, int n_rot, int T, float* z, int32_t* argmax, cudaStream_t st);

@@ -39,7 +39,23 @@ __global__ void __launch_bounds__(NT) k_sgemm(Op op) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < op.K; k0 += BK) {
+  // two-level accumulation: every FLUSH k-blocks the running sums are folded into `tot`, so no
+  // fp32 chain is longer than FLUSH*BK terms (keeps the error well below 1e-6 for K ~ 50k)
+  constexpr int FLUSH = 16;
+  float tot[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) tot[i][j] = 0.f;
+
+  for (int k0 = 0, blk = 0; k0 < op.K; k0 += BK, ++blk) {
+    if (blk == FLUSH) {
+      blk = 0;
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+    }
     for (int e = tid; e < BM * BK; e += NT) {
       int mm, kk;
       if (Op::kAContigK) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
@@ -72,7 +88,7 @@ __global__ void __launch_bounds__(NT) k_sgemm(Op op) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int m = m0 + ty * TM + i, n = n0 + tx * TN + j;
-      if (m < op.M && n < op.N) op.store(m, n, acc[i][j]);
+      if (m < op.M && n < op.N) op.store(m, n, tot[i][j] + acc[i][j]);
     }
 }
 

@@ -1,20 +1,26 @@
-// tcgen05 forward of ConvIntrinsic (GCB_PREC_TF32 / GCB_PREC_TF32X3).
+// tcgen05 forward of ConvIntrinsic (GCB_PREC_TF32 / GCB_PREC_TF32X3), fused with AngularMaxPooling.
 //
-// One CTA = 128 output vertices x (a group of g rotations) x (a chunk n_t of templates).
 //   Y[k,i,t] = act( sum_{x,y,f} Weff[t,x,(y+o_i)%A,f] * I[k,x,y,f] + X[k]·Wself[t] + b[t] )
 // is a GEMM with M = vertices, N = (rotation, template), K = (x, y, f) plus one centre slab (f).
-// The rotation never moves data: for a fixed (x, f-chunk) all A angular B tiles (weights) sit in
-// shared memory and rotation i simply pairs the gathered A tile y with B tile (y+o_i)%A, so every
-// operand tile is staged once and used g times.
+// The rotation never moves data: for a fixed (x, f-chunk) "super-step" all A angular B tiles
+// (weights) sit in shared memory and rotation i pairs the gathered A tile y with B tile
+// (y+o_i)%A, so every operand tile is staged once and used g times.
 //
-// Warp roles (320 threads):
-//   warps 0-7  producers: barycentric 3-neighbour gather of signal rows (float4 loads, L2-resident
-//              signal) + weighted sum in registers, rounded to tf32 (RN) and written straight into
-//              the 128B/64B/32B-swizzled K-major UMMA layout; then the epilogue (tcgen05.ld ->
-//              bias + activation -> global).
-//   warp 8     TMA: weight tiles (cp.async.bulk.tensor, hardware swizzle) into the B ring.
-//   warp 9     MMA: one thread issues tcgen05.mma kind::tf32 into TMEM accumulators (g * n_t columns)
-//              and releases stages with tcgen05.commit.
+// Kernel 1  k_tc_conv: one CTA = 128 vertices x g rotations x n_t templates x one K split.
+//   warps 0-7  producers: barycentric 3-neighbour gather of signal rows (float4 loads of the
+//              L2-resident signal, records of the current radial ring cached in smem) + weighted
+//              sum in registers, rounded to tf32 (RN), written straight into the swizzled K-major
+//              UMMA layout; afterwards they drain TMEM to the split's partial-sum buffer.
+//   warp 8     TMA: weight tiles (cp.async.bulk.tensor, hardware swizzle) into the B slots.
+//   warp 9     MMA: one thread issues tcgen05.mma kind::tf32 into TMEM accumulators (g*n_t columns)
+//              and releases operand slots with tcgen05.commit.
+//   The contraction is split over CTAs (split-K) for two reasons: 108 tiles do not fill 148 SMs at
+//   the FAUST shape, and the tensor core accumulates with truncation, so a chain of thousands of
+//   accumulations loses ~1e-5 relative; short chains + an fp32 (RN) sum of the partials do not.
+// Kernel 2  k_tc_finish: per vertex, sums the K-split partials in a fixed order, adds bias,
+//   applies the activation, writes Y, and in the same pass does the angular max-pooling
+//   (norm over templates, first-max argmax over rotations, row select -> Z, argmax).
+//
 // TF32X3 (fp32-faithful): operands are split v = hi + lo (both tf32) and D += Ahi*Bhi + Ahi*Blo +
 // Alo*Bhi - three MMAs per k-step, relative error ~2^-21 per product.
 #include <cuda.h>
@@ -29,18 +35,20 @@ constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_BAR_BYTES = 1024;
+constexpr int TC_REC_BYTES = TC_M * 32;  // one (x,y) slot of packed records for a 128-vertex tile
+constexpr int TC_X3_CHAIN_K = 3072;      // TF32X3: contraction length per accumulator chain
 
 struct TcFwdParams {
   const float* x;       // [v_src, F]
-  const uint4* recs;    // [(R*A+1), v_pad, 2]: {i0,i1,i2,-} {w0,w1,w2,-}; slot R*A = centre (self, 1)
-  const float* bias;    // [T]
-  float* y;             // [v_out, n_rot, T]
-  int v_out, v_pad, R, A, F, T, n_rot, act;
+  const uint4* recs;    // [R*A, v_pad, 2]: {i0,i1,i2,-} {w0,w1,w2,-}
+  float* partial;       // [ksplit, v_pad, n_rot, T] raw accumulators
+  int v_out, v_pad, R, A, F, T, n_rot;
   int nfc;              // F / KC
   int n_t;              // templates per CTA (MMA N)
   int g;                // rotations per CTA
   int ns_a;             // A-tile ring depth
   int tmem_cols;        // power of two >= g*n_t
+  int ksplit;           // K splits (grid.z = t_chunks * ksplit)
   RotTable rot;         // offsets in [0, A)
   int8_t last_user[GCB_MAX_ROT][GCB_MAX_ROT];  // [group][yb]: last A tile y (0..A-1) that reads B tile yb
 };
@@ -62,8 +70,8 @@ static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3) {
       if (F % kc != 0) continue;
       size_t b_bytes = (size_t)A * nprod * n_t * kc * 4;
       size_t a_stage = (size_t)nprod * TC_M * kc * 4;
-      size_t fixed = b_bytes + TC_BAR_BYTES + 1024 /* alignment slack */;
-      if (fixed + 3 * a_stage > (size_t)TC_SMEM_LIMIT) continue;
+      size_t fixed = b_bytes + (size_t)A * TC_REC_BYTES + TC_BAR_BYTES + 1024 /* alignment slack */;
+      if (fixed + 4 * a_stage > (size_t)TC_SMEM_LIMIT) continue;
       int ns_a = (int)(((size_t)TC_SMEM_LIMIT - fixed) / a_stage);
       if (ns_a > 8) ns_a = 8;
       int g_max = 512 / n_t;
@@ -81,24 +89,38 @@ static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3) {
   return c;
 }
 
+// K-split count: enough to keep 3xTF32 accumulation chains short, then tuned so the grid fills
+// whole waves of 148 SMs.
+static int tc_pick_ksplit(const TcConfig& cfg, int v_out, int R, int A, int F, int T, bool x3) {
+  const int n_ss = (R + 1) * (F / cfg.kc);
+  const int64_t units = ceil_div64(v_out, TC_M) * cfg.n_groups * (T / cfg.n_t);
+  int s_min = 1;
+  if (x3) s_min = (int)ceil_div64((int64_t)(R * A + 1) * F, TC_X3_CHAIN_K);
+  if (s_min > n_ss) s_min = n_ss;
+  if (units >= 148 * 6) return s_min;
+  int best = s_min;
+  double best_eff = -1.0;
+  for (int s = s_min; s <= s_min + 8 && s <= n_ss; ++s) {
+    int64_t ctas = units * s;
+    double eff = (double)ctas / (double)(ceil_div64(ctas, 148) * 148);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
 // ---- preparation kernels ---------------------------------------------------------------------
 // slot-major packed barycentric records, padded to a multiple of 128 vertices
 __global__ void k_tc_pack_recs(const int32_t* __restrict__ idx, const float* __restrict__ w, int v_out,
                                int v_pad, int RA, uint4* __restrict__ recs) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int64_t total = (int64_t)(RA + 1) * v_pad;
+  int64_t total = (int64_t)RA * v_pad;
   if (e >= total) return;
   int slot = (int)(e / v_pad), v = (int)(e - (int64_t)slot * v_pad);
   uint4 ri = make_uint4(0, 0, 0, 0), rw = make_uint4(0, 0, 0, 0);
   if (v < v_out) {
-    if (slot < RA) {
-      size_t base = ((size_t)v * RA + slot) * 3;
-      ri = make_uint4((uint32_t)idx[base], (uint32_t)idx[base + 1], (uint32_t)idx[base + 2], 0);
-      rw = make_uint4(__float_as_uint(w[base]), __float_as_uint(w[base + 1]), __float_as_uint(w[base + 2]), 0);
-    } else {
-      ri = make_uint4((uint32_t)v, (uint32_t)v, (uint32_t)v, 0);
-      rw = make_uint4(__float_as_uint(1.f), 0, 0, 0);
-    }
+    size_t base = ((size_t)v * RA + slot) * 3;
+    ri = make_uint4((uint32_t)idx[base], (uint32_t)idx[base + 1], (uint32_t)idx[base + 2], 0);
+    rw = make_uint4(__float_as_uint(w[base]), __float_as_uint(w[base + 1]), __float_as_uint(w[base + 2]), 0);
   }
   recs[e * 2] = ri;
   recs[e * 2 + 1] = rw;
@@ -117,7 +139,7 @@ __global__ void k_tc_wcat(const float* __restrict__ w_eff, const float* __restri
   if (lo) lo[e] = v - h;
 }
 
-// ---- the kernel --------------------------------------------------------------------------------
+// ---- kernel 1: the contraction ---------------------------------------------------------------
 template <int KC>
 __device__ __forceinline__ uint32_t swz_chunk(int row, int c) {
   if (KC == 32) return (uint32_t)(c ^ (row & 7));
@@ -125,14 +147,18 @@ __device__ __forceinline__ uint32_t swz_chunk(int row, int c) {
   return (uint32_t)(c ^ ((row >> 2) & 1));
 }
 
+__device__ __forceinline__ void producer_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCER_WARPS * 32) : "memory");
+}
+
 template <int KC, bool X3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_tc_fwd(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
-         const TcFwdParams p) {
+k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
+          const TcFwdParams p) {
   constexpr int ROW_BYTES = KC * 4;
   constexpr int NPROD = X3 ? 2 : 1;
   constexpr int A_TILE_BYTES = TC_M * ROW_BYTES;
-  constexpr int CPR = KC / 4;          // 16-byte chunks per row
+  constexpr int CPR = KC / 4;                // 16-byte chunks per row
   constexpr int ROWS_PER_PASS = 32 / CPR;
   constexpr int ITEMS = 32 / ROWS_PER_PASS;  // float4 items per lane per 32-row sub-tile
 
@@ -141,7 +167,8 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CU
   const int b_tile_bytes = p.n_t * ROW_BYTES;
   const uint32_t b_base = smem_base;                                        // [A][NPROD][b_tile]
   const uint32_t a_base = b_base + (uint32_t)(p.A * NPROD * b_tile_bytes);  // [ns_a][NPROD][A_TILE]
-  const uint32_t bar_base = a_base + (uint32_t)(p.ns_a * NPROD * A_TILE_BYTES);
+  const uint32_t rec_base = a_base + (uint32_t)(p.ns_a * NPROD * A_TILE_BYTES);  // [A][128][32 B]
+  const uint32_t bar_base = rec_base + (uint32_t)(p.A * TC_REC_BYTES);
   const uint32_t a_full = bar_base;
   const uint32_t a_empty = a_full + 8u * p.ns_a;
   const uint32_t b_full = a_empty + 8u * p.ns_a;
@@ -153,11 +180,14 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_M;
   const int grp = blockIdx.y;
-  const int t0 = blockIdx.z * p.n_t;
+  const int tz = blockIdx.z / p.ksplit, sk = blockIdx.z - tz * p.ksplit;
+  const int t0 = tz * p.n_t;
   const int rot0 = grp * p.g;
   const int g_cnt = min(p.g, p.n_rot - rot0);
   const int RA = p.R * p.A;
   const int n_ss = (p.R + 1) * p.nfc;  // super-steps: (x, f-chunk) for x < R, then the centre slab
+  const int ss_begin = (int)(((int64_t)n_ss * sk) / p.ksplit);
+  const int ss_end = (int)(((int64_t)n_ss * (sk + 1)) / p.ksplit);
 
   if (warp == TC_PRODUCER_WARPS && lane == 0) {
     for (int s = 0; s < p.ns_a; ++s) {
@@ -187,30 +217,59 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CU
     const int pg = warp >> 2, wq = warp & 3;
     const int c = lane % CPR;
     const int row_l = lane / CPR;
+    const uint4* rec_smem = reinterpret_cast<const uint4*>(smem_gen + (rec_base - smem_base));
+    int ring = -1;
     int n = 0;
-    for (int ss = 0; ss < n_ss; ++ss) {
+    for (int ss = ss_begin; ss < ss_end; ++ss) {
       const bool centre = ss >= p.R * p.nfc;
-      const int xr = centre ? 0 : ss / p.nfc;
-      const int fc = centre ? ss - p.R * p.nfc : ss - xr * p.nfc;
+      const int xr = centre ? p.R : ss / p.nfc;
+      const int fc = ss - xr * p.nfc;
       const int n_y = centre ? 1 : p.A;
+      if (!centre && xr != ring) {
+        // stage this radial ring's packed records (A slots x 128 vertices x 32 B) in smem
+        producer_bar_sync();
+        uint4* dst = reinterpret_cast<uint4*>(smem_gen + (rec_base - smem_base));
+        for (int y = 0; y < p.A; ++y)
+          dst[y * (TC_M * 2) + threadIdx.x] =
+              __ldg(p.recs + ((size_t)(xr * p.A + y) * p.v_pad + m0) * 2 + threadIdx.x);
+        producer_bar_sync();
+        ring = xr;
+      }
       for (int y = 0; y < n_y; ++y, ++n) {
         if ((n & 1) != pg) continue;
-        const int slot = centre ? RA : xr * p.A + y;
-        const uint4* rec = p.recs + ((size_t)slot * p.v_pad + m0 + 32 * wq + row_l) * 2;
         const float* xcol = p.x + fc * KC + c * 4;
         float4 v[ITEMS];
+        if (!centre) {
+          const uint4* rec = rec_smem + (size_t)(y * TC_M + 32 * wq + row_l) * 2;
+          uint4 ri[ITEMS], rw[ITEMS];
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-          const uint4 ri = __ldg(rec + (size_t)j * ROWS_PER_PASS * 2);
-          const uint4 rw = __ldg(rec + (size_t)j * ROWS_PER_PASS * 2 + 1);
-          const float4 x0 = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.x * p.F));
-          const float4 x1 = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.y * p.F));
-          const float4 x2 = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.z * p.F));
-          const float w0 = __uint_as_float(rw.x), w1 = __uint_as_float(rw.y), w2 = __uint_as_float(rw.z);
-          v[j].x = fmaf(x2.x, w2, fmaf(x1.x, w1, x0.x * w0));
-          v[j].y = fmaf(x2.y, w2, fmaf(x1.y, w1, x0.y * w0));
-          v[j].z = fmaf(x2.z, w2, fmaf(x1.z, w1, x0.z * w0));
-          v[j].w = fmaf(x2.w, w2, fmaf(x1.w, w1, x0.w * w0));
+          for (int j = 0; j < ITEMS; ++j) {
+            ri[j] = rec[j * ROWS_PER_PASS * 2];
+            rw[j] = rec[j * ROWS_PER_PASS * 2 + 1];
+          }
+          float4 x0[ITEMS], x1[ITEMS], x2[ITEMS];
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) {
+            x0[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].x * p.F));
+            x1[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].y * p.F));
+            x2[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].z * p.F));
+          }
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) {
+            const float w0 = __uint_as_float(rw[j].x), w1 = __uint_as_float(rw[j].y),
+                        w2 = __uint_as_float(rw[j].z);
+            v[j].x = fmaf(x2[j].x, w2, fmaf(x1[j].x, w1, x0[j].x * w0));
+            v[j].y = fmaf(x2[j].y, w2, fmaf(x1[j].y, w1, x0[j].y * w0));
+            v[j].z = fmaf(x2[j].z, w2, fmaf(x1[j].z, w1, x0[j].z * w0));
+            v[j].w = fmaf(x2[j].w, w2, fmaf(x1[j].w, w1, x0[j].w * w0));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) {
+            const int row = m0 + 32 * wq + row_l + j * ROWS_PER_PASS;
+            v[j] = row < p.v_out ? __ldg(reinterpret_cast<const float4*>(xcol + (size_t)row * p.F))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         const int stage = n % p.ns_a;
         ptx::mbar_wait(a_empty + 8u * stage, (((uint32_t)(n / p.ns_a)) & 1u) ^ 1u);
@@ -234,39 +293,30 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CU
         if (lane == 0) ptx::mbar_arrive(a_full + 8u * stage);
       }
     }
-    // ===================== epilogue: TMEM -> bias + activation -> Y =====================
+    // ===================== drain: TMEM -> this split's partial sums =====================
     ptx::mbar_wait(acc_full, 0);
     ptx::tc_fence_after();
-    const int row = m0 + 32 * wq + lane;
+    const int row = m0 + 32 * wq + lane;  // < v_pad: the partial buffer is padded
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * wq) << 16);
+    float* prow = p.partial + (((size_t)sk * p.v_pad + row) * p.n_rot + rot0) * p.T + t0;
     for (int il = pg; il < g_cnt; il += 2) {
-      float* yrow = p.y + ((size_t)row * p.n_rot + (rot0 + il)) * p.T + t0;
       for (int c0 = 0; c0 < p.n_t; c0 += 16) {
         uint32_t r[16];
         ptx::tmem_ld_32x32b_x16(lane_addr + (uint32_t)(il * p.n_t + c0), r);
         ptx::tmem_ld_wait();
-        if (row < p.v_out) {
 #pragma unroll
-          for (int q = 0; q < 16; q += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + t0 + c0 + q));
-            float4 o;
-            o.x = act_apply(p.act, __uint_as_float(r[q + 0]) + b.x);
-            o.y = act_apply(p.act, __uint_as_float(r[q + 1]) + b.y);
-            o.z = act_apply(p.act, __uint_as_float(r[q + 2]) + b.z);
-            o.w = act_apply(p.act, __uint_as_float(r[q + 3]) + b.w);
-            *reinterpret_cast<float4*>(yrow + c0 + q) = o;
-          }
-        }
+        for (int q = 0; q < 16; q += 4)
+          *reinterpret_cast<uint4*>(prow + (size_t)il * p.T + c0 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
       }
     }
   } else if (warp == TC_PRODUCER_WARPS) {
-    // ===================== TMA: weight tiles -> B buffer =====================
+    // ===================== TMA: weight tiles -> B slots =====================
     if (lane == 0) {
       uint32_t loads = 0;  // bit yb = parity of the number of loads issued into slot yb
-      for (int ss = 0; ss < n_ss; ++ss) {
+      for (int ss = ss_begin; ss < ss_end; ++ss) {
         const bool centre = ss >= p.R * p.nfc;
-        const int xr = centre ? 0 : ss / p.nfc;
-        const int fc = centre ? ss - p.R * p.nfc : ss - xr * p.nfc;
+        const int xr = centre ? p.R : ss / p.nfc;
+        const int fc = ss - xr * p.nfc;
         const int n_y = centre ? 1 : p.A;
         for (int yb = 0; yb < n_y; ++yb) {
           ptx::mbar_wait(b_empty + 8u * yb, ((loads >> yb) & 1u) ^ 1u);
@@ -286,7 +336,7 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CU
       uint32_t uses = 0;   // bit yb = parity of completed uses of B slot yb
       uint32_t ready = 0;  // bit yb = b_full already observed for the current use
       int n = 0;
-      for (int ss = 0; ss < n_ss; ++ss) {
+      for (int ss = ss_begin; ss < ss_end; ++ss) {
         const bool centre = ss >= p.R * p.nfc;
         const int n_y = centre ? 1 : p.A;
         for (int y = 0; y < n_y; ++y, ++n) {
@@ -343,6 +393,47 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CU
   }
 }
 
+// ---- kernel 2: split reduction + bias + activation + angular max-pooling -------------------------
+// One warp per vertex; lanes own float4 column groups.  Summation order over splits is fixed.
+__global__ void k_tc_finish(const float* __restrict__ partial, const float* __restrict__ bias, int ksplit,
+                            int v_out, int v_pad, int n_rot, int T, int act, float* __restrict__ y,
+                            float* __restrict__ z, int32_t* __restrict__ argmax) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= v_out) return;
+  const size_t split_stride = (size_t)v_pad * n_rot * T;
+  const int T4 = T >> 2;
+  float best = -1.f;
+  int arg = 0;
+  for (int i = 0; i < n_rot; ++i) {
+    const float* src = partial + ((size_t)k * n_rot + i) * T;
+    float* dst = y + ((size_t)k * n_rot + i) * T;
+    float s = 0.f;
+    for (int q = lane; q < T4; q += 32) {
+      float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + q);
+      for (int sp = 0; sp < ksplit; ++sp) {
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(src + sp * split_stride) + q);
+        acc.x += pv.x; acc.y += pv.y; acc.z += pv.z; acc.w += pv.w;
+      }
+      float4 o;
+      o.x = act_apply(act, acc.x); o.y = act_apply(act, acc.y);
+      o.z = act_apply(act, acc.z); o.w = act_apply(act, acc.w);
+      reinterpret_cast<float4*>(dst)[q] = o;
+      s = fmaf(o.x, o.x, s); s = fmaf(o.y, o.y, s); s = fmaf(o.z, o.z, s); s = fmaf(o.w, o.w, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float nrm = sqrtf(s);
+    if (nrm > best) { best = nrm; arg = i; }
+  }
+  if (z) {
+    __syncwarp();
+    const float4* sel = reinterpret_cast<const float4*>(y + ((size_t)k * n_rot + arg) * T);
+    for (int q = lane; q < T4; q += 32) reinterpret_cast<float4*>(z + (size_t)k * T)[q] = sel[q];
+    if (lane == 0) argmax[k] = arg;
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -384,52 +475,66 @@ bool tc_supported(int R, int A, int F, int T, int n_rot) {
 
 static size_t tc_recs_bytes(int v_out, int R, int A) {
   size_t v_pad = (size_t)ceil_div64(v_out, TC_M) * TC_M;
-  return align_up((size_t)(R * A + 1) * v_pad * 32, 256);
+  return align_up((size_t)R * A * v_pad * 32, 256);
 }
 static size_t tc_wcat_bytes(int R, int A, int F, int T) {
   return align_up((size_t)T * ((size_t)R * A * F + F) * sizeof(float), 256);
 }
+static size_t tc_partial_bytes(int v_out, int n_rot, int T, int ksplit) {
+  size_t v_pad = (size_t)ceil_div64(v_out, TC_M) * TC_M;
+  return align_up((size_t)ksplit * v_pad * n_rot * T * sizeof(float), 256);
+}
 
 size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, int precision) {
-  (void)n_rot;
-  return tc_recs_bytes(v_out, R, A) + (precision == GCB_PREC_TF32X3 ? 2 : 1) * tc_wcat_bytes(R, A, F, T) + 1024;
+  const bool x3 = precision == GCB_PREC_TF32X3;
+  TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3);
+  if (!cfg.ok) return 0;
+  int ksplit = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3);
+  return tc_recs_bytes(v_out, R, A) + (x3 ? 2 : 1) * tc_wcat_bytes(R, A, F, T) +
+         tc_partial_bytes(v_out, n_rot, T, ksplit) + 1024;
 }
 
 template <int KC, bool X3>
 static int tc_launch(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdParams& p, const TcConfig& cfg,
                      dim3 grid, cudaStream_t st) {
-  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_fwd<KC, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_conv<KC, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)cfg.smem_bytes));
-  k_tc_fwd<KC, X3><<<grid, TC_THREADS, cfg.smem_bytes, st>>>(mh, ml, p);
+  k_tc_conv<KC, X3><<<grid, TC_THREADS, cfg.smem_bytes, st>>>(mh, ml, p);
   GCB_LAUNCH_OK();
   return GCB_OK;
 }
 
 int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
                 const float* bias, const RotTable& rot, int n_rot, int v_out, int v_src, int R, int A, int F,
-                int T, int act, int precision, float* y, void* workspace, size_t workspace_bytes,
-                cudaStream_t st) {
+                int T, int act, int precision, float* y, float* z, int32_t* argmax, void* workspace,
+                size_t workspace_bytes, cudaStream_t st) {
   (void)v_src;
   const bool x3 = precision == GCB_PREC_TF32X3;
   TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3);
   GCB_REQUIRE(cfg.ok, GCB_EUNSUPPORTED, "tc_conv_fwd: no tcgen05 tiling for A=%d F=%d T=%d", A, F, T);
   GCB_REQUIRE(workspace_bytes >= tc_fwd_workspace_bytes(v_out, R, A, F, T, n_rot, precision), GCB_EWORKSPACE,
               "tc_conv_fwd: workspace too small");
-  GCB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)bias % 16 == 0), GCB_EINVAL,
-              "tc_conv_fwd: x, y and bias must be 16-byte aligned");
+  GCB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)bias % 16 == 0) &&
+                  ((uintptr_t)z % 16 == 0),
+              GCB_EINVAL, "tc_conv_fwd: x, y, z and bias must be 16-byte aligned");
+  const int ksplit = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3);
   const int RA = R * A, KRA = RA * F, kcat = KRA + F;
   const int m_tiles = (int)ceil_div64(v_out, TC_M);
   const int v_pad = m_tiles * TC_M;
-  char* ws = (char*)workspace;
-  ws = (char*)align_up((size_t)ws, 256);
+  char* ws = (char*)align_up((size_t)workspace, 256);
   uint4* recs = (uint4*)ws;
   ws += tc_recs_bytes(v_out, R, A);
   float* wc_hi = (float*)ws;
   ws += tc_wcat_bytes(R, A, F, T);
-  float* wc_lo = x3 ? (float*)ws : nullptr;
+  float* wc_lo = nullptr;
+  if (x3) {
+    wc_lo = (float*)ws;
+    ws += tc_wcat_bytes(R, A, F, T);
+  }
+  float* partial = (float*)ws;
 
   {
-    int64_t total = (int64_t)(RA + 1) * v_pad;
+    int64_t total = (int64_t)RA * v_pad;
     k_tc_pack_recs<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(idx, w, v_out, v_pad, RA, recs);
     GCB_LAUNCH_OK();
     int64_t wt = (int64_t)T * kcat;
@@ -443,9 +548,10 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   if (rc) return rc;
 
   TcFwdParams p;
-  p.x = x; p.recs = recs; p.bias = bias; p.y = y;
-  p.v_out = v_out; p.v_pad = v_pad; p.R = R; p.A = A; p.F = F; p.T = T; p.n_rot = n_rot; p.act = act;
+  p.x = x; p.recs = recs; p.partial = partial;
+  p.v_out = v_out; p.v_pad = v_pad; p.R = R; p.A = A; p.F = F; p.T = T; p.n_rot = n_rot;
   p.nfc = F / cfg.kc; p.n_t = cfg.n_t; p.g = cfg.g; p.ns_a = cfg.ns_a; p.tmem_cols = cfg.tmem_cols;
+  p.ksplit = ksplit;
   p.rot = rot;
   for (int grp = 0; grp < GCB_MAX_ROT; ++grp)
     for (int yb = 0; yb < GCB_MAX_ROT; ++yb) p.last_user[grp][yb] = -1;
@@ -460,10 +566,16 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
       p.last_user[grp][yb] = (int8_t)last;
     }
   }
-  dim3 grid((unsigned)m_tiles, (unsigned)cfg.n_groups, (unsigned)(T / cfg.n_t));
-  if (cfg.kc == 32) return x3 ? tc_launch<32, true>(mh, ml, p, cfg, grid, st) : tc_launch<32, false>(mh, ml, p, cfg, grid, st);
-  if (cfg.kc == 16) return x3 ? tc_launch<16, true>(mh, ml, p, cfg, grid, st) : tc_launch<16, false>(mh, ml, p, cfg, grid, st);
-  return x3 ? tc_launch<8, true>(mh, ml, p, cfg, grid, st) : tc_launch<8, false>(mh, ml, p, cfg, grid, st);
+  dim3 grid((unsigned)m_tiles, (unsigned)cfg.n_groups, (unsigned)((T / cfg.n_t) * ksplit));
+  if (cfg.kc == 32) rc = x3 ? tc_launch<32, true>(mh, ml, p, cfg, grid, st) : tc_launch<32, false>(mh, ml, p, cfg, grid, st);
+  else if (cfg.kc == 16) rc = x3 ? tc_launch<16, true>(mh, ml, p, cfg, grid, st) : tc_launch<16, false>(mh, ml, p, cfg, grid, st);
+  else rc = x3 ? tc_launch<8, true>(mh, ml, p, cfg, grid, st) : tc_launch<8, false>(mh, ml, p, cfg, grid, st);
+  if (rc) return rc;
+  const int warps_per_block = 8;
+  k_tc_finish<<<(unsigned)ceil_div64(v_out, warps_per_block), warps_per_block * 32, 0, st>>>(
+      partial, bias, ksplit, v_out, v_pad, n_rot, T, act, y, z, argmax);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
 }
 
 }  // namespace gcb
