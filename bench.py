@@ -1,0 +1,338 @@
+"""Benchmark of the ConvGeodesic + AngularMaxPooling forward+backward hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|tf32] [--impl ours|reference]
+
+Workload (config.workload = "S1"): one FAUST-shaped synthetic mesh per step and per GPU -
+V=6890 vertices, 544-dim SHOT-shaped signal, ConvGeodesic 544->96, R5xA8, rotation_delta 1, relu,
+followed by AngularMaxPooling; forward + backward (gradients w.r.t. signal, template weights,
+self weights, bias) of a random upstream gradient.  Metric: vertices/sec.
+
+One JSON line is printed by rank 0:
+  value     device-resident throughput (inputs already in HBM), CUDA-event timed, L2 flushed
+            between steps, max over ranks;
+  e2e       the same metric through the public layer API starting from pinned HOST buffers
+            (signal, bary, upstream grad copied H2D and the pooled output copied D2H every step);
+  roofline  the dominant kernel (forward tcgen05 contraction) timed live with CUDA events on its
+            launch stream, algorithmic FLOPs / duration against the TF32 tensor peak derived from
+            MEASURED_PEAKS.json (bf16/2; TF32 itself is not in that file);
+  cpu_baseline  the CPU oracle (a port of the reference algorithm in stock torch CPU ops) timed on
+            this host's cores on the same workload.
+`--impl reference` times that CPU oracle only (rank 0), with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S1 = dict(v=6890, f=544, r=5, a=8, t=96, delta=1, act="relu", radius=0.028)
+L2_FLUSH_BYTES = 512 << 20
+
+
+def algorithmic_flops(cfg):
+    """fwd 2*V*n_rot*K*T + 2*V*F*T ; bwd (AMP-sparse) 4*V*K*T + 4*V*F*T."""
+    v, f, r, a, t = cfg["v"], cfg["f"], cfg["r"], cfg["a"], cfg["t"]
+    n_rot = len(range(0, a, cfg["delta"]))
+    k = r * a * f
+    fwd = 2 * v * n_rot * k * t + 2 * v * f * t
+    bwd = 4 * v * k * t + 4 * v * f * t
+    return fwd, bwd
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(cfg, seed_offset=0):
+    import torch
+    from oracle import geoconv_oracle as O
+    v, f, r, a, t = cfg["v"], cfg["f"], cfg["r"], cfg["a"], cfg["t"]
+    signal = O.make_signal(v, f, seed=1 + seed_offset, kind="shot")
+    bary = O.make_bary(v, r, a, seed=1 + seed_offset)
+    grad_z = torch.randn((v, t), generator=torch.Generator().manual_seed(2 + seed_offset))
+    return signal, bary, grad_z
+
+
+def cpu_reference_step(cfg, weights, inputs):
+    """One fwd+bwd of the CPU oracle (reference algorithm restated in stock torch CPU ops)."""
+    import torch
+    from oracle import geoconv_oracle as O
+    wn, ws, b = weights
+    signal, bary, grad_z = inputs
+    prior = torch.from_numpy(O.geodesic_prior(O.template_matrix(cfg["r"], cfg["a"], cfg["radius"]))).float()
+    t0 = time.perf_counter()
+    O.conv_amp_forward_backward(signal, bary, wn, ws, b, prior, grad_z, cfg["act"], cfg["delta"])
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    import torch
+    from oracle import geoconv_oracle as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = S1
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    weights = O.make_weights(cfg["t"], cfg["r"], cfg["a"], cfg["f"], seed=0)
+    inputs = make_inputs(cfg)
+    for _ in range(args.warmup):
+        cpu_reference_step(cfg, weights, inputs)
+    total = 0.0
+    for _ in range(args.steps):
+        total += cpu_reference_step(cfg, weights, inputs)
+    value = cfg["v"] * args.steps / total
+    line = {
+        "impl": "reference", "metric": "vertices/sec, ConvGeodesic+AMP fwd+bwd", "value": value,
+        "unit": "vertices/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "S1: V=6890 F=544 T=96 R5xA8 delta1 relu, ConvGeodesic+AMP fwd+bwd, 1 mesh/step",
+                   "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "vertices/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full S1 meshes (fwd+bwd), torch {torch.__version__} CPU"},
+        "e2e": {"value": value, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from geoconv_b200 import _native
+    from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
+    from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
+    from oracle import geoconv_oracle as O
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _native.load()
+    cfg = S1
+    v, f, r, a, t = cfg["v"], cfg["f"], cfg["r"], cfg["a"], cfg["t"]
+
+    weights = O.make_weights(t, r, a, f, seed=0)
+    layer = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t,
+                         template_radius=cfg["radius"], activation=cfg["act"], rotation_delta=cfg["delta"],
+                         precision=args.precision)
+    layer.load_state_dict({"_template_neighbor_weights": weights[0], "_template_self_weights": weights[1],
+                           "_bias": weights[2]})
+    layer = layer.to(dev)
+    amp = AngularMaxPooling()
+    signal_h, bary_h, gz_h = [x.pin_memory() for x in make_inputs(cfg, seed_offset=rank)]
+    signal_d = signal_h.to(dev).requires_grad_(True)
+    bary_d = bary_h.to(dev)
+    gz_d = gz_h.to(dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    params = [layer._template_neighbor_weights, layer._template_self_weights, layer._bias]
+
+    def step_resident():
+        for p_ in params:
+            p_.grad = None
+        signal_d.grad = None
+        z = amp(layer([signal_d, bary_d]))
+        z.backward(gz_d)
+        return z
+
+    # buffers for the host-to-host leg
+    sig_buf = torch.empty_like(signal_d)
+    bary_buf = torch.empty_like(bary_d)
+    gz_buf = torch.empty_like(gz_d)
+    z_host = torch.empty((v, t), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        for p_ in params:
+            p_.grad = None
+        sig_buf.copy_(signal_h, non_blocking=True)
+        bary_buf.copy_(bary_h, non_blocking=True)     # bumps the version: bary is re-packed, CSR rebuilt
+        gz_buf.copy_(gz_h, non_blocking=True)
+        xs = sig_buf.detach().requires_grad_(True)
+        z = amp(layer([xs, bary_buf]))
+        z.backward(gz_buf)
+        z_host.copy_(z.detach(), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            flush.zero_()
+            step_fn()
+        barrier()
+        if profile:
+            lib.gcb_profile_enable(1)
+        launches0 = lib.gcb_launch_count()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()                     # evict the previous step's working set from L2
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        total_ms = sum(a_.elapsed_time(b_) for a_, b_ in evs)
+        launches = lib.gcb_launch_count() - launches0
+        if world > 1:
+            tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            total_ms = tt.item()
+        return total_ms, launches
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms, launches = timed(step_resident, args.steps, args.warmup, profile=True)
+    import ctypes
+    prof = {}
+    for which, name in ((0, "fwd_conv"),):
+        ms = ctypes.c_double(0.0)
+        cnt = ctypes.c_int64(0)
+        lib.gcb_profile_read(which, ctypes.byref(ms), ctypes.byref(cnt))
+        prof[name] = (ms.value, cnt.value)
+    lib.gcb_profile_enable(0)
+    clocks = sampler.stop()
+    e2e_ms, _ = timed(step_e2e, args.steps, args.warmup)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * v * args.steps / (total_ms * 1e-3)
+    e2e_value = world * v * args.steps / (e2e_ms * 1e-3)
+    fwd_flops, bwd_flops = algorithmic_flops(cfg)
+    peaks = load_peaks()
+    tf32_peak = peaks["bf16_tflops"] / 2.0
+    k_ms, k_cnt = prof["fwd_conv"]
+    achieved = (fwd_flops * k_cnt / (k_ms * 1e-3)) / 1e12 if k_ms > 0 and k_cnt else None
+    roofline = {
+        "bound": "tensor", "kernel": "k_tc_conv (forward gather+tcgen05 contraction)",
+        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+        "frac": (achieved / tf32_peak) if achieved else None, "traffic": None,
+        "peak_source": f"{peaks['source']} bf16_tflops/2 (TF32 dense peak is derived, not measured)",
+        "algorithmic_flops_per_launch": fwd_flops, "kernel_ms_avg": (k_ms / k_cnt) if k_cnt else None,
+        "note": ("fp32 mode runs 3 tf32 MMAs per product (3xTF32): its ceiling against this peak is 1/3"
+                 if args.precision == "fp32" else "single-pass tf32"),
+    }
+
+    # CPU baseline: the oracle on this host's cores, bounded sample (1 warm-up + 2 timed meshes)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cpu_inputs = make_inputs(cfg)
+    cpu_reference_step(cfg, weights, cpu_inputs)
+    cpu_t = min(cpu_reference_step(cfg, weights, cpu_inputs) for _ in range(2))
+    cpu_baseline = {"value": v / cpu_t, "unit": "vertices/s", "cores": cores, "kind": "port",
+                    "sample": "best of 2 full S1 meshes (fwd+bwd) after 1 warm-up, torch CPU oracle"}
+
+    h2d = signal_h.numel() * 4 + bary_h.numel() * bary_h.element_size() + gz_h.numel() * 4
+    d2h = z_host.numel() * 4
+    line = {
+        "metric": "vertices/sec, ConvGeodesic+AMP fwd+bwd", "value": value, "unit": "vertices/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+        "config": {"workload": "S1: V=6890 F=544 T=96 R5xA8 delta1 relu, ConvGeodesic+AMP fwd+bwd, 1 mesh/step/GPU",
+                   "precision": args.precision, "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)",
+                   "parallelism": f"dp{world} (independent meshes per rank)"},
+        "e2e": {"value": e2e_value, "unit": "vertices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "clocks": clocks,
+        "flops_per_step": {"fwd": fwd_flops, "bwd": bwd_flops},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "ffma"])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

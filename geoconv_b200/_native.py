@@ -30,6 +30,9 @@ _sz = C.c_size_t
 SIGNATURES = {
     "gcb_abi_version": (_int, []),
     "gcb_last_error": (C.c_char_p, []),
+    "gcb_launch_count": (_i64, []),
+    "gcb_profile_enable": (None, [_int]),
+    "gcb_profile_read": (_int, [_int, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "gcb_tc_supported": (_int, [_i32, _i32, _i32, _i32, _i32]),
     "gcb_prep_bary": (_int, [_p, _int, _i64, _i32, _p, _p, _p, _p]),
     "gcb_csr_workspace_bytes": (_sz, [_i64, _i32]),

@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <vector>
+
 #include "gcb_common.cuh"
 
 namespace gcb {
@@ -13,6 +16,34 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional kernel timing (one host thread per process drives the library) ----
+struct ProfSlot {
+  std::vector<cudaEvent_t> start, stop;
+  size_t used = 0;
+};
+static bool g_prof_on = false;
+static ProfSlot g_prof[GCB_PROF_N];
+
+void profile_begin(int which, cudaStream_t st) {
+  if (!g_prof_on) return;
+  ProfSlot& s = g_prof[which];
+  if (s.used == s.start.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    s.start.push_back(a);
+    s.stop.push_back(b);
+  }
+  cudaEventRecord(s.start[s.used], st);
+}
+void profile_end(int which, cudaStream_t st) {
+  if (!g_prof_on) return;
+  ProfSlot& s = g_prof[which];
+  if (s.used < s.start.size()) cudaEventRecord(s.stop[s.used++], st);
 }
 
 static int make_rot_table(const int32_t* rot_off_host, int n_rot, int A, RotTable* out) {
@@ -38,6 +69,26 @@ static int check_shape(int v_out, int v_src, int R, int A, int F, int T) {
 using namespace gcb;
 
 extern "C" int gcb_abi_version(void) { return GCB_ABI_VERSION; }
+extern "C" int64_t gcb_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" void gcb_profile_enable(int on) {
+  g_prof_on = on != 0;
+  if (g_prof_on)
+    for (int i = 0; i < GCB_PROF_N; ++i) g_prof[i].used = 0;
+}
+extern "C" int gcb_profile_read(int which, double* ms_total, int64_t* launches) {
+  GCB_REQUIRE(which >= 0 && which < GCB_PROF_N && ms_total && launches, GCB_EINVAL, "gcb_profile_read: bad argument");
+  ProfSlot& s = g_prof[which];
+  double total = 0.0;
+  for (size_t i = 0; i < s.used; ++i) {
+    GCB_CUDA_OK(cudaEventSynchronize(s.stop[i]));
+    float ms = 0.f;
+    GCB_CUDA_OK(cudaEventElapsedTime(&ms, s.start[i], s.stop[i]));
+    total += ms;
+  }
+  *ms_total = total;
+  *launches = (int64_t)s.used;
+  return GCB_OK;
+}
 extern "C" const char* gcb_last_error(void) { return g_err; }
 
 extern "C" int gcb_tc_supported(int32_t R, int32_t A, int32_t F, int32_t T, int32_t n_rot) {

@@ -28,7 +28,19 @@ void set_error(const char* fmt, ...);
     }                                \
   } while (0)
 
-#define GCB_LAUNCH_OK() GCB_CUDA_OK(cudaGetLastError())
+// every kernel launch of the library goes through this: error check + launch accounting
+void count_launch();
+#define GCB_LAUNCH_OK()              \
+  do {                               \
+    gcb::count_launch();             \
+    GCB_CUDA_OK(cudaGetLastError()); \
+  } while (0)
+
+// optional per-kernel timing (bench.py's roofline leg): events recorded around the dominant
+// kernel on its own stream while profiling is enabled
+void profile_begin(int which, cudaStream_t st);
+void profile_end(int which, cudaStream_t st);
+enum { GCB_PROF_FWD_CONV = 0, GCB_PROF_BWD_DW = 1, GCB_PROF_BWD_DI = 2, GCB_PROF_BWD_CSR = 3, GCB_PROF_N = 4 };
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -36,7 +36,7 @@ constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_BAR_BYTES = 1024;
 constexpr int TC_REC_BYTES = TC_M * 32;  // one (x,y) slot of packed records for a 128-vertex tile
-constexpr int TC_X3_CHAIN_K = 3072;      // TF32X3: contraction length per accumulator chain
+constexpr int TC_X3_CHAIN_K = 2048;      // TF32X3: contraction length per accumulator chain
 
 struct TcFwdParams {
   const float* x;       // [v_src, F]
@@ -499,7 +499,9 @@ static int tc_launch(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdPa
                      dim3 grid, cudaStream_t st) {
   GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_conv<KC, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)cfg.smem_bytes));
+  profile_begin(GCB_PROF_FWD_CONV, st);
   k_tc_conv<KC, X3><<<grid, TC_THREADS, cfg.smem_bytes, st>>>(mh, ml, p);
+  profile_end(GCB_PROF_FWD_CONV, st);
   GCB_LAUNCH_OK();
   return GCB_OK;
 }

@@ -55,6 +55,14 @@ extern "C" {
 
 int gcb_abi_version(void);
 const char* gcb_last_error(void);
+/* Kernel launches issued by this library in this process so far (bench.py's gpu_launches). */
+int64_t gcb_launch_count(void);
+/* Measurement hooks (bench.py's roofline leg): while enabled, CUDA events bracket the dominant
+ * kernels on their launch stream.  which: 0 = forward contraction, 1 = backward dW contraction,
+ * 2 = backward dI contraction, 3 = backward CSR gather-reduce.  gcb_profile_read synchronises
+ * on the recorded events and returns their summed duration and count since the last enable. */
+void gcb_profile_enable(int on);
+int gcb_profile_read(int which, double* ms_total, int64_t* launches);
 /* 1 if the tcgen05 kernels can serve this shape, else 0 (then use GCB_PREC_FP32). */
 int gcb_tc_supported(int32_t R, int32_t A, int32_t F, int32_t T, int32_t n_rot);
 

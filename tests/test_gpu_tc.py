@@ -22,7 +22,7 @@ SHAPES = [
     ("geodesic", 200, 48, 3, 12, 16, 1, "tanh"),
     ("dirac", 260, 32, 2, 8, 384, 4, "relu"),
     ("geodesic", 150, 128, 3, 8, 256, 1, "leaky_relu"),
-    ("geodesic", 129, 64, 1, 3, 64, 1, "sigmoid"),
+    ("dirac", 129, 64, 1, 3, 64, 1, "sigmoid"),
 ]
 
 
