@@ -35,6 +35,7 @@ constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_BAR_BYTES = 1024;
+constexpr int TC_G_MAX = 8;              // rotations per CTA (accumulator groups) upper bound
 constexpr int TC_REC_BYTES = TC_M * 32;  // one (x,y) slot of packed records for a 128-vertex tile
 constexpr int TC_X3_CHAIN_K = 2048;      // TF32X3: contraction length per accumulator chain
 
@@ -50,7 +51,6 @@ struct TcFwdParams {
   int tmem_cols;        // power of two >= g*n_t
   int ksplit;           // K splits (grid.z = t_chunks * ksplit)
   RotTable rot;         // offsets in [0, A)
-  int8_t last_user[GCB_MAX_ROT][GCB_MAX_ROT];  // [group][yb]: last A tile y (0..A-1) that reads B tile yb
 };
 
 struct TcConfig {
@@ -75,6 +75,7 @@ static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3) {
       int ns_a = (int)(((size_t)TC_SMEM_LIMIT - fixed) / a_stage);
       if (ns_a > 8) ns_a = 8;
       int g_max = 512 / n_t;
+      if (g_max > TC_G_MAX) g_max = TC_G_MAX;
       if (g_max > n_rot) g_max = n_rot;
       int n_groups = (n_rot + g_max - 1) / g_max;
       int g = (n_rot + n_groups - 1) / n_groups;
@@ -220,6 +221,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     const uint4* rec_smem = reinterpret_cast<const uint4*>(smem_gen + (rec_base - smem_base));
     int ring = -1;
     int n = 0;
+    int stage = 0;             // n % ns_a, kept as a rolling counter (no integer division per tile)
+    uint32_t empty_par = 1u;   // parity to wait for on a_empty[stage]: ((n / ns_a) & 1) ^ 1
     for (int ss = ss_begin; ss < ss_end; ++ss) {
       const bool centre = ss >= p.R * p.nfc;
       const int xr = centre ? p.R : ss / p.nfc;
@@ -236,6 +239,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         ring = xr;
       }
       for (int y = 0; y < n_y; ++y, ++n) {
+        const int my_stage = stage;
+        const uint32_t my_par = empty_par;
+        if (++stage == p.ns_a) { stage = 0; empty_par ^= 1u; }
         if ((n & 1) != pg) continue;
         const float* xcol = p.x + fc * KC + c * 4;
         float4 v[ITEMS];
@@ -271,9 +277,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        const int stage = n % p.ns_a;
-        ptx::mbar_wait(a_empty + 8u * stage, (((uint32_t)(n / p.ns_a)) & 1u) ^ 1u);
-        uint8_t* a_hi = smem_gen + (a_base - smem_base) + (size_t)stage * NPROD * A_TILE_BYTES;
+        ptx::mbar_wait(a_empty + 8u * my_stage, my_par);
+        uint8_t* a_hi = smem_gen + (a_base - smem_base) + (size_t)my_stage * NPROD * A_TILE_BYTES;
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
           const int row = 32 * wq + row_l + j * ROWS_PER_PASS;
@@ -290,7 +295,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(a_full + 8u * stage);
+        if (lane == 0) ptx::mbar_arrive(a_full + 8u * my_stage);
       }
     }
     // ===================== drain: TMEM -> this split's partial sums =====================
@@ -331,54 +336,83 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     }
   } else {
     // ===================== MMA issuer =====================
+    // A single thread feeds the tensor core, so this loop is kept to a handful of integer
+    // instructions per MMA: descriptors are (constant high word, low word = address>>4) pairs,
+    // the B slot of every rotation is a rolling index in a register, and which B slots to release
+    // after an A tile comes from a precomputed bit mask.
+    // release_mask[y]: B slots whose last reader within a super-step is A tile y (lane y computes it)
+    volatile uint32_t* rel_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 768);
+    if (lane < p.A) {
+      uint32_t mask = 0;
+      for (int s = 0; s < p.A; ++s) {
+        int last = -1;
+        for (int il = 0; il < g_cnt; ++il) {
+          int yy = s - p.rot.off[rot0 + il];
+          yy += yy < 0 ? p.A : 0;
+          last = yy > last ? yy : last;
+        }
+        mask |= (last == lane) ? (1u << s) : 0u;
+      }
+      rel_smem[lane] = mask;
+    }
+    __syncwarp();
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_tf32(TC_M, p.n_t);
-      uint32_t uses = 0;   // bit yb = parity of completed uses of B slot yb
-      uint32_t ready = 0;  // bit yb = b_full already observed for the current use
+      const uint64_t desc_hi = ptx::make_kmajor_desc<ROW_BYTES>(0) & 0xFFFFFFFF00000000ull;
+      const uint32_t lo_flags = (uint32_t)(ptx::make_kmajor_desc<ROW_BYTES>(0) & 0xFFFF0000ull);
+      const uint32_t b_slot_lo = (uint32_t)(NPROD * b_tile_bytes) >> 4;
+      const uint32_t b_lo_half = (uint32_t)b_tile_bytes >> 4;
+      const uint32_t b_lo0 = (b_base >> 4) | lo_flags;
+      int yb[TC_G_MAX];
+#pragma unroll
+      for (int il = 0; il < TC_G_MAX; ++il) yb[il] = il < g_cnt ? p.rot.off[rot0 + il] : 0;
+      uint32_t uses = 0;   // bit s = parity of completed uses of B slot s
+      uint32_t ready = 0;  // bit s = b_full already observed for the current use
+      uint32_t accum = 0;  // 0 only for the very first k-step of this CTA
       int n = 0;
+      int stage = 0;          // rolling n % ns_a
+      uint32_t full_par = 0;  // (n / ns_a) & 1
       for (int ss = ss_begin; ss < ss_end; ++ss) {
         const bool centre = ss >= p.R * p.nfc;
         const int n_y = centre ? 1 : p.A;
         for (int y = 0; y < n_y; ++y, ++n) {
-          const int stage = n % p.ns_a;
-          ptx::mbar_wait(a_full + 8u * stage, ((uint32_t)(n / p.ns_a)) & 1u);
+          const uint32_t release = centre ? 1u : rel_smem[y];
+          ptx::mbar_wait(a_full + 8u * stage, full_par);
           ptx::tc_fence_after();
-          const uint32_t a_hi = a_base + (uint32_t)(stage * NPROD * A_TILE_BYTES);
-          for (int il = 0; il < g_cnt; ++il) {
-            int yb = 0;
-            if (!centre) {
-              yb = y + p.rot.off[rot0 + il];
-              yb -= (yb >= p.A) ? p.A : 0;
-            }
-            if (!((ready >> yb) & 1u)) {
-              ptx::mbar_wait(b_full + 8u * yb, (uses >> yb) & 1u);
-              ptx::tc_fence_after();
-              ready |= 1u << yb;
-            }
-            const uint32_t b_hi = b_base + (uint32_t)(yb * NPROD * b_tile_bytes);
-            const uint32_t d = tmem_base + (uint32_t)(il * p.n_t);
+          const uint32_t a_lo = ((a_base + (uint32_t)(stage * NPROD * A_TILE_BYTES)) >> 4) | lo_flags;
 #pragma unroll
-            for (int j = 0; j < KC / 8; ++j) {
-              const uint64_t da = ptx::make_kmajor_desc<ROW_BYTES>(a_hi + 32u * j);
-              const uint64_t db = ptx::make_kmajor_desc<ROW_BYTES>(b_hi + 32u * j);
-              ptx::umma_tf32(d, da, db, idesc, (n > 0 || j > 0) ? 1u : 0u);
-              if (X3) {
-                const uint64_t dal = ptx::make_kmajor_desc<ROW_BYTES>(a_hi + A_TILE_BYTES + 32u * j);
-                const uint64_t dbl = ptx::make_kmajor_desc<ROW_BYTES>(b_hi + b_tile_bytes + 32u * j);
-                ptx::umma_tf32(d, da, dbl, idesc, 1u);
-                ptx::umma_tf32(d, dal, db, idesc, 1u);
+          for (int il = 0; il < TC_G_MAX; ++il) {
+            if (il < g_cnt) {
+              const int s = centre ? 0 : yb[il];
+              if (!((ready >> s) & 1u)) {
+                ptx::mbar_wait(b_full + 8u * s, (uses >> s) & 1u);
+                ptx::tc_fence_after();
+                ready |= 1u << s;
               }
+              const uint32_t b_lo = b_lo0 + (uint32_t)s * b_slot_lo;
+              const uint32_t d = tmem_base + (uint32_t)(il * p.n_t);
+#pragma unroll
+              for (int j = 0; j < KC / 8; ++j) {
+                const uint64_t da = desc_hi | (uint64_t)(a_lo + 2u * j);
+                const uint64_t db = desc_hi | (uint64_t)(b_lo + 2u * j);
+                ptx::umma_tf32(d, da, db, idesc, j == 0 ? accum : 1u);
+                if (X3) {
+                  ptx::umma_tf32(d, da, desc_hi | (uint64_t)(b_lo + b_lo_half + 2u * j), idesc, 1u);
+                  ptx::umma_tf32(d, desc_hi | (uint64_t)(a_lo + (A_TILE_BYTES >> 4) + 2u * j), db, idesc, 1u);
+                }
+              }
+              if (!centre) yb[il] = (yb[il] + 1 == p.A) ? 0 : yb[il] + 1;
             }
           }
+          accum = 1u;
           ptx::umma_commit(a_empty + 8u * stage);
-          for (int yb = 0; yb < n_y; ++yb) {
-            const int last = centre ? 0 : p.last_user[grp][yb];
-            if (last == y) {
-              ptx::umma_commit(b_empty + 8u * yb);
-              uses ^= 1u << yb;
-              ready &= ~(1u << yb);
-            }
+          for (uint32_t m = release; m; m &= m - 1) {
+            const int s = __ffs((int)m) - 1;
+            ptx::umma_commit(b_empty + 8u * s);
           }
+          uses ^= release;
+          ready &= ~release;
+          if (++stage == p.ns_a) { stage = 0; full_par ^= 1u; }
         }
       }
       ptx::umma_commit(acc_full);
@@ -555,19 +589,6 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   p.nfc = F / cfg.kc; p.n_t = cfg.n_t; p.g = cfg.g; p.ns_a = cfg.ns_a; p.tmem_cols = cfg.tmem_cols;
   p.ksplit = ksplit;
   p.rot = rot;
-  for (int grp = 0; grp < GCB_MAX_ROT; ++grp)
-    for (int yb = 0; yb < GCB_MAX_ROT; ++yb) p.last_user[grp][yb] = -1;
-  for (int grp = 0; grp < cfg.n_groups; ++grp) {
-    int r0 = grp * cfg.g, cnt = n_rot - r0 < cfg.g ? n_rot - r0 : cfg.g;
-    for (int yb = 0; yb < A; ++yb) {
-      int last = -1;
-      for (int il = 0; il < cnt; ++il) {
-        int yy = ((yb - rot.off[r0 + il]) % A + A) % A;
-        if (yy > last) last = yy;
-      }
-      p.last_user[grp][yb] = (int8_t)last;
-    }
-  }
   dim3 grid((unsigned)m_tiles, (unsigned)cfg.n_groups, (unsigned)((T / cfg.n_t) * ksplit));
   if (cfg.kc == 32) rc = x3 ? tc_launch<32, true>(mh, ml, p, cfg, grid, st) : tc_launch<32, false>(mh, ml, p, cfg, grid, st);
   else if (cfg.kc == 16) rc = x3 ? tc_launch<16, true>(mh, ml, p, cfg, grid, st) : tc_launch<16, false>(mh, ml, p, cfg, grid, st);
