@@ -32,7 +32,8 @@ namespace gcb {
 
 constexpr int TC_M = 128;
 constexpr int TC_PRODUCER_WARPS = 8;
-constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;
+constexpr int TC_MMA_WARPS = 4;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + TC_MMA_WARPS) * 32;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_BAR_BYTES = 1024;
 constexpr int TC_G_MAX = 8;              // rotations per CTA (accumulator groups) upper bound
@@ -193,13 +194,13 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   if (warp == TC_PRODUCER_WARPS && lane == 0) {
     for (int s = 0; s < p.ns_a; ++s) {
       ptx::mbar_init(a_full + 8u * s, 4);
-      ptx::mbar_init(a_empty + 8u * s, 1);
+      ptx::mbar_init(a_empty + 8u * s, (uint32_t)min(g_cnt, TC_MMA_WARPS));
     }
     for (int s = 0; s < p.A; ++s) {
       ptx::mbar_init(b_full + 8u * s, 1);
-      ptx::mbar_init(b_empty + 8u * s, 1);
+      ptx::mbar_init(b_empty + 8u * s, (uint32_t)g_cnt);
     }
-    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(acc_full, (uint32_t)min(g_cnt, TC_MMA_WARPS));
     ptx::fence_mbar_init();
     ptx::prefetch_tensormap(&tmap_hi);
     if (X3) ptx::prefetch_tensormap(&tmap_lo);
@@ -335,60 +336,43 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       }
     }
   } else {
-    // ===================== MMA issuer =====================
-    // A single thread feeds the tensor core, so this loop is kept to a handful of integer
-    // instructions per MMA: descriptors are (constant high word, low word = address>>4) pairs,
-    // the B slot of every rotation is a rolling index in a register, and which B slots to release
-    // after an A tile comes from a precomputed bit mask.
-    // release_mask[y]: B slots whose last reader within a super-step is A tile y (lane y computes it)
-    volatile uint32_t* rel_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 768);
-    if (lane < p.A) {
-      uint32_t mask = 0;
-      for (int s = 0; s < p.A; ++s) {
-        int last = -1;
-        for (int il = 0; il < g_cnt; ++il) {
-          int yy = s - p.rot.off[rot0 + il];
-          yy += yy < 0 ? p.A : 0;
-          last = yy > last ? yy : last;
-        }
-        mask |= (last == lane) ? (1u << s) : 0u;
-      }
-      rel_smem[lane] = mask;
-    }
-    __syncwarp();
-    if (lane == 0) {
+    // ===================== MMA issuers =====================
+    // tcgen05.mma is issued by one thread, and at N = n_t <= 256 that thread's integer bookkeeping
+    // (~25 instructions per MMA) would outlast the 48-cycle MMAs.  Rotations accumulate into
+    // disjoint TMEM columns, so they are independent: MMA warp mw owns rotations mw, mw+4, ...
+    // and the issue work runs TC_MMA_WARPS-wide.  Every owner commits to the stage / slot barriers
+    // itself (a_empty counts active MMA warps, b_empty counts rotations).
+    const int mw = warp - (TC_PRODUCER_WARPS + 1);
+    if (lane == 0 && mw < g_cnt) {
       const uint32_t idesc = ptx::make_idesc_tf32(TC_M, p.n_t);
       const uint64_t desc_hi = ptx::make_kmajor_desc<ROW_BYTES>(0) & 0xFFFFFFFF00000000ull;
       const uint32_t lo_flags = (uint32_t)(ptx::make_kmajor_desc<ROW_BYTES>(0) & 0xFFFF0000ull);
       const uint32_t b_slot_lo = (uint32_t)(NPROD * b_tile_bytes) >> 4;
       const uint32_t b_lo_half = (uint32_t)b_tile_bytes >> 4;
       const uint32_t b_lo0 = (b_base >> 4) | lo_flags;
-      int yb[TC_G_MAX];
+      constexpr int OWN = TC_G_MAX / TC_MMA_WARPS;
+      int yb[OWN];  // rolling B slot of each owned rotation
 #pragma unroll
-      for (int il = 0; il < TC_G_MAX; ++il) yb[il] = il < g_cnt ? p.rot.off[rot0 + il] : 0;
-      uint32_t uses = 0;   // bit s = parity of completed uses of B slot s
-      uint32_t ready = 0;  // bit s = b_full already observed for the current use
-      uint32_t accum = 0;  // 0 only for the very first k-step of this CTA
-      int n = 0;
+      for (int q = 0; q < OWN; ++q) yb[q] = (mw + q * TC_MMA_WARPS) < g_cnt ? p.rot.off[rot0 + mw + q * TC_MMA_WARPS] : 0;
+      const uint32_t all_slots = p.A >= 32 ? 0xFFFFFFFFu : ((1u << p.A) - 1u);
+      uint32_t fills = 0;     // bit s = parity of completed fills of B slot s
+      uint32_t accum = 0;     // 0 only for the very first k-step of this CTA
       int stage = 0;          // rolling n % ns_a
       uint32_t full_par = 0;  // (n / ns_a) & 1
       for (int ss = ss_begin; ss < ss_end; ++ss) {
         const bool centre = ss >= p.R * p.nfc;
         const int n_y = centre ? 1 : p.A;
-        for (int y = 0; y < n_y; ++y, ++n) {
-          const uint32_t release = centre ? 1u : rel_smem[y];
+        for (int y = 0; y < n_y; ++y) {
           ptx::mbar_wait(a_full + 8u * stage, full_par);
           ptx::tc_fence_after();
           const uint32_t a_lo = ((a_base + (uint32_t)(stage * NPROD * A_TILE_BYTES)) >> 4) | lo_flags;
 #pragma unroll
-          for (int il = 0; il < TC_G_MAX; ++il) {
+          for (int q = 0; q < OWN; ++q) {
+            const int il = mw + q * TC_MMA_WARPS;
             if (il < g_cnt) {
-              const int s = centre ? 0 : yb[il];
-              if (!((ready >> s) & 1u)) {
-                ptx::mbar_wait(b_full + 8u * s, (uses >> s) & 1u);
-                ptx::tc_fence_after();
-                ready |= 1u << s;
-              }
+              const int s = centre ? 0 : yb[q];
+              ptx::mbar_wait(b_full + 8u * s, (fills >> s) & 1u);
+              ptx::tc_fence_after();
               const uint32_t b_lo = b_lo0 + (uint32_t)s * b_slot_lo;
               const uint32_t d = tmem_base + (uint32_t)(il * p.n_t);
 #pragma unroll
@@ -401,19 +385,15 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
                   ptx::umma_tf32(d, desc_hi | (uint64_t)(a_lo + (A_TILE_BYTES >> 4) + 2u * j), db, idesc, 1u);
                 }
               }
-              if (!centre) yb[il] = (yb[il] + 1 == p.A) ? 0 : yb[il] + 1;
+              ptx::umma_commit(b_empty + 8u * s);
+              if (!centre) yb[q] = (yb[q] + 1 == p.A) ? 0 : yb[q] + 1;
             }
           }
           accum = 1u;
           ptx::umma_commit(a_empty + 8u * stage);
-          for (uint32_t m = release; m; m &= m - 1) {
-            const int s = __ffs((int)m) - 1;
-            ptx::umma_commit(b_empty + 8u * s);
-          }
-          uses ^= release;
-          ready &= ~release;
           if (++stage == p.ns_a) { stage = 0; full_par ^= 1u; }
         }
+        fills ^= centre ? 1u : all_slots;
       }
       ptx::umma_commit(acc_full);
     }
