@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "gcb_common.cuh"
+#include "gcb_tc.cuh"
 
 namespace gcb {
 
@@ -144,9 +145,13 @@ extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, 
 
 extern "C" size_t gcb_conv_bwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A,
                                                int32_t F, int32_t T, int precision) {
-  (void)v_src; (void)T; (void)precision;
   size_t d_full = align_up((size_t)v_out * R * A * F * sizeof(float), 256);
-  return d_full + ffma_bwd_workspace_bytes(v_out, R, A, F) + 256;
+  size_t ffma = d_full + ffma_bwd_workspace_bytes(v_out, R, A, F) + 256;
+  if (precision != GCB_PREC_FP32 && tc_bwd_supported(R, A, F, T)) {
+    size_t tc = tc_bwd_workspace_bytes(v_out, v_src, R, A, F, T, precision) + 256;
+    return tc > ffma ? tc : ffma;
+  }
+  return ffma;
 }
 
 extern "C" int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
@@ -167,7 +172,9 @@ extern "C" int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, 
   char* ws = (char*)workspace;
   float* d_full = (float*)ws;
   ws += align_up((size_t)v_out * R * A * F * sizeof(float), 256);
-  // TODO(tc-bwd): precision TF32/TF32X3 currently share the fp32 CUDA-core contraction.
+  if (precision != GCB_PREC_FP32 && w_eff && tc_bwd_supported(R, A, F, T))
+    return tc_conv_bwd(x, idx, w, w_eff, w_self, h, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T,
+                       precision, accumulate, d_x, d_w_eff, d_w_self, d_bias, workspace, workspace_bytes, st);
   rc = ffma_conv_bwd(x, idx, w, w_eff, h, rot_sel, v_out, v_src, R, A, F, T, accumulate, d_w_eff, d_w_self,
                      d_bias, d_x ? d_full : nullptr, ws, st);
   if (rc || !d_x) return rc;

@@ -27,6 +27,7 @@
 
 #include "gcb_common.cuh"
 #include "gcb_ptx.cuh"
+#include "gcb_tc.cuh"
 
 namespace gcb {
 
@@ -466,19 +467,42 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-static int make_weight_tmap(CUtensorMap* out, const float* base, int T, int kcat, int kc, int n_t) {
+int tc_make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_t outer,
+                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
   PFN_encodeTiled enc = get_encode_fn();
   GCB_REQUIRE(enc, GCB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {(cuuint64_t)kcat, (cuuint64_t)T};
-  cuuint64_t strides[1] = {(cuuint64_t)kcat * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_t};
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)row_stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUtensorMapSwizzle sw = kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                   : (kc == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMapSwizzle sw = box_inner == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                          : (box_inner == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GCB_REQUIRE(r == CUDA_SUCCESS, GCB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return GCB_OK;
+}
+
+static int make_weight_tmap(CUtensorMap* out, const float* base, int T, int kcat, int kc, int n_t) {
+  return tc_make_tmap_2d(out, base, (uint64_t)kcat, (uint64_t)T, (uint64_t)kcat * sizeof(float), (uint32_t)kc,
+                         (uint32_t)n_t);
+}
+
+int tc_pack_recs(const int32_t* idx, const float* w, int v_out, int R, int A, uint4* recs, cudaStream_t st) {
+  const int v_pad = (int)ceil_div64(v_out, TC_M) * TC_M;
+  int64_t total = (int64_t)R * A * v_pad;
+  k_tc_pack_recs<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(idx, w, v_out, v_pad, R * A, recs);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+int tc_build_wcat(const float* w_eff, const float* w_self, int T, int R, int A, int F, float* hi, float* lo,
+                  cudaStream_t st) {
+  const int KRA = R * A * F;
+  int64_t wt = (int64_t)T * (KRA + F);
+  k_tc_wcat<<<(unsigned)ceil_div64(wt, 256), 256, 0, st>>>(w_eff, w_self, T, KRA, F, hi, lo);
+  GCB_LAUNCH_OK();
   return GCB_OK;
 }
 
@@ -487,11 +511,11 @@ bool tc_supported(int R, int A, int F, int T, int n_rot) {
   return tc_pick_config(A, F, T, n_rot, true).ok && tc_pick_config(A, F, T, n_rot, false).ok;
 }
 
-static size_t tc_recs_bytes(int v_out, int R, int A) {
+size_t tc_recs_bytes(int v_out, int R, int A) {
   size_t v_pad = (size_t)ceil_div64(v_out, TC_M) * TC_M;
   return align_up((size_t)R * A * v_pad * 32, 256);
 }
-static size_t tc_wcat_bytes(int R, int A, int F, int T) {
+size_t tc_wcat_bytes(int R, int A, int F, int T) {
   return align_up((size_t)T * ((size_t)R * A * F + F) * sizeof(float), 256);
 }
 static size_t tc_partial_bytes(int v_out, int n_rot, int T, int ksplit) {
@@ -549,16 +573,12 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   }
   float* partial = (float*)ws;
 
-  {
-    int64_t total = (int64_t)RA * v_pad;
-    k_tc_pack_recs<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(idx, w, v_out, v_pad, RA, recs);
-    GCB_LAUNCH_OK();
-    int64_t wt = (int64_t)T * kcat;
-    k_tc_wcat<<<(unsigned)ceil_div64(wt, 256), 256, 0, st>>>(w_eff, w_self, T, KRA, F, wc_hi, wc_lo);
-    GCB_LAUNCH_OK();
-  }
+  int rc = tc_pack_recs(idx, w, v_out, R, A, recs, st);
+  if (rc) return rc;
+  rc = tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);
+  if (rc) return rc;
   CUtensorMap mh, ml;
-  int rc = make_weight_tmap(&mh, wc_hi, T, kcat, cfg.kc, cfg.n_t);
+  rc = make_weight_tmap(&mh, wc_hi, T, kcat, cfg.kc, cfg.n_t);
   if (rc) return rc;
   rc = make_weight_tmap(&ml, x3 ? wc_lo : wc_hi, T, kcat, cfg.kc, cfg.n_t);
   if (rc) return rc;
