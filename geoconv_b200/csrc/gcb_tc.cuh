@@ -8,8 +8,10 @@ namespace gcb {
 
 // 2-D fp32 tensor map: `inner` contiguous elements per row, `outer` rows of `row_stride_bytes`;
 // box = box_inner x box_outer; swizzle span = box_inner * 4 bytes (128 / 64 / 32).
+// atom32 = true selects the 128B swizzle with 32-byte atoms (the only layout UMMA accepts for
+// MN-major tf32 operands).
 int tc_make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_t outer,
-                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, bool atom32 = false);
 
 // slot-major packed barycentric records [R*A][v_pad][2 x uint4], v_pad = multiple of 128
 size_t tc_recs_bytes(int v_out, int R, int A);

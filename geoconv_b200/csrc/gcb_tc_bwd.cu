@@ -24,15 +24,17 @@ namespace gcb {
 
 constexpr int BW_SMEM_LIMIT = 227 * 1024;
 
-// MN-major SWIZZLE_128B descriptor: 32 fp32 along M/N are contiguous (128 B), 8 K-rows of 128 B form
-// a 1024 B atom; `lbo` = byte distance between atoms along M/N, `sbo` = along K.
+// MN-major descriptor for tf32: the only layout UMMA accepts is SWIZZLE_128B_BASE32B (layout type 1):
+// 32 fp32 along M/N are contiguous (a 128 B row), 4 K-rows form a 512 B atom whose four 32-byte chunks
+// are XOR-swizzled with (row % 4), i.e. Swizzle<2,5,2> on byte addresses.  `lbo` = byte distance between
+// atoms along M/N, `sbo` = between 4-row groups along K (one K=8 MMA reads two of them).
 __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)(lbo >> 4) << 16;
   d |= (uint64_t)(sbo >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;
   return d;
 }
 
@@ -199,9 +201,9 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUt
       }
       ptx::mbar_wait(empty + 8u * stage, empty_par);
       uint8_t* a_hi = smem_gen + (size_t)stage * stage_bytes;
-      // MN-major: atom (mn_blk j, k_blk) at j*4096 + k_blk*1024; row (vertex%8) of 128 B, swizzled chunks
-      const uint32_t off_row = (uint32_t)(vrow >> 3) * 1024u + (uint32_t)(vrow & 7) * 128u +
-                               (uint32_t)((c8 ^ (vrow & 7)) * 16);
+      // MN-major tf32 tile: feature block j at j*4096, vertex row at vrow*128, 32-byte chunks
+      // swizzled with (row % 4) (SWIZZLE_128B_BASE32B)
+      const uint32_t off_row = (uint32_t)vrow * 128u + (uint32_t)((((c8 >> 1) ^ (vrow & 3)) << 5) | ((c8 & 1) << 4));
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float4 hv;
@@ -267,13 +269,13 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUt
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int kb = mw * 2 + q;
-          const uint64_t da = make_mnmajor_desc(a_hi + kb * 1024, 4096, 1024);
+          const uint64_t da = make_mnmajor_desc(a_hi + kb * 1024, 4096, 512);
           const uint64_t db = ptx::make_kmajor_desc<128>(b_hi + kb * 32);
           ptx::umma_tf32(d, da, db, idesc, accum);
           accum = 1u;
           if (X3) {
             ptx::umma_tf32(d, da, ptx::make_kmajor_desc<128>(b_hi + b_bytes + kb * 32), idesc, 1u);
-            ptx::umma_tf32(d, make_mnmajor_desc(a_hi + DW_A_BYTES + kb * 1024, 4096, 1024), db, idesc, 1u);
+            ptx::umma_tf32(d, make_mnmajor_desc(a_hi + DW_A_BYTES + kb * 1024, 4096, 512), db, idesc, 1u);
           }
         }
         ptx::umma_commit(empty + 8u * stage);
@@ -424,11 +426,11 @@ k_tc_di(const __grid_constant__ CUtensorMap tmap_h_hi, const __grid_constant__ C
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
             const uint64_t da = ptx::make_kmajor_desc<128>(a_hi + kb * 32);
-            const uint64_t db = make_mnmajor_desc(b_hi + kb * 1024, 4096, 1024);
+            const uint64_t db = make_mnmajor_desc(b_hi + kb * 1024, 4096, 512);
             ptx::umma_tf32(d, da, db, idesc, accum);
             accum = 1u;
             if (X3) {
-              ptx::umma_tf32(d, da, make_mnmajor_desc(b_hi + DI_STAGE_B + kb * 1024, 4096, 1024), idesc, 1u);
+              ptx::umma_tf32(d, da, make_mnmajor_desc(b_hi + DI_STAGE_B + kb * 1024, 4096, 512), idesc, 1u);
               ptx::umma_tf32(d, ptx::make_kmajor_desc<128>(a_hi + DI_STAGE_A + kb * 32), db, idesc, 1u);
             }
           }
@@ -642,9 +644,9 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     if (rc) return rc;
     rc = tc_make_tmap_2d(&hl, x3 ? hr_lo : hr_hi, (uint64_t)T, (uint64_t)L.v_pad, (uint64_t)T * 4, 32, 128);
     if (rc) return rc;
-    rc = tc_make_tmap_2d(&wh, wc_hi, (uint64_t)L.kcat, (uint64_t)T, (uint64_t)L.kcat * 4, 32, 32);
+    rc = tc_make_tmap_2d(&wh, wc_hi, (uint64_t)L.kcat, (uint64_t)T, (uint64_t)L.kcat * 4, 32, 32, true);
     if (rc) return rc;
-    rc = tc_make_tmap_2d(&wl, x3 ? wc_lo : wc_hi, (uint64_t)L.kcat, (uint64_t)T, (uint64_t)L.kcat * 4, 32, 32);
+    rc = tc_make_tmap_2d(&wl, x3 ? wc_lo : wc_hi, (uint64_t)L.kcat, (uint64_t)T, (uint64_t)L.kcat * 4, 32, 32, true);
     if (rc) return rc;
     TcDiParams p;
     p.d_full = d_full; p.v_out = v_out; p.KRA = KRA; p.T = T;

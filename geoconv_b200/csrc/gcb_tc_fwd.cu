@@ -468,7 +468,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 int tc_make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_t outer,
-                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, bool atom32) {
   PFN_encodeTiled enc = get_encode_fn();
   GCB_REQUIRE(enc, GCB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -477,6 +477,7 @@ int tc_make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_
   cuuint32_t estr[2] = {1, 1};
   CUtensorMapSwizzle sw = box_inner == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
                                           : (box_inner == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  if (atom32) sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
