@@ -176,6 +176,8 @@ class ConvIntrinsicFn(torch.autograd.Function):
     def forward(ctx, signal, w_eff, w_self, bias, pack: BaryPack, rot_offsets, act_id, precision, w_anchor=None):
         lib = N.load()
         _need_cuda(signal, "signal")
+        # `precision` is one code for both directions or a (forward, backward) pair
+        precision, precision_bwd = precision if isinstance(precision, tuple) else (precision, precision)
         x = signal.contiguous()
         v_src, f = x.shape
         t = w_self.shape[0]
@@ -198,7 +200,7 @@ class ConvIntrinsicFn(torch.autograd.Function):
         ctx.pack = pack
         ctx.rot_offsets = tuple(int(o) for o in rot_offsets)
         ctx.act_id = act_id
-        ctx.precision = precision
+        ctx.precision = precision_bwd
         ctx.has_neighbor = w_eff is not None
         # all-zero prior: the neighbour weights still receive an all-zeros gradient, like the reference
         ctx.anchor_shape = None if w_anchor is None else tuple(w_anchor.shape)

@@ -82,6 +82,7 @@ class ConvIntrinsic(ABC, nn.Module):
         self.initializer = initializer
         self.include_prior = include_prior
         self.precision = precision or os.environ.get("GEOCONV_B200_PRECISION", "fp32")
+        self.backward_precision = None  # None: same as `precision`
         self.check_indices = True
 
         self._activation = ACTIVATIONS[self.activation_fn]
@@ -188,6 +189,9 @@ class ConvIntrinsic(ABC, nn.Module):
         w_eff = self._effective_weights(offsets)
         r, a = self._template_size
         prec = ops.resolve_precision(self.precision, r, a, self._feature_dim, self.amt_templates, len(offsets))
+        if self.backward_precision is not None:
+            prec = (prec, ops.resolve_precision(self.backward_precision, r, a, self._feature_dim,
+                                                self.amt_templates, len(offsets)))
         anchor = self._template_neighbor_weights if w_eff is None else None
         return ops.ConvIntrinsicFn.apply(signal, w_eff, self._template_self_weights, self._bias, pack,
                                          tuple(offsets), self._act_id, prec, anchor)

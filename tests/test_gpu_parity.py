@@ -223,6 +223,16 @@ def test_faust_shape_against_oracle(precision):
     assert nerr(y, ref["y"]) < tol
     flips = (arg != ref["argmax"]).sum().item()
     assert argmax_ok(arg, ref["argmax"], ref["y"], 2e-6 if tol == TOL_FP32 else 4 * tol)
+    if tol == TOL_TF32:
+        # gradients of a TF32 forward legitimately differ where a ReLU mask or a rotation flips;
+        # check the TF32 backward arithmetic behind an exact forward instead
+        layer.precision, layer.backward_precision = "ffma", precision
+        for prm in layer.parameters():
+            prm.grad = None
+        xs = signal.to(DEV).requires_grad_(True)
+        y = layer([xs, bary.to(DEV)])
+        z = AngularMaxPooling()(y)
+        flips = (y._gcb_pooled[1].cpu() != ref["argmax"]).sum().item()
     z.backward(grad_z.to(DEV))
     if flips == 0:
         assert nerr(z, ref["z"]) < tol
