@@ -59,7 +59,11 @@ __global__ void k_select_rot(const int32_t* __restrict__ argmax, RotTable rot, i
 // dX[v,:] (+)= sum_{slots s -> v} w[s] * D[k_s, x_s, (y_s + rot_sel[k_s]) % A, :]
 //               + [v < v_out] sum_t h[v,t] * Wself[t,:]
 // D is the unrotated dI [v_out,R,A,F]; the per-vertex rotation is applied as an index here.
-// One block per source vertex; VEC = 4 uses float4 lanes.
+// One block per source vertex.  The entry list is decoded cooperatively (one thread per entry:
+// slot id -> row of D and weight) into shared memory, then every thread streams its float4 column
+// over the rows with 8 independent loads in flight.  Fixed order => bit-reproducible.
+constexpr int CSR_CHUNK = 256;
+
 template <int VEC>
 __global__ void k_csr_reduce_dx(const float* __restrict__ d_full, const float* __restrict__ w,
                                 const float* __restrict__ h, const float* __restrict__ w_self,
@@ -67,46 +71,80 @@ __global__ void k_csr_reduce_dx(const float* __restrict__ d_full, const float* _
                                 const int32_t* __restrict__ row_ptr,
                                 const int32_t* __restrict__ entries, int v_out, int R, int A,
                                 int F, int T, int accumulate, float* __restrict__ d_x) {
+  __shared__ uint32_t s_row[CSR_CHUNK];
+  __shared__ float s_w[CSR_CHUNK];
   const int v = blockIdx.x;
   const int beg = d_full ? row_ptr[v] : 0, end = d_full ? row_ptr[v + 1] : 0;  // d_full NULL: centre only
   const int RA = R * A;
   const int FV = F / VEC;
-  for (int fv = threadIdx.x; fv < FV; fv += blockDim.x) {
-    float acc[VEC];
+  const int fv = threadIdx.x;          // blockDim.x >= FV
+  const bool active = fv < FV;
+  float acc[VEC];
 #pragma unroll
-    for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
-    if (v < v_out) {
-      for (int t = 0; t < T; ++t) {
-        float hv = h[(size_t)v * T + t];
-        const float* ws = w_self + (size_t)t * F + (size_t)fv * VEC;
+  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+  if (active && v < v_out) {
+    for (int t = 0; t < T; ++t) {
+      const float hv = h[(size_t)v * T + t];
+      const float* ws = w_self + (size_t)t * F + (size_t)fv * VEC;
+      if constexpr (VEC == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(ws));
+        acc[0] = fmaf(hv, q.x, acc[0]); acc[1] = fmaf(hv, q.y, acc[1]);
+        acc[2] = fmaf(hv, q.z, acc[2]); acc[3] = fmaf(hv, q.w, acc[3]);
+      } else {
+        acc[0] = fmaf(hv, __ldg(ws), acc[0]);
+      }
+    }
+  }
+  for (int base = beg; base < end; base += CSR_CHUNK) {
+    const int n = min(CSR_CHUNK, end - base);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int s = entries[base + i];
+      const int cell = s / 3;          // (k, x, y)
+      const int k = cell / RA;
+      const int slot = cell - k * RA;
+      const int xr = slot / A, ya = slot - xr * A;
+      int yr = ya + rot_sel[k];
+      yr -= (yr >= A) ? A : 0;
+      s_row[i] = (uint32_t)(k * RA + xr * A + yr);
+      s_w[i] = w[s];
+    }
+    __syncthreads();
+    if (active) {
+      const float* col = d_full + (size_t)fv * VEC;
+      int i = 0;
+      for (; i + 8 <= n; i += 8) {
         if constexpr (VEC == 4) {
-          float4 q = *reinterpret_cast<const float4*>(ws);
-          acc[0] = fmaf(hv, q.x, acc[0]); acc[1] = fmaf(hv, q.y, acc[1]);
-          acc[2] = fmaf(hv, q.z, acc[2]); acc[3] = fmaf(hv, q.w, acc[3]);
+          float4 q[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) q[u] = __ldg(reinterpret_cast<const float4*>(col + (size_t)s_row[i + u] * F));
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float ws = s_w[i + u];
+            acc[0] = fmaf(ws, q[u].x, acc[0]); acc[1] = fmaf(ws, q[u].y, acc[1]);
+            acc[2] = fmaf(ws, q[u].z, acc[2]); acc[3] = fmaf(ws, q[u].w, acc[3]);
+          }
         } else {
-          acc[0] = fmaf(hv, ws[0], acc[0]);
+          float q[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) q[u] = __ldg(col + (size_t)s_row[i + u] * F);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[0] = fmaf(s_w[i + u], q[u], acc[0]);
+        }
+      }
+      for (; i < n; ++i) {
+        const float ws = s_w[i];
+        if constexpr (VEC == 4) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(col + (size_t)s_row[i] * F));
+          acc[0] = fmaf(ws, q.x, acc[0]); acc[1] = fmaf(ws, q.y, acc[1]);
+          acc[2] = fmaf(ws, q.z, acc[2]); acc[3] = fmaf(ws, q.w, acc[3]);
+        } else {
+          acc[0] = fmaf(ws, __ldg(col + (size_t)s_row[i] * F), acc[0]);
         }
       }
     }
-#pragma unroll 4
-    for (int e = beg; e < end; ++e) {
-      int s = entries[e];
-      float ws = w[s];
-      int cell = s / 3;          // (k, x, y)
-      int k = cell / RA;
-      int slot = cell - k * RA;
-      int xr = slot / A, ya = slot - xr * A;
-      int yr = ya + rot_sel[k];
-      yr -= (yr >= A) ? A : 0;
-      const float* src = d_full + ((size_t)k * RA + (size_t)(xr * A + yr)) * F + (size_t)fv * VEC;
-      if constexpr (VEC == 4) {
-        float4 q = __ldg(reinterpret_cast<const float4*>(src));
-        acc[0] = fmaf(ws, q.x, acc[0]); acc[1] = fmaf(ws, q.y, acc[1]);
-        acc[2] = fmaf(ws, q.z, acc[2]); acc[3] = fmaf(ws, q.w, acc[3]);
-      } else {
-        acc[0] = fmaf(ws, __ldg(src), acc[0]);
-      }
-    }
+    __syncthreads();
+  }
+  if (active) {
     float* dst = d_x + (size_t)v * F + (size_t)fv * VEC;
 #pragma unroll
     for (int c = 0; c < VEC; ++c) dst[c] = accumulate ? dst[c] + acc[c] : acc[c];
@@ -128,7 +166,8 @@ int csr_reduce_dx(const float* d_full, const float* w, const float* h, const flo
   if (v_src <= 0) return GCB_OK;
   bool vec4 = (F % 4 == 0) && (((uintptr_t)d_full | (uintptr_t)w_self | (uintptr_t)d_x) % 16 == 0);
   int lanes = vec4 ? F / 4 : F;
-  int threads = lanes < 32 ? 32 : (lanes > 256 ? 256 : (lanes + 31) / 32 * 32);
+  GCB_REQUIRE(lanes <= 1024, GCB_EUNSUPPORTED, "csr_reduce_dx: feature dimension %d too large", F);
+  int threads = lanes < 32 ? 32 : (lanes + 31) / 32 * 32;
   if (vec4)
     k_csr_reduce_dx<4><<<v_src, threads, 0, st>>>(d_full, w, h, w_self, rot_sel, row_ptr, entries, v_out, R, A, F, T, accumulate, d_x);
   else

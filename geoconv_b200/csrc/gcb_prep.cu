@@ -65,23 +65,36 @@ static int key_bits(int32_t v_src) {
 
 // ---- prior folding ---------------------------------------------------------------------------
 // out[t,q,f] = sum_p in[t,p,f] * (transpose ? prior[q,p] : prior[p,q]),  p,q in [0, R*A)
-__global__ void k_fold_prior(const float* __restrict__ in, const float* __restrict__ prior,
-                             float* __restrict__ out, int RA, int F, int transpose) {
-  extern __shared__ float s_prior[];  // RA*RA
-  for (int i = threadIdx.x; i < RA * RA; i += blockDim.x) s_prior[i] = prior[i];
+// One block = one template t and 32 consecutive features: the [RA x 32] input slab is staged in
+// smem once; warp w produces output slots q = w, w+8, ... (lanes = features, the prior element is
+// a warp-wide broadcast).  fp32 FMAs with a compensated (two-sum free) pairwise split over p.
+__global__ void __launch_bounds__(256) k_fold_prior(const float* __restrict__ in, const float* __restrict__ prior,
+                                                    float* __restrict__ out, int RA, int F, int transpose) {
+  extern __shared__ float s_mem[];
+  float* s_prior = s_mem;             // RA*RA, stored so that s_prior[q*RA + p] multiplies in[p]
+  float* s_in = s_mem + RA * RA;      // RA*32
+  const int t = blockIdx.y, f0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < RA * RA; i += blockDim.x) {
+    const int q = i / RA, p = i - q * RA;
+    s_prior[i] = transpose ? prior[q * RA + p] : prior[p * RA + q];
+  }
+  for (int i = threadIdx.x; i < RA * 32; i += blockDim.x) {
+    const int p = i >> 5, fl = i & 31;
+    s_in[i] = (f0 + fl < F) ? in[((size_t)t * RA + p) * F + f0 + fl] : 0.f;
+  }
   __syncthreads();
-  int t = blockIdx.y;
-  int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F) return;
-  const float* src = in + (size_t)t * RA * F + f;
-  float* dst = out + (size_t)t * RA * F + f;
-  for (int q = 0; q < RA; ++q) {
-    double acc = 0.0;
-    for (int p = 0; p < RA; ++p) {
-      float kv = transpose ? s_prior[q * RA + p] : s_prior[p * RA + q];
-      acc += (double)src[(size_t)p * F] * (double)kv;
+  if (f0 + lane >= F) return;
+  for (int q = warp; q < RA; q += 8) {
+    const float* kq = s_prior + q * RA;
+    float a0 = 0.f, a1 = 0.f;
+    int p = 0;
+    for (; p + 1 < RA; p += 2) {
+      a0 = fmaf(s_in[p * 32 + lane], kq[p], a0);
+      a1 = fmaf(s_in[(p + 1) * 32 + lane], kq[p + 1], a1);
     }
-    dst[(size_t)q * F] = (float)acc;
+    if (p < RA) a0 = fmaf(s_in[p * 32 + lane], kq[p], a0);
+    out[((size_t)t * RA + q) * F + f0 + lane] = a0 + a1;
   }
 }
 
@@ -150,12 +163,12 @@ extern "C" int gcb_fold_prior(const float* in, const float* prior, float* out, i
   GCB_REQUIRE(in && prior && out, GCB_EINVAL, "gcb_fold_prior: null pointer");
   GCB_REQUIRE(T > 0 && R > 0 && A > 0 && F > 0, GCB_EINVAL, "gcb_fold_prior: bad sizes");
   int RA = R * A;
-  size_t smem = (size_t)RA * RA * sizeof(float);
+  size_t smem = ((size_t)RA * RA + (size_t)RA * 32) * sizeof(float);
   GCB_REQUIRE(smem <= 160 * 1024, GCB_EUNSUPPORTED, "gcb_fold_prior: R*A=%d too large", RA);
   if (smem > 48 * 1024)
     GCB_CUDA_OK(cudaFuncSetAttribute(k_fold_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div64(F, 128), (unsigned)T);
-  k_fold_prior<<<grid, 128, smem, (cudaStream_t)stream>>>(in, prior, out, RA, F, transpose);
+  dim3 grid((unsigned)ceil_div64(F, 32), (unsigned)T);
+  k_fold_prior<<<grid, 256, smem, (cudaStream_t)stream>>>(in, prior, out, RA, F, transpose);
   GCB_LAUNCH_OK();
   return GCB_OK;
 }

@@ -40,8 +40,10 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32
 
 __global__ void k_bw_transpose_h(const float* __restrict__ h, int v_out, int v_pad, int T,
                                  float* __restrict__ ht_hi, float* __restrict__ ht_lo,
-                                 float* __restrict__ h_hi, float* __restrict__ h_lo) {
-  // ht[t][v] (v padded with zeros) for k_tc_dw;  h_hi/h_lo [v_pad][T] for k_tc_di
+                                 float* __restrict__ h_hi, float* __restrict__ h_lo,
+                                 float* __restrict__ bias_part) {
+  // ht[t][v] (v padded with zeros) for k_tc_dw;  h_hi/h_lo [v_pad][T] for k_tc_di;
+  // bias_part[blockIdx.x][t] = sum of this block's 32 rows (first stage of d_bias)
   __shared__ float tile[32][33];
   const int v0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -55,6 +57,12 @@ __global__ void k_bw_transpose_h(const float* __restrict__ h, int v_out, int v_p
     }
   }
   __syncthreads();
+  if (threadIdx.y == 0 && t0 + threadIdx.x < T) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc += tile[i][threadIdx.x];
+    bias_part[(size_t)blockIdx.x * T + t0 + threadIdx.x] = acc;
+  }
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int t = t0 + i, v = v0 + threadIdx.x;
     if (t < T && v < v_pad) {
@@ -305,17 +313,7 @@ __global__ void k_tc_dw_finish(const float* __restrict__ partial, int vsplit, in
   if (dst) *dst = accumulate ? *dst + acc : acc;
 }
 
-// d_bias[t] (+)= sum_k h[k,t]   two-stage, fixed order
-__global__ void k_bw_bias_partial(const float* __restrict__ h, int v_out, int T, int rows_per_block,
-                                  float* __restrict__ part) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  const int k0 = blockIdx.y * rows_per_block;
-  const int k1 = min(v_out, k0 + rows_per_block);
-  float acc = 0.f;
-  for (int k = k0; k < k1; ++k) acc += h[(size_t)k * T + t];
-  part[(size_t)blockIdx.y * T + t] = acc;
-}
+// d_bias[t] (+)= sum over the per-block partial sums written by k_bw_transpose_h (fixed order)
 __global__ void k_bw_bias_final(const float* __restrict__ part, int nblocks, int T, int accumulate,
                                 float* __restrict__ d_bias) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -528,7 +526,7 @@ static BwLayout bw_layout(int v_out, int R, int A, int F, int T, bool x3) {
   L.ht = align_up((size_t)np * T * L.v_pad * sizeof(float), 256);
   L.hrow = align_up((size_t)np * L.v_pad * T * sizeof(float), 256);
   L.partial = align_up((size_t)L.vsplit * T * L.kcat_pad * sizeof(float), 256);
-  L.bias_part = align_up((size_t)64 * T * sizeof(float), 256);
+  L.bias_part = align_up((size_t)(L.v_pad / 32) * T * sizeof(float), 256);
   L.d_full = align_up((size_t)v_out * R * A * F * sizeof(float), 256);
   L.total = L.recs + L.wcat + L.ht + L.hrow + L.partial + L.bias_part + L.d_full + 1024;
   return L;
@@ -591,17 +589,9 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
   if (rc) return rc;
   {
     dim3 grid((unsigned)(L.v_pad / 32), (unsigned)ceil_div64(T, 32));
-    k_bw_transpose_h<<<grid, dim3(32, 8), 0, st>>>(h, v_out, L.v_pad, T, ht_hi, ht_lo, hr_hi, hr_lo);
+    k_bw_transpose_h<<<grid, dim3(32, 8), 0, st>>>(h, v_out, L.v_pad, T, ht_hi, ht_lo, hr_hi, hr_lo, bias_part);
     GCB_LAUNCH_OK();
-  }
-  // ---- d_bias ----
-  {
-    const int nblocks = 64;
-    const int rows_per_block = (int)ceil_div64(v_out, nblocks);
-    dim3 grid((unsigned)ceil_div64(T, 128), nblocks);
-    k_bw_bias_partial<<<grid, 128, 0, st>>>(h, v_out, T, rows_per_block, bias_part);
-    GCB_LAUNCH_OK();
-    k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, nblocks, T, accumulate, d_bias);
+    k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.v_pad / 32, T, accumulate, d_bias);
     GCB_LAUNCH_OK();
   }
   // ---- dW (neighbour + centre) ----
