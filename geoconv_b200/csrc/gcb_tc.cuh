@@ -22,6 +22,13 @@ size_t tc_wcat_bytes(int R, int A, int F, int T);
 int tc_build_wcat(const float* w_eff, const float* w_self, int T, int R, int A, int F, float* hi, float* lo,
                   cudaStream_t st);
 
+// dSignal through G[v, rotated slot, t] and a dense tcgen05 GEMM (gcb_tc_dx.cu)
+size_t tc_dx_workspace_bytes(int v_src, int R, int A, int T, bool x3);
+int tc_dx_via_g(const float* h, const float* w, const int32_t* rot_sel, const int32_t* csr_row_ptr,
+                const int32_t* csr_entries, const float* wcat_hi, const float* wcat_lo, int v_out, int v_src,
+                int R, int A, int F, int T, bool x3, int accumulate, float* d_x, void* workspace,
+                size_t workspace_bytes, cudaStream_t st);
+
 // tensor-core backward (gcb_tc_bwd.cu)
 bool tc_bwd_supported(int R, int A, int F, int T);
 size_t tc_bwd_workspace_bytes(int v_out, int v_src, int R, int A, int F, int T, int precision);

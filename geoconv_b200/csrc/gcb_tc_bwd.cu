@@ -499,7 +499,7 @@ struct BwLayout {
   int v_pad, v_pad32, kcat, kcat_pad, vsplit, n_chunks, n_t;
 };
 
-static BwLayout bw_layout(int v_out, int R, int A, int F, int T, bool x3) {
+static BwLayout bw_layout(int v_out, int v_src, int R, int A, int F, int T, bool x3) {
   BwLayout L{};
   L.v_pad = (int)ceil_div64(v_out, 128) * 128;
   L.v_pad32 = L.v_pad;  // multiple of 128 is a multiple of 32
@@ -527,14 +527,13 @@ static BwLayout bw_layout(int v_out, int R, int A, int F, int T, bool x3) {
   L.hrow = align_up((size_t)np * L.v_pad * T * sizeof(float), 256);
   L.partial = align_up((size_t)L.vsplit * T * L.kcat_pad * sizeof(float), 256);
   L.bias_part = align_up((size_t)(L.v_pad / 32) * T * sizeof(float), 256);
-  L.d_full = align_up((size_t)v_out * R * A * F * sizeof(float), 256);
+  L.d_full = tc_dx_workspace_bytes(v_src, R, A, T, x3);   // the G operand of the dSignal GEMM
   L.total = L.recs + L.wcat + L.ht + L.hrow + L.partial + L.bias_part + L.d_full + 1024;
   return L;
 }
 
 size_t tc_bwd_workspace_bytes(int v_out, int v_src, int R, int A, int F, int T, int precision) {
-  (void)v_src;
-  return bw_layout(v_out, R, A, F, T, precision == GCB_PREC_TF32X3).total;
+  return bw_layout(v_out, v_src, R, A, F, T, precision == GCB_PREC_TF32X3).total;
 }
 
 template <bool X3>
@@ -566,10 +565,10 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
                 cudaStream_t st) {
   const bool x3 = precision == GCB_PREC_TF32X3;
   const int np = x3 ? 2 : 1;
-  BwLayout L = bw_layout(v_out, R, A, F, T, x3);
+  BwLayout L = bw_layout(v_out, v_src, R, A, F, T, x3);
   GCB_REQUIRE(workspace_bytes >= L.total, GCB_EWORKSPACE, "tc_conv_bwd: workspace too small");
   GCB_REQUIRE((uintptr_t)x % 16 == 0, GCB_EINVAL, "tc_conv_bwd: x must be 16-byte aligned");
-  const int RA = R * A, KRA = RA * F;
+  const int KRA = R * A * F;
   char* ws = (char*)align_up((size_t)workspace, 256);
   uint4* recs = (uint4*)ws; ws += L.recs;
   float* wc_hi = (float*)ws;
@@ -625,38 +624,11 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     GCB_LAUNCH_OK();
   }
   if (!d_x) return GCB_OK;
-  // ---- unrotated dI = h x Weff, then the CSR gather-reduce ----
-  {
-    rc = tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);
-    if (rc) return rc;
-    CUtensorMap hh, hl, wh, wl;
-    rc = tc_make_tmap_2d(&hh, hr_hi, (uint64_t)T, (uint64_t)L.v_pad, (uint64_t)T * 4, 32, 128);
-    if (rc) return rc;
-    rc = tc_make_tmap_2d(&hl, x3 ? hr_lo : hr_hi, (uint64_t)T, (uint64_t)L.v_pad, (uint64_t)T * 4, 32, 128);
-    if (rc) return rc;
-    rc = tc_make_tmap_2d(&wh, wc_hi, (uint64_t)L.kcat, (uint64_t)T, (uint64_t)L.kcat * 4, 32, 32, true);
-    if (rc) return rc;
-    rc = tc_make_tmap_2d(&wl, x3 ? wc_lo : wc_hi, (uint64_t)L.kcat, (uint64_t)T, (uint64_t)L.kcat * 4, 32, 32, true);
-    if (rc) return rc;
-    TcDiParams p;
-    p.d_full = d_full; p.v_out = v_out; p.KRA = KRA; p.T = T;
-    p.n_mtiles = L.v_pad / 128;
-    p.n_ntiles = (int)ceil_div64(KRA, DI_BN);
-    const size_t stage_bytes = (size_t)np * (DI_STAGE_A + DI_STAGE_B);
-    int ns = (int)((BW_SMEM_LIMIT - 2048) / stage_bytes);
-    if (ns > 6) ns = 6;
-    p.ns = ns;
-    const size_t smem = 2048 + (size_t)ns * stage_bytes;
-    int n_tiles = p.n_mtiles * p.n_ntiles;
-    int grid = n_tiles < 148 ? n_tiles : 148;
-    rc = x3 ? launch_di<true>(hh, hl, wh, wl, p, grid, smem, st) : launch_di<false>(hh, hl, wh, wl, p, grid, smem, st);
-    if (rc) return rc;
-  }
-  profile_begin(GCB_PROF_BWD_CSR, st);
-  rc = csr_reduce_dx(d_full, w, h, w_self, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T, accumulate,
-                     d_x, st);
-  profile_end(GCB_PROF_BWD_CSR, st);
-  return rc;
+  // ---- dSignal: G (entries regrouped by rotated slot) x weights on tensor cores (gcb_tc_dx.cu) ----
+  rc = tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);
+  if (rc) return rc;
+  return tc_dx_via_g(h, w, rot_sel, csr_row_ptr, csr_entries, wc_hi, wc_lo, v_out, v_src, R, A, F, T, x3, accumulate,
+                     d_x, d_full, L.d_full, st);
 }
 
 }  // namespace gcb

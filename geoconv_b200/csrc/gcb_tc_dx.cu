@@ -1,0 +1,341 @@
+// dSignal on tensor cores without materialising dI.
+//
+//   dX[v,f] = sum_{slots s->v} w[s] * sum_t h[k_s,t] * Weff[t, x_s, (y_s+rot[k_s])%A, f]  +  h[v]·Wself[:,f]
+// is regrouped by the ROTATED slot s' = (x, (y+rot)%A) of every entry:
+//   G[v, s', t] = sum_{entries e of v with rotated slot s'} w_e * h[k_e, t]           (k_bw_build_g)
+//   dX[v, f]    = sum_{s',t} G[v,s',t] * Weff[t,s',f] + sum_t h[v,t] * Wself[t,f]     (k_tc_gemm)
+// G is V x (R*A+1)*T floats (109 MB at the FAUST shape) instead of the 600 MB dI that would have to be
+// written once and re-read three times; the second line is a plain dense GEMM
+// [V x (R*A+1)T] x [(R*A+1)T x F] whose B operand is the weight tensor itself read as MN-major tiles.
+//   k_bw_build_g : one block per source vertex, CSR entry list decoded cooperatively, thread t owns
+//                  column t of the (R*A) x T accumulator in shared memory; sequential over the
+//                  vertex's entries (fixed order, no atomics); writes tf32 hi (+ lo) rows of G.
+//   k_tc_gemm    : persistent tcgen05 GEMM, 128 x 128 tiles, TMA-fed (A K-major, B MN-major
+//                  SWIZZLE_128B_BASE32B), two accumulators per tile (even / odd K chunks, summed in
+//                  the epilogue: halves the accumulation chains) and two tiles in flight in TMEM.
+#include <cuda.h>
+
+#include "gcb_common.cuh"
+#include "gcb_ptx.cuh"
+#include "gcb_tc.cuh"
+
+namespace gcb {
+
+constexpr int DX_SMEM_LIMIT = 227 * 1024;
+constexpr int G_CHUNK = 128;
+
+__device__ __forceinline__ uint64_t dx_mnmajor_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;   // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+// ---- G[v, s', t] ----------------------------------------------------------------------------------
+__global__ void k_bw_build_g(const float* __restrict__ h, const float* __restrict__ w,
+                             const int32_t* __restrict__ rot_sel, const int32_t* __restrict__ row_ptr,
+                             const int32_t* __restrict__ entries, int v_out, int v_src, int R, int A, int T,
+                             int kg /* (R*A+1)*T */, float* __restrict__ g_hi, float* __restrict__ g_lo) {
+  extern __shared__ float s_acc[];                       // [RA][T]
+  __shared__ int s_k[G_CHUNK];
+  __shared__ int s_slot[G_CHUNK];
+  __shared__ float s_w[G_CHUNK];
+  const int v = blockIdx.x;
+  const int RA = R * A;
+  const int t = threadIdx.x;
+  float* out_hi = g_hi + (size_t)v * kg;
+  float* out_lo = g_lo ? g_lo + (size_t)v * kg : nullptr;
+  if (v >= v_src) {                                      // padding rows of the GEMM's A operand
+    for (int i = threadIdx.x; i < kg; i += blockDim.x) {
+      out_hi[i] = 0.f;
+      if (out_lo) out_lo[i] = 0.f;
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i < RA * T; i += blockDim.x) s_acc[i] = 0.f;
+  const int beg = row_ptr[v], end = row_ptr[v + 1];
+  for (int base = beg; base < end; base += G_CHUNK) {
+    const int n = min(G_CHUNK, end - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int s = entries[base + i];
+      const int cell = s / 3;
+      const int k = cell / RA;
+      const int slot = cell - k * RA;
+      const int xr = slot / A, ya = slot - xr * A;
+      int yr = ya + rot_sel[k];
+      yr -= (yr >= A) ? A : 0;
+      s_k[i] = k;
+      s_slot[i] = xr * A + yr;
+      s_w[i] = w[s];
+    }
+    __syncthreads();
+    if (t < T) {
+      int i = 0;
+      for (; i + 8 <= n; i += 8) {
+        float hv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) hv[u] = __ldg(h + (size_t)s_k[i + u] * T + t);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float* a = s_acc + s_slot[i + u] * T + t;
+          *a = fmaf(s_w[i + u], hv[u], *a);
+        }
+      }
+      for (; i < n; ++i) {
+        float* a = s_acc + s_slot[i] * T + t;
+        *a = fmaf(s_w[i], __ldg(h + (size_t)s_k[i] * T + t), *a);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < RA * T; i += blockDim.x) {
+    const float val = s_acc[i];
+    const float hi = ptx::to_tf32(val);
+    out_hi[i] = hi;
+    if (out_lo) out_lo[i] = val - hi;
+  }
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {   // centre slab: h[v] itself (zero for halo rows)
+    const float val = v < v_out ? h[(size_t)v * T + i] : 0.f;
+    const float hi = ptx::to_tf32(val);
+    out_hi[RA * T + i] = hi;
+    if (out_lo) out_lo[RA * T + i] = val - hi;
+  }
+}
+
+// ---- persistent TMA-fed tcgen05 GEMM ---------------------------------------------------------------
+constexpr int GM_EPI_WARPS = 4;
+constexpr int GM_THREADS = (2 + GM_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int GM_BN = 128;
+constexpr int GM_STAGE_A = 16 * 1024;   // 128 rows x 32 k
+constexpr int GM_STAGE_B = 16 * 1024;   // 32 k x 128 n (four MN-major column blocks)
+
+struct TcGemmParams {
+  float* out;
+  int ld_out, rows_valid, cols_valid, accumulate;
+  int n_mtiles, n_ntiles, ns;
+  int n_kc;               // K chunks of 32
+  int kc_per_group;       // B tile of chunk kc: rows (kc % kc_per_group)*32, cols (kc / kc_per_group)*group_stride + n0
+  int group_stride;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(GM_THREADS, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
+          const __grid_constant__ CUtensorMap tmap_b_hi, const __grid_constant__ CUtensorMap tmap_b_lo,
+          const TcGemmParams p) {
+  constexpr int NPROD = X3 ? 2 : 1;
+  constexpr int STAGE_BYTES = NPROD * (GM_STAGE_A + GM_STAGE_B);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + (uint32_t)(p.ns * STAGE_BYTES);
+  const uint32_t full = bar_base, empty = full + 8u * p.ns;
+  const uint32_t tm_full = empty + 8u * p.ns, tm_empty = tm_full + 16u;
+  const uint32_t tmem_slot = tm_empty + 16u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.n_mtiles * p.n_ntiles;
+  const bool dual = p.n_kc >= 2;   // even / odd K chunks accumulate separately
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.ns; ++s) {
+      ptx::mbar_init(full + 8u * s, 1);
+      ptx::mbar_init(empty + 8u * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(tm_full + 8u * b, 1);
+      ptx::mbar_init(tm_empty + 8u * b, GM_EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+    ptx::prefetch_tensormap(&tmap_a_hi);
+    ptx::prefetch_tensormap(&tmap_b_hi);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 4 * GM_BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t par = 1u;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
+        int grp = 0, in_grp = 0;
+        for (int kc = 0; kc < p.n_kc; ++kc) {
+          ptx::mbar_wait(empty + 8u * stage, par);
+          const uint32_t a_dst = smem_base + (uint32_t)(stage * STAGE_BYTES);
+          const uint32_t b_dst = a_dst + NPROD * GM_STAGE_A;
+          const int b_row = in_grp * 32, b_col = grp * p.group_stride + nt * GM_BN;
+          ptx::mbar_arrive_expect_tx(full + 8u * stage, (uint32_t)STAGE_BYTES);
+          ptx::tma_load_2d(a_dst, &tmap_a_hi, full + 8u * stage, kc * 32, mt * 128);
+          if (X3) ptx::tma_load_2d(a_dst + GM_STAGE_A, &tmap_a_lo, full + 8u * stage, kc * 32, mt * 128);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ptx::tma_load_2d(b_dst + j * 4096, &tmap_b_hi, full + 8u * stage, b_col + 32 * j, b_row);
+            if (X3) ptx::tma_load_2d(b_dst + GM_STAGE_B + j * 4096, &tmap_b_lo, full + 8u * stage, b_col + 32 * j, b_row);
+          }
+          if (++in_grp == p.kc_per_group) { in_grp = 0; ++grp; }
+          if (++stage == p.ns) { stage = 0; par ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_tf32(128, GM_BN) | (1u << 16);   // B MN-major
+      int stage = 0;
+      uint32_t par = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        ptx::mbar_wait(tm_empty + 8u * buf, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        uint32_t accum[2] = {0u, 0u};
+        for (int kc = 0; kc < p.n_kc; ++kc) {
+          const int half = dual ? (kc & 1) : 0;
+          const uint32_t d = tmem_base + (uint32_t)((buf * 2 + half) * GM_BN);
+          ptx::mbar_wait(full + 8u * stage, par);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = smem_base + (uint32_t)(stage * STAGE_BYTES);
+          const uint32_t b_hi = a_hi + NPROD * GM_STAGE_A;
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint64_t da = ptx::make_kmajor_desc<128>(a_hi + kb * 32);
+            const uint64_t db = dx_mnmajor_desc(b_hi + kb * 1024, 4096, 512);
+            ptx::umma_tf32(d, da, db, idesc, accum[half]);
+            accum[half] = 1u;
+            if (X3) {
+              ptx::umma_tf32(d, da, dx_mnmajor_desc(b_hi + GM_STAGE_B + kb * 1024, 4096, 512), idesc, 1u);
+              ptx::umma_tf32(d, ptx::make_kmajor_desc<128>(a_hi + GM_STAGE_A + kb * 32), db, idesc, 1u);
+            }
+          }
+          ptx::umma_commit(empty + 8u * stage);
+          if (++stage == p.ns) { stage = 0; par ^= 1u; }
+        }
+        ptx::umma_commit(tm_full + 8u * buf);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
+      const int buf = it & 1;
+      ptx::mbar_wait(tm_full + 8u * buf, ((uint32_t)(it >> 1)) & 1u);
+      ptx::tc_fence_after();
+      const int row = mt * 128 + 32 * q + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 2 * GM_BN);
+      float* out = p.out + (size_t)row * p.ld_out + nt * GM_BN;
+      for (int c0 = 0; c0 < GM_BN; c0 += 16) {
+        uint32_t r0[16], r1[16];
+        ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r0);
+        if (dual) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(GM_BN + c0), r1);
+        ptx::tmem_ld_wait();
+        if (row < p.rows_valid && nt * GM_BN + c0 < p.cols_valid) {
+#pragma unroll
+          for (int u = 0; u < 16; u += 4) {
+            float4 o;
+            o.x = __uint_as_float(r0[u]); o.y = __uint_as_float(r0[u + 1]);
+            o.z = __uint_as_float(r0[u + 2]); o.w = __uint_as_float(r0[u + 3]);
+            if (dual) {
+              o.x += __uint_as_float(r1[u]); o.y += __uint_as_float(r1[u + 1]);
+              o.z += __uint_as_float(r1[u + 2]); o.w += __uint_as_float(r1[u + 3]);
+            }
+            float4* dst = reinterpret_cast<float4*>(out + c0 + u);
+            if (p.accumulate) {
+              const float4 old = *dst;
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *dst = o;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tm_empty + 8u * buf);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, 4 * GM_BN);
+  }
+}
+
+template <bool X3>
+static int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                       const TcGemmParams& p, int grid, size_t smem, cudaStream_t st) {
+  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  profile_begin(GCB_PROF_BWD_DI, st);
+  k_tc_gemm<X3><<<grid, GM_THREADS, smem, st>>>(ah, al, bh, bl, p);
+  profile_end(GCB_PROF_BWD_DI, st);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+size_t tc_dx_workspace_bytes(int v_src, int R, int A, int T, bool x3) {
+  const size_t v_pad = (size_t)ceil_div64(v_src, 128) * 128;
+  return align_up((x3 ? 2 : 1) * v_pad * (size_t)(R * A + 1) * T * sizeof(float), 256) + 256;
+}
+
+// d_x[v_src, F] (+)= via G and the weight tensor maps over Wcat [T x (R*A*F + F)] (hi / lo)
+int tc_dx_via_g(const float* h, const float* w, const int32_t* rot_sel, const int32_t* csr_row_ptr,
+                const int32_t* csr_entries, const float* wcat_hi, const float* wcat_lo, int v_out, int v_src,
+                int R, int A, int F, int T, bool x3, int accumulate, float* d_x, void* workspace,
+                size_t workspace_bytes, cudaStream_t st) {
+  GCB_REQUIRE(workspace_bytes >= tc_dx_workspace_bytes(v_src, R, A, T, x3), GCB_EWORKSPACE,
+              "tc_dx_via_g: workspace too small");
+  GCB_REQUIRE((uintptr_t)d_x % 16 == 0 && F % 4 == 0, GCB_EINVAL, "tc_dx_via_g: d_x must be 16-byte aligned");
+  const int RA = R * A, KRA = RA * F, kcat = KRA + F;
+  const int kg = (RA + 1) * T;
+  const int v_pad = (int)ceil_div64(v_src, 128) * 128;
+  float* g_hi = (float*)align_up((size_t)workspace, 256);
+  float* g_lo = x3 ? g_hi + (size_t)v_pad * kg : nullptr;
+  {
+    const size_t smem = (size_t)RA * T * sizeof(float);
+    GCB_REQUIRE(smem <= 200 * 1024, GCB_EUNSUPPORTED, "tc_dx_via_g: R*A*T too large for the G accumulator");
+    if (smem > 48 * 1024)
+      GCB_CUDA_OK(cudaFuncSetAttribute(k_bw_build_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int threads = (T + 31) / 32 * 32;
+    if (threads < 64) threads = 64;
+    profile_begin(GCB_PROF_BWD_CSR, st);
+    k_bw_build_g<<<v_pad, threads, smem, st>>>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, kg,
+                                               g_hi, g_lo);
+    profile_end(GCB_PROF_BWD_CSR, st);
+    GCB_LAUNCH_OK();
+  }
+  CUtensorMap ah, al, bh, bl;
+  int rc = tc_make_tmap_2d(&ah, g_hi, (uint64_t)kg, (uint64_t)v_pad, (uint64_t)kg * 4, 32, 128);
+  if (rc) return rc;
+  rc = tc_make_tmap_2d(&al, x3 ? g_lo : g_hi, (uint64_t)kg, (uint64_t)v_pad, (uint64_t)kg * 4, 32, 128);
+  if (rc) return rc;
+  rc = tc_make_tmap_2d(&bh, wcat_hi, (uint64_t)kcat, (uint64_t)T, (uint64_t)kcat * 4, 32, 32, true);
+  if (rc) return rc;
+  rc = tc_make_tmap_2d(&bl, x3 ? wcat_lo : wcat_hi, (uint64_t)kcat, (uint64_t)T, (uint64_t)kcat * 4, 32, 32, true);
+  if (rc) return rc;
+  TcGemmParams p;
+  p.out = d_x; p.ld_out = F; p.rows_valid = v_src; p.cols_valid = F; p.accumulate = accumulate;
+  p.n_mtiles = v_pad / 128;
+  p.n_ntiles = (int)ceil_div64(F, GM_BN);
+  p.n_kc = kg / 32;
+  p.kc_per_group = T / 32;
+  p.group_stride = F;
+  const size_t stage_bytes = (size_t)(x3 ? 2 : 1) * (GM_STAGE_A + GM_STAGE_B);
+  int ns = (int)((DX_SMEM_LIMIT - 2048) / stage_bytes);
+  if (ns > 6) ns = 6;
+  p.ns = ns;
+  const size_t smem = 2048 + (size_t)ns * stage_bytes;
+  const int n_tiles = p.n_mtiles * p.n_ntiles;
+  const int grid = n_tiles < 148 ? n_tiles : 148;
+  return x3 ? launch_gemm<true>(ah, al, bh, bl, p, grid, smem, st) : launch_gemm<false>(ah, al, bh, bl, p, grid, smem, st);
+}
+
+}  // namespace gcb
