@@ -11,8 +11,9 @@
 //                  column t of the (R*A) x T accumulator in shared memory; sequential over the
 //                  vertex's entries (fixed order, no atomics); writes tf32 hi (+ lo) rows of G.
 //   k_tc_gemm    : persistent tcgen05 GEMM, 128 x 128 tiles, TMA-fed (A K-major, B MN-major
-//                  SWIZZLE_128B_BASE32B), two accumulators per tile (even / odd K chunks, summed in
-//                  the epilogue: halves the accumulation chains) and two tiles in flight in TMEM.
+//                  SWIZZLE_128B_BASE32B), four TMEM accumulators per tile fed round-robin by the K
+//                  chunks and summed in fp32 by the epilogue (the tensor core accumulates with
+//                  truncation, so short chains are what keeps the 3xTF32 mode within 1e-5).
 #include <cuda.h>
 
 #include "gcb_common.cuh"
@@ -138,17 +139,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
   const uint32_t tmem_slot = tm_empty + 16u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.n_mtiles * p.n_ntiles;
-  const bool dual = p.n_kc >= 2;   // even / odd K chunks accumulate separately
+  const int nacc = p.n_kc >= 4 ? 4 : 1;   // K chunks round-robin over this many accumulators
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.ns; ++s) {
       ptx::mbar_init(full + 8u * s, 1);
       ptx::mbar_init(empty + 8u * s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(tm_full + 8u * b, 1);
-      ptx::mbar_init(tm_empty + 8u * b, GM_EPI_WARPS);
-    }
+    ptx::mbar_init(tm_full, 1);
+    ptx::mbar_init(tm_empty, GM_EPI_WARPS);
     ptx::fence_mbar_init();
     ptx::prefetch_tensormap(&tmap_a_hi);
     ptx::prefetch_tensormap(&tmap_b_hi);
@@ -194,13 +193,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
       uint32_t par = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        ptx::mbar_wait(tm_empty + 8u * buf, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+        ptx::mbar_wait(tm_empty, (((uint32_t)it) & 1u) ^ 1u);
         ptx::tc_fence_after();
-        uint32_t accum[2] = {0u, 0u};
+        uint32_t started = 0;   // bit a: accumulator a already holds a partial sum
         for (int kc = 0; kc < p.n_kc; ++kc) {
-          const int half = dual ? (kc & 1) : 0;
-          const uint32_t d = tmem_base + (uint32_t)((buf * 2 + half) * GM_BN);
+          const int acc = nacc == 4 ? (kc & 3) : 0;
+          const uint32_t d = tmem_base + (uint32_t)(acc * GM_BN);
           ptx::mbar_wait(full + 8u * stage, par);
           ptx::tc_fence_after();
           const uint32_t a_hi = smem_base + (uint32_t)(stage * STAGE_BYTES);
@@ -209,8 +207,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
           for (int kb = 0; kb < 4; ++kb) {
             const uint64_t da = ptx::make_kmajor_desc<128>(a_hi + kb * 32);
             const uint64_t db = dx_mnmajor_desc(b_hi + kb * 1024, 4096, 512);
-            ptx::umma_tf32(d, da, db, idesc, accum[half]);
-            accum[half] = 1u;
+            ptx::umma_tf32(d, da, db, idesc, (started >> acc) & 1u);
+            started |= 1u << acc;
             if (X3) {
               ptx::umma_tf32(d, da, dx_mnmajor_desc(b_hi + GM_STAGE_B + kb * 1024, 4096, 512), idesc, 1u);
               ptx::umma_tf32(d, ptx::make_kmajor_desc<128>(a_hi + GM_STAGE_A + kb * 32), db, idesc, 1u);
@@ -219,7 +217,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
           ptx::umma_commit(empty + 8u * stage);
           if (++stage == p.ns) { stage = 0; par ^= 1u; }
         }
-        ptx::umma_commit(tm_full + 8u * buf);
+        ptx::umma_commit(tm_full);
       }
     }
   } else {
@@ -227,16 +225,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
-      const int buf = it & 1;
-      ptx::mbar_wait(tm_full + 8u * buf, ((uint32_t)(it >> 1)) & 1u);
+      ptx::mbar_wait(tm_full, ((uint32_t)it) & 1u);
       ptx::tc_fence_after();
       const int row = mt * 128 + 32 * q + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 2 * GM_BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16);
       float* out = p.out + (size_t)row * p.ld_out + nt * GM_BN;
       for (int c0 = 0; c0 < GM_BN; c0 += 16) {
-        uint32_t r0[16], r1[16];
+        uint32_t r0[16], r1[16], r2[16], r3[16];
         ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r0);
-        if (dual) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(GM_BN + c0), r1);
+        if (nacc == 4) {
+          ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(GM_BN + c0), r1);
+          ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(2 * GM_BN + c0), r2);
+          ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(3 * GM_BN + c0), r3);
+        }
         ptx::tmem_ld_wait();
         if (row < p.rows_valid && nt * GM_BN + c0 < p.cols_valid) {
 #pragma unroll
@@ -244,9 +245,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
             float4 o;
             o.x = __uint_as_float(r0[u]); o.y = __uint_as_float(r0[u + 1]);
             o.z = __uint_as_float(r0[u + 2]); o.w = __uint_as_float(r0[u + 3]);
-            if (dual) {
-              o.x += __uint_as_float(r1[u]); o.y += __uint_as_float(r1[u + 1]);
-              o.z += __uint_as_float(r1[u + 2]); o.w += __uint_as_float(r1[u + 3]);
+            if (nacc == 4) {
+              o.x = (o.x + __uint_as_float(r1[u])) + (__uint_as_float(r2[u]) + __uint_as_float(r3[u]));
+              o.y = (o.y + __uint_as_float(r1[u + 1])) + (__uint_as_float(r2[u + 1]) + __uint_as_float(r3[u + 1]));
+              o.z = (o.z + __uint_as_float(r1[u + 2])) + (__uint_as_float(r2[u + 2]) + __uint_as_float(r3[u + 2]));
+              o.w = (o.w + __uint_as_float(r1[u + 3])) + (__uint_as_float(r2[u + 3]) + __uint_as_float(r3[u + 3]));
             }
             float4* dst = reinterpret_cast<float4*>(out + c0 + u);
             if (p.accumulate) {
@@ -259,7 +262,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tm_empty + 8u * buf);
+      if (lane == 0) ptx::mbar_arrive(tm_empty);
     }
   }
   ptx::tc_fence_before();
