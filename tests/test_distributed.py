@@ -1,0 +1,136 @@
+"""Multi-GPU host logic: vertex-row shard plans / halo exchange and the data-parallel gradient
+all-reduce.  CPU tests run two ranks over gloo; the GPU test emulates the ranks one after the
+other on one device (no concurrent spinning ranks on one GPU - B200_PROFILING.md)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import geoconv_oracle as O
+from geoconv_b200 import distributed as D
+from tests.helpers import TOL_FP32, nerr
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_row_ranges_cover():
+    for n, w in ((10, 3), (2_000_000, 8), (5, 8)):
+        r = D.row_ranges(n, w)
+        assert r[0][0] == 0 and r[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_sharded_oracle_equals_unsharded(world):
+    """Index remapping is exact: running the CPU oracle shard by shard on (local ++ halo) rows
+    reproduces the unsharded output rows bit for bit."""
+    v, f, r, a, t = 203, 10, 3, 6, 5
+    wn, ws, b = O.make_weights(t, r, a, f, seed=0)
+    signal = O.make_signal(v, f, kind="randn")
+    bary = O.make_bary(v, r, a, seed=5, fallback_frac=0.05)
+    y_ref = O.conv_forward(signal, bary, wn, ws, b, None, "relu", 1)
+    plans = D.build_shard_plans(bary, world)
+    assert sum(p.n_local for p in plans) == v
+    for p in plans:
+        lo, hi = p.ranges[p.rank]
+        halo_rows = torch.cat(p.recv_rows) if world > 1 else torch.empty(0, dtype=torch.long)
+        full = torch.cat([signal[lo:hi], signal[halo_rows]])
+        idx_local = p.bary_local[..., 0].long()
+        assert idx_local.min() >= 0 and idx_local.max() < full.shape[0]
+        # every remapped index points at the same signal row as before
+        assert torch.equal(full[idx_local.reshape(-1)], signal[bary[lo:hi, ..., 0].long().reshape(-1)])
+        # interpolation + contraction see identical operands => identical output rows
+        interp = O.signal_retrieval(full, p.bary_local)
+        assert torch.equal(interp, O.signal_retrieval(signal, bary)[lo:hi])
+        # send lists mirror receive lists
+        for q in range(world):
+            assert torch.equal(plans[q].send_rows[p.rank] + p.ranges[q][0], p.recv_rows[q])
+    assert y_ref.shape[0] == v
+
+
+def _worker(rank, world, port, v, f):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r, a = 2, 4
+        signal = O.make_signal(v, f, kind="randn")
+        bary = O.make_bary(v, r, a, seed=9)
+        plan = D.build_shard_plans(bary, world)[rank]
+        lo, hi = plan.ranges[rank]
+        local = signal[lo:hi].clone().requires_grad_(True)
+        full = D.halo_exchange(local, plan)
+        halo_rows = torch.cat(plan.recv_rows)
+        assert torch.equal(full.detach(), torch.cat([signal[lo:hi], signal[halo_rows]]))
+        # backward: d/dX of sum_i c_i * full_i where c depends on the GLOBAL row id
+        glob_ids = torch.cat([torch.arange(lo, hi), halo_rows]).double()
+        weight = (1.0 + glob_ids * (rank + 1)).unsqueeze(1).to(full.dtype)
+        (full * weight).sum().backward()
+        # expected: own rows get (1 + id*(rank+1)); plus for every peer q that holds row id as halo: (1 + id*(q+1))
+        expect = (1.0 + torch.arange(lo, hi).double() * (rank + 1))
+        all_plans = D.build_shard_plans(bary, world)
+        for q in range(world):
+            if q != rank:
+                rows = all_plans[q].recv_rows[rank]
+                expect[rows - lo] += 1.0 + rows.double() * (q + 1)
+        assert torch.allclose(local.grad[:, 0].double(), expect, rtol=1e-6)
+        # data-parallel gradient all-reduce
+        p1 = torch.nn.Parameter(torch.zeros(3, 4))
+        p2 = torch.nn.Parameter(torch.zeros(5))
+        p1.grad = torch.full((3, 4), float(rank + 1))
+        p2.grad = torch.arange(5.0) * (rank + 1)
+        D.allreduce_gradients([p1, p2])
+        tot = sum(range(1, world + 1))
+        assert torch.equal(p1.grad, torch.full((3, 4), float(tot)))
+        assert torch.equal(p2.grad, torch.arange(5.0) * tot)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_exchange_and_allreduce_gloo_world2():
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, 57, 6), nprocs=2, join=True)
+
+
+@pytest.mark.gpu
+def test_sharded_layer_matches_unsharded_on_gpu():
+    from geoconv_b200.pytorch.layers.conv_dirac import ConvDirac
+    dev = "cuda:0"
+    v, f, r, a, t = 1500, 64, 3, 8, 32
+    wn, ws, b = O.make_weights(t, r, a, f, seed=0)
+    signal = O.make_signal(v, f, kind="randn")
+    bary = O.make_bary(v, r, a, seed=5)
+    layer = ConvDirac(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.03)
+    layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
+    layer = layer.to(dev)
+    x_full = signal.to(dev).requires_grad_(True)
+    y_full = layer([x_full, bary.to(dev)])
+    g = torch.randn(y_full.shape, generator=torch.Generator().manual_seed(3)).to(dev)
+    (y_full * g).sum().backward()
+    ref_dx = x_full.grad.clone()
+    ref_dw = layer._template_neighbor_weights.grad.clone()
+    layer.zero_grad()
+    world = 3
+    plans = D.build_shard_plans(bary, world)
+    dx = torch.zeros_like(ref_dx)
+    for p in plans:                      # ranks emulated one after the other
+        lo, hi = p.ranges[p.rank]
+        halo_rows = torch.cat(p.recv_rows)
+        full = torch.cat([signal[lo:hi], signal[halo_rows]]).to(dev).requires_grad_(True)
+        y = layer([full, p.bary_local.to(dev)])
+        assert nerr(y, y_full[lo:hi]) < 1e-6
+        (y * g[lo:hi]).sum().backward()
+        dx[lo:hi] += full.grad[: hi - lo]
+        dx[halo_rows.to(dev)] += full.grad[hi - lo:]
+    assert nerr(dx, ref_dx) < TOL_FP32
+    assert nerr(layer._template_neighbor_weights.grad, ref_dw) < TOL_FP32     # accumulated over shards
