@@ -131,6 +131,8 @@ class ConvIntrinsic(ABC, nn.Module):
         """Evaluates the subclass prior once (conv_intrinsic.py:242-244) and classifies it."""
         values = np.asarray(self.define_kernel_values(self._template_vertices.cpu().numpy())).astype(np.float32)
         self.register_buffer("_kernel", torch.tensor(values), persistent=False)
+        self._kernel_host = values          # numpy copy for host-side checks (no device sync per step)
+        self._symmetry_checked = {}
         self._prior_is_zero = bool(self.include_prior and not np.any(values))
         steps = range(0, self._all_rotations, max(int(self.rotation_delta), 1))
         self._prior_is_symmetric = _rotation_symmetric(values, steps) if self.include_prior else True
@@ -147,8 +149,10 @@ class ConvIntrinsic(ABC, nn.Module):
             return self._template_neighbor_weights
         if self._prior_is_zero:
             return None
-        if not _rotation_symmetric(self._kernel.detach().cpu().numpy(),
-                                   [o % self._all_rotations for o in offsets]):
+        steps = tuple(sorted({o % self._all_rotations for o in offsets}))
+        if steps not in self._symmetry_checked:   # host-side check once per rotation set, never per step
+            self._symmetry_checked[steps] = _rotation_symmetric(self._kernel_host, steps)
+        if not self._symmetry_checked[steps]:
             raise NotImplementedError(
                 "geoconv_b200: the prior returned by define_kernel_values is not invariant under the requested "
                 "template rotations (K[r,a,x,y] != K[r,a+s,x,y+s]); only rotation-symmetric priors (every prior "
