@@ -154,7 +154,12 @@ __device__ __forceinline__ void producer_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCER_WARPS * 32) : "memory");
 }
 
-template <int KC, bool X3>
+// CL = 2: the two CTAs of a (1,2,1) cluster work on the SAME 128-vertex tile and K range with
+// different rotation groups.  Each gathers and interpolates only half of the rows and writes them
+// into both CTAs' A stages (st.shared::cluster), so the gather traffic of a tile is paid once, not
+// once per rotation group.  Stage barriers span the pair: a_full collects both CTAs' producers
+// (remote mbarrier arrive), a_empty both CTAs' MMA warps (tcgen05.commit multicast).
+template <int KC, bool X3, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
           const TcFwdParams p) {
@@ -163,7 +168,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   constexpr int A_TILE_BYTES = TC_M * ROW_BYTES;
   constexpr int CPR = KC / 4;                // 16-byte chunks per row
   constexpr int ROWS_PER_PASS = 32 / CPR;
-  constexpr int ITEMS = 32 / ROWS_PER_PASS;  // float4 items per lane per 32-row sub-tile
+  constexpr int WARP_ROWS = 32 / CL;         // tile rows one producer warp fills
+  constexpr int ITEMS = WARP_ROWS / ROWS_PER_PASS;  // float4 items per lane per tile
+  static_assert(ITEMS >= 1, "tile too narrow for this cluster split");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -192,10 +199,16 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   const int ss_begin = (int)(((int64_t)n_ss * sk) / p.ksplit);
   const int ss_end = (int)(((int64_t)n_ss * (sk + 1)) / p.ksplit);
 
+  const uint32_t crank = CL == 2 ? ptx::cluster_ctarank() : 0u;
+  int mma_arrivals = min(g_cnt, TC_MMA_WARPS);
+  if (CL == 2) {
+    const int g_peer = min(p.g, p.n_rot - (grp ^ 1) * p.g);
+    mma_arrivals += min(g_peer, TC_MMA_WARPS);
+  }
   if (warp == TC_PRODUCER_WARPS && lane == 0) {
     for (int s = 0; s < p.ns_a; ++s) {
-      ptx::mbar_init(a_full + 8u * s, 4);
-      ptx::mbar_init(a_empty + 8u * s, (uint32_t)min(g_cnt, TC_MMA_WARPS));
+      ptx::mbar_init(a_full + 8u * s, 4 * CL);
+      ptx::mbar_init(a_empty + 8u * s, (uint32_t)mma_arrivals);
     }
     for (int s = 0; s < p.A; ++s) {
       ptx::mbar_init(b_full + 8u * s, 1);
@@ -212,12 +225,14 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL == 2) ptx::cluster_sync();   // the peer's barriers exist before anyone arrives on them remotely
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   if (warp < TC_PRODUCER_WARPS) {
     // ===================== producers: gather + interpolate -> swizzled A tiles =====================
     const int pg = warp >> 2, wq = warp & 3;
+    const int row_w = (CL == 2 ? 64 * (int)crank : 0) + WARP_ROWS * wq;   // first tile row of this warp
     const int c = lane % CPR;
     const int row_l = lane / CPR;
     const uint4* rec_smem = reinterpret_cast<const uint4*>(smem_gen + (rec_base - smem_base));
@@ -248,7 +263,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         const float* xcol = p.x + fc * KC + c * 4;
         float4 v[ITEMS];
         if (!centre) {
-          const uint4* rec = rec_smem + (size_t)(y * TC_M + 32 * wq + row_l) * 2;
+          const uint4* rec = rec_smem + (size_t)(y * TC_M + row_w + row_l) * 2;
           uint4 ri[ITEMS], rw[ITEMS];
 #pragma unroll
           for (int j = 0; j < ITEMS; ++j) {
@@ -274,30 +289,37 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         } else {
 #pragma unroll
           for (int j = 0; j < ITEMS; ++j) {
-            const int row = m0 + 32 * wq + row_l + j * ROWS_PER_PASS;
+            const int row = m0 + row_w + row_l + j * ROWS_PER_PASS;
             v[j] = row < p.v_out ? __ldg(reinterpret_cast<const float4*>(xcol + (size_t)row * p.F))
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         ptx::mbar_wait(a_empty + 8u * my_stage, my_par);
-        uint8_t* a_hi = smem_gen + (a_base - smem_base) + (size_t)my_stage * NPROD * A_TILE_BYTES;
+        const uint32_t a_stage_addr = a_base + (uint32_t)(my_stage * NPROD * A_TILE_BYTES);
+        uint8_t* a_hi = smem_gen + (a_stage_addr - smem_base);
+        const uint32_t a_peer = CL == 2 ? ptx::mapa(a_stage_addr, crank ^ 1u) : 0u;
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-          const int row = 32 * wq + row_l + j * ROWS_PER_PASS;
+          const int row = row_w + row_l + j * ROWS_PER_PASS;
           const uint32_t off = (uint32_t)row * ROW_BYTES + swz_chunk<KC>(row, c) * 16u;
           float4 h;
           h.x = ptx::to_tf32(v[j].x); h.y = ptx::to_tf32(v[j].y);
           h.z = ptx::to_tf32(v[j].z); h.w = ptx::to_tf32(v[j].w);
           *reinterpret_cast<float4*>(a_hi + off) = h;
+          if (CL == 2) ptx::st_cluster_v4(a_peer + off, h);
           if (X3) {
             float4 l;
             l.x = v[j].x - h.x; l.y = v[j].y - h.y; l.z = v[j].z - h.z; l.w = v[j].w - h.w;
             *reinterpret_cast<float4*>(a_hi + A_TILE_BYTES + off) = l;
+            if (CL == 2) ptx::st_cluster_v4(a_peer + A_TILE_BYTES + off, l);
           }
         }
-        ptx::fence_proxy_async_smem();
+        if (CL == 2) ptx::fence_proxy_async_all(); else ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(a_full + 8u * my_stage);
+        if (lane == 0) {
+          ptx::mbar_arrive(a_full + 8u * my_stage);
+          if (CL == 2) ptx::mbar_arrive_cluster(ptx::mapa(a_full + 8u * my_stage, crank ^ 1u));
+        }
       }
     }
     // ===================== drain: TMEM -> this split's partial sums =====================
@@ -391,7 +413,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
             }
           }
           accum = 1u;
-          ptx::umma_commit(a_empty + 8u * stage);
+          if (CL == 2) ptx::umma_commit_mc(a_empty + 8u * stage, (uint16_t)3); else ptx::umma_commit(a_empty + 8u * stage);
           if (++stage == p.ns_a) { stage = 0; full_par ^= 1u; }
         }
         fills ^= centre ? 1u : all_slots;
@@ -406,6 +428,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     __syncwarp();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+  if (CL == 2) ptx::cluster_sync();   // neither CTA leaves while the peer may still write / arrive here
 }
 
 // ---- kernel 2: split reduction + bias + activation + angular max-pooling -------------------------
@@ -533,16 +556,37 @@ size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, 
          tc_partial_bytes(v_out, n_rot, T, ksplit) + 1024;
 }
 
+template <int KC, bool X3, int CL>
+static int tc_launch_cl(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdParams& p, const TcConfig& cfg,
+                        dim3 grid, cudaStream_t st) {
+  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_conv<KC, X3, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)cfg.smem_bytes));
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = grid;
+  lc.blockDim = dim3(TC_THREADS);
+  lc.dynamicSmemBytes = cfg.smem_bytes;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = CL;
+  attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  profile_begin(GCB_PROF_FWD_CONV, st);
+  cudaError_t e = cudaLaunchKernelEx(&lc, k_tc_conv<KC, X3, CL>, mh, ml, p);
+  profile_end(GCB_PROF_FWD_CONV, st);
+  GCB_CUDA_OK(e);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+// pairs of rotation groups share their gathered tiles through a 2-CTA cluster when the count is even
 template <int KC, bool X3>
 static int tc_launch(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdParams& p, const TcConfig& cfg,
                      dim3 grid, cudaStream_t st) {
-  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_conv<KC, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)cfg.smem_bytes));
-  profile_begin(GCB_PROF_FWD_CONV, st);
-  k_tc_conv<KC, X3><<<grid, TC_THREADS, cfg.smem_bytes, st>>>(mh, ml, p);
-  profile_end(GCB_PROF_FWD_CONV, st);
-  GCB_LAUNCH_OK();
-  return GCB_OK;
+  if (cfg.n_groups % 2 == 0 && KC >= 16) return tc_launch_cl<KC, X3, 2>(mh, ml, p, cfg, grid, st);
+  return tc_launch_cl<KC, X3, 1>(mh, ml, p, cfg, grid, st);
 }
 
 int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
