@@ -168,9 +168,12 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   constexpr int A_TILE_BYTES = TC_M * ROW_BYTES;
   constexpr int CPR = KC / 4;                // 16-byte chunks per row
   constexpr int ROWS_PER_PASS = 32 / CPR;
-  constexpr int WARP_ROWS = 32 / CL;         // tile rows one producer warp fills
+  constexpr int WARP_ROWS = 32;              // tile rows one producer warp fills
   constexpr int ITEMS = WARP_ROWS / ROWS_PER_PASS;  // float4 items per lane per tile
-  static_assert(ITEMS >= 1, "tile too narrow for this cluster split");
+  // producer warps form NGRP groups that take tiles round-robin; a group covers this CTA's share of
+  // the tile rows (128 rows alone, 64 rows in a cluster pair), so CL = 2 keeps 4 tiles in flight
+  constexpr int NGRP = 2 * CL;
+  constexpr int GRP_WARPS = TC_PRODUCER_WARPS / NGRP;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -207,7 +210,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   }
   if (warp == TC_PRODUCER_WARPS && lane == 0) {
     for (int s = 0; s < p.ns_a; ++s) {
-      ptx::mbar_init(a_full + 8u * s, 4 * CL);
+      ptx::mbar_init(a_full + 8u * s, GRP_WARPS * CL);
       ptx::mbar_init(a_empty + 8u * s, (uint32_t)mma_arrivals);
     }
     for (int s = 0; s < p.A; ++s) {
@@ -231,7 +234,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
 
   if (warp < TC_PRODUCER_WARPS) {
     // ===================== producers: gather + interpolate -> swizzled A tiles =====================
-    const int pg = warp >> 2, wq = warp & 3;
+    const int pg = warp / GRP_WARPS, wq = warp % GRP_WARPS;
     const int row_w = (CL == 2 ? 64 * (int)crank : 0) + WARP_ROWS * wq;   // first tile row of this warp
     const int c = lane % CPR;
     const int row_l = lane / CPR;
@@ -259,7 +262,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         const int my_stage = stage;
         const uint32_t my_par = empty_par;
         if (++stage == p.ns_a) { stage = 0; empty_par ^= 1u; }
-        if ((n & 1) != pg) continue;
+        if ((n & (NGRP - 1)) != pg) continue;
         const float* xcol = p.x + fc * KC + c * 4;
         float4 v[ITEMS];
         if (!centre) {
@@ -306,29 +309,37 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
           h.x = ptx::to_tf32(v[j].x); h.y = ptx::to_tf32(v[j].y);
           h.z = ptx::to_tf32(v[j].z); h.w = ptx::to_tf32(v[j].w);
           *reinterpret_cast<float4*>(a_hi + off) = h;
-          if (CL == 2) ptx::st_cluster_v4(a_peer + off, h);
           if (X3) {
             float4 l;
             l.x = v[j].x - h.x; l.y = v[j].y - h.y; l.z = v[j].z - h.z; l.w = v[j].w - h.w;
             *reinterpret_cast<float4*>(a_hi + A_TILE_BYTES + off) = l;
-            if (CL == 2) ptx::st_cluster_v4(a_peer + A_TILE_BYTES + off, l);
           }
         }
-        if (CL == 2) ptx::fence_proxy_async_all(); else ptx::fence_proxy_async_smem();
+        ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           ptx::mbar_arrive(a_full + 8u * my_stage);
-          if (CL == 2) ptx::mbar_arrive_cluster(ptx::mapa(a_full + 8u * my_stage, crank ^ 1u));
+          if (CL == 2) {
+            // hand this warp's 32-row slab (hi, then lo) to the peer CTA with the bulk-copy engine;
+            // the copy completes on the peer's a_full barrier, which also gets this warp's arrival
+            const uint32_t slab = (uint32_t)row_w * ROW_BYTES, slab_bytes = WARP_ROWS * ROW_BYTES;
+            const uint32_t bar_peer = ptx::mapa(a_full + 8u * my_stage, crank ^ 1u);
+            ptx::mbar_arrive_expect_tx_cluster(bar_peer, NPROD * slab_bytes);
+            ptx::bulk_copy_to_peer(a_peer + slab, a_stage_addr + slab, slab_bytes, bar_peer);
+            if (X3) ptx::bulk_copy_to_peer(a_peer + A_TILE_BYTES + slab, a_stage_addr + A_TILE_BYTES + slab,
+                                           slab_bytes, bar_peer);
+          }
         }
       }
     }
     // ===================== drain: TMEM -> this split's partial sums =====================
     ptx::mbar_wait(acc_full, 0);
     ptx::tc_fence_after();
-    const int row = m0 + 32 * wq + lane;  // < v_pad: the partial buffer is padded
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * wq) << 16);
+    const int dq = warp & 3, dh = warp >> 2;   // TMEM lane quadrant of this warp, and which half of the rotations
+    const int row = m0 + 32 * dq + lane;       // < v_pad: the partial buffer is padded
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * dq) << 16);
     float* prow = p.partial + (((size_t)sk * p.v_pad + row) * p.n_rot + rot0) * p.T + t0;
-    for (int il = pg; il < g_cnt; il += 2) {
+    for (int il = dh; il < g_cnt; il += 2) {
       for (int c0 = 0; c0 < p.n_t; c0 += 16) {
         uint32_t r[16];
         ptx::tmem_ld_32x32b_x16(lane_addr + (uint32_t)(il * p.n_t + c0), r);
