@@ -203,11 +203,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   const int ss_end = (int)(((int64_t)n_ss * (sk + 1)) / p.ksplit);
 
   const uint32_t crank = CL == 2 ? ptx::cluster_ctarank() : 0u;
-  const int mma_own = (g_cnt + 1) / 2;   // one MMA warp per rotation pair
-  int mma_arrivals = mma_own;
+  int mma_arrivals = min(g_cnt, TC_MMA_WARPS);
   if (CL == 2) {
     const int g_peer = min(p.g, p.n_rot - (grp ^ 1) * p.g);
-    mma_arrivals += (g_peer + 1) / 2;
+    mma_arrivals += min(g_peer, TC_MMA_WARPS);
   }
   if (warp == TC_PRODUCER_WARPS && lane == 0) {
     for (int s = 0; s < p.ns_a; ++s) {
@@ -218,7 +217,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       ptx::mbar_init(b_full + 8u * s, 1);
       ptx::mbar_init(b_empty + 8u * s, (uint32_t)g_cnt);
     }
-    ptx::mbar_init(acc_full, (uint32_t)mma_own);
+    ptx::mbar_init(acc_full, (uint32_t)min(g_cnt, TC_MMA_WARPS));
     ptx::fence_mbar_init();
     ptx::prefetch_tensormap(&tmap_hi);
     if (X3) ptx::prefetch_tensormap(&tmap_lo);
@@ -362,56 +361,38 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         for (int yb = 0; yb < n_y; ++yb) {
           ptx::mbar_wait(b_empty + 8u * yb, ((loads >> yb) & 1u) ^ 1u);
           const int col = (centre ? RA * p.F : (xr * p.A + yb) * p.F) + fc * KC;
-          const uint32_t dst = b_base + (uint32_t)(yb * b_tile_bytes);   // hi tiles of all slots, then lo tiles
+          const uint32_t dst = b_base + (uint32_t)(yb * NPROD * b_tile_bytes);
           ptx::mbar_arrive_expect_tx(b_full + 8u * yb, (uint32_t)(NPROD * b_tile_bytes));
           ptx::tma_load_2d(dst, &tmap_hi, b_full + 8u * yb, col, t0);
-          if (X3) ptx::tma_load_2d(dst + p.A * b_tile_bytes, &tmap_lo, b_full + 8u * yb, col, t0);
+          if (X3) ptx::tma_load_2d(dst + b_tile_bytes, &tmap_lo, b_full + 8u * yb, col, t0);
           loads ^= 1u << yb;
         }
       }
     }
   } else {
     // ===================== MMA issuers =====================
-    // tcgen05.mma is issued by one thread, and that thread's integer bookkeeping (~25 instructions
-    // per MMA) would outlast short MMAs.  Rotations accumulate into disjoint TMEM columns, so they
-    // are independent: MMA warp mw owns the rotation PAIR (2mw, 2mw+1) and the issue work runs up to
-    // TC_MMA_WARPS wide.  When the pair's two weight tiles sit in adjacent B slots (consecutive
-    // rotation offsets, no wrap-around at this angular position) both rotations are issued as ONE
-    // MMA of N = 2*n_t: the A tile is read from shared memory once per 2*n_t columns, which keeps
-    // the operand traffic (A 4 KB + B 2*n_t*32 B per MMA) under the 128 B/cycle the SM can feed.
-    // Every owner commits to the stage / slot barriers itself (a_empty counts active MMA warps,
-    // b_empty counts rotations).
+    // tcgen05.mma is issued by one thread, and at N = n_t <= 256 that thread's integer bookkeeping
+    // (~25 instructions per MMA) would outlast the 48-cycle MMAs.  Rotations accumulate into
+    // disjoint TMEM columns, so they are independent: MMA warp mw owns rotations mw, mw+4, ...
+    // and the issue work runs TC_MMA_WARPS-wide.  Every owner commits to the stage / slot barriers
+    // itself (a_empty counts active MMA warps, b_empty counts rotations).
     const int mw = warp - (TC_PRODUCER_WARPS + 1);
-    if (lane == 0 && 2 * mw < g_cnt) {
-      const bool has2 = 2 * mw + 1 < g_cnt;
-      const bool can_merge = has2 && 2 * p.n_t <= 256;
-      const uint32_t idesc1 = ptx::make_idesc_tf32(TC_M, p.n_t);
-      const uint32_t idesc2 = ptx::make_idesc_tf32(TC_M, 2 * p.n_t);
+    if (lane == 0 && mw < g_cnt) {
+      const uint32_t idesc = ptx::make_idesc_tf32(TC_M, p.n_t);
       const uint64_t desc_hi = ptx::make_kmajor_desc<ROW_BYTES>(0) & 0xFFFFFFFF00000000ull;
       const uint32_t lo_flags = (uint32_t)(ptx::make_kmajor_desc<ROW_BYTES>(0) & 0xFFFF0000ull);
-      const uint32_t b_slot_lo = (uint32_t)b_tile_bytes >> 4;
-      const uint32_t b_lo_part = (uint32_t)(p.A * b_tile_bytes) >> 4;   // hi tiles of all slots, then lo tiles
+      const uint32_t b_slot_lo = (uint32_t)(NPROD * b_tile_bytes) >> 4;
+      const uint32_t b_lo_half = (uint32_t)b_tile_bytes >> 4;
       const uint32_t b_lo0 = (b_base >> 4) | lo_flags;
-      int yb0 = p.rot.off[rot0 + 2 * mw];                      // rolling B slots of the two rotations
-      int yb1 = has2 ? p.rot.off[rot0 + 2 * mw + 1] : 0;
-      const uint32_t d0 = tmem_base + (uint32_t)(2 * mw * p.n_t);
+      constexpr int OWN = TC_G_MAX / TC_MMA_WARPS;
+      int yb[OWN];  // rolling B slot of each owned rotation
+#pragma unroll
+      for (int q = 0; q < OWN; ++q) yb[q] = (mw + q * TC_MMA_WARPS) < g_cnt ? p.rot.off[rot0 + mw + q * TC_MMA_WARPS] : 0;
       const uint32_t all_slots = p.A >= 32 ? 0xFFFFFFFFu : ((1u << p.A) - 1u);
       uint32_t fills = 0;     // bit s = parity of completed fills of B slot s
       uint32_t accum = 0;     // 0 only for the very first k-step of this CTA
       int stage = 0;          // rolling n % ns_a
       uint32_t full_par = 0;  // (n / ns_a) & 1
-      auto issue = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
-#pragma unroll
-        for (int j = 0; j < KC / 8; ++j) {
-          const uint64_t da = desc_hi | (uint64_t)(a_lo + 2u * j);
-          const uint64_t db = desc_hi | (uint64_t)(b_lo + 2u * j);
-          ptx::umma_tf32(d, da, db, idesc, j == 0 ? accum : 1u);
-          if (X3) {
-            ptx::umma_tf32(d, da, desc_hi | (uint64_t)(b_lo + b_lo_part + 2u * j), idesc, 1u);
-            ptx::umma_tf32(d, desc_hi | (uint64_t)(a_lo + (A_TILE_BYTES >> 4) + 2u * j), db, idesc, 1u);
-          }
-        }
-      };
       for (int ss = ss_begin; ss < ss_end; ++ss) {
         const bool centre = ss >= p.R * p.nfc;
         const int n_y = centre ? 1 : p.A;
@@ -419,21 +400,28 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
           ptx::mbar_wait(a_full + 8u * stage, full_par);
           ptx::tc_fence_after();
           const uint32_t a_lo = ((a_base + (uint32_t)(stage * NPROD * A_TILE_BYTES)) >> 4) | lo_flags;
-          const int s0 = centre ? 0 : yb0, s1 = centre ? 0 : yb1;
-          ptx::mbar_wait(b_full + 8u * s0, (fills >> s0) & 1u);
-          if (has2) ptx::mbar_wait(b_full + 8u * s1, (fills >> s1) & 1u);
-          ptx::tc_fence_after();
-          if (can_merge && s1 == s0 + 1) {
-            issue(d0, a_lo, b_lo0 + (uint32_t)s0 * b_slot_lo, idesc2);
-          } else {
-            issue(d0, a_lo, b_lo0 + (uint32_t)s0 * b_slot_lo, idesc1);
-            if (has2) issue(d0 + (uint32_t)p.n_t, a_lo, b_lo0 + (uint32_t)s1 * b_slot_lo, idesc1);
-          }
-          ptx::umma_commit(b_empty + 8u * s0);
-          if (has2) ptx::umma_commit(b_empty + 8u * s1);
-          if (!centre) {
-            yb0 = (yb0 + 1 == p.A) ? 0 : yb0 + 1;
-            yb1 = (yb1 + 1 == p.A) ? 0 : yb1 + 1;
+#pragma unroll
+          for (int q = 0; q < OWN; ++q) {
+            const int il = mw + q * TC_MMA_WARPS;
+            if (il < g_cnt) {
+              const int s = centre ? 0 : yb[q];
+              ptx::mbar_wait(b_full + 8u * s, (fills >> s) & 1u);
+              ptx::tc_fence_after();
+              const uint32_t b_lo = b_lo0 + (uint32_t)s * b_slot_lo;
+              const uint32_t d = tmem_base + (uint32_t)(il * p.n_t);
+#pragma unroll
+              for (int j = 0; j < KC / 8; ++j) {
+                const uint64_t da = desc_hi | (uint64_t)(a_lo + 2u * j);
+                const uint64_t db = desc_hi | (uint64_t)(b_lo + 2u * j);
+                ptx::umma_tf32(d, da, db, idesc, j == 0 ? accum : 1u);
+                if (X3) {
+                  ptx::umma_tf32(d, da, desc_hi | (uint64_t)(b_lo + b_lo_half + 2u * j), idesc, 1u);
+                  ptx::umma_tf32(d, desc_hi | (uint64_t)(a_lo + (A_TILE_BYTES >> 4) + 2u * j), db, idesc, 1u);
+                }
+              }
+              ptx::umma_commit(b_empty + 8u * s);
+              if (!centre) yb[q] = (yb[q] + 1 == p.A) ? 0 : yb[q] + 1;
+            }
           }
           accum = 1u;
           if (CL == 2) ptx::umma_commit_mc(a_empty + 8u * stage, (uint16_t)3); else ptx::umma_commit(a_empty + 8u * stage);
