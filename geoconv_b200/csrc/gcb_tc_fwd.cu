@@ -24,6 +24,7 @@
 // TF32X3 (fp32-faithful): operands are split v = hi + lo (both tf32) and D += Ahi*Bhi + Ahi*Blo +
 // Alo*Bhi - three MMAs per k-step, relative error ~2^-21 per product.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gcb_common.cuh"
 #include "gcb_ptx.cuh"
@@ -596,7 +597,11 @@ static int tc_launch_cl(const CUtensorMap& mh, const CUtensorMap& ml, const TcFw
 template <int KC, bool X3>
 static int tc_launch(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdParams& p, const TcConfig& cfg,
                      dim3 grid, cudaStream_t st) {
-  if (cfg.n_groups % 2 == 0 && KC >= 16) return tc_launch_cl<KC, X3, 2>(mh, ml, p, cfg, grid, st);
+  // Measured on B200 at the FAUST shape (profiles/r01_notes.md): sharing halves the L1/L2 gather load
+  // but the kernels are bound on the MMA side (operand reads from shared memory), so the pair mode
+  // is not faster (TF32 0.536 vs 0.532 ms, 3xTF32 1.14 vs 1.08 ms).  It is kept behind a switch.
+  static const bool use_pairs = getenv("GCB_TC_CLUSTER") && atoi(getenv("GCB_TC_CLUSTER")) != 0;
+  if (use_pairs && cfg.n_groups % 2 == 0 && KC >= 16) return tc_launch_cl<KC, X3, 2>(mh, ml, p, cfg, grid, st);
   return tc_launch_cl<KC, X3, 1>(mh, ml, p, cfg, grid, st);
 }
 
