@@ -40,7 +40,7 @@ constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_BAR_BYTES = 1024;
 constexpr int TC_G_MAX = 8;              // rotations per CTA (accumulator groups) upper bound
 constexpr int TC_REC_BYTES = TC_M * 32;  // one (x,y) slot of packed records for a 128-vertex tile
-constexpr int TC_X3_CHAIN_K = 2048;      // TF32X3: contraction length per accumulator chain
+constexpr int TC_X3_CHAIN_K = 3072;      // TF32X3: contraction length per accumulator chain
 
 struct TcFwdParams {
   const float* x;       // [v_src, F]
