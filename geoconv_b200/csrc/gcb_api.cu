@@ -108,7 +108,8 @@ extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, 
                             const float* w_self, const float* bias, const int32_t* rot_off_host,
                             int32_t n_rot, int32_t v_out, int32_t v_src, int32_t R, int32_t A,
                             int32_t F, int32_t T, int act, int precision, float* y, float* z,
-                            int32_t* argmax, void* workspace, size_t workspace_bytes, void* stream) {
+                            int32_t* argmax, float* interp_out, void* workspace, size_t workspace_bytes,
+                            void* stream) {
   GCB_REQUIRE(x && idx && w && w_self && bias, GCB_EINVAL, "gcb_conv_fwd: null input pointer");
   GCB_REQUIRE(y || z, GCB_EINVAL, "gcb_conv_fwd: need y and/or z");
   GCB_REQUIRE((z == nullptr) == (argmax == nullptr), GCB_EINVAL, "gcb_conv_fwd: z and argmax go together");
@@ -134,7 +135,7 @@ extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, 
                 "gcb_conv_fwd: tcgen05 path does not support R=%d A=%d F=%d T=%d n_rot=%d", R, A, F, T, n_rot);
     // the tensor-core path pools in its own finishing kernel
     return tc_conv_fwd(x, idx, w, w_eff, w_self, bias, rot, n_rot, v_out, v_src, R, A, F, T, act, precision,
-                       y_out, z, argmax, ws, workspace_bytes, st);
+                       y_out, z, argmax, interp_out, ws, workspace_bytes, st);
   } else {
     GCB_REQUIRE(false, GCB_EINVAL, "gcb_conv_fwd: unknown precision %d", precision);
   }
@@ -158,8 +159,8 @@ extern "C" int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, 
                             const float* w_self, const float* h, const int32_t* rot_sel,
                             const int32_t* csr_row_ptr, const int32_t* csr_entries, int32_t v_out,
                             int32_t v_src, int32_t R, int32_t A, int32_t F, int32_t T, int precision,
-                            int accumulate, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias,
-                            void* workspace, size_t workspace_bytes, void* stream) {
+                            int accumulate, const float* interp, float* d_x, float* d_w_eff, float* d_w_self,
+                            float* d_bias, void* workspace, size_t workspace_bytes, void* stream) {
   GCB_REQUIRE(x && idx && w && w_self && h && rot_sel, GCB_EINVAL, "gcb_conv_bwd: null input pointer");
   GCB_REQUIRE(!d_x || !w_eff || (csr_row_ptr && csr_entries), GCB_EINVAL, "gcb_conv_bwd: d_x needs the CSR");
   GCB_REQUIRE(d_w_eff && d_w_self && d_bias, GCB_EINVAL, "gcb_conv_bwd: null output pointer");
@@ -174,7 +175,7 @@ extern "C" int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, 
   ws += align_up((size_t)v_out * R * A * F * sizeof(float), 256);
   if (precision != GCB_PREC_FP32 && w_eff && tc_bwd_supported(R, A, F, T))
     return tc_conv_bwd(x, idx, w, w_eff, w_self, h, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T,
-                       precision, accumulate, d_x, d_w_eff, d_w_self, d_bias, workspace, workspace_bytes, st);
+                       precision, accumulate, interp, d_x, d_w_eff, d_w_self, d_bias, workspace, workspace_bytes, st);
   rc = ffma_conv_bwd(x, idx, w, w_eff, h, rot_sel, v_out, v_src, R, A, F, T, accumulate, d_w_eff, d_w_self,
                      d_bias, d_x ? d_full : nullptr, ws, st);
   if (rc || !d_x) return rc;

@@ -98,7 +98,8 @@ size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, 
 int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                 const float* w_self, const float* bias, const RotTable& rot, int n_rot, int v_out,
                 int v_src, int R, int A, int F, int T, int act, int precision, float* y,
-                float* z /* nullable: fused AngularMaxPooling */, int32_t* argmax, void* workspace,
+                float* z /* nullable: fused AngularMaxPooling */, int32_t* argmax,
+                float* interp_out /* nullable: keep I[v_out,R,A,F] for the backward */, void* workspace,
                 size_t workspace_bytes, cudaStream_t st);
 
 // shared small kernels (gcb_pool.cu)

@@ -34,8 +34,8 @@ bool tc_bwd_supported(int R, int A, int F, int T);
 size_t tc_bwd_workspace_bytes(int v_out, int v_src, int R, int A, int F, int T, int precision);
 int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
                 const float* h, const int32_t* rot_sel, const int32_t* csr_row_ptr, const int32_t* csr_entries,
-                int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate, float* d_x,
-                float* d_w_eff, float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes,
-                cudaStream_t st);
+                int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,
+                const float* interp /* nullable: I saved by the forward */, float* d_x, float* d_w_eff,
+                float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 }  // namespace gcb

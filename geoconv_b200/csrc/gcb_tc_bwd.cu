@@ -87,6 +87,7 @@ struct TcDwParams {
   const float* x;
   const uint4* recs;        // [R*A][v_pad][2]
   const int32_t* rot_sel;   // [v_out]
+  const float* interp;      // optional [v_out][R*A*F] saved by the forward: read instead of re-gathering
   float* partial;           // [vsplit][T][kcat_pad]
   int v_out, v_pad, R, A, F, T, kcat, kcat_pad, n_t, vsplit, n_chunks, ns, tmem_cols;
 };
@@ -164,7 +165,15 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUt
       const int rot = rot_s[n * DW_VC + vrow];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (valid_j[j] && slot_j[j] < RA) {
+        if (valid_j[j] && slot_j[j] < RA && p.interp) {
+          // saved interpolation: one row segment of I[k, x, (y'-rot)%A, :] replaces three gathers
+          const int xr = slot_j[j] / p.A;
+          int ys = slot_j[j] - xr * p.A - rot;
+          ys += ys < 0 ? p.A : 0;
+          ri[j] = make_uint4((uint32_t)(xr * p.A + ys), 0u, 0u, 0u);
+          rw[j] = make_uint4(__float_as_uint(k < p.v_out ? 1.f : 0.f), 0u, 0u, 0u);
+          if (k >= p.v_out) ri[j].x = 0u;
+        } else if (valid_j[j] && slot_j[j] < RA) {
           if (j > 0 && slot_j[j] == slot_j[j - 1]) {
             ri[j] = ri[j - 1];
             rw[j] = rw[j - 1];
@@ -190,13 +199,21 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUt
     for (int n = 0; n < n_local; ++n) {
       float4 x0[4], x1[4], x2[4];
       float w0[4], w1[4], w2[4];
+      const int kcur = (chunk_begin + n) * DW_VC + vrow;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float* xcol = p.x + f0_j[j] + c8 * 4;
-        x0[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].x * p.F));
-        x1[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].y * p.F));
-        x2[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].z * p.F));
         w0[j] = __uint_as_float(rw[j].x); w1[j] = __uint_as_float(rw[j].y); w2[j] = __uint_as_float(rw[j].z);
+        if (p.interp && valid_j[j] && slot_j[j] < RA) {
+          const size_t krow = (size_t)(kcur < p.v_out ? kcur : 0) * RA + ri[j].x;
+          x0[j] = __ldg(reinterpret_cast<const float4*>(p.interp + krow * p.F + f0_j[j] + c8 * 4));
+          x1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          x2[j] = x1[j];
+        } else {
+          x0[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].x * p.F));
+          x1[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].y * p.F));
+          x2[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].z * p.F));
+        }
       }
       if (n + 1 < n_local) load_recs(n + 1);   // records of the next stage fly while X arrives
       float4 v[4];
@@ -560,9 +577,9 @@ static int launch_di(const CUtensorMap& hh, const CUtensorMap& hl, const CUtenso
 
 int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
                 const float* h, const int32_t* rot_sel, const int32_t* csr_row_ptr, const int32_t* csr_entries,
-                int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate, float* d_x,
-                float* d_w_eff, float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes,
-                cudaStream_t st) {
+                int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,
+                const float* interp, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias, void* workspace,
+                size_t workspace_bytes, cudaStream_t st) {
   const bool x3 = precision == GCB_PREC_TF32X3;
   const int np = x3 ? 2 : 1;
   BwLayout L = bw_layout(v_out, v_src, R, A, F, T, x3);
@@ -602,7 +619,7 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
                          (uint32_t)L.n_t);
     if (rc) return rc;
     TcDwParams p;
-    p.x = x; p.recs = recs; p.rot_sel = rot_sel; p.partial = partial;
+    p.x = x; p.recs = recs; p.rot_sel = rot_sel; p.partial = partial; p.interp = interp;
     p.v_out = v_out; p.v_pad = L.v_pad; p.R = R; p.A = A; p.F = F; p.T = T;
     p.kcat = w_eff ? L.kcat : L.kcat;  // centre-only layers never reach this path
     p.kcat_pad = L.kcat_pad; p.n_t = L.n_t; p.vsplit = L.vsplit; p.n_chunks = L.n_chunks;

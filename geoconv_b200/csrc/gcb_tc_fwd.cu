@@ -46,6 +46,7 @@ struct TcFwdParams {
   const float* x;       // [v_src, F]
   const uint4* recs;    // [R*A, v_pad, 2]: {i0,i1,i2,-} {w0,w1,w2,-}
   float* partial;       // [ksplit, v_pad, n_rot, T] raw accumulators
+  float* interp_out;    // optional [v_out, R*A*F]: the interpolations, kept for the backward's dW
   int v_out, v_pad, R, A, F, T, n_rot;
   int nfc;              // F / KC
   int n_t;              // templates per CTA (MMA N)
@@ -296,6 +297,15 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
             const int row = m0 + row_w + row_l + j * ROWS_PER_PASS;
             v[j] = row < p.v_out ? __ldg(reinterpret_cast<const float4*>(xcol + (size_t)row * p.F))
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (p.interp_out && !centre && tz == 0 && (CL == 2 ? (grp >> 1) == 0 : grp == 0)) {
+          // every (vertex, slot, feature) value is produced exactly once across the K splits: keep it
+          float* irow = p.interp_out + (size_t)(xr * p.A + y) * p.F + fc * KC + c * 4;
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) {
+            const int row = m0 + row_w + row_l + j * ROWS_PER_PASS;
+            if (row < p.v_out) *reinterpret_cast<float4*>(irow + (size_t)row * RA * p.F) = v[j];
           }
         }
         ptx::mbar_wait(a_empty + 8u * my_stage, my_par);
@@ -607,8 +617,8 @@ static int tc_launch(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdPa
 
 int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
                 const float* bias, const RotTable& rot, int n_rot, int v_out, int v_src, int R, int A, int F,
-                int T, int act, int precision, float* y, float* z, int32_t* argmax, void* workspace,
-                size_t workspace_bytes, cudaStream_t st) {
+                int T, int act, int precision, float* y, float* z, int32_t* argmax, float* interp_out,
+                void* workspace, size_t workspace_bytes, cudaStream_t st) {
   (void)v_src;
   const bool x3 = precision == GCB_PREC_TF32X3;
   TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3);
@@ -645,7 +655,7 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   if (rc) return rc;
 
   TcFwdParams p;
-  p.x = x; p.recs = recs; p.partial = partial;
+  p.x = x; p.recs = recs; p.partial = partial; p.interp_out = interp_out;
   p.v_out = v_out; p.v_pad = v_pad; p.R = R; p.A = A; p.F = F; p.T = T; p.n_rot = n_rot;
   p.nfc = F / cfg.kc; p.n_t = cfg.n_t; p.g = cfg.g; p.ns_a = cfg.ns_a; p.tmem_cols = cfg.tmem_cols;
   p.ksplit = ksplit;

@@ -12,6 +12,9 @@ import torch
 
 from . import _native as N
 
+# keep the interpolations of a training forward for its backward (V*R*A*F floats per call)
+SAVE_INTERPOLATIONS = True
+
 PRECISIONS = {"fp32": None, "ffma": N.PREC_FP32, "tf32": N.PREC_TF32, "tf32x3": N.PREC_TF32X3}
 
 
@@ -190,13 +193,20 @@ class ConvIntrinsicFn(torch.autograd.Function):
         z = torch.empty((pack.v_out, t), dtype=torch.float32, device=dev)
         arg = torch.empty((pack.v_out,), dtype=torch.int32, device=dev)
         rot = N.rot_array(rot_offsets)
+        # Training: let the tensor-core forward keep the interpolations I [V,R,A,F] (the reference
+        # materialises the same tensor) so the backward's dW contraction reads them back instead of
+        # gathering three signal rows per template vertex again.
+        keep = (SAVE_INTERPOLATIONS and w_eff_c is not None and precision != N.PREC_FP32
+                and precision_bwd != N.PREC_FP32 and any(ctx.needs_input_grad[:4]))
+        interp = torch.empty((pack.v_out, pack.r * pack.a * f), dtype=torch.float32, device=dev) if keep else None
         ws_bytes = lib.gcb_conv_fwd_workspace_bytes(pack.v_out, v_src, pack.r, pack.a, f, t, n_rot, precision)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             N.check(lib.gcb_conv_fwd(x.data_ptr(), pack.idx.data_ptr(), pack.w.data_ptr(), _ptr(w_eff_c),
                                      w_self_c.data_ptr(), bias_c.data_ptr(), rot, n_rot, pack.v_out, v_src,
                                      pack.r, pack.a, f, t, act_id, precision, y.data_ptr(), z.data_ptr(),
-                                     arg.data_ptr(), ws.data_ptr(), ws_bytes, _stream(x)), "gcb_conv_fwd")
+                                     arg.data_ptr(), _ptr(interp), ws.data_ptr(), ws_bytes, _stream(x)),
+                    "gcb_conv_fwd")
         ctx.pack = pack
         ctx.rot_offsets = tuple(int(o) for o in rot_offsets)
         ctx.act_id = act_id
@@ -206,7 +216,9 @@ class ConvIntrinsicFn(torch.autograd.Function):
         ctx.anchor_shape = None if w_anchor is None else tuple(w_anchor.shape)
         ctx.w_self_shape = tuple(w_self.shape)
         ctx.bias_shape = tuple(bias.shape)
-        ctx.save_for_backward(x, w_eff_c if w_eff_c is not None else x.new_empty(0), w_self_c, y, z, arg)
+        ctx.has_interp = interp is not None
+        ctx.save_for_backward(x, w_eff_c if w_eff_c is not None else x.new_empty(0), w_self_c, y, z, arg,
+                              interp if interp is not None else x.new_empty(0))
         ctx.mark_non_differentiable(arg)
         ctx.set_materialize_grads(False)
         return y, z, arg
@@ -214,7 +226,8 @@ class ConvIntrinsicFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_y, grad_z, _grad_arg):
         lib = N.load()
-        x, w_eff, w_self, y, z, arg = ctx.saved_tensors
+        x, w_eff, w_self, y, z, arg, interp = ctx.saved_tensors
+        interp_ptr = interp.data_ptr() if ctx.has_interp else None
         pack: BaryPack = ctx.pack
         has_nb = ctx.has_neighbor
         v_src, f = x.shape
@@ -241,7 +254,7 @@ class ConvIntrinsicFn(torch.autograd.Function):
             N.check(lib.gcb_conv_bwd(x.data_ptr(), pack.idx.data_ptr(), pack.w.data_ptr(),
                                      w_eff.data_ptr() if has_nb else None, w_self.data_ptr(), h.data_ptr(),
                                      rot_sel.data_ptr(), _ptr(row_ptr), _ptr(entries), pack.v_out, v_src,
-                                     pack.r, pack.a, f, t, ctx.precision, accumulate, _ptr(d_x),
+                                     pack.r, pack.a, f, t, ctx.precision, accumulate, interp_ptr, _ptr(d_x),
                                      d_w_eff.data_ptr(), d_w_self.data_ptr(), d_bias.data_ptr(),
                                      ws.data_ptr(), ws_bytes, st), "gcb_conv_bwd")
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GCB_ABI_VERSION 1
+#define GCB_ABI_VERSION 2
 #define GCB_MAX_ROT 32
 
 /* error codes */
@@ -101,14 +101,17 @@ int gcb_fold_prior(const float* in, const float* prior, float* out, int32_t T, i
  * rot_off_host: n_rot ints on the HOST (the rotation list arange(0,A,delta) or `orientations`).
  * y [V_out,n_rot,T] (may be NULL if z given); z [V_out,T] and argmax [V_out] (both or neither).
  * w_eff == NULL means an identically-zero prior (ConvZero, conv_zero.py:12-15): the neighbour
- * term is skipped and only the centre term is computed.                                       */
+ * term is skipped and only the centre term is computed.
+ * interp_out (nullable) [V_out,R,A,F]: the tensor-core path stores the interpolations I there
+ * (the reference materialises the same tensor, conv_intrinsic.py:240); handing it to
+ * gcb_conv_bwd saves the backward one full gather pass.  Ignored by the CUDA-core path.        */
 size_t gcb_conv_fwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
                                     int32_t T, int32_t n_rot, int precision);
 int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                  const float* w_self, const float* bias, const int32_t* rot_off_host,
                  int32_t n_rot, int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
                  int32_t T, int act, int precision, float* y, float* z, int32_t* argmax,
-                 void* workspace, size_t workspace_bytes, void* stream);
+                 float* interp_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- AngularMaxPooling on a materialised Y -----------------------------------------------
  * Replaces angular_max_pooling.py:27-29 and its autograd (index_put).                        */
@@ -143,8 +146,9 @@ int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, const float
                  const float* w_self, const float* h, const int32_t* rot_sel,
                  const int32_t* csr_row_ptr, const int32_t* csr_entries, int32_t v_out,
                  int32_t v_src, int32_t R, int32_t A, int32_t F, int32_t T, int precision,
-                 int accumulate, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias,
-                 void* workspace, size_t workspace_bytes, void* stream);
+                 int accumulate, const float* interp /* nullable: interp_out of the forward */, float* d_x,
+                 float* d_w_eff, float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes,
+                 void* stream);
 
 /* ---- vertex-row sharding helper (halo exchange) ---------------------------
  * out[i,:] = src[rows[i],:]  (packs the signal rows a peer asked for into a send buffer). */
