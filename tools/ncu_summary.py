@@ -25,7 +25,11 @@ srows = list(csv.reader(src.splitlines()))
 try:
     hi = next(i for i, r in enumerate(srows) if r and r[0] == "Address")
     sh = srows[hi]; sci = {h: i for i, h in enumerate(sh)}
-    body = [r for r in srows[hi + 1:] if len(r) == len(sh)]
+    body = []
+    for r in srows[hi + 1:]:
+        if len(r) != len(sh) or r[0] == "Address":   # a second kernel's table starts: stop
+            break
+        body.append(r)
     tot = sum(float(r[sci["# Samples"]] or 0) for r in body)
     top = sorted(body, key=lambda r: -float(r[sci["# Samples"]] or 0))[:12]
     print(f"\n## top stall samples (first kernel in report; {int(tot)} samples)")
