@@ -52,7 +52,11 @@ def test_sweep(kind, r, a, delta):
     assert y.shape == (V, n_rot, T) and z.shape == (V, T)
     # pooling properties on the produced tensors
     norms = torch.linalg.vector_norm(y, dim=-1)
-    assert torch.equal(arg.long(), torch.argmax(norms, dim=1))
+    # first maximum of the norms; rotations whose norms agree to ~1 ulp may be ordered differently by
+    # a different summation order (torch.linalg.vector_norm vs the kernel's warp reduction)
+    picked = norms[torch.arange(V, device=DEV), arg.long()]
+    assert (picked >= norms.max(dim=1).values * (1 - 2e-6)).all()
+    assert (arg.long() != torch.argmax(norms, dim=1)).sum() <= 3
     assert torch.equal(z, y[torch.arange(V, device=DEV), arg.long()])
     assert torch.isfinite(dx).all() and torch.isfinite(dw).all()
     if kind == "zero":
