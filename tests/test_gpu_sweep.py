@@ -38,10 +38,14 @@ def test_sweep(kind, r, a, delta):
     bary = O.make_bary(V, r, a, seed=1).to(DEV)
     gz = torch.randn((V, T), generator=torch.Generator().manual_seed(2)).to(DEV)
     outs = {}
-    for precision in ("fp32", "ffma"):
-        if precision == "ffma" and kind != "zero" and r * a > 40:
+    # "fp32": tensor cores both ways; "ffma": CUDA cores both ways; "mixed": exact forward, tensor-core
+    # backward (so both backward implementations see the same ReLU mask and rotations)
+    for precision in ("fp32", "ffma", "mixed"):
+        if precision != "fp32" and kind != "zero" and r * a > 40:
             continue                                   # keep the exact path to the moderate shapes
-        layer = build(kind, r, a, delta, precision)
+        layer = build(kind, r, a, delta, "ffma" if precision == "mixed" else precision)
+        if precision == "mixed":
+            layer.backward_precision = "fp32"
         xs = signal.clone().requires_grad_(True)
         y = layer([xs, bary])
         z = AngularMaxPooling()(y)
@@ -65,10 +69,12 @@ def test_sweep(kind, r, a, delta):
         assert dw.abs().max() == 0
     if "ffma" in outs:
         y2, z2, arg2, dx2, dw2 = outs["ffma"]
+        _, _, arg3, dx3, dw3 = outs["mixed"]
         assert nerr(y, y2) < TOL_FP32
         if torch.equal(arg, arg2):
             assert nerr(z, z2) < TOL_FP32
-            assert nerr(dx, dx2) < TOL_FP32
-            assert nerr(dw, dw2) < TOL_FP32 or kind == "zero"
         else:
             assert (arg != arg2).sum() <= 4        # near-tie flips only
+        assert torch.equal(arg2, arg3)
+        assert nerr(dx3, dx2) < TOL_FP32
+        assert nerr(dw3, dw2) < TOL_FP32 or kind == "zero"
