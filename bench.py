@@ -378,13 +378,16 @@ def run_ours(args):
     }
 
     # CPU baseline: the oracle on this host's cores, bounded sample (1 warm-up + 2 timed meshes)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cpu_inputs = make_inputs(cfg)
-    cpu_reference_step(cfg, weights, cpu_inputs)
-    cpu_t = min(cpu_reference_step(cfg, weights, cpu_inputs) for _ in range(2))
-    cpu_baseline = {"value": v / cpu_t, "unit": "vertices/s", "cores": cores, "kind": "port",
-                    "sample": "best of 2 full S1 meshes (fwd+bwd) after 1 warm-up, torch CPU oracle"}
+    # (timed at N = 1 only; multi-rank runs report null and rely on `--impl reference`)
+    cpu_baseline = None
+    if world == 1:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cpu_inputs = make_inputs(cfg)
+        cpu_reference_step(cfg, weights, cpu_inputs)
+        cpu_t = min(cpu_reference_step(cfg, weights, cpu_inputs) for _ in range(2))
+        cpu_baseline = {"value": v / cpu_t, "unit": "vertices/s", "cores": cores, "kind": "port",
+                        "sample": "best of 2 full S1 meshes (fwd+bwd) after 1 warm-up, torch CPU oracle"}
 
     h2d = signal_h.numel() * 4 + bary_h.numel() * bary_h.element_size() + gz_h.numel() * 4
     d2h = z_host.numel() * 4

@@ -33,7 +33,10 @@
 namespace gcb {
 
 constexpr int TC_M = 128;
-constexpr int TC_PRODUCER_WARPS = 8;
+// 16 producer warps: traced on B200, a producer warp needs ~1100-1900 cycles per 32-row slab even when
+// its loads hit L1 (a single warp's dependent instruction stream), so the tile rate is set by how
+// many warps share a tile, not by memory.  8 warps x 16 rows per tile, two tiles in flight.
+constexpr int TC_PRODUCER_WARPS = 16;
 constexpr int TC_MMA_WARPS = 4;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + TC_MMA_WARPS) * 32;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
@@ -54,6 +57,8 @@ struct TcFwdParams {
   int ns_a;             // A-tile ring depth
   int tmem_cols;        // power of two >= g*n_t
   int ksplit;           // K splits (grid.z = t_chunks * ksplit)
+  int debug;            // GCB_TC_DEBUG bits (timing experiments only): 1 = no gathers, 2 = no MMAs
+  long long* trace;     // GCB_TC_TRACE: clock64 stamps of CTA (1,0,0), [role 0..3][tile 0..127][4]
   RotTable rot;         // offsets in [0, A)
 };
 
@@ -170,7 +175,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   constexpr int A_TILE_BYTES = TC_M * ROW_BYTES;
   constexpr int CPR = KC / 4;                // 16-byte chunks per row
   constexpr int ROWS_PER_PASS = 32 / CPR;
-  constexpr int WARP_ROWS = 32;              // tile rows one producer warp fills
+  constexpr int WARP_ROWS = 128 * 2 / TC_PRODUCER_WARPS;   // tile rows one producer warp fills (16)
   constexpr int ITEMS = WARP_ROWS / ROWS_PER_PASS;  // float4 items per lane per tile
   // producer warps form NGRP groups that take tiles round-robin; a group covers this CTA's share of
   // the tile rows (128 rows alone, 64 rows in a cluster pair), so CL = 2 keeps 4 tiles in flight
@@ -255,16 +260,29 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         producer_bar_sync();
         uint4* dst = reinterpret_cast<uint4*>(smem_gen + (rec_base - smem_base));
         for (int y = 0; y < p.A; ++y)
-          dst[y * (TC_M * 2) + threadIdx.x] =
-              __ldg(p.recs + ((size_t)(xr * p.A + y) * p.v_pad + m0) * 2 + threadIdx.x);
+          for (int i = threadIdx.x; i < TC_M * 2; i += TC_PRODUCER_WARPS * 32)
+            dst[y * (TC_M * 2) + i] = __ldg(p.recs + ((size_t)(xr * p.A + y) * p.v_pad + m0) * 2 + i);
         producer_bar_sync();
         ring = xr;
       }
-      for (int y = 0; y < n_y; ++y, ++n) {
+      for (int yy = 0; yy < n_y; ++yy, ++n) {
+        // Tiles are visited in the order y = yy - off[first rotation of this group]: rotation j of the
+        // group then reads B slot (yy + off_j - off_0) % A, so slots are released in index order and
+        // every slot has A - (off_last - off_0) tile times to be refilled for the next super-step,
+        // whichever rotation group this CTA serves.
+        int y = yy;
+        if (!centre) {
+          y = yy - p.rot.off[rot0];
+          y += y < 0 ? p.A : 0;
+        }
         const int my_stage = stage;
         const uint32_t my_par = empty_par;
         if (++stage == p.ns_a) { stage = 0; empty_par ^= 1u; }
         if ((n & (NGRP - 1)) != pg) continue;
+        const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
+                        wq == 0 && n < 128;
+        long long* trp = tr ? p.trace + ((size_t)pg * 128 + n) * 4 : nullptr;
+        if (tr) trp[0] = clock64();
         const float* xcol = p.x + fc * KC + c * 4;
         float4 v[ITEMS];
         if (!centre) {
@@ -276,6 +294,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
             rw[j] = rec[j * ROWS_PER_PASS * 2 + 1];
           }
           float4 x0[ITEMS], x1[ITEMS], x2[ITEMS];
+          if (p.debug & 1) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) { ri[j].x = 0; ri[j].y = 0; ri[j].z = 0; }
+          }
 #pragma unroll
           for (int j = 0; j < ITEMS; ++j) {
             x0[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].x * p.F));
@@ -308,7 +330,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
             if (row < p.v_out) *reinterpret_cast<float4*>(irow + (size_t)row * RA * p.F) = v[j];
           }
         }
+        if (tr) trp[1] = clock64();
         ptx::mbar_wait(a_empty + 8u * my_stage, my_par);
+        if (tr) trp[2] = clock64();
         const uint32_t a_stage_addr = a_base + (uint32_t)(my_stage * NPROD * A_TILE_BYTES);
         uint8_t* a_hi = smem_gen + (a_stage_addr - smem_base);
         const uint32_t a_peer = CL == 2 ? ptx::mapa(a_stage_addr, crank ^ 1u) : 0u;
@@ -326,8 +350,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
             *reinterpret_cast<float4*>(a_hi + A_TILE_BYTES + off) = l;
           }
         }
-        ptx::fence_proxy_async_smem();
+        if (!(p.debug & 8)) ptx::fence_proxy_async_smem();
         __syncwarp();
+        if (tr) trp[3] = clock64();
         if (lane == 0) {
           ptx::mbar_arrive(a_full + 8u * my_stage);
           if (CL == 2) {
@@ -346,11 +371,11 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     // ===================== drain: TMEM -> this split's partial sums =====================
     ptx::mbar_wait(acc_full, 0);
     ptx::tc_fence_after();
-    const int dq = warp & 3, dh = warp >> 2;   // TMEM lane quadrant of this warp, and which half of the rotations
+    const int dq = warp & 3, dh = warp >> 2;   // TMEM lane quadrant of this warp, and which share of the rotations
     const int row = m0 + 32 * dq + lane;       // < v_pad: the partial buffer is padded
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * dq) << 16);
     float* prow = p.partial + (((size_t)sk * p.v_pad + row) * p.n_rot + rot0) * p.T + t0;
-    for (int il = dh; il < g_cnt; il += 2) {
+    for (int il = dh; il < g_cnt; il += TC_PRODUCER_WARPS / 4) {
       for (int c0 = 0; c0 < p.n_t; c0 += 16) {
         uint32_t r[16];
         ptx::tmem_ld_32x32b_x16(lane_addr + (uint32_t)(il * p.n_t + c0), r);
@@ -364,13 +389,19 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     // ===================== TMA: weight tiles -> B slots =====================
     if (lane == 0) {
       uint32_t loads = 0;  // bit yb = parity of the number of loads issued into slot yb
+      int load_no = 0;
       for (int ss = ss_begin; ss < ss_end; ++ss) {
         const bool centre = ss >= p.R * p.nfc;
         const int xr = centre ? p.R : ss / p.nfc;
         const int fc = ss - xr * p.nfc;
         const int n_y = centre ? 1 : p.A;
         for (int yb = 0; yb < n_y; ++yb) {
+          const int nl = load_no++;
+          const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && nl < 128;
+          long long* trp = tr ? p.trace + ((size_t)3 * 128 + nl) * 4 : nullptr;
+          if (tr) trp[0] = clock64();
           ptx::mbar_wait(b_empty + 8u * yb, ((loads >> yb) & 1u) ^ 1u);
+          if (tr) trp[1] = clock64();
           const int col = (centre ? RA * p.F : (xr * p.A + yb) * p.F) + fc * KC;
           const uint32_t dst = b_base + (uint32_t)(yb * NPROD * b_tile_bytes);
           ptx::mbar_arrive_expect_tx(b_full + 8u * yb, (uint32_t)(NPROD * b_tile_bytes));
@@ -398,17 +429,26 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       constexpr int OWN = TC_G_MAX / TC_MMA_WARPS;
       int yb[OWN];  // rolling B slot of each owned rotation
 #pragma unroll
-      for (int q = 0; q < OWN; ++q) yb[q] = (mw + q * TC_MMA_WARPS) < g_cnt ? p.rot.off[rot0 + mw + q * TC_MMA_WARPS] : 0;
+      for (int q = 0; q < OWN; ++q) {   // relative to the group's first rotation (see the producers' tile order)
+        int rel = (mw + q * TC_MMA_WARPS) < g_cnt ? p.rot.off[rot0 + mw + q * TC_MMA_WARPS] - p.rot.off[rot0] : 0;
+        yb[q] = rel < 0 ? rel + p.A : rel;
+      }
       const uint32_t all_slots = p.A >= 32 ? 0xFFFFFFFFu : ((1u << p.A) - 1u);
       uint32_t fills = 0;     // bit s = parity of completed fills of B slot s
       uint32_t accum = 0;     // 0 only for the very first k-step of this CTA
       int stage = 0;          // rolling n % ns_a
       uint32_t full_par = 0;  // (n / ns_a) & 1
+      int tile_no = 0;
       for (int ss = ss_begin; ss < ss_end; ++ss) {
         const bool centre = ss >= p.R * p.nfc;
         const int n_y = centre ? 1 : p.A;
         for (int y = 0; y < n_y; ++y) {
+          const int ntile = tile_no++;
+          const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && mw == 0 && ntile < 128;
+          long long* trp = tr ? p.trace + ((size_t)2 * 128 + ntile) * 4 : nullptr;
+          if (tr) trp[0] = clock64();
           ptx::mbar_wait(a_full + 8u * stage, full_par);
+          if (tr) trp[1] = clock64();
           ptx::tc_fence_after();
           const uint32_t a_lo = ((a_base + (uint32_t)(stage * NPROD * A_TILE_BYTES)) >> 4) | lo_flags;
 #pragma unroll
@@ -417,6 +457,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
             if (il < g_cnt) {
               const int s = centre ? 0 : yb[q];
               ptx::mbar_wait(b_full + 8u * s, (fills >> s) & 1u);
+              if (tr && q == 0) trp[2] = clock64();
               ptx::tc_fence_after();
               const uint32_t b_lo = b_lo0 + (uint32_t)s * b_slot_lo;
               const uint32_t d = tmem_base + (uint32_t)(il * p.n_t);
@@ -424,18 +465,22 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
               for (int j = 0; j < KC / 8; ++j) {
                 const uint64_t da = desc_hi | (uint64_t)(a_lo + 2u * j);
                 const uint64_t db = desc_hi | (uint64_t)(b_lo + 2u * j);
+                if (p.debug & 2) continue;
                 ptx::umma_tf32(d, da, db, idesc, j == 0 ? accum : 1u);
                 if (X3) {
                   ptx::umma_tf32(d, da, desc_hi | (uint64_t)(b_lo + b_lo_half + 2u * j), idesc, 1u);
                   ptx::umma_tf32(d, desc_hi | (uint64_t)(a_lo + (A_TILE_BYTES >> 4) + 2u * j), db, idesc, 1u);
                 }
               }
-              ptx::umma_commit(b_empty + 8u * s);
+              if (p.debug & 4) ptx::mbar_arrive(b_empty + 8u * s); else ptx::umma_commit(b_empty + 8u * s);
               if (!centre) yb[q] = (yb[q] + 1 == p.A) ? 0 : yb[q] + 1;
             }
           }
           accum = 1u;
-          if (CL == 2) ptx::umma_commit_mc(a_empty + 8u * stage, (uint16_t)3); else ptx::umma_commit(a_empty + 8u * stage);
+          if (tr) trp[3] = clock64();
+          if (CL == 2) ptx::umma_commit_mc(a_empty + 8u * stage, (uint16_t)3);
+          else if (p.debug & 4) ptx::mbar_arrive(a_empty + 8u * stage);
+          else ptx::umma_commit(a_empty + 8u * stage);
           if (++stage == p.ns_a) { stage = 0; full_par ^= 1u; }
         }
         fills ^= centre ? 1u : all_slots;
@@ -659,6 +704,14 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   p.v_out = v_out; p.v_pad = v_pad; p.R = R; p.A = A; p.F = F; p.T = T; p.n_rot = n_rot;
   p.nfc = F / cfg.kc; p.n_t = cfg.n_t; p.g = cfg.g; p.ns_a = cfg.ns_a; p.tmem_cols = cfg.tmem_cols;
   p.ksplit = ksplit;
+  p.debug = getenv("GCB_TC_DEBUG") ? atoi(getenv("GCB_TC_DEBUG")) : 0;
+  p.trace = nullptr;
+  static long long* trace_dev = nullptr;
+  if (getenv("GCB_TC_TRACE")) {   // debugging aid only: the one place the library touches cudaMalloc
+    if (!trace_dev) GCB_CUDA_OK(cudaMalloc(&trace_dev, 4 * 128 * 4 * sizeof(long long)));
+    GCB_CUDA_OK(cudaMemsetAsync(trace_dev, 0, 4 * 128 * 4 * sizeof(long long), st));
+    p.trace = trace_dev;
+  }
   p.rot = rot;
   dim3 grid((unsigned)m_tiles, (unsigned)cfg.n_groups, (unsigned)((T / cfg.n_t) * ksplit));
   if (cfg.kc == 32) rc = x3 ? tc_launch<32, true>(mh, ml, p, cfg, grid, st) : tc_launch<32, false>(mh, ml, p, cfg, grid, st);
@@ -669,6 +722,22 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   k_tc_finish<<<(unsigned)ceil_div64(v_out, warps_per_block), warps_per_block * 32, 0, st>>>(
       partial, bias, ksplit, v_out, v_pad, n_rot, T, act, y, z, argmax);
   GCB_LAUNCH_OK();
+  if (p.trace) {
+    static long long host[4 * 128 * 4];
+    GCB_CUDA_OK(cudaMemcpyAsync(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost, st));
+    GCB_CUDA_OK(cudaStreamSynchronize(st));
+    long long t0 = host[0];
+    const char* names[4] = {"prod0", "prod1", "mma0", "tma"};
+    for (int role = 0; role < 4; ++role) {
+      fprintf(stderr, "[trace %s] tile: start  +loads  +empty_wait  +stored | (mma: wait_a, a_ready, b_ready, issued)\n", names[role]);
+      for (int n = 0; n < 40; ++n) {
+        long long* e = host + ((size_t)role * 128 + n) * 4;
+        if (!e[0]) continue;
+        fprintf(stderr, "  %3d: %8lld %8lld %8lld %8lld\n", n, e[0] - t0, e[1] ? e[1] - t0 : -1, e[2] ? e[2] - t0 : -1,
+                e[3] ? e[3] - t0 : -1);
+      }
+    }
+  }
   return GCB_OK;
 }
 
