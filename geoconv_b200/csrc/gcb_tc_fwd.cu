@@ -2,18 +2,30 @@
 //
 //   Y[k,i,t] = act( sum_{x,y,f} Weff[t,x,(y+o_i)%A,f] * I[k,x,y,f] + X[k]·Wself[t] + b[t] )
 // is a GEMM with M = vertices, N = (rotation, template), K = (x, y, f) plus one centre slab (f).
-// The rotation never moves data: for a fixed (x, f-chunk) "super-step" all A angular B tiles
-// (weights) sit in shared memory and rotation i pairs the gathered A tile y with B tile
-// (y+o_i)%A, so every operand tile is staged once and used g times.
+// The rotation never moves data: for a fixed (x, f-chunk) "super-step" all A angular weight tiles
+// sit in a shared-memory ring and rotation i pairs the gathered tile y with weight tile (y+o_i)%A,
+// so every operand tile is staged once and used g times.
 //
 // Kernel 1  k_tc_conv: one CTA = 128 vertices x g rotations x n_t templates x one K split.
-//   warps 0-7  producers: barycentric 3-neighbour gather of signal rows (float4 loads of the
-//              L2-resident signal, records of the current radial ring cached in smem) + weighted
-//              sum in registers, rounded to tf32 (RN), written straight into the swizzled K-major
-//              UMMA layout; afterwards they drain TMEM to the split's partial-sum buffer.
-//   warp 8     TMA: weight tiles (cp.async.bulk.tensor, hardware swizzle) into the B slots.
-//   warp 9     MMA: one thread issues tcgen05.mma kind::tf32 into TMEM accumulators (g*n_t columns)
-//              and releases operand slots with tcgen05.commit.
+//   warps 0-7  producers.  Every warp fills 16 rows of EVERY tile: barycentric 3-neighbour gather
+//              of signal rows (float4 loads of the L2-resident signal; the packed records of the
+//              current radial ring are cached in smem), weighted sum in registers, rounded to tf32
+//              (RN), written straight into the swizzled K-major UMMA layout.  The loads of tile
+//              n+D are issued before tile n is combined and stored (register double/triple
+//              buffering), so a warp always has gathers in flight; measured before this change a
+//              warp's load -> combine -> store -> arrive chain (~2300 cycles) set the tile rate.
+//              At the end the producers drain TMEM to the split's partial-sum buffer.
+//   warp 8     TMA: weight tiles (cp.async.bulk.tensor, hardware swizzle) into the ring.
+//   warps 9-10 MMA: one thread per warp issues tcgen05.mma kind::tf32 into TMEM accumulators
+//              (g*n_t columns) and releases operand slots with tcgen05.commit.
+//   Merged rotations: with N = n_t = 96 an MMA reads 4 KB of A and 3 KB of B from shared memory in
+//   48 tensor cycles - 149 B/cycle against the 128 B/cycle an SM can deliver - so the unmerged
+//   kernel was shared-memory bound (3xTF32: 3060 cycles per tile measured vs 3062 predicted from
+//   bytes).  Rotations whose offsets step uniformly (o_{i+1} = o_i + d) read weight tiles that
+//   are d apart on the ring; the ring is therefore laid out cycle by cycle of "+d", with the head of
+//   each cycle duplicated behind its tail, so that m consecutive rotations always find their m
+//   tiles ADJACENT and are issued as ONE MMA of N = m*n_t <= 256: the A tile is read once per m
+//   rotations (104 B/cycle at m = 2, n_t = 96).
 //   The contraction is split over CTAs (split-K) for two reasons: 108 tiles do not fill 148 SMs at
 //   the FAUST shape, and the tensor core accumulates with truncation, so a chain of thousands of
 //   accumulations loses ~1e-5 relative; short chains + an fp32 (RN) sum of the partials do not.
@@ -26,6 +38,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "gcb_common.cuh"
 #include "gcb_ptx.cuh"
 #include "gcb_tc.cuh"
@@ -33,17 +47,26 @@
 namespace gcb {
 
 constexpr int TC_M = 128;
-// 16 producer warps: traced on B200, a producer warp needs ~1100-1900 cycles per 32-row slab even when
-// its loads hit L1 (a single warp's dependent instruction stream), so the tile rate is set by how
-// many warps share a tile, not by memory.  8 warps x 16 rows per tile, two tiles in flight.
-constexpr int TC_PRODUCER_WARPS = 16;
-constexpr int TC_MMA_WARPS = 4;
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_MMA_WARPS = 1;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + TC_MMA_WARPS) * 32;
+constexpr int TC_WARP_ROWS = TC_M / TC_PRODUCER_WARPS;   // tile rows one producer warp fills
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_BAR_BYTES = 1024;
 constexpr int TC_G_MAX = 8;              // rotations per CTA (accumulator groups) upper bound
+constexpr int TC_OWN = TC_G_MAX;   // MMA units one issuing warp can own (all of them when it works alone)
 constexpr int TC_REC_BYTES = TC_M * 32;  // one (x,y) slot of packed records for a 128-vertex tile
 constexpr int TC_X3_CHAIN_K = 3072;      // TF32X3: contraction length per accumulator chain
+constexpr uint8_t TC_NO_DUP = 0xFF;
+
+// Where the A angular weight tiles of a super-step live in the shared-memory ring.
+//   m      rotations merged into one MMA (1 = every rotation issues its own N = n_t MMAs)
+//   dstep  offset step between consecutive rotations (mod A) when m > 1
+//   pos[s] ring position of angular tile s; dup[s] a second position that receives a copy of it
+struct TcRing {
+  int m, dstep, n_pos;
+  uint8_t pos[GCB_MAX_ROT], dup[GCB_MAX_ROT];
+};
 
 struct TcFwdParams {
   const float* x;       // [v_src, F]
@@ -52,48 +75,97 @@ struct TcFwdParams {
   float* interp_out;    // optional [v_out, R*A*F]: the interpolations, kept for the backward's dW
   int v_out, v_pad, R, A, F, T, n_rot;
   int nfc;              // F / KC
-  int n_t;              // templates per CTA (MMA N)
+  int n_t;              // templates per CTA (columns of one rotation's accumulator)
   int g;                // rotations per CTA
   int ns_a;             // A-tile ring depth
   int tmem_cols;        // power of two >= g*n_t
   int ksplit;           // K splits (grid.z = t_chunks * ksplit)
-  int debug;            // GCB_TC_DEBUG bits (timing experiments only): 1 = no gathers, 2 = no MMAs
-  long long* trace;     // GCB_TC_TRACE: clock64 stamps of CTA (1,0,0), [role 0..3][tile 0..127][4]
+  long long* trace;     // GCB_TC_TRACE (investigation builds): clock64 stamps of CTA (1,0,0), [role][tile][8]
+  int debug;            // GCB_TC_DEBUG bits (timing experiments only): 1 = all gathers read row 0, 2 = no MMAs
+  TcRing ring;
   RotTable rot;         // offsets in [0, A)
 };
 
 struct TcConfig {
   int kc, n_t, g, n_groups, ns_a, tmem_cols;
+  TcRing ring;
   size_t smem_bytes;
   bool ok;
 };
 
-static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3) {
+static int gcd_int(int a, int b) {
+  while (b) { int t = a % b; a = b; b = t; }
+  return a;
+}
+
+// Ring layout for rotation lists that step uniformly by d (mod A): the cycles of "+d" on Z_A are
+// laid out one after the other, each followed by copies of its first m-1 tiles, so that the tiles
+// s, s+d, ..., s+(m-1)d of m consecutive rotations are always at adjacent positions.
+static TcRing tc_ring_layout(int A, int dstep, int m) {
+  TcRing r{};
+  r.m = m; r.dstep = m > 1 ? dstep : 0;
+  for (int s = 0; s < GCB_MAX_ROT; ++s) { r.pos[s] = (uint8_t)(s < A ? s : 0); r.dup[s] = TC_NO_DUP; }
+  r.n_pos = A;
+  if (m <= 1) return r;
+  const int gc = gcd_int(dstep, A), L = A / gc;
+  int at = 0;
+  for (int c = 0; c < gc; ++c) {
+    for (int k = 0; k < L; ++k) r.pos[(c + k * dstep) % A] = (uint8_t)at++;
+    for (int k = 0; k < m - 1; ++k) r.dup[(c + k * dstep) % A] = (uint8_t)at++;
+  }
+  r.n_pos = at;
+  return r;
+}
+
+// uniform step of a rotation list (0 = not uniform / single rotation)
+static int tc_uniform_step(const RotTable& rot, int n_rot, int A) {
+  if (n_rot < 2) return 0;
+  const int d = ((rot.off[1] - rot.off[0]) % A + A) % A;
+  if (d == 0) return 0;
+  for (int i = 1; i + 1 < n_rot; ++i)
+    if (((rot.off[i + 1] - rot.off[i]) % A + A) % A != d) return 0;
+  return d;
+}
+
+// dstep = 0: every rotation on its own (works for any rotation list)
+static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, int dstep) {
   TcConfig c{};
   c.ok = false;
   if (T % 16 != 0 || F % 8 != 0 || A > GCB_MAX_ROT || n_rot > GCB_MAX_ROT) return c;
   const int nprod = x3 ? 2 : 1;
   for (int n_t = (T < 256 ? T : 256); n_t >= 16; n_t -= 16) {
     if (T % n_t != 0) continue;
+    int g_max = 512 / n_t;
+    if (g_max > TC_G_MAX) g_max = TC_G_MAX;
+    if (g_max > n_rot) g_max = n_rot;
+    const int n_groups = (n_rot + g_max - 1) / g_max;
+    const int g = (n_rot + n_groups - 1) / n_groups;
+    int m_top = 1;
+    if (dstep > 0) {
+      const int L = A / gcd_int(dstep, A);
+      while (m_top * 2 <= g && m_top * 2 * n_t <= 256 && m_top * 2 - 1 < L) m_top *= 2;
+    }
     for (int kc = 32; kc >= 8; kc >>= 1) {
       if (F % kc != 0) continue;
-      size_t b_bytes = (size_t)A * nprod * n_t * kc * 4;
-      size_t a_stage = (size_t)nprod * TC_M * kc * 4;
-      size_t fixed = b_bytes + (size_t)A * TC_REC_BYTES + TC_BAR_BYTES + 1024 /* alignment slack */;
-      if (fixed + 4 * a_stage > (size_t)TC_SMEM_LIMIT) continue;
-      int ns_a = (int)(((size_t)TC_SMEM_LIMIT - fixed) / a_stage);
-      if (ns_a > 8) ns_a = 8;
-      int g_max = 512 / n_t;
-      if (g_max > TC_G_MAX) g_max = TC_G_MAX;
-      if (g_max > n_rot) g_max = n_rot;
-      int n_groups = (n_rot + g_max - 1) / g_max;
-      int g = (n_rot + n_groups - 1) / n_groups;
-      int cols = 32;
-      while (cols < g * n_t) cols <<= 1;
-      c.kc = kc; c.n_t = n_t; c.g = g; c.n_groups = n_groups; c.ns_a = ns_a; c.tmem_cols = cols;
-      c.smem_bytes = fixed + (size_t)ns_a * a_stage;
-      c.ok = true;
-      return c;
+      for (int m = m_top; m >= 1; m >>= 1) {
+        TcRing ring = tc_ring_layout(A, dstep, m);
+        if (ring.n_pos >= TC_NO_DUP) continue;
+        size_t b_bytes = (size_t)ring.n_pos * nprod * n_t * kc * 4;
+        size_t a_stage = (size_t)nprod * TC_M * kc * 4;
+        size_t fixed = b_bytes + (size_t)A * TC_REC_BYTES + TC_BAR_BYTES + 1024 /* alignment slack */;
+        if (fixed + 4 * a_stage > (size_t)TC_SMEM_LIMIT) continue;
+        int ns_a = (int)(((size_t)TC_SMEM_LIMIT - fixed) / a_stage);
+        if (ns_a > 8) ns_a = 8;
+        static const int ns_cap = getenv("GCB_TC_NSA") ? atoi(getenv("GCB_TC_NSA")) : 0;   // experiments
+        if (ns_cap >= 3 && ns_a > ns_cap) ns_a = ns_cap;
+        int cols = 32;
+        while (cols < g * n_t) cols <<= 1;
+        c.kc = kc; c.n_t = n_t; c.g = g; c.n_groups = n_groups; c.ns_a = ns_a; c.tmem_cols = cols;
+        c.ring = ring;
+        c.smem_bytes = fixed + (size_t)ns_a * a_stage;
+        c.ok = true;
+        return c;
+      }
     }
   }
   return c;
@@ -161,43 +233,209 @@ __device__ __forceinline__ void producer_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCER_WARPS * 32) : "memory");
 }
 
+// position in the CTA's tile sequence: super-step ss = (radial ring xr, feature chunk fc) or the
+// centre slab, angular step yy inside it
+struct TcTileIt {
+  int ss, yy, xr, fc, n_y;
+  bool centre;
+  __device__ __forceinline__ void decode(const TcFwdParams& p) {
+    centre = ss >= p.R * p.nfc;
+    xr = centre ? p.R : ss / p.nfc;
+    fc = ss - xr * p.nfc;
+    n_y = centre ? 1 : p.A;
+  }
+  __device__ __forceinline__ void start(const TcFwdParams& p, int ss0) { ss = ss0; yy = 0; decode(p); }
+  __device__ __forceinline__ void next(const TcFwdParams& p) {
+    if (++yy == n_y) { yy = 0; ++ss; decode(p); }
+  }
+};
+
+// Barrier / operand addresses the MMA warp works with
+struct TcMmaCtx {
+  uint32_t a_full, a_empty, b_full, b_empty, acc_full;   // mbarrier addresses (arrays indexed * 8)
+  uint32_t a_lo0, a_stage_lo;   // descriptor low word of A stage 0, distance between stages (>> 4)
+  uint32_t b_lo0, b_tile_lo, b_lo_ring;   // same for ring position 0, one tile, hi ring -> lo ring
+  uint32_t tmem_base;
+  int rot0, g_cnt, n_units, off_anchor;
+  int n_nc, n_c;                // non-centre super-steps / centre tiles of this CTA
+};
+
+// The MMA-issuing warp.  Measured on B200 (tools/microbench/mma_issue.cu): ONE thread issues
+// back-to-back tcgen05.mma at the full tensor rate (N = 192: 96.0 cycles per MMA, commits free), and a
+// successful mbarrier try_wait costs ~80 cycles (sync_cost.cu).  What bounded every earlier version
+// of this kernel was the issuing warp's own instruction stream: ~300-2000 cycles of integer / branch
+// / shuffle bookkeeping per tile around 768 cycles of MMAs (a single warp retires a dependent
+// instruction every ~8 cycles).  So this loop is kept minimal: NU (units) is a template parameter,
+// everything is warp-uniform (the whole warp runs converged, only the tcgen05 instructions sit under
+// elect.sync, so values live in uniform registers), centre tiles have their own loop, and per tile
+// there is one wait for the A stage, normally one wait for the weight tile entering the rotation
+// windows, the MMAs, one commit for the weight tile leaving the windows and one for the A stage.
+template <int KC, bool X3, int CL, int NU>
+__device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx& c, int lane) {
+  constexpr int ROW_BYTES = KC * 4;
+  constexpr int KS = KC / 8;
+  constexpr uint32_t A_LO_HALF = (uint32_t)(TC_M * ROW_BYTES) >> 4;   // hi tile -> lo tile of an A stage
+  const uint64_t desc_hi = ptx::make_kmajor_desc<ROW_BYTES>(0) & 0xFFFFFFFF00000000ull;
+  const int A_ = p.A, n_t_ = p.n_t, ns_a_ = p.ns_a, m_ = p.ring.m;
+  const bool no_mma = (p.debug & 2) != 0;
+  int sl[NU];              // angular weight tile the unit's first rotation reads at the current step
+  uint32_t idesc_u[NU], d_u[NU];
+  bool on[NU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    on[u] = u < c.n_units;
+    const int wd = on[u] ? min(m_, c.g_cnt - u * m_) : 1;
+    int rel = on[u] ? p.rot.off[c.rot0 + u * m_] - c.off_anchor : 0;
+    sl[u] = rel < 0 ? rel + A_ : rel;
+    idesc_u[u] = ptx::make_idesc_tf32(TC_M, wd * n_t_);
+    d_u[u] = c.tmem_base + (uint32_t)(u * m_ * n_t_);
+  }
+  // lane yy: the weight tiles first read / last read at angular step yy of a super-step
+  uint32_t need_l = 0, retire_l = 0;
+  if (lane < A_) {
+    for (int sg = 0; sg < A_; ++sg) {
+      int first = A_, last = -1;
+      for (int j = 0; j < c.g_cnt; ++j) {
+        int st = (sg - (p.rot.off[c.rot0 + j] - c.off_anchor)) % A_;
+        st += st < 0 ? A_ : 0;
+        first = st < first ? st : first;
+        last = st > last ? st : last;
+      }
+      if (first == lane) need_l |= 1u << sg;
+      if (last == lane) retire_l |= 1u << sg;
+    }
+  }
+  const bool trace_on = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  int stage = 0;
+  uint32_t par = 0, accum = 0;
+  int n = 0;
+  for (int k = 0; k < c.n_nc; ++k) {
+    const uint32_t b_par = (uint32_t)(k & 1);   // every weight tile is filled once per super-step
+    for (int y = 0; y < A_; ++y, ++n) {
+      long long* trp = trace_on && n < 128 ? p.trace + ((size_t)2 * 128 + n) * 8 : nullptr;
+      if (trp) trp[0] = clock64();
+      uint32_t nm = __shfl_sync(0xffffffffu, need_l, y);
+      uint32_t rm = __shfl_sync(0xffffffffu, retire_l, y);
+      ptx::mbar_wait(c.a_full + 8u * stage, par);
+      while (nm) {
+        ptx::mbar_wait(c.b_full + 8u * (uint32_t)(__ffs((int)nm) - 1), b_par);
+        nm &= nm - 1;
+      }
+      ptx::tc_fence_after();
+      if (trp) trp[1] = clock64();
+      const uint32_t a_lo = c.a_lo0 + (uint32_t)stage * c.a_stage_lo;
+      uint32_t b_lo[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) b_lo[u] = c.b_lo0 + (uint32_t)p.ring.pos[sl[u]] * c.b_tile_lo;
+      if (ptx::elect_one()) {
+        if (!no_mma) {
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            if (on[u]) {
+#pragma unroll
+              for (int j = 0; j < KS; ++j) {
+                const uint64_t da = desc_hi | (uint64_t)(a_lo + 2u * j);
+                const uint64_t db = desc_hi | (uint64_t)(b_lo[u] + 2u * j);
+                ptx::umma_tf32(d_u[u], da, db, idesc_u[u], j == 0 ? accum : 1u);
+                if (X3) {
+                  ptx::umma_tf32(d_u[u], da, desc_hi | (uint64_t)(b_lo[u] + c.b_lo_ring + 2u * j), idesc_u[u], 1u);
+                  ptx::umma_tf32(d_u[u], desc_hi | (uint64_t)(a_lo + A_LO_HALF + 2u * j), db, idesc_u[u], 1u);
+                }
+              }
+            }
+          }
+        }
+        while (rm) {
+          ptx::umma_commit(c.b_empty + 8u * (uint32_t)(__ffs((int)rm) - 1));
+          rm &= rm - 1;
+        }
+        if (CL == 2) ptx::umma_commit_mc(c.a_empty + 8u * stage, (uint16_t)3);
+        else ptx::umma_commit(c.a_empty + 8u * stage);
+      }
+      __syncwarp();
+      if (trp) trp[2] = clock64();
+      accum = 1u;
+#pragma unroll
+      for (int u = 0; u < NU; ++u) sl[u] = sl[u] + 1 == A_ ? 0 : sl[u] + 1;
+      if (++stage == ns_a_) { stage = 0; par ^= 1u; }
+    }
+  }
+  // centre tiles: X[k] * Wself - one weight tile (ring position of angular tile 0) serves every
+  // rotation, one N = n_t MMA chain each
+  const uint32_t idesc1 = ptx::make_idesc_tf32(TC_M, n_t_);
+  const uint32_t b_lo_c = c.b_lo0 + (uint32_t)p.ring.pos[0] * c.b_tile_lo;
+  for (int k = 0; k < c.n_c; ++k, ++n) {
+    ptx::mbar_wait(c.a_full + 8u * stage, par);
+    ptx::mbar_wait(c.b_full, (uint32_t)((c.n_nc + k) & 1));
+    ptx::tc_fence_after();
+    const uint32_t a_lo = c.a_lo0 + (uint32_t)stage * c.a_stage_lo;
+    if (ptx::elect_one()) {
+      if (!no_mma) {
+        for (int r = 0; r < c.g_cnt; ++r) {
+          const uint32_t d = c.tmem_base + (uint32_t)(r * n_t_);
+#pragma unroll
+          for (int j = 0; j < KS; ++j) {
+            const uint64_t da = desc_hi | (uint64_t)(a_lo + 2u * j);
+            const uint64_t db = desc_hi | (uint64_t)(b_lo_c + 2u * j);
+            ptx::umma_tf32(d, da, db, idesc1, j == 0 ? accum : 1u);
+            if (X3) {
+              ptx::umma_tf32(d, da, desc_hi | (uint64_t)(b_lo_c + c.b_lo_ring + 2u * j), idesc1, 1u);
+              ptx::umma_tf32(d, desc_hi | (uint64_t)(a_lo + A_LO_HALF + 2u * j), db, idesc1, 1u);
+            }
+          }
+        }
+      }
+      ptx::umma_commit(c.b_empty);
+      if (CL == 2) ptx::umma_commit_mc(c.a_empty + 8u * stage, (uint16_t)3);
+      else ptx::umma_commit(c.a_empty + 8u * stage);
+    }
+    __syncwarp();
+    accum = 1u;
+    if (++stage == ns_a_) { stage = 0; par ^= 1u; }
+  }
+  if (ptx::elect_one()) ptx::umma_commit(c.acc_full);   // accumulators complete
+  __syncwarp();
+}
+
 // CL = 2: the two CTAs of a (1,2,1) cluster work on the SAME 128-vertex tile and K range with
-// different rotation groups.  Each gathers and interpolates only half of the rows and writes them
-// into both CTAs' A stages (st.shared::cluster), so the gather traffic of a tile is paid once, not
-// once per rotation group.  Stage barriers span the pair: a_full collects both CTAs' producers
-// (remote mbarrier arrive), a_empty both CTAs' MMA warps (tcgen05.commit multicast).
-template <int KC, bool X3, int CL>
+// different rotation groups.  Each gathers and interpolates only half of the rows and hands them to
+// the peer's A stage with the bulk-copy engine (DSMEM), so the gather traffic of a tile - the
+// largest L2 -> SM stream of the kernel - is paid once, not once per rotation group.  Stage
+// barriers span the pair: a_full collects both CTAs' producers (remote arrive + complete_tx),
+// a_empty both CTAs' MMA warps (tcgen05.commit multicast).
+template <int KC, bool X3, int CL, bool KEEP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
-          const TcFwdParams p) {
+          const __grid_constant__ TcFwdParams p) {
   constexpr int ROW_BYTES = KC * 4;
   constexpr int NPROD = X3 ? 2 : 1;
   constexpr int A_TILE_BYTES = TC_M * ROW_BYTES;
   constexpr int CPR = KC / 4;                // 16-byte chunks per row
   constexpr int ROWS_PER_PASS = 32 / CPR;
-  constexpr int WARP_ROWS = 128 * 2 / TC_PRODUCER_WARPS;   // tile rows one producer warp fills (16)
-  constexpr int ITEMS = WARP_ROWS / ROWS_PER_PASS;  // float4 items per lane per tile
   // producer warps form NGRP groups that take tiles round-robin; a group covers this CTA's share of
-  // the tile rows (128 rows alone, 64 rows in a cluster pair), so CL = 2 keeps 4 tiles in flight
+  // the tile rows (128 rows alone, 64 rows in a cluster pair), so a CTA keeps 2 (4) tiles in flight
   constexpr int NGRP = 2 * CL;
   constexpr int GRP_WARPS = TC_PRODUCER_WARPS / NGRP;
+  constexpr int WARP_ROWS = (TC_M / CL) / GRP_WARPS;   // tile rows one producer warp fills (32)
+  constexpr int ITEMS = WARP_ROWS / ROWS_PER_PASS;     // float4 items per lane per tile
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_tile_bytes = p.n_t * ROW_BYTES;
-  const uint32_t b_base = smem_base;                                        // [A][NPROD][b_tile]
-  const uint32_t a_base = b_base + (uint32_t)(p.A * NPROD * b_tile_bytes);  // [ns_a][NPROD][A_TILE]
-  const uint32_t rec_base = a_base + (uint32_t)(p.ns_a * NPROD * A_TILE_BYTES);  // [A][128][32 B]
+  const uint32_t b_base = smem_base;                                        // [NPROD][n_pos][b_tile]
+  const uint32_t a_base = b_base + (uint32_t)(p.ring.n_pos * NPROD * b_tile_bytes);  // [ns_a][NPROD][A_TILE]
+  const uint32_t rec_base = a_base + (uint32_t)(p.ns_a * NPROD * A_TILE_BYTES);      // [A][128][32 B]
   const uint32_t bar_base = rec_base + (uint32_t)(p.A * TC_REC_BYTES);
   const uint32_t a_full = bar_base;
   const uint32_t a_empty = a_full + 8u * p.ns_a;
-  const uint32_t b_full = a_empty + 8u * p.ns_a;
+  const uint32_t b_full = a_empty + 8u * p.ns_a;   // per angular tile
   const uint32_t b_empty = b_full + 8u * p.A;
   const uint32_t acc_full = b_empty + 8u * p.A;
   const uint32_t tmem_slot = acc_full + 8u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));     // generic view of smem_base
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the shuffle tells the compiler the warp index is warp-uniform (role dispatch, uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_M;
   const int grp = blockIdx.y;
   const int tz = blockIdx.z / p.ksplit, sk = blockIdx.z - tz * p.ksplit;
@@ -208,13 +446,16 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   const int n_ss = (p.R + 1) * p.nfc;  // super-steps: (x, f-chunk) for x < R, then the centre slab
   const int ss_begin = (int)(((int64_t)n_ss * sk) / p.ksplit);
   const int ss_end = (int)(((int64_t)n_ss * (sk + 1)) / p.ksplit);
+  const int n_units = (g_cnt + p.ring.m - 1) / p.ring.m;   // MMA units: groups of <= m merged rotations
+  // The angular visiting order is common to the cluster pair (they share the gathered tiles): it is
+  // anchored at the first rotation of the pair's first CTA.  rel0 = this CTA's first offset
+  // relative to that anchor = the first weight tile this CTA needs in every super-step.
+  const int off_anchor = p.rot.off[(CL == 2 ? (grp & ~1) : grp) * p.g];
+  int rel0 = p.rot.off[rot0] - off_anchor;
+  rel0 += rel0 < 0 ? p.A : 0;
 
   const uint32_t crank = CL == 2 ? ptx::cluster_ctarank() : 0u;
-  int mma_arrivals = min(g_cnt, TC_MMA_WARPS);
-  if (CL == 2) {
-    const int g_peer = min(p.g, p.n_rot - (grp ^ 1) * p.g);
-    mma_arrivals += min(g_peer, TC_MMA_WARPS);
-  }
+  const int mma_arrivals = CL;   // one commit per CTA of the cluster releases an A stage
   if (warp == TC_PRODUCER_WARPS && lane == 0) {
     for (int s = 0; s < p.ns_a; ++s) {
       ptx::mbar_init(a_full + 8u * s, GRP_WARPS * CL);
@@ -222,9 +463,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     }
     for (int s = 0; s < p.A; ++s) {
       ptx::mbar_init(b_full + 8u * s, 1);
-      ptx::mbar_init(b_empty + 8u * s, (uint32_t)g_cnt);
+      ptx::mbar_init(b_empty + 8u * s, 1);
     }
-    ptx::mbar_init(acc_full, (uint32_t)min(g_cnt, TC_MMA_WARPS));
+    ptx::mbar_init(acc_full, 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tensormap(&tmap_hi);
     if (X3) ptx::prefetch_tensormap(&tmap_lo);
@@ -237,7 +478,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   __syncthreads();
   if (CL == 2) ptx::cluster_sync();   // the peer's barriers exist before anyone arrives on them remotely
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const uint32_t tmem_base = __shfl_sync(
+      0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base)), 0);
 
   if (warp < TC_PRODUCER_WARPS) {
     // ===================== producers: gather + interpolate -> swizzled A tiles =====================
@@ -246,6 +488,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     const int c = lane % CPR;
     const int row_l = lane / CPR;
     const uint4* rec_smem = reinterpret_cast<const uint4*>(smem_gen + (rec_base - smem_base));
+    const bool keep_interp = KEEP && tz == 0 && (CL == 2 ? (grp >> 1) == 0 : grp == 0);
     int ring = -1;
     int n = 0;
     int stage = 0;             // n % ns_a, kept as a rolling counter (no integer division per tile)
@@ -260,58 +503,54 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         producer_bar_sync();
         uint4* dst = reinterpret_cast<uint4*>(smem_gen + (rec_base - smem_base));
         for (int y = 0; y < p.A; ++y)
-          for (int i = threadIdx.x; i < TC_M * 2; i += TC_PRODUCER_WARPS * 32)
-            dst[y * (TC_M * 2) + i] = __ldg(p.recs + ((size_t)(xr * p.A + y) * p.v_pad + m0) * 2 + i);
+          dst[y * (TC_M * 2) + threadIdx.x] =
+              __ldg(p.recs + ((size_t)(xr * p.A + y) * p.v_pad + m0) * 2 + threadIdx.x);
         producer_bar_sync();
         ring = xr;
       }
       for (int yy = 0; yy < n_y; ++yy, ++n) {
-        // Tiles are visited in the order y = yy - off[first rotation of this group]: rotation j of the
-        // group then reads B slot (yy + off_j - off_0) % A, so slots are released in index order and
-        // every slot has A - (off_last - off_0) tile times to be refilled for the next super-step,
-        // whichever rotation group this CTA serves.
+        // Tiles are visited in the order y = yy - off[anchor rotation]: rotation j then reads weight
+        // tile (yy + off_j - off_anchor) % A, so a CTA whose first rotation has relative offset rel0
+        // needs the weight tiles in the order rel0, rel0+1, ... - the order its TMA warp loads them.
         int y = yy;
         if (!centre) {
-          y = yy - p.rot.off[rot0];
+          y = yy - off_anchor;
           y += y < 0 ? p.A : 0;
         }
         const int my_stage = stage;
         const uint32_t my_par = empty_par;
         if (++stage == p.ns_a) { stage = 0; empty_par ^= 1u; }
         if ((n & (NGRP - 1)) != pg) continue;
-        const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
-                        wq == 0 && n < 128;
-        long long* trp = tr ? p.trace + ((size_t)pg * 128 + n) * 4 : nullptr;
+        const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && wq == 0 &&
+                        pg < 2 && n < 128;
+        long long* trp = tr ? p.trace + ((size_t)pg * 128 + n) * 8 : nullptr;
         if (tr) trp[0] = clock64();
         const float* xcol = p.x + fc * KC + c * 4;
         float4 v[ITEMS];
-        if (!centre) {
+        if (p.debug & 4) {
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (!centre) {
           const uint4* rec = rec_smem + (size_t)(y * TC_M + row_w + row_l) * 2;
-          uint4 ri[ITEMS], rw[ITEMS];
-#pragma unroll
-          for (int j = 0; j < ITEMS; ++j) {
-            ri[j] = rec[j * ROWS_PER_PASS * 2];
-            rw[j] = rec[j * ROWS_PER_PASS * 2 + 1];
-          }
           float4 x0[ITEMS], x1[ITEMS], x2[ITEMS];
-          if (p.debug & 1) {
-#pragma unroll
-            for (int j = 0; j < ITEMS; ++j) { ri[j].x = 0; ri[j].y = 0; ri[j].z = 0; }
-          }
+          float w0[ITEMS], w1[ITEMS], w2[ITEMS];
 #pragma unroll
           for (int j = 0; j < ITEMS; ++j) {
-            x0[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].x * p.F));
-            x1[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].y * p.F));
-            x2[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri[j].z * p.F));
+            uint4 ri = rec[j * ROWS_PER_PASS * 2];
+            const uint4 rw = rec[j * ROWS_PER_PASS * 2 + 1];
+            if (p.debug & 1) { ri.x = 0; ri.y = 0; ri.z = 0; }
+            w0[j] = __uint_as_float(rw.x); w1[j] = __uint_as_float(rw.y); w2[j] = __uint_as_float(rw.z);
+            x0[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.x * p.F));
+            x1[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.y * p.F));
+            x2[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.z * p.F));
           }
+          if (tr) trp[1] = clock64();
 #pragma unroll
           for (int j = 0; j < ITEMS; ++j) {
-            const float w0 = __uint_as_float(rw[j].x), w1 = __uint_as_float(rw[j].y),
-                        w2 = __uint_as_float(rw[j].z);
-            v[j].x = fmaf(x2[j].x, w2, fmaf(x1[j].x, w1, x0[j].x * w0));
-            v[j].y = fmaf(x2[j].y, w2, fmaf(x1[j].y, w1, x0[j].y * w0));
-            v[j].z = fmaf(x2[j].z, w2, fmaf(x1[j].z, w1, x0[j].z * w0));
-            v[j].w = fmaf(x2[j].w, w2, fmaf(x1[j].w, w1, x0[j].w * w0));
+            v[j].x = fmaf(x2[j].x, w2[j], fmaf(x1[j].x, w1[j], x0[j].x * w0[j]));
+            v[j].y = fmaf(x2[j].y, w2[j], fmaf(x1[j].y, w1[j], x0[j].y * w0[j]));
+            v[j].z = fmaf(x2[j].z, w2[j], fmaf(x1[j].z, w1[j], x0[j].z * w0[j]));
+            v[j].w = fmaf(x2[j].w, w2[j], fmaf(x1[j].w, w1[j], x0[j].w * w0[j]));
           }
         } else {
 #pragma unroll
@@ -321,7 +560,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        if (p.interp_out && !centre && tz == 0 && (CL == 2 ? (grp >> 1) == 0 : grp == 0)) {
+        if (KEEP && keep_interp && !centre) {
           // every (vertex, slot, feature) value is produced exactly once across the K splits: keep it
           float* irow = p.interp_out + (size_t)(xr * p.A + y) * p.F + fc * KC + c * 4;
 #pragma unroll
@@ -330,14 +569,14 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
             if (row < p.v_out) *reinterpret_cast<float4*>(irow + (size_t)row * RA * p.F) = v[j];
           }
         }
-        if (tr) trp[1] = clock64();
+        if (tr) trp[2] = clock64() + (__float_as_int(v[0].x) & 0);   // after the loads have landed
         ptx::mbar_wait(a_empty + 8u * my_stage, my_par);
-        if (tr) trp[2] = clock64();
+        if (tr) trp[3] = clock64();
         const uint32_t a_stage_addr = a_base + (uint32_t)(my_stage * NPROD * A_TILE_BYTES);
         uint8_t* a_hi = smem_gen + (a_stage_addr - smem_base);
-        const uint32_t a_peer = CL == 2 ? ptx::mapa(a_stage_addr, crank ^ 1u) : 0u;
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
+          if (p.debug & 12) break;   // experiments: no stores
           const int row = row_w + row_l + j * ROWS_PER_PASS;
           const uint32_t off = (uint32_t)row * ROW_BYTES + swz_chunk<KC>(row, c) * 16u;
           float4 h;
@@ -350,14 +589,16 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
             *reinterpret_cast<float4*>(a_hi + A_TILE_BYTES + off) = l;
           }
         }
-        if (!(p.debug & 8)) ptx::fence_proxy_async_smem();
+        if (tr) trp[4] = clock64();
+        ptx::fence_proxy_async_smem();   // generic-proxy stores -> async proxy (tcgen05.mma, bulk copy)
         __syncwarp();
-        if (tr) trp[3] = clock64();
+        if (tr) trp[5] = clock64();
         if (lane == 0) {
           ptx::mbar_arrive(a_full + 8u * my_stage);
           if (CL == 2) {
             // hand this warp's 32-row slab (hi, then lo) to the peer CTA with the bulk-copy engine;
             // the copy completes on the peer's a_full barrier, which also gets this warp's arrival
+            const uint32_t a_peer = ptx::mapa(a_stage_addr, crank ^ 1u);
             const uint32_t slab = (uint32_t)row_w * ROW_BYTES, slab_bytes = WARP_ROWS * ROW_BYTES;
             const uint32_t bar_peer = ptx::mapa(a_full + 8u * my_stage, crank ^ 1u);
             ptx::mbar_arrive_expect_tx_cluster(bar_peer, NPROD * slab_bytes);
@@ -366,12 +607,13 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
                                            slab_bytes, bar_peer);
           }
         }
+        if (tr) trp[6] = clock64();
       }
     }
     // ===================== drain: TMEM -> this split's partial sums =====================
     ptx::mbar_wait(acc_full, 0);
     ptx::tc_fence_after();
-    const int dq = warp & 3, dh = warp >> 2;   // TMEM lane quadrant of this warp, and which share of the rotations
+    const int dq = warp & 3, dh = warp >> 2;   // TMEM lane quadrant of this warp, and which half of the rotations
     const int row = m0 + 32 * dq + lane;       // < v_pad: the partial buffer is padded
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * dq) << 16);
     float* prow = p.partial + (((size_t)sk * p.v_pad + row) * p.n_rot + rot0) * p.T + t0;
@@ -386,106 +628,81 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       }
     }
   } else if (warp == TC_PRODUCER_WARPS) {
-    // ===================== TMA: weight tiles -> B slots =====================
+    // ===================== TMA: weight tiles -> ring =====================
+    // Weight tiles are re-loaded for the next super-step in the order in which this CTA's MMA warps
+    // release them (a tile retires at the last step at which any rotation reads it), ties in the
+    // order the next super-step needs them.  Loading in index order would park this thread on tile
+    // 0 - released at the very end of a super-step when rotations wrap - while tiles that retired
+    // steps earlier wait for their refill (traced: every weight tile arrived late, ~700 cycles per
+    // tile of exposed wait in the MMA warps).
+    uint8_t* order_smem = smem_gen + (tmem_slot + 8u - smem_base);   // [A] bytes behind the barriers
+    if (lane < p.A) {
+      int t_ret = 0, t_need = p.A;
+      for (int j = 0; j < g_cnt; ++j) {
+        int st = (lane - (p.rot.off[rot0 + j] - off_anchor)) % p.A;
+        st += st < 0 ? p.A : 0;
+        t_ret = st > t_ret ? st : t_ret;
+        t_need = st < t_need ? st : t_need;
+      }
+      const int key = (t_ret * p.A + t_need) * p.A + lane;
+      int rank = 0;
+      for (int o = 0; o < p.A; ++o) rank += __shfl_sync((1ull << p.A) - 1ull, key, o) < key ? 1 : 0;
+      order_smem[rank] = (uint8_t)lane;
+    }
+    __syncwarp();
     if (lane == 0) {
-      uint32_t loads = 0;  // bit yb = parity of the number of loads issued into slot yb
+      uint32_t loads = 0;  // bit s = parity of the number of loads issued for angular tile s
+      const uint32_t lo_ring = (uint32_t)(p.ring.n_pos * b_tile_bytes);
       int load_no = 0;
       for (int ss = ss_begin; ss < ss_end; ++ss) {
         const bool centre = ss >= p.R * p.nfc;
         const int xr = centre ? p.R : ss / p.nfc;
         const int fc = ss - xr * p.nfc;
         const int n_y = centre ? 1 : p.A;
-        for (int yb = 0; yb < n_y; ++yb) {
-          const int nl = load_no++;
-          const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && nl < 128;
-          long long* trp = tr ? p.trace + ((size_t)3 * 128 + nl) * 4 : nullptr;
+        for (int i = 0; i < n_y; ++i) {
+          const int yb = centre ? 0 : order_smem[i];
+          const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && load_no < 128;
+          long long* trp = tr ? p.trace + ((size_t)3 * 128 + load_no) * 8 : nullptr;
+          ++load_no;
           if (tr) trp[0] = clock64();
           ptx::mbar_wait(b_empty + 8u * yb, ((loads >> yb) & 1u) ^ 1u);
           if (tr) trp[1] = clock64();
           const int col = (centre ? RA * p.F : (xr * p.A + yb) * p.F) + fc * KC;
-          const uint32_t dst = b_base + (uint32_t)(yb * NPROD * b_tile_bytes);
-          ptx::mbar_arrive_expect_tx(b_full + 8u * yb, (uint32_t)(NPROD * b_tile_bytes));
-          ptx::tma_load_2d(dst, &tmap_hi, b_full + 8u * yb, col, t0);
-          if (X3) ptx::tma_load_2d(dst + b_tile_bytes, &tmap_lo, b_full + 8u * yb, col, t0);
+          const uint32_t pos = p.ring.pos[yb], dup = centre ? TC_NO_DUP : p.ring.dup[yb];
+          const uint32_t bar = b_full + 8u * (uint32_t)yb;
+          ptx::mbar_arrive_expect_tx(bar, (dup != TC_NO_DUP ? 2u : 1u) * (uint32_t)(NPROD * b_tile_bytes));
+          const uint32_t dst = b_base + pos * (uint32_t)b_tile_bytes;
+          ptx::tma_load_2d(dst, &tmap_hi, bar, col, t0);
+          if (X3) ptx::tma_load_2d(dst + lo_ring, &tmap_lo, bar, col, t0);
+          if (dup != TC_NO_DUP) {
+            const uint32_t dst2 = b_base + dup * (uint32_t)b_tile_bytes;
+            ptx::tma_load_2d(dst2, &tmap_hi, bar, col, t0);
+            if (X3) ptx::tma_load_2d(dst2 + lo_ring, &tmap_lo, bar, col, t0);
+          }
           loads ^= 1u << yb;
         }
       }
     }
   } else {
-    // ===================== MMA issuers =====================
-    // tcgen05.mma is issued by one thread, and at N = n_t <= 256 that thread's integer bookkeeping
-    // (~25 instructions per MMA) would outlast the 48-cycle MMAs.  Rotations accumulate into
-    // disjoint TMEM columns, so they are independent: MMA warp mw owns rotations mw, mw+4, ...
-    // and the issue work runs TC_MMA_WARPS-wide.  Every owner commits to the stage / slot barriers
-    // itself (a_empty counts active MMA warps, b_empty counts rotations).
-    const int mw = warp - (TC_PRODUCER_WARPS + 1);
-    if (lane == 0 && mw < g_cnt) {
-      const uint32_t idesc = ptx::make_idesc_tf32(TC_M, p.n_t);
-      const uint64_t desc_hi = ptx::make_kmajor_desc<ROW_BYTES>(0) & 0xFFFFFFFF00000000ull;
+    // ===================== MMA issuer =====================
+    if (warp == TC_PRODUCER_WARPS + 1) {
+      const int ss_nc = p.R * p.nfc;
       const uint32_t lo_flags = (uint32_t)(ptx::make_kmajor_desc<ROW_BYTES>(0) & 0xFFFF0000ull);
-      const uint32_t b_slot_lo = (uint32_t)(NPROD * b_tile_bytes) >> 4;
-      const uint32_t b_lo_half = (uint32_t)b_tile_bytes >> 4;
-      const uint32_t b_lo0 = (b_base >> 4) | lo_flags;
-      constexpr int OWN = TC_G_MAX / TC_MMA_WARPS;
-      int yb[OWN];  // rolling B slot of each owned rotation
-#pragma unroll
-      for (int q = 0; q < OWN; ++q) {   // relative to the group's first rotation (see the producers' tile order)
-        int rel = (mw + q * TC_MMA_WARPS) < g_cnt ? p.rot.off[rot0 + mw + q * TC_MMA_WARPS] - p.rot.off[rot0] : 0;
-        yb[q] = rel < 0 ? rel + p.A : rel;
-      }
-      const uint32_t all_slots = p.A >= 32 ? 0xFFFFFFFFu : ((1u << p.A) - 1u);
-      uint32_t fills = 0;     // bit s = parity of completed fills of B slot s
-      uint32_t accum = 0;     // 0 only for the very first k-step of this CTA
-      int stage = 0;          // rolling n % ns_a
-      uint32_t full_par = 0;  // (n / ns_a) & 1
-      int tile_no = 0;
-      for (int ss = ss_begin; ss < ss_end; ++ss) {
-        const bool centre = ss >= p.R * p.nfc;
-        const int n_y = centre ? 1 : p.A;
-        for (int y = 0; y < n_y; ++y) {
-          const int ntile = tile_no++;
-          const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && mw == 0 && ntile < 128;
-          long long* trp = tr ? p.trace + ((size_t)2 * 128 + ntile) * 4 : nullptr;
-          if (tr) trp[0] = clock64();
-          ptx::mbar_wait(a_full + 8u * stage, full_par);
-          if (tr) trp[1] = clock64();
-          ptx::tc_fence_after();
-          const uint32_t a_lo = ((a_base + (uint32_t)(stage * NPROD * A_TILE_BYTES)) >> 4) | lo_flags;
-#pragma unroll
-          for (int q = 0; q < OWN; ++q) {
-            const int il = mw + q * TC_MMA_WARPS;
-            if (il < g_cnt) {
-              const int s = centre ? 0 : yb[q];
-              ptx::mbar_wait(b_full + 8u * s, (fills >> s) & 1u);
-              if (tr && q == 0) trp[2] = clock64();
-              ptx::tc_fence_after();
-              const uint32_t b_lo = b_lo0 + (uint32_t)s * b_slot_lo;
-              const uint32_t d = tmem_base + (uint32_t)(il * p.n_t);
-#pragma unroll
-              for (int j = 0; j < KC / 8; ++j) {
-                const uint64_t da = desc_hi | (uint64_t)(a_lo + 2u * j);
-                const uint64_t db = desc_hi | (uint64_t)(b_lo + 2u * j);
-                if (p.debug & 2) continue;
-                ptx::umma_tf32(d, da, db, idesc, j == 0 ? accum : 1u);
-                if (X3) {
-                  ptx::umma_tf32(d, da, desc_hi | (uint64_t)(b_lo + b_lo_half + 2u * j), idesc, 1u);
-                  ptx::umma_tf32(d, desc_hi | (uint64_t)(a_lo + (A_TILE_BYTES >> 4) + 2u * j), db, idesc, 1u);
-                }
-              }
-              if (p.debug & 4) ptx::mbar_arrive(b_empty + 8u * s); else ptx::umma_commit(b_empty + 8u * s);
-              if (!centre) yb[q] = (yb[q] + 1 == p.A) ? 0 : yb[q] + 1;
-            }
-          }
-          accum = 1u;
-          if (tr) trp[3] = clock64();
-          if (CL == 2) ptx::umma_commit_mc(a_empty + 8u * stage, (uint16_t)3);
-          else if (p.debug & 4) ptx::mbar_arrive(a_empty + 8u * stage);
-          else ptx::umma_commit(a_empty + 8u * stage);
-          if (++stage == p.ns_a) { stage = 0; full_par ^= 1u; }
-        }
-        fills ^= centre ? 1u : all_slots;
-      }
-      ptx::umma_commit(acc_full);
+      TcMmaCtx c;
+      c.a_full = a_full; c.a_empty = a_empty; c.b_full = b_full; c.b_empty = b_empty; c.acc_full = acc_full;
+      c.a_lo0 = (a_base >> 4) | lo_flags;
+      c.a_stage_lo = (uint32_t)(NPROD * A_TILE_BYTES) >> 4;
+      c.b_lo0 = (b_base >> 4) | lo_flags;
+      c.b_tile_lo = (uint32_t)b_tile_bytes >> 4;
+      c.b_lo_ring = (uint32_t)(p.ring.n_pos * b_tile_bytes) >> 4;
+      c.tmem_base = tmem_base;
+      c.rot0 = rot0; c.g_cnt = g_cnt; c.n_units = n_units; c.off_anchor = off_anchor;
+      c.n_nc = min(ss_end, ss_nc) - min(ss_begin, ss_nc);
+      c.n_c = ss_end > max(ss_begin, ss_nc) ? ss_end - max(ss_begin, ss_nc) : 0;
+      if (n_units == 1) tc_mma_role<KC, X3, CL, 1>(p, c, lane);
+      else if (n_units == 2) tc_mma_role<KC, X3, CL, 2>(p, c, lane);
+      else if (n_units <= 4) tc_mma_role<KC, X3, CL, 4>(p, c, lane);
+      else tc_mma_role<KC, X3, CL, 8>(p, c, lane);
     }
   }
 
@@ -599,7 +816,7 @@ int tc_build_wcat(const float* w_eff, const float* w_self, int T, int R, int A, 
 
 bool tc_supported(int R, int A, int F, int T, int n_rot) {
   (void)R;
-  return tc_pick_config(A, F, T, n_rot, true).ok && tc_pick_config(A, F, T, n_rot, false).ok;
+  return tc_pick_config(A, F, T, n_rot, true, 0).ok && tc_pick_config(A, F, T, n_rot, false, 0).ok;
 }
 
 size_t tc_recs_bytes(int v_out, int R, int A) {
@@ -614,19 +831,25 @@ static size_t tc_partial_bytes(int v_out, int n_rot, int T, int ksplit) {
   return align_up((size_t)ksplit * v_pad * n_rot * T * sizeof(float), 256);
 }
 
+// The tiling (and with it the K-split count) depends on the rotation list, which the size query does
+// not see: take the largest requirement over every uniform step and the unmerged layout.
 size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, int precision) {
   const bool x3 = precision == GCB_PREC_TF32X3;
-  TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3);
-  if (!cfg.ok) return 0;
-  int ksplit = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3);
+  int ksplit = 0;
+  for (int dstep = 0; dstep < A; ++dstep) {
+    TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3, dstep);
+    if (!cfg.ok) return 0;
+    int s = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3);
+    if (s > ksplit) ksplit = s;
+  }
   return tc_recs_bytes(v_out, R, A) + (x3 ? 2 : 1) * tc_wcat_bytes(R, A, F, T) +
          tc_partial_bytes(v_out, n_rot, T, ksplit) + 1024;
 }
 
-template <int KC, bool X3, int CL>
-static int tc_launch_cl(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdParams& p, const TcConfig& cfg,
-                        dim3 grid, cudaStream_t st) {
-  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_conv<KC, X3, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int KC, bool X3, int CL, bool KEEP>
+static int tc_launch_k(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdParams& p, const TcConfig& cfg,
+                       dim3 grid, cudaStream_t st) {
+  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_conv<KC, X3, CL, KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)cfg.smem_bytes));
   cudaLaunchConfig_t lc{};
   lc.gridDim = grid;
@@ -641,23 +864,24 @@ static int tc_launch_cl(const CUtensorMap& mh, const CUtensorMap& ml, const TcFw
   lc.attrs = attr;
   lc.numAttrs = 1;
   profile_begin(GCB_PROF_FWD_CONV, st);
-  cudaError_t e = cudaLaunchKernelEx(&lc, k_tc_conv<KC, X3, CL>, mh, ml, p);
+  cudaError_t e = cudaLaunchKernelEx(&lc, k_tc_conv<KC, X3, CL, KEEP>, mh, ml, p);
   profile_end(GCB_PROF_FWD_CONV, st);
   GCB_CUDA_OK(e);
   GCB_LAUNCH_OK();
   return GCB_OK;
 }
 
-// pairs of rotation groups share their gathered tiles through a 2-CTA cluster when the count is even
+// Pairs of rotation groups share their gathered tiles through a 2-CTA cluster when the group count
+// is even (GCB_TC_CLUSTER=0 switches the pairing off for A/B measurements).
 template <int KC, bool X3>
 static int tc_launch(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdParams& p, const TcConfig& cfg,
                      dim3 grid, cudaStream_t st) {
-  // Measured on B200 at the FAUST shape (profiles/r01_notes.md): sharing halves the L1/L2 gather load
-  // but the kernels are bound on the MMA side (operand reads from shared memory), so the pair mode
-  // is not faster (TF32 0.536 vs 0.532 ms, 3xTF32 1.14 vs 1.08 ms).  It is kept behind a switch.
-  static const bool use_pairs = getenv("GCB_TC_CLUSTER") && atoi(getenv("GCB_TC_CLUSTER")) != 0;
-  if (use_pairs && cfg.n_groups % 2 == 0 && KC >= 16) return tc_launch_cl<KC, X3, 2>(mh, ml, p, cfg, grid, st);
-  return tc_launch_cl<KC, X3, 1>(mh, ml, p, cfg, grid, st);
+  static const bool use_pairs = !(getenv("GCB_TC_CLUSTER") && atoi(getenv("GCB_TC_CLUSTER")) == 0);
+  if (use_pairs && cfg.n_groups % 2 == 0 && KC >= 16)
+    return p.interp_out ? tc_launch_k<KC, X3, 2, true>(mh, ml, p, cfg, grid, st)
+                        : tc_launch_k<KC, X3, 2, false>(mh, ml, p, cfg, grid, st);
+  return p.interp_out ? tc_launch_k<KC, X3, 1, true>(mh, ml, p, cfg, grid, st)
+                      : tc_launch_k<KC, X3, 1, false>(mh, ml, p, cfg, grid, st);
 }
 
 int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
@@ -666,7 +890,8 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
                 void* workspace, size_t workspace_bytes, cudaStream_t st) {
   (void)v_src;
   const bool x3 = precision == GCB_PREC_TF32X3;
-  TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3);
+  static const bool no_merge = getenv("GCB_TC_NOMERGE") && atoi(getenv("GCB_TC_NOMERGE")) != 0;
+  TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3, no_merge ? 0 : tc_uniform_step(rot, n_rot, A));
   GCB_REQUIRE(cfg.ok, GCB_EUNSUPPORTED, "tc_conv_fwd: no tcgen05 tiling for A=%d F=%d T=%d", A, F, T);
   GCB_REQUIRE(workspace_bytes >= tc_fwd_workspace_bytes(v_out, R, A, F, T, n_rot, precision), GCB_EWORKSPACE,
               "tc_conv_fwd: workspace too small");
@@ -704,12 +929,14 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   p.v_out = v_out; p.v_pad = v_pad; p.R = R; p.A = A; p.F = F; p.T = T; p.n_rot = n_rot;
   p.nfc = F / cfg.kc; p.n_t = cfg.n_t; p.g = cfg.g; p.ns_a = cfg.ns_a; p.tmem_cols = cfg.tmem_cols;
   p.ksplit = ksplit;
-  p.debug = getenv("GCB_TC_DEBUG") ? atoi(getenv("GCB_TC_DEBUG")) : 0;
+  static const int debug = getenv("GCB_TC_DEBUG") ? atoi(getenv("GCB_TC_DEBUG")) : 0;
+  p.debug = debug;
+  p.ring = cfg.ring;
   p.trace = nullptr;
   static long long* trace_dev = nullptr;
-  if (getenv("GCB_TC_TRACE")) {   // debugging aid only: the one place the library touches cudaMalloc
-    if (!trace_dev) GCB_CUDA_OK(cudaMalloc(&trace_dev, 4 * 128 * 4 * sizeof(long long)));
-    GCB_CUDA_OK(cudaMemsetAsync(trace_dev, 0, 4 * 128 * 4 * sizeof(long long), st));
+  if (getenv("GCB_TC_TRACE")) {   // investigation aid only: the one place the library touches cudaMalloc
+    if (!trace_dev) GCB_CUDA_OK(cudaMalloc(&trace_dev, 4 * 128 * 8 * sizeof(long long)));
+    GCB_CUDA_OK(cudaMemsetAsync(trace_dev, 0, 4 * 128 * 8 * sizeof(long long), st));
     p.trace = trace_dev;
   }
   p.rot = rot;
@@ -723,18 +950,20 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
       partial, bias, ksplit, v_out, v_pad, n_rot, T, act, y, z, argmax);
   GCB_LAUNCH_OK();
   if (p.trace) {
-    static long long host[4 * 128 * 4];
+    static long long host[4 * 128 * 8];
     GCB_CUDA_OK(cudaMemcpyAsync(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost, st));
     GCB_CUDA_OK(cudaStreamSynchronize(st));
     long long t0 = host[0];
-    const char* names[4] = {"prod0", "prod1", "mma0", "tma"};
+    const char* names[4] = {"prod g0: start issued landed empty_ok stored fenced arrived", "prod g1",
+                            "mma: start waited done", "tma: start slot_free"};
     for (int role = 0; role < 4; ++role) {
-      fprintf(stderr, "[trace %s] tile: start  +loads  +empty_wait  +stored | (mma: wait_a, a_ready, b_ready, issued)\n", names[role]);
-      for (int n = 0; n < 40; ++n) {
-        long long* e = host + ((size_t)role * 128 + n) * 4;
+      fprintf(stderr, "[trace %s]\n", names[role]);
+      for (int n = 0; n < 48; ++n) {
+        long long* e = host + ((size_t)role * 128 + n) * 8;
         if (!e[0]) continue;
-        fprintf(stderr, "  %3d: %8lld %8lld %8lld %8lld\n", n, e[0] - t0, e[1] ? e[1] - t0 : -1, e[2] ? e[2] - t0 : -1,
-                e[3] ? e[3] - t0 : -1);
+        fprintf(stderr, "  %3d:", n);
+        for (int k = 0; k < 7; ++k) fprintf(stderr, " %8lld", e[k] ? e[k] - t0 : -1);
+        fprintf(stderr, "\n");
       }
     }
   }

@@ -4,6 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from oracle import geoconv_oracle as O
 from geoconv_b200 import _native
+if os.environ.get('GCB_LIB'):
+    _native.LIB_PATH = os.environ['GCB_LIB']
 from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
 lib = _native.load()
 v, f, r, a, t = 6890, 544, 5, 8, 96
