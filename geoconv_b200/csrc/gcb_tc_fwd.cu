@@ -7,7 +7,12 @@
 // so every operand tile is staged once and used g times.
 //
 // Kernel 1  k_tc_conv: one CTA = 128 vertices x g rotations x n_t templates x one K split.
-//   warps 0-7  producers.  Every warp fills 16 rows of EVERY tile: barycentric 3-neighbour gather
+//   warp 0     TMA: weight tiles (cp.async.bulk.tensor, hardware swizzle) into the ring.
+//   warps 1-2  MMA: one thread per warp issues tcgen05.mma kind::tf32 into the TMEM accumulators of the
+//              units it owns (g*n_t columns in total) and releases operand slots with tcgen05.commit.
+//              Two issuers because the tensor pipe queues only ~2 MMAs: while one warp is in its
+//              barrier waits / bookkeeping the other keeps the pipe fed.
+//   warps 3-10 producers.  Every warp fills its rows of the tiles its group owns: barycentric 3-neighbour gather
 //              of signal rows (float4 loads of the L2-resident signal; the packed records of the
 //              current radial ring are cached in smem), weighted sum in registers, rounded to tf32
 //              (RN), written straight into the swizzled K-major UMMA layout.  The loads of tile
@@ -15,9 +20,6 @@
 //              buffering), so a warp always has gathers in flight; measured before this change a
 //              warp's load -> combine -> store -> arrive chain (~2300 cycles) set the tile rate.
 //              At the end the producers drain TMEM to the split's partial-sum buffer.
-//   warp 8     TMA: weight tiles (cp.async.bulk.tensor, hardware swizzle) into the ring.
-//   warps 9-10 MMA: one thread per warp issues tcgen05.mma kind::tf32 into TMEM accumulators
-//              (g*n_t columns) and releases operand slots with tcgen05.commit.
 //   Merged rotations: with N = n_t = 96 an MMA reads 4 KB of A and 3 KB of B from shared memory in
 //   48 tensor cycles - 149 B/cycle against the 128 B/cycle an SM can deliver - so the unmerged
 //   kernel was shared-memory bound (3xTF32: 3060 cycles per tile measured vs 3062 predicted from
@@ -48,8 +50,14 @@ namespace gcb {
 
 constexpr int TC_M = 128;
 constexpr int TC_PRODUCER_WARPS = 8;
-constexpr int TC_MMA_WARPS = 1;
+constexpr int TC_MMA_WARPS = 2;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + TC_MMA_WARPS) * 32;
+// Warp roles.  The two control warps come FIRST: measured (clock64 traces), the warp scheduler favours
+// the oldest (lowest-numbered) ready warp, and with the producers in front the TMA warp needed
+// ~5000 cycles for ~60 instructions whenever the producers of its scheduler were busy.
+constexpr int TC_WARP_TMA = 0;
+constexpr int TC_WARP_MMA = 1;
+constexpr int TC_WARP_PROD0 = TC_WARP_MMA + TC_MMA_WARPS;
 constexpr int TC_WARP_ROWS = TC_M / TC_PRODUCER_WARPS;   // tile rows one producer warp fills
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_BAR_BYTES = 1024;
@@ -80,6 +88,7 @@ struct TcFwdParams {
   int ns_a;             // A-tile ring depth
   int tmem_cols;        // power of two >= g*n_t
   int ksplit;           // K splits (grid.z = t_chunks * ksplit)
+  int phase_shift;      // angular visiting order of super-step k starts at (k * phase_shift) % A
   long long* trace;     // GCB_TC_TRACE (investigation builds): clock64 stamps of CTA (1,0,0), [role][tile][8]
   int debug;            // GCB_TC_DEBUG bits (timing experiments only): 1 = all gathers read row 0, 2 = no MMAs
   TcRing ring;
@@ -127,6 +136,38 @@ static int tc_uniform_step(const RotTable& rot, int n_rot, int A) {
   return d;
 }
 
+// per-phase weight-tile schedules in shared memory: need / retire masks (uint32) and first / last steps (uint8)
+static size_t tc_tab_bytes(int A) { return align_up((size_t)A * A * 11 + A, 16); }
+
+// How far the angular visiting order advances from one super-step to the next.  A weight-tile slot is
+// free from its last reader in super-step k (step last_0) to its first reader in super-step k+1 (step
+// first_shift): pick the shift that maximises the smallest such gap over every rotation group, so that
+// no refill (commit -> TMA -> barrier, ~2000 cycles) lands on the critical path.
+static int tc_pick_phase_shift(const RotTable& rot, int n_rot, int A, int g, int n_groups, bool pairs) {
+  int best = 0, best_gap = -1;
+  for (int shift = 0; shift < A; ++shift) {
+    int gap = 2 * A;
+    for (int grp = 0; grp < n_groups; ++grp) {
+      const int rot0 = grp * g;
+      const int g_cnt = g < n_rot - rot0 ? g : n_rot - rot0;
+      const int anchor = rot.off[(pairs ? (grp & ~1) : grp) * g];
+      for (int sg = 0; sg < A; ++sg) {
+        int last0 = -1, first1 = A;
+        for (int j = 0; j < g_cnt; ++j) {
+          const int rel = rot.off[rot0 + j] - anchor;
+          const int st0 = ((sg - rel) % A + A) % A, st1 = ((sg - rel - shift) % A + A) % A;
+          last0 = st0 > last0 ? st0 : last0;
+          first1 = st1 < first1 ? st1 : first1;
+        }
+        const int free_steps = (A - 1 - last0) + first1;
+        gap = free_steps < gap ? free_steps : gap;
+      }
+    }
+    if (gap > best_gap) { best_gap = gap; best = shift; }
+  }
+  return best;
+}
+
 // dstep = 0: every rotation on its own (works for any rotation list)
 static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, int dstep) {
   TcConfig c{};
@@ -152,7 +193,7 @@ static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, int dste
         if (ring.n_pos >= TC_NO_DUP) continue;
         size_t b_bytes = (size_t)ring.n_pos * nprod * n_t * kc * 4;
         size_t a_stage = (size_t)nprod * TC_M * kc * 4;
-        size_t fixed = b_bytes + (size_t)A * TC_REC_BYTES + TC_BAR_BYTES + 1024 /* alignment slack */;
+        size_t fixed = b_bytes + (size_t)A * TC_REC_BYTES + TC_BAR_BYTES + tc_tab_bytes(A) + 1024 /* alignment slack */;
         if (fixed + 4 * a_stage > (size_t)TC_SMEM_LIMIT) continue;
         int ns_a = (int)(((size_t)TC_SMEM_LIMIT - fixed) / a_stage);
         if (ns_a > 8) ns_a = 8;
@@ -257,6 +298,7 @@ struct TcMmaCtx {
   uint32_t b_lo0, b_tile_lo, b_lo_ring;   // same for ring position 0, one tile, hi ring -> lo ring
   uint32_t tmem_base;
   int rot0, g_cnt, n_units, off_anchor;
+  int mw, n_mma;                // this issuing warp and how many are active: warp mw owns units mw, mw + n_mma, ...
   int n_nc, n_c;                // non-centre super-steps / centre tiles of this CTA
 };
 
@@ -267,98 +309,152 @@ struct TcMmaCtx {
 // / shuffle bookkeeping per tile around 768 cycles of MMAs (a single warp retires a dependent
 // instruction every ~8 cycles).  So this loop is kept minimal: NU (units) is a template parameter,
 // everything is warp-uniform (the whole warp runs converged, only the tcgen05 instructions sit under
-// elect.sync, so values live in uniform registers), centre tiles have their own loop, and per tile
-// there is one wait for the A stage, normally one wait for the weight tile entering the rotation
-// windows, the MMAs, one commit for the weight tile leaving the windows and one for the A stage.
+// elect.sync, so values live in uniform registers) and centre tiles have their own loop.
+//
+// Two measured stalls shape the loop (clock64 traces, FAUST shape):
+//  * the tensor pipe queues only ~2 MMAs behind the one executing, so the ~300 cycles the thread
+//    spent between the last MMA of a tile and the first of the next (commits, loop, two barrier
+//    waits) left the pipe idle ~160-300 cycles per tile.  The barrier waits of tile n+1 now sit in
+//    the MIDDLE of tile n's MMA list: they run while the first half executes, the second half and
+//    the next tile's first MMAs then issue back to back.
+//  * a weight tile can only be reloaded after its last reader; with the visiting order fixed, the
+//    tiles read at the last step of a super-step (rotation windows that wrap) were also the first
+//    ones needed by the next super-step: ~2000 cycles of exposed commit -> TMA -> barrier latency
+//    per super-step.  The visiting order now starts `phase_shift` steps later every super-step
+//    (chosen on the host so that every slot stays free for at least one step before its next use);
+//    the per-phase first/last-use tables are built once per CTA in shared memory.
+template <int KC, bool X3, int NU, int U0, int U1, int J0, int J1>
+__device__ __forceinline__ void tc_issue_range(const uint64_t desc_hi, const uint32_t a_lo, const uint32_t (&b_lo)[NU],
+                                               const uint32_t (&d_u)[NU], const uint32_t (&idesc_u)[NU],
+                                               const bool (&on)[NU], const uint32_t b_lo_ring, const uint32_t accum) {
+  constexpr int ROW_BYTES = KC * 4;
+  constexpr uint32_t A_LO_HALF = (uint32_t)(TC_M * ROW_BYTES) >> 4;   // hi tile -> lo tile of an A stage
+#pragma unroll
+  for (int u = U0; u < U1; ++u) {
+    if (on[u]) {
+#pragma unroll
+      for (int j = J0; j < J1; ++j) {
+        const uint64_t da = desc_hi | (uint64_t)(a_lo + 2u * j);
+        const uint64_t db = desc_hi | (uint64_t)(b_lo[u] + 2u * j);
+        ptx::umma_tf32(d_u[u], da, db, idesc_u[u], j == 0 ? accum : 1u);
+        if (X3) {
+          ptx::umma_tf32(d_u[u], da, desc_hi | (uint64_t)(b_lo[u] + b_lo_ring + 2u * j), idesc_u[u], 1u);
+          ptx::umma_tf32(d_u[u], desc_hi | (uint64_t)(a_lo + A_LO_HALF + 2u * j), db, idesc_u[u], 1u);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tc_wait_bits(uint32_t bar0, uint32_t bits, uint32_t parity) {
+  while (bits) {
+    ptx::mbar_wait(bar0 + 8u * (uint32_t)(__ffs((int)bits) - 1), parity);
+    bits &= bits - 1;
+  }
+}
+
 template <int KC, bool X3, int CL, int NU>
-__device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx& c, int lane) {
+__device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx& c, int lane,
+                                            const uint32_t* need_tab, const uint32_t* retire_tab) {
   constexpr int ROW_BYTES = KC * 4;
   constexpr int KS = KC / 8;
-  constexpr uint32_t A_LO_HALF = (uint32_t)(TC_M * ROW_BYTES) >> 4;   // hi tile -> lo tile of an A stage
+  constexpr uint32_t A_LO_HALF = (uint32_t)(TC_M * ROW_BYTES) >> 4;
+  // the MMA list of a tile is issued in two halves around the next tile's barrier waits
+  constexpr int U_SPLIT = NU >= 2 ? NU / 2 : NU;
+  constexpr int J_SPLIT = NU >= 2 ? KS : (KS >= 2 ? KS / 2 : KS);
   const uint64_t desc_hi = ptx::make_kmajor_desc<ROW_BYTES>(0) & 0xFFFFFFFF00000000ull;
-  const int A_ = p.A, n_t_ = p.n_t, ns_a_ = p.ns_a, m_ = p.ring.m;
+  const int A_ = p.A, n_t_ = p.n_t, ns_a_ = p.ns_a, m_ = p.ring.m, shift_ = p.phase_shift;
   const bool no_mma = (p.debug & 2) != 0;
   int sl[NU];              // angular weight tile the unit's first rotation reads at the current step
   uint32_t idesc_u[NU], d_u[NU];
   bool on[NU];
 #pragma unroll
   for (int u = 0; u < NU; ++u) {
-    on[u] = u < c.n_units;
-    const int wd = on[u] ? min(m_, c.g_cnt - u * m_) : 1;
-    int rel = on[u] ? p.rot.off[c.rot0 + u * m_] - c.off_anchor : 0;
+    const int gu = c.mw + c.n_mma * u;   // unit index in the CTA
+    on[u] = gu < c.n_units;
+    const int wd = on[u] ? min(m_, c.g_cnt - gu * m_) : 1;
+    int rel = on[u] ? p.rot.off[c.rot0 + gu * m_] - c.off_anchor : 0;
     sl[u] = rel < 0 ? rel + A_ : rel;
     idesc_u[u] = ptx::make_idesc_tf32(TC_M, wd * n_t_);
-    d_u[u] = c.tmem_base + (uint32_t)(u * m_ * n_t_);
+    d_u[u] = c.tmem_base + (uint32_t)(gu * m_ * n_t_);
   }
-  // lane yy: the weight tiles first read / last read at angular step yy of a super-step
-  uint32_t need_l = 0, retire_l = 0;
-  if (lane < A_) {
-    for (int sg = 0; sg < A_; ++sg) {
-      int first = A_, last = -1;
-      for (int j = 0; j < c.g_cnt; ++j) {
-        int st = (sg - (p.rot.off[c.rot0 + j] - c.off_anchor)) % A_;
-        st += st < 0 ? A_ : 0;
-        first = st < first ? st : first;
-        last = st > last ? st : last;
-      }
-      if (first == lane) need_l |= 1u << sg;
-      if (last == lane) retire_l |= 1u << sg;
-    }
-  }
-  const bool trace_on = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  const bool trace_on = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && c.mw == 0;
   int stage = 0;
   uint32_t par = 0, accum = 0;
-  int n = 0;
+  int n = 0, phi = 0;
+  if (c.n_nc > 0) {   // readiness of the very first tile; every later tile is waited for one tile ahead
+    ptx::mbar_wait(c.a_full, 0);
+    tc_wait_bits(c.b_full, need_tab[0], 0);
+    ptx::tc_fence_after();
+  }
   for (int k = 0; k < c.n_nc; ++k) {
     const uint32_t b_par = (uint32_t)(k & 1);   // every weight tile is filled once per super-step
+    int phi_n = phi + shift_;
+    phi_n -= phi_n >= A_ ? A_ : 0;
     for (int y = 0; y < A_; ++y, ++n) {
       long long* trp = trace_on && n < 128 ? p.trace + ((size_t)2 * 128 + n) * 8 : nullptr;
       if (trp) trp[0] = clock64();
-      uint32_t nm = __shfl_sync(0xffffffffu, need_l, y);
-      uint32_t rm = __shfl_sync(0xffffffffu, retire_l, y);
-      ptx::mbar_wait(c.a_full + 8u * stage, par);
-      while (nm) {
-        ptx::mbar_wait(c.b_full + 8u * (uint32_t)(__ffs((int)nm) - 1), b_par);
-        nm &= nm - 1;
-      }
-      ptx::tc_fence_after();
-      if (trp) trp[1] = clock64();
+      const uint32_t rm = retire_tab[phi * A_ + y];
       const uint32_t a_lo = c.a_lo0 + (uint32_t)stage * c.a_stage_lo;
       uint32_t b_lo[NU];
 #pragma unroll
       for (int u = 0; u < NU; ++u) b_lo[u] = c.b_lo0 + (uint32_t)p.ring.pos[sl[u]] * c.b_tile_lo;
+      if (!no_mma && ptx::elect_one())
+        tc_issue_range<KC, X3, NU, 0, U_SPLIT, 0, J_SPLIT>(desc_hi, a_lo, b_lo, d_u, idesc_u, on, c.b_lo_ring, accum);
+      __syncwarp();
+      // ---- readiness of the next tile, checked while the first half executes ----
+      int stage_n = stage + 1;
+      uint32_t par_n = par;
+      if (stage_n == ns_a_) { stage_n = 0; par_n ^= 1u; }
+      uint32_t defer = 0;
+      if (y + 1 < A_) {
+        ptx::mbar_wait(c.a_full + 8u * stage_n, par_n);
+        if (trp) trp[3] = clock64();
+        tc_wait_bits(c.b_full, need_tab[phi * A_ + y + 1], b_par);
+      } else if (k + 1 < c.n_nc) {
+        // first step of the next super-step: a weight tile that retires at THIS step is refilled only
+        // after the commit below - waiting for it here would deadlock, so it is waited for afterwards
+        const uint32_t nmn = need_tab[phi_n * A_];
+        defer = nmn & rm;
+        ptx::mbar_wait(c.a_full + 8u * stage_n, par_n);
+        if (trp) trp[3] = clock64();
+        tc_wait_bits(c.b_full, nmn & ~defer, b_par ^ 1u);
+      }
+      ptx::tc_fence_after();
+      if (trp) trp[1] = clock64();
       if (ptx::elect_one()) {
         if (!no_mma) {
-#pragma unroll
-          for (int u = 0; u < NU; ++u) {
-            if (on[u]) {
-#pragma unroll
-              for (int j = 0; j < KS; ++j) {
-                const uint64_t da = desc_hi | (uint64_t)(a_lo + 2u * j);
-                const uint64_t db = desc_hi | (uint64_t)(b_lo[u] + 2u * j);
-                ptx::umma_tf32(d_u[u], da, db, idesc_u[u], j == 0 ? accum : 1u);
-                if (X3) {
-                  ptx::umma_tf32(d_u[u], da, desc_hi | (uint64_t)(b_lo[u] + c.b_lo_ring + 2u * j), idesc_u[u], 1u);
-                  ptx::umma_tf32(d_u[u], desc_hi | (uint64_t)(a_lo + A_LO_HALF + 2u * j), db, idesc_u[u], 1u);
-                }
-              }
-            }
-          }
+          if (U_SPLIT < NU)
+            tc_issue_range<KC, X3, NU, U_SPLIT, NU, 0, KS>(desc_hi, a_lo, b_lo, d_u, idesc_u, on, c.b_lo_ring, accum);
+          else if (J_SPLIT < KS)
+            tc_issue_range<KC, X3, NU, 0, NU, J_SPLIT, KS>(desc_hi, a_lo, b_lo, d_u, idesc_u, on, c.b_lo_ring, accum);
         }
-        while (rm) {
-          ptx::umma_commit(c.b_empty + 8u * (uint32_t)(__ffs((int)rm) - 1));
-          rm &= rm - 1;
+        uint32_t r = rm;
+        while (r) {
+          ptx::umma_commit(c.b_empty + 8u * (uint32_t)(__ffs((int)r) - 1));
+          r &= r - 1;
         }
         if (CL == 2) ptx::umma_commit_mc(c.a_empty + 8u * stage, (uint16_t)3);
         else ptx::umma_commit(c.a_empty + 8u * stage);
       }
       __syncwarp();
+      if (defer) {
+        tc_wait_bits(c.b_full, defer, b_par ^ 1u);
+        ptx::tc_fence_after();
+      }
       if (trp) trp[2] = clock64();
       accum = 1u;
 #pragma unroll
       for (int u = 0; u < NU; ++u) sl[u] = sl[u] + 1 == A_ ? 0 : sl[u] + 1;
-      if (++stage == ns_a_) { stage = 0; par ^= 1u; }
+      stage = stage_n;
+      par = par_n;
     }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      sl[u] += shift_;
+      sl[u] -= sl[u] >= A_ ? A_ : 0;
+    }
+    phi = phi_n;
   }
   // centre tiles: X[k] * Wself - one weight tile (ring position of angular tile 0) serves every
   // rotation, one N = n_t MMA chain each
@@ -371,7 +467,7 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
     const uint32_t a_lo = c.a_lo0 + (uint32_t)stage * c.a_stage_lo;
     if (ptx::elect_one()) {
       if (!no_mma) {
-        for (int r = 0; r < c.g_cnt; ++r) {
+        for (int r = c.mw; r < c.g_cnt; r += c.n_mma) {
           const uint32_t d = c.tmem_base + (uint32_t)(r * n_t_);
 #pragma unroll
           for (int j = 0; j < KS; ++j) {
@@ -432,7 +528,17 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   const uint32_t b_empty = b_full + 8u * p.A;
   const uint32_t acc_full = b_empty + 8u * p.A;
   const uint32_t tmem_slot = acc_full + 8u;
+  const uint32_t tab_base = bar_base + TC_BAR_BYTES;   // per-phase weight-tile schedules, see below
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));     // generic view of smem_base
+  // [phase][tile]: first / last step of a super-step at which this CTA reads angular weight tile s when
+  // the visiting order starts at `phase`;  [phase][step]: bit s = tile s is first / last read at that step
+  uint32_t* need_tab = reinterpret_cast<uint32_t*>(smem_gen + (tab_base - smem_base));
+  uint32_t* retire_tab = need_tab + p.A * p.A;
+  uint8_t* first_tab = reinterpret_cast<uint8_t*>(retire_tab + p.A * p.A);
+  uint8_t* last_tab = first_tab + p.A * p.A;
+  // [phase][i]: the i-th weight tile the TMA warp (re)loads for a super-step visited at `phase` (row A:
+  // the CTA's first super-step, when every slot is free)
+  uint8_t* order_tab = last_tab + p.A * p.A;
 
   // the shuffle tells the compiler the warp index is warp-uniform (role dispatch, uniform registers)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -455,24 +561,73 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   rel0 += rel0 < 0 ? p.A : 0;
 
   const uint32_t crank = CL == 2 ? ptx::cluster_ctarank() : 0u;
-  const int mma_arrivals = CL;   // one commit per CTA of the cluster releases an A stage
-  if (warp == TC_PRODUCER_WARPS && lane == 0) {
+  // issuing warps: units are dealt round-robin to up to TC_MMA_WARPS warps (separate accumulators, so
+  // the order in which the tensor pipe interleaves their MMAs does not change any result)
+  const int n_mma = n_units < TC_MMA_WARPS ? n_units : TC_MMA_WARPS;
+  int mma_arrivals = n_mma;      // commits that release an A stage: every issuing warp of the cluster
+  if (CL == 2) {
+    const int rot0_peer = (grp ^ 1) * p.g;
+    const int units_peer = (min(p.g, p.n_rot - rot0_peer) + p.ring.m - 1) / p.ring.m;
+    mma_arrivals += units_peer < TC_MMA_WARPS ? units_peer : TC_MMA_WARPS;
+  }
+  if (warp == TC_WARP_TMA && lane == 0) {
     for (int s = 0; s < p.ns_a; ++s) {
       ptx::mbar_init(a_full + 8u * s, GRP_WARPS * CL);
       ptx::mbar_init(a_empty + 8u * s, (uint32_t)mma_arrivals);
     }
     for (int s = 0; s < p.A; ++s) {
       ptx::mbar_init(b_full + 8u * s, 1);
-      ptx::mbar_init(b_empty + 8u * s, 1);
+      ptx::mbar_init(b_empty + 8u * s, (uint32_t)n_mma);
     }
-    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(acc_full, (uint32_t)n_mma);
     ptx::fence_mbar_init();
     ptx::prefetch_tensormap(&tmap_hi);
     if (X3) ptx::prefetch_tensormap(&tmap_lo);
   }
-  if (warp == TC_PRODUCER_WARPS + 1) {
+  if (warp == TC_WARP_MMA) {
     ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.A * p.A; i += blockDim.x) {
+    const int phi = i / p.A, sg = i - phi * p.A;
+    int first = p.A, last = -1;
+    for (int j = 0; j < g_cnt; ++j) {
+      int st = (sg - (p.rot.off[rot0 + j] - off_anchor) - phi) % p.A;
+      st += st < 0 ? p.A : 0;
+      first = st < first ? st : first;
+      last = st > last ? st : last;
+    }
+    first_tab[i] = (uint8_t)first;
+    last_tab[i] = (uint8_t)last;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.A * p.A; i += blockDim.x) {
+    const int phi = i / p.A, yy = i - phi * p.A;
+    uint32_t need = 0, retire = 0;
+    for (int sg = 0; sg < p.A; ++sg) {
+      need |= first_tab[phi * p.A + sg] == yy ? 1u << sg : 0u;
+      retire |= last_tab[phi * p.A + sg] == yy ? 1u << sg : 0u;
+    }
+    need_tab[i] = need;
+    retire_tab[i] = retire;
+  }
+  // Reload order: weight tiles are re-loaded for the next super-step in the order in which the MMA warp
+  // releases them (a tile retires at the last step at which any rotation reads it - under the PREVIOUS
+  // super-step's phase), ties in the order the next super-step needs them.  Loading in index order
+  // would park the TMA thread on a tile that is released late while tiles that retired steps earlier
+  // wait for their refill.
+  for (int i = threadIdx.x; i < (p.A + 1) * p.A; i += blockDim.x) {
+    const int row = i / p.A, sg = i - row * p.A;
+    const int phi = row < p.A ? row : 0;
+    int phi_prev = phi - p.phase_shift;
+    phi_prev += phi_prev < 0 ? p.A : 0;
+    const int my_key = ((row < p.A ? last_tab[phi_prev * p.A + sg] : 0) * p.A + first_tab[phi * p.A + sg]) * p.A + sg;
+    int rank = 0;
+    for (int o = 0; o < p.A; ++o) {
+      const int key = ((row < p.A ? last_tab[phi_prev * p.A + o] : 0) * p.A + first_tab[phi * p.A + o]) * p.A + o;
+      rank += key < my_key ? 1 : 0;
+    }
+    order_tab[row * p.A + rank] = (uint8_t)sg;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -481,9 +636,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   const uint32_t tmem_base = __shfl_sync(
       0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base)), 0);
 
-  if (warp < TC_PRODUCER_WARPS) {
+  if (warp >= TC_WARP_PROD0) {
     // ===================== producers: gather + interpolate -> swizzled A tiles =====================
-    const int pg = warp / GRP_WARPS, wq = warp % GRP_WARPS;
+    const int pw = warp - TC_WARP_PROD0, ptid = (int)threadIdx.x - TC_WARP_PROD0 * 32;
+    const int pg = pw / GRP_WARPS, wq = pw % GRP_WARPS;
     const int row_w = (CL == 2 ? 64 * (int)crank : 0) + WARP_ROWS * wq;   // first tile row of this warp
     const int c = lane % CPR;
     const int row_l = lane / CPR;
@@ -491,6 +647,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     const bool keep_interp = KEEP && tz == 0 && (CL == 2 ? (grp >> 1) == 0 : grp == 0);
     int ring = -1;
     int n = 0;
+    int phi = 0;               // visiting-order phase of the current super-step
     int stage = 0;             // n % ns_a, kept as a rolling counter (no integer division per tile)
     uint32_t empty_par = 1u;   // parity to wait for on a_empty[stage]: ((n / ns_a) & 1) ^ 1
     for (int ss = ss_begin; ss < ss_end; ++ss) {
@@ -503,19 +660,20 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         producer_bar_sync();
         uint4* dst = reinterpret_cast<uint4*>(smem_gen + (rec_base - smem_base));
         for (int y = 0; y < p.A; ++y)
-          dst[y * (TC_M * 2) + threadIdx.x] =
-              __ldg(p.recs + ((size_t)(xr * p.A + y) * p.v_pad + m0) * 2 + threadIdx.x);
+          dst[y * (TC_M * 2) + ptid] =
+              __ldg(p.recs + ((size_t)(xr * p.A + y) * p.v_pad + m0) * 2 + ptid);
         producer_bar_sync();
         ring = xr;
       }
       for (int yy = 0; yy < n_y; ++yy, ++n) {
-        // Tiles are visited in the order y = yy - off[anchor rotation]: rotation j then reads weight
-        // tile (yy + off_j - off_anchor) % A, so a CTA whose first rotation has relative offset rel0
-        // needs the weight tiles in the order rel0, rel0+1, ... - the order its TMA warp loads them.
+        // Tiles are visited in the order y = yy + phase - off[anchor rotation]: rotation j then reads
+        // weight tile (yy + phase + off_j - off_anchor) % A, so a CTA whose first rotation has relative
+        // offset rel0 needs the weight tiles in the order phase+rel0, phase+rel0+1, ...
         int y = yy;
         if (!centre) {
-          y = yy - off_anchor;
+          y = yy + phi - off_anchor;
           y += y < 0 ? p.A : 0;
+          y -= y >= p.A ? p.A : 0;
         }
         const int my_stage = stage;
         const uint32_t my_par = empty_par;
@@ -609,11 +767,15 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         }
         if (tr) trp[6] = clock64();
       }
+      if (!centre) {
+        phi += p.phase_shift;
+        phi -= phi >= p.A ? p.A : 0;
+      }
     }
     // ===================== drain: TMEM -> this split's partial sums =====================
     ptx::mbar_wait(acc_full, 0);
     ptx::tc_fence_after();
-    const int dq = warp & 3, dh = warp >> 2;   // TMEM lane quadrant of this warp, and which half of the rotations
+    const int dq = warp & 3, dh = pw >> 2;   // TMEM lane quadrant of this warp (hardware: warp id % 4), and which half of the rotations
     const int row = m0 + 32 * dq + lane;       // < v_pad: the partial buffer is padded
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * dq) << 16);
     float* prow = p.partial + (((size_t)sk * p.v_pad + row) * p.n_rot + rot0) * p.T + t0;
@@ -627,40 +789,23 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
           *reinterpret_cast<uint4*>(prow + (size_t)il * p.T + c0 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
       }
     }
-  } else if (warp == TC_PRODUCER_WARPS) {
+  } else if (warp == TC_WARP_TMA) {
     // ===================== TMA: weight tiles -> ring =====================
-    // Weight tiles are re-loaded for the next super-step in the order in which this CTA's MMA warps
-    // release them (a tile retires at the last step at which any rotation reads it), ties in the
-    // order the next super-step needs them.  Loading in index order would park this thread on tile
-    // 0 - released at the very end of a super-step when rotations wrap - while tiles that retired
-    // steps earlier wait for their refill (traced: every weight tile arrived late, ~700 cycles per
-    // tile of exposed wait in the MMA warps).
-    uint8_t* order_smem = smem_gen + (tmem_slot + 8u - smem_base);   // [A] bytes behind the barriers
-    if (lane < p.A) {
-      int t_ret = 0, t_need = p.A;
-      for (int j = 0; j < g_cnt; ++j) {
-        int st = (lane - (p.rot.off[rot0 + j] - off_anchor)) % p.A;
-        st += st < 0 ? p.A : 0;
-        t_ret = st > t_ret ? st : t_ret;
-        t_need = st < t_need ? st : t_need;
-      }
-      const int key = (t_ret * p.A + t_need) * p.A + lane;
-      int rank = 0;
-      for (int o = 0; o < p.A; ++o) rank += __shfl_sync((1ull << p.A) - 1ull, key, o) < key ? 1 : 0;
-      order_smem[rank] = (uint8_t)lane;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      uint32_t loads = 0;  // bit s = parity of the number of loads issued for angular tile s
-      const uint32_t lo_ring = (uint32_t)(p.ring.n_pos * b_tile_bytes);
-      int load_no = 0;
-      for (int ss = ss_begin; ss < ss_end; ++ss) {
-        const bool centre = ss >= p.R * p.nfc;
-        const int xr = centre ? p.R : ss / p.nfc;
-        const int fc = ss - xr * p.nfc;
-        const int n_y = centre ? 1 : p.A;
+    // (reload order: order_tab, built in the prologue)
+    uint32_t loads = 0;  // bit s = parity of the number of loads issued for angular tile s
+    const uint32_t lo_ring = (uint32_t)(p.ring.n_pos * b_tile_bytes);
+    int load_no = 0;
+    int phi = 0;
+    bool first_ss = true;
+    for (int ss = ss_begin; ss < ss_end; ++ss) {
+      const bool centre = ss >= p.R * p.nfc;
+      const int xr = centre ? p.R : ss / p.nfc;
+      const int fc = ss - xr * p.nfc;
+      const int n_y = centre ? 1 : p.A;
+      const uint8_t* order = order_tab + (first_ss ? p.A : phi) * p.A;
+      if (lane == 0) {
         for (int i = 0; i < n_y; ++i) {
-          const int yb = centre ? 0 : order_smem[i];
+          const int yb = centre ? 0 : order[i];
           const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && load_no < 128;
           long long* trp = tr ? p.trace + ((size_t)3 * 128 + load_no) * 8 : nullptr;
           ++load_no;
@@ -680,12 +825,19 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
             if (X3) ptx::tma_load_2d(dst2 + lo_ring, &tmap_lo, bar, col, t0);
           }
           loads ^= 1u << yb;
+          if (tr) trp[2] = clock64();
         }
+      }
+      if (!centre) {
+        first_ss = false;
+        phi += p.phase_shift;
+        phi -= phi >= p.A ? p.A : 0;
       }
     }
   } else {
     // ===================== MMA issuer =====================
-    if (warp == TC_PRODUCER_WARPS + 1) {
+    const int mw = warp - TC_WARP_MMA;
+    if (mw < n_mma) {
       const int ss_nc = p.R * p.nfc;
       const uint32_t lo_flags = (uint32_t)(ptx::make_kmajor_desc<ROW_BYTES>(0) & 0xFFFF0000ull);
       TcMmaCtx c;
@@ -699,16 +851,18 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       c.rot0 = rot0; c.g_cnt = g_cnt; c.n_units = n_units; c.off_anchor = off_anchor;
       c.n_nc = min(ss_end, ss_nc) - min(ss_begin, ss_nc);
       c.n_c = ss_end > max(ss_begin, ss_nc) ? ss_end - max(ss_begin, ss_nc) : 0;
-      if (n_units == 1) tc_mma_role<KC, X3, CL, 1>(p, c, lane);
-      else if (n_units == 2) tc_mma_role<KC, X3, CL, 2>(p, c, lane);
-      else if (n_units <= 4) tc_mma_role<KC, X3, CL, 4>(p, c, lane);
-      else tc_mma_role<KC, X3, CL, 8>(p, c, lane);
+      c.mw = mw; c.n_mma = n_mma;
+      const int n_own = (n_units - mw + n_mma - 1) / n_mma;
+      if (n_own == 1) tc_mma_role<KC, X3, CL, 1>(p, c, lane, need_tab, retire_tab);
+      else if (n_own == 2) tc_mma_role<KC, X3, CL, 2>(p, c, lane, need_tab, retire_tab);
+      else if (n_own <= 4) tc_mma_role<KC, X3, CL, 4>(p, c, lane, need_tab, retire_tab);
+      else tc_mma_role<KC, X3, CL, 8>(p, c, lane, need_tab, retire_tab);
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == TC_PRODUCER_WARPS + 1) {
+  if (warp == TC_WARP_MMA) {
     __syncwarp();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -873,11 +1027,15 @@ static int tc_launch_k(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwd
 
 // Pairs of rotation groups share their gathered tiles through a 2-CTA cluster when the group count
 // is even (GCB_TC_CLUSTER=0 switches the pairing off for A/B measurements).
+static bool tc_use_pairs() {
+  static const bool use_pairs = !(getenv("GCB_TC_CLUSTER") && atoi(getenv("GCB_TC_CLUSTER")) == 0);
+  return use_pairs;
+}
+
 template <int KC, bool X3>
 static int tc_launch(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdParams& p, const TcConfig& cfg,
                      dim3 grid, cudaStream_t st) {
-  static const bool use_pairs = !(getenv("GCB_TC_CLUSTER") && atoi(getenv("GCB_TC_CLUSTER")) == 0);
-  if (use_pairs && cfg.n_groups % 2 == 0 && KC >= 16)
+  if (tc_use_pairs() && cfg.n_groups % 2 == 0 && KC >= 16)
     return p.interp_out ? tc_launch_k<KC, X3, 2, true>(mh, ml, p, cfg, grid, st)
                         : tc_launch_k<KC, X3, 2, false>(mh, ml, p, cfg, grid, st);
   return p.interp_out ? tc_launch_k<KC, X3, 1, true>(mh, ml, p, cfg, grid, st)
@@ -929,6 +1087,11 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   p.v_out = v_out; p.v_pad = v_pad; p.R = R; p.A = A; p.F = F; p.T = T; p.n_rot = n_rot;
   p.nfc = F / cfg.kc; p.n_t = cfg.n_t; p.g = cfg.g; p.ns_a = cfg.ns_a; p.tmem_cols = cfg.tmem_cols;
   p.ksplit = ksplit;
+  {
+    static const int shift_env = getenv("GCB_TC_PHASE") ? atoi(getenv("GCB_TC_PHASE")) : -1;   // experiments
+    const bool pairs = tc_use_pairs() && cfg.n_groups % 2 == 0 && cfg.kc >= 16;
+    p.phase_shift = shift_env >= 0 ? shift_env % A : tc_pick_phase_shift(rot, n_rot, A, cfg.g, cfg.n_groups, pairs);
+  }
   static const int debug = getenv("GCB_TC_DEBUG") ? atoi(getenv("GCB_TC_DEBUG")) : 0;
   p.debug = debug;
   p.ring = cfg.ring;
@@ -955,7 +1118,7 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
     GCB_CUDA_OK(cudaStreamSynchronize(st));
     long long t0 = host[0];
     const char* names[4] = {"prod g0: start issued landed empty_ok stored fenced arrived", "prod g1",
-                            "mma: start waited done", "tma: start slot_free"};
+                            "mma: start waited done a_full_next", "tma: start slot_free issued ss_top"};
     for (int role = 0; role < 4; ++role) {
       fprintf(stderr, "[trace %s]\n", names[role]);
       for (int n = 0; n < 48; ++n) {
