@@ -13,6 +13,10 @@ namespace gcb {
 int tc_make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_t outer,
                     uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, bool atom32 = false);
 
+// MN-major operand view of a row-major matrix (3-D map: 32-column atoms), see gcb_tc_fwd.cu
+int tc_make_tmap_mn(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                    uint32_t box_rows, uint32_t box_atoms);
+
 // slot-major packed barycentric records [R*A][v_pad][2 x uint4], v_pad = multiple of 128
 size_t tc_recs_bytes(int v_out, int R, int A);
 int tc_pack_recs(const int32_t* idx, const float* w, int v_out, int R, int A, uint4* recs, cudaStream_t st);
@@ -22,12 +26,21 @@ size_t tc_wcat_bytes(int R, int A, int F, int T);
 int tc_build_wcat(const float* w_eff, const float* w_self, int T, int R, int A, int F, float* hi, float* lo,
                   cudaStream_t st);
 
-// dSignal through G[v, rotated slot, t] and a dense tcgen05 GEMM (gcb_tc_dx.cu)
-size_t tc_dx_workspace_bytes(int v_src, int R, int A, int T, bool x3);
-int tc_dx_via_g(const float* h, const float* w, const int32_t* rot_sel, const int32_t* csr_row_ptr,
-                const int32_t* csr_entries, const float* wcat_hi, const float* wcat_lo, int v_out, int v_src,
-                int R, int A, int F, int T, bool x3, int accumulate, float* d_x, void* workspace,
-                size_t workspace_bytes, cudaStream_t st);
+// Backward through G[v, rotated slot, t] (gcb_tc_dx.cu): G is built once from the CSR inversion, then
+//   dSignal = G x [Weff | Wself]   and   d[Weff | Wself] = G^T x X   are two dense tcgen05 GEMMs.
+struct TcGLayout {
+  size_t g_bytes, xsplit_bytes, partial_bytes, total;
+  int v_pad, kg, m_pad, bn, n_ntiles, vsplit, n_kch;
+};
+TcGLayout tc_g_layout(int v_src, int R, int A, int F, int T, bool x3);
+int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int32_t* csr_row_ptr,
+               const int32_t* csr_entries, int v_out, int v_src, int R, int A, int T, bool x3, float* g_hi,
+               float* g_lo, cudaStream_t st);
+int tc_dx_from_g(const float* g_hi, const float* g_lo, const float* wcat_hi, const float* wcat_lo, int v_src, int R,
+                 int A, int F, int T, bool x3, int accumulate, float* d_x, cudaStream_t st);
+int tc_dw_from_g(const float* g_hi, const float* g_lo, const float* x, int v_src, int R, int A, int F, int T,
+                 bool x3, int accumulate, float* d_w_eff, float* d_w_self, float* x_hi, float* x_lo, float* partial,
+                 cudaStream_t st);
 
 // tensor-core backward (gcb_tc_bwd.cu)
 bool tc_bwd_supported(int R, int A, int F, int T);

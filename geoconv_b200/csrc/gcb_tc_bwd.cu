@@ -9,11 +9,9 @@
 //             (vertex) is the row index and no transpose is ever materialised.  h^T tiles come by TMA.
 //             Vertices are split over CTAs (fills the SMs, keeps accumulation chains short); partials
 //             are summed in fp32 by k_tc_dw_finish in a fixed order.
-//   k_tc_di   unrotated dI:  D[k, kk] = sum_t h[k,t] * Weff[t, kk]   (M = 128 vertices, N = 128 kk,
-//             K = templates).  Persistent CTAs, TMA-fed (h K-major, Weff rows as an MN-major operand),
-//             double-buffered TMEM accumulators, epilogue warps stream the 128x128 tile to HBM.  This
-//             stage is bound by writing V*R*A*F floats; the per-vertex rotation is applied later as an
-//             index by the CSR gather-reduce (gcb_pool.cu) that forms dSignal without atomics.
+//             This gather-fed kernel is the route taken when the caller supplies no CSR inversion of the
+//             barycentric indices; with the CSR (what the torch layer always passes) both gradients go
+//             through G (gcb_tc_dx.cu): d[Weff|Wself] = G^T X and dSignal = G [Weff|Wself], two dense GEMMs.
 #include <cuda.h>
 
 #include "gcb_common.cuh"
@@ -40,9 +38,8 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32
 
 __global__ void k_bw_transpose_h(const float* __restrict__ h, int v_out, int v_pad, int T,
                                  float* __restrict__ ht_hi, float* __restrict__ ht_lo,
-                                 float* __restrict__ h_hi, float* __restrict__ h_lo,
                                  float* __restrict__ bias_part) {
-  // ht[t][v] (v padded with zeros) for k_tc_dw;  h_hi/h_lo [v_pad][T] for k_tc_di;
+  // ht[t][v] (v padded with zeros) for k_tc_dw;
   // bias_part[blockIdx.x][t] = sum of this block's 32 rows (first stage of d_bias)
   __shared__ float tile[32][33];
   const int v0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
@@ -50,11 +47,6 @@ __global__ void k_bw_transpose_h(const float* __restrict__ h, int v_out, int v_p
     int v = v0 + i, t = t0 + threadIdx.x;
     float val = (v < v_out && t < T) ? h[(size_t)v * T + t] : 0.f;
     tile[i][threadIdx.x] = val;
-    if (t < T && v < v_pad) {
-      float hi = ptx::to_tf32(val);
-      h_hi[(size_t)v * T + t] = hi;
-      if (h_lo) h_lo[(size_t)v * T + t] = val - hi;
-    }
   }
   __syncthreads();
   if (threadIdx.y == 0 && t0 + threadIdx.x < T) {
@@ -330,7 +322,19 @@ __global__ void k_tc_dw_finish(const float* __restrict__ partial, int vsplit, in
   if (dst) *dst = accumulate ? *dst + acc : acc;
 }
 
-// d_bias[t] (+)= sum over the per-block partial sums written by k_bw_transpose_h (fixed order)
+// bias_part[b][t] = sum of h[r][t] over the rows of strip b (first stage of d_bias, fixed order)
+__global__ void k_bw_bias_partial(const float* __restrict__ h, int v_out, int T, int rows_per_block,
+                                  float* __restrict__ bias_part) {
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(v_out, r0 + rows_per_block);
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float acc = 0.f;
+    for (int r = r0; r < r1; ++r) acc += __ldg(h + (size_t)r * T + t);
+    bias_part[(size_t)blockIdx.x * T + t] = acc;
+  }
+}
+
+// d_bias[t] (+)= sum over the per-block partial sums (fixed order)
 __global__ void k_bw_bias_final(const float* __restrict__ part, int nblocks, int T, int accumulate,
                                 float* __restrict__ d_bias) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -338,156 +342,6 @@ __global__ void k_bw_bias_final(const float* __restrict__ part, int nblocks, int
   float acc = 0.f;
   for (int b = 0; b < nblocks; ++b) acc += part[(size_t)b * T + t];
   d_bias[t] = accumulate ? d_bias[t] + acc : acc;
-}
-
-// =================================================================================================
-// k_tc_di
-// =================================================================================================
-constexpr int DI_EPI_WARPS = 4;
-constexpr int DI_THREADS = (2 + DI_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int DI_BN = 128;
-constexpr int DI_STAGE_A = 16 * 1024;   // 128 vertices x 32 templates
-constexpr int DI_STAGE_B = 16 * 1024;   // 32 templates x 128 kk  (4 MN-major atoms columns)
-
-struct TcDiParams {
-  float* d_full;    // [v_out][KRA]
-  int v_out, KRA, T, n_mtiles, n_ntiles, ns;
-};
-
-template <bool X3>
-__global__ void __launch_bounds__(DI_THREADS, 1)
-k_tc_di(const __grid_constant__ CUtensorMap tmap_h_hi, const __grid_constant__ CUtensorMap tmap_h_lo,
-        const __grid_constant__ CUtensorMap tmap_w_hi, const __grid_constant__ CUtensorMap tmap_w_lo,
-        const TcDiParams p) {
-  constexpr int NPROD = X3 ? 2 : 1;
-  constexpr int STAGE_BYTES = NPROD * (DI_STAGE_A + DI_STAGE_B);
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + (uint32_t)(p.ns * STAGE_BYTES);
-  const uint32_t full = bar_base, empty = full + 8u * p.ns;
-  const uint32_t tm_full = empty + 8u * p.ns, tm_empty = tm_full + 16u;
-  const uint32_t tmem_slot = tm_empty + 16u;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = p.n_mtiles * p.n_ntiles;
-  const int n_kc = p.T / 32;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.ns; ++s) {
-      ptx::mbar_init(full + 8u * s, 1);
-      ptx::mbar_init(empty + 8u * s, 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(tm_full + 8u * b, 1);
-      ptx::mbar_init(tm_empty + 8u * b, DI_EPI_WARPS);
-    }
-    ptx::fence_mbar_init();
-    ptx::prefetch_tensormap(&tmap_h_hi);
-    ptx::prefetch_tensormap(&tmap_w_hi);
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 2 * DI_BN);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
-
-  if (warp == 0) {
-    // ============ TMA producer ============
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t par = 1u;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
-        for (int kc = 0; kc < n_kc; ++kc) {
-          ptx::mbar_wait(empty + 8u * stage, par);
-          const uint32_t a_dst = smem_base + (uint32_t)(stage * STAGE_BYTES);
-          const uint32_t b_dst = a_dst + NPROD * DI_STAGE_A;
-          ptx::mbar_arrive_expect_tx(full + 8u * stage, (uint32_t)STAGE_BYTES);
-          ptx::tma_load_2d(a_dst, &tmap_h_hi, full + 8u * stage, kc * 32, mt * 128);
-          if (X3) ptx::tma_load_2d(a_dst + DI_STAGE_A, &tmap_h_lo, full + 8u * stage, kc * 32, mt * 128);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            ptx::tma_load_2d(b_dst + j * 4096, &tmap_w_hi, full + 8u * stage, nt * DI_BN + 32 * j, kc * 32);
-            if (X3)
-              ptx::tma_load_2d(b_dst + DI_STAGE_B + j * 4096, &tmap_w_lo, full + 8u * stage, nt * DI_BN + 32 * j,
-                               kc * 32);
-          }
-          if (++stage == p.ns) { stage = 0; par ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ============ MMA issuer ============
-    if (lane == 0) {
-      // A K-major (h), B MN-major (Weff rows: kk contiguous) -> bit 16
-      const uint32_t idesc = ptx::make_idesc_tf32(128, DI_BN) | (1u << 16);
-      int stage = 0;
-      uint32_t par = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        ptx::mbar_wait(tm_empty + 8u * buf, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
-        ptx::tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(buf * DI_BN);
-        uint32_t accum = 0;
-        for (int kc = 0; kc < n_kc; ++kc) {
-          ptx::mbar_wait(full + 8u * stage, par);
-          ptx::tc_fence_after();
-          const uint32_t a_hi = smem_base + (uint32_t)(stage * STAGE_BYTES);
-          const uint32_t b_hi = a_hi + NPROD * DI_STAGE_A;
-#pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
-            const uint64_t da = ptx::make_kmajor_desc<128>(a_hi + kb * 32);
-            const uint64_t db = make_mnmajor_desc(b_hi + kb * 1024, 4096, 512);
-            ptx::umma_tf32(d, da, db, idesc, accum);
-            accum = 1u;
-            if (X3) {
-              ptx::umma_tf32(d, da, make_mnmajor_desc(b_hi + DI_STAGE_B + kb * 1024, 4096, 512), idesc, 1u);
-              ptx::umma_tf32(d, ptx::make_kmajor_desc<128>(a_hi + DI_STAGE_A + kb * 32), db, idesc, 1u);
-            }
-          }
-          ptx::umma_commit(empty + 8u * stage);
-          if (++stage == p.ns) { stage = 0; par ^= 1u; }
-        }
-        ptx::umma_commit(tm_full + 8u * buf);
-      }
-    }
-  } else {
-    // ============ epilogue: TMEM -> HBM ============
-    const int q = warp & 3;   // TMEM lane quadrant this warp may read
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
-      const int buf = it & 1;
-      ptx::mbar_wait(tm_full + 8u * buf, ((uint32_t)(it >> 1)) & 1u);
-      ptx::tc_fence_after();
-      const int row = mt * 128 + 32 * q + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * DI_BN);
-      float* out = p.d_full + (size_t)row * p.KRA + nt * DI_BN;
-      for (int c0 = 0; c0 < DI_BN; c0 += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
-        ptx::tmem_ld_wait();
-        if (row < p.v_out && nt * DI_BN + c0 < p.KRA) {
-#pragma unroll
-          for (int u = 0; u < 16; u += 4)
-            *reinterpret_cast<uint4*>(out + c0 + u) = make_uint4(r[u], r[u + 1], r[u + 2], r[u + 3]);
-        }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tm_empty + 8u * buf);
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    ptx::tmem_dealloc(tmem_base, 2 * DI_BN);
-  }
 }
 
 // =================================================================================================
@@ -512,14 +366,13 @@ static int dw_pick_nt(int T) {
 }
 
 struct BwLayout {
-  size_t recs, wcat, ht, hrow, partial, bias_part, d_full, total;
-  int v_pad, v_pad32, kcat, kcat_pad, vsplit, n_chunks, n_t;
+  size_t recs, wcat, ht, partial, bias_part, via_g, total;
+  int v_pad, kcat, kcat_pad, vsplit, n_chunks, n_t, bias_blocks, bias_rows;
 };
 
 static BwLayout bw_layout(int v_out, int v_src, int R, int A, int F, int T, bool x3) {
   BwLayout L{};
   L.v_pad = (int)ceil_div64(v_out, 128) * 128;
-  L.v_pad32 = L.v_pad;  // multiple of 128 is a multiple of 32
   L.kcat = R * A * F + F;
   L.kcat_pad = (int)ceil_div64(L.kcat, 128) * 128;
   L.n_chunks = L.v_pad / DW_VC;
@@ -538,14 +391,19 @@ static BwLayout bw_layout(int v_out, int v_src, int R, int A, int F, int T, bool
   }
   L.vsplit = best;
   const int np = x3 ? 2 : 1;
+  L.bias_rows = (int)ceil_div64(v_out, 256);
+  if (L.bias_rows < 8) L.bias_rows = 8;
+  L.bias_blocks = (int)ceil_div64(v_out, L.bias_rows);
   L.recs = tc_recs_bytes(v_out, R, A);
   L.wcat = np * tc_wcat_bytes(R, A, F, T);
   L.ht = align_up((size_t)np * T * L.v_pad * sizeof(float), 256);
-  L.hrow = align_up((size_t)np * L.v_pad * T * sizeof(float), 256);
   L.partial = align_up((size_t)L.vsplit * T * L.kcat_pad * sizeof(float), 256);
-  L.bias_part = align_up((size_t)(L.v_pad / 32) * T * sizeof(float), 256);
-  L.d_full = tc_dx_workspace_bytes(v_src, R, A, T, x3);   // the G operand of the dSignal GEMM
-  L.total = L.recs + L.wcat + L.ht + L.hrow + L.partial + L.bias_part + L.d_full + 1024;
+  const size_t bias_a = align_up((size_t)(L.v_pad / 32) * T * sizeof(float), 256);
+  const size_t bias_b = align_up((size_t)L.bias_blocks * T * sizeof(float), 256);
+  L.bias_part = bias_a > bias_b ? bias_a : bias_b;
+  L.via_g = tc_g_layout(v_src, R, A, F, T, x3).total;   // G, the split signal, the GEMM partials
+  const size_t gather_route = L.recs + L.ht + L.partial;
+  L.total = L.bias_part + L.wcat + (gather_route > L.via_g ? gather_route : L.via_g) + 1024;
   return L;
 }
 
@@ -564,88 +422,91 @@ static int launch_dw(const CUtensorMap& mh, const CUtensorMap& ml, const TcDwPar
   return GCB_OK;
 }
 
-template <bool X3>
-static int launch_di(const CUtensorMap& hh, const CUtensorMap& hl, const CUtensorMap& wh, const CUtensorMap& wl,
-                     const TcDiParams& p, int grid, size_t smem, cudaStream_t st) {
-  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_di<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  profile_begin(GCB_PROF_BWD_DI, st);
-  k_tc_di<X3><<<grid, DI_THREADS, smem, st>>>(hh, hl, wh, wl, p);
-  profile_end(GCB_PROF_BWD_DI, st);
-  GCB_LAUNCH_OK();
-  return GCB_OK;
-}
-
 int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
                 const float* h, const int32_t* rot_sel, const int32_t* csr_row_ptr, const int32_t* csr_entries,
                 int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,
                 const float* interp, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias, void* workspace,
                 size_t workspace_bytes, cudaStream_t st) {
   const bool x3 = precision == GCB_PREC_TF32X3;
-  const int np = x3 ? 2 : 1;
   BwLayout L = bw_layout(v_out, v_src, R, A, F, T, x3);
   GCB_REQUIRE(workspace_bytes >= L.total, GCB_EWORKSPACE, "tc_conv_bwd: workspace too small");
   GCB_REQUIRE((uintptr_t)x % 16 == 0, GCB_EINVAL, "tc_conv_bwd: x must be 16-byte aligned");
   const int KRA = R * A * F;
   char* ws = (char*)align_up((size_t)workspace, 256);
-  uint4* recs = (uint4*)ws; ws += L.recs;
+  float* bias_part = (float*)ws; ws += L.bias_part;
   float* wc_hi = (float*)ws;
   float* wc_lo = x3 ? (float*)(ws + L.wcat / 2) : nullptr;
   ws += L.wcat;
+  int rc;
+
+  if (csr_row_ptr && csr_entries) {
+    // ---- both gradients through G: dWcat = G^T X, dSignal = G Wcat (gcb_tc_dx.cu) ----
+    const TcGLayout GL = tc_g_layout(v_src, R, A, F, T, x3);
+    float* g_hi = (float*)ws;
+    float* g_lo = x3 ? g_hi + (size_t)GL.v_pad * GL.kg : nullptr;
+    ws += GL.g_bytes;
+    float* x_hi = (float*)ws;
+    float* x_lo = x3 ? x_hi + (size_t)v_src * F : nullptr;
+    ws += GL.xsplit_bytes;
+    float* partial = (float*)ws;
+    k_bw_bias_partial<<<(unsigned)L.bias_blocks, 128, 0, st>>>(h, v_out, T, L.bias_rows, bias_part);
+    GCB_LAUNCH_OK();
+    k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.bias_blocks, T, accumulate, d_bias);
+    GCB_LAUNCH_OK();
+    rc = tc_build_g(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, x3, g_hi, g_lo, st);
+    if (rc) return rc;
+    rc = tc_dw_from_g(g_hi, g_lo, x, v_src, R, A, F, T, x3, accumulate, d_w_eff, d_w_self, x_hi, x_lo, partial, st);
+    if (rc || !d_x) return rc;
+    rc = tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);
+    if (rc) return rc;
+    return tc_dx_from_g(g_hi, g_lo, wc_hi, wc_lo, v_src, R, A, F, T, x3, accumulate, d_x, st);
+  }
+
+  // ---- no CSR: weight gradients by the gather-fed contraction (dSignal needs the CSR) ----
+  GCB_REQUIRE(!d_x, GCB_EINVAL, "tc_conv_bwd: d_x needs the CSR inversion of the barycentric indices");
+  uint4* recs = (uint4*)ws; ws += L.recs;
   float* ht_hi = (float*)ws;
   float* ht_lo = x3 ? ht_hi + (size_t)T * L.v_pad : nullptr;
   ws += L.ht;
-  float* hr_hi = (float*)ws;
-  float* hr_lo = x3 ? hr_hi + (size_t)L.v_pad * T : nullptr;
-  ws += L.hrow;
-  float* partial = (float*)ws; ws += L.partial;
-  float* bias_part = (float*)ws; ws += L.bias_part;
-  float* d_full = (float*)ws;
-
-  int rc = tc_pack_recs(idx, w, v_out, R, A, recs, st);
+  float* partial = (float*)ws;
+  rc = tc_pack_recs(idx, w, v_out, R, A, recs, st);
   if (rc) return rc;
   {
     dim3 grid((unsigned)(L.v_pad / 32), (unsigned)ceil_div64(T, 32));
-    k_bw_transpose_h<<<grid, dim3(32, 8), 0, st>>>(h, v_out, L.v_pad, T, ht_hi, ht_lo, hr_hi, hr_lo, bias_part);
+    k_bw_transpose_h<<<grid, dim3(32, 8), 0, st>>>(h, v_out, L.v_pad, T, ht_hi, ht_lo, bias_part);
     GCB_LAUNCH_OK();
     k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.v_pad / 32, T, accumulate, d_bias);
     GCB_LAUNCH_OK();
   }
-  // ---- dW (neighbour + centre) ----
-  {
-    CUtensorMap mh, ml;
-    rc = tc_make_tmap_2d(&mh, ht_hi, (uint64_t)L.v_pad, (uint64_t)T, (uint64_t)L.v_pad * 4, 32, (uint32_t)L.n_t);
-    if (rc) return rc;
-    rc = tc_make_tmap_2d(&ml, x3 ? ht_lo : ht_hi, (uint64_t)L.v_pad, (uint64_t)T, (uint64_t)L.v_pad * 4, 32,
-                         (uint32_t)L.n_t);
-    if (rc) return rc;
-    TcDwParams p;
-    p.x = x; p.recs = recs; p.rot_sel = rot_sel; p.partial = partial; p.interp = interp;
-    p.v_out = v_out; p.v_pad = L.v_pad; p.R = R; p.A = A; p.F = F; p.T = T;
-    p.kcat = w_eff ? L.kcat : L.kcat;  // centre-only layers never reach this path
-    p.kcat_pad = L.kcat_pad; p.n_t = L.n_t; p.vsplit = L.vsplit; p.n_chunks = L.n_chunks;
-    int cols = 32;
-    while (cols < 2 * L.n_t) cols <<= 1;
-    p.tmem_cols = cols;
-    const size_t stage_bytes = (size_t)np * (DW_A_BYTES + (size_t)L.n_t * 128);
-    const size_t fixed = 1024 + ((size_t)((L.n_chunks + L.vsplit - 1) / L.vsplit + 1) * DW_VC * 4 + 16) + 512;
-    int ns = (int)((BW_SMEM_LIMIT - fixed) / stage_bytes);
-    if (ns > 8) ns = 8;
-    GCB_REQUIRE(ns >= 2, GCB_EUNSUPPORTED, "tc_conv_bwd: dW stage does not fit in shared memory");
-    p.ns = ns;
-    const size_t smem = fixed + (size_t)ns * stage_bytes;
-    dim3 grid((unsigned)(L.kcat_pad / 128), (unsigned)L.vsplit, (unsigned)(T / L.n_t));
-    rc = x3 ? launch_dw<true>(mh, ml, p, grid, smem, st) : launch_dw<false>(mh, ml, p, grid, smem, st);
-    if (rc) return rc;
-    k_tc_dw_finish<<<(unsigned)ceil_div64((int64_t)T * L.kcat, 256), 256, 0, st>>>(
-        partial, L.vsplit, T, L.kcat, L.kcat_pad, KRA, F, accumulate, d_w_eff, d_w_self);
-    GCB_LAUNCH_OK();
-  }
-  if (!d_x) return GCB_OK;
-  // ---- dSignal: G (entries regrouped by rotated slot) x weights on tensor cores (gcb_tc_dx.cu) ----
-  rc = tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);
+  CUtensorMap mh, ml;
+  rc = tc_make_tmap_2d(&mh, ht_hi, (uint64_t)L.v_pad, (uint64_t)T, (uint64_t)L.v_pad * 4, 32, (uint32_t)L.n_t);
   if (rc) return rc;
-  return tc_dx_via_g(h, w, rot_sel, csr_row_ptr, csr_entries, wc_hi, wc_lo, v_out, v_src, R, A, F, T, x3, accumulate,
-                     d_x, d_full, L.d_full, st);
+  rc = tc_make_tmap_2d(&ml, x3 ? ht_lo : ht_hi, (uint64_t)L.v_pad, (uint64_t)T, (uint64_t)L.v_pad * 4, 32,
+                       (uint32_t)L.n_t);
+  if (rc) return rc;
+  TcDwParams p;
+  p.x = x; p.recs = recs; p.rot_sel = rot_sel; p.partial = partial; p.interp = interp;
+  p.v_out = v_out; p.v_pad = L.v_pad; p.R = R; p.A = A; p.F = F; p.T = T;
+  p.kcat = L.kcat;
+  p.kcat_pad = L.kcat_pad; p.n_t = L.n_t; p.vsplit = L.vsplit; p.n_chunks = L.n_chunks;
+  int cols = 32;
+  while (cols < 2 * L.n_t) cols <<= 1;
+  p.tmem_cols = cols;
+  const int np = x3 ? 2 : 1;
+  const size_t stage_bytes = (size_t)np * (DW_A_BYTES + (size_t)L.n_t * 128);
+  const size_t fixed = 1024 + ((size_t)((L.n_chunks + L.vsplit - 1) / L.vsplit + 1) * DW_VC * 4 + 16) + 512;
+  int ns = (int)((BW_SMEM_LIMIT - fixed) / stage_bytes);
+  if (ns > 8) ns = 8;
+  GCB_REQUIRE(ns >= 2, GCB_EUNSUPPORTED, "tc_conv_bwd: dW stage does not fit in shared memory");
+  p.ns = ns;
+  const size_t smem = fixed + (size_t)ns * stage_bytes;
+  dim3 grid((unsigned)(L.kcat_pad / 128), (unsigned)L.vsplit, (unsigned)(T / L.n_t));
+  rc = x3 ? launch_dw<true>(mh, ml, p, grid, smem, st) : launch_dw<false>(mh, ml, p, grid, smem, st);
+  if (rc) return rc;
+  k_tc_dw_finish<<<(unsigned)ceil_div64((int64_t)T * L.kcat, 256), 256, 0, st>>>(
+      partial, L.vsplit, T, L.kcat, L.kcat_pad, KRA, F, accumulate, d_w_eff, d_w_self);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
 }
 
 }  // namespace gcb

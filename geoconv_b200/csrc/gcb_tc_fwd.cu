@@ -946,6 +946,25 @@ int tc_make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_
   return GCB_OK;
 }
 
+// Row-major fp32 matrix [rows][cols] seen as (32 columns, rows, cols / 32): one box = `box_atoms`
+// 32-column atoms x `box_rows` rows, written to shared memory atom after atom - the MN-major UMMA
+// operand layout (SWIZZLE_128B with 32-byte atoms) for `box_atoms * 32` rows/columns of M or N.
+int tc_make_tmap_mn(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                    uint32_t box_rows, uint32_t box_atoms) {
+  PFN_encodeTiled enc = get_encode_fn();
+  GCB_REQUIRE(enc, GCB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  GCB_REQUIRE(cols % 32 == 0, GCB_EINVAL, "tc_make_tmap_mn: cols must be a multiple of 32");
+  cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride_bytes, 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_atoms};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GCB_REQUIRE(r == CUDA_SUCCESS, GCB_ECUDA, "cuTensorMapEncodeTiled (3-D, MN-major) failed with CUresult %d", (int)r);
+  return GCB_OK;
+}
+
 static int make_weight_tmap(CUtensorMap* out, const float* base, int T, int kcat, int kc, int n_t) {
   return tc_make_tmap_2d(out, base, (uint64_t)kcat, (uint64_t)T, (uint64_t)kcat * sizeof(float), (uint32_t)kc,
                          (uint32_t)n_t);

@@ -246,7 +246,8 @@ class ConvIntrinsicFn(torch.autograd.Function):
         d_bias = torch.empty((t,), dtype=torch.float32, device=dev)
         ws_bytes = lib.gcb_conv_bwd_workspace_bytes(pack.v_out, v_src, pack.r, pack.a, f, t, ctx.precision)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        row_ptr, entries = pack.csr() if (need_dx and has_nb) else (None, None)
+        # the CSR inversion also feeds the weight gradients (dW = G^T X on tensor cores), not only dSignal
+        row_ptr, entries = pack.csr() if has_nb else (None, None)
         h = torch.empty((pack.v_out, t), dtype=torch.float32, device=dev)
         rot_sel = torch.empty((pack.v_out,), dtype=torch.int32, device=dev)
         st = _stream(x)
