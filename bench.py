@@ -55,7 +55,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).
+
+    Samples NVML from a thread every 10 ms (the timed region is ~0.1 s: `nvidia-smi -lms` starts too
+    slowly to see it); falls back to the nvidia-smi query loop if NVML is unavailable."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -64,21 +67,74 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.lines = []
+        self.samples = []          # (sm_mhz, reasons_bitmask, power_w)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = self.gpu_index
+            if visible:
+                ids = [x for x in visible.split(",") if x.strip()]
+                if self.gpu_index < len(ids) and ids[self.gpu_index].strip().isdigit():
+                    index = int(ids[self.gpu_index])
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self._nvml = (pynvml, handle)
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:  # noqa: BLE001 - fall back to the command-line tool
+            self._nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def _poll(self):
+        pynvml, handle = self._nvml
+        while not self._stop.is_set():
+            try:
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+                reasons = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                power = pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0
+                self.samples.append((mhz, reasons, power))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.01)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Samples taken from now on belong to the timed region."""
+        self.samples = []
+        self.lines = []
+
     def stop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self._nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            pynvml = self._nvml[0]
+            bits = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            sm = sorted(m for m, _r, _p in self.samples)
+            reasons = sorted(n for n in names if any(r & bits[n] for _m, r, _p in self.samples))
+            power = max((p for _m, _r, p in self.samples), default=None)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "power_w_max": power, "reasons": reasons, "source": "nvml, 10 ms period, timed region only"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -87,7 +143,6 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
@@ -102,15 +157,15 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 50"}
 
 
 def make_inputs(cfg, seed_offset=0):
     import torch
-    from oracle import geoconv_oracle as O
+    from geoconv_b200 import synthetic as S
     v, f, r, a, t = cfg["v"], cfg["f"], cfg["r"], cfg["a"], cfg["t"]
-    signal = O.make_signal(v, f, seed=1 + seed_offset, kind="shot")
-    bary = O.make_bary(v, r, a, seed=1 + seed_offset)
+    signal = S.make_signal(v, f, seed=1 + seed_offset, kind="shot")
+    bary = S.make_bary(v, r, a, seed=1 + seed_offset)
     grad_z = torch.randn((v, t), generator=torch.Generator().manual_seed(2 + seed_offset))
     return signal, bary, grad_z
 
@@ -129,14 +184,14 @@ def cpu_reference_step(cfg, weights, inputs):
 
 def run_reference(args):
     import torch
-    from oracle import geoconv_oracle as O
+    from geoconv_b200 import synthetic as S
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = S1
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    weights = O.make_weights(cfg["t"], cfg["r"], cfg["a"], cfg["f"], seed=0)
+    weights = S.make_weights(cfg["t"], cfg["r"], cfg["a"], cfg["f"], seed=0)
     inputs = make_inputs(cfg)
     for _ in range(args.warmup):
         cpu_reference_step(cfg, weights, inputs)
@@ -166,7 +221,7 @@ def run_ours(args):
     from geoconv_b200.distributed import allreduce_gradients
     from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
     from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
-    from oracle import geoconv_oracle as O
+    from geoconv_b200 import synthetic as S   # the oracle is imported by the cpu_baseline leg only
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -180,7 +235,7 @@ def run_ours(args):
     cfg = S1
     v, f, r, a, t = cfg["v"], cfg["f"], cfg["r"], cfg["a"], cfg["t"]
 
-    weights = O.make_weights(t, r, a, f, seed=0)
+    weights = S.make_weights(t, r, a, f, seed=0)
     layer = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t,
                          template_radius=cfg["radius"], activation=cfg["act"], rotation_delta=cfg["delta"],
                          precision=args.precision)
@@ -193,6 +248,8 @@ def run_ours(args):
     bary_d = bary_h.to(dev)
     gz_d = gz_h.to(dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     params = [layer._template_neighbor_weights, layer._template_self_weights, layer._bias]
 
     def step_resident():
@@ -229,11 +286,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps, warmup, profile=False):
+    def timed(step_fn, steps, warmup, profile=False, sampler=None):
         for _ in range(warmup):
             flush.zero_()
             step_fn()
         barrier()
+        if sampler is not None:
+            sampler.mark()
         if profile:
             lib.gcb_profile_enable(1)
         launches0 = lib.gcb_launch_count()
@@ -295,9 +354,7 @@ def run_ours(args):
             sys.stderr.write(f"bench: CUDA graph capture failed ({exc}); timing eager launches\n")
             torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    total_ms, launches = timed(step_value, args.steps, args.warmup)
+    total_ms, launches = timed(step_value, args.steps, args.warmup, sampler=sampler)
     if launches_per_step is not None:
         launches = launches_per_step * args.steps
     # roofline leg: the same steps launched eagerly with CUDA events around the dominant kernel
@@ -416,7 +473,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "ffma"])

@@ -66,36 +66,43 @@ static int key_bits(int32_t v_src) {
 // ---- prior folding ---------------------------------------------------------------------------
 // out[t,q,f] = sum_p in[t,p,f] * (transpose ? prior[q,p] : prior[p,q]),  p,q in [0, R*A)
 // One block = one template t and 32 consecutive features: the [RA x 32] input slab is staged in
-// smem once; warp w produces output slots q = w, w+8, ... (lanes = features, the prior element is
-// a warp-wide broadcast).  fp32 FMAs with a compensated (two-sum free) pairwise split over p.
-__global__ void __launch_bounds__(256) k_fold_prior(const float* __restrict__ in, const float* __restrict__ prior,
-                                                    float* __restrict__ out, int RA, int F, int transpose) {
-  extern __shared__ float s_mem[];
-  float* s_prior = s_mem;             // RA*RA, stored so that s_prior[q*RA + p] multiplies in[p]
-  float* s_in = s_mem + RA * RA;      // RA*32
+// smem once; warp w produces the 8 output slots q = 8w .. 8w+7 in registers (lanes = features).  Per
+// input slot p a thread reads its own value once and the 8 prior elements as two broadcast
+// 128-bit loads, so the loop runs at 8 FMAs per 3 shared-memory instructions (the first version did
+// 1 FMA per 2 and was shared-memory-issue bound at 31 us for 8.4 MB).
+__global__ void __launch_bounds__(1024) k_fold_prior(const float* __restrict__ in, const float* __restrict__ prior,
+                                                    float* __restrict__ out, int RA, int RAp, int F, int transpose) {
+  extern __shared__ float4 s_mem4[];
+  float* s_prior = reinterpret_cast<float*>(s_mem4);   // [RA][RAp]: s_prior[p*RAp + q] multiplies in[p] into out[q]
+  float* s_in = s_prior + RA * RAp;                    // [RA][32]
   const int t = blockIdx.y, f0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < RA * RA; i += blockDim.x) {
-    const int q = i / RA, p = i - q * RA;
-    s_prior[i] = transpose ? prior[q * RA + p] : prior[p * RA + q];
+  for (int i = threadIdx.x; i < RA * RAp; i += blockDim.x) {
+    const int p = i / RAp, q = i - p * RAp;
+    s_prior[i] = q < RA ? (transpose ? prior[q * RA + p] : prior[p * RA + q]) : 0.f;
   }
   for (int i = threadIdx.x; i < RA * 32; i += blockDim.x) {
     const int p = i >> 5, fl = i & 31;
     s_in[i] = (f0 + fl < F) ? in[((size_t)t * RA + p) * F + f0 + fl] : 0.f;
   }
   __syncthreads();
-  if (f0 + lane >= F) return;
-  for (int q = warp; q < RA; q += 8) {
-    const float* kq = s_prior + q * RA;
-    float a0 = 0.f, a1 = 0.f;
-    int p = 0;
-    for (; p + 1 < RA; p += 2) {
-      a0 = fmaf(s_in[p * 32 + lane], kq[p], a0);
-      a1 = fmaf(s_in[(p + 1) * 32 + lane], kq[p + 1], a1);
-    }
-    if (p < RA) a0 = fmaf(s_in[p * 32 + lane], kq[p], a0);
-    out[((size_t)t * RA + q) * F + f0 + lane] = a0 + a1;
+  const int q0 = warp * 8;
+  if (q0 >= RA || f0 + lane >= F) return;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int p = 0; p < RA; ++p) {
+    const float x = s_in[p * 32 + lane];
+    const float4 k0 = *reinterpret_cast<const float4*>(s_prior + p * RAp + q0);
+    const float4 k1 = *reinterpret_cast<const float4*>(s_prior + p * RAp + q0 + 4);
+    acc[0] = fmaf(x, k0.x, acc[0]); acc[1] = fmaf(x, k0.y, acc[1]);
+    acc[2] = fmaf(x, k0.z, acc[2]); acc[3] = fmaf(x, k0.w, acc[3]);
+    acc[4] = fmaf(x, k1.x, acc[4]); acc[5] = fmaf(x, k1.y, acc[5]);
+    acc[6] = fmaf(x, k1.z, acc[6]); acc[7] = fmaf(x, k1.w, acc[7]);
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (q0 + j < RA) out[((size_t)t * RA + q0 + j) * F + f0 + lane] = acc[j];
 }
 
 __global__ void k_pack_rows(const float* __restrict__ src, const int32_t* __restrict__ rows,
@@ -163,12 +170,13 @@ extern "C" int gcb_fold_prior(const float* in, const float* prior, float* out, i
   GCB_REQUIRE(in && prior && out, GCB_EINVAL, "gcb_fold_prior: null pointer");
   GCB_REQUIRE(T > 0 && R > 0 && A > 0 && F > 0, GCB_EINVAL, "gcb_fold_prior: bad sizes");
   int RA = R * A;
-  size_t smem = ((size_t)RA * RA + (size_t)RA * 32) * sizeof(float);
-  GCB_REQUIRE(smem <= 160 * 1024, GCB_EUNSUPPORTED, "gcb_fold_prior: R*A=%d too large", RA);
+  const int RAp = (RA + 7) / 8 * 8;
+  size_t smem = ((size_t)RA * RAp + (size_t)RA * 32) * sizeof(float);
+  GCB_REQUIRE(smem <= 160 * 1024 && RAp / 8 <= 32, GCB_EUNSUPPORTED, "gcb_fold_prior: R*A=%d too large", RA);
   if (smem > 48 * 1024)
     GCB_CUDA_OK(cudaFuncSetAttribute(k_fold_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div64(F, 32), (unsigned)T);
-  k_fold_prior<<<grid, 256, smem, (cudaStream_t)stream>>>(in, prior, out, RA, F, transpose);
+  k_fold_prior<<<grid, (unsigned)(RAp / 8 * 32), smem, (cudaStream_t)stream>>>(in, prior, out, RA, RAp, F, transpose);
   GCB_LAUNCH_OK();
   return GCB_OK;
 }

@@ -322,15 +322,24 @@ __global__ void k_tc_dw_finish(const float* __restrict__ partial, int vsplit, in
   if (dst) *dst = accumulate ? *dst + acc : acc;
 }
 
-// bias_part[b][t] = sum of h[r][t] over the rows of strip b (first stage of d_bias, fixed order)
+// bias_part[b][t] = sum of h[r][t] over the rows of strip b (first stage of d_bias, fixed order):
+// 8 row lanes per column stride through the strip, then a fixed-order sum over the lanes
 __global__ void k_bw_bias_partial(const float* __restrict__ h, int v_out, int T, int rows_per_block,
                                   float* __restrict__ bias_part) {
+  __shared__ float s_part[8][33];
+  const int t = blockIdx.y * 32 + threadIdx.x;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(v_out, r0 + rows_per_block);
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    float acc = 0.f;
-    for (int r = r0; r < r1; ++r) acc += __ldg(h + (size_t)r * T + t);
-    bias_part[(size_t)blockIdx.x * T + t] = acc;
+  float acc = 0.f;
+  if (t < T)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += __ldg(h + (size_t)r * T + t);
+  s_part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && t < T) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += s_part[i][threadIdx.x];
+    bias_part[(size_t)blockIdx.x * T + t] = sum;
   }
 }
 
@@ -391,7 +400,7 @@ static BwLayout bw_layout(int v_out, int v_src, int R, int A, int F, int T, bool
   }
   L.vsplit = best;
   const int np = x3 ? 2 : 1;
-  L.bias_rows = (int)ceil_div64(v_out, 256);
+  L.bias_rows = (int)ceil_div64(v_out, 48);
   if (L.bias_rows < 8) L.bias_rows = 8;
   L.bias_blocks = (int)ceil_div64(v_out, L.bias_rows);
   L.recs = tc_recs_bytes(v_out, R, A);
@@ -449,7 +458,8 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     float* x_lo = x3 ? x_hi + (size_t)v_src * F : nullptr;
     ws += GL.xsplit_bytes;
     float* partial = (float*)ws;
-    k_bw_bias_partial<<<(unsigned)L.bias_blocks, 128, 0, st>>>(h, v_out, T, L.bias_rows, bias_part);
+    k_bw_bias_partial<<<dim3((unsigned)L.bias_blocks, (unsigned)ceil_div64(T, 32)), dim3(32, 8), 0, st>>>(
+        h, v_out, T, L.bias_rows, bias_part);
     GCB_LAUNCH_OK();
     k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.bias_blocks, T, accumulate, d_bias);
     GCB_LAUNCH_OK();

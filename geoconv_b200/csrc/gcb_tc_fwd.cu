@@ -212,21 +212,27 @@ static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, int dste
   return c;
 }
 
-// K-split count: enough to keep 3xTF32 accumulation chains short, then tuned so the grid fills
-// whole waves of 148 SMs.
-static int tc_pick_ksplit(const TcConfig& cfg, int v_out, int R, int A, int F, int T, bool x3) {
+// K-split count: enough to keep 3xTF32 accumulation chains short, then the split that minimises a
+// simple time model: whole waves of 148 CTAs, each paying its share of the tile MMAs plus a fixed
+// prologue/drain, plus the partial-sum traffic every extra split adds (written by this kernel, read back
+// by k_tc_finish).
+static int tc_pick_ksplit(const TcConfig& cfg, int v_out, int R, int A, int F, int T, bool x3, int n_rot) {
   const int n_ss = (R + 1) * (F / cfg.kc);
   const int64_t units = ceil_div64(v_out, TC_M) * cfg.n_groups * (T / cfg.n_t);
   int s_min = 1;
   if (x3) s_min = (int)ceil_div64((int64_t)(R * A + 1) * F, TC_X3_CHAIN_K);
   if (s_min > n_ss) s_min = n_ss;
   if (units >= 148 * 6) return s_min;
+  const double tile_cycles = (double)(cfg.kc / 8) * (x3 ? 3 : 1) * cfg.g * cfg.n_t / 2.0;   // MMA time of one tile
+  const double work = (double)R * (F / cfg.kc) * A * tile_cycles * 1.15;                     // whole K range of one unit
+  const double cta_fixed = 9000.0;                                                           // prologue + first loads + drain
+  const double split_cost = 2.0 * (double)ceil_div64(v_out, TC_M) * TC_M * n_rot * T * 4.0 / 6.5e12 * 1.7e9;
   int best = s_min;
-  double best_eff = -1.0;
-  for (int s = s_min; s <= s_min + 8 && s <= n_ss; ++s) {
-    int64_t ctas = units * s;
-    double eff = (double)ctas / (double)(ceil_div64(ctas, 148) * 148);
-    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  double best_t = 0.0;
+  for (int s = s_min; s <= s_min + 12 && s <= n_ss; ++s) {
+    const double waves = (double)ceil_div64(units * s, 148);
+    const double t = waves * (work / s + cta_fixed) + s * split_cost;
+    if (s == s_min || t < best_t) { best_t = t; best = s; }
   }
   return best;
 }
@@ -1012,7 +1018,7 @@ size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, 
   for (int dstep = 0; dstep < A; ++dstep) {
     TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3, dstep);
     if (!cfg.ok) return 0;
-    int s = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3);
+    int s = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3, n_rot);
     if (s > ksplit) ksplit = s;
   }
   return tc_recs_bytes(v_out, R, A) + (x3 ? 2 : 1) * tc_wcat_bytes(R, A, F, T) +
@@ -1075,7 +1081,7 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   GCB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)bias % 16 == 0) &&
                   ((uintptr_t)z % 16 == 0),
               GCB_EINVAL, "tc_conv_fwd: x, y, z and bias must be 16-byte aligned");
-  const int ksplit = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3);
+  const int ksplit = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3, n_rot);
   const int RA = R * A, KRA = RA * F, kcat = KRA + F;
   const int m_tiles = (int)ceil_div64(v_out, TC_M);
   const int v_pad = m_tiles * TC_M;
