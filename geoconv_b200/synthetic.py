@@ -52,3 +52,19 @@ def xavier_uniform(shape, gen):
 def make_weights(t, r, a, f, seed=0):
     g = torch.Generator().manual_seed(seed)
     return (xavier_uniform((t, r, a, f), g), xavier_uniform((t, 1, f), g), xavier_uniform((1, t), g))
+
+
+def make_bary_local(v, r, a, window=512, seed=1, fallback_frac=0.02, dtype=torch.float32):
+    """Barycentric tensor of a mesh whose vertex order preserves locality: the three
+    indices of every template vertex lie within `window` rows of the vertex itself (wrapping around),
+    so a row-partitioned mesh only needs a thin halo."""
+    g = torch.Generator().manual_seed(seed)
+    own = torch.arange(v).view(v, 1, 1, 1)
+    idx = (own + torch.randint(-window, window + 1, (v, r, a, 3), generator=g)) % v
+    w = torch.rand((v, r, a, 3), generator=g)
+    w = w / w.sum(dim=-1, keepdim=True)
+    if fallback_frac > 0:
+        dead = torch.rand((v, r, a), generator=g) < fallback_frac
+        idx[dead] = 0
+        w[dead] = 0.0
+    return torch.stack([idx.to(dtype), w.to(dtype)], dim=-1)
