@@ -29,6 +29,48 @@ __global__ void k_amp_fwd(const float* __restrict__ y, int v, int n_rot, int T,
   if (lane == 0) argmax[warp] = arg;
 }
 
+// AngularMinPooling / AngularAvgPooling on a materialised Y (mode GCB_POOL_MIN / GCB_POOL_AVG); one warp per vertex
+__global__ void k_apool_fwd(const float* __restrict__ y, int v, int n_rot, int T, int mode,
+                            float* __restrict__ z, int32_t* __restrict__ arg_out) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= v) return;
+  const float* row = y + (size_t)warp * n_rot * T;
+  if (mode == GCB_POOL_AVG) {
+    for (int t = lane; t < T; t += 32) {
+      float acc = 0.f;
+      for (int i = 0; i < n_rot; ++i) acc += row[(size_t)i * T + t];   // rotation order, like torch.mean's reduction
+      z[(size_t)warp * T + t] = acc / (float)n_rot;
+    }
+    return;
+  }
+  float best = 0.f;
+  int arg = 0;
+  for (int i = 0; i < n_rot; ++i) {
+    float s = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      float e = row[(size_t)i * T + t];
+      s = fmaf(e, e, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    float nrm = sqrtf(s);
+    const bool better = mode == GCB_POOL_MIN ? nrm < best : nrm > best;
+    if (i == 0 || better) { best = nrm; arg = i; }
+  }
+  for (int t = lane; t < T; t += 32) z[(size_t)warp * T + t] = row[(size_t)arg * T + t];
+  if (lane == 0 && arg_out) arg_out[warp] = arg;
+}
+
+__global__ void k_aavg_bwd(const float* __restrict__ gz, int64_t n /* v*n_rot*T */, int n_rot, int T,
+                           float* __restrict__ gy) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  int t = (int)(e % T);
+  int64_t k = e / T / n_rot;
+  gy[e] = gz[k * T + t] / (float)n_rot;
+}
+
 // autograd of the row select: dY[k,i,:] = (i == argmax[k]) ? dZ[k,:] : 0
 __global__ void k_amp_bwd(const float* __restrict__ gz, const int32_t* __restrict__ argmax,
                           int64_t n /* v*n_rot*T */, int n_rot, int T, float* __restrict__ gy) {
@@ -193,6 +235,39 @@ extern "C" int gcb_amp_bwd(const float* grad_z, const int32_t* argmax, int32_t v
   int64_t n = (int64_t)v * n_rot * T;
   if (n <= 0) return GCB_OK;
   k_amp_bwd<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(grad_z, argmax, n, n_rot, T, grad_y);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+extern "C" int gcb_apool_fwd(const float* y, int32_t v, int32_t n_rot, int32_t T, int mode, float* z,
+                             int32_t* arg, void* stream) {
+  GCB_REQUIRE(y && z, GCB_EINVAL, "gcb_apool_fwd: null pointer");
+  GCB_REQUIRE(v >= 0 && n_rot > 0 && T > 0, GCB_EINVAL, "gcb_apool_fwd: bad sizes");
+  GCB_REQUIRE(mode == GCB_POOL_MAX || mode == GCB_POOL_MIN || mode == GCB_POOL_AVG, GCB_EINVAL,
+              "gcb_apool_fwd: unknown pooling mode %d", mode);
+  GCB_REQUIRE(mode == GCB_POOL_AVG || arg, GCB_EINVAL, "gcb_apool_fwd: max / min pooling needs the index output");
+  if (v == 0) return GCB_OK;
+  if (mode == GCB_POOL_MAX) return amp_fwd(y, v, n_rot, T, z, arg, (cudaStream_t)stream);
+  const int warps_per_block = 8;
+  k_apool_fwd<<<(unsigned)ceil_div64(v, warps_per_block), warps_per_block * 32, 0, (cudaStream_t)stream>>>(
+      y, v, n_rot, T, mode, z, arg);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+extern "C" int gcb_apool_bwd(const float* grad_z, const int32_t* arg, int32_t v, int32_t n_rot, int32_t T,
+                             int mode, float* grad_y, void* stream) {
+  GCB_REQUIRE(grad_z && grad_y, GCB_EINVAL, "gcb_apool_bwd: null pointer");
+  GCB_REQUIRE(mode == GCB_POOL_MAX || mode == GCB_POOL_MIN || mode == GCB_POOL_AVG, GCB_EINVAL,
+              "gcb_apool_bwd: unknown pooling mode %d", mode);
+  int64_t n = (int64_t)v * n_rot * T;
+  if (n <= 0) return GCB_OK;
+  if (mode == GCB_POOL_AVG) {
+    k_aavg_bwd<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(grad_z, n, n_rot, T, grad_y);
+  } else {
+    GCB_REQUIRE(arg, GCB_EINVAL, "gcb_apool_bwd: max / min pooling needs the selected indices");
+    k_amp_bwd<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(grad_z, arg, n, n_rot, T, grad_y);
+  }
   GCB_LAUNCH_OK();
   return GCB_OK;
 }

@@ -320,6 +320,42 @@ class AngularMaxPoolFn(torch.autograd.Function):
         return gy
 
 
+POOL_MAX, POOL_MIN, POOL_AVG = 0, 1, 2
+
+
+class AngularPoolFn(torch.autograd.Function):
+    """Angular max / min / average pooling of a materialised (V, n_rot, T) tensor."""
+
+    @staticmethod
+    def forward(ctx, y, mode):
+        lib = N.load()
+        _need_cuda(y, "inputs")
+        yc = y.contiguous().to(torch.float32)
+        v, n_rot, t = yc.shape
+        z = torch.empty((v, t), dtype=torch.float32, device=yc.device)
+        arg = torch.empty((v,), dtype=torch.int32, device=yc.device)
+        with torch.cuda.device(yc.device):
+            N.check(lib.gcb_apool_fwd(yc.data_ptr(), v, n_rot, t, mode, z.data_ptr(), arg.data_ptr(), _stream(yc)),
+                    "gcb_apool_fwd")
+        ctx.save_for_backward(arg)
+        ctx.shape = (v, n_rot, t)
+        ctx.mode = mode
+        ctx.mark_non_differentiable(arg)
+        return z, arg
+
+    @staticmethod
+    def backward(ctx, grad_z, _):
+        lib = N.load()
+        (arg,) = ctx.saved_tensors
+        v, n_rot, t = ctx.shape
+        gz = grad_z.contiguous().to(torch.float32)
+        gy = torch.empty((v, n_rot, t), dtype=torch.float32, device=gz.device)
+        with torch.cuda.device(gz.device):
+            N.check(lib.gcb_apool_bwd(gz.data_ptr(), arg.data_ptr(), v, n_rot, t, ctx.mode, gy.data_ptr(),
+                                      _stream(gz)), "gcb_apool_bwd")
+        return gy, None
+
+
 def pack_rows(src: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
     """out[i] = src[rows[i]] (halo send-buffer packing)."""
     lib = N.load()

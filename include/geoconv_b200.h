@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GCB_ABI_VERSION 2
+#define GCB_ABI_VERSION 3
 #define GCB_MAX_ROT 32
 
 /* error codes */
@@ -119,6 +119,18 @@ int gcb_amp_fwd(const float* y, int32_t v, int32_t n_rot, int32_t T, float* z, i
                 void* stream);
 int gcb_amp_bwd(const float* grad_z, const int32_t* argmax, int32_t v, int32_t n_rot, int32_t T,
                 float* grad_y, void* stream);
+
+/* ---- AngularMinPooling / AngularAvgPooling (and max again) on a materialised Y ---------------
+ * Replaces angular_min_pooling.py:27-29 (argmin of the row norms, first minimum wins) and
+ * angular_avg_pooling.py:27 (mean over rotations) with their autograd.  `arg` may be NULL for
+ * GCB_POOL_AVG.                                                                                */
+#define GCB_POOL_MAX 0
+#define GCB_POOL_MIN 1
+#define GCB_POOL_AVG 2
+int gcb_apool_fwd(const float* y, int32_t v, int32_t n_rot, int32_t T, int mode, float* z, int32_t* arg,
+                  void* stream);
+int gcb_apool_bwd(const float* grad_z, const int32_t* arg, int32_t v, int32_t n_rot, int32_t T, int mode,
+                  float* grad_y, void* stream);
 
 /* h = grad * act'(.) with act' written in terms of the activation OUTPUT `out` (n elements). */
 int gcb_act_grad(const float* grad, const float* out, int64_t n, int act, float* h, void* stream);

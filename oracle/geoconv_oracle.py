@@ -126,7 +126,71 @@ def zero_prior(template: np.ndarray) -> np.ndarray:
     return np.zeros((r, a, r, a), dtype=np.float64)
 
 
-PRIORS = {"geodesic": geodesic_prior, "dirac": dirac_prior, "zero": zero_prior}
+def _softmax_over_template(pdf: np.ndarray) -> np.ndarray:
+    flat = pdf.reshape(pdf.shape[0], pdf.shape[1], -1)
+    flat = flat - flat.max(axis=-1, keepdims=True)
+    e = np.exp(flat)
+    return (e / e.sum(axis=-1, keepdims=True)).reshape(pdf.shape)
+
+
+def _polar_distances(template: np.ndarray):
+    """|rho - mean_rho| and the wrap-around angular distance for every (mean, point) pair, after the
+    in-place radial normalisation the three priors below apply (conv_exp.py:47, conv_chi_squared.py:79,
+    conv_student_t.py:75: template_matrix[:, :, 0] /= max)."""
+    rho = template[:, :, 0] / template[:, :, 0].max()
+    theta = template[:, :, 1]
+    d_rho = np.abs(rho[None, None, :, :] - rho[:, :, None, None])
+    hi = np.maximum(theta[:, :, None, None], theta[None, None, :, :])
+    lo = np.minimum(theta[:, :, None, None], theta[None, None, :, :])
+    return d_rho, np.minimum(hi - lo, lo + 2.0 * np.pi - hi)
+
+
+def exp_prior(template: np.ndarray, exp_lambda=1) -> np.ndarray:
+    """conv_exp.py:8-38, 41-62: lambda^2 * exp(-lambda * (d_rho + d_theta)), soft-maxed per (r, a)."""
+    d_rho, d_theta = _polar_distances(template)
+    return _softmax_over_template(exp_lambda ** 2 * np.exp(-exp_lambda * (d_rho + d_theta)))
+
+
+def _chi_gamma(dof):
+    """The reference's own recursion (conv_chi_squared.py:8-28) - not the Gamma function, kept as is."""
+    r = dof / 2
+    if dof == 1 / 2:
+        return np.sqrt(np.pi)
+    if dof == 1:
+        return 1.0
+    return r * _chi_gamma(dof - 1)
+
+
+def chi_squared_prior(template: np.ndarray, dof=2) -> np.ndarray:
+    """conv_chi_squared.py:31-70, 73-94, including its dof == 1 special cases (weight 1 at zero distance)."""
+    d_rho, d_theta = _polar_distances(template)
+    gamma = (1 / (2 ** (dof / 2) * _chi_gamma(dof))) ** 2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        pdf = gamma * d_rho ** (dof / 2 - 1) * d_theta ** (dof / 2 - 1) * np.exp(-(d_rho + d_theta) / 2)
+    if dof == 1:
+        pdf = np.where((d_theta == 0) | (d_rho == 0), 1.0, pdf)
+    return _softmax_over_template(pdf)
+
+
+def _student_gamma(x):
+    """conv_student_t.py:9-27 (factorial based; np.math there is math)."""
+    n = math.floor(x)
+    if x - n == 1 / 2:
+        return (math.factorial(2 * n) / (math.factorial(n) * 4 ** n)) * np.sqrt(np.pi)
+    return math.factorial(n)
+
+
+def student_t_prior(template: np.ndarray, dof=2) -> np.ndarray:
+    """conv_student_t.py:30-65, 68-89."""
+    d_rho, d_theta = _polar_distances(template)
+    t_theta = (1 + d_theta ** 2 / dof) ** (-(dof + 1) / 2)
+    t_rho = (1 + d_rho ** 2 / dof) ** (-(dof + 1) / 2)
+    quotient = (_student_gamma((dof + 1) / 2) / (np.sqrt(dof * np.pi) * _student_gamma(dof / 2))) ** 2
+    return _softmax_over_template(quotient * t_rho * t_theta)
+
+
+PRIORS = {"geodesic": geodesic_prior, "dirac": dirac_prior, "zero": zero_prior, "exp": exp_prior,
+          "chi_squared": chi_squared_prior, "student_t": student_t_prior}
 
 
 def rotation_offsets(n_angular: int, rotation_delta: int) -> list[int]:
@@ -186,6 +250,18 @@ def amp_forward(y: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     norms = torch.linalg.vector_norm(y, ord=2, dim=-1)
     arg = torch.argmax(norms, dim=1)
     return y[torch.arange(y.shape[0]), arg], arg.to(torch.int32)
+
+
+def amin_forward(y: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """AngularMinPooling.forward (angular_min_pooling.py:27-29): smallest norm, first minimum wins."""
+    norms = torch.linalg.vector_norm(y, ord=2, dim=-1)
+    arg = torch.argmin(norms, dim=1)
+    return y[torch.arange(y.shape[0]), arg], arg.to(torch.int32)
+
+
+def aavg_forward(y: torch.Tensor) -> torch.Tensor:
+    """AngularAvgPooling.forward (angular_avg_pooling.py:27)."""
+    return torch.mean(y, dim=1)
 
 
 def conv_amp_forward(signal, bary, w_neighbor, w_self, bias, prior, act="relu", rotation_delta=1):

@@ -8,8 +8,17 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_cases():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+NEXT_PREFIXES = ("exp", "chi", "student")   # fixtures of the SURVEY.md §8(f-4) rows (other priors / poolings)
+
+
+def golden_cases(which="path"):
+    """Fixture names: "path" = the hot path's own layers (geodesic / dirac / zero), "next" = the §8(f-4)
+    rows, "all" = both."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    is_next = lambda n: n.split("_")[0] in NEXT_PREFIXES  # noqa: E731
+    if which == "all":
+        return names
+    return [n for n in names if is_next(n) == (which == "next")]
 
 
 def load_golden(name):

@@ -6,7 +6,7 @@ import torch
 from oracle import geoconv_oracle as O
 from tests.helpers import TOL_FP32, golden_cases, load_golden, nerr
 
-CASES = golden_cases()
+CASES = golden_cases("all")
 
 
 def _prior(g):
@@ -25,10 +25,11 @@ def test_template_and_prior(name):
     radius = g["template"][-1, 0, 0].item()
     tm = O.template_matrix(r, a, radius)
     np.testing.assert_allclose(tm, g["template"].numpy(), rtol=0, atol=1e-15)
-    prior = O.PRIORS[g["kind"]](tm).astype(np.float32)
+    args = (g["prior_param"],) if "prior_param" in g else ()   # exp_lambda / dof of the parametrised priors
+    prior = O.PRIORS[g["kind"]](tm, *args).astype(np.float32)
     np.testing.assert_allclose(prior, g["prior"].numpy(), rtol=0, atol=1e-7)
     if g["kind"] != "dirac":
-        assert O.prior_is_rotation_symmetric(O.PRIORS[g["kind"]](tm), g["delta"])
+        assert O.prior_is_rotation_symmetric(O.PRIORS[g["kind"]](tm, *args), g["delta"])
 
 
 @pytest.mark.parametrize("name", CASES)
