@@ -424,10 +424,20 @@ def run_ours(args):
     tf32_peak = peaks["bf16_tflops"] / 2.0
     k_ms, k_cnt = prof["fwd_conv"]
     achieved = (fwd_flops * k_cnt / (k_ms * 1e-3)) / 1e12 if k_ms > 0 and k_cnt else None
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):      # DRAM bytes of one launch, from the committed ncu --set full capture
+        with open(tpath) as fh:
+            rec = json.load(fh).get(args.precision)
+        if rec:
+            traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+            traffic_src = rec["source"]
     roofline = {
         "bound": "tensor", "kernel": "k_tc_conv (forward gather+tcgen05 contraction)",
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-        "frac": (achieved / tf32_peak) if achieved else None, "traffic": None,
+        "frac": (achieved / tf32_peak) if achieved else None, "traffic": traffic,
+        "traffic_unit": "bytes of DRAM read+write per launch (ncu)", "traffic_source": traffic_src,
+        "algorithmic_bytes_per_launch": 4 * (v * f + 6 * v * r * a + t * (r * a * f + f) + t + v * t) + 4 * v,
         "peak_source": f"{peaks['source']} bf16_tflops/2 (TF32 dense peak is derived, not measured)",
         "algorithmic_flops_per_launch": fwd_flops, "kernel_ms_avg": (k_ms / k_cnt) if k_cnt else None,
         "note": ("fp32 mode runs 3 tf32 MMAs per product (3xTF32): its ceiling against this peak is 1/3"
