@@ -1,5 +1,6 @@
 """Drop-in for ``geoconv.pytorch.layers.angular_max_pooling.AngularMaxPooling``
 (/root/reference/src/geoconv/pytorch/layers/angular_max_pooling.py:6-29)."""
+import torch
 from torch import nn
 
 from geoconv_b200 import ops
@@ -9,6 +10,7 @@ class AngularMaxPooling(nn.Module):
     """Per vertex, keep the rotation whose template-response vector has the largest Euclidean norm
     (first maximum wins): (V, n_rotations, T) -> (V, T)."""
 
+    @torch.compiler.disable
     def forward(self, inputs):
         fused = getattr(inputs, "_gcb_pooled", None)
         if fused is not None and fused[2] == inputs._version:

@@ -1,5 +1,6 @@
 """Drop-in for ``geoconv.pytorch.layers.angular_min_pooling.AngularMinPooling``
 (/root/reference/src/geoconv/pytorch/layers/angular_min_pooling.py:6-29)."""
+import torch
 from torch import nn
 
 from geoconv_b200 import ops
@@ -9,6 +10,7 @@ class AngularMinPooling(nn.Module):
     """Per vertex, keep the rotation whose template-response vector has the SMALLEST Euclidean norm
     (first minimum wins): (V, n_rotations, T) -> (V, T)."""
 
+    @torch.compiler.disable
     def forward(self, inputs):
         if inputs.dim() != 3:
             raise ValueError(f"expected (n_vertices, n_rotations, feature_dim), got {tuple(inputs.shape)}")

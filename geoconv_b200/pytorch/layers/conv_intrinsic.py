@@ -175,7 +175,11 @@ class ConvIntrinsic(ABC, nn.Module):
         _, z, arg = self._run(inputs, orientations)
         return z, arg
 
+    @torch.compiler.disable
     def _run(self, inputs, orientations):
+        # Opaque to torch.compile (the reference demo compiles its model, training_demo.py:127): the body
+        # hands raw device pointers to libgeoconv_b200.so through ctypes, which Dynamo cannot trace; the
+        # surrounding modules still compile, this call runs as a graph break.
         mesh_signal, bary_coordinates = inputs
         ops._need_cuda(mesh_signal, "signal")
         ops._need_cuda(bary_coordinates, "barycentric coordinates")

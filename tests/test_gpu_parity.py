@@ -242,3 +242,36 @@ def test_faust_shape_against_oracle(precision):
         assert nerr(layer._bias.grad, ref["d_bias"]) < tol
     else:  # gradients of the flipped vertices differ legitimately: compare on the rest via closed form
         assert flips <= 8
+
+
+@pytest.mark.gpu
+def test_survives_torch_compile():
+    """The reference demo wraps its model in torch.compile (training_demo.py:127): the drop-in layers run as
+    graph breaks inside a compiled module and give the same result and gradients as the eager call."""
+    dev = "cuda:0"
+    v, f, r, a, t = 300, 32, 3, 6, 32
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.down = torch.nn.Linear(f, f)
+            self.conv = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.03)
+            self.amp = AngularMaxPooling()
+            self.head = torch.nn.Linear(t, 5)
+
+        def forward(self, x, bary):
+            return self.head(self.amp(self.conv([self.down(x), bary])))
+
+    torch.manual_seed(0)
+    net = Net().to(dev)
+    x = O.make_signal(v, f, kind="randn").to(dev)
+    bary = O.make_bary(v, r, a, seed=2).to(dev)
+    ref = net(x, bary)
+    ref.sum().backward()
+    ref_grad = net.conv._template_neighbor_weights.grad.clone()
+    net.zero_grad()
+    compiled = torch.compile(net, backend="aot_eager")   # no codegen toolchain needed on the test box
+    out = compiled(x, bary)
+    out.sum().backward()
+    assert nerr(out, ref) < 1e-6
+    assert nerr(net.conv._template_neighbor_weights.grad, ref_grad) < 1e-6
