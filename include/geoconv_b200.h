@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GCB_ABI_VERSION 3
+#define GCB_ABI_VERSION 4
 #define GCB_MAX_ROT 32
 
 /* error codes */
@@ -65,6 +65,17 @@ void gcb_profile_enable(int on);
 int gcb_profile_read(int which, double* ms_total, int64_t* launches);
 /* 1 if the tcgen05 kernels can serve this shape, else 0 (then use GCB_PREC_FP32). */
 int gcb_tc_supported(int32_t R, int32_t A, int32_t F, int32_t T, int32_t n_rot);
+
+/* ---- GPC systems -> barycentric coordinates (the preprocessing step before the path) -----
+ * Replaces geoconv/preprocessing/barycentric_coordinates.py:127-175 (with :7-69): for every GPC
+ * system v and template vertex q the first triangle, in the system's face order, that contains
+ * q; float64 with the reference's operation order.
+ * tri_xy [n_tri,3,2] f64 cartesian GPC coordinates of the triangle corners, tri_idx [n_tri,3] i32
+ * their mesh vertex ids, tri_ptr [V+1] i64 (system v owns triangles tri_ptr[v] .. tri_ptr[v+1]),
+ * template_xy [RA,2] f64 cartesian template vertices; bary_out [V,RA,3,2] f64 = (index, weight),
+ * zeros where no triangle contains the template vertex.                                     */
+int gcb_bary_from_gpc(const double* tri_xy, const int32_t* tri_idx, const int64_t* tri_ptr, int32_t V,
+                      const double* template_xy, int32_t RA, double* bary_out, void* stream);
 
 /* ---- bary -> (idx, w) ------------------------------------------------------------------
  * Replaces conv_intrinsic.py:213-221 (cast to fp32, `[...,0].long()`, `[...,1]`).
