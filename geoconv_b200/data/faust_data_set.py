@@ -1,0 +1,142 @@
+"""Drop-in for ``geoconv_examples.mpi_faust.pytorch.faust_data_set``
+(/root/reference/src/geoconv_examples/mpi_faust/pytorch/faust_data_set.py:11-140): the reader of the
+preprocessed FAUST archive - a zip of ``SIGNAL_*.npy`` (V, F), ``BC_*.npy`` (V, R, A, 3, 2), ``GT_*.npy`` (V,)
+and optionally ``COORD_*.npy`` written by ``preprocess_faust.py:153-210``.
+
+``faust_generator`` / ``FaustDataset`` keep the reference's signature, splits, ordering (file numbers), dtypes and
+the training-time noise |N(0, 1e-5)| on the barycentric WEIGHT column only.
+
+New here (not in the reference): ``DeviceFaustCache`` uploads every mesh of a split ONCE and then serves
+``((signal, bc), gt)`` from HBM - the reference re-reads the zip, converts float64 -> float32 and copies 24 MB
+host-to-device per mesh and epoch.  The training noise is drawn on the device and a fresh barycentric tensor is
+handed out per epoch, so the layers' per-tensor cache (index split, CSR inversion) sees it as new data, exactly
+like the reference pipeline does.
+"""
+import os
+import random
+
+import numpy as np
+import torch
+from torch.utils.data import IterableDataset
+
+SPLITS = {0: range(70), 1: range(70, 80), 2: range(80, 100), 3: range(100)}   # faust_data_set.py:64-73
+NOISE_SCALE = 1e-5                                                            # :90
+
+
+def get_file_number(file_name):
+    """First all-digit token of the file name, extension dropped (preprocess_faust.py:15-32)."""
+    for elem in file_name.split(".")[0].split("_"):
+        if elem.isdigit():
+            return int(elem)
+    raise RuntimeError(f"Filename '{file_name}' has no digit.")
+
+
+def _sorted_names(dataset, prefix):
+    """Archive keys of one kind ordered by file number (faust_data_set.py:55-59).  The reference looks the
+    basenames up directly, which works for the flat archive preprocess_faust.py writes; keys with a directory
+    prefix are accepted here as well."""
+    names = [fn for fn in dataset.files if os.path.basename(fn).startswith(prefix)]
+    names.sort(key=lambda fn: get_file_number(os.path.basename(fn)))
+    return names
+
+
+def _indices(set_type, set_indices, shuffle=True):
+    if set_indices is not None:
+        return list(set_indices)
+    if set_type not in SPLITS:
+        raise RuntimeError(
+            f"There is no 'set_type'={set_type}. Choose from: [0: 'train', 1: 'val', 2: 'test', 3: 'all'].")
+    indices = list(SPLITS[set_type])
+    if set_type == 0 and shuffle:
+        random.shuffle(indices)
+    return indices
+
+
+def faust_generator(path_to_zip, set_type=0, only_signal=False, device=None, return_coordinates=False,
+                    set_indices=None):
+    """One preprocessed mesh per ``next``: ``(signal, bc), gt`` (faust_data_set.py:11-111)."""
+    dataset = np.load(path_to_zip, allow_pickle=True)
+    signal_names, bc_names, gt_names = (_sorted_names(dataset, p) for p in ("SIGNAL", "BC", "GT"))
+    coord_names = _sorted_names(dataset, "COORD") if return_coordinates else None
+    for idx in _indices(set_type, set_indices):
+        signal = torch.tensor(dataset[signal_names[idx]], dtype=torch.float32)
+        bc = torch.tensor(dataset[bc_names[idx]], dtype=torch.float32)
+        if set_type == 0:
+            noise = np.abs(np.random.normal(size=tuple(bc.shape[:3]) + (3, 2), scale=NOISE_SCALE))
+            noise[:, :, :, :, 0] = 0
+            bc = bc + torch.from_numpy(noise)   # float32 + float64 -> float64, like the reference's tensor + ndarray
+        gt = torch.tensor(dataset[gt_names[idx]], dtype=torch.int64).view(-1,)
+        if device:
+            if only_signal:
+                yield signal.to(device)
+            else:
+                yield (signal.to(device), bc.to(device)), gt.to(device)
+        elif only_signal:
+            yield signal
+        elif return_coordinates:
+            coord = torch.tensor(dataset[coord_names[idx]], dtype=torch.float32)
+            yield (signal, bc, coord), gt
+        else:
+            yield (signal, bc), gt
+
+
+class FaustDataset(IterableDataset):
+    """faust_data_set.py:114-140."""
+
+    def __init__(self, path_to_zip, set_type=0, only_signal=False, device=None, return_coordinates=False):
+        self.path_to_zip = path_to_zip
+        self.set_type = set_type
+        self.only_signal = only_signal
+        self.return_coordinates = return_coordinates
+        self.device = device
+        self.reset()
+
+    def __iter__(self):
+        return self.dataset
+
+    def reset(self):
+        self.dataset = faust_generator(self.path_to_zip, set_type=self.set_type, only_signal=self.only_signal,
+                                       device=self.device, return_coordinates=self.return_coordinates)
+
+
+class DeviceFaustCache(IterableDataset):
+    """A split of the archive resident in HBM: every mesh is read, converted and uploaded once.
+
+    Iterating yields ``((signal, bc), gt)`` device tensors in the reference's order (training split shuffled per
+    epoch).  For the training split the barycentric tensor handed out is ``bc + noise`` with
+    noise = |N(0, 1e-5)| on the weight column, drawn on the device from ``generator`` - a new tensor every epoch."""
+
+    def __init__(self, path_to_zip, set_type=0, device="cuda", set_indices=None, generator=None):
+        self.set_type = set_type
+        self.device = torch.device(device)
+        self.generator = generator
+        dataset = np.load(path_to_zip, allow_pickle=True)
+        signal_names, bc_names, gt_names = (_sorted_names(dataset, p) for p in ("SIGNAL", "BC", "GT"))
+        self.indices = _indices(set_type, set_indices, shuffle=False)
+        self.meshes = {}
+        for idx in self.indices:
+            signal = torch.tensor(dataset[signal_names[idx]], dtype=torch.float32).to(self.device)
+            bc = torch.tensor(dataset[bc_names[idx]], dtype=torch.float32).to(self.device)
+            gt = torch.tensor(dataset[gt_names[idx]], dtype=torch.int64).view(-1,).to(self.device)
+            self.meshes[idx] = (signal, bc, gt)
+
+    def __len__(self):
+        return len(self.indices)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for m in self.meshes.values() for t in m)
+
+    def __iter__(self):
+        order = list(self.indices)
+        if self.set_type == 0:
+            random.shuffle(order)
+        for idx in order:
+            signal, bc, gt = self.meshes[idx]
+            if self.set_type == 0:
+                noise = torch.randn(bc.shape[:4], device=self.device, generator=self.generator,
+                                    dtype=torch.float32).abs_().mul_(NOISE_SCALE)
+                noisy = bc.clone()
+                noisy[..., 1] += noise
+                yield (signal, noisy), gt
+            else:
+                yield (signal, bc), gt

@@ -1,0 +1,93 @@
+"""reader of the preprocessed FAUST archive (host generator + device-resident cache)."""
+import os
+import zipfile
+
+import numpy as np
+import pytest
+import torch
+
+from geoconv_b200.data.faust_data_set import DeviceFaustCache, FaustDataset, faust_generator, get_file_number
+
+
+@pytest.fixture(scope="module")
+def archive(tmp_path_factory):
+    """100 tiny meshes in the layout preprocess_faust.py:153-210 writes (one .npy per kind and mesh, zipped)."""
+    root = tmp_path_factory.mktemp("faust")
+    rng = np.random.default_rng(0)
+    path = os.path.join(root, "faust.zip")
+    with zipfile.ZipFile(path, "w") as zf:
+        for m in reversed(range(100)):                      # written out of order: the reader sorts by number
+            v = 12 + m % 5
+            sig = rng.random((v, 6))                         # float64 on disk, like np.save of SHOT descriptors
+            bc = np.zeros((v, 2, 4, 3, 2))
+            bc[..., 0] = rng.integers(0, v, (v, 2, 4, 3))
+            bc[..., 1] = rng.random((v, 2, 4, 3))
+            gt = rng.permutation(v)
+            for kind, arr in (("SIGNAL", sig), ("BC", bc), ("GT", gt), ("COORD", rng.random((v, 3)))):
+                tmp = os.path.join(root, f"{kind}_tr_reg_{m:03d}.npy")
+                np.save(tmp, arr)
+                zf.write(tmp, arcname=f"faust/{kind}_tr_reg_{m:03d}.npy")
+                os.remove(tmp)
+    return path
+
+
+def test_file_number():
+    assert get_file_number("SIGNAL_tr_reg_042.npy") == 42
+    with pytest.raises(RuntimeError):
+        get_file_number("SIGNAL_tr_reg.npy")
+
+
+def test_splits_order_and_dtypes(archive):
+    val = list(faust_generator(archive, set_type=1))
+    assert len(val) == 10
+    (signal, bc), gt = val[0]
+    assert signal.dtype == torch.float32 and bc.dtype == torch.float32 and gt.dtype == torch.int64
+    assert signal.shape[0] == 12 + 70 % 5 and gt.dim() == 1            # mesh 70 comes first: sorted by file number
+    assert len(list(faust_generator(archive, set_type=2))) == 20
+    assert len(list(faust_generator(archive, set_type=3))) == 100
+    assert len(list(faust_generator(archive, set_type=3, set_indices=[5, 1]))) == 2
+    with pytest.raises(RuntimeError):
+        next(faust_generator(archive, set_type=7))
+    (s, b, c), g = next(faust_generator(archive, set_type=1, return_coordinates=True))
+    assert c.shape == (s.shape[0], 3)
+    assert torch.equal(next(faust_generator(archive, set_type=1, only_signal=True)), signal)
+
+
+def test_training_noise_only_on_weights(archive):
+    clean = {tuple(bc.shape): bc for (_, bc), _ in faust_generator(archive, set_type=3, set_indices=[3])}
+    np.random.seed(0)
+    (_, noisy), _ = next(faust_generator(archive, set_type=0, set_indices=[3]))
+    ref = clean[tuple(noisy.shape)]
+    assert torch.equal(noisy[..., 0].float(), ref[..., 0])              # indices untouched
+    d = noisy[..., 1].double() - ref[..., 1].double()
+    assert (d >= 0).all() and d.max() < 1e-3 and d.mean() > 1e-6        # |N(0, 1e-5)|
+    ds = FaustDataset(archive, set_type=0)
+    assert len(list(ds)) == 70
+    ds.reset()
+    assert len(list(ds)) == 70
+
+
+@pytest.mark.gpu
+def test_device_cache_feeds_the_layer(archive):
+    from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
+    from geoconv_b200.pytorch.layers.conv_dirac import ConvDirac
+    host = list(faust_generator(archive, set_type=1))
+    cache = DeviceFaustCache(archive, set_type=1)
+    assert len(cache) == 10 and cache.nbytes() > 0
+    layer = ConvDirac(input_shape=[(None, 6), (None, 2, 4, 3, 2)], amt_templates=4, template_radius=0.03).cuda()
+    n = 0
+    for ((signal, bc), gt), ((hs, hb), hg) in zip(cache, host):     # same order: sorted by file number
+        assert signal.is_cuda and bc.is_cuda and gt.is_cuda
+        assert torch.equal(signal.cpu(), hs) and torch.equal(bc.cpu(), hb) and torch.equal(gt.cpu(), hg)
+        z = AngularMaxPooling()(layer([signal, bc]))
+        assert z.shape == (signal.shape[0], 4)
+        n += 1
+    assert n == 10
+    train = DeviceFaustCache(archive, set_type=0, set_indices=[0, 1], generator=torch.Generator(device="cuda").manual_seed(1))
+    (s1, b1), _ = next(iter(train))
+    (s2, b2), _ = next(iter(train))
+    assert b1 is not b2                                                  # a new tensor per epoch -> re-packed by the layer
+    clean = train.meshes[0][1] if b1.shape == train.meshes[0][1].shape else train.meshes[1][1]
+    assert torch.equal(b1[..., 0], clean[..., 0])
+    d = (b1[..., 1] - clean[..., 1])
+    assert (d >= 0).all() and d.max() < 1e-3
