@@ -388,43 +388,78 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
   int stage = 0;
   uint32_t par = 0, accum = 0;
   int n = 0, phi = 0;
+  // The per-step schedule of a super-step lives in the LANES of this warp: lane y holds what step y needs
+  // (weight tiles to wait for, tiles to release, descriptor address words of the units' weight tiles), read
+  // from shared / constant memory once per super-step; a tile then costs a few shuffles instead of dependent
+  // memory reads in the issuing thread's critical path.
+  uint32_t need_l = 0, retire_l = 0, blo_l[NU];
+  auto load_schedule = [&](int ph, const int (&s0)[NU], uint32_t& need_o, uint32_t& retire_o, uint32_t (&blo_o)[NU]) {
+    const int yy = lane < A_ ? lane : 0;
+    need_o = need_tab[ph * A_ + yy];
+    retire_o = retire_tab[ph * A_ + yy];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      int sg = s0[u] + yy;
+      sg -= sg >= A_ ? A_ : 0;
+      blo_o[u] = c.b_lo0 + (uint32_t)p.ring.pos[sg] * c.b_tile_lo;
+    }
+  };
+  load_schedule(0, sl, need_l, retire_l, blo_l);
+  uint32_t b_lo[NU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) b_lo[u] = __shfl_sync(0xffffffffu, blo_l[u], 0);
   if (c.n_nc > 0) {   // readiness of the very first tile; every later tile is waited for one tile ahead
     ptx::mbar_wait(c.a_full, 0);
-    tc_wait_bits(c.b_full, need_tab[0], 0);
+    tc_wait_bits(c.b_full, __shfl_sync(0xffffffffu, need_l, 0), 0);
     ptx::tc_fence_after();
   }
   for (int k = 0; k < c.n_nc; ++k) {
     const uint32_t b_par = (uint32_t)(k & 1);   // every weight tile is filled once per super-step
     int phi_n = phi + shift_;
     phi_n -= phi_n >= A_ ? A_ : 0;
+    int sl_n[NU];            // the units' first weight tiles at step 0 of the next super-step
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      sl_n[u] = sl[u] + shift_;
+      sl_n[u] -= sl_n[u] >= A_ ? A_ : 0;
+    }
+    uint32_t need_nl = 0, retire_nl = 0, blo_nl[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) blo_nl[u] = 0;
     for (int y = 0; y < A_; ++y, ++n) {
       long long* trp = trace_on && n < 128 ? p.trace + ((size_t)2 * 128 + n) * 8 : nullptr;
       if (trp) trp[0] = clock64();
-      const uint32_t rm = retire_tab[phi * A_ + y];
       const uint32_t a_lo = c.a_lo0 + (uint32_t)stage * c.a_stage_lo;
-      uint32_t b_lo[NU];
-#pragma unroll
-      for (int u = 0; u < NU; ++u) b_lo[u] = c.b_lo0 + (uint32_t)p.ring.pos[sl[u]] * c.b_tile_lo;
       if (!no_mma && ptx::elect_one())
         tc_issue_range<KC, X3, NU, 0, U_SPLIT, 0, J_SPLIT>(desc_hi, a_lo, b_lo, d_u, idesc_u, on, c.b_lo_ring, accum);
       __syncwarp();
-      // ---- readiness of the next tile, checked while the first half executes ----
+      // ---- while the first half executes: this step's releases, the next tile's addresses and readiness ----
+      const uint32_t rm = __shfl_sync(0xffffffffu, retire_l, y);
       int stage_n = stage + 1;
       uint32_t par_n = par;
       if (stage_n == ns_a_) { stage_n = 0; par_n ^= 1u; }
       uint32_t defer = 0;
+      uint32_t b_lo_n[NU];
       if (y + 1 < A_) {
+#pragma unroll
+        for (int u = 0; u < NU; ++u) b_lo_n[u] = __shfl_sync(0xffffffffu, blo_l[u], y + 1);
+        const uint32_t nm = __shfl_sync(0xffffffffu, need_l, y + 1);
         ptx::mbar_wait(c.a_full + 8u * stage_n, par_n);
         if (trp) trp[3] = clock64();
-        tc_wait_bits(c.b_full, need_tab[phi * A_ + y + 1], b_par);
-      } else if (k + 1 < c.n_nc) {
-        // first step of the next super-step: a weight tile that retires at THIS step is refilled only
-        // after the commit below - waiting for it here would deadlock, so it is waited for afterwards
-        const uint32_t nmn = need_tab[phi_n * A_];
-        defer = nmn & rm;
-        ptx::mbar_wait(c.a_full + 8u * stage_n, par_n);
-        if (trp) trp[3] = clock64();
-        tc_wait_bits(c.b_full, nmn & ~defer, b_par ^ 1u);
+        tc_wait_bits(c.b_full, nm, b_par);
+      } else {
+        if (k + 1 < c.n_nc) load_schedule(phi_n, sl_n, need_nl, retire_nl, blo_nl);
+#pragma unroll
+        for (int u = 0; u < NU; ++u) b_lo_n[u] = __shfl_sync(0xffffffffu, blo_nl[u], 0);
+        if (k + 1 < c.n_nc) {
+          // first step of the next super-step: a weight tile that retires at THIS step is refilled only
+          // after the commit below - waiting for it here would deadlock, so it is waited for afterwards
+          const uint32_t nmn = __shfl_sync(0xffffffffu, need_nl, 0);
+          defer = nmn & rm;
+          ptx::mbar_wait(c.a_full + 8u * stage_n, par_n);
+          if (trp) trp[3] = clock64();
+          tc_wait_bits(c.b_full, nmn & ~defer, b_par ^ 1u);
+        }
       }
       ptx::tc_fence_after();
       if (trp) trp[1] = clock64();
@@ -451,15 +486,17 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
       if (trp) trp[2] = clock64();
       accum = 1u;
 #pragma unroll
-      for (int u = 0; u < NU; ++u) sl[u] = sl[u] + 1 == A_ ? 0 : sl[u] + 1;
+      for (int u = 0; u < NU; ++u) b_lo[u] = b_lo_n[u];
       stage = stage_n;
       par = par_n;
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
-      sl[u] += shift_;
-      sl[u] -= sl[u] >= A_ ? A_ : 0;
+      sl[u] = sl_n[u];
+      blo_l[u] = blo_nl[u];
     }
+    need_l = need_nl;
+    retire_l = retire_nl;
     phi = phi_n;
   }
   // centre tiles: X[k] * Wself - one weight tile (ring position of angular tile 0) serves every
