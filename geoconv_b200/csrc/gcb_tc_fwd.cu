@@ -60,7 +60,6 @@ constexpr int TC_WARP_MMA = 1;
 constexpr int TC_WARP_PROD0 = TC_WARP_MMA + TC_MMA_WARPS;
 constexpr int TC_WARP_ROWS = TC_M / TC_PRODUCER_WARPS;   // tile rows one producer warp fills
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
-constexpr int TC_BAR_BYTES = 1024;
 constexpr int TC_G_MAX = 8;              // rotations per CTA (accumulator groups) upper bound
 constexpr int TC_OWN = TC_G_MAX;   // MMA units one issuing warp can own (all of them when it works alone)
 constexpr int TC_REC_BYTES = TC_M * 32;  // one (x,y) slot of packed records for a 128-vertex tile
@@ -71,9 +70,14 @@ constexpr uint8_t TC_NO_DUP = 0xFF;
 //   m      rotations merged into one MMA (1 = every rotation issues its own N = n_t MMAs)
 //   dstep  offset step between consecutive rotations (mod A) when m > 1
 //   pos[s] ring position of angular tile s; dup[s] a second position that receives a copy of it
+//   tile_of[q]  the angular tile whose data sits at position q (main position or copy)
+//   shift  odd super-steps use the same layout `shift` positions further on (n_pos + shift positions in
+//          total): the entries of the next super-step then land in positions that were vacated several
+//          steps earlier instead of the ones their namesakes still occupy
+// All tile indices here are relative to the CTA's first rotation (tile s of the CTA = (s - rel0) mod A).
 struct TcRing {
-  int m, dstep, n_pos;
-  uint8_t pos[GCB_MAX_ROT], dup[GCB_MAX_ROT];
+  int m, dstep, n_pos, shift;
+  uint8_t pos[GCB_MAX_ROT], dup[GCB_MAX_ROT], tile_of[2 * GCB_MAX_ROT];
 };
 
 struct TcFwdParams {
@@ -89,6 +93,8 @@ struct TcFwdParams {
   int tmem_cols;        // power of two >= g*n_t
   int ksplit;           // K splits (grid.z = t_chunks * ksplit)
   int phase_shift;      // angular visiting order of super-step k starts at (k * phase_shift) % A
+  int phase_alt;        // 1: the phase alternates 0, phase_shift, 0, ... with the two ring layouts instead of accumulating
+  int bar_bytes;        // size of the mbarrier block in shared memory
   long long* trace;     // GCB_TC_TRACE (investigation builds): clock64 stamps of CTA (1,0,0), [role][tile][8]
   int debug;            // GCB_TC_DEBUG bits (timing experiments only): 1 = all gathers read row 0, 2 = no MMAs
   TcRing ring;
@@ -115,12 +121,13 @@ static TcRing tc_ring_layout(int A, int dstep, int m) {
   r.m = m; r.dstep = m > 1 ? dstep : 0;
   for (int s = 0; s < GCB_MAX_ROT; ++s) { r.pos[s] = (uint8_t)(s < A ? s : 0); r.dup[s] = TC_NO_DUP; }
   r.n_pos = A;
+  for (int s = 0; s < 2 * GCB_MAX_ROT; ++s) r.tile_of[s] = (uint8_t)(s < A ? s : 0);
   if (m <= 1) return r;
   const int gc = gcd_int(dstep, A), L = A / gc;
   int at = 0;
   for (int c = 0; c < gc; ++c) {
-    for (int k = 0; k < L; ++k) r.pos[(c + k * dstep) % A] = (uint8_t)at++;
-    for (int k = 0; k < m - 1; ++k) r.dup[(c + k * dstep) % A] = (uint8_t)at++;
+    for (int k = 0; k < L; ++k) { r.tile_of[at] = (uint8_t)((c + k * dstep) % A); r.pos[(c + k * dstep) % A] = (uint8_t)at++; }
+    for (int k = 0; k < m - 1; ++k) { r.tile_of[at] = (uint8_t)((c + k * dstep) % A); r.dup[(c + k * dstep) % A] = (uint8_t)at++; }
   }
   r.n_pos = at;
   return r;
@@ -137,39 +144,83 @@ static int tc_uniform_step(const RotTable& rot, int n_rot, int A) {
 }
 
 // per-phase weight-tile schedules in shared memory: need / retire masks (uint32) and first / last steps (uint8)
-static size_t tc_tab_bytes(int A) { return align_up((size_t)A * A * 11 + A, 16); }
+static bool tc_use_pairs() {
+  static const bool use_pairs = !(getenv("GCB_TC_CLUSTER") && atoi(getenv("GCB_TC_CLUSTER")) == 0);
+  return use_pairs;
+}
 
-// How far the angular visiting order advances from one super-step to the next.  A weight-tile slot is
-// free from its last reader in super-step k (step last_0) to its first reader in super-step k+1 (step
-// first_shift): pick the shift that maximises the smallest such gap over every rotation group, so that
-// no refill (commit -> TMA -> barrier, ~2000 cycles) lands on the critical path.
-static int tc_pick_phase_shift(const RotTable& rot, int n_rot, int A, int g, int n_groups, bool pairs) {
-  int best = 0, best_gap = -1;
-  for (int shift = 0; shift < A; ++shift) {
-    int gap = 2 * A;
-    for (int grp = 0; grp < n_groups; ++grp) {
-      const int rot0 = grp * g;
-      const int g_cnt = g < n_rot - rot0 ? g : n_rot - rot0;
-      const int anchor = rot.off[(pairs ? (grp & ~1) : grp) * g];
-      for (int sg = 0; sg < A; ++sg) {
-        int last0 = -1, first1 = A;
-        for (int j = 0; j < g_cnt; ++j) {
-          const int rel = rot.off[rot0 + j] - anchor;
-          const int st0 = ((sg - rel) % A + A) % A, st1 = ((sg - rel - shift) % A + A) % A;
-          last0 = st0 > last0 ? st0 : last0;
-          first1 = st1 < first1 ? st1 : first1;
+// schedules of the weight ring in shared memory, per phase (and super-step parity), in ring-POSITION space
+static size_t tc_tab_bytes(int A, int n_pos) {
+  return align_up((size_t)A * A * 16 + 8 * A + (size_t)A * n_pos * 2 + (size_t)(2 * A + 1) * n_pos + (size_t)2 * A * n_pos + 64, 16);
+}
+// mbarriers: A-stage full/empty (<= 8 stages), per (parity, position) full, per absolute position empty,
+// accumulators; TMEM slot
+static size_t tc_bar_bytes(int n_pos, int n_ring) { return align_up((size_t)8 * (16 + 2 * n_pos + n_ring + 1) + 16, 64); }
+
+// Refill slack of the weight ring for a visiting order that advances `phase_shift` steps per super-step and a
+// ring that alternates between two layouts `ring.shift` positions apart: the smallest number of whole steps
+// between the last reader of a position in super-step k and the first reader of the entry that replaces it in
+// super-step k+1, over every rotation group and both parities.  A refill (commit -> TMA -> barrier) takes
+// ~2000 cycles, i.e. two to three steps; with one layout no visiting order leaves more than one step when a
+// CTA owns A/2 rotations.  Entries are ring positions (a tile's copy is loaded on its own).
+static int tc_refill_slack(const RotTable& rot, int n_rot, int A, int g, int n_groups, bool pairs, const TcRing& ring,
+                           int phase_shift, bool alt) {
+  int slack = 4 * A;
+  for (int grp = 0; grp < n_groups; ++grp) {
+    const int rot0 = grp * g;
+    const int g_cnt = g < n_rot - rot0 ? g : n_rot - rot0;
+    const int anchor = rot.off[(pairs ? (grp & ~1) : grp) * g];
+    const int rel0 = ((rot.off[rot0] - anchor) % A + A) % A;
+    int first[32], last_prev[32], last_cur[32];
+    auto reads = [&](int phase, int* fo, int* lo) {
+      for (int q = 0; q < 32; ++q) { fo[q] = A; lo[q] = -1; }
+      for (int y = 0; y < A; ++y)
+        for (int u = 0; u * ring.m < g_cnt; ++u) {
+          const int rel = rot.off[rot0 + u * ring.m] - anchor;
+          const int s0 = ((y + phase + rel - rel0) % A + A) % A;
+          const int wd = ring.m < g_cnt - u * ring.m ? ring.m : g_cnt - u * ring.m;
+          for (int i = 0; i < wd; ++i) {
+            const int q = ring.pos[s0] + i;
+            if (fo[q] > y) fo[q] = y;
+            lo[q] = y;
+          }
         }
-        const int free_steps = (A - 1 - last0) + first1;
-        gap = free_steps < gap ? free_steps : gap;
+    };
+    // walk the sequence of super-steps (parity alternates; the phase accumulates or alternates) until it repeats
+    int phase = 0;
+    reads(phase, first, last_prev);
+    for (int k = 0; k < 2 * A; ++k) {
+      const int par = k & 1;                     // parity of super-step k; k + 1 has the other
+      const int phase_n = alt ? (par ? 0 : phase_shift % A) : (phase + phase_shift) % A;
+      reads(phase_n, first, last_cur);
+      for (int q = 0; q < ring.n_pos; ++q) {     // entry q of super-step k + 1
+        if (last_cur[q] < 0) continue;           // never read: never loaded
+        const int qp = q + (par ^ 1) * ring.shift - par * ring.shift;   // the same position in k's numbering
+        const int ret = (qp >= 0 && qp < ring.n_pos) ? last_prev[qp] : -1;
+        const int free_steps = (ret < 0 ? A : A - 1 - ret) + first[q];
+        slack = free_steps < slack ? free_steps : slack;
       }
+      for (int q = 0; q < 32; ++q) last_prev[q] = last_cur[q];
+      phase = phase_n;
     }
-    if (gap > best_gap) { best_gap = gap; best = shift; }
   }
+  return slack;
+}
+
+// best visiting-order advance for a given ring (ties: the smallest)
+static int tc_pick_phase_shift(const RotTable& rot, int n_rot, int A, int g, int n_groups, bool pairs,
+                               const TcRing& ring, bool alt, int* slack_out) {
+  int best = 0, best_slack = -1;
+  for (int shift = 0; shift < A; ++shift) {
+    const int sl = tc_refill_slack(rot, n_rot, A, g, n_groups, pairs, ring, shift, alt);
+    if (sl > best_slack) { best_slack = sl; best = shift; }
+  }
+  if (slack_out) *slack_out = best_slack;
   return best;
 }
 
 // dstep = 0: every rotation on its own (works for any rotation list)
-static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, int dstep) {
+static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, int dstep, int ring_shift = 0) {
   TcConfig c{};
   c.ok = false;
   if (T % 16 != 0 || F % 8 != 0 || A > GCB_MAX_ROT || n_rot > GCB_MAX_ROT) return c;
@@ -190,10 +241,13 @@ static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, int dste
       if (F % kc != 0) continue;
       for (int m = m_top; m >= 1; m >>= 1) {
         TcRing ring = tc_ring_layout(A, dstep, m);
-        if (ring.n_pos >= TC_NO_DUP) continue;
-        size_t b_bytes = (size_t)ring.n_pos * nprod * n_t * kc * 4;
+        if (ring.n_pos > 32) continue;   // position masks are 32-bit
+        ring.shift = ring_shift;
+        const bool pairs = tc_use_pairs() && n_groups % 2 == 0 && kc >= 16;   // a pair member stages half of the records
+        size_t b_bytes = (size_t)(ring.n_pos + ring_shift) * nprod * n_t * kc * 4;
         size_t a_stage = (size_t)nprod * TC_M * kc * 4;
-        size_t fixed = b_bytes + (size_t)A * TC_REC_BYTES + TC_BAR_BYTES + tc_tab_bytes(A) + 1024 /* alignment slack */;
+        size_t fixed = b_bytes + (size_t)A * TC_REC_BYTES / (pairs ? 2 : 1) + tc_bar_bytes(ring.n_pos, ring.n_pos + ring_shift) +
+                       tc_tab_bytes(A, ring.n_pos) + 1024 /* alignment slack */;
         if (fixed + 4 * a_stage > (size_t)TC_SMEM_LIMIT) continue;
         int ns_a = (int)(((size_t)TC_SMEM_LIMIT - fixed) / a_stage);
         if (ns_a > 8) ns_a = 8;
@@ -276,6 +330,13 @@ __device__ __forceinline__ uint32_t swz_chunk(int row, int c) {
   return (uint32_t)(c ^ ((row >> 2) & 1));
 }
 
+// phase of the super-step after one with phase `phi`
+__device__ __forceinline__ int tc_next_phase(const TcFwdParams& p, int phi) {
+  if (p.phase_alt) return phi == 0 ? p.phase_shift : 0;
+  const int n = phi + p.phase_shift;
+  return n >= p.A ? n - p.A : n;
+}
+
 __device__ __forceinline__ void producer_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCER_WARPS * 32) : "memory");
 }
@@ -303,7 +364,7 @@ struct TcMmaCtx {
   uint32_t a_lo0, a_stage_lo;   // descriptor low word of A stage 0, distance between stages (>> 4)
   uint32_t b_lo0, b_tile_lo, b_lo_ring;   // same for ring position 0, one tile, hi ring -> lo ring
   uint32_t tmem_base;
-  int rot0, g_cnt, n_units, off_anchor;
+  int rot0, g_cnt, n_units, off_anchor, rel0;
   int mw, n_mma;                // this issuing warp and how many are active: warp mw owns units mw, mw + n_mma, ...
   int n_nc, n_c;                // non-centre super-steps / centre tiles of this CTA
 };
@@ -352,16 +413,21 @@ __device__ __forceinline__ void tc_issue_range(const uint64_t desc_hi, const uin
   }
 }
 
-__device__ __forceinline__ void tc_wait_bits(uint32_t bar0, uint32_t bits, uint32_t parity) {
+// wait for the ring entries in `bits` (barrier set of one super-step parity); `seen` holds, per entry, the
+// parity of the barrier phase the next wait is for
+__device__ __forceinline__ void tc_wait_entries(uint32_t bar0, uint32_t bits, uint32_t& seen) {
   while (bits) {
-    ptx::mbar_wait(bar0 + 8u * (uint32_t)(__ffs((int)bits) - 1), parity);
+    const uint32_t q = (uint32_t)(__ffs((int)bits) - 1);
+    ptx::mbar_wait(bar0 + 8u * q, (seen >> q) & 1u);
+    seen ^= 1u << q;
     bits &= bits - 1;
   }
 }
 
 template <int KC, bool X3, int CL, int NU>
 __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx& c, int lane,
-                                            const uint32_t* need_tab, const uint32_t* retire_tab) {
+                                            const uint32_t* need_tab, const uint32_t* retire_tab,
+                                            const uint32_t* seam_tab, const uint32_t* early_tab) {
   constexpr int ROW_BYTES = KC * 4;
   constexpr int KS = KC / 8;
   constexpr uint32_t A_LO_HALF = (uint32_t)(TC_M * ROW_BYTES) >> 4;
@@ -379,7 +445,8 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
     const int gu = c.mw + c.n_mma * u;   // unit index in the CTA
     on[u] = gu < c.n_units;
     const int wd = on[u] ? min(m_, c.g_cnt - gu * m_) : 1;
-    int rel = on[u] ? p.rot.off[c.rot0 + gu * m_] - c.off_anchor : 0;
+    int rel = on[u] ? p.rot.off[c.rot0 + gu * m_] - c.off_anchor - c.rel0 : 0;   // relative to the CTA's first rotation
+    rel += rel < 0 ? A_ : 0;
     sl[u] = rel < 0 ? rel + A_ : rel;
     idesc_u[u] = ptx::make_idesc_tf32(TC_M, wd * n_t_);
     d_u[u] = c.tmem_base + (uint32_t)(gu * m_ * n_t_);
@@ -392,38 +459,47 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
   // (weight tiles to wait for, tiles to release, descriptor address words of the units' weight tiles), read
   // from shared / constant memory once per super-step; a tile then costs a few shuffles instead of dependent
   // memory reads in the issuing thread's critical path.
-  uint32_t need_l = 0, retire_l = 0, blo_l[NU];
-  auto load_schedule = [&](int ph, const int (&s0)[NU], uint32_t& need_o, uint32_t& retire_o, uint32_t (&blo_o)[NU]) {
+  uint32_t need_l = 0, retire_l = 0, early_l = 0, blo_l[NU];
+  auto load_schedule = [&](int ph, int layout, uint32_t ring_off, const int (&s0)[NU], uint32_t& need_o,
+                           uint32_t& retire_o, uint32_t& early_o, uint32_t (&blo_o)[NU]) {
     const int yy = lane < A_ ? lane : 0;
     need_o = need_tab[ph * A_ + yy];
     retire_o = retire_tab[ph * A_ + yy];
+    early_o = early_tab[(layout * A_ + ph) * A_ + yy];
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       int sg = s0[u] + yy;
       sg -= sg >= A_ ? A_ : 0;
-      blo_o[u] = c.b_lo0 + (uint32_t)p.ring.pos[sg] * c.b_tile_lo;
+      blo_o[u] = c.b_lo0 + ((uint32_t)p.ring.pos[sg] + ring_off) * c.b_tile_lo;
     }
   };
-  load_schedule(0, sl, need_l, retire_l, blo_l);
+  // Loop state that swaps at every super-step (the two ring layouts alternate): barrier set, layout offset and,
+  // per ring entry, the parity of the barrier phase the next wait is for.  All in registers.
+  const uint32_t np8 = 8u * (uint32_t)p.ring.n_pos;
+  uint32_t bf_cur = c.b_full, bf_nxt = c.b_full + np8;
+  uint32_t ring_cur = 0u, ring_nxt = (uint32_t)p.ring.shift;
+  uint32_t seen_cur = 0u, seen_nxt = 0u;
+  load_schedule(0, 0, ring_cur, sl, need_l, retire_l, early_l, blo_l);
   uint32_t b_lo[NU];
 #pragma unroll
   for (int u = 0; u < NU; ++u) b_lo[u] = __shfl_sync(0xffffffffu, blo_l[u], 0);
   if (c.n_nc > 0) {   // readiness of the very first tile; every later tile is waited for one tile ahead
     ptx::mbar_wait(c.a_full, 0);
-    tc_wait_bits(c.b_full, __shfl_sync(0xffffffffu, need_l, 0), 0);
+    tc_wait_entries(bf_cur, __shfl_sync(0xffffffffu, need_l, 0), seen_cur);
     ptx::tc_fence_after();
   }
   for (int k = 0; k < c.n_nc; ++k) {
-    const uint32_t b_par = (uint32_t)(k & 1);   // every weight tile is filled once per super-step
-    int phi_n = phi + shift_;
-    phi_n -= phi_n >= A_ ? A_ : 0;
+    const int phi_n = tc_next_phase(p, phi);
+    const uint32_t seam = seam_tab[(k & 1) * A_ + phi];
     int sl_n[NU];            // the units' first weight tiles at step 0 of the next super-step
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
-      sl_n[u] = sl[u] + shift_;
+      sl_n[u] = sl[u] + (phi_n - phi);   // the units' tiles move with the phase
+      sl_n[u] += sl_n[u] < 0 ? A_ : 0;
       sl_n[u] -= sl_n[u] >= A_ ? A_ : 0;
     }
-    uint32_t need_nl = 0, retire_nl = 0, blo_nl[NU];
+    uint32_t need_nl = 0, retire_nl = 0, early_nl = 0, blo_nl[NU];
+    uint32_t early_done = 0;   // entries of the next super-step already waited for
 #pragma unroll
     for (int u = 0; u < NU; ++u) blo_nl[u] = 0;
     for (int y = 0; y < A_; ++y, ++n) {
@@ -446,19 +522,24 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
         const uint32_t nm = __shfl_sync(0xffffffffu, need_l, y + 1);
         ptx::mbar_wait(c.a_full + 8u * stage_n, par_n);
         if (trp) trp[3] = clock64();
-        tc_wait_bits(c.b_full, nm, b_par);
+        tc_wait_entries(bf_cur, nm, seen_cur);
+        if (k + 1 < c.n_nc) {
+          const uint32_t ew = __shfl_sync(0xffffffffu, early_l, y);
+          tc_wait_entries(bf_nxt, ew, seen_nxt);
+          early_done |= ew;
+        }
       } else {
-        if (k + 1 < c.n_nc) load_schedule(phi_n, sl_n, need_nl, retire_nl, blo_nl);
+        if (k + 1 < c.n_nc) load_schedule(phi_n, (k & 1) ^ 1, ring_nxt, sl_n, need_nl, retire_nl, early_nl, blo_nl);
 #pragma unroll
         for (int u = 0; u < NU; ++u) b_lo_n[u] = __shfl_sync(0xffffffffu, blo_nl[u], 0);
         if (k + 1 < c.n_nc) {
-          // first step of the next super-step: a weight tile that retires at THIS step is refilled only
-          // after the commit below - waiting for it here would deadlock, so it is waited for afterwards
+          // first step of the next super-step: an entry whose ring position is only vacated at THIS step is
+          // refilled after the commit below - waiting for it here would deadlock, so it is waited for afterwards
           const uint32_t nmn = __shfl_sync(0xffffffffu, need_nl, 0);
-          defer = nmn & rm;
+          defer = nmn & seam;
           ptx::mbar_wait(c.a_full + 8u * stage_n, par_n);
           if (trp) trp[3] = clock64();
-          tc_wait_bits(c.b_full, nmn & ~defer, b_par ^ 1u);
+          tc_wait_entries(bf_nxt, nmn & ~defer & ~early_done, seen_nxt);
         }
       }
       ptx::tc_fence_after();
@@ -471,8 +552,8 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
             tc_issue_range<KC, X3, NU, 0, NU, J_SPLIT, KS>(desc_hi, a_lo, b_lo, d_u, idesc_u, on, c.b_lo_ring, accum);
         }
         uint32_t r = rm;
-        while (r) {
-          ptx::umma_commit(c.b_empty + 8u * (uint32_t)(__ffs((int)r) - 1));
+        while (r) {   // vacate the ring positions read for the last time
+          ptx::umma_commit(c.b_empty + 8u * ((uint32_t)(__ffs((int)r) - 1) + ring_cur));
           r &= r - 1;
         }
         if (CL == 2) ptx::umma_commit_mc(c.a_empty + 8u * stage, (uint16_t)3);
@@ -480,7 +561,7 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
       }
       __syncwarp();
       if (defer) {
-        tc_wait_bits(c.b_full, defer, b_par ^ 1u);
+        tc_wait_entries(bf_nxt, defer, seen_nxt);
         ptx::tc_fence_after();
       }
       if (trp) trp[2] = clock64();
@@ -497,20 +578,29 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
     }
     need_l = need_nl;
     retire_l = retire_nl;
+    early_l = early_nl;
     phi = phi_n;
+    { const uint32_t t = seen_cur; seen_cur = seen_nxt; seen_nxt = t; }
+    { const uint32_t t = bf_cur; bf_cur = bf_nxt; bf_nxt = t; }
+    { const uint32_t t = ring_cur; ring_cur = ring_nxt; ring_nxt = t; }
   }
-  // centre tiles: X[k] * Wself - one weight tile (ring position of angular tile 0) serves every
-  // rotation, one N = n_t MMA chain each
+  // centre tiles: X[k] * Wself - one weight tile (the ring position of tile 0 in the current layout) serves
+  // every rotation, one N = n_t MMA chain each; the layouts keep alternating
   const uint32_t idesc1 = ptx::make_idesc_tf32(TC_M, n_t_);
-  const uint32_t b_lo_c = c.b_lo0 + (uint32_t)p.ring.pos[0] * c.b_tile_lo;
+  const uint32_t q_c = (uint32_t)p.ring.pos[0];
   for (int k = 0; k < c.n_c; ++k, ++n) {
+    const uint32_t pos_c = q_c + ring_cur;
+    const uint32_t b_lo_c = c.b_lo0 + pos_c * c.b_tile_lo;
     ptx::mbar_wait(c.a_full + 8u * stage, par);
-    ptx::mbar_wait(c.b_full, (uint32_t)((c.n_nc + k) & 1));
+    tc_wait_entries(bf_cur, 1u << q_c, seen_cur);
     ptx::tc_fence_after();
     const uint32_t a_lo = c.a_lo0 + (uint32_t)stage * c.a_stage_lo;
     if (ptx::elect_one()) {
       if (!no_mma) {
-        for (int r = c.mw; r < c.g_cnt; r += c.n_mma) {
+        for (int r = 0; r < c.g_cnt; ++r) {
+          // a rotation's accumulator belongs to the warp that owns its unit in the main loop: MMAs of two
+          // threads into the same accumulator would execute in an order that varies from run to run
+          if ((r / m_) % c.n_mma != c.mw) continue;
           const uint32_t d = c.tmem_base + (uint32_t)(r * n_t_);
 #pragma unroll
           for (int j = 0; j < KS; ++j) {
@@ -524,13 +614,16 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
           }
         }
       }
-      ptx::umma_commit(c.b_empty);
+      ptx::umma_commit(c.b_empty + 8u * pos_c);
       if (CL == 2) ptx::umma_commit_mc(c.a_empty + 8u * stage, (uint16_t)3);
       else ptx::umma_commit(c.a_empty + 8u * stage);
     }
     __syncwarp();
     accum = 1u;
     if (++stage == ns_a_) { stage = 0; par ^= 1u; }
+    { const uint32_t t = seen_cur; seen_cur = seen_nxt; seen_nxt = t; }
+    { const uint32_t t = bf_cur; bf_cur = bf_nxt; bf_nxt = t; }
+    { const uint32_t t = ring_cur; ring_cur = ring_nxt; ring_nxt = t; }
   }
   if (ptx::elect_one()) ptx::umma_commit(c.acc_full);   // accumulators complete
   __syncwarp();
@@ -562,26 +655,42 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_tile_bytes = p.n_t * ROW_BYTES;
   const uint32_t b_base = smem_base;                                        // [NPROD][n_pos][b_tile]
-  const uint32_t a_base = b_base + (uint32_t)(p.ring.n_pos * NPROD * b_tile_bytes);  // [ns_a][NPROD][A_TILE]
-  const uint32_t rec_base = a_base + (uint32_t)(p.ns_a * NPROD * A_TILE_BYTES);      // [A][128][32 B]
-  const uint32_t bar_base = rec_base + (uint32_t)(p.A * TC_REC_BYTES);
+  const int NP = p.ring.n_pos;                                                // ring entries (positions of one layout)
+  const int n_ring = NP + p.ring.shift;                                       // ring positions in shared memory
+  const uint32_t a_base = b_base + (uint32_t)(n_ring * NPROD * b_tile_bytes);        // [ns_a][NPROD][A_TILE]
+  const uint32_t rec_base = a_base + (uint32_t)(p.ns_a * NPROD * A_TILE_BYTES);      // [A][rows of this CTA][32 B]
+  const uint32_t bar_base = rec_base + (uint32_t)(p.A * (TC_REC_BYTES / CL));
   const uint32_t a_full = bar_base;
   const uint32_t a_empty = a_full + 8u * p.ns_a;
-  const uint32_t b_full = a_empty + 8u * p.ns_a;   // per angular tile
-  const uint32_t b_empty = b_full + 8u * p.A;
-  const uint32_t acc_full = b_empty + 8u * p.A;
+  // per (super-step parity, ring entry): its data has landed.  Two sets because the two ring layouts let the
+  // TMA warp fill an entry of super-step k+1 before the entry of the same index of super-step k has been
+  // consumed: one barrier would then run two phases ahead of its waiter.
+  const uint32_t b_full = a_empty + 8u * p.ns_a;
+  const uint32_t b_empty = b_full + 16u * NP;      // per ring POSITION: every reader of its occupant is done
+  const uint32_t acc_full = b_empty + 8u * n_ring;
   const uint32_t tmem_slot = acc_full + 8u;
-  const uint32_t tab_base = bar_base + TC_BAR_BYTES;   // per-phase weight-tile schedules, see below
+  const uint32_t tab_base = bar_base + (uint32_t)p.bar_bytes;   // weight-ring schedules, built below
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));     // generic view of smem_base
-  // [phase][tile]: first / last step of a super-step at which this CTA reads angular weight tile s when
-  // the visiting order starts at `phase`;  [phase][step]: bit s = tile s is first / last read at that step
+  const int AA = p.A * p.A;
+  // [phase][step]: ring entries (positions of the even layout) first / last read at that step
   uint32_t* need_tab = reinterpret_cast<uint32_t*>(smem_gen + (tab_base - smem_base));
-  uint32_t* retire_tab = need_tab + p.A * p.A;
-  uint8_t* first_tab = reinterpret_cast<uint8_t*>(retire_tab + p.A * p.A);
-  uint8_t* last_tab = first_tab + p.A * p.A;
-  // [phase][i]: the i-th weight tile the TMA warp (re)loads for a super-step visited at `phase` (row A:
-  // the CTA's first super-step, when every slot is free)
-  uint8_t* order_tab = last_tab + p.A * p.A;
+  uint32_t* retire_tab = need_tab + AA;
+  // [parity][phase]: entries of the NEXT super-step whose position is only vacated by the last step of this one
+  uint32_t* seam_tab = retire_tab + AA;
+  // [parity][phase][step]: entries of the NEXT super-step's first step that can already be waited for at this
+  // step (their refill was issued at least two steps earlier): spreads the barrier waits of a seam over the
+  // preceding tiles - each wait costs ~250 cycles of the issuing thread under load, four of them at one tile
+  // boundary drained the tensor pipe
+  uint32_t* early_tab = seam_tab + 2 * p.A;
+  // [phase][entry]: first / last step at which the entry is read (0xFF: never - then it is never loaded)
+  uint8_t* firstp_tab = reinterpret_cast<uint8_t*>(early_tab + 2 * AA);
+  uint8_t* lastp_tab = firstp_tab + p.A * NP;
+  // [parity * A + phase][i]: the i-th entry the TMA warp (re)loads for such a super-step (row 2A: the CTA's
+  // first super-step, when every position is vacant)
+  uint8_t* order_tab = lastp_tab + p.A * NP;           // [2 * A + 1][NP]
+  // [parity][phase][entry]: 1 + last step at which the previous super-step still reads the entry's position
+  // (0 = vacant for the whole previous super-step)
+  uint8_t* occ_tab = order_tab + (2 * p.A + 1) * NP;   // [2][A][NP]
 
   // the shuffle tells the compiler the warp index is warp-uniform (role dispatch, uniform registers)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -618,10 +727,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       ptx::mbar_init(a_full + 8u * s, GRP_WARPS * CL);
       ptx::mbar_init(a_empty + 8u * s, (uint32_t)mma_arrivals);
     }
-    for (int s = 0; s < p.A; ++s) {
-      ptx::mbar_init(b_full + 8u * s, 1);
-      ptx::mbar_init(b_empty + 8u * s, (uint32_t)n_mma);
-    }
+    for (int s = 0; s < 2 * NP; ++s) ptx::mbar_init(b_full + 8u * s, 1);
+    for (int s = 0; s < n_ring; ++s) ptx::mbar_init(b_empty + 8u * s, (uint32_t)n_mma);
     ptx::mbar_init(acc_full, (uint32_t)n_mma);
     ptx::fence_mbar_init();
     ptx::prefetch_tensormap(&tmap_hi);
@@ -631,47 +738,81 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.A * p.A; i += blockDim.x) {
-    const int phi = i / p.A, sg = i - phi * p.A;
-    int first = p.A, last = -1;
-    for (int j = 0; j < g_cnt; ++j) {
-      int st = (sg - (p.rot.off[rot0 + j] - off_anchor) - phi) % p.A;
-      st += st < 0 ? p.A : 0;
-      first = st < first ? st : first;
-      last = st > last ? st : last;
-    }
-    first_tab[i] = (uint8_t)first;
-    last_tab[i] = (uint8_t)last;
+  for (int i = threadIdx.x; i < p.A * NP; i += blockDim.x) {
+    // first / last reader of ring entry q under phase phi: a unit reads m adjacent positions starting at the
+    // position of its first tile (tiles relabelled by this CTA's first rotation)
+    const int phi = i / NP, q = i - phi * NP;
+    int first = 0xFF, last = 0xFF;
+    for (int y = 0; y < p.A; ++y)
+      for (int u = 0; u < n_units; ++u) {
+        int s0 = (y + phi + p.rot.off[rot0 + u * p.ring.m] - off_anchor - rel0) % p.A;
+        s0 += s0 < 0 ? p.A : 0;
+        const int wd = min(p.ring.m, g_cnt - u * p.ring.m);
+        const int q0 = p.ring.pos[s0];
+        if (q >= q0 && q < q0 + wd) {
+          if (first == 0xFF) first = y;
+          last = y;
+        }
+      }
+    firstp_tab[i] = (uint8_t)first;
+    lastp_tab[i] = (uint8_t)last;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < p.A * p.A; i += blockDim.x) {
+  for (int i = threadIdx.x; i < AA; i += blockDim.x) {
     const int phi = i / p.A, yy = i - phi * p.A;
     uint32_t need = 0, retire = 0;
-    for (int sg = 0; sg < p.A; ++sg) {
-      need |= first_tab[phi * p.A + sg] == yy ? 1u << sg : 0u;
-      retire |= last_tab[phi * p.A + sg] == yy ? 1u << sg : 0u;
+    for (int q = 0; q < NP; ++q) {
+      need |= firstp_tab[phi * NP + q] == yy ? 1u << q : 0u;
+      retire |= lastp_tab[phi * NP + q] == yy ? 1u << q : 0u;
     }
     need_tab[i] = need;
     retire_tab[i] = retire;
   }
-  // Reload order: weight tiles are re-loaded for the next super-step in the order in which the MMA warp
-  // releases them (a tile retires at the last step at which any rotation reads it - under the PREVIOUS
-  // super-step's phase), ties in the order the next super-step needs them.  Loading in index order
-  // would park the TMA thread on a tile that is released late while tiles that retired steps earlier
-  // wait for their refill.
-  for (int i = threadIdx.x; i < (p.A + 1) * p.A; i += blockDim.x) {
-    const int row = i / p.A, sg = i - row * p.A;
-    const int phi = row < p.A ? row : 0;
-    int phi_prev = phi - p.phase_shift;
+  for (int i = threadIdx.x; i < 2 * p.A * NP; i += blockDim.x) {
+    const int par = i / (p.A * NP), phi = (i / NP) % p.A, q = i % NP;   // entry q of a super-step (par, phi)
+    int phi_prev = phi - p.phase_shift;            // accumulating phases; alternating: the other of {0, phase_shift}
     phi_prev += phi_prev < 0 ? p.A : 0;
-    const int my_key = ((row < p.A ? last_tab[phi_prev * p.A + sg] : 0) * p.A + first_tab[phi * p.A + sg]) * p.A + sg;
-    int rank = 0;
-    for (int o = 0; o < p.A; ++o) {
-      const int key = ((row < p.A ? last_tab[phi_prev * p.A + o] : 0) * p.A + first_tab[phi * p.A + o]) * p.A + o;
-      rank += key < my_key ? 1 : 0;
-    }
-    order_tab[row * p.A + rank] = (uint8_t)sg;
+    if (p.phase_alt) phi_prev = phi == 0 ? p.phase_shift : 0;
+    const int qp = q + par * p.ring.shift - (par ^ 1) * p.ring.shift;  // its position in the previous layout's numbering
+    int ret = 0;
+    if (qp >= 0 && qp < NP && lastp_tab[phi_prev * NP + qp] != 0xFF) ret = 1 + (int)lastp_tab[phi_prev * NP + qp];
+    occ_tab[i] = (uint8_t)ret;
   }
+  __syncthreads();
+  // Reload order: the entries of the next super-step are loaded in the order in which their positions are
+  // vacated (under the PREVIOUS super-step's phase), ties in the order the next super-step needs them; entries
+  // nobody reads come last and are skipped.  Loading in index order would park the TMA thread on a position
+  // that is vacated late while others wait for their refill.
+  for (int i = threadIdx.x; i < (2 * p.A + 1) * NP; i += blockDim.x) {
+    const int row = i / NP, q = i - row * NP;
+    const bool steady = row < 2 * p.A;
+    const int phi = steady ? row % p.A : 0;
+    auto key_of = [&](int e) {
+      const int fr = firstp_tab[phi * NP + e];
+      return fr == 0xFF ? (1 << 30) + e : ((steady ? occ_tab[row * NP + e] : 0) * (p.A + 1) + fr) * NP + e;
+    };
+    const int my_key = key_of(q);
+    int rank = 0;
+    for (int o = 0; o < NP; ++o) rank += key_of(o) < my_key ? 1 : 0;
+    order_tab[row * NP + rank] = (uint8_t)q;
+  }
+  for (int i = threadIdx.x; i < 2 * p.A; i += blockDim.x) {
+    const int par = i / p.A, phi = i - par * p.A;
+    const int phi_n = tc_next_phase(p, phi);
+    uint32_t seam = 0;
+    for (int q = 0; q < NP; ++q) seam |= occ_tab[((par ^ 1) * p.A + phi_n) * NP + q] == p.A ? 1u << q : 0u;
+    seam_tab[i] = seam;
+    for (int y = 0; y < p.A; ++y) early_tab[i * p.A + y] = 0u;
+    const uint32_t need0 = need_tab[phi_n * p.A];
+    for (int q = 0; q < NP; ++q) {
+      if (!((need0 >> q) & 1u) || ((seam >> q) & 1u)) continue;
+      int ye = (int)occ_tab[((par ^ 1) * p.A + phi_n) * NP + q] + 2;   // vacated after step occ - 1, refill lands ~2 steps later
+      ye = ye < 2 ? 2 : ye;
+      if (ye <= p.A - 2) early_tab[i * p.A + ye] |= 1u << q;
+    }
+  }
+  int n_ent = 0;   // entries that are read at all (the same for every phase: every step of a super-step is visited)
+  for (int q = 0; q < NP; ++q) n_ent += firstp_tab[q] != 0xFF ? 1 : 0;
   ptx::tc_fence_before();
   __syncthreads();
   if (CL == 2) ptx::cluster_sync();   // the peer's barriers exist before anyone arrives on them remotely
@@ -683,7 +824,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     // ===================== producers: gather + interpolate -> swizzled A tiles =====================
     const int pw = warp - TC_WARP_PROD0, ptid = (int)threadIdx.x - TC_WARP_PROD0 * 32;
     const int pg = pw / GRP_WARPS, wq = pw % GRP_WARPS;
-    const int row_w = (CL == 2 ? 64 * (int)crank : 0) + WARP_ROWS * wq;   // first tile row of this warp
+    constexpr int ROWS_CTA = TC_M / CL;                                   // tile rows this CTA gathers
+    const int row_cta0 = CL == 2 ? ROWS_CTA * (int)crank : 0;
+    const int row_w = row_cta0 + WARP_ROWS * wq;                          // first tile row of this warp
     const int c = lane % CPR;
     const int row_l = lane / CPR;
     const uint4* rec_smem = reinterpret_cast<const uint4*>(smem_gen + (rec_base - smem_base));
@@ -701,10 +844,12 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       if (!centre && xr != ring) {
         // stage this radial ring's packed records (A slots x 128 vertices x 32 B) in smem
         producer_bar_sync();
+        // (a cluster-pair member only gathers - and stages - its own half of the tile rows)
         uint4* dst = reinterpret_cast<uint4*>(smem_gen + (rec_base - smem_base));
-        for (int y = 0; y < p.A; ++y)
-          dst[y * (TC_M * 2) + ptid] =
-              __ldg(p.recs + ((size_t)(xr * p.A + y) * p.v_pad + m0) * 2 + ptid);
+        if (ptid < ROWS_CTA * 2)
+          for (int y = 0; y < p.A; ++y)
+            dst[y * (ROWS_CTA * 2) + ptid] =
+                __ldg(p.recs + ((size_t)(xr * p.A + y) * p.v_pad + m0 + row_cta0) * 2 + ptid);
         producer_bar_sync();
         ring = xr;
       }
@@ -732,7 +877,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < ITEMS; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         } else if (!centre) {
-          const uint4* rec = rec_smem + (size_t)(y * TC_M + row_w + row_l) * 2;
+          const uint4* rec = rec_smem + (size_t)(y * ROWS_CTA + (row_w - row_cta0) + row_l) * 2;
           float4 x0[ITEMS], x1[ITEMS], x2[ITEMS];
           float w0[ITEMS], w1[ITEMS], w2[ITEMS];
 #pragma unroll
@@ -810,10 +955,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         }
         if (tr) trp[6] = clock64();
       }
-      if (!centre) {
-        phi += p.phase_shift;
-        phi -= phi >= p.A ? p.A : 0;
-      }
+      if (!centre) phi = tc_next_phase(p, phi);
     }
     // ===================== drain: TMEM -> this split's partial sums =====================
     ptx::mbar_wait(acc_full, 0);
@@ -834,47 +976,44 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     }
   } else if (warp == TC_WARP_TMA) {
     // ===================== TMA: weight tiles -> ring =====================
-    // (reload order: order_tab, built in the prologue)
-    uint32_t loads = 0;  // bit s = parity of the number of loads issued for angular tile s
-    const uint32_t lo_ring = (uint32_t)(p.ring.n_pos * b_tile_bytes);
+    // (reload order: order_tab, built in the prologue; an entry = one ring position of the current layout)
+    uint64_t fills = 0;  // bit P = parity of the number of fills of ring position P
+    const uint32_t lo_ring = (uint32_t)(n_ring * b_tile_bytes);
     int load_no = 0;
-    int phi = 0;
+    int phi = 0, par = 0;
     bool first_ss = true;
     for (int ss = ss_begin; ss < ss_end; ++ss) {
       const bool centre = ss >= p.R * p.nfc;
       const int xr = centre ? p.R : ss / p.nfc;
       const int fc = ss - xr * p.nfc;
-      const int n_y = centre ? 1 : p.A;
-      const uint8_t* order = order_tab + (first_ss ? p.A : phi) * p.A;
+      const int n_load = centre ? 1 : n_ent;
+      const uint8_t* order = order_tab + (first_ss ? 2 * p.A : par * p.A + phi) * NP;
       if (lane == 0) {
-        for (int i = 0; i < n_y; ++i) {
-          const int yb = centre ? 0 : order[i];
+        for (int i = 0; i < n_load; ++i) {
+          const int q = centre ? p.ring.pos[0] : order[i];          // entry; the centre slab uses tile 0's
+          const uint32_t pos = (uint32_t)(q + par * p.ring.shift);  // ring position in shared memory
+          int sg = p.ring.tile_of[q] + rel0;                        // angular tile (absolute)
+          sg -= sg >= p.A ? p.A : 0;
           const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && load_no < 128;
           long long* trp = tr ? p.trace + ((size_t)3 * 128 + load_no) * 8 : nullptr;
           ++load_no;
           if (tr) trp[0] = clock64();
-          ptx::mbar_wait(b_empty + 8u * yb, ((loads >> yb) & 1u) ^ 1u);
+          ptx::mbar_wait(b_empty + 8u * pos, ((uint32_t)(fills >> pos) & 1u) ^ 1u);
           if (tr) trp[1] = clock64();
-          const int col = (centre ? RA * p.F : (xr * p.A + yb) * p.F) + fc * KC;
-          const uint32_t pos = p.ring.pos[yb], dup = centre ? TC_NO_DUP : p.ring.dup[yb];
-          const uint32_t bar = b_full + 8u * (uint32_t)yb;
-          ptx::mbar_arrive_expect_tx(bar, (dup != TC_NO_DUP ? 2u : 1u) * (uint32_t)(NPROD * b_tile_bytes));
+          const int col = (centre ? RA * p.F : (xr * p.A + sg) * p.F) + fc * KC;
+          const uint32_t bar = b_full + 8u * (uint32_t)(par * NP + q);
+          ptx::mbar_arrive_expect_tx(bar, (uint32_t)(NPROD * b_tile_bytes));
           const uint32_t dst = b_base + pos * (uint32_t)b_tile_bytes;
           ptx::tma_load_2d(dst, &tmap_hi, bar, col, t0);
           if (X3) ptx::tma_load_2d(dst + lo_ring, &tmap_lo, bar, col, t0);
-          if (dup != TC_NO_DUP) {
-            const uint32_t dst2 = b_base + dup * (uint32_t)b_tile_bytes;
-            ptx::tma_load_2d(dst2, &tmap_hi, bar, col, t0);
-            if (X3) ptx::tma_load_2d(dst2 + lo_ring, &tmap_lo, bar, col, t0);
-          }
-          loads ^= 1u << yb;
+          fills ^= 1ull << pos;
           if (tr) trp[2] = clock64();
         }
       }
+      par ^= 1;   // centre super-steps alternate layouts too
       if (!centre) {
         first_ss = false;
-        phi += p.phase_shift;
-        phi -= phi >= p.A ? p.A : 0;
+        phi = tc_next_phase(p, phi);
       }
     }
   } else {
@@ -889,17 +1028,17 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       c.a_stage_lo = (uint32_t)(NPROD * A_TILE_BYTES) >> 4;
       c.b_lo0 = (b_base >> 4) | lo_flags;
       c.b_tile_lo = (uint32_t)b_tile_bytes >> 4;
-      c.b_lo_ring = (uint32_t)(p.ring.n_pos * b_tile_bytes) >> 4;
+      c.b_lo_ring = (uint32_t)(n_ring * b_tile_bytes) >> 4;
       c.tmem_base = tmem_base;
-      c.rot0 = rot0; c.g_cnt = g_cnt; c.n_units = n_units; c.off_anchor = off_anchor;
+      c.rot0 = rot0; c.g_cnt = g_cnt; c.n_units = n_units; c.off_anchor = off_anchor; c.rel0 = rel0;
       c.n_nc = min(ss_end, ss_nc) - min(ss_begin, ss_nc);
       c.n_c = ss_end > max(ss_begin, ss_nc) ? ss_end - max(ss_begin, ss_nc) : 0;
       c.mw = mw; c.n_mma = n_mma;
       const int n_own = (n_units - mw + n_mma - 1) / n_mma;
-      if (n_own == 1) tc_mma_role<KC, X3, CL, 1>(p, c, lane, need_tab, retire_tab);
-      else if (n_own == 2) tc_mma_role<KC, X3, CL, 2>(p, c, lane, need_tab, retire_tab);
-      else if (n_own <= 4) tc_mma_role<KC, X3, CL, 4>(p, c, lane, need_tab, retire_tab);
-      else tc_mma_role<KC, X3, CL, 8>(p, c, lane, need_tab, retire_tab);
+      if (n_own == 1) tc_mma_role<KC, X3, CL, 1>(p, c, lane, need_tab, retire_tab, seam_tab, early_tab);
+      else if (n_own == 2) tc_mma_role<KC, X3, CL, 2>(p, c, lane, need_tab, retire_tab, seam_tab, early_tab);
+      else if (n_own <= 4) tc_mma_role<KC, X3, CL, 4>(p, c, lane, need_tab, retire_tab, seam_tab, early_tab);
+      else tc_mma_role<KC, X3, CL, 8>(p, c, lane, need_tab, retire_tab, seam_tab, early_tab);
     }
   }
 
@@ -1089,11 +1228,6 @@ static int tc_launch_k(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwd
 
 // Pairs of rotation groups share their gathered tiles through a 2-CTA cluster when the group count
 // is even (GCB_TC_CLUSTER=0 switches the pairing off for A/B measurements).
-static bool tc_use_pairs() {
-  static const bool use_pairs = !(getenv("GCB_TC_CLUSTER") && atoi(getenv("GCB_TC_CLUSTER")) == 0);
-  return use_pairs;
-}
-
 template <int KC, bool X3>
 static int tc_launch(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdParams& p, const TcConfig& cfg,
                      dim3 grid, cudaStream_t st) {
@@ -1111,8 +1245,34 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   (void)v_src;
   const bool x3 = precision == GCB_PREC_TF32X3;
   static const bool no_merge = getenv("GCB_TC_NOMERGE") && atoi(getenv("GCB_TC_NOMERGE")) != 0;
-  TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3, no_merge ? 0 : tc_uniform_step(rot, n_rot, A));
+  const int dstep = no_merge ? 0 : tc_uniform_step(rot, n_rot, A);
+  TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3, dstep);
   GCB_REQUIRE(cfg.ok, GCB_EUNSUPPORTED, "tc_conv_fwd: no tcgen05 tiling for A=%d F=%d T=%d", A, F, T);
+  // Weight ring: spend spare shared memory on a second, shifted layout when that buys refill slack (3 steps
+  // cover the commit -> TMA -> barrier latency) without changing the tiling or starving the A ring.
+  int phase_shift = 0;
+  {
+    static const int shift_env = getenv("GCB_TC_RINGSHIFT") ? atoi(getenv("GCB_TC_RINGSHIFT")) : -1;   // experiments
+    static const int phase_env = getenv("GCB_TC_PHASE") ? atoi(getenv("GCB_TC_PHASE")) : -1;
+    const bool pairs = tc_use_pairs() && cfg.n_groups % 2 == 0 && cfg.kc >= 16;
+    int best_slack = -1;
+    phase_shift = tc_pick_phase_shift(rot, n_rot, A, cfg.g, cfg.n_groups, pairs, cfg.ring, false, &best_slack);
+    for (int rs = 1; rs <= 4; ++rs) {
+      if (shift_env >= 0 && rs != shift_env) continue;
+      if (shift_env < 0 && best_slack >= 3) break;
+      TcConfig c2 = tc_pick_config(A, F, T, n_rot, x3, dstep, rs);
+      if (!c2.ok || c2.kc != cfg.kc || c2.ring.m != cfg.ring.m || c2.n_t != cfg.n_t || c2.g != cfg.g || c2.ns_a < 4) break;
+      int sl2 = -1;
+      const int ph2 = tc_pick_phase_shift(rot, n_rot, A, c2.g, c2.n_groups, pairs, c2.ring, true, &sl2);   // two layouts: two phases
+      if (sl2 > best_slack || shift_env >= 0) { best_slack = sl2; phase_shift = ph2; cfg = c2; }
+    }
+    if (phase_env >= 0) phase_shift = phase_env % A;
+    static const bool verbose = getenv("GCB_TC_VERBOSE") != nullptr;
+    if (verbose)
+      fprintf(stderr, "[gcb] tc forward: kc %d n_t %d g %d groups %d m %d ring %d+%d positions, phase shift %d, refill slack %d steps, A stages %d\n",
+              cfg.kc, cfg.n_t, cfg.g, cfg.n_groups, cfg.ring.m, cfg.ring.n_pos, cfg.ring.shift, phase_shift,
+              tc_refill_slack(rot, n_rot, A, cfg.g, cfg.n_groups, pairs, cfg.ring, phase_shift, cfg.ring.shift > 0), cfg.ns_a);
+  }
   GCB_REQUIRE(workspace_bytes >= tc_fwd_workspace_bytes(v_out, R, A, F, T, n_rot, precision), GCB_EWORKSPACE,
               "tc_conv_fwd: workspace too small");
   GCB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)bias % 16 == 0) &&
@@ -1149,11 +1309,9 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   p.v_out = v_out; p.v_pad = v_pad; p.R = R; p.A = A; p.F = F; p.T = T; p.n_rot = n_rot;
   p.nfc = F / cfg.kc; p.n_t = cfg.n_t; p.g = cfg.g; p.ns_a = cfg.ns_a; p.tmem_cols = cfg.tmem_cols;
   p.ksplit = ksplit;
-  {
-    static const int shift_env = getenv("GCB_TC_PHASE") ? atoi(getenv("GCB_TC_PHASE")) : -1;   // experiments
-    const bool pairs = tc_use_pairs() && cfg.n_groups % 2 == 0 && cfg.kc >= 16;
-    p.phase_shift = shift_env >= 0 ? shift_env % A : tc_pick_phase_shift(rot, n_rot, A, cfg.g, cfg.n_groups, pairs);
-  }
+  p.phase_shift = phase_shift;
+  p.phase_alt = cfg.ring.shift > 0 ? 1 : 0;
+  p.bar_bytes = (int)tc_bar_bytes(cfg.ring.n_pos, cfg.ring.n_pos + cfg.ring.shift);
   static const int debug = getenv("GCB_TC_DEBUG") ? atoi(getenv("GCB_TC_DEBUG")) : 0;
   p.debug = debug;
   p.ring = cfg.ring;
