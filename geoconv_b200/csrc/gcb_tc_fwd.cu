@@ -51,13 +51,15 @@ namespace gcb {
 constexpr int TC_M = 128;
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_MMA_WARPS = 2;
-constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + TC_MMA_WARPS) * 32;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2 + TC_MMA_WARPS) * 32;
 // Warp roles.  The two control warps come FIRST: measured (clock64 traces), the warp scheduler favours
 // the oldest (lowest-numbered) ready warp, and with the producers in front the TMA warp needed
 // ~5000 cycles for ~60 instructions whenever the producers of its scheduler were busy.
 constexpr int TC_WARP_TMA = 0;
 constexpr int TC_WARP_MMA = 1;
-constexpr int TC_WARP_PROD0 = TC_WARP_MMA + TC_MMA_WARPS;
+constexpr int TC_WARP_SCOUT = TC_WARP_MMA + TC_MMA_WARPS;   // collects the landing barriers of a tile into one
+constexpr int TC_WARP_PROD0 = TC_WARP_SCOUT + 1;
+constexpr int TC_READY_RING = 16;   // tile-ready barriers (> the A ring depth, so the scout cannot lap a waiter)
 constexpr int TC_WARP_ROWS = TC_M / TC_PRODUCER_WARPS;   // tile rows one producer warp fills
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_G_MAX = 8;              // rotations per CTA (accumulator groups) upper bound
@@ -151,11 +153,13 @@ static bool tc_use_pairs() {
 
 // schedules of the weight ring in shared memory, per phase (and super-step parity), in ring-POSITION space
 static size_t tc_tab_bytes(int A, int n_pos) {
-  return align_up((size_t)A * A * 16 + 8 * A + (size_t)A * n_pos * 2 + (size_t)(2 * A + 1) * n_pos + (size_t)2 * A * n_pos + 64, 16);
+  return align_up((size_t)A * A * 8 + 8 * A + (size_t)A * n_pos * 2 + (size_t)(2 * A + 1) * n_pos + (size_t)2 * A * n_pos + 64, 16);
 }
 // mbarriers: A-stage full/empty (<= 8 stages), per (parity, position) full, per absolute position empty,
 // accumulators; TMEM slot
-static size_t tc_bar_bytes(int n_pos, int n_ring) { return align_up((size_t)8 * (16 + 2 * n_pos + n_ring + 1) + 16, 64); }
+static size_t tc_bar_bytes(int n_pos, int n_ring) {
+  return align_up((size_t)8 * (16 + 2 * n_pos + n_ring + 1 + TC_READY_RING) + 16, 64);
+}
 
 // Refill slack of the weight ring for a visiting order that advances `phase_shift` steps per super-step and a
 // ring that alternates between two layouts `ring.shift` positions apart: the smallest number of whole steps
@@ -360,7 +364,7 @@ struct TcTileIt {
 
 // Barrier / operand addresses the MMA warp works with
 struct TcMmaCtx {
-  uint32_t a_full, a_empty, b_full, b_empty, acc_full;   // mbarrier addresses (arrays indexed * 8)
+  uint32_t a_full, a_empty, b_full, b_empty, acc_full, ready;   // mbarrier addresses (arrays indexed * 8)
   uint32_t a_lo0, a_stage_lo;   // descriptor low word of A stage 0, distance between stages (>> 4)
   uint32_t b_lo0, b_tile_lo, b_lo_ring;   // same for ring position 0, one tile, hi ring -> lo ring
   uint32_t tmem_base;
@@ -427,7 +431,7 @@ __device__ __forceinline__ void tc_wait_entries(uint32_t bar0, uint32_t bits, ui
 template <int KC, bool X3, int CL, int NU>
 __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx& c, int lane,
                                             const uint32_t* need_tab, const uint32_t* retire_tab,
-                                            const uint32_t* seam_tab, const uint32_t* early_tab) {
+                                            const uint32_t* seam_tab) {
   constexpr int ROW_BYTES = KC * 4;
   constexpr int KS = KC / 8;
   constexpr uint32_t A_LO_HALF = (uint32_t)(TC_M * ROW_BYTES) >> 4;
@@ -459,13 +463,10 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
   // (weight tiles to wait for, tiles to release, descriptor address words of the units' weight tiles), read
   // from shared / constant memory once per super-step; a tile then costs a few shuffles instead of dependent
   // memory reads in the issuing thread's critical path.
-  uint32_t need_l = 0, retire_l = 0, early_l = 0, blo_l[NU];
-  auto load_schedule = [&](int ph, int layout, uint32_t ring_off, const int (&s0)[NU], uint32_t& need_o,
-                           uint32_t& retire_o, uint32_t& early_o, uint32_t (&blo_o)[NU]) {
+  uint32_t retire_l = 0, blo_l[NU];
+  auto load_schedule = [&](int ph, uint32_t ring_off, const int (&s0)[NU], uint32_t& retire_o, uint32_t (&blo_o)[NU]) {
     const int yy = lane < A_ ? lane : 0;
-    need_o = need_tab[ph * A_ + yy];
     retire_o = retire_tab[ph * A_ + yy];
-    early_o = early_tab[(layout * A_ + ph) * A_ + yy];
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       int sg = s0[u] + yy;
@@ -473,24 +474,23 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
       blo_o[u] = c.b_lo0 + ((uint32_t)p.ring.pos[sg] + ring_off) * c.b_tile_lo;
     }
   };
-  // Loop state that swaps at every super-step (the two ring layouts alternate): barrier set, layout offset and,
-  // per ring entry, the parity of the barrier phase the next wait is for.  All in registers.
-  const uint32_t np8 = 8u * (uint32_t)p.ring.n_pos;
-  uint32_t bf_cur = c.b_full, bf_nxt = c.b_full + np8;
-  uint32_t ring_cur = 0u, ring_nxt = (uint32_t)p.ring.shift;
-  uint32_t seen_cur = 0u, seen_nxt = 0u;
-  load_schedule(0, 0, ring_cur, sl, need_l, retire_l, early_l, blo_l);
+  // wait until the scout has seen everything tile `t` reads (one barrier per tile, ring of TC_READY_RING)
+  auto wait_ready = [&](int t) {
+    ptx::mbar_wait(c.ready + 8u * (uint32_t)(t & (TC_READY_RING - 1)), (uint32_t)(t / TC_READY_RING) & 1u);
+    ptx::tc_fence_after();
+  };
+  uint32_t ring_cur = 0u, ring_nxt = (uint32_t)p.ring.shift;   // the two ring layouts alternate per super-step
+  load_schedule(0, ring_cur, sl, retire_l, blo_l);
   uint32_t b_lo[NU];
 #pragma unroll
   for (int u = 0; u < NU; ++u) b_lo[u] = __shfl_sync(0xffffffffu, blo_l[u], 0);
-  if (c.n_nc > 0) {   // readiness of the very first tile; every later tile is waited for one tile ahead
-    ptx::mbar_wait(c.a_full, 0);
-    tc_wait_entries(bf_cur, __shfl_sync(0xffffffffu, need_l, 0), seen_cur);
-    ptx::tc_fence_after();
-  }
+  const int n_tiles = c.n_nc * A_ + c.n_c;
+  if (n_tiles > 0) wait_ready(0);   // every later tile is waited for one tile ahead
   for (int k = 0; k < c.n_nc; ++k) {
     const int phi_n = tc_next_phase(p, phi);
-    const uint32_t seam = seam_tab[(k & 1) * A_ + phi];
+    // the next super-step's first tile may need an entry whose ring position this super-step only vacates with
+    // the commit of its last tile: then that tile must be committed before the wait (else: deadlock)
+    const bool seam_dep = (seam_tab[(k & 1) * A_ + phi] & need_tab[phi_n * A_]) != 0u;
     int sl_n[NU];            // the units' first weight tiles at step 0 of the next super-step
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
@@ -498,8 +498,7 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
       sl_n[u] += sl_n[u] < 0 ? A_ : 0;
       sl_n[u] -= sl_n[u] >= A_ ? A_ : 0;
     }
-    uint32_t need_nl = 0, retire_nl = 0, early_nl = 0, blo_nl[NU];
-    uint32_t early_done = 0;   // entries of the next super-step already waited for
+    uint32_t retire_nl = 0, blo_nl[NU];
 #pragma unroll
     for (int u = 0; u < NU; ++u) blo_nl[u] = 0;
     for (int y = 0; y < A_; ++y, ++n) {
@@ -511,38 +510,18 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
       __syncwarp();
       // ---- while the first half executes: this step's releases, the next tile's addresses and readiness ----
       const uint32_t rm = __shfl_sync(0xffffffffu, retire_l, y);
-      int stage_n = stage + 1;
-      uint32_t par_n = par;
-      if (stage_n == ns_a_) { stage_n = 0; par_n ^= 1u; }
-      uint32_t defer = 0;
+      const bool last_y = y + 1 == A_;
       uint32_t b_lo_n[NU];
-      if (y + 1 < A_) {
+      if (!last_y) {
 #pragma unroll
         for (int u = 0; u < NU; ++u) b_lo_n[u] = __shfl_sync(0xffffffffu, blo_l[u], y + 1);
-        const uint32_t nm = __shfl_sync(0xffffffffu, need_l, y + 1);
-        ptx::mbar_wait(c.a_full + 8u * stage_n, par_n);
-        if (trp) trp[3] = clock64();
-        tc_wait_entries(bf_cur, nm, seen_cur);
-        if (k + 1 < c.n_nc) {
-          const uint32_t ew = __shfl_sync(0xffffffffu, early_l, y);
-          tc_wait_entries(bf_nxt, ew, seen_nxt);
-          early_done |= ew;
-        }
       } else {
-        if (k + 1 < c.n_nc) load_schedule(phi_n, (k & 1) ^ 1, ring_nxt, sl_n, need_nl, retire_nl, early_nl, blo_nl);
+        if (k + 1 < c.n_nc) load_schedule(phi_n, ring_nxt, sl_n, retire_nl, blo_nl);
 #pragma unroll
         for (int u = 0; u < NU; ++u) b_lo_n[u] = __shfl_sync(0xffffffffu, blo_nl[u], 0);
-        if (k + 1 < c.n_nc) {
-          // first step of the next super-step: an entry whose ring position is only vacated at THIS step is
-          // refilled after the commit below - waiting for it here would deadlock, so it is waited for afterwards
-          const uint32_t nmn = __shfl_sync(0xffffffffu, need_nl, 0);
-          defer = nmn & seam;
-          ptx::mbar_wait(c.a_full + 8u * stage_n, par_n);
-          if (trp) trp[3] = clock64();
-          tc_wait_entries(bf_nxt, nmn & ~defer & ~early_done, seen_nxt);
-        }
       }
-      ptx::tc_fence_after();
+      const bool wait_late = last_y && (seam_dep || k + 1 == c.n_nc);   // (centre tiles wait at their own top)
+      if (n + 1 < n_tiles && !wait_late) wait_ready(n + 1);
       if (trp) trp[1] = clock64();
       if (ptx::elect_one()) {
         if (!no_mma) {
@@ -560,28 +539,20 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
         else ptx::umma_commit(c.a_empty + 8u * stage);
       }
       __syncwarp();
-      if (defer) {
-        tc_wait_entries(bf_nxt, defer, seen_nxt);
-        ptx::tc_fence_after();
-      }
+      if (n + 1 < n_tiles && wait_late && k + 1 < c.n_nc) wait_ready(n + 1);
       if (trp) trp[2] = clock64();
       accum = 1u;
 #pragma unroll
       for (int u = 0; u < NU; ++u) b_lo[u] = b_lo_n[u];
-      stage = stage_n;
-      par = par_n;
+      if (++stage == ns_a_) { stage = 0; par ^= 1u; }
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       sl[u] = sl_n[u];
       blo_l[u] = blo_nl[u];
     }
-    need_l = need_nl;
     retire_l = retire_nl;
-    early_l = early_nl;
     phi = phi_n;
-    { const uint32_t t = seen_cur; seen_cur = seen_nxt; seen_nxt = t; }
-    { const uint32_t t = bf_cur; bf_cur = bf_nxt; bf_nxt = t; }
     { const uint32_t t = ring_cur; ring_cur = ring_nxt; ring_nxt = t; }
   }
   // centre tiles: X[k] * Wself - one weight tile (the ring position of tile 0 in the current layout) serves
@@ -591,9 +562,7 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
   for (int k = 0; k < c.n_c; ++k, ++n) {
     const uint32_t pos_c = q_c + ring_cur;
     const uint32_t b_lo_c = c.b_lo0 + pos_c * c.b_tile_lo;
-    ptx::mbar_wait(c.a_full + 8u * stage, par);
-    tc_wait_entries(bf_cur, 1u << q_c, seen_cur);
-    ptx::tc_fence_after();
+    if (n > 0) wait_ready(n);
     const uint32_t a_lo = c.a_lo0 + (uint32_t)stage * c.a_stage_lo;
     if (ptx::elect_one()) {
       if (!no_mma) {
@@ -621,8 +590,6 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
     __syncwarp();
     accum = 1u;
     if (++stage == ns_a_) { stage = 0; par ^= 1u; }
-    { const uint32_t t = seen_cur; seen_cur = seen_nxt; seen_nxt = t; }
-    { const uint32_t t = bf_cur; bf_cur = bf_nxt; bf_nxt = t; }
     { const uint32_t t = ring_cur; ring_cur = ring_nxt; ring_nxt = t; }
   }
   if (ptx::elect_one()) ptx::umma_commit(c.acc_full);   // accumulators complete
@@ -668,7 +635,11 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   const uint32_t b_full = a_empty + 8u * p.ns_a;
   const uint32_t b_empty = b_full + 16u * NP;      // per ring POSITION: every reader of its occupant is done
   const uint32_t acc_full = b_empty + 8u * n_ring;
-  const uint32_t tmem_slot = acc_full + 8u;
+  // tile n is ready (its A stage and every weight entry it reads have landed): the scout warp collects the
+  // individual barriers, so an issuing warp pays ONE barrier wait per tile (each costs the issuing thread
+  // ~250 cycles under load; 2-5 of them per tile boundary drained the tensor pipe, traced)
+  const uint32_t ready = acc_full + 8u;
+  const uint32_t tmem_slot = ready + 8u * TC_READY_RING;
   const uint32_t tab_base = bar_base + (uint32_t)p.bar_bytes;   // weight-ring schedules, built below
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));     // generic view of smem_base
   const int AA = p.A * p.A;
@@ -677,13 +648,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   uint32_t* retire_tab = need_tab + AA;
   // [parity][phase]: entries of the NEXT super-step whose position is only vacated by the last step of this one
   uint32_t* seam_tab = retire_tab + AA;
-  // [parity][phase][step]: entries of the NEXT super-step's first step that can already be waited for at this
-  // step (their refill was issued at least two steps earlier): spreads the barrier waits of a seam over the
-  // preceding tiles - each wait costs ~250 cycles of the issuing thread under load, four of them at one tile
-  // boundary drained the tensor pipe
-  uint32_t* early_tab = seam_tab + 2 * p.A;
   // [phase][entry]: first / last step at which the entry is read (0xFF: never - then it is never loaded)
-  uint8_t* firstp_tab = reinterpret_cast<uint8_t*>(early_tab + 2 * AA);
+  uint8_t* firstp_tab = reinterpret_cast<uint8_t*>(seam_tab + 2 * p.A);
   uint8_t* lastp_tab = firstp_tab + p.A * NP;
   // [parity * A + phase][i]: the i-th entry the TMA warp (re)loads for such a super-step (row 2A: the CTA's
   // first super-step, when every position is vacant)
@@ -730,6 +696,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     for (int s = 0; s < 2 * NP; ++s) ptx::mbar_init(b_full + 8u * s, 1);
     for (int s = 0; s < n_ring; ++s) ptx::mbar_init(b_empty + 8u * s, (uint32_t)n_mma);
     ptx::mbar_init(acc_full, (uint32_t)n_mma);
+    for (int s = 0; s < TC_READY_RING; ++s) ptx::mbar_init(ready + 8u * s, 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tensormap(&tmap_hi);
     if (X3) ptx::prefetch_tensormap(&tmap_lo);
@@ -802,14 +769,6 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     uint32_t seam = 0;
     for (int q = 0; q < NP; ++q) seam |= occ_tab[((par ^ 1) * p.A + phi_n) * NP + q] == p.A ? 1u << q : 0u;
     seam_tab[i] = seam;
-    for (int y = 0; y < p.A; ++y) early_tab[i * p.A + y] = 0u;
-    const uint32_t need0 = need_tab[phi_n * p.A];
-    for (int q = 0; q < NP; ++q) {
-      if (!((need0 >> q) & 1u) || ((seam >> q) & 1u)) continue;
-      int ye = (int)occ_tab[((par ^ 1) * p.A + phi_n) * NP + q] + 2;   // vacated after step occ - 1, refill lands ~2 steps later
-      ye = ye < 2 ? 2 : ye;
-      if (ye <= p.A - 2) early_tab[i * p.A + ye] |= 1u << q;
-    }
   }
   int n_ent = 0;   // entries that are read at all (the same for every phase: every step of a super-step is visited)
   for (int q = 0; q < NP; ++q) n_ent += firstp_tab[q] != 0xFF ? 1 : 0;
@@ -868,7 +827,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         if (++stage == p.ns_a) { stage = 0; empty_par ^= 1u; }
         if ((n & (NGRP - 1)) != pg) continue;
         const bool tr = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && wq == 0 &&
-                        pg < 2 && n < 128;
+                        pg < 1 && n < 128;
         long long* trp = tr ? p.trace + ((size_t)pg * 128 + n) * 8 : nullptr;
         if (tr) trp[0] = clock64();
         const float* xcol = p.x + fc * KC + c * 4;
@@ -1016,6 +975,41 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         phi = tc_next_phase(p, phi);
       }
     }
+  } else if (warp == TC_WARP_SCOUT) {
+    // ===================== scout: per tile, wait for its A stage and weight entries, then publish =====================
+    if (lane == 0) {
+      const int ss_nc = p.R * p.nfc;
+      const int n_nc = min(ss_end, ss_nc) - min(ss_begin, ss_nc);
+      const int n_c = ss_end > max(ss_begin, ss_nc) ? ss_end - max(ss_begin, ss_nc) : 0;
+      uint32_t seen_cur = 0u, seen_nxt = 0u;
+      uint32_t bf_cur = b_full, bf_nxt = b_full + 8u * (uint32_t)NP;
+      int stage = 0, n = 0, phi = 0;
+      uint32_t par = 0;
+      auto publish = [&]() {
+        ptx::mbar_arrive(ready + 8u * (uint32_t)(n & (TC_READY_RING - 1)));
+        ++n;
+        if (++stage == p.ns_a) { stage = 0; par ^= 1u; }
+      };
+      for (int k = 0; k < n_nc + n_c; ++k) {
+        const bool centre = k >= n_nc;
+        const int n_y = centre ? 1 : p.A;
+        for (int y = 0; y < n_y; ++y) {
+          long long* trp = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && n < 128
+                               ? p.trace + ((size_t)1 * 128 + n) * 8 : nullptr;
+          if (trp) trp[0] = clock64();
+          // weight entries first: they landed steps ago (refill slack), so their waits (~350 cycles each,
+          // four at the first step of a super-step) overlap the producers' latency for this tile's A stage
+          tc_wait_entries(bf_cur, centre ? 1u << p.ring.pos[0] : need_tab[phi * p.A + y], seen_cur);
+          if (trp) trp[1] = clock64();
+          ptx::mbar_wait(a_full + 8u * stage, par);
+          if (trp) trp[2] = clock64();
+          publish();
+        }
+        if (!centre) phi = tc_next_phase(p, phi);
+        { const uint32_t t = seen_cur; seen_cur = seen_nxt; seen_nxt = t; }
+        { const uint32_t t = bf_cur; bf_cur = bf_nxt; bf_nxt = t; }
+      }
+    }
   } else {
     // ===================== MMA issuer =====================
     const int mw = warp - TC_WARP_MMA;
@@ -1024,6 +1018,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       const uint32_t lo_flags = (uint32_t)(ptx::make_kmajor_desc<ROW_BYTES>(0) & 0xFFFF0000ull);
       TcMmaCtx c;
       c.a_full = a_full; c.a_empty = a_empty; c.b_full = b_full; c.b_empty = b_empty; c.acc_full = acc_full;
+      c.ready = ready;
       c.a_lo0 = (a_base >> 4) | lo_flags;
       c.a_stage_lo = (uint32_t)(NPROD * A_TILE_BYTES) >> 4;
       c.b_lo0 = (b_base >> 4) | lo_flags;
@@ -1035,10 +1030,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       c.n_c = ss_end > max(ss_begin, ss_nc) ? ss_end - max(ss_begin, ss_nc) : 0;
       c.mw = mw; c.n_mma = n_mma;
       const int n_own = (n_units - mw + n_mma - 1) / n_mma;
-      if (n_own == 1) tc_mma_role<KC, X3, CL, 1>(p, c, lane, need_tab, retire_tab, seam_tab, early_tab);
-      else if (n_own == 2) tc_mma_role<KC, X3, CL, 2>(p, c, lane, need_tab, retire_tab, seam_tab, early_tab);
-      else if (n_own <= 4) tc_mma_role<KC, X3, CL, 4>(p, c, lane, need_tab, retire_tab, seam_tab, early_tab);
-      else tc_mma_role<KC, X3, CL, 8>(p, c, lane, need_tab, retire_tab, seam_tab, early_tab);
+      if (n_own == 1) tc_mma_role<KC, X3, CL, 1>(p, c, lane, need_tab, retire_tab, seam_tab);
+      else if (n_own == 2) tc_mma_role<KC, X3, CL, 2>(p, c, lane, need_tab, retire_tab, seam_tab);
+      else if (n_own <= 4) tc_mma_role<KC, X3, CL, 4>(p, c, lane, need_tab, retire_tab, seam_tab);
+      else tc_mma_role<KC, X3, CL, 8>(p, c, lane, need_tab, retire_tab, seam_tab);
     }
   }
 
@@ -1337,7 +1332,7 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
     GCB_CUDA_OK(cudaMemcpyAsync(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost, st));
     GCB_CUDA_OK(cudaStreamSynchronize(st));
     long long t0 = host[0];
-    const char* names[4] = {"prod g0: start issued landed empty_ok stored fenced arrived", "prod g1",
+    const char* names[4] = {"prod g0: start issued landed empty_ok stored fenced arrived", "scout: start entries a_full",
                             "mma: start waited done a_full_next", "tma: start slot_free issued ss_top"};
     for (int role = 0; role < 4; ++role) {
       fprintf(stderr, "[trace %s]\n", names[role]);
