@@ -211,7 +211,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def run_ours(args):
@@ -227,9 +227,6 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        # NCCL writes its debug lines (e.g. "NCCL version ..." when NCCL_DEBUG is set in the environment) to
-        # stdout by default; stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
@@ -599,9 +596,29 @@ def run_ours(args):
         "clocks": clocks,
         "flops_per_step": {"fwd": fwd_flops, "bwd": bwd_flops},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_FD = None
+
+
+def emit(text):
+    """The one JSON line, written to the process's ORIGINAL stdout."""
+    if _RESULT_FD is None:
+        print(text, flush=True)
+    else:
+        os.write(_RESULT_FD, (text + "\n").encode())
+
+
+def quiet_stdout():
+    """stdout carries exactly one JSON line: anything a library prints there at the C level (NCCL writes
+    "NCCL version ..." to stdout when NCCL_DEBUG is set in the environment) is sent to stderr instead."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
@@ -617,6 +634,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
