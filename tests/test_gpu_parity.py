@@ -275,3 +275,25 @@ def test_survives_torch_compile():
     out.sum().backward()
     assert nerr(out, ref) < 1e-6
     assert nerr(net.conv._template_neighbor_weights.grad, ref_grad) < 1e-6
+
+
+@pytest.mark.gpu
+def test_faust_shape_randn_signal_stays_inside_fp32_tolerance():
+    """Parity stress of SURVEY.md §8d: a randn signal makes the contraction cancel heavily, which is where the
+    truncating fp32 accumulation of the tensor core shows; the K-split count is chosen so that the fp32 mode
+    stays inside 1e-5 against a float64 evaluation of the reference algorithm."""
+    import os
+    v, f, r, a, t = 6890, 544, 5, 8, 96
+    wn, ws, b = O.make_weights(t, r, a, f, seed=0)
+    signal = O.make_signal(v, f, seed=1, kind="randn")
+    bary = O.make_bary(v, r, a, seed=1)
+    prior = torch.from_numpy(O.geodesic_prior(O.template_matrix(r, a, 0.028)))
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref64 = O.conv_forward(signal.double(), bary, wn.double(), ws.double(), b.double(), prior.double(), "relu", 1)
+    layer = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.028,
+                         precision="fp32")
+    layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
+    layer = layer.to("cuda:0")
+    with torch.no_grad():
+        y = layer([signal.to("cuda:0"), bary.to("cuda:0")])
+    assert nerr(y, ref64) < TOL_FP32
