@@ -173,7 +173,7 @@ extern "C" int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, 
   char* ws = (char*)workspace;
   float* d_full = (float*)ws;
   ws += align_up((size_t)v_out * R * A * F * sizeof(float), 256);
-  if (precision != GCB_PREC_FP32 && w_eff && tc_bwd_supported(R, A, F, T))
+  if (precision != GCB_PREC_FP32 && tc_bwd_supported(R, A, F, T))   // (w_eff == NULL: centre-only GEMMs, no CSR needed)
     return tc_conv_bwd(x, idx, w, w_eff, w_self, h, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T,
                        precision, accumulate, interp, d_x, d_w_eff, d_w_self, d_bias, workspace, workspace_bytes, st);
   rc = ffma_conv_bwd(x, idx, w, w_eff, h, rot_sel, v_out, v_src, R, A, F, T, accumulate, d_w_eff, d_w_self,

@@ -107,6 +107,7 @@ struct FwdOp {
   static constexpr bool kAContigK = true, kBContigK = true;
   int M, N, K;
   int KRA, A, F, T, act;
+  int n_bcast;   // > 1: centre-only layer (all-zero prior) - every rotation gets the same row: N = T, written n_bcast times
   const float *interp, *x, *w_eff, *w_self, *bias;
   float* y;
   RotTable rot;
@@ -124,7 +125,12 @@ struct FwdOp {
   }
   __device__ void store(int m, int n, float acc) const {
     int t = n % T;
-    y[(size_t)m * N + n] = act_apply(act, acc + bias[t]);
+    const float v = act_apply(act, acc + bias[t]);
+    if (n_bcast <= 1) {
+      y[(size_t)m * N + n] = v;
+    } else {
+      for (int i = 0; i < n_bcast; ++i) y[((size_t)m * n_bcast + i) * T + t] = v;
+    }
   }
 };
 
@@ -181,7 +187,10 @@ int ffma_conv_fwd(const float* x, const int32_t* idx, const float* w, const floa
     GCB_LAUNCH_OK();
   }
   FwdOp op;
-  op.M = v_out; op.N = n_rot * T; op.KRA = w_eff ? R * A * F : 0; op.K = op.KRA + F;
+  // ConvZero (reference: conv_zero.py:12-15 still pays the dense cost): the neighbour term vanishes, so all
+  // rotations share one row - contract once (N = T) and write it n_rot times
+  op.M = v_out; op.N = w_eff ? n_rot * T : T; op.KRA = w_eff ? R * A * F : 0; op.K = op.KRA + F;
+  op.n_bcast = w_eff ? 1 : n_rot;
   op.A = A; op.F = F; op.T = T; op.act = act;
   op.interp = interp; op.x = x; op.w_eff = w_eff; op.w_self = w_self; op.bias = bias; op.y = y;
   op.rot = rot;

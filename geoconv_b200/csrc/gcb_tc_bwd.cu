@@ -343,6 +343,17 @@ __global__ void k_bw_bias_partial(const float* __restrict__ h, int v_out, int T,
   }
 }
 
+// rows of h as a GEMM operand: tf32 hi (+ lo), zero rows from v_out up to v_pad
+__global__ void k_bw_split_rows(const float* __restrict__ h, int v_out, int v_pad, int T, float* __restrict__ hi,
+                                float* __restrict__ lo) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= (int64_t)v_pad * T) return;
+  const float val = e < (int64_t)v_out * T ? h[e] : 0.f;
+  const float hv = ptx::to_tf32(val);
+  hi[e] = hv;
+  if (lo) lo[e] = val - hv;
+}
+
 // d_bias[t] (+)= sum over the per-block partial sums (fixed order)
 __global__ void k_bw_bias_final(const float* __restrict__ part, int nblocks, int T, int accumulate,
                                 float* __restrict__ d_bias) {
@@ -447,6 +458,32 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
   float* wc_lo = x3 ? (float*)(ws + L.wcat / 2) : nullptr;
   ws += L.wcat;
   int rc;
+
+  if (!w_eff) {
+    // ---- centre-only layer (all-zero prior, ConvZero): G degenerates to its centre slab, h itself ----
+    //   d_w_self = h^T X,  d_x = h Wself  (the same two tensor-core GEMMs with R*A = 0),  d_w_eff = 0
+    const TcGLayout GL = tc_g_layout(v_src, 0, 1, F, T, x3);
+    float* g_hi = (float*)ws;
+    float* g_lo = x3 ? g_hi + (size_t)GL.v_pad * GL.kg : nullptr;
+    ws += tc_g_layout(v_src, R, A, F, T, x3).g_bytes;
+    float* x_hi = (float*)ws;
+    float* x_lo = x3 ? x_hi + (size_t)v_src * F : nullptr;
+    ws += GL.xsplit_bytes;
+    float* partial = (float*)ws;
+    k_bw_bias_partial<<<dim3((unsigned)L.bias_blocks, (unsigned)ceil_div64(T, 32)), dim3(32, 8), 0, st>>>(
+        h, v_out, T, L.bias_rows, bias_part);
+    GCB_LAUNCH_OK();
+    k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.bias_blocks, T, accumulate, d_bias);
+    GCB_LAUNCH_OK();
+    if (!accumulate) GCB_CUDA_OK(cudaMemsetAsync(d_w_eff, 0, (size_t)T * R * A * F * sizeof(float), st));
+    k_bw_split_rows<<<(unsigned)ceil_div64((int64_t)GL.v_pad * T, 256), 256, 0, st>>>(h, v_out, GL.v_pad, T, g_hi, g_lo);
+    GCB_LAUNCH_OK();
+    rc = tc_dw_from_g(g_hi, g_lo, x, v_src, 0, 1, F, T, x3, accumulate, nullptr, d_w_self, x_hi, x_lo, partial, st);
+    if (rc || !d_x) return rc;
+    rc = tc_build_wcat(nullptr, w_self, T, 0, 1, F, wc_hi, wc_lo, st);
+    if (rc) return rc;
+    return tc_dx_from_g(g_hi, g_lo, wc_hi, wc_lo, v_src, 0, 1, F, T, x3, accumulate, d_x, st);
+  }
 
   if (csr_row_ptr && csr_entries) {
     // ---- both gradients through G: dWcat = G^T X, dSignal = G Wcat (gcb_tc_dx.cu) ----
