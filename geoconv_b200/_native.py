@@ -14,10 +14,10 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgeoconv_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_ROT = 32
 
-PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
+PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_F16X3 = 0, 1, 2, 3
 ACT_IDS = {"relu": 0, "elu": 1, "leaky_relu": 2, "selu": 3, "sigmoid": 4, "tanh": 5}
 
 _p = C.c_void_p
@@ -34,6 +34,7 @@ SIGNATURES = {
     "gcb_profile_enable": (None, [_int]),
     "gcb_profile_read": (_int, [_int, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "gcb_tc_supported": (_int, [_i32, _i32, _i32, _i32, _i32]),
+    "gcb_tc_half_supported": (_int, [_i32, _i32, _i32, _i32, _i32]),
     "gcb_prep_bary": (_int, [_p, _int, _i64, _i32, _p, _p, _p, _p]),
     "gcb_csr_workspace_bytes": (_sz, [_i64, _i32]),
     "gcb_csr_build": (_int, [_p, _p, _i64, _i32, _p, _p, _p, _sz, _p]),

@@ -94,6 +94,7 @@ int ffma_conv_bwd(const float* x, const int32_t* idx, const float* w, const floa
 
 // tcgen05 path (gcb_tc_fwd.cu / gcb_tc_bwd.cu)
 bool tc_supported(int R, int A, int F, int T, int n_rot);
+bool tc_half_supported(int R, int A, int F, int T, int n_rot);
 size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, int precision);
 int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                 const float* w_self, const float* bias, const RotTable& rot, int n_rot, int v_out,

@@ -150,6 +150,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with fp16 operands (kind::f16: K = 16 halves = 32 bytes per instruction, twice the tf32 rate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool HALF>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if (HALF) umma_f16(d_tmem, a_desc, b_desc, idesc, accumulate);
+  else umma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
 // mbarrier arrives once every tcgen05.mma issued so far by this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -223,6 +239,15 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
 //   [15] A major 0=K  [16] B major 0=K   [17,23) N>>3   [24,29) M>>4
 __device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// kind::f16 with fp16 A and B (format 0), fp32 accumulate, both K-major
+__device__ __forceinline__ uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+template <bool HALF>
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+  return HALF ? make_idesc_f16(m, n) : make_idesc_tf32(m, n);
 }
 
 }  // namespace ptx

@@ -37,7 +37,16 @@
 //
 // TF32X3 (fp32-faithful): operands are split v = hi + lo (both tf32) and D += Ahi*Bhi + Ahi*Blo +
 // Alo*Bhi - three MMAs per k-step, relative error ~2^-21 per product.
+//
+// F16X3 (fp32-faithful at twice the tensor rate): fp16 has the same 11-bit significand as tf32 and
+// kind::f16 contracts 16 elements per instruction where kind::tf32 contracts 8.  Both operands are
+// multiplied by a power of two chosen per call from max|X| * max(sum_j |w_j|) and max|Wcat| so that the
+// largest element sits in [2^14, 2^15) (no overflow; what falls into the fp16 subnormal range keeps an
+// ABSOLUTE error of 2^-25, i.e. 2^-39 of the largest element), split v*s = hi + lo in fp16, contracted
+// with the same three products, and the finishing kernel multiplies the sum by the exact inverse scale.
+// Shared-memory layouts are identical byte for byte (a row of KC 4-byte units now holds 2*KC features).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -91,8 +100,9 @@ struct TcFwdParams {
   const uint4* recs;    // [R*A, v_pad, 2]: {i0,i1,i2,-} {w0,w1,w2,-}
   float* partial;       // [ksplit, v_pad, n_rot, T] raw accumulators
   float* interp_out;    // optional [v_out, R*A*F]: the interpolations, kept for the backward's dW
+  const float* scales;  // F16X3: {scale of the gathered operand, scale of the weights, 1 / (product)}
   int v_out, v_pad, R, A, F, T, n_rot;
-  int nfc;              // F / KC
+  int nfc;              // F / (features per tile row: KC, or 2*KC with fp16 operands)
   int n_t;              // templates per CTA (columns of one rotation's accumulator)
   int g;                // rotations per CTA
   int ns_a;             // A-tile ring depth
@@ -228,7 +238,7 @@ static int tc_pick_phase_shift(const RotTable& rot, int n_rot, int A, int g, int
 }
 
 // dstep = 0: every rotation on its own (works for any rotation list)
-static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, int dstep, int ring_shift = 0) {
+static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, bool half, int dstep, int ring_shift = 0) {
   TcConfig c{};
   c.ok = false;
   if (T % 16 != 0 || F % 8 != 0 || A > GCB_MAX_ROT || n_rot > GCB_MAX_ROT) return c;
@@ -245,8 +255,12 @@ static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, int dste
       const int L = A / gcd_int(dstep, A);
       while (m_top * 2 <= g && m_top * 2 * n_t <= 256 && m_top * 2 - 1 < L) m_top *= 2;
     }
-    for (int kc = 32; kc >= 8; kc >>= 1) {
-      if (F % kc != 0) continue;
+    static const int kc_env = getenv("GCB_TC_KC") ? atoi(getenv("GCB_TC_KC")) : 0;   // experiments
+    // kc = 4-byte units per tile row; fp16 rows hold 2 * kc features and stay <= 64 bytes so that a producer
+    // lane keeps the same number of gathered float4 in flight as in the tf32 layouts
+    for (int kc = half ? 16 : 32; kc >= 8; kc >>= 1) {
+      if (F % (half ? 2 * kc : kc) != 0) continue;
+      if (kc_env > 0 && kc != kc_env) continue;
       for (int m = m_top; m >= 1; m >>= 1) {
         TcRing ring = tc_ring_layout(A, dstep, m);
         if (ring.n_pos > 32) continue;   // position masks are 32-bit
@@ -278,8 +292,9 @@ static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, int dste
 // simple time model: whole waves of 148 CTAs, each paying its share of the tile MMAs plus a fixed
 // prologue/drain, plus the partial-sum traffic every extra split adds (written by this kernel, read back
 // by k_tc_finish).
-static int tc_pick_ksplit(const TcConfig& cfg, int v_out, int R, int A, int F, int T, bool x3, int n_rot) {
-  const int n_ss = (R + 1) * (F / cfg.kc);
+static int tc_pick_ksplit(const TcConfig& cfg, int v_out, int R, int A, int F, int T, bool x3, bool half, int n_rot) {
+  const int kf = half ? 2 * cfg.kc : cfg.kc;   // features per tile row
+  const int n_ss = (R + 1) * (F / kf);
   const int64_t units = ceil_div64(v_out, TC_M) * cfg.n_groups * (T / cfg.n_t);
   static const int ks_env = getenv("GCB_TC_KSPLIT") ? atoi(getenv("GCB_TC_KSPLIT")) : 0;   // experiments
   if (ks_env > 0) return ks_env < n_ss ? ks_env : n_ss;
@@ -288,7 +303,7 @@ static int tc_pick_ksplit(const TcConfig& cfg, int v_out, int R, int A, int F, i
   if (s_min > n_ss) s_min = n_ss;
   if (units >= 148 * 6) return s_min;
   const double tile_cycles = (double)(cfg.kc / 8) * (x3 ? 3 : 1) * cfg.g * cfg.n_t / 2.0;   // MMA time of one tile
-  const double work = (double)R * (F / cfg.kc) * A * tile_cycles * 1.15;                     // whole K range of one unit
+  const double work = (double)R * (F / kf) * A * tile_cycles * 1.15;                     // whole K range of one unit
   const double cta_fixed = 9000.0;                                                           // prologue + first loads + drain
   const double split_cost = 2.0 * (double)ceil_div64(v_out, TC_M) * TC_M * n_rot * T * 4.0 / 6.5e12 * 1.7e9;
   int best = s_min;
@@ -303,20 +318,74 @@ static int tc_pick_ksplit(const TcConfig& cfg, int v_out, int R, int A, int F, i
 
 // ---- preparation kernels ---------------------------------------------------------------------
 // slot-major packed barycentric records, padded to a multiple of 128 vertices
+// (wsum_max, optional: max over slots of |w0| + |w1| + |w2| as fp32 bits - bounds |interpolation| / max|X|)
 __global__ void k_tc_pack_recs(const int32_t* __restrict__ idx, const float* __restrict__ w, int v_out,
-                               int v_pad, int RA, uint4* __restrict__ recs) {
+                               int v_pad, int RA, uint4* __restrict__ recs, unsigned* __restrict__ wsum_max) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t total = (int64_t)RA * v_pad;
-  if (e >= total) return;
-  int slot = (int)(e / v_pad), v = (int)(e - (int64_t)slot * v_pad);
-  uint4 ri = make_uint4(0, 0, 0, 0), rw = make_uint4(0, 0, 0, 0);
-  if (v < v_out) {
-    size_t base = ((size_t)v * RA + slot) * 3;
-    ri = make_uint4((uint32_t)idx[base], (uint32_t)idx[base + 1], (uint32_t)idx[base + 2], 0);
-    rw = make_uint4(__float_as_uint(w[base]), __float_as_uint(w[base + 1]), __float_as_uint(w[base + 2]), 0);
+  float ws = 0.f;
+  if (e < total) {
+    int slot = (int)(e / v_pad), v = (int)(e - (int64_t)slot * v_pad);
+    uint4 ri = make_uint4(0, 0, 0, 0), rw = make_uint4(0, 0, 0, 0);
+    if (v < v_out) {
+      size_t base = ((size_t)v * RA + slot) * 3;
+      ri = make_uint4((uint32_t)idx[base], (uint32_t)idx[base + 1], (uint32_t)idx[base + 2], 0);
+      rw = make_uint4(__float_as_uint(w[base]), __float_as_uint(w[base + 1]), __float_as_uint(w[base + 2]), 0);
+      ws = fabsf(w[base]) + fabsf(w[base + 1]) + fabsf(w[base + 2]);
+    }
+    recs[e * 2] = ri;
+    recs[e * 2 + 1] = rw;
   }
-  recs[e * 2] = ri;
-  recs[e * 2 + 1] = rw;
+  if (wsum_max) {   // (max of non-negative floats = max of their bit patterns; order-independent)
+    unsigned b = __float_as_uint(ws);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(wsum_max, b);
+  }
+}
+
+// max |a[i]| over two arrays, as fp32 bits (a NaN gives a pattern above +inf: the caller sees "not finite")
+__global__ void k_tc_absmax(const float* __restrict__ a, int64_t na, const float* __restrict__ b2, int64_t nb,
+                            unsigned* __restrict__ out) {
+  unsigned m = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < na; i += stride)
+    m = max(m, __float_as_uint(fabsf(__ldg(a + i))));
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += stride)
+    m = max(m, __float_as_uint(fabsf(__ldg(b2 + i))));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// power-of-two operand scales of the fp16 mode.  mx = {max|X|, max sum|w|, max|Wcat|} (fp32 bits);
+// scales = {sA, sB, 1 / (sA * sB)} with bound * s in [2^14, 2^15).
+__global__ void k_tc_scales(const unsigned* __restrict__ mx, float* __restrict__ scales) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float xm = __uint_as_float(mx[0]), wm = fmaxf(__uint_as_float(mx[1]), 1.f), bm = __uint_as_float(mx[2]);
+  auto pow2_for = [](float bound) {
+    if (!(bound > 0.f) || !isfinite(bound)) return 0;
+    int e = 14 - ilogbf(bound);
+    return e < -60 ? -60 : (e > 60 ? 60 : e);
+  };
+  const int ea = pow2_for(xm * wm), eb = pow2_for(bm);
+  scales[0] = ldexpf(1.f, ea);
+  scales[1] = ldexpf(1.f, eb);
+  scales[2] = ldexpf(1.f, -(ea + eb));
+}
+
+// fp16 variant of k_tc_wcat: Wcat * scales[1] = hi + lo (both fp16)
+__global__ void k_tc_wcat_h(const float* __restrict__ w_eff, const float* __restrict__ w_self, int T, int KRA,
+                            int F, const float* __restrict__ scales, __half* __restrict__ hi,
+                            __half* __restrict__ lo) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int kcat = KRA + F;
+  if (e >= (int64_t)T * kcat) return;
+  int t = (int)(e / kcat), k = (int)(e - (int64_t)t * kcat);
+  float v = (k < KRA ? w_eff[(size_t)t * KRA + k] : w_self[(size_t)t * F + (k - KRA)]) * __ldg(scales + 1);
+  const __half h = __float2half_rn(v);
+  hi[e] = h;
+  lo[e] = __float2half_rn(v - __half2float(h));
 }
 
 // Wcat[t, 0:KRA] = Weff[t], Wcat[t, KRA:KRA+F] = Wself[t], split into tf32 hi (+ lo for X3)
@@ -338,6 +407,16 @@ __device__ __forceinline__ uint32_t swz_chunk(int row, int c) {
   if (KC == 32) return (uint32_t)(c ^ (row & 7));
   if (KC == 16) return (uint32_t)(c ^ ((row >> 1) & 3));
   return (uint32_t)(c ^ ((row >> 2) & 1));
+}
+
+// (a, b) * s = hi + lo with hi, lo fp16 pairs
+__device__ __forceinline__ void split_half2(float a, float b, float s, uint32_t& hi, uint32_t& lo) {
+  a *= s; b *= s;
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // phase of the super-step after one with phase `phi`
@@ -400,7 +479,7 @@ struct TcMmaCtx {
 //    per super-step.  The visiting order now starts `phase_shift` steps later every super-step
 //    (chosen on the host so that every slot stays free for at least one step before its next use);
 //    the per-phase first/last-use tables are built once per CTA in shared memory.
-template <int KC, bool X3, int NU, int U0, int U1, int J0, int J1>
+template <int KC, bool X3, bool H, int NU, int U0, int U1, int J0, int J1>
 __device__ __forceinline__ void tc_issue_range(const uint64_t desc_hi, const uint32_t a_lo, const uint32_t (&b_lo)[NU],
                                                const uint32_t (&d_u)[NU], const uint32_t (&idesc_u)[NU],
                                                const bool (&on)[NU], const uint32_t b_lo_ring, const uint32_t accum) {
@@ -413,10 +492,10 @@ __device__ __forceinline__ void tc_issue_range(const uint64_t desc_hi, const uin
       for (int j = J0; j < J1; ++j) {
         const uint64_t da = desc_hi | (uint64_t)(a_lo + 2u * j);
         const uint64_t db = desc_hi | (uint64_t)(b_lo[u] + 2u * j);
-        ptx::umma_tf32(d_u[u], da, db, idesc_u[u], j == 0 ? accum : 1u);
+        ptx::umma<H>(d_u[u], da, db, idesc_u[u], j == 0 ? accum : 1u);
         if (X3) {
-          ptx::umma_tf32(d_u[u], da, desc_hi | (uint64_t)(b_lo[u] + b_lo_ring + 2u * j), idesc_u[u], 1u);
-          ptx::umma_tf32(d_u[u], desc_hi | (uint64_t)(a_lo + A_LO_HALF + 2u * j), db, idesc_u[u], 1u);
+          ptx::umma<H>(d_u[u], da, desc_hi | (uint64_t)(b_lo[u] + b_lo_ring + 2u * j), idesc_u[u], 1u);
+          ptx::umma<H>(d_u[u], desc_hi | (uint64_t)(a_lo + A_LO_HALF + 2u * j), db, idesc_u[u], 1u);
         }
       }
     }
@@ -434,7 +513,7 @@ __device__ __forceinline__ void tc_wait_entries(uint32_t bar0, uint32_t bits, ui
   }
 }
 
-template <int KC, bool X3, int CL, int NU>
+template <int KC, bool X3, bool H, int CL, int NU>
 __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx& c, int lane,
                                             const uint32_t* need_tab, const uint32_t* retire_tab,
                                             const uint32_t* seam_tab) {
@@ -458,7 +537,7 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
     int rel = on[u] ? p.rot.off[c.rot0 + gu * m_] - c.off_anchor - c.rel0 : 0;   // relative to the CTA's first rotation
     rel += rel < 0 ? A_ : 0;
     sl[u] = rel < 0 ? rel + A_ : rel;
-    idesc_u[u] = ptx::make_idesc_tf32(TC_M, wd * n_t_);
+    idesc_u[u] = ptx::make_idesc<H>(TC_M, wd * n_t_);
     d_u[u] = c.tmem_base + (uint32_t)(gu * m_ * n_t_);
   }
   const bool trace_on = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && c.mw == 0;
@@ -512,7 +591,7 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
       if (trp) trp[0] = clock64();
       const uint32_t a_lo = c.a_lo0 + (uint32_t)stage * c.a_stage_lo;
       if (!no_mma && ptx::elect_one())
-        tc_issue_range<KC, X3, NU, 0, U_SPLIT, 0, J_SPLIT>(desc_hi, a_lo, b_lo, d_u, idesc_u, on, c.b_lo_ring, accum);
+        tc_issue_range<KC, X3, H, NU, 0, U_SPLIT, 0, J_SPLIT>(desc_hi, a_lo, b_lo, d_u, idesc_u, on, c.b_lo_ring, accum);
       __syncwarp();
       // ---- while the first half executes: this step's releases, the next tile's addresses and readiness ----
       const uint32_t rm = __shfl_sync(0xffffffffu, retire_l, y);
@@ -532,9 +611,9 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
       if (ptx::elect_one()) {
         if (!no_mma) {
           if (U_SPLIT < NU)
-            tc_issue_range<KC, X3, NU, U_SPLIT, NU, 0, KS>(desc_hi, a_lo, b_lo, d_u, idesc_u, on, c.b_lo_ring, accum);
+            tc_issue_range<KC, X3, H, NU, U_SPLIT, NU, 0, KS>(desc_hi, a_lo, b_lo, d_u, idesc_u, on, c.b_lo_ring, accum);
           else if (J_SPLIT < KS)
-            tc_issue_range<KC, X3, NU, 0, NU, J_SPLIT, KS>(desc_hi, a_lo, b_lo, d_u, idesc_u, on, c.b_lo_ring, accum);
+            tc_issue_range<KC, X3, H, NU, 0, NU, J_SPLIT, KS>(desc_hi, a_lo, b_lo, d_u, idesc_u, on, c.b_lo_ring, accum);
         }
         uint32_t r = rm;
         while (r) {   // vacate the ring positions read for the last time
@@ -563,7 +642,7 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
   }
   // centre tiles: X[k] * Wself - one weight tile (the ring position of tile 0 in the current layout) serves
   // every rotation, one N = n_t MMA chain each; the layouts keep alternating
-  const uint32_t idesc1 = ptx::make_idesc_tf32(TC_M, n_t_);
+  const uint32_t idesc1 = ptx::make_idesc<H>(TC_M, n_t_);
   const uint32_t q_c = (uint32_t)p.ring.pos[0];
   for (int k = 0; k < c.n_c; ++k, ++n) {
     const uint32_t pos_c = q_c + ring_cur;
@@ -581,10 +660,10 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
           for (int j = 0; j < KS; ++j) {
             const uint64_t da = desc_hi | (uint64_t)(a_lo + 2u * j);
             const uint64_t db = desc_hi | (uint64_t)(b_lo_c + 2u * j);
-            ptx::umma_tf32(d, da, db, idesc1, j == 0 ? accum : 1u);
+            ptx::umma<H>(d, da, db, idesc1, j == 0 ? accum : 1u);
             if (X3) {
-              ptx::umma_tf32(d, da, desc_hi | (uint64_t)(b_lo_c + c.b_lo_ring + 2u * j), idesc1, 1u);
-              ptx::umma_tf32(d, desc_hi | (uint64_t)(a_lo + A_LO_HALF + 2u * j), db, idesc1, 1u);
+              ptx::umma<H>(d, da, desc_hi | (uint64_t)(b_lo_c + c.b_lo_ring + 2u * j), idesc1, 1u);
+              ptx::umma<H>(d, desc_hi | (uint64_t)(a_lo + A_LO_HALF + 2u * j), db, idesc1, 1u);
             }
           }
         }
@@ -608,7 +687,7 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
 // largest L2 -> SM stream of the kernel - is paid once, not once per rotation group.  Stage
 // barriers span the pair: a_full collects both CTAs' producers (remote arrive + complete_tx),
 // a_empty both CTAs' MMA warps (tcgen05.commit multicast).
-template <int KC, bool X3, int CL, bool KEEP>
+template <int KC, bool X3, bool H, int CL, bool KEEP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
           const __grid_constant__ TcFwdParams p) {
@@ -622,7 +701,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   constexpr int NGRP = 2 * CL;
   constexpr int GRP_WARPS = TC_PRODUCER_WARPS / NGRP;
   constexpr int WARP_ROWS = (TC_M / CL) / GRP_WARPS;   // tile rows one producer warp fills (32)
-  constexpr int ITEMS = WARP_ROWS / ROWS_PER_PASS;     // float4 items per lane per tile
+  constexpr int ITEMS = WARP_ROWS / ROWS_PER_PASS;     // 16-byte tile chunks per lane per tile
+  constexpr int NV = H ? 2 : 1;                        // float4 of features behind one chunk (8 halves / 4 tf32)
+  constexpr int KF = KC * NV;                          // features per tile row
+  static_assert(!H || X3, "fp16 operands are only used in the three-product mode");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -796,6 +878,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     const int row_l = lane / CPR;
     const uint4* rec_smem = reinterpret_cast<const uint4*>(smem_gen + (rec_base - smem_base));
     const bool keep_interp = KEEP && tz == 0 && (CL == 2 ? (grp >> 1) == 0 : grp == 0);
+    const float scale_a = H ? __ldg(p.scales) : 1.f;
     int ring = -1;
     int n = 0;
     int phi = 0;               // visiting-order phase of the current super-step
@@ -836,14 +919,14 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
                         pg < 1 && n < 128;
         long long* trp = tr ? p.trace + ((size_t)pg * 128 + n) * 8 : nullptr;
         if (tr) trp[0] = clock64();
-        const float* xcol = p.x + fc * KC + c * 4;
-        float4 v[ITEMS];
+        const float* xcol = p.x + fc * KF + c * (4 * NV);
+        float4 v[ITEMS * NV];
         if (p.debug & 4) {
 #pragma unroll
-          for (int j = 0; j < ITEMS; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < ITEMS * NV; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         } else if (!centre) {
           const uint4* rec = rec_smem + (size_t)(y * ROWS_CTA + (row_w - row_cta0) + row_l) * 2;
-          float4 x0[ITEMS], x1[ITEMS], x2[ITEMS];
+          float4 x0[ITEMS * NV], x1[ITEMS * NV], x2[ITEMS * NV];
           float w0[ITEMS], w1[ITEMS], w2[ITEMS];
 #pragma unroll
           for (int j = 0; j < ITEMS; ++j) {
@@ -851,33 +934,41 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
             const uint4 rw = rec[j * ROWS_PER_PASS * 2 + 1];
             if (p.debug & 1) { ri.x = 0; ri.y = 0; ri.z = 0; }
             w0[j] = __uint_as_float(rw.x); w1[j] = __uint_as_float(rw.y); w2[j] = __uint_as_float(rw.z);
-            x0[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.x * p.F));
-            x1[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.y * p.F));
-            x2[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.z * p.F));
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+              x0[j * NV + q] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.x * p.F) + q);
+              x1[j * NV + q] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.y * p.F) + q);
+              x2[j * NV + q] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)ri.z * p.F) + q);
+            }
           }
           if (tr) trp[1] = clock64();
 #pragma unroll
-          for (int j = 0; j < ITEMS; ++j) {
-            v[j].x = fmaf(x2[j].x, w2[j], fmaf(x1[j].x, w1[j], x0[j].x * w0[j]));
-            v[j].y = fmaf(x2[j].y, w2[j], fmaf(x1[j].y, w1[j], x0[j].y * w0[j]));
-            v[j].z = fmaf(x2[j].z, w2[j], fmaf(x1[j].z, w1[j], x0[j].z * w0[j]));
-            v[j].w = fmaf(x2[j].w, w2[j], fmaf(x1[j].w, w1[j], x0[j].w * w0[j]));
+          for (int i = 0; i < ITEMS * NV; ++i) {
+            const int j = i / NV;
+            v[i].x = fmaf(x2[i].x, w2[j], fmaf(x1[i].x, w1[j], x0[i].x * w0[j]));
+            v[i].y = fmaf(x2[i].y, w2[j], fmaf(x1[i].y, w1[j], x0[i].y * w0[j]));
+            v[i].z = fmaf(x2[i].z, w2[j], fmaf(x1[i].z, w1[j], x0[i].z * w0[j]));
+            v[i].w = fmaf(x2[i].w, w2[j], fmaf(x1[i].w, w1[j], x0[i].w * w0[j]));
           }
         } else {
 #pragma unroll
           for (int j = 0; j < ITEMS; ++j) {
             const int row = m0 + row_w + row_l + j * ROWS_PER_PASS;
-            v[j] = row < p.v_out ? __ldg(reinterpret_cast<const float4*>(xcol + (size_t)row * p.F))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < NV; ++q)
+              v[j * NV + q] = row < p.v_out ? __ldg(reinterpret_cast<const float4*>(xcol + (size_t)row * p.F) + q)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         if (KEEP && keep_interp && !centre) {
           // every (vertex, slot, feature) value is produced exactly once across the K splits: keep it
-          float* irow = p.interp_out + (size_t)(xr * p.A + y) * p.F + fc * KC + c * 4;
+          float* irow = p.interp_out + (size_t)(xr * p.A + y) * p.F + fc * KF + c * (4 * NV);
 #pragma unroll
           for (int j = 0; j < ITEMS; ++j) {
             const int row = m0 + row_w + row_l + j * ROWS_PER_PASS;
-            if (row < p.v_out) *reinterpret_cast<float4*>(irow + (size_t)row * RA * p.F) = v[j];
+#pragma unroll
+            for (int q = 0; q < NV; ++q)
+              if (row < p.v_out) *(reinterpret_cast<float4*>(irow + (size_t)row * RA * p.F) + q) = v[j * NV + q];
           }
         }
         if (tr) trp[2] = clock64() + (__float_as_int(v[0].x) & 0);   // after the loads have landed
@@ -890,14 +981,26 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
           if (p.debug & 12) break;   // experiments: no stores
           const int row = row_w + row_l + j * ROWS_PER_PASS;
           const uint32_t off = (uint32_t)row * ROW_BYTES + swz_chunk<KC>(row, c) * 16u;
-          float4 h;
-          h.x = ptx::to_tf32(v[j].x); h.y = ptx::to_tf32(v[j].y);
-          h.z = ptx::to_tf32(v[j].z); h.w = ptx::to_tf32(v[j].w);
-          *reinterpret_cast<float4*>(a_hi + off) = h;
-          if (X3) {
-            float4 l;
-            l.x = v[j].x - h.x; l.y = v[j].y - h.y; l.z = v[j].z - h.z; l.w = v[j].w - h.w;
-            *reinterpret_cast<float4*>(a_hi + A_TILE_BYTES + off) = l;
+          if (H) {
+            // 8 features -> 8 fp16 hi + 8 fp16 lo of the scaled value
+            const float4 va = v[j * NV], vb = v[j * NV + NV - 1];
+            uint4 h, l;
+            split_half2(va.x, va.y, scale_a, h.x, l.x);
+            split_half2(va.z, va.w, scale_a, h.y, l.y);
+            split_half2(vb.x, vb.y, scale_a, h.z, l.z);
+            split_half2(vb.z, vb.w, scale_a, h.w, l.w);
+            *reinterpret_cast<uint4*>(a_hi + off) = h;
+            *reinterpret_cast<uint4*>(a_hi + A_TILE_BYTES + off) = l;
+          } else {
+            float4 h;
+            h.x = ptx::to_tf32(v[j].x); h.y = ptx::to_tf32(v[j].y);
+            h.z = ptx::to_tf32(v[j].z); h.w = ptx::to_tf32(v[j].w);
+            *reinterpret_cast<float4*>(a_hi + off) = h;
+            if (X3) {
+              float4 l;
+              l.x = v[j].x - h.x; l.y = v[j].y - h.y; l.z = v[j].z - h.z; l.w = v[j].w - h.w;
+              *reinterpret_cast<float4*>(a_hi + A_TILE_BYTES + off) = l;
+            }
           }
         }
         if (tr) trp[4] = clock64();
@@ -965,7 +1068,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
           if (tr) trp[0] = clock64();
           ptx::mbar_wait(b_empty + 8u * pos, ((uint32_t)(fills >> pos) & 1u) ^ 1u);
           if (tr) trp[1] = clock64();
-          const int col = (centre ? RA * p.F : (xr * p.A + sg) * p.F) + fc * KC;
+          const int col = (centre ? RA * p.F : (xr * p.A + sg) * p.F) + fc * KF;
           const uint32_t bar = b_full + 8u * (uint32_t)(par * NP + q);
           ptx::mbar_arrive_expect_tx(bar, (uint32_t)(NPROD * b_tile_bytes));
           const uint32_t dst = b_base + pos * (uint32_t)b_tile_bytes;
@@ -1036,10 +1139,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       c.n_c = ss_end > max(ss_begin, ss_nc) ? ss_end - max(ss_begin, ss_nc) : 0;
       c.mw = mw; c.n_mma = n_mma;
       const int n_own = (n_units - mw + n_mma - 1) / n_mma;
-      if (n_own == 1) tc_mma_role<KC, X3, CL, 1>(p, c, lane, need_tab, retire_tab, seam_tab);
-      else if (n_own == 2) tc_mma_role<KC, X3, CL, 2>(p, c, lane, need_tab, retire_tab, seam_tab);
-      else if (n_own <= 4) tc_mma_role<KC, X3, CL, 4>(p, c, lane, need_tab, retire_tab, seam_tab);
-      else tc_mma_role<KC, X3, CL, 8>(p, c, lane, need_tab, retire_tab, seam_tab);
+      if (n_own == 1) tc_mma_role<KC, X3, H, CL, 1>(p, c, lane, need_tab, retire_tab, seam_tab);
+      else if (n_own == 2) tc_mma_role<KC, X3, H, CL, 2>(p, c, lane, need_tab, retire_tab, seam_tab);
+      else if (n_own <= 4) tc_mma_role<KC, X3, H, CL, 4>(p, c, lane, need_tab, retire_tab, seam_tab);
+      else tc_mma_role<KC, X3, H, CL, 8>(p, c, lane, need_tab, retire_tab, seam_tab);
     }
   }
 
@@ -1054,9 +1157,11 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
 
 // ---- kernel 2: split reduction + bias + activation + angular max-pooling -------------------------
 // One warp per vertex; lanes own float4 column groups.  Summation order over splits is fixed.
+// (scales != NULL: the partial sums carry the fp16 mode's operand scales; their sum is multiplied by the exact
+// inverse, scales[2], before the bias is added)
 __global__ void k_tc_finish(const float* __restrict__ partial, const float* __restrict__ bias, int ksplit,
-                            int v_out, int v_pad, int n_rot, int T, int act, float* __restrict__ y,
-                            float* __restrict__ z, int32_t* __restrict__ argmax) {
+                            int v_out, int v_pad, int n_rot, int T, int act, const float* __restrict__ scales,
+                            float* __restrict__ y, float* __restrict__ z, int32_t* __restrict__ argmax) {
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (k >= v_out) return;
@@ -1064,15 +1169,21 @@ __global__ void k_tc_finish(const float* __restrict__ partial, const float* __re
   const int T4 = T >> 2;
   float best = -1.f;
   int arg = 0;
+  const float inv = scales ? __ldg(scales + 2) : 1.f;
   for (int i = 0; i < n_rot; ++i) {
     const float* src = partial + ((size_t)k * n_rot + i) * T;
     float* dst = y + ((size_t)k * n_rot + i) * T;
     float s = 0.f;
     for (int q = lane; q < T4; q += 32) {
-      float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + q);
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + q);
+      float4 acc = scales ? make_float4(0.f, 0.f, 0.f, 0.f) : bv;
       for (int sp = 0; sp < ksplit; ++sp) {
         const float4 pv = __ldg(reinterpret_cast<const float4*>(src + sp * split_stride) + q);
         acc.x += pv.x; acc.y += pv.y; acc.z += pv.z; acc.w += pv.w;
+      }
+      if (scales) {
+        acc.x = fmaf(acc.x, inv, bv.x); acc.y = fmaf(acc.y, inv, bv.y);
+        acc.z = fmaf(acc.z, inv, bv.z); acc.w = fmaf(acc.w, inv, bv.w);
       }
       float4 o;
       o.x = act_apply(act, acc.x); o.y = act_apply(act, acc.y);
@@ -1153,12 +1264,34 @@ static int make_weight_tmap(CUtensorMap* out, const float* base, int T, int kcat
                          (uint32_t)n_t);
 }
 
-int tc_pack_recs(const int32_t* idx, const float* w, int v_out, int R, int A, uint4* recs, cudaStream_t st) {
+// fp16 weights [T][kcat]: box = 2 * kc halves (kc 4-byte units) x n_t rows, swizzle span = the box row
+static int make_weight_tmap_h(CUtensorMap* out, const __half* base, int T, int kcat, int kc, int n_t) {
+  PFN_encodeTiled enc = get_encode_fn();
+  GCB_REQUIRE(enc, GCB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)kcat, (cuuint64_t)T};
+  cuuint64_t strides[1] = {(cuuint64_t)kcat * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)(2 * kc), (cuuint32_t)n_t};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                         : (kc == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GCB_REQUIRE(r == CUDA_SUCCESS, GCB_ECUDA, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d", (int)r);
+  return GCB_OK;
+}
+
+static int tc_pack_recs_max(const int32_t* idx, const float* w, int v_out, int R, int A, uint4* recs,
+                            unsigned* wsum_max, cudaStream_t st) {
   const int v_pad = (int)ceil_div64(v_out, TC_M) * TC_M;
   int64_t total = (int64_t)R * A * v_pad;
-  k_tc_pack_recs<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(idx, w, v_out, v_pad, R * A, recs);
+  k_tc_pack_recs<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(idx, w, v_out, v_pad, R * A, recs, wsum_max);
   GCB_LAUNCH_OK();
   return GCB_OK;
+}
+
+int tc_pack_recs(const int32_t* idx, const float* w, int v_out, int R, int A, uint4* recs, cudaStream_t st) {
+  return tc_pack_recs_max(idx, w, v_out, R, A, recs, nullptr, st);
 }
 
 int tc_build_wcat(const float* w_eff, const float* w_self, int T, int R, int A, int F, float* hi, float* lo,
@@ -1172,7 +1305,7 @@ int tc_build_wcat(const float* w_eff, const float* w_self, int T, int R, int A, 
 
 bool tc_supported(int R, int A, int F, int T, int n_rot) {
   (void)R;
-  return tc_pick_config(A, F, T, n_rot, true, 0).ok && tc_pick_config(A, F, T, n_rot, false, 0).ok;
+  return tc_pick_config(A, F, T, n_rot, true, false, 0).ok && tc_pick_config(A, F, T, n_rot, false, false, 0).ok;
 }
 
 size_t tc_recs_bytes(int v_out, int R, int A) {
@@ -1189,23 +1322,32 @@ static size_t tc_partial_bytes(int v_out, int n_rot, int T, int ksplit) {
 
 // The tiling (and with it the K-split count) depends on the rotation list, which the size query does
 // not see: take the largest requirement over every uniform step and the unmerged layout.
+// fp16 operands need 16 features per row at least (a 32-byte swizzle span)
+bool tc_half_supported(int R, int A, int F, int T, int n_rot) {
+  (void)R;
+  return tc_pick_config(A, F, T, n_rot, true, true, 0).ok;
+}
+
+constexpr size_t TC_SCALES_BYTES = 256;   // {max|X|, max sum|w|, max|Wcat|} as bits, then the three scales
+
 size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, int precision) {
-  const bool x3 = precision == GCB_PREC_TF32X3;
+  const bool half = precision == GCB_PREC_F16X3;
+  const bool x3 = half || precision == GCB_PREC_TF32X3;
   int ksplit = 0;
   for (int dstep = 0; dstep < A; ++dstep) {
-    TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3, dstep);
+    TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3, half, dstep);
     if (!cfg.ok) return 0;
-    int s = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3, n_rot);
+    int s = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3, half, n_rot);
     if (s > ksplit) ksplit = s;
   }
   return tc_recs_bytes(v_out, R, A) + (x3 ? 2 : 1) * tc_wcat_bytes(R, A, F, T) +
-         tc_partial_bytes(v_out, n_rot, T, ksplit) + 1024;
+         tc_partial_bytes(v_out, n_rot, T, ksplit) + TC_SCALES_BYTES + 1024;
 }
 
-template <int KC, bool X3, int CL, bool KEEP>
+template <int KC, bool X3, bool H, int CL, bool KEEP>
 static int tc_launch_k(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdParams& p, const TcConfig& cfg,
                        dim3 grid, cudaStream_t st) {
-  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_conv<KC, X3, CL, KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_conv<KC, X3, H, CL, KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)cfg.smem_bytes));
   cudaLaunchConfig_t lc{};
   lc.gridDim = grid;
@@ -1220,7 +1362,7 @@ static int tc_launch_k(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwd
   lc.attrs = attr;
   lc.numAttrs = 1;
   profile_begin(GCB_PROF_FWD_CONV, st);
-  cudaError_t e = cudaLaunchKernelEx(&lc, k_tc_conv<KC, X3, CL, KEEP>, mh, ml, p);
+  cudaError_t e = cudaLaunchKernelEx(&lc, k_tc_conv<KC, X3, H, CL, KEEP>, mh, ml, p);
   profile_end(GCB_PROF_FWD_CONV, st);
   GCB_CUDA_OK(e);
   GCB_LAUNCH_OK();
@@ -1229,25 +1371,25 @@ static int tc_launch_k(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwd
 
 // Pairs of rotation groups share their gathered tiles through a 2-CTA cluster when the group count
 // is even (GCB_TC_CLUSTER=0 switches the pairing off for A/B measurements).
-template <int KC, bool X3>
+template <int KC, bool X3, bool H = false>
 static int tc_launch(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdParams& p, const TcConfig& cfg,
                      dim3 grid, cudaStream_t st) {
   if (tc_use_pairs() && cfg.n_groups % 2 == 0 && KC >= 16)
-    return p.interp_out ? tc_launch_k<KC, X3, 2, true>(mh, ml, p, cfg, grid, st)
-                        : tc_launch_k<KC, X3, 2, false>(mh, ml, p, cfg, grid, st);
-  return p.interp_out ? tc_launch_k<KC, X3, 1, true>(mh, ml, p, cfg, grid, st)
-                      : tc_launch_k<KC, X3, 1, false>(mh, ml, p, cfg, grid, st);
+    return p.interp_out ? tc_launch_k<KC, X3, H, 2, true>(mh, ml, p, cfg, grid, st)
+                        : tc_launch_k<KC, X3, H, 2, false>(mh, ml, p, cfg, grid, st);
+  return p.interp_out ? tc_launch_k<KC, X3, H, 1, true>(mh, ml, p, cfg, grid, st)
+                      : tc_launch_k<KC, X3, H, 1, false>(mh, ml, p, cfg, grid, st);
 }
 
 int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
                 const float* bias, const RotTable& rot, int n_rot, int v_out, int v_src, int R, int A, int F,
                 int T, int act, int precision, float* y, float* z, int32_t* argmax, float* interp_out,
                 void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  (void)v_src;
-  const bool x3 = precision == GCB_PREC_TF32X3;
+  const bool half = precision == GCB_PREC_F16X3;
+  const bool x3 = half || precision == GCB_PREC_TF32X3;
   static const bool no_merge = getenv("GCB_TC_NOMERGE") && atoi(getenv("GCB_TC_NOMERGE")) != 0;
   const int dstep = no_merge ? 0 : tc_uniform_step(rot, n_rot, A);
-  TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3, dstep);
+  TcConfig cfg = tc_pick_config(A, F, T, n_rot, x3, half, dstep);
   GCB_REQUIRE(cfg.ok, GCB_EUNSUPPORTED, "tc_conv_fwd: no tcgen05 tiling for A=%d F=%d T=%d", A, F, T);
   // Weight ring: spend spare shared memory on a second, shifted layout when that buys refill slack (3 steps
   // cover the commit -> TMA -> barrier latency) without changing the tiling or starving the A ring.
@@ -1261,7 +1403,7 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
     for (int rs = 1; rs <= 4; ++rs) {
       if (shift_env >= 0 && rs != shift_env) continue;
       if (shift_env < 0 && best_slack >= 3) break;
-      TcConfig c2 = tc_pick_config(A, F, T, n_rot, x3, dstep, rs);
+      TcConfig c2 = tc_pick_config(A, F, T, n_rot, x3, half, dstep, rs);
       if (!c2.ok || c2.kc != cfg.kc || c2.ring.m != cfg.ring.m || c2.n_t != cfg.n_t || c2.g != cfg.g || c2.ns_a < 4) break;
       int sl2 = -1;
       const int ph2 = tc_pick_phase_shift(rot, n_rot, A, c2.g, c2.n_groups, pairs, c2.ring, true, &sl2);   // two layouts: two phases
@@ -1279,7 +1421,7 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   GCB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)bias % 16 == 0) &&
                   ((uintptr_t)z % 16 == 0),
               GCB_EINVAL, "tc_conv_fwd: x, y, z and bias must be 16-byte aligned");
-  const int ksplit = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3, n_rot);
+  const int ksplit = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3, half, n_rot);
   const int RA = R * A, KRA = RA * F, kcat = KRA + F;
   const int m_tiles = (int)ceil_div64(v_out, TC_M);
   const int v_pad = m_tiles * TC_M;
@@ -1294,21 +1436,45 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
     ws += tc_wcat_bytes(R, A, F, T);
   }
   float* partial = (float*)ws;
+  ws += tc_partial_bytes(v_out, n_rot, T, ksplit);
+  unsigned* mx = (unsigned*)ws;                 // fp16 mode: operand maxima, then the scales
+  float* scales = half ? (float*)(mx + 4) : nullptr;
 
-  int rc = tc_pack_recs(idx, w, v_out, R, A, recs, st);
-  if (rc) return rc;
-  rc = tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);
-  if (rc) return rc;
+  int rc;
   CUtensorMap mh, ml;
-  rc = make_weight_tmap(&mh, wc_hi, T, kcat, cfg.kc, cfg.n_t);
-  if (rc) return rc;
-  rc = make_weight_tmap(&ml, x3 ? wc_lo : wc_hi, T, kcat, cfg.kc, cfg.n_t);
-  if (rc) return rc;
+  if (half) {
+    GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 16, st));
+    k_tc_absmax<<<148 * 2, 256, 0, st>>>(x, (int64_t)v_src * F, nullptr, 0, mx);
+    GCB_LAUNCH_OK();
+    k_tc_absmax<<<148 * 2, 256, 0, st>>>(w_eff, (int64_t)T * RA * F, w_self, (int64_t)T * F, mx + 2);
+    GCB_LAUNCH_OK();
+    rc = tc_pack_recs_max(idx, w, v_out, R, A, recs, mx + 1, st);
+    if (rc) return rc;
+    k_tc_scales<<<1, 32, 0, st>>>(mx, scales);
+    GCB_LAUNCH_OK();
+    const int64_t wt = (int64_t)T * kcat;
+    k_tc_wcat_h<<<(unsigned)ceil_div64(wt, 256), 256, 0, st>>>(w_eff, w_self, T, KRA, F, scales, (__half*)wc_hi,
+                                                               (__half*)wc_lo);
+    GCB_LAUNCH_OK();
+    rc = make_weight_tmap_h(&mh, (const __half*)wc_hi, T, kcat, cfg.kc, cfg.n_t);
+    if (rc) return rc;
+    rc = make_weight_tmap_h(&ml, (const __half*)wc_lo, T, kcat, cfg.kc, cfg.n_t);
+    if (rc) return rc;
+  } else {
+    rc = tc_pack_recs(idx, w, v_out, R, A, recs, st);
+    if (rc) return rc;
+    rc = tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);
+    if (rc) return rc;
+    rc = make_weight_tmap(&mh, wc_hi, T, kcat, cfg.kc, cfg.n_t);
+    if (rc) return rc;
+    rc = make_weight_tmap(&ml, x3 ? wc_lo : wc_hi, T, kcat, cfg.kc, cfg.n_t);
+    if (rc) return rc;
+  }
 
   TcFwdParams p;
-  p.x = x; p.recs = recs; p.partial = partial; p.interp_out = interp_out;
+  p.x = x; p.recs = recs; p.partial = partial; p.interp_out = interp_out; p.scales = scales;
   p.v_out = v_out; p.v_pad = v_pad; p.R = R; p.A = A; p.F = F; p.T = T; p.n_rot = n_rot;
-  p.nfc = F / cfg.kc; p.n_t = cfg.n_t; p.g = cfg.g; p.ns_a = cfg.ns_a; p.tmem_cols = cfg.tmem_cols;
+  p.nfc = F / (half ? 2 * cfg.kc : cfg.kc); p.n_t = cfg.n_t; p.g = cfg.g; p.ns_a = cfg.ns_a; p.tmem_cols = cfg.tmem_cols;
   p.ksplit = ksplit;
   p.phase_shift = phase_shift;
   p.phase_alt = cfg.ring.shift > 0 ? 1 : 0;
@@ -1325,13 +1491,14 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   }
   p.rot = rot;
   dim3 grid((unsigned)m_tiles, (unsigned)cfg.n_groups, (unsigned)((T / cfg.n_t) * ksplit));
-  if (cfg.kc == 32) rc = x3 ? tc_launch<32, true>(mh, ml, p, cfg, grid, st) : tc_launch<32, false>(mh, ml, p, cfg, grid, st);
+  if (half) rc = cfg.kc == 16 ? tc_launch<16, true, true>(mh, ml, p, cfg, grid, st) : tc_launch<8, true, true>(mh, ml, p, cfg, grid, st);
+  else if (cfg.kc == 32) rc = x3 ? tc_launch<32, true>(mh, ml, p, cfg, grid, st) : tc_launch<32, false>(mh, ml, p, cfg, grid, st);
   else if (cfg.kc == 16) rc = x3 ? tc_launch<16, true>(mh, ml, p, cfg, grid, st) : tc_launch<16, false>(mh, ml, p, cfg, grid, st);
   else rc = x3 ? tc_launch<8, true>(mh, ml, p, cfg, grid, st) : tc_launch<8, false>(mh, ml, p, cfg, grid, st);
   if (rc) return rc;
   const int warps_per_block = 8;
   k_tc_finish<<<(unsigned)ceil_div64(v_out, warps_per_block), warps_per_block * 32, 0, st>>>(
-      partial, bias, ksplit, v_out, v_pad, n_rot, T, act, y, z, argmax);
+      partial, bias, ksplit, v_out, v_pad, n_rot, T, act, scales, y, z, argmax);
   GCB_LAUNCH_OK();
   if (p.trace) {
     static long long host[4 * 128 * 8];

@@ -5,6 +5,7 @@ the current stream.  Nothing in this file computes the convolution with torch op
 """
 from __future__ import annotations
 
+import os
 import weakref
 from dataclasses import dataclass, field
 
@@ -18,7 +19,13 @@ from . import _native as N
 # it is built from stays in L2.  Off by default; the switch remains for shapes with a tiny signal.
 SAVE_INTERPOLATIONS = False
 
-PRECISIONS = {"fp32": None, "ffma": N.PREC_FP32, "tf32": N.PREC_TF32, "tf32x3": N.PREC_TF32X3}
+# 'fp32' (the fp32-faithful default) runs the tensor-core kernels with fp16 hi/lo operand splits (three
+# kind::f16 products: same significand bits as 3xTF32 at twice the rate) when the shape allows;
+# GEOCONV_B200_FP32_VIA=tf32x3 selects the tf32 splits instead.
+FP32_VIA_F16 = os.environ.get("GEOCONV_B200_FP32_VIA", "f16x3") != "tf32x3"
+
+PRECISIONS = {"fp32": None, "ffma": N.PREC_FP32, "tf32": N.PREC_TF32, "tf32x3": N.PREC_TF32X3,
+              "f16x3": N.PREC_F16X3}
 
 
 def _stream(t: torch.Tensor) -> int:
@@ -42,9 +49,14 @@ def resolve_precision(mode: str, r: int, a: int, f: int, t: int, n_rot: int) -> 
         raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {mode!r}")
     lib = N.load()
     tc_ok = bool(lib.gcb_tc_supported(r, a, f, t, n_rot))
+    half_ok = tc_ok and bool(lib.gcb_tc_half_supported(r, a, f, t, n_rot))
     if mode == "fp32":
-        return N.PREC_TF32X3 if tc_ok else N.PREC_FP32
+        if not tc_ok:
+            return N.PREC_FP32
+        return N.PREC_F16X3 if half_ok and FP32_VIA_F16 else N.PREC_TF32X3
     code = PRECISIONS[mode]
+    if code == N.PREC_F16X3 and not half_ok:
+        code = N.PREC_TF32X3
     if code != N.PREC_FP32 and not tc_ok:
         return N.PREC_FP32  # exact arithmetic is always an admissible substitute for a faster mode
     return code

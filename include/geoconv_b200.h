@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GCB_ABI_VERSION 4
+#define GCB_ABI_VERSION 5
 #define GCB_MAX_ROT 32
 
 /* error codes */
@@ -52,6 +52,9 @@ extern "C" {
 #define GCB_PREC_FP32 0   /* CUDA-core FFMA, plain fp32 */
 #define GCB_PREC_TF32 1   /* tcgen05 kind::tf32, one pass (<=2e-3 normalised error) */
 #define GCB_PREC_TF32X3 2 /* tcgen05 kind::tf32, 3-term split, fp32-faithful (<=1e-5) */
+#define GCB_PREC_F16X3 3  /* tcgen05 kind::f16, operands scaled by powers of two and split into fp16 hi + lo
+                             (same 11-bit significands as tf32), 3 products at twice the tf32 rate,
+                             fp32-faithful (<=1e-5); shapes: gcb_tc_half_supported */
 
 int gcb_abi_version(void);
 const char* gcb_last_error(void);
@@ -65,6 +68,9 @@ void gcb_profile_enable(int on);
 int gcb_profile_read(int which, double* ms_total, int64_t* launches);
 /* 1 if the tcgen05 kernels can serve this shape, else 0 (then use GCB_PREC_FP32). */
 int gcb_tc_supported(int32_t R, int32_t A, int32_t F, int32_t T, int32_t n_rot);
+/* 1 if GCB_PREC_F16X3 can serve this shape (needs F % 16 == 0 on top of gcb_tc_supported), else use
+ * GCB_PREC_TF32X3. */
+int gcb_tc_half_supported(int32_t R, int32_t A, int32_t F, int32_t T, int32_t n_rot);
 
 /* ---- GPC systems -> barycentric coordinates (the preprocessing step before the path) -----
  * Replaces geoconv/preprocessing/barycentric_coordinates.py:127-175 (with :7-69): for every GPC
