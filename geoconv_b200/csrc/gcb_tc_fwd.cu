@@ -111,6 +111,7 @@ struct TcFwdParams {
   int phase_shift;      // angular visiting order of super-step k starts at (k * phase_shift) % A
   int phase_alt;        // 1: the phase alternates 0, phase_shift, 0, ... with the two ring layouts instead of accumulating
   int bar_bytes;        // size of the mbarrier block in shared memory
+  int drain_cw;         // accumulator columns staged per bulk store in the drain (0: registers -> global directly)
   long long* trace;     // GCB_TC_TRACE (investigation builds): clock64 stamps of CTA (1,0,0), [role][tile][8]
   int debug;            // GCB_TC_DEBUG bits (timing experiments only): 1 = all gathers read row 0, 2 = no MMAs
   TcRing ring;
@@ -426,6 +427,10 @@ __device__ __forceinline__ int tc_next_phase(const TcFwdParams& p, int phi) {
   return n >= p.A ? n - p.A : n;
 }
 
+constexpr int TC_CTRL_THREADS = TC_WARP_PROD0 * 32;   // the control warps come first
+__device__ __forceinline__ void ctrl_bar_sync() {
+  asm volatile("bar.sync 2, %0;" ::"n"(TC_CTRL_THREADS) : "memory");
+}
 __device__ __forceinline__ void producer_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCER_WARPS * 32) : "memory");
 }
@@ -707,6 +712,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   static_assert(!H || X3, "fp16 operands are only used in the three-product mode");
 
   extern __shared__ uint8_t smem_raw[];
+  // life-cycle stamps of one CTA (GCB_TC_TRACE): entry, prologue done, accumulators complete, drained, exit
+  long long* const life = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 &&
+                                  threadIdx.x == TC_WARP_PROD0 * 32 ? p.trace + ((size_t)3 * 128 + 127) * 8 : nullptr;
+  if (life) life[0] = clock64();
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_tile_bytes = p.n_t * ROW_BYTES;
   const uint32_t b_base = smem_base;                                        // [NPROD][n_pos][b_tile]
@@ -793,73 +802,6 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.A * NP; i += blockDim.x) {
-    // first / last reader of ring entry q under phase phi: a unit reads m adjacent positions starting at the
-    // position of its first tile (tiles relabelled by this CTA's first rotation)
-    const int phi = i / NP, q = i - phi * NP;
-    int first = 0xFF, last = 0xFF;
-    for (int y = 0; y < p.A; ++y)
-      for (int u = 0; u < n_units; ++u) {
-        int s0 = (y + phi + p.rot.off[rot0 + u * p.ring.m] - off_anchor - rel0) % p.A;
-        s0 += s0 < 0 ? p.A : 0;
-        const int wd = min(p.ring.m, g_cnt - u * p.ring.m);
-        const int q0 = p.ring.pos[s0];
-        if (q >= q0 && q < q0 + wd) {
-          if (first == 0xFF) first = y;
-          last = y;
-        }
-      }
-    firstp_tab[i] = (uint8_t)first;
-    lastp_tab[i] = (uint8_t)last;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < AA; i += blockDim.x) {
-    const int phi = i / p.A, yy = i - phi * p.A;
-    uint32_t need = 0, retire = 0;
-    for (int q = 0; q < NP; ++q) {
-      need |= firstp_tab[phi * NP + q] == yy ? 1u << q : 0u;
-      retire |= lastp_tab[phi * NP + q] == yy ? 1u << q : 0u;
-    }
-    need_tab[i] = need;
-    retire_tab[i] = retire;
-  }
-  for (int i = threadIdx.x; i < 2 * p.A * NP; i += blockDim.x) {
-    const int par = i / (p.A * NP), phi = (i / NP) % p.A, q = i % NP;   // entry q of a super-step (par, phi)
-    int phi_prev = phi - p.phase_shift;            // accumulating phases; alternating: the other of {0, phase_shift}
-    phi_prev += phi_prev < 0 ? p.A : 0;
-    if (p.phase_alt) phi_prev = phi == 0 ? p.phase_shift : 0;
-    const int qp = q + par * p.ring.shift - (par ^ 1) * p.ring.shift;  // its position in the previous layout's numbering
-    int ret = 0;
-    if (qp >= 0 && qp < NP && lastp_tab[phi_prev * NP + qp] != 0xFF) ret = 1 + (int)lastp_tab[phi_prev * NP + qp];
-    occ_tab[i] = (uint8_t)ret;
-  }
-  __syncthreads();
-  // Reload order: the entries of the next super-step are loaded in the order in which their positions are
-  // vacated (under the PREVIOUS super-step's phase), ties in the order the next super-step needs them; entries
-  // nobody reads come last and are skipped.  Loading in index order would park the TMA thread on a position
-  // that is vacated late while others wait for their refill.
-  for (int i = threadIdx.x; i < (2 * p.A + 1) * NP; i += blockDim.x) {
-    const int row = i / NP, q = i - row * NP;
-    const bool steady = row < 2 * p.A;
-    const int phi = steady ? row % p.A : 0;
-    auto key_of = [&](int e) {
-      const int fr = firstp_tab[phi * NP + e];
-      return fr == 0xFF ? (1 << 30) + e : ((steady ? occ_tab[row * NP + e] : 0) * (p.A + 1) + fr) * NP + e;
-    };
-    const int my_key = key_of(q);
-    int rank = 0;
-    for (int o = 0; o < NP; ++o) rank += key_of(o) < my_key ? 1 : 0;
-    order_tab[row * NP + rank] = (uint8_t)q;
-  }
-  for (int i = threadIdx.x; i < 2 * p.A; i += blockDim.x) {
-    const int par = i / p.A, phi = i - par * p.A;
-    const int phi_n = tc_next_phase(p, phi);
-    uint32_t seam = 0;
-    for (int q = 0; q < NP; ++q) seam |= occ_tab[((par ^ 1) * p.A + phi_n) * NP + q] == p.A ? 1u << q : 0u;
-    seam_tab[i] = seam;
-  }
-  int n_ent = 0;   // entries that are read at all (the same for every phase: every step of a super-step is visited)
-  for (int q = 0; q < NP; ++q) n_ent += firstp_tab[q] != 0xFF ? 1 : 0;
   ptx::tc_fence_before();
   __syncthreads();
   if (CL == 2) ptx::cluster_sync();   // the peer's barriers exist before anyone arrives on them remotely
@@ -867,6 +809,81 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   const uint32_t tmem_base = __shfl_sync(
       0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base)), 0);
 
+  // The weight-ring schedules are only read by the control warps (TMA, MMA issuers, scout): they build them
+  // while the producers already stage their records and gather the first tiles (traced: the prologue cost
+  // 10.6 k cycles per CTA when all 12 warps sat through it).
+  int n_ent = 0;
+  if (warp < TC_WARP_PROD0) {
+    for (int i = threadIdx.x; i < p.A * NP; i += TC_CTRL_THREADS) {
+      // first / last reader of ring entry q under phase phi: a unit reads m adjacent positions starting at the
+      // position of its first tile (tiles relabelled by this CTA's first rotation)
+      const int phi = i / NP, q = i - phi * NP;
+      int first = 0xFF, last = 0xFF;
+      for (int y = 0; y < p.A; ++y)
+        for (int u = 0; u < n_units; ++u) {
+          int s0 = (y + phi + p.rot.off[rot0 + u * p.ring.m] - off_anchor - rel0) % p.A;
+          s0 += s0 < 0 ? p.A : 0;
+          const int wd = min(p.ring.m, g_cnt - u * p.ring.m);
+          const int q0 = p.ring.pos[s0];
+          if (q >= q0 && q < q0 + wd) {
+            if (first == 0xFF) first = y;
+            last = y;
+          }
+        }
+      firstp_tab[i] = (uint8_t)first;
+      lastp_tab[i] = (uint8_t)last;
+    }
+    ctrl_bar_sync();
+    for (int i = threadIdx.x; i < AA; i += TC_CTRL_THREADS) {
+      const int phi = i / p.A, yy = i - phi * p.A;
+      uint32_t need = 0, retire = 0;
+      for (int q = 0; q < NP; ++q) {
+        need |= firstp_tab[phi * NP + q] == yy ? 1u << q : 0u;
+        retire |= lastp_tab[phi * NP + q] == yy ? 1u << q : 0u;
+      }
+      need_tab[i] = need;
+      retire_tab[i] = retire;
+    }
+    for (int i = threadIdx.x; i < 2 * p.A * NP; i += TC_CTRL_THREADS) {
+      const int par = i / (p.A * NP), phi = (i / NP) % p.A, q = i % NP;   // entry q of a super-step (par, phi)
+      int phi_prev = phi - p.phase_shift;            // accumulating phases; alternating: the other of {0, phase_shift}
+      phi_prev += phi_prev < 0 ? p.A : 0;
+      if (p.phase_alt) phi_prev = phi == 0 ? p.phase_shift : 0;
+      const int qp = q + par * p.ring.shift - (par ^ 1) * p.ring.shift;  // its position in the previous layout's numbering
+      int ret = 0;
+      if (qp >= 0 && qp < NP && lastp_tab[phi_prev * NP + qp] != 0xFF) ret = 1 + (int)lastp_tab[phi_prev * NP + qp];
+      occ_tab[i] = (uint8_t)ret;
+    }
+    ctrl_bar_sync();
+    // Reload order: the entries of the next super-step are loaded in the order in which their positions are
+    // vacated (under the PREVIOUS super-step's phase), ties in the order the next super-step needs them; entries
+    // nobody reads come last and are skipped.  Loading in index order would park the TMA thread on a position
+    // that is vacated late while others wait for their refill.
+    for (int i = threadIdx.x; i < (2 * p.A + 1) * NP; i += TC_CTRL_THREADS) {
+      const int row = i / NP, q = i - row * NP;
+      const bool steady = row < 2 * p.A;
+      const int phi = steady ? row % p.A : 0;
+      auto key_of = [&](int e) {
+        const int fr = firstp_tab[phi * NP + e];
+        return fr == 0xFF ? (1 << 30) + e : ((steady ? occ_tab[row * NP + e] : 0) * (p.A + 1) + fr) * NP + e;
+      };
+      const int my_key = key_of(q);
+      int rank = 0;
+      for (int o = 0; o < NP; ++o) rank += key_of(o) < my_key ? 1 : 0;
+      order_tab[row * NP + rank] = (uint8_t)q;
+    }
+    for (int i = threadIdx.x; i < 2 * p.A; i += TC_CTRL_THREADS) {
+      const int par = i / p.A, phi = i - par * p.A;
+      const int phi_n = tc_next_phase(p, phi);
+      uint32_t seam = 0;
+      for (int q = 0; q < NP; ++q) seam |= occ_tab[((par ^ 1) * p.A + phi_n) * NP + q] == p.A ? 1u << q : 0u;
+      seam_tab[i] = seam;
+    }
+    ctrl_bar_sync();
+    n_ent = 0;   // entries that are read at all (the same for every phase: every step of a super-step is visited)
+    for (int q = 0; q < NP; ++q) n_ent += firstp_tab[q] != 0xFF ? 1 : 0;
+  }
+  if (life) life[1] = clock64();
   if (warp >= TC_WARP_PROD0) {
     // ===================== producers: gather + interpolate -> swizzled A tiles =====================
     const int pw = warp - TC_WARP_PROD0, ptid = (int)threadIdx.x - TC_WARP_PROD0 * 32;
@@ -1026,22 +1043,53 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       if (!centre) phi = tc_next_phase(p, phi);
     }
     // ===================== drain: TMEM -> this split's partial sums =====================
+    if (life) life[2] = clock64();
     ptx::mbar_wait(acc_full, 0);
     ptx::tc_fence_after();
+    if (life) life[3] = clock64();
     const int dq = warp & 3, dh = pw >> 2;   // TMEM lane quadrant of this warp (hardware: warp id % 4), and which half of the rotations
     const int row = m0 + 32 * dq + lane;       // < v_pad: the partial buffer is padded
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * dq) << 16);
     float* prow = p.partial + (((size_t)sk * p.v_pad + row) * p.n_rot + rot0) * p.T + t0;
-    for (int il = dh; il < g_cnt; il += TC_PRODUCER_WARPS / 4) {
-      for (int c0 = 0; c0 < p.n_t; c0 += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(lane_addr + (uint32_t)(il * p.n_t + c0), r);
-        ptx::tmem_ld_wait();
+    if (p.drain_cw > 0) {
+      // A lane holds one accumulator ROW, and rows are n_rot * T floats apart in the partial buffer: storing from
+      // registers made every warp store touch 32 sectors (traced: 20.7 k cycles per CTA for 196 KB).  Instead
+      // the lane parks up to drain_cw columns of its row in the (now idle) weight ring - row stride = an odd
+      // number of 16-byte units, so the 128-bit stores are conflict-free - and hands the row to the bulk-copy
+      // engine as one contiguous piece.
+      const uint32_t row_bytes = (uint32_t)p.drain_cw * 4u + 16u;
+      const uint32_t my_row = b_base + ((uint32_t)pw * 32u + (uint32_t)lane) * row_bytes;
+      for (int il = dh; il < g_cnt; il += TC_PRODUCER_WARPS / 4) {
+        for (int c0 = 0; c0 < p.n_t; c0 += p.drain_cw) {
+          const int cw = min(p.drain_cw, p.n_t - c0);
+          ptx::bulk_wait_read_all();   // the previous piece has left this lane's staging row
+          for (int cc = 0; cc < cw; cc += 16) {
+            uint32_t r[16];
+            ptx::tmem_ld_32x32b_x16(lane_addr + (uint32_t)(il * p.n_t + c0 + cc), r);
+            ptx::tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; q += 4)
-          *reinterpret_cast<uint4*>(prow + (size_t)il * p.T + c0 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
+            for (int q = 0; q < 16; q += 4)
+              ptx::st_shared_v4(my_row + (uint32_t)(cc + q) * 4u, r[q], r[q + 1], r[q + 2], r[q + 3]);
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::bulk_store_global(prow + (size_t)il * p.T + c0, my_row, (uint32_t)cw * 4u);
+          ptx::bulk_commit_group();
+        }
+      }
+      ptx::bulk_wait_read_all();   // shared memory must outlive the copies' reads
+    } else {
+      for (int il = dh; il < g_cnt; il += TC_PRODUCER_WARPS / 4) {
+        for (int c0 = 0; c0 < p.n_t; c0 += 16) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(lane_addr + (uint32_t)(il * p.n_t + c0), r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 16; q += 4)
+            *reinterpret_cast<uint4*>(prow + (size_t)il * p.T + c0 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
+        }
       }
     }
+    if (life) life[4] = clock64();
   } else if (warp == TC_WARP_TMA) {
     // ===================== TMA: weight tiles -> ring =====================
     // (reload order: order_tab, built in the prologue; an entry = one ring position of the current layout)
@@ -1153,6 +1201,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
   if (CL == 2) ptx::cluster_sync();   // neither CTA leaves while the peer may still write / arrive here
+  if (life) life[5] = clock64();
 }
 
 // ---- kernel 2: split reduction + bias + activation + angular max-pooling -------------------------
@@ -1479,6 +1528,15 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   p.phase_shift = phase_shift;
   p.phase_alt = cfg.ring.shift > 0 ? 1 : 0;
   p.bar_bytes = (int)tc_bar_bytes(cfg.ring.n_pos, cfg.ring.n_pos + cfg.ring.shift);
+  {
+    // drain staging: 8 warps x 32 rows x (cw * 4 + 16) bytes inside the weight ring
+    static const int drain_env = getenv("GCB_TC_DRAIN") ? atoi(getenv("GCB_TC_DRAIN")) : -1;   // experiments (0: direct)
+    const size_t ring_bytes = (size_t)(cfg.ring.n_pos + cfg.ring.shift) * (x3 ? 2 : 1) * cfg.n_t * cfg.kc * 4;
+    int cw = cfg.n_t < 128 ? cfg.n_t : 128;
+    while (cw >= 16 && (size_t)TC_PRODUCER_WARPS * 32 * (cw * 4 + 16) > ring_bytes) cw -= 16;
+    p.drain_cw = cw >= 16 ? cw : 0;
+    if (drain_env >= 0) p.drain_cw = drain_env < p.drain_cw ? (drain_env / 16) * 16 : p.drain_cw;
+  }
   static const int debug = getenv("GCB_TC_DEBUG") ? atoi(getenv("GCB_TC_DEBUG")) : 0;
   p.debug = debug;
   p.ring = cfg.ring;
@@ -1507,6 +1565,11 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
     long long t0 = host[0];
     const char* names[4] = {"prod g0: start issued landed empty_ok stored fenced arrived", "scout: start entries a_full",
                             "mma: start waited done a_full_next", "tma: start slot_free issued ss_top"};
+    {
+      long long* e = host + ((size_t)3 * 128 + 127) * 8;
+      fprintf(stderr, "[trace life: entry %lld, prologue done %lld, producers done %lld, accumulators complete %lld, drained %lld, exit %lld]\n",
+              e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0);
+    }
     for (int role = 0; role < 4; ++role) {
       fprintf(stderr, "[trace %s]\n", names[role]);
       for (int n = 0; n < 48; ++n) {
