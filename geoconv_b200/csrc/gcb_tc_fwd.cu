@@ -79,6 +79,10 @@ constexpr int TC_REC_BYTES = TC_M * 32;  // one (x,y) slot of packed records for
 // normalised error against float64 is 1.27e-5 / 9.4e-6 / 8.5e-6 / 5.8e-6 for 8 / 10 / 12 / 16 K splits
 // (tools/prec_check.py); 1920 gives 12 splits there, inside the 1e-5 bar, for 2 % of forward time.
 constexpr int TC_X3_CHAIN_K = 1920;
+// F16X3: kind::f16 sums 16 products per instruction, so a chain of the same element count has half the
+// accumulations; measured at the FAUST shape (tile-balanced splits): 8 splits 5.9e-6 (randn) / 2.0e-6 (SHOT-shaped),
+// 12 splits 4.3e-6 / 1.3e-6, 6 splits 9.2e-6 / 2.6e-6.
+constexpr int TC_H3_CHAIN_K = 2880;
 constexpr uint8_t TC_NO_DUP = 0xFF;
 
 // Where the A angular weight tiles of a super-step live in the shared-memory ring.
@@ -111,6 +115,8 @@ struct TcFwdParams {
   int phase_shift;      // angular visiting order of super-step k starts at (k * phase_shift) % A
   int phase_alt;        // 1: the phase alternates 0, phase_shift, 0, ... with the two ring layouts instead of accumulating
   int bar_bytes;        // size of the mbarrier block in shared memory
+  int tab_bytes;        // size of one rotation group's ring schedules (k_tc_build_tabs)
+  const uint8_t* tabs;  // [n_groups][tab_bytes]
   int drain_cw;         // accumulator columns staged per bulk store in the drain (0: registers -> global directly)
   long long* trace;     // GCB_TC_TRACE (investigation builds): clock64 stamps of CTA (1,0,0), [role][tile][8]
   int debug;            // GCB_TC_DEBUG bits (timing experiments only): 1 = all gathers read row 0, 2 = no MMAs
@@ -300,12 +306,12 @@ static int tc_pick_ksplit(const TcConfig& cfg, int v_out, int R, int A, int F, i
   static const int ks_env = getenv("GCB_TC_KSPLIT") ? atoi(getenv("GCB_TC_KSPLIT")) : 0;   // experiments
   if (ks_env > 0) return ks_env < n_ss ? ks_env : n_ss;
   int s_min = 1;
-  if (x3) s_min = (int)ceil_div64((int64_t)(R * A + 1) * F, TC_X3_CHAIN_K);
+  if (x3) s_min = (int)ceil_div64((int64_t)(R * A + 1) * F, half ? TC_H3_CHAIN_K : TC_X3_CHAIN_K);
   if (s_min > n_ss) s_min = n_ss;
   if (units >= 148 * 6) return s_min;
   const double tile_cycles = (double)(cfg.kc / 8) * (x3 ? 3 : 1) * cfg.g * cfg.n_t / 2.0;   // MMA time of one tile
-  const double work = (double)R * (F / kf) * A * tile_cycles * 1.15;                     // whole K range of one unit
-  const double cta_fixed = 9000.0;                                                           // prologue + first loads + drain
+  const double work = ((double)R * A + 1.0) * (F / kf) * tile_cycles * 1.1;                 // whole K range of one unit
+  const double cta_fixed = 22000.0;   // prologue + pipeline fill + drain + exit (traced: ~25 k cycles, part of it overlapped)
   const double split_cost = 2.0 * (double)ceil_div64(v_out, TC_M) * TC_M * n_rot * T * 4.0 / 6.5e12 * 1.7e9;
   int best = s_min;
   double best_t = 0.0;
@@ -433,6 +439,16 @@ __device__ __forceinline__ void ctrl_bar_sync() {
 }
 __device__ __forceinline__ void producer_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCER_WARPS * 32) : "memory");
+}
+
+// First super-step of K split `sk`: splits are balanced by TILES (a radial super-step has A tiles, a centre
+// super-step one), cut at super-step boundaries.  n_nc / n_c = radial / centre super-steps.
+__host__ __device__ __forceinline__ int tc_split_begin(int n_nc, int n_c, int A, int sk, int ksplit) {
+  const long long total = (long long)n_nc * A + n_c;
+  const long long t = (total * sk + ksplit / 2) / ksplit;   // target tile count before the split
+  if (sk >= ksplit) return n_nc + n_c;
+  if (t >= (long long)n_nc * A) return n_nc + (int)(t - (long long)n_nc * A);
+  return (int)((t + A / 2) / A);
 }
 
 // position in the CTA's tile sequence: super-step ss = (radial ring xr, feature chunk fc) or the
@@ -686,6 +702,111 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
   __syncwarp();
 }
 
+// Weight-ring schedules of rotation group `grp` (they do not depend on the vertex tile or the K split): built
+// once per launch by k_tc_build_tabs into global memory; every CTA copies its group's ~1 KB.  Layout:
+//   need_tab / retire_tab [phase][step] u32: ring entries (positions of the even layout) first / last read at that step
+//   seam_tab [parity][phase] u32: entries of the NEXT super-step whose position is only vacated by the last step
+//   firstp / lastp [phase][entry] u8: first / last step at which the entry is read (0xFF: never - never loaded)
+//   order_tab [parity * A + phase][i] u8: the i-th entry the TMA warp (re)loads (row 2A: the first super-step)
+//   occ_tab [parity][phase][entry] u8: 1 + last step at which the previous super-step still reads the position
+//   last 16 bytes: n_ent = entries that are read at all
+__global__ void k_tc_build_tabs(const __grid_constant__ TcFwdParams p, int pairs, int tab_bytes,
+                                uint8_t* __restrict__ tabs) {
+  extern __shared__ __align__(16) uint8_t tab_smem[];
+  const int tid = threadIdx.x, nthr = blockDim.x, grp = blockIdx.x;
+  const int NP = p.ring.n_pos, AA = p.A * p.A;
+  uint32_t* need_tab = reinterpret_cast<uint32_t*>(tab_smem);
+  uint32_t* retire_tab = need_tab + AA;
+  uint32_t* seam_tab = retire_tab + AA;
+  uint8_t* firstp_tab = reinterpret_cast<uint8_t*>(seam_tab + 2 * p.A);
+  uint8_t* lastp_tab = firstp_tab + p.A * NP;
+  uint8_t* order_tab = lastp_tab + p.A * NP;
+  uint8_t* occ_tab = order_tab + (2 * p.A + 1) * NP;
+  const int rot0 = grp * p.g;
+  const int g_cnt = min(p.g, p.n_rot - rot0);
+  const int n_units = (g_cnt + p.ring.m - 1) / p.ring.m;
+  const int off_anchor = p.rot.off[(pairs ? (grp & ~1) : grp) * p.g];
+  int rel0 = p.rot.off[rot0] - off_anchor;
+  rel0 += rel0 < 0 ? p.A : 0;
+  for (int i = tid; i < tab_bytes / 4; i += nthr) reinterpret_cast<uint32_t*>(tab_smem)[i] = 0u;
+  __syncthreads();
+  for (int i = tid; i < p.A * NP; i += nthr) {
+    // first / last reader of ring entry q under phase phi: a unit reads m adjacent positions starting at the
+    // position of its first tile (tiles relabelled by this CTA's first rotation)
+    const int phi = i / NP, q = i - phi * NP;
+    int first = 0xFF, last = 0xFF;
+    for (int y = 0; y < p.A; ++y)
+      for (int u = 0; u < n_units; ++u) {
+        int s0 = (y + phi + p.rot.off[rot0 + u * p.ring.m] - off_anchor - rel0) % p.A;
+        s0 += s0 < 0 ? p.A : 0;
+        const int wd = min(p.ring.m, g_cnt - u * p.ring.m);
+        const int q0 = p.ring.pos[s0];
+        if (q >= q0 && q < q0 + wd) {
+          if (first == 0xFF) first = y;
+          last = y;
+        }
+      }
+    firstp_tab[i] = (uint8_t)first;
+    lastp_tab[i] = (uint8_t)last;
+  }
+  __syncthreads();
+  for (int i = tid; i < AA; i += nthr) {
+    const int phi = i / p.A, yy = i - phi * p.A;
+    uint32_t need = 0, retire = 0;
+    for (int q = 0; q < NP; ++q) {
+      need |= firstp_tab[phi * NP + q] == yy ? 1u << q : 0u;
+      retire |= lastp_tab[phi * NP + q] == yy ? 1u << q : 0u;
+    }
+    need_tab[i] = need;
+    retire_tab[i] = retire;
+  }
+  for (int i = tid; i < 2 * p.A * NP; i += nthr) {
+    const int par = i / (p.A * NP), phi = (i / NP) % p.A, q = i % NP;   // entry q of a super-step (par, phi)
+    int phi_prev = phi - p.phase_shift;            // accumulating phases; alternating: the other of {0, phase_shift}
+    phi_prev += phi_prev < 0 ? p.A : 0;
+    if (p.phase_alt) phi_prev = phi == 0 ? p.phase_shift : 0;
+    const int qp = q + par * p.ring.shift - (par ^ 1) * p.ring.shift;  // its position in the previous layout's numbering
+    int ret = 0;
+    if (qp >= 0 && qp < NP && lastp_tab[phi_prev * NP + qp] != 0xFF) ret = 1 + (int)lastp_tab[phi_prev * NP + qp];
+    occ_tab[i] = (uint8_t)ret;
+  }
+  __syncthreads();
+  // Reload order: the entries of the next super-step are loaded in the order in which their positions are
+  // vacated (under the PREVIOUS super-step's phase), ties in the order the next super-step needs them; entries
+  // nobody reads come last and are skipped.  Loading in index order would park the TMA thread on a position
+  // that is vacated late while others wait for their refill.
+  for (int i = tid; i < (2 * p.A + 1) * NP; i += nthr) {
+    const int row = i / NP, q = i - row * NP;
+    const bool steady = row < 2 * p.A;
+    const int phi = steady ? row % p.A : 0;
+    auto key_of = [&](int e) {
+      const int fr = firstp_tab[phi * NP + e];
+      return fr == 0xFF ? (1 << 30) + e : ((steady ? occ_tab[row * NP + e] : 0) * (p.A + 1) + fr) * NP + e;
+    };
+    const int my_key = key_of(q);
+    int rank = 0;
+    for (int o = 0; o < NP; ++o) rank += key_of(o) < my_key ? 1 : 0;
+    order_tab[row * NP + rank] = (uint8_t)q;
+  }
+  for (int i = tid; i < 2 * p.A; i += nthr) {
+    const int par = i / p.A, phi = i - par * p.A;
+    const int phi_n = tc_next_phase(p, phi);
+    uint32_t seam = 0;
+    for (int q = 0; q < NP; ++q) seam |= occ_tab[((par ^ 1) * p.A + phi_n) * NP + q] == p.A ? 1u << q : 0u;
+    seam_tab[i] = seam;
+  }
+  __syncthreads();
+  __syncthreads();
+  if (tid == 0) {
+    int n_ent = 0;
+    for (int q = 0; q < NP; ++q) n_ent += firstp_tab[q] != 0xFF ? 1 : 0;
+    *reinterpret_cast<int*>(tab_smem + tab_bytes - 16) = n_ent;
+  }
+  __syncthreads();
+  for (int i = tid; i < tab_bytes / 16; i += nthr)
+    reinterpret_cast<uint4*>(tabs + (size_t)grp * tab_bytes)[i] = reinterpret_cast<const uint4*>(tab_smem)[i];
+}
+
 // CL = 2: the two CTAs of a (1,2,1) cluster work on the SAME 128-vertex tile and K range with
 // different rotation groups.  Each gathers and interpolates only half of the rows and hands them to
 // the peer's A stage with the bulk-copy engine (DSMEM), so the gather traffic of a tile - the
@@ -765,8 +886,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   const int g_cnt = min(p.g, p.n_rot - rot0);
   const int RA = p.R * p.A;
   const int n_ss = (p.R + 1) * p.nfc;  // super-steps: (x, f-chunk) for x < R, then the centre slab
-  const int ss_begin = (int)(((int64_t)n_ss * sk) / p.ksplit);
-  const int ss_end = (int)(((int64_t)n_ss * (sk + 1)) / p.ksplit);
+  const int ss_begin = tc_split_begin(p.R * p.nfc, p.nfc, p.A, sk, p.ksplit);
+  const int ss_end = tc_split_begin(p.R * p.nfc, p.nfc, p.A, sk + 1, p.ksplit);
   const int n_units = (g_cnt + p.ring.m - 1) / p.ring.m;   // MMA units: groups of <= m merged rotations
   // The angular visiting order is common to the cluster pair (they share the gathered tiles): it is
   // anchored at the first rotation of the pair's first CTA.  rel0 = this CTA's first offset
@@ -802,6 +923,11 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
   }
+  if (warp == TC_WARP_SCOUT) {   // this group's ring schedules (k_tc_build_tabs), ~1 KB from L2
+    const uint4* src = reinterpret_cast<const uint4*>(p.tabs + (size_t)grp * p.tab_bytes);
+    uint4* dst = reinterpret_cast<uint4*>(smem_gen + (tab_base - smem_base));
+    for (int i = lane; i < p.tab_bytes / 16; i += 32) dst[i] = __ldg(src + i);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (CL == 2) ptx::cluster_sync();   // the peer's barriers exist before anyone arrives on them remotely
@@ -809,80 +935,6 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   const uint32_t tmem_base = __shfl_sync(
       0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base)), 0);
 
-  // The weight-ring schedules are only read by the control warps (TMA, MMA issuers, scout): they build them
-  // while the producers already stage their records and gather the first tiles (traced: the prologue cost
-  // 10.6 k cycles per CTA when all 12 warps sat through it).
-  int n_ent = 0;
-  if (warp < TC_WARP_PROD0) {
-    for (int i = threadIdx.x; i < p.A * NP; i += TC_CTRL_THREADS) {
-      // first / last reader of ring entry q under phase phi: a unit reads m adjacent positions starting at the
-      // position of its first tile (tiles relabelled by this CTA's first rotation)
-      const int phi = i / NP, q = i - phi * NP;
-      int first = 0xFF, last = 0xFF;
-      for (int y = 0; y < p.A; ++y)
-        for (int u = 0; u < n_units; ++u) {
-          int s0 = (y + phi + p.rot.off[rot0 + u * p.ring.m] - off_anchor - rel0) % p.A;
-          s0 += s0 < 0 ? p.A : 0;
-          const int wd = min(p.ring.m, g_cnt - u * p.ring.m);
-          const int q0 = p.ring.pos[s0];
-          if (q >= q0 && q < q0 + wd) {
-            if (first == 0xFF) first = y;
-            last = y;
-          }
-        }
-      firstp_tab[i] = (uint8_t)first;
-      lastp_tab[i] = (uint8_t)last;
-    }
-    ctrl_bar_sync();
-    for (int i = threadIdx.x; i < AA; i += TC_CTRL_THREADS) {
-      const int phi = i / p.A, yy = i - phi * p.A;
-      uint32_t need = 0, retire = 0;
-      for (int q = 0; q < NP; ++q) {
-        need |= firstp_tab[phi * NP + q] == yy ? 1u << q : 0u;
-        retire |= lastp_tab[phi * NP + q] == yy ? 1u << q : 0u;
-      }
-      need_tab[i] = need;
-      retire_tab[i] = retire;
-    }
-    for (int i = threadIdx.x; i < 2 * p.A * NP; i += TC_CTRL_THREADS) {
-      const int par = i / (p.A * NP), phi = (i / NP) % p.A, q = i % NP;   // entry q of a super-step (par, phi)
-      int phi_prev = phi - p.phase_shift;            // accumulating phases; alternating: the other of {0, phase_shift}
-      phi_prev += phi_prev < 0 ? p.A : 0;
-      if (p.phase_alt) phi_prev = phi == 0 ? p.phase_shift : 0;
-      const int qp = q + par * p.ring.shift - (par ^ 1) * p.ring.shift;  // its position in the previous layout's numbering
-      int ret = 0;
-      if (qp >= 0 && qp < NP && lastp_tab[phi_prev * NP + qp] != 0xFF) ret = 1 + (int)lastp_tab[phi_prev * NP + qp];
-      occ_tab[i] = (uint8_t)ret;
-    }
-    ctrl_bar_sync();
-    // Reload order: the entries of the next super-step are loaded in the order in which their positions are
-    // vacated (under the PREVIOUS super-step's phase), ties in the order the next super-step needs them; entries
-    // nobody reads come last and are skipped.  Loading in index order would park the TMA thread on a position
-    // that is vacated late while others wait for their refill.
-    for (int i = threadIdx.x; i < (2 * p.A + 1) * NP; i += TC_CTRL_THREADS) {
-      const int row = i / NP, q = i - row * NP;
-      const bool steady = row < 2 * p.A;
-      const int phi = steady ? row % p.A : 0;
-      auto key_of = [&](int e) {
-        const int fr = firstp_tab[phi * NP + e];
-        return fr == 0xFF ? (1 << 30) + e : ((steady ? occ_tab[row * NP + e] : 0) * (p.A + 1) + fr) * NP + e;
-      };
-      const int my_key = key_of(q);
-      int rank = 0;
-      for (int o = 0; o < NP; ++o) rank += key_of(o) < my_key ? 1 : 0;
-      order_tab[row * NP + rank] = (uint8_t)q;
-    }
-    for (int i = threadIdx.x; i < 2 * p.A; i += TC_CTRL_THREADS) {
-      const int par = i / p.A, phi = i - par * p.A;
-      const int phi_n = tc_next_phase(p, phi);
-      uint32_t seam = 0;
-      for (int q = 0; q < NP; ++q) seam |= occ_tab[((par ^ 1) * p.A + phi_n) * NP + q] == p.A ? 1u << q : 0u;
-      seam_tab[i] = seam;
-    }
-    ctrl_bar_sync();
-    n_ent = 0;   // entries that are read at all (the same for every phase: every step of a super-step is visited)
-    for (int q = 0; q < NP; ++q) n_ent += firstp_tab[q] != 0xFF ? 1 : 0;
-  }
   if (life) life[1] = clock64();
   if (warp >= TC_WARP_PROD0) {
     // ===================== producers: gather + interpolate -> swizzled A tiles =====================
@@ -1095,6 +1147,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     // (reload order: order_tab, built in the prologue; an entry = one ring position of the current layout)
     uint64_t fills = 0;  // bit P = parity of the number of fills of ring position P
     const uint32_t lo_ring = (uint32_t)(n_ring * b_tile_bytes);
+    const int n_ent = *reinterpret_cast<const int*>(smem_gen + (tab_base - smem_base) + p.tab_bytes - 16);
     int load_no = 0;
     int phi = 0, par = 0;
     bool first_ss = true;
@@ -1377,6 +1430,7 @@ bool tc_half_supported(int R, int A, int F, int T, int n_rot) {
   return tc_pick_config(A, F, T, n_rot, true, true, 0).ok;
 }
 
+constexpr size_t TC_TABS_BYTES = (size_t)GCB_MAX_ROT * 16384;   // ring schedules of every rotation group
 constexpr size_t TC_SCALES_BYTES = 256;   // {max|X|, max sum|w|, max|Wcat|} as bits, then the three scales
 
 size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, int precision) {
@@ -1390,7 +1444,7 @@ size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, 
     if (s > ksplit) ksplit = s;
   }
   return tc_recs_bytes(v_out, R, A) + (x3 ? 2 : 1) * tc_wcat_bytes(R, A, F, T) +
-         tc_partial_bytes(v_out, n_rot, T, ksplit) + TC_SCALES_BYTES + 1024;
+         tc_partial_bytes(v_out, n_rot, T, ksplit) + TC_SCALES_BYTES + TC_TABS_BYTES + 1024;
 }
 
 template <int KC, bool X3, bool H, int CL, bool KEEP>
@@ -1528,6 +1582,9 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   p.phase_shift = phase_shift;
   p.phase_alt = cfg.ring.shift > 0 ? 1 : 0;
   p.bar_bytes = (int)tc_bar_bytes(cfg.ring.n_pos, cfg.ring.n_pos + cfg.ring.shift);
+  p.tab_bytes = (int)tc_tab_bytes(A, cfg.ring.n_pos);
+  p.tabs = (const uint8_t*)mx + TC_SCALES_BYTES;
+  GCB_REQUIRE((size_t)cfg.n_groups * p.tab_bytes <= TC_TABS_BYTES, GCB_EUNSUPPORTED, "tc_conv_fwd: ring schedules exceed their workspace");
   {
     // drain staging: 8 warps x 32 rows x (cw * 4 + 16) bytes inside the weight ring
     static const int drain_env = getenv("GCB_TC_DRAIN") ? atoi(getenv("GCB_TC_DRAIN")) : -1;   // experiments (0: direct)
@@ -1548,6 +1605,11 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
     p.trace = trace_dev;
   }
   p.rot = rot;
+  {
+    const bool pairs = tc_use_pairs() && cfg.n_groups % 2 == 0 && cfg.kc >= 16;
+    k_tc_build_tabs<<<cfg.n_groups, 128, p.tab_bytes, st>>>(p, pairs ? 1 : 0, p.tab_bytes, (uint8_t*)p.tabs);
+    GCB_LAUNCH_OK();
+  }
   dim3 grid((unsigned)m_tiles, (unsigned)cfg.n_groups, (unsigned)((T / cfg.n_t) * ksplit));
   if (half) rc = cfg.kc == 16 ? tc_launch<16, true, true>(mh, ml, p, cfg, grid, st) : tc_launch<8, true, true>(mh, ml, p, cfg, grid, st);
   else if (cfg.kc == 32) rc = x3 ? tc_launch<32, true>(mh, ml, p, cfg, grid, st) : tc_launch<32, false>(mh, ml, p, cfg, grid, st);

@@ -234,14 +234,30 @@ def test_faust_shape_against_oracle(precision):
         z = AngularMaxPooling()(y)
         flips = (y._gcb_pooled[1].cpu() != ref["argmax"]).sum().item()
     z.backward(grad_z.to(DEV))
+    # A ReLU derivative bit may differ from the reference's where the pre-activation is within rounding of
+    # zero (|z| and |z_ref| below 2e-6 of the largest output): admissible, like a rotation flip at a near tie.
+    zc, zr = z.detach().cpu(), ref["z"]
+    mask_diff = (zc > 0) != (zr > 0)
     if flips == 0:
         assert nerr(z, ref["z"]) < tol
+        assert (torch.maximum(zc, zr)[mask_diff] <= 2e-6 * ref["y"].abs().max()).all()
+    assert flips <= 8 and mask_diff.sum().item() <= 8
+    if flips == 0 and not mask_diff.any():
         assert nerr(xs.grad, ref["d_signal"]) < tol
         assert nerr(layer._template_neighbor_weights.grad, ref["d_w_neighbor"]) < tol
         assert nerr(layer._template_self_weights.grad, ref["d_w_self"]) < tol
         assert nerr(layer._bias.grad, ref["d_bias"]) < tol
-    else:  # gradients of the flipped vertices differ legitimately: compare on the rest via closed form
-        assert flips <= 8
+    else:
+        # the gradients then legitimately differ from autograd over the reference forward: check the backward
+        # arithmetic against the closed form evaluated at THIS forward's selected rotations and outputs
+        arg_own = y._gcb_pooled[1].cpu()
+        dx, dweff, dws, db = O.conv_amp_backward_closed_form(
+            signal.double(), bary, O.fold_prior(wn.double(), prior.double()), ws.double(), zc.double(),
+            arg_own.long(), grad_z.double(), "relu")
+        assert nerr(xs.grad, dx) < tol
+        assert nerr(layer._template_neighbor_weights.grad, O.unfold_prior_grad(dweff, prior.double())) < tol
+        assert nerr(layer._template_self_weights.grad, dws) < tol
+        assert nerr(layer._bias.grad, db) < tol
 
 
 @pytest.mark.gpu
