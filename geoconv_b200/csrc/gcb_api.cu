@@ -100,9 +100,6 @@ extern "C" int gcb_tc_half_supported(int32_t R, int32_t A, int32_t F, int32_t T,
   return tc_supported(R, A, F, T, n_rot) && tc_half_supported(R, A, F, T, n_rot) ? 1 : 0;
 }
 
-// the backward kernels have no fp16 variant yet: GCB_PREC_F16X3 runs them in 3xTF32
-static int bwd_precision(int precision) { return precision == GCB_PREC_F16X3 ? GCB_PREC_TF32X3 : precision; }
-
 extern "C" size_t gcb_conv_fwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A,
                                                int32_t F, int32_t T, int32_t n_rot, int precision) {
   (void)v_src;
@@ -155,7 +152,6 @@ extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, 
 
 extern "C" size_t gcb_conv_bwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A,
                                                int32_t F, int32_t T, int precision) {
-  precision = bwd_precision(precision);
   size_t d_full = align_up((size_t)v_out * R * A * F * sizeof(float), 256);
   size_t ffma = d_full + ffma_bwd_workspace_bytes(v_out, R, A, F) + 256;
   if (precision != GCB_PREC_FP32 && tc_bwd_supported(R, A, F, T)) {
@@ -172,7 +168,6 @@ extern "C" int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, 
                             int accumulate, const float* interp, float* d_x, float* d_w_eff, float* d_w_self,
                             float* d_bias, void* workspace, size_t workspace_bytes, void* stream) {
   GCB_REQUIRE(x && idx && w && w_self && h && rot_sel, GCB_EINVAL, "gcb_conv_bwd: null input pointer");
-  precision = bwd_precision(precision);
   GCB_REQUIRE(!d_x || !w_eff || (csr_row_ptr && csr_entries), GCB_EINVAL, "gcb_conv_bwd: d_x needs the CSR");
   GCB_REQUIRE(d_w_eff && d_w_self && d_bias, GCB_EINVAL, "gcb_conv_bwd: null output pointer");
   int rc = check_shape(v_out, v_src, R, A, F, T);

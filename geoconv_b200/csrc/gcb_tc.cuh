@@ -1,6 +1,7 @@
 // Helpers shared by the tensor-core translation units (gcb_tc_fwd.cu defines them).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "gcb_common.cuh"
 
@@ -17,6 +18,20 @@ int tc_make_tmap_2d(CUtensorMap* out, const float* base, uint64_t inner, uint64_
 int tc_make_tmap_mn(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                     uint32_t box_rows, uint32_t box_atoms);
 
+// fp16 variants (GCB_PREC_F16X3).  2-D: box_inner halves per row, swizzle span = box_inner * 2 bytes.
+// MN-major: row-major fp16 matrix [rows][cols_ld] seen as (64 columns, rows, cols_ld / 64); a box = `box_atoms`
+// 64-column atoms x `box_rows` rows, each atom deposited as rows of 128 bytes with the standard 128-byte
+// swizzle - the canonical MN-major layout of 16-bit UMMA operands (cols_ld % 64 == 0).
+int tc_make_tmap_2d_h(CUtensorMap* out, const __half* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer);
+int tc_make_tmap_mn_h(CUtensorMap* out, const __half* base, uint64_t rows, uint64_t cols_ld, uint64_t row_stride_bytes,
+                      uint32_t box_rows, uint32_t box_atoms);
+// Wcat * (*scale) = hi + lo in fp16, [T][R*A*F + F]
+int tc_build_wcat_h(const float* w_eff, const float* w_self, int T, int R, int A, int F, const float* scale,
+                    __half* hi, __half* lo, cudaStream_t st);
+// max |a[i]| over up to two arrays as fp32 bits, atomicMax'ed into *out (zero it first)
+int tc_absmax(const float* a, int64_t na, const float* b, int64_t nb, unsigned* out, cudaStream_t st);
+
 // slot-major packed barycentric records [R*A][v_pad][2 x uint4], v_pad = multiple of 128
 size_t tc_recs_bytes(int v_out, int R, int A);
 int tc_pack_recs(const int32_t* idx, const float* w, int v_out, int R, int A, uint4* recs, cudaStream_t st);
@@ -32,15 +47,21 @@ struct TcGLayout {
   size_t g_bytes, xsplit_bytes, partial_bytes, total;
   int v_pad, kg, m_pad, bn, n_ntiles, vsplit, n_kch;
 };
-TcGLayout tc_g_layout(int v_src, int R, int A, int F, int T, bool x3);
+TcGLayout tc_g_layout(int v_src, int R, int A, int F, int T, bool x3, bool half = false);
+// fp16 route (half = true: `scales` = {sG, sW, sX, 1/(sG*sW), 1/(sG*sX)} on the device; g_hi / g_lo / wcat / x_hi /
+// x_lo are then __half buffers with row strides kg_ld = align(kg, 64), x_ld = align(F, 64))
+size_t tc_bwd_scales_bytes();
+int tc_bwd_scales(const float* h, const float* w, const int32_t* csr_row_ptr, const float* w_eff, const float* w_self,
+                  const float* x, int v_out, int v_src, int R, int A, int F, int T, void* scratch, cudaStream_t st);
 int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int32_t* csr_row_ptr,
                const int32_t* csr_entries, int v_out, int v_src, int R, int A, int T, bool x3, float* g_hi,
-               float* g_lo, cudaStream_t st);
+               float* g_lo, cudaStream_t st, const float* scales = nullptr);
 int tc_dx_from_g(const float* g_hi, const float* g_lo, const float* wcat_hi, const float* wcat_lo, int v_src, int R,
-                 int A, int F, int T, bool x3, int accumulate, float* d_x, cudaStream_t st);
+                 int A, int F, int T, bool x3, int accumulate, float* d_x, cudaStream_t st,
+                 const float* scales = nullptr);
 int tc_dw_from_g(const float* g_hi, const float* g_lo, const float* x, int v_src, int R, int A, int F, int T,
                  bool x3, int accumulate, float* d_w_eff, float* d_w_self, float* x_hi, float* x_lo, float* partial,
-                 cudaStream_t st);
+                 cudaStream_t st, const float* scales = nullptr);
 
 // tensor-core backward (gcb_tc_bwd.cu)
 bool tc_bwd_supported(int R, int A, int F, int T);

@@ -423,12 +423,12 @@ static BwLayout bw_layout(int v_out, int v_src, int R, int A, int F, int T, bool
   L.bias_part = bias_a > bias_b ? bias_a : bias_b;
   L.via_g = tc_g_layout(v_src, R, A, F, T, x3).total;   // G, the split signal, the GEMM partials
   const size_t gather_route = L.recs + L.ht + L.partial;
-  L.total = L.bias_part + L.wcat + (gather_route > L.via_g ? gather_route : L.via_g) + 1024;
+  L.total = L.bias_part + L.wcat + (gather_route > L.via_g ? gather_route : L.via_g) + tc_bwd_scales_bytes() + 1024;
   return L;
 }
 
 size_t tc_bwd_workspace_bytes(int v_out, int v_src, int R, int A, int F, int T, int precision) {
-  return bw_layout(v_out, v_src, R, A, F, T, precision == GCB_PREC_TF32X3).total;
+  return bw_layout(v_out, v_src, R, A, F, T, precision == GCB_PREC_TF32X3 || precision == GCB_PREC_F16X3).total;
 }
 
 template <bool X3>
@@ -447,7 +447,11 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
                 int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,
                 const float* interp, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias, void* workspace,
                 size_t workspace_bytes, cudaStream_t st) {
-  const bool x3 = precision == GCB_PREC_TF32X3;
+  // fp16 operand splits (GCB_PREC_F16X3) serve the route through G; the centre-only and gather-fed routes run
+  // the same precision request as 3xTF32
+  static const bool no_half = getenv("GCB_BWD_NO_HALF") && atoi(getenv("GCB_BWD_NO_HALF")) != 0;   // A/B measurements
+  const bool half = precision == GCB_PREC_F16X3 && w_eff && csr_row_ptr && csr_entries && !no_half;
+  const bool x3 = precision == GCB_PREC_TF32X3 || precision == GCB_PREC_F16X3;
   BwLayout L = bw_layout(v_out, v_src, R, A, F, T, x3);
   GCB_REQUIRE(workspace_bytes >= L.total, GCB_EWORKSPACE, "tc_conv_bwd: workspace too small");
   GCB_REQUIRE((uintptr_t)x % 16 == 0, GCB_EINVAL, "tc_conv_bwd: x must be 16-byte aligned");
@@ -457,6 +461,8 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
   float* wc_hi = (float*)ws;
   float* wc_lo = x3 ? (float*)(ws + L.wcat / 2) : nullptr;
   ws += L.wcat;
+  void* scale_scratch = ws;
+  ws += tc_bwd_scales_bytes();
   int rc;
 
   if (!w_eff) {
@@ -490,6 +496,13 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     const TcGLayout GL = tc_g_layout(v_src, R, A, F, T, x3);
     float* g_hi = (float*)ws;
     float* g_lo = x3 ? g_hi + (size_t)GL.v_pad * GL.kg : nullptr;
+    const float* scales = nullptr;
+    if (half) {   // fp16 buffers: rows of kg_ld halves (they fit in the 3xTF32 sizes)
+      g_lo = (float*)((__half*)g_hi + (size_t)GL.v_pad * (ceil_div64(GL.kg, 64) * 64));
+      rc = tc_bwd_scales(h, w, csr_row_ptr, w_eff, w_self, x, v_out, v_src, R, A, F, T, scale_scratch, st);
+      if (rc) return rc;
+      scales = (const float*)((const unsigned*)scale_scratch + 8);
+    }
     ws += GL.g_bytes;
     float* x_hi = (float*)ws;
     float* x_lo = x3 ? x_hi + (size_t)v_src * F : nullptr;
@@ -500,13 +513,15 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     GCB_LAUNCH_OK();
     k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.bias_blocks, T, accumulate, d_bias);
     GCB_LAUNCH_OK();
-    rc = tc_build_g(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, x3, g_hi, g_lo, st);
+    rc = tc_build_g(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, x3, g_hi, g_lo, st, scales);
     if (rc) return rc;
-    rc = tc_dw_from_g(g_hi, g_lo, x, v_src, R, A, F, T, x3, accumulate, d_w_eff, d_w_self, x_hi, x_lo, partial, st);
+    rc = tc_dw_from_g(g_hi, g_lo, x, v_src, R, A, F, T, x3, accumulate, d_w_eff, d_w_self, x_hi, x_lo, partial, st,
+                      scales);
     if (rc || !d_x) return rc;
-    rc = tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);
+    rc = half ? tc_build_wcat_h(w_eff, w_self, T, R, A, F, scales + 1, (__half*)wc_hi, (__half*)wc_lo, st)
+              : tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);
     if (rc) return rc;
-    return tc_dx_from_g(g_hi, g_lo, wc_hi, wc_lo, v_src, R, A, F, T, x3, accumulate, d_x, st);
+    return tc_dx_from_g(g_hi, g_lo, wc_hi, wc_lo, v_src, R, A, F, T, x3, accumulate, d_x, st, scales);
   }
 
   // ---- no CSR: weight gradients by the gather-fed contraction (dSignal needs the CSR) ----

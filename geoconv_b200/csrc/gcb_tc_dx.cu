@@ -21,6 +21,8 @@
 //                  chunks and summed in fp32 by the epilogue (the tensor core accumulates with
 //                  truncation, so short chains are what keeps the 3xTF32 mode within 1e-5).
 #include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "gcb_common.cuh"
 #include "gcb_ptx.cuh"
@@ -41,11 +43,33 @@ __device__ __forceinline__ uint64_t dx_mnmajor_desc(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// fp16 MN-major operand, standard 128-byte swizzle: atoms of 64 (M or N) elements x 8 k-rows of 128 bytes;
+// lbo = byte distance between atoms along M/N, sbo = between 8-row groups along K
+__device__ __forceinline__ uint64_t dx_mnmajor_desc_h(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+// v * s = hi + lo (fp16)
+__device__ __forceinline__ void split_half(float v, float s, __half& hi, __half& lo) {
+  v *= s;
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
 // ---- G[v, s', t] ----------------------------------------------------------------------------------
+// H: G * scales[0] as fp16 hi / lo rows of kg_ld (>= kg, padded with zeros) halves
+template <bool H>
 __global__ void k_bw_build_g(const float* __restrict__ h, const float* __restrict__ w,
                              const int32_t* __restrict__ rot_sel, const int32_t* __restrict__ row_ptr,
                              const int32_t* __restrict__ entries, int v_out, int v_src, int R, int A, int T,
-                             int kg /* (R*A+1)*T */, float* __restrict__ g_hi, float* __restrict__ g_lo) {
+                             int kg /* (R*A+1)*T */, int kg_ld, const float* __restrict__ scales,
+                             float* __restrict__ g_hi, float* __restrict__ g_lo) {
   extern __shared__ float s_acc[];                       // [RA][T]
   __shared__ int s_k[G_CHUNK];
   __shared__ int s_slot[G_CHUNK];
@@ -55,8 +79,15 @@ __global__ void k_bw_build_g(const float* __restrict__ h, const float* __restric
   const int t = threadIdx.x;
   float* out_hi = g_hi + (size_t)v * kg;
   float* out_lo = g_lo ? g_lo + (size_t)v * kg : nullptr;
+  __half* hh = reinterpret_cast<__half*>(g_hi) + (size_t)v * kg_ld;
+  __half* hl = reinterpret_cast<__half*>(g_lo) + (size_t)v * kg_ld;
+  const float sg = H ? __ldg(scales) : 1.f;
+  if (H) {
+    for (int i = kg + threadIdx.x; i < kg_ld; i += blockDim.x) { hh[i] = __float2half_rn(0.f); hl[i] = __float2half_rn(0.f); }
+  }
   if (v >= v_src) {                                      // padding rows of the GEMM's A operand
     for (int i = threadIdx.x; i < kg; i += blockDim.x) {
+      if (H) { hh[i] = __float2half_rn(0.f); hl[i] = __float2half_rn(0.f); continue; }
       out_hi[i] = 0.f;
       if (out_lo) out_lo[i] = 0.f;
     }
@@ -101,12 +132,14 @@ __global__ void k_bw_build_g(const float* __restrict__ h, const float* __restric
   __syncthreads();
   for (int i = threadIdx.x; i < RA * T; i += blockDim.x) {
     const float val = s_acc[i];
+    if (H) { split_half(val, sg, hh[i], hl[i]); continue; }
     const float hi = ptx::to_tf32(val);
     out_hi[i] = hi;
     if (out_lo) out_lo[i] = val - hi;
   }
   for (int i = threadIdx.x; i < T; i += blockDim.x) {   // centre slab: h[v] itself (zero for halo rows)
     const float val = v < v_out ? h[(size_t)v * T + i] : 0.f;
+    if (H) { split_half(val, sg, hh[RA * T + i], hl[RA * T + i]); continue; }
     const float hi = ptx::to_tf32(val);
     out_hi[RA * T + i] = hi;
     if (out_lo) out_lo[RA * T + i] = val - hi;
@@ -121,6 +154,8 @@ constexpr int GM_STAGE_A = 16 * 1024;   // 128 rows x 32 k
 constexpr int GM_STAGE_B = 16 * 1024;   // 32 k x 128 n (four MN-major column blocks)
 
 struct TcGemmParams {
+  const float* inv_scale;  // fp16 route: the accumulators carry the operand scales; *inv_scale undoes them
+  uint32_t h_lbo, h_sbo, h_kstep;   // fp16 MN-major descriptor fields (bytes)
   float* out;
   int ld_out, rows_valid, cols_valid, accumulate;
   int n_mtiles, n_ntiles, ns;
@@ -129,19 +164,25 @@ struct TcGemmParams {
   int group_stride;
 };
 
-template <bool X3>
+// H (fp16 operands): a stage holds two sub-chunks of 32 k, each an (A 128 x 64 B K-major SWIZZLE_64B, B 32 k x 128 n
+// as two 64-column MN-major atoms) pair laid out like the tf32 stage at half the size.
+template <bool X3, bool H>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
           const __grid_constant__ CUtensorMap tmap_b_hi, const __grid_constant__ CUtensorMap tmap_b_lo,
           const TcGemmParams p) {
   constexpr int NPROD = X3 ? 2 : 1;
-  constexpr int STAGE_BYTES = NPROD * (GM_STAGE_A + GM_STAGE_B);
+  constexpr int NSUB = H ? 2 : 1;                       // 32-k sub-chunks per stage
+  constexpr int SUB_A = GM_STAGE_A / NSUB, SUB_B = GM_STAGE_B / NSUB;
+  constexpr int SUB_BYTES = NPROD * (SUB_A + SUB_B);
+  constexpr int STAGE_BYTES = NSUB * SUB_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + (uint32_t)(p.ns * STAGE_BYTES);
   const uint32_t full = bar_base, empty = full + 8u * p.ns;
   const uint32_t tm_full = empty + 8u * p.ns, tm_empty = tm_full + 16u;
+  const int n_st = (p.n_kc + NSUB - 1) / NSUB;         // stages per tile
   const uint32_t tmem_slot = tm_empty + 16u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.n_mtiles * p.n_ntiles;
@@ -174,27 +215,34 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
         int grp = 0, in_grp = 0;
-        for (int kc = 0; kc < p.n_kc; ++kc) {
+        for (int si = 0; si < n_st; ++si) {
           ptx::mbar_wait(empty + 8u * stage, par);
-          const uint32_t a_dst = smem_base + (uint32_t)(stage * STAGE_BYTES);
-          const uint32_t b_dst = a_dst + NPROD * GM_STAGE_A;
-          const int b_row = in_grp * 32, b_col = grp * p.group_stride + nt * GM_BN;
-          ptx::mbar_arrive_expect_tx(full + 8u * stage, (uint32_t)STAGE_BYTES);
-          ptx::tma_load_2d(a_dst, &tmap_a_hi, full + 8u * stage, kc * 32, mt * 128);
-          if (X3) ptx::tma_load_2d(a_dst + GM_STAGE_A, &tmap_a_lo, full + 8u * stage, kc * 32, mt * 128);
+          const int n_sub = min(NSUB, p.n_kc - si * NSUB);
+          ptx::mbar_arrive_expect_tx(full + 8u * stage, (uint32_t)(n_sub * SUB_BYTES));
+          for (int sub = 0; sub < n_sub; ++sub) {
+            const int kc = si * NSUB + sub;
+            const uint32_t a_dst = smem_base + (uint32_t)(stage * STAGE_BYTES + sub * SUB_BYTES);
+            const uint32_t b_dst = a_dst + NPROD * SUB_A;
+            const int b_row = in_grp * 32, b_col = grp * p.group_stride + nt * GM_BN;
+            ptx::tma_load_2d(a_dst, &tmap_a_hi, full + 8u * stage, kc * 32, mt * 128);
+            if (X3) ptx::tma_load_2d(a_dst + SUB_A, &tmap_a_lo, full + 8u * stage, kc * 32, mt * 128);
+            constexpr int BOX_N = H ? 64 : 32;            // columns per MN-major atom (128 bytes)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            ptx::tma_load_2d(b_dst + j * 4096, &tmap_b_hi, full + 8u * stage, b_col + 32 * j, b_row);
-            if (X3) ptx::tma_load_2d(b_dst + GM_STAGE_B + j * 4096, &tmap_b_lo, full + 8u * stage, b_col + 32 * j, b_row);
+            for (int j = 0; j < GM_BN / BOX_N; ++j) {
+              ptx::tma_load_2d(b_dst + j * 4096, &tmap_b_hi, full + 8u * stage, b_col + BOX_N * j, b_row);
+              if (X3) ptx::tma_load_2d(b_dst + SUB_B + j * 4096, &tmap_b_lo, full + 8u * stage, b_col + BOX_N * j, b_row);
+            }
+            if (++in_grp == p.kc_per_group) { in_grp = 0; ++grp; }
           }
-          if (++in_grp == p.kc_per_group) { in_grp = 0; ++grp; }
           if (++stage == p.ns) { stage = 0; par ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_tf32(128, GM_BN) | (1u << 16);   // B MN-major
+      const uint32_t idesc = ptx::make_idesc<H>(128, GM_BN) | (1u << 16);   // B MN-major
+      constexpr int A_ROW = H ? 64 : 128;                 // bytes of one K-major A row (32 k)
+      constexpr int KB = H ? 2 : 4;                       // MMAs per 32-k sub-chunk (K = 16 halves / 8 tf32)
       int stage = 0;
       uint32_t par = 0;
       int it = 0;
@@ -202,22 +250,30 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
         ptx::mbar_wait(tm_empty, (((uint32_t)it) & 1u) ^ 1u);
         ptx::tc_fence_after();
         uint32_t started = 0;   // bit a: accumulator a already holds a partial sum
-        for (int kc = 0; kc < p.n_kc; ++kc) {
-          const int acc = nacc == 4 ? (kc & 3) : 0;
-          const uint32_t d = tmem_base + (uint32_t)(acc * GM_BN);
+        for (int si = 0; si < n_st; ++si) {
           ptx::mbar_wait(full + 8u * stage, par);
           ptx::tc_fence_after();
-          const uint32_t a_hi = smem_base + (uint32_t)(stage * STAGE_BYTES);
-          const uint32_t b_hi = a_hi + NPROD * GM_STAGE_A;
+          const int n_sub = min(NSUB, p.n_kc - si * NSUB);
+          for (int sub = 0; sub < n_sub; ++sub) {
+            const int kc = si * NSUB + sub;
+            const int acc = nacc == 4 ? (kc & 3) : 0;
+            const uint32_t d = tmem_base + (uint32_t)(acc * GM_BN);
+            const uint32_t a_hi = smem_base + (uint32_t)(stage * STAGE_BYTES + sub * SUB_BYTES);
+            const uint32_t b_hi = a_hi + NPROD * SUB_A;
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
-            const uint64_t da = ptx::make_kmajor_desc<128>(a_hi + kb * 32);
-            const uint64_t db = dx_mnmajor_desc(b_hi + kb * 1024, 4096, 512);
-            ptx::umma_tf32(d, da, db, idesc, (started >> acc) & 1u);
-            started |= 1u << acc;
-            if (X3) {
-              ptx::umma_tf32(d, da, dx_mnmajor_desc(b_hi + GM_STAGE_B + kb * 1024, 4096, 512), idesc, 1u);
-              ptx::umma_tf32(d, ptx::make_kmajor_desc<128>(a_hi + GM_STAGE_A + kb * 32), db, idesc, 1u);
+            for (int kb = 0; kb < KB; ++kb) {
+              const uint64_t da = ptx::make_kmajor_desc<A_ROW>(a_hi + kb * 32);
+              const uint64_t da_lo = ptx::make_kmajor_desc<A_ROW>(a_hi + SUB_A + kb * 32);
+              const uint64_t db = H ? dx_mnmajor_desc_h(b_hi + kb * p.h_kstep, p.h_lbo, p.h_sbo)
+                                    : dx_mnmajor_desc(b_hi + kb * 1024, 4096, 512);
+              const uint64_t db_lo = H ? dx_mnmajor_desc_h(b_hi + SUB_B + kb * p.h_kstep, p.h_lbo, p.h_sbo)
+                                       : dx_mnmajor_desc(b_hi + SUB_B + kb * 1024, 4096, 512);
+              ptx::umma<H>(d, da, db, idesc, (started >> acc) & 1u);
+              started |= 1u << acc;
+              if (X3) {
+                ptx::umma<H>(d, da, db_lo, idesc, 1u);
+                ptx::umma<H>(d, da_lo, db, idesc, 1u);
+              }
             }
           }
           ptx::umma_commit(empty + 8u * stage);
@@ -228,6 +284,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
     }
   } else {
     const int q = warp & 3;
+    const float inv = H ? __ldg(p.inv_scale) : 1.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
@@ -257,6 +314,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
               o.z = (o.z + __uint_as_float(r1[u + 2])) + (__uint_as_float(r2[u + 2]) + __uint_as_float(r3[u + 2]));
               o.w = (o.w + __uint_as_float(r1[u + 3])) + (__uint_as_float(r2[u + 3]) + __uint_as_float(r3[u + 3]));
             }
+            if (H) { o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv; }
             float4* dst = reinterpret_cast<float4*>(out + c0 + u);
             if (p.accumulate) {
               const float4 old = *dst;
@@ -279,12 +337,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
   }
 }
 
-template <bool X3>
+template <bool X3, bool H = false>
 static int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                        const TcGemmParams& p, int grid, size_t smem, cudaStream_t st) {
-  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<X3, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   profile_begin(GCB_PROF_BWD_DI, st);
-  k_tc_gemm<X3><<<grid, GM_THREADS, smem, st>>>(ah, al, bh, bl, p);
+  k_tc_gemm<X3, H><<<grid, GM_THREADS, smem, st>>>(ah, al, bh, bl, p);
   profile_end(GCB_PROF_BWD_DI, st);
   GCB_LAUNCH_OK();
   return GCB_OK;
@@ -296,6 +354,9 @@ constexpr int TN_STAGE_A = 128 * TN_KCH * 4;   // 8 KB: four 32-row atoms of M
 constexpr int TN_THREADS = (2 + GM_EPI_WARPS) * 32;
 
 struct TcGemmTnParams {
+  const float* inv_scale;           // fp16 route: undoes the operand scales
+  uint32_t h_lbo, h_sbo, h_kstep;   // fp16 MN-major descriptor fields (bytes)
+  int kch;           // contraction rows (source vertices) per stage: TN_KCH, or 32 with fp16 operands
   float* partial;    // [vsplit][m_pad][ld]
   int ld, n_cols;    // row length of the output (= columns of X)
   int m_pad, n_mtiles, n_ntiles, vsplit;
@@ -304,7 +365,9 @@ struct TcGemmTnParams {
   int ns, nacc;
 };
 
-template <bool X3>
+// H (fp16 operands): 64-column atoms (3-D boxes 64 x 32 rows x atoms, standard 128-byte swizzle), 32 contraction
+// rows per stage = two K = 16 steps.
+template <bool X3, bool H>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
              const __grid_constant__ CUtensorMap tmap_b_hi, const __grid_constant__ CUtensorMap tmap_b_lo,
@@ -313,7 +376,9 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  const int stage_b = p.bn * TN_KCH * 4;
+  constexpr int KCH = H ? 32 : TN_KCH;          // contraction rows per stage
+  constexpr int ATOM = H ? 64 : 32;             // operand columns per 128-byte atom row
+  const int stage_b = p.bn * TN_KCH * 4;        // (= bn * 32 rows * 2 bytes with fp16 operands)
   const int stage_bytes = NPROD * (TN_STAGE_A + stage_b);
   const uint32_t bar_base = smem_base + (uint32_t)(p.ns * stage_bytes);
   const uint32_t full = bar_base, empty = full + 8u * p.ns;
@@ -368,10 +433,10 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constan
           const uint32_t a_dst = smem_base + (uint32_t)(stage * stage_bytes);
           const uint32_t b_dst = a_dst + NPROD * TN_STAGE_A;
           ptx::mbar_arrive_expect_tx(full + 8u * stage, (uint32_t)stage_bytes);
-          ptx::tma_load_3d(a_dst, &tmap_a_hi, full + 8u * stage, 0, kc * TN_KCH, mt * 4);
-          if (X3) ptx::tma_load_3d(a_dst + TN_STAGE_A, &tmap_a_lo, full + 8u * stage, 0, kc * TN_KCH, mt * 4);
-          ptx::tma_load_3d(b_dst, &tmap_b_hi, full + 8u * stage, 0, kc * TN_KCH, nt * (p.bn / 32));
-          if (X3) ptx::tma_load_3d(b_dst + stage_b, &tmap_b_lo, full + 8u * stage, 0, kc * TN_KCH, nt * (p.bn / 32));
+          ptx::tma_load_3d(a_dst, &tmap_a_hi, full + 8u * stage, 0, kc * KCH, mt * (128 / ATOM));
+          if (X3) ptx::tma_load_3d(a_dst + TN_STAGE_A, &tmap_a_lo, full + 8u * stage, 0, kc * KCH, mt * (128 / ATOM));
+          ptx::tma_load_3d(b_dst, &tmap_b_hi, full + 8u * stage, 0, kc * KCH, nt * (p.bn / ATOM));
+          if (X3) ptx::tma_load_3d(b_dst + stage_b, &tmap_b_lo, full + 8u * stage, 0, kc * KCH, nt * (p.bn / ATOM));
           if (++stage == p.ns) { stage = 0; par ^= 1u; }
         }
       }
@@ -386,7 +451,7 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constan
         decode(tile, mt, vs, nt);
         k_range(vs, kb, ke);
         const int n_valid = min(p.bn, p.n_cols - nt * p.bn);
-        const uint32_t idesc = ptx::make_idesc_tf32(128, n_valid) | (1u << 15) | (1u << 16);   // A and B MN-major
+        const uint32_t idesc = ptx::make_idesc<H>(128, n_valid) | (1u << 15) | (1u << 16);   // A and B MN-major
         ptx::mbar_wait(tm_empty, (((uint32_t)it) & 1u) ^ 1u);
         ptx::tc_fence_after();
         uint32_t started = 0;   // bit a: accumulator a already holds a partial sum
@@ -398,14 +463,20 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constan
           const uint32_t a_hi = smem_base + (uint32_t)(stage * stage_bytes);
           const uint32_t b_hi = a_hi + NPROD * TN_STAGE_A;
 #pragma unroll
-          for (int k8 = 0; k8 < TN_KCH / 8; ++k8) {
-            const uint64_t da = dx_mnmajor_desc(a_hi + k8 * 1024, TN_KCH * 128, 512);
-            const uint64_t db = dx_mnmajor_desc(b_hi + k8 * 1024, TN_KCH * 128, 512);
-            ptx::umma_tf32(d, da, db, idesc, (started >> acc) & 1u);
+          for (int k8 = 0; k8 < 2; ++k8) {   // two K steps per stage (8 tf32 rows / 16 fp16 rows each)
+            const uint64_t da = H ? dx_mnmajor_desc_h(a_hi + k8 * p.h_kstep, p.h_lbo, p.h_sbo)
+                                  : dx_mnmajor_desc(a_hi + k8 * 1024, TN_KCH * 128, 512);
+            const uint64_t db = H ? dx_mnmajor_desc_h(b_hi + k8 * p.h_kstep, p.h_lbo, p.h_sbo)
+                                  : dx_mnmajor_desc(b_hi + k8 * 1024, TN_KCH * 128, 512);
+            ptx::umma<H>(d, da, db, idesc, (started >> acc) & 1u);
             started |= 1u << acc;
             if (X3) {
-              ptx::umma_tf32(d, da, dx_mnmajor_desc(b_hi + stage_b + k8 * 1024, TN_KCH * 128, 512), idesc, 1u);
-              ptx::umma_tf32(d, dx_mnmajor_desc(a_hi + TN_STAGE_A + k8 * 1024, TN_KCH * 128, 512), db, idesc, 1u);
+              const uint64_t db_lo = H ? dx_mnmajor_desc_h(b_hi + stage_b + k8 * p.h_kstep, p.h_lbo, p.h_sbo)
+                                       : dx_mnmajor_desc(b_hi + stage_b + k8 * 1024, TN_KCH * 128, 512);
+              const uint64_t da_lo = H ? dx_mnmajor_desc_h(a_hi + TN_STAGE_A + k8 * p.h_kstep, p.h_lbo, p.h_sbo)
+                                       : dx_mnmajor_desc(a_hi + TN_STAGE_A + k8 * 1024, TN_KCH * 128, 512);
+              ptx::umma<H>(d, da, db_lo, idesc, 1u);
+              ptx::umma<H>(d, da_lo, db, idesc, 1u);
             }
           }
           ptx::umma_commit(empty + 8u * stage);
@@ -416,6 +487,7 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constan
     }
   } else {
     const int q = warp & 3;
+    const float inv = H ? __ldg(p.inv_scale) : 1.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       int mt, vs, nt, kb, ke;
@@ -438,6 +510,10 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constan
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int u = 0; u < 16; ++u) o[u] += __uint_as_float(r[u]);
+        }
+        if (H) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) o[u] *= inv;
         }
 #pragma unroll
         for (int u = 0; u < 16; u += 4)
@@ -468,6 +544,71 @@ __global__ void k_split_tf32(const float4* __restrict__ src, int64_t n4, float4*
   if (lo) lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
 }
 
+// src[rows][cols] * (*scale) = hi + lo in fp16, rows of ld (>= cols, zero padded) halves
+__global__ void k_split_half(const float* __restrict__ src, int64_t rows, int cols, int ld,
+                             const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= rows * ld) return;
+  const int64_t r = i / ld;
+  const int c = (int)(i - r * ld);
+  const float v = c < cols ? __ldg(src + r * cols + c) : 0.f;
+  split_half(v, __ldg(scale), hi[i], lo[i]);
+}
+
+// longest CSR row (entries per source vertex), atomicMax'ed into *out
+__global__ void k_bw_max_row(const int32_t* __restrict__ row_ptr, int v_src, unsigned* __restrict__ out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned m = v < v_src ? (unsigned)(row_ptr[v + 1] - row_ptr[v]) : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// Power-of-two operand scales of the fp16 backward.  mx = {max|h|, max|w|, longest CSR row, max|Wcat|, max|X|};
+// |G| <= max|h| * max|w| * longest row - a loose bound only costs absolute resolution far below fp32's
+// (2^-25 of 2^14 / looseness).  scales = {sG, sW, sX, 1/(sG*sW), 1/(sG*sX)}, bound * s in [2^14, 2^15).
+__global__ void k_bw_scales(const unsigned* __restrict__ mx, int have_csr, float* __restrict__ scales) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  auto pow2_for = [](float bound) {
+    if (!(bound > 0.f) || !isfinite(bound)) return 0;
+    int e = 14 - ilogbf(bound);
+    return e < -60 ? -60 : (e > 60 ? 60 : e);
+  };
+  const float hm = __uint_as_float(mx[0]);
+  const float gm = have_csr ? fmaxf(hm * __uint_as_float(mx[1]) * (float)mx[2], hm) : hm;
+  const int eg = pow2_for(gm), ew = pow2_for(__uint_as_float(mx[3])), ex = pow2_for(__uint_as_float(mx[4]));
+  scales[0] = ldexpf(1.f, eg);
+  scales[1] = ldexpf(1.f, ew);
+  scales[2] = ldexpf(1.f, ex);
+  scales[3] = ldexpf(1.f, -(eg + ew));
+  scales[4] = ldexpf(1.f, -(eg + ex));
+}
+
+size_t tc_bwd_scales_bytes() { return 256; }
+
+// scratch: 8 unsigned maxima, then the 5 scales (the caller passes scratch + 8 words as `scales`)
+int tc_bwd_scales(const float* h, const float* w, const int32_t* csr_row_ptr, const float* w_eff, const float* w_self,
+                  const float* x, int v_out, int v_src, int R, int A, int F, int T, void* scratch, cudaStream_t st) {
+  unsigned* mx = (unsigned*)scratch;
+  GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 32, st));
+  int rc = tc_absmax(h, (int64_t)v_out * T, nullptr, 0, mx, st);
+  if (rc) return rc;
+  const bool have_csr = csr_row_ptr && w_eff;
+  if (have_csr) {
+    rc = tc_absmax(w, (int64_t)v_out * R * A * 3, nullptr, 0, mx + 1, st);
+    if (rc) return rc;
+    k_bw_max_row<<<(unsigned)ceil_div64(v_src, 256), 256, 0, st>>>(csr_row_ptr, v_src, mx + 2);
+    GCB_LAUNCH_OK();
+  }
+  rc = tc_absmax(w_eff, w_eff ? (int64_t)T * R * A * F : 0, w_self, (int64_t)T * F, mx + 3, st);
+  if (rc) return rc;
+  rc = tc_absmax(x, (int64_t)v_src * F, nullptr, 0, mx + 4, st);
+  if (rc) return rc;
+  k_bw_scales<<<1, 32, 0, st>>>(mx, have_csr ? 1 : 0, (float*)(mx + 8));
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
 // sums the vertex-split partials [vs][(s',t)][f] in a fixed order and scatters to d_w_eff[t][s'][f] / d_w_self[t][f]
 __global__ void k_tc_dwg_finish(const float* __restrict__ partial, int vsplit, int m_pad, int T, int RA, int F,
                                 int accumulate, float* __restrict__ d_w_eff, float* __restrict__ d_w_self) {
@@ -493,30 +634,33 @@ __global__ void k_tc_dwg_finish(const float* __restrict__ partial, int vsplit, i
   *dst = acc;
 }
 
-template <bool X3>
+template <bool X3, bool H = false>
 static int launch_gemm_tn(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                           const TcGemmTnParams& p, int grid, size_t smem, cudaStream_t st) {
-  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm_tn<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GCB_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm_tn<X3, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   profile_begin(GCB_PROF_BWD_DW, st);
-  k_tc_gemm_tn<X3><<<grid, TN_THREADS, smem, st>>>(ah, al, bh, bl, p);
+  k_tc_gemm_tn<X3, H><<<grid, TN_THREADS, smem, st>>>(ah, al, bh, bl, p);
   profile_end(GCB_PROF_BWD_DW, st);
   GCB_LAUNCH_OK();
   return GCB_OK;
 }
 
-TcGLayout tc_g_layout(int v_src, int R, int A, int F, int T, bool x3) {
+// (half: fp16 operands - 64-column atoms, 32 contraction rows per stage; the buffer sizes stay those of the
+// 3xTF32 route, which bound the fp16 ones)
+TcGLayout tc_g_layout(int v_src, int R, int A, int F, int T, bool x3, bool half) {
   TcGLayout L{};
   const int np = x3 ? 2 : 1;
+  const int atom = half ? 64 : 32;
   L.v_pad = (int)ceil_div64(v_src, 128) * 128;
   L.kg = (R * A + 1) * T;
   L.m_pad = (int)ceil_div64(L.kg, 128) * 128;
   L.n_ntiles = (int)ceil_div64(F, 256);
-  L.bn = (int)ceil_div64(ceil_div64(F, L.n_ntiles), 32) * 32;
+  L.bn = (int)ceil_div64(ceil_div64(F, L.n_ntiles), atom) * atom;
   L.n_ntiles = (int)ceil_div64(F, L.bn);
-  L.n_kch = L.v_pad / TN_KCH;
+  L.n_kch = L.v_pad / (half ? 32 : TN_KCH);
   const int nacc = 512 / L.bn >= 4 ? 4 : (512 / L.bn >= 2 ? 2 : 1);
   // vertex splits: chains of at most ~512 (3xTF32) / ~1024 accumulations per TMEM accumulator, then fill the SMs
-  const int64_t per_chunk = (int64_t)(TN_KCH / 8) * (x3 ? 3 : 1);
+  const int64_t per_chunk = (int64_t)2 * (x3 ? 3 : 1);   // two K steps per stage
   int s_min = (int)ceil_div64((int64_t)L.n_kch * per_chunk, (int64_t)nacc * (x3 ? 512 : 1024));
   if (s_min < 1) s_min = 1;
   if (s_min > L.n_kch) s_min = L.n_kch;
@@ -538,19 +682,27 @@ TcGLayout tc_g_layout(int v_src, int R, int A, int F, int T, bool x3) {
 
 int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int32_t* csr_row_ptr,
                const int32_t* csr_entries, int v_out, int v_src, int R, int A, int T, bool x3, float* g_hi,
-               float* g_lo, cudaStream_t st) {
+               float* g_lo, cudaStream_t st, const float* scales) {
   const int RA = R * A;
   const int kg = (RA + 1) * T;
   const int v_pad = (int)ceil_div64(v_src, 128) * 128;
   const size_t smem = (size_t)RA * T * sizeof(float);
   GCB_REQUIRE(smem <= 200 * 1024, GCB_EUNSUPPORTED, "tc_build_g: R*A*T too large for the G accumulator");
-  if (smem > 48 * 1024)
-    GCB_CUDA_OK(cudaFuncSetAttribute(k_bw_build_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool half = scales != nullptr;
+  const int kg_ld = (int)ceil_div64(kg, 64) * 64;
+  if (smem > 48 * 1024) {
+    GCB_CUDA_OK(cudaFuncSetAttribute(k_bw_build_g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GCB_CUDA_OK(cudaFuncSetAttribute(k_bw_build_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   int threads = (T + 31) / 32 * 32;
   if (threads < 64) threads = 64;
   profile_begin(GCB_PROF_BWD_CSR, st);
-  k_bw_build_g<<<v_pad, threads, smem, st>>>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, kg, g_hi,
-                                             x3 ? g_lo : nullptr);
+  if (half)
+    k_bw_build_g<true><<<v_pad, threads, smem, st>>>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, kg,
+                                                     kg_ld, scales, g_hi, g_lo);
+  else
+    k_bw_build_g<false><<<v_pad, threads, smem, st>>>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T,
+                                                      kg, kg, nullptr, g_hi, x3 ? g_lo : nullptr);
   profile_end(GCB_PROF_BWD_CSR, st);
   GCB_LAUNCH_OK();
   return GCB_OK;
@@ -558,21 +710,45 @@ int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int
 
 // d_x[v_src, F] (+)= G x Wcat, the weight tensor maps over Wcat [T x (R*A*F + F)] (hi / lo)
 int tc_dx_from_g(const float* g_hi, const float* g_lo, const float* wcat_hi, const float* wcat_lo, int v_src, int R,
-                 int A, int F, int T, bool x3, int accumulate, float* d_x, cudaStream_t st) {
+                 int A, int F, int T, bool x3, int accumulate, float* d_x, cudaStream_t st, const float* scales) {
   GCB_REQUIRE((uintptr_t)d_x % 16 == 0 && F % 4 == 0, GCB_EINVAL, "tc_dx_from_g: d_x must be 16-byte aligned");
   const int RA = R * A, KRA = RA * F, kcat = KRA + F;
   const int kg = (RA + 1) * T;
   const int v_pad = (int)ceil_div64(v_src, 128) * 128;
+  const bool half = scales != nullptr;
   CUtensorMap ah, al, bh, bl;
-  int rc = tc_make_tmap_2d(&ah, g_hi, (uint64_t)kg, (uint64_t)v_pad, (uint64_t)kg * 4, 32, 128);
-  if (rc) return rc;
-  rc = tc_make_tmap_2d(&al, x3 ? g_lo : g_hi, (uint64_t)kg, (uint64_t)v_pad, (uint64_t)kg * 4, 32, 128);
-  if (rc) return rc;
-  rc = tc_make_tmap_2d(&bh, wcat_hi, (uint64_t)kcat, (uint64_t)T, (uint64_t)kcat * 4, 32, 32, true);
-  if (rc) return rc;
-  rc = tc_make_tmap_2d(&bl, x3 ? wcat_lo : wcat_hi, (uint64_t)kcat, (uint64_t)T, (uint64_t)kcat * 4, 32, 32, true);
-  if (rc) return rc;
+  int rc;
+  if (half) {
+    const uint64_t kg_ld = (uint64_t)ceil_div64(kg, 64) * 64;
+    rc = tc_make_tmap_2d_h(&ah, (const __half*)g_hi, (uint64_t)kg, (uint64_t)v_pad, kg_ld * 2, 32, 128);
+    if (rc) return rc;
+    rc = tc_make_tmap_2d_h(&al, (const __half*)g_lo, (uint64_t)kg, (uint64_t)v_pad, kg_ld * 2, 32, 128);
+    if (rc) return rc;
+    // B: 32 template rows x 64 feature columns of Wcat per box = one MN-major atom column (4 KB)
+    rc = tc_make_tmap_2d_h(&bh, (const __half*)wcat_hi, (uint64_t)kcat, (uint64_t)T, (uint64_t)kcat * 2, 64, 32);
+    if (rc) return rc;
+    rc = tc_make_tmap_2d_h(&bl, (const __half*)wcat_lo, (uint64_t)kcat, (uint64_t)T, (uint64_t)kcat * 2, 64, 32);
+    if (rc) return rc;
+  } else {
+    rc = tc_make_tmap_2d(&ah, g_hi, (uint64_t)kg, (uint64_t)v_pad, (uint64_t)kg * 4, 32, 128);
+    if (rc) return rc;
+    rc = tc_make_tmap_2d(&al, x3 ? g_lo : g_hi, (uint64_t)kg, (uint64_t)v_pad, (uint64_t)kg * 4, 32, 128);
+    if (rc) return rc;
+    rc = tc_make_tmap_2d(&bh, wcat_hi, (uint64_t)kcat, (uint64_t)T, (uint64_t)kcat * 4, 32, 32, true);
+    if (rc) return rc;
+    rc = tc_make_tmap_2d(&bl, x3 ? wcat_lo : wcat_hi, (uint64_t)kcat, (uint64_t)T, (uint64_t)kcat * 4, 32, 32, true);
+    if (rc) return rc;
+  }
   TcGemmParams p;
+  p.inv_scale = half ? scales + 3 : nullptr;
+  {
+    static const int lbo_env = getenv("GCB_H_LBO") ? atoi(getenv("GCB_H_LBO")) : 0;   // experiments
+    static const int sbo_env = getenv("GCB_H_SBO") ? atoi(getenv("GCB_H_SBO")) : 0;
+    static const int ks_env = getenv("GCB_H_KSTEP") ? atoi(getenv("GCB_H_KSTEP")) : 0;
+    p.h_lbo = lbo_env > 0 ? lbo_env : 4096;   // between 64-column atoms (32 rows x 128 bytes)
+    p.h_sbo = sbo_env > 0 ? sbo_env : 1024;   // between 8-row groups
+    p.h_kstep = ks_env > 0 ? ks_env : 2048;   // 16 rows
+  }
   p.out = d_x; p.ld_out = F; p.rows_valid = v_src; p.cols_valid = F; p.accumulate = accumulate;
   p.n_mtiles = v_pad / 128;
   p.n_ntiles = (int)ceil_div64(F, GM_BN);
@@ -586,35 +762,63 @@ int tc_dx_from_g(const float* g_hi, const float* g_lo, const float* wcat_hi, con
   const size_t smem = 2048 + (size_t)ns * stage_bytes;
   const int n_tiles = p.n_mtiles * p.n_ntiles;
   const int grid = n_tiles < 148 ? n_tiles : 148;
+  if (half) return launch_gemm<true, true>(ah, al, bh, bl, p, grid, smem, st);
   return x3 ? launch_gemm<true>(ah, al, bh, bl, p, grid, smem, st) : launch_gemm<false>(ah, al, bh, bl, p, grid, smem, st);
 }
 
 // d_w_eff[T,R,A,F], d_w_self[T,F] (+)= G^T x X
 int tc_dw_from_g(const float* g_hi, const float* g_lo, const float* x, int v_src, int R, int A, int F, int T,
                  bool x3, int accumulate, float* d_w_eff, float* d_w_self, float* x_hi, float* x_lo, float* partial,
-                 cudaStream_t st) {
+                 cudaStream_t st, const float* scales) {
+  const bool half = scales != nullptr;
   GCB_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)d_w_self % 16 == 0 && (uintptr_t)d_w_eff % 16 == 0 && F % 32 == 0 &&
                   T % 32 == 0,
               GCB_EINVAL, "tc_dw_from_g: operands must be 16-byte aligned, F and T multiples of 32");
-  const TcGLayout L = tc_g_layout(v_src, R, A, F, T, x3);
-  {
+  const TcGLayout L = tc_g_layout(v_src, R, A, F, T, x3, half);
+  CUtensorMap ah, al, bh, bl;
+  int rc;
+  if (half) {
+    const int x_ld = (int)ceil_div64(F, 64) * 64, kg_ld = (int)ceil_div64(L.kg, 64) * 64;
+    __half* xh = (__half*)x_hi;
+    __half* xl = xh + (size_t)v_src * x_ld;
+    const int64_t n = (int64_t)v_src * x_ld;
+    k_split_half<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(x, v_src, F, x_ld, scales + 2, xh, xl);
+    GCB_LAUNCH_OK();
+    rc = tc_make_tmap_mn_h(&ah, (const __half*)g_hi, (uint64_t)L.v_pad, (uint64_t)kg_ld, (uint64_t)kg_ld * 2, 32, 2);
+    if (rc) return rc;
+    rc = tc_make_tmap_mn_h(&al, (const __half*)g_lo, (uint64_t)L.v_pad, (uint64_t)kg_ld, (uint64_t)kg_ld * 2, 32, 2);
+    if (rc) return rc;
+    rc = tc_make_tmap_mn_h(&bh, xh, (uint64_t)v_src, (uint64_t)x_ld, (uint64_t)x_ld * 2, 32, (uint32_t)(L.bn / 64));
+    if (rc) return rc;
+    rc = tc_make_tmap_mn_h(&bl, xl, (uint64_t)v_src, (uint64_t)x_ld, (uint64_t)x_ld * 2, 32, (uint32_t)(L.bn / 64));
+    if (rc) return rc;
+  } else {
     const int64_t n4 = (int64_t)v_src * F / 4;
     k_split_tf32<<<(unsigned)ceil_div64(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), n4,
                                                                 reinterpret_cast<float4*>(x_hi),
                                                                 x3 ? reinterpret_cast<float4*>(x_lo) : nullptr);
     GCB_LAUNCH_OK();
+    rc = tc_make_tmap_mn(&ah, g_hi, (uint64_t)L.v_pad, (uint64_t)L.kg, (uint64_t)L.kg * 4, TN_KCH, 4);
+    if (rc) return rc;
+    rc = tc_make_tmap_mn(&al, x3 ? g_lo : g_hi, (uint64_t)L.v_pad, (uint64_t)L.kg, (uint64_t)L.kg * 4, TN_KCH, 4);
+    if (rc) return rc;
+    rc = tc_make_tmap_mn(&bh, x_hi, (uint64_t)v_src, (uint64_t)F, (uint64_t)F * 4, TN_KCH, (uint32_t)(L.bn / 32));
+    if (rc) return rc;
+    rc = tc_make_tmap_mn(&bl, x3 ? x_lo : x_hi, (uint64_t)v_src, (uint64_t)F, (uint64_t)F * 4, TN_KCH,
+                         (uint32_t)(L.bn / 32));
+    if (rc) return rc;
   }
-  CUtensorMap ah, al, bh, bl;
-  int rc = tc_make_tmap_mn(&ah, g_hi, (uint64_t)L.v_pad, (uint64_t)L.kg, (uint64_t)L.kg * 4, TN_KCH, 4);
-  if (rc) return rc;
-  rc = tc_make_tmap_mn(&al, x3 ? g_lo : g_hi, (uint64_t)L.v_pad, (uint64_t)L.kg, (uint64_t)L.kg * 4, TN_KCH, 4);
-  if (rc) return rc;
-  rc = tc_make_tmap_mn(&bh, x_hi, (uint64_t)v_src, (uint64_t)F, (uint64_t)F * 4, TN_KCH, (uint32_t)(L.bn / 32));
-  if (rc) return rc;
-  rc = tc_make_tmap_mn(&bl, x3 ? x_lo : x_hi, (uint64_t)v_src, (uint64_t)F, (uint64_t)F * 4, TN_KCH,
-                       (uint32_t)(L.bn / 32));
-  if (rc) return rc;
   TcGemmTnParams p;
+  p.inv_scale = half ? scales + 4 : nullptr;
+  p.kch = half ? 32 : TN_KCH;
+  {
+    static const int lbo_env = getenv("GCB_H_LBO") ? atoi(getenv("GCB_H_LBO")) : 0;   // experiments
+    static const int sbo_env = getenv("GCB_H_SBO") ? atoi(getenv("GCB_H_SBO")) : 0;
+    static const int ks_env = getenv("GCB_H_KSTEP") ? atoi(getenv("GCB_H_KSTEP")) : 0;
+    p.h_lbo = lbo_env > 0 ? lbo_env : 4096;
+    p.h_sbo = sbo_env > 0 ? sbo_env : 1024;
+    p.h_kstep = ks_env > 0 ? ks_env : 2048;
+  }
   p.partial = partial; p.ld = F; p.n_cols = F;
   p.m_pad = L.m_pad; p.n_mtiles = L.m_pad / 128; p.n_ntiles = L.n_ntiles; p.vsplit = L.vsplit;
   p.bn = L.bn; p.n_kch = L.n_kch;
@@ -627,7 +831,8 @@ int tc_dw_from_g(const float* g_hi, const float* g_lo, const float* x, int v_src
   const size_t smem = 2048 + (size_t)ns * stage_bytes;
   const int n_tiles = p.n_mtiles * p.vsplit * p.n_ntiles;
   const int grid = n_tiles < 148 ? n_tiles : 148;
-  rc = x3 ? launch_gemm_tn<true>(ah, al, bh, bl, p, grid, smem, st) : launch_gemm_tn<false>(ah, al, bh, bl, p, grid, smem, st);
+  if (half) rc = launch_gemm_tn<true, true>(ah, al, bh, bl, p, grid, smem, st);
+  else rc = x3 ? launch_gemm_tn<true>(ah, al, bh, bl, p, grid, smem, st) : launch_gemm_tn<false>(ah, al, bh, bl, p, grid, smem, st);
   if (rc) return rc;
   const int64_t n_out = (int64_t)T * (R * A + 1) * (F / 4);
   k_tc_dwg_finish<<<(unsigned)ceil_div64(n_out, 256), 256, 0, st>>>(partial, L.vsplit, L.m_pad, T, R * A, F, accumulate,

@@ -117,6 +117,7 @@ struct TcFwdParams {
   int bar_bytes;        // size of the mbarrier block in shared memory
   int tab_bytes;        // size of one rotation group's ring schedules (k_tc_build_tabs)
   const uint8_t* tabs;  // [n_groups][tab_bytes]
+  const int* splits;    // [ksplit + 1] first super-step of every K split (tc_split_table)
   int drain_cw;         // accumulator columns staged per bulk store in the drain (0: registers -> global directly)
   long long* trace;     // GCB_TC_TRACE (investigation builds): clock64 stamps of CTA (1,0,0), [role][tile][8]
   int debug;            // GCB_TC_DEBUG bits (timing experiments only): 1 = all gathers read row 0, 2 = no MMAs
@@ -381,7 +382,7 @@ __global__ void k_tc_scales(const unsigned* __restrict__ mx, float* __restrict__
   scales[2] = ldexpf(1.f, -(ea + eb));
 }
 
-// fp16 variant of k_tc_wcat: Wcat * scales[1] = hi + lo (both fp16)
+// fp16 variant of k_tc_wcat: Wcat * (*scales) = hi + lo (both fp16)
 __global__ void k_tc_wcat_h(const float* __restrict__ w_eff, const float* __restrict__ w_self, int T, int KRA,
                             int F, const float* __restrict__ scales, __half* __restrict__ hi,
                             __half* __restrict__ lo) {
@@ -389,7 +390,7 @@ __global__ void k_tc_wcat_h(const float* __restrict__ w_eff, const float* __rest
   int kcat = KRA + F;
   if (e >= (int64_t)T * kcat) return;
   int t = (int)(e / kcat), k = (int)(e - (int64_t)t * kcat);
-  float v = (k < KRA ? w_eff[(size_t)t * KRA + k] : w_self[(size_t)t * F + (k - KRA)]) * __ldg(scales + 1);
+  float v = (k < KRA ? w_eff[(size_t)t * KRA + k] : w_self[(size_t)t * F + (k - KRA)]) * __ldg(scales);
   const __half h = __float2half_rn(v);
   hi[e] = h;
   lo[e] = __float2half_rn(v - __half2float(h));
@@ -441,14 +442,23 @@ __device__ __forceinline__ void producer_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCER_WARPS * 32) : "memory");
 }
 
-// First super-step of K split `sk`: splits are balanced by TILES (a radial super-step has A tiles, a centre
-// super-step one), cut at super-step boundaries.  n_nc / n_c = radial / centre super-steps.
-__host__ __device__ __forceinline__ int tc_split_begin(int n_nc, int n_c, int A, int sk, int ksplit) {
+// K-split boundaries: splits are balanced by TILES (a radial super-step has A tiles, a centre super-step one),
+// cut at super-step boundaries, every split at least one super-step long (an empty split would drain an
+// accumulator nobody wrote).  n_nc / n_c = radial / centre super-steps; out[0..ksplit], ksplit <= n_nc + n_c.
+__device__ inline void tc_split_table(int n_nc, int n_c, int A, int ksplit, int* out) {
   const long long total = (long long)n_nc * A + n_c;
-  const long long t = (total * sk + ksplit / 2) / ksplit;   // target tile count before the split
-  if (sk >= ksplit) return n_nc + n_c;
-  if (t >= (long long)n_nc * A) return n_nc + (int)(t - (long long)n_nc * A);
-  return (int)((t + A / 2) / A);
+  const int n_ss = n_nc + n_c;
+  int b = 0;
+  out[0] = 0;
+  for (int j = 1; j < ksplit; ++j) {
+    const long long t = (total * j + ksplit / 2) / ksplit;   // target tile count before split j
+    int cand = t >= (long long)n_nc * A ? n_nc + (int)(t - (long long)n_nc * A) : (int)((t + A / 2) / A);
+    b = cand > b + 1 ? cand : b + 1;
+    const int hi = n_ss - (ksplit - j);
+    b = b < hi ? b : hi;
+    out[j] = b;
+  }
+  out[ksplit] = n_ss;
 }
 
 // position in the CTA's tile sequence: super-step ss = (radial ring xr, feature chunk fc) or the
@@ -711,9 +721,10 @@ __device__ __forceinline__ void tc_mma_role(const TcFwdParams& p, const TcMmaCtx
 //   occ_tab [parity][phase][entry] u8: 1 + last step at which the previous super-step still reads the position
 //   last 16 bytes: n_ent = entries that are read at all
 __global__ void k_tc_build_tabs(const __grid_constant__ TcFwdParams p, int pairs, int tab_bytes,
-                                uint8_t* __restrict__ tabs) {
+                                uint8_t* __restrict__ tabs, int* __restrict__ splits) {
   extern __shared__ __align__(16) uint8_t tab_smem[];
   const int tid = threadIdx.x, nthr = blockDim.x, grp = blockIdx.x;
+  if (grp == 0 && tid == nthr - 1) tc_split_table(p.R * p.nfc, p.nfc, p.A, p.ksplit, splits);
   const int NP = p.ring.n_pos, AA = p.A * p.A;
   uint32_t* need_tab = reinterpret_cast<uint32_t*>(tab_smem);
   uint32_t* retire_tab = need_tab + AA;
@@ -886,8 +897,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   const int g_cnt = min(p.g, p.n_rot - rot0);
   const int RA = p.R * p.A;
   const int n_ss = (p.R + 1) * p.nfc;  // super-steps: (x, f-chunk) for x < R, then the centre slab
-  const int ss_begin = tc_split_begin(p.R * p.nfc, p.nfc, p.A, sk, p.ksplit);
-  const int ss_end = tc_split_begin(p.R * p.nfc, p.nfc, p.A, sk + 1, p.ksplit);
+  const int ss_begin = __ldg(p.splits + sk), ss_end = __ldg(p.splits + sk + 1);   // tc_split_table
   const int n_units = (g_cnt + p.ring.m - 1) / p.ring.m;   // MMA units: groups of <= m merged rotations
   // The angular visiting order is common to the cluster pair (they share the gathered tiles): it is
   // anchored at the first rotation of the pair's first CTA.  rel0 = this CTA's first offset
@@ -1366,20 +1376,57 @@ static int make_weight_tmap(CUtensorMap* out, const float* base, int T, int kcat
                          (uint32_t)n_t);
 }
 
-// fp16 weights [T][kcat]: box = 2 * kc halves (kc 4-byte units) x n_t rows, swizzle span = the box row
-static int make_weight_tmap_h(CUtensorMap* out, const __half* base, int T, int kcat, int kc, int n_t) {
+int tc_make_tmap_2d_h(CUtensorMap* out, const __half* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
   PFN_encodeTiled enc = get_encode_fn();
   GCB_REQUIRE(enc, GCB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {(cuuint64_t)kcat, (cuuint64_t)T};
-  cuuint64_t strides[1] = {(cuuint64_t)kcat * sizeof(__half)};
-  cuuint32_t box[2] = {(cuuint32_t)(2 * kc), (cuuint32_t)n_t};
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)row_stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapSwizzle sw = kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                         : (kc == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUtensorMapSwizzle sw = box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                : (box_inner == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GCB_REQUIRE(r == CUDA_SUCCESS, GCB_ECUDA, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d", (int)r);
+  return GCB_OK;
+}
+
+int tc_make_tmap_mn_h(CUtensorMap* out, const __half* base, uint64_t rows, uint64_t cols_ld, uint64_t row_stride_bytes,
+                      uint32_t box_rows, uint32_t box_atoms) {
+  PFN_encodeTiled enc = get_encode_fn();
+  GCB_REQUIRE(enc, GCB_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  GCB_REQUIRE(cols_ld % 64 == 0, GCB_EINVAL, "tc_make_tmap_mn_h: the row length must be a multiple of 64");
+  cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(cols_ld / 64)};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride_bytes, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)box_atoms};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GCB_REQUIRE(r == CUDA_SUCCESS, GCB_ECUDA, "cuTensorMapEncodeTiled (fp16, MN-major) failed with CUresult %d", (int)r);
+  return GCB_OK;
+}
+
+// fp16 weights [T][kcat]: box = 2 * kc halves (kc 4-byte units) x n_t rows, swizzle span = the box row
+static int make_weight_tmap_h(CUtensorMap* out, const __half* base, int T, int kcat, int kc, int n_t) {
+  return tc_make_tmap_2d_h(out, base, (uint64_t)kcat, (uint64_t)T, (uint64_t)kcat * sizeof(__half), (uint32_t)(2 * kc),
+                           (uint32_t)n_t);
+}
+
+int tc_build_wcat_h(const float* w_eff, const float* w_self, int T, int R, int A, int F, const float* scale,
+                    __half* hi, __half* lo, cudaStream_t st) {
+  const int KRA = R * A * F;
+  const int64_t wt = (int64_t)T * (KRA + F);
+  k_tc_wcat_h<<<(unsigned)ceil_div64(wt, 256), 256, 0, st>>>(w_eff, w_self, T, KRA, F, scale, hi, lo);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+int tc_absmax(const float* a, int64_t na, const float* b, int64_t nb, unsigned* out, cudaStream_t st) {
+  k_tc_absmax<<<148 * 2, 256, 0, st>>>(a, na, b, nb, out);
+  GCB_LAUNCH_OK();
   return GCB_OK;
 }
 
@@ -1431,6 +1478,7 @@ bool tc_half_supported(int R, int A, int F, int T, int n_rot) {
 }
 
 constexpr size_t TC_TABS_BYTES = (size_t)GCB_MAX_ROT * 16384;   // ring schedules of every rotation group
+constexpr size_t TC_SPLITS_BYTES = 16384;   // K-split boundaries
 constexpr size_t TC_SCALES_BYTES = 256;   // {max|X|, max sum|w|, max|Wcat|} as bits, then the three scales
 
 size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, int precision) {
@@ -1444,7 +1492,7 @@ size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, 
     if (s > ksplit) ksplit = s;
   }
   return tc_recs_bytes(v_out, R, A) + (x3 ? 2 : 1) * tc_wcat_bytes(R, A, F, T) +
-         tc_partial_bytes(v_out, n_rot, T, ksplit) + TC_SCALES_BYTES + TC_TABS_BYTES + 1024;
+         tc_partial_bytes(v_out, n_rot, T, ksplit) + TC_SCALES_BYTES + TC_TABS_BYTES + TC_SPLITS_BYTES + 1024;
 }
 
 template <int KC, bool X3, bool H, int CL, bool KEEP>
@@ -1547,18 +1595,16 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   CUtensorMap mh, ml;
   if (half) {
     GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 16, st));
-    k_tc_absmax<<<148 * 2, 256, 0, st>>>(x, (int64_t)v_src * F, nullptr, 0, mx);
-    GCB_LAUNCH_OK();
-    k_tc_absmax<<<148 * 2, 256, 0, st>>>(w_eff, (int64_t)T * RA * F, w_self, (int64_t)T * F, mx + 2);
-    GCB_LAUNCH_OK();
+    rc = tc_absmax(x, (int64_t)v_src * F, nullptr, 0, mx, st);
+    if (rc) return rc;
+    rc = tc_absmax(w_eff, (int64_t)T * RA * F, w_self, (int64_t)T * F, mx + 2, st);
+    if (rc) return rc;
     rc = tc_pack_recs_max(idx, w, v_out, R, A, recs, mx + 1, st);
     if (rc) return rc;
     k_tc_scales<<<1, 32, 0, st>>>(mx, scales);
     GCB_LAUNCH_OK();
-    const int64_t wt = (int64_t)T * kcat;
-    k_tc_wcat_h<<<(unsigned)ceil_div64(wt, 256), 256, 0, st>>>(w_eff, w_self, T, KRA, F, scales, (__half*)wc_hi,
-                                                               (__half*)wc_lo);
-    GCB_LAUNCH_OK();
+    rc = tc_build_wcat_h(w_eff, w_self, T, R, A, F, scales + 1, (__half*)wc_hi, (__half*)wc_lo, st);
+    if (rc) return rc;
     rc = make_weight_tmap_h(&mh, (const __half*)wc_hi, T, kcat, cfg.kc, cfg.n_t);
     if (rc) return rc;
     rc = make_weight_tmap_h(&ml, (const __half*)wc_lo, T, kcat, cfg.kc, cfg.n_t);
@@ -1584,6 +1630,8 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   p.bar_bytes = (int)tc_bar_bytes(cfg.ring.n_pos, cfg.ring.n_pos + cfg.ring.shift);
   p.tab_bytes = (int)tc_tab_bytes(A, cfg.ring.n_pos);
   p.tabs = (const uint8_t*)mx + TC_SCALES_BYTES;
+  p.splits = (const int*)(p.tabs + TC_TABS_BYTES);
+  GCB_REQUIRE((size_t)(ksplit + 1) * sizeof(int) <= TC_SPLITS_BYTES, GCB_EUNSUPPORTED, "tc_conv_fwd: too many K splits");
   GCB_REQUIRE((size_t)cfg.n_groups * p.tab_bytes <= TC_TABS_BYTES, GCB_EUNSUPPORTED, "tc_conv_fwd: ring schedules exceed their workspace");
   {
     // drain staging: 8 warps x 32 rows x (cw * 4 + 16) bytes inside the weight ring
@@ -1607,7 +1655,8 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   p.rot = rot;
   {
     const bool pairs = tc_use_pairs() && cfg.n_groups % 2 == 0 && cfg.kc >= 16;
-    k_tc_build_tabs<<<cfg.n_groups, 128, p.tab_bytes, st>>>(p, pairs ? 1 : 0, p.tab_bytes, (uint8_t*)p.tabs);
+    k_tc_build_tabs<<<cfg.n_groups, 128, p.tab_bytes, st>>>(p, pairs ? 1 : 0, p.tab_bytes, (uint8_t*)p.tabs,
+                                                             (int*)p.splits);
     GCB_LAUNCH_OK();
   }
   dim3 grid((unsigned)m_tiles, (unsigned)cfg.n_groups, (unsigned)((T / cfg.n_t) * ksplit));

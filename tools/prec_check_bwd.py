@@ -1,4 +1,4 @@
-"""Backward (3xTF32 tensor-core GEMMs) error at the FAUST shape behind an exact forward (CUDA-core fp32), so that
+"""Backward (tensor-core GEMMs, GCB_BWD_PREC = fp32 | tf32x3 | f16x3) error at the FAUST shape behind an exact forward (CUDA-core fp32), so that
 both sides select the same rotations and ReLU masks; compared with autograd over the CPU oracle."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,7 +16,7 @@ for kind in sys.argv[1:] or ["shot", "randn"]:
     gz = torch.randn((v, t), generator=torch.Generator().manual_seed(2))
     ref = O.conv_amp_forward_backward(signal.double(), bary, wn.double(), ws.double(), b.double(), prior.double(), gz.double(), "relu", 1)
     layer = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.028, precision="ffma")
-    layer.backward_precision = "tf32x3"
+    layer.backward_precision = os.environ.get("GCB_BWD_PREC", "fp32")
     layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b}); layer = layer.cuda()
     x = signal.cuda().requires_grad_(True)
     z = AngularMaxPooling()(layer([x, bary.cuda()])); z.backward(gz.cuda())
