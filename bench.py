@@ -217,7 +217,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from geoconv_b200 import _native
+    from geoconv_b200 import _native, ops
     from geoconv_b200.distributed import allreduce_gradients
     from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
     from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
@@ -540,7 +540,12 @@ def run_ours(args):
     e2e_value = world * v * args.steps / (e2e_ms * 1e-3)
     fwd_flops, bwd_flops = algorithmic_flops(cfg)
     peaks = load_peaks()
-    tf32_peak = peaks["bf16_tflops"] / 2.0
+    # fp32 mode contracts fp16 hi/lo operand splits with kind::f16 MMAs (same rate as bf16: the MEASURED peak),
+    # three per product; tf32 mode (and GEOCONV_B200_FP32_VIA=tf32x3) runs kind::tf32 at half that rate (derived)
+    fp32_via_f16 = args.precision == "f16x3" or (args.precision == "fp32" and ops.FP32_VIA_F16)
+    three_products = args.precision in ("fp32", "f16x3", "tf32x3")
+    tensor_peak = peaks["bf16_tflops"] if fp32_via_f16 else peaks["bf16_tflops"] / 2.0
+    ceiling = (1.0 / 3.0) if three_products else 1.0
     k_ms, k_cnt = prof["fwd_conv"]
     achieved = (fwd_flops * k_cnt / (k_ms * 1e-3)) / 1e12 if k_ms > 0 and k_cnt else None
     traffic, traffic_src = None, None
@@ -553,14 +558,19 @@ def run_ours(args):
             traffic_src = rec["source"]
     roofline = {
         "bound": "tensor", "kernel": "k_tc_conv (forward gather+tcgen05 contraction)",
-        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-        "frac": (achieved / tf32_peak) if achieved else None, "traffic": traffic,
+        "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+        "frac": (achieved / tensor_peak) if achieved else None,
+        "ceiling_frac": ceiling, "frac_of_ceiling": (achieved / (tensor_peak * ceiling)) if achieved else None,
+        "traffic": traffic,
         "traffic_unit": "bytes of DRAM read+write per launch (ncu)", "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": 4 * (v * f + 6 * v * r * a + t * (r * a * f + f) + t + v * t) + 4 * v,
-        "peak_source": f"{peaks['source']} bf16_tflops/2 (TF32 dense peak is derived, not measured)",
+        "peak_source": (f"{peaks['source']} bf16_tflops (kind::f16 issues at the bf16 rate)" if fp32_via_f16 else
+                        f"{peaks['source']} bf16_tflops/2 (TF32 dense peak is derived, not measured)"),
         "algorithmic_flops_per_launch": fwd_flops, "kernel_ms_avg": (k_ms / k_cnt) if k_cnt else None,
-        "note": ("fp32 mode runs 3 tf32 MMAs per product (3xTF32): its ceiling against this peak is 1/3"
-                 if args.precision == "fp32" else "single-pass tf32"),
+        "note": (("fp32-faithful mode: operands split into fp16 hi + lo (power-of-two scaled), 3 kind::f16 MMAs per "
+                  "product, so algorithmic FLOP/s cannot exceed 1/3 of this peak" if fp32_via_f16 else
+                  "fp32-faithful mode: 3 tf32 MMAs per product (3xTF32): its ceiling against this peak is 1/3")
+                 if three_products else "single-pass tf32"),
     }
 
     # CPU baseline: the oracle on this host's cores, bounded sample (1 warm-up + 2 timed meshes)
@@ -581,7 +591,7 @@ def run_ours(args):
         "metric": "vertices/sec, ConvGeodesic+AMP fwd+bwd", "value": value, "unit": "vertices/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": "S1: V=6890 F=544 T=96 R5xA8 delta1 relu, ConvGeodesic+AMP fwd+bwd, 1 mesh/step/GPU",
                    "precision": args.precision, "launch": launch_mode, "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)",
                    "parallelism": f"dp{world} (one mesh per rank per step" + (", NCCL all-reduce of weight gradients)" if world > 1 else ")")},
@@ -627,7 +637,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "ffma"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "ffma", "tf32x3", "f16x3"])
     ap.add_argument("--graph", type=int, default=1, help="1: replay the resident step from a CUDA graph (default)")
     ap.add_argument("--e2e-pipeline", type=int, default=1,
                     help="1: overlap the H2D of step n+1 with the compute of step n in the host-to-host leg (default)")

@@ -61,8 +61,10 @@ class ConvIntrinsic(ABC, nn.Module):
 
     Extra keyword (not in the reference)
     ----------
-    precision: "fp32" (default; fp32-faithful, <=1e-5 normalised error), "tf32" (<=2e-3) or "ffma"
-        (force the CUDA-core kernels).  Default can be overridden with GEOCONV_B200_PRECISION.
+    precision: "fp32" (default; fp32-faithful, <=1e-5 normalised error: tensor cores on fp16 hi/lo operand
+        splits - "f16x3" - where the shape allows, else on tf32 splits - "tf32x3" - else CUDA cores),
+        "tf32" (<=2e-3) or "ffma" (force the CUDA-core kernels); "f16x3" / "tf32x3" select a split explicitly.
+        Default can be overridden with GEOCONV_B200_PRECISION.
     """
 
     def __init__(self,

@@ -1,4 +1,4 @@
-"""tcgen05 forward kernel (TF32 and 3xTF32) against the CPU oracle over the tilings it selects:
+"""tcgen05 forward kernel (TF32, 3xTF32 and the fp16-split 3xFP16) against the CPU oracle over the tilings it selects:
 swizzle width KC in {32,16,8}, one or several rotation groups, template chunks, ragged vertex
 counts, rotation_delta > 1."""
 import pytest
@@ -26,7 +26,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "-".join(map(str, s)))
 def test_tc_forward_matches_oracle(shape, precision):
     kind, v, f, r, a, t, delta, act = shape
@@ -60,7 +60,7 @@ def test_tc_matches_ffma_on_device_and_is_deterministic():
     signal = O.make_signal(v, f, seed=2, kind="shot").to(DEV)
     bary = O.make_bary(v, r, a, seed=2).to(DEV)
     outs = {}
-    for precision in ("ffma", "tf32x3", "tf32"):
+    for precision in ("ffma", "tf32x3", "f16x3", "tf32"):
         layer = ConvDirac(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.03,
                           precision=precision)
         layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
@@ -69,6 +69,7 @@ def test_tc_matches_ffma_on_device_and_is_deterministic():
         again = layer([signal, bary]).detach()
         assert torch.equal(outs[precision], again)
     assert nerr(outs["tf32x3"], outs["ffma"]) < TOL_FP32
+    assert nerr(outs["f16x3"], outs["ffma"]) < TOL_FP32
     assert nerr(outs["tf32"], outs["ffma"]) < TOL_TF32
 
 
@@ -81,7 +82,7 @@ BWD_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("shape", BWD_SHAPES, ids=lambda s: "-".join(map(str, s)))
 def test_tc_backward_matches_oracle(shape, precision):
     """AMP-sparse backward through the tcgen05 dW / dI kernels + CSR gather-reduce vs autograd over
@@ -112,3 +113,68 @@ def test_tc_backward_matches_oracle(shape, precision):
             "d_w_self": nerr(layer._template_self_weights.grad, ref["d_w_self"]),
             "d_bias": nerr(layer._bias.grad, ref["d_bias"])}
     assert all(e < tol for e in errs.values()), errs
+
+
+RANGE_CASES = [
+    # signal scale, weight scale, upstream-gradient scale, outlier factor (one signal element multiplied by it)
+    (1.0, 1.0, 1.0, 1.0),
+    # (signal and weight scales cancel, so the pre-activations keep their magnitude and the activation does
+    # not amplify or hide the contraction error)
+    (3.7e6, 2.7e-7, 1.3e-7, 1.0),      # every operand far outside the fp16 range before scaling
+    (4.1e-9, 2.4e8, 8.8e5, 1.0),
+    (1.0, 1.0, 1.0, 1.0e3),            # one element a thousand times the rest
+]
+
+
+@pytest.mark.parametrize("case", RANGE_CASES, ids=lambda c: "x%g-w%g-g%g-o%g" % c)
+def test_f16x3_operand_scaling(case):
+    """The fp16 hi/lo split (GCB_PREC_F16X3, what precision='fp32' resolves to) rescales every operand by a
+    power of two taken from device-side maxima: forward and gradients stay fp32-faithful for data far outside
+    the fp16 range and for a wide dynamic range inside one tensor."""
+    sx, sw, sg, outlier = case
+    v, f, r, a, t = 700, 96, 3, 8, 96
+    assert _native.load().gcb_tc_half_supported(r, a, f, t, a)
+    wn, ws, b = O.make_weights(t, r, a, f, seed=5)
+    wn, ws, b = wn * sw, ws * sw, b * (sx * sw)
+    signal = O.make_signal(v, f, seed=6, kind="randn") * sx
+    signal[17, 5] *= outlier
+    bary = O.make_bary(v, r, a, seed=6, fallback_frac=0.03)
+    gz = torch.randn((v, t), generator=torch.Generator().manual_seed(7)) * sg
+    prior = torch.from_numpy(O.geodesic_prior(O.template_matrix(r, a, 0.03))).float()
+    ref = O.conv_amp_forward_backward(signal.double(), bary, wn.double(), ws.double(), b.double(), prior.double(),
+                                      gz.double(), "tanh" if outlier == 1.0 else "elu", 1)
+    act = "tanh" if outlier == 1.0 else "elu"
+    layer = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.03,
+                         activation=act, precision="f16x3")
+    layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
+    layer = layer.to(DEV)
+    assert ops.resolve_precision("f16x3", r, a, f, t, a) == _native.PREC_F16X3
+    xs = signal.to(DEV).requires_grad_(True)
+    y = layer([xs, bary.to(DEV)])
+    z = AngularMaxPooling()(y)
+    assert nerr(y, ref["y"]) < TOL_FP32
+    if not torch.equal(y._gcb_pooled[1].cpu(), ref["argmax"]):
+        pytest.skip("near-tie rotation flip")
+    z.backward(gz.to(DEV))
+    errs = {"d_signal": nerr(xs.grad, ref["d_signal"]),
+            "d_w_neighbor": nerr(layer._template_neighbor_weights.grad, ref["d_w_neighbor"]),
+            "d_w_self": nerr(layer._template_self_weights.grad, ref["d_w_self"]),
+            "d_bias": nerr(layer._bias.grad, ref["d_bias"])}
+    assert all(e < TOL_FP32 for e in errs.values()), errs
+
+
+def test_f16x3_zero_and_constant_inputs():
+    """All-zero signal (the scale kernel sees a zero bound) and all-zero weights give exact results."""
+    v, f, r, a, t = 300, 64, 3, 8, 32
+    wn, ws, b = O.make_weights(t, r, a, f, seed=8)
+    bary = O.make_bary(v, r, a, seed=8).to(DEV)
+    layer = ConvDirac(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.03,
+                      activation="relu", precision="f16x3")
+    layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
+    layer = layer.to(DEV)
+    y0 = layer([torch.zeros(v, f, device=DEV), bary])
+    expect = torch.relu(b.to(DEV)).reshape(1, 1, t).expand(v, a, t)
+    assert torch.equal(y0, expect)
+    layer.load_state_dict({"_template_neighbor_weights": wn * 0, "_template_self_weights": ws * 0, "_bias": b})
+    y1 = layer([O.make_signal(v, f, seed=9, kind="randn").to(DEV), bary])
+    assert torch.equal(y1, expect)
