@@ -29,6 +29,12 @@ int tc_make_tmap_mn_h(CUtensorMap* out, const __half* base, uint64_t rows, uint6
 // Wcat * (*scale) = hi + lo in fp16, [T][R*A*F + F]
 int tc_build_wcat_h(const float* w_eff, const float* w_self, int T, int R, int A, int F, const float* scale,
                     __half* hi, __half* lo, cudaStream_t st);
+// fused operand maxima + fp16-mode scales (k_tc_maxima in gcb_tc_fwd.cu): mx = 8 zeroed words (mx[7] is the block
+// ticket), segments of floats (max |a[i]|) or of a CSR row pointer (longest row), each reduced into mx[slot]
+constexpr int TC_MAX_SEGS = 6;
+struct TcMaxSeg { const void* ptr; long long n; int is_rowptr; int slot; };
+struct TcMaxJob { TcMaxSeg seg[TC_MAX_SEGS]; int n_seg, mode, have_csr; };
+int tc_maxima_scales(const TcMaxJob& job, unsigned* mx, float* scales, cudaStream_t st);
 // max |a[i]| over up to two arrays as fp32 bits, atomicMax'ed into *out (zero it first)
 int tc_absmax(const float* a, int64_t na, const float* b, int64_t nb, unsigned* out, cudaStream_t st);
 

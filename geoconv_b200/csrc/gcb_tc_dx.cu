@@ -20,6 +20,9 @@
 //                  SWIZZLE_128B_BASE32B), four TMEM accumulators per tile fed round-robin by the K
 //                  chunks and summed in fp32 by the epilogue (the tensor core accumulates with
 //                  truncation, so short chains are what keeps the 3xTF32 mode within 1e-5).
+// GCB_PREC_F16X3 (template flag H): G, X and the weights are written as power-of-two scaled fp16 hi / lo pairs
+// (k_tc_maxima -> scales), both GEMMs issue kind::f16 (K = 16 per instruction: half the tensor time), the
+// MN-major operands use 64-column atoms with the standard 128-byte swizzle, the epilogues undo the scales.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -356,7 +359,6 @@ constexpr int TN_THREADS = (2 + GM_EPI_WARPS) * 32;
 struct TcGemmTnParams {
   const float* inv_scale;           // fp16 route: undoes the operand scales
   uint32_t h_lbo, h_sbo, h_kstep;   // fp16 MN-major descriptor fields (bytes)
-  int kch;           // contraction rows (source vertices) per stage: TN_KCH, or 32 with fp16 operands
   float* partial;    // [vsplit][m_pad][ld]
   int ld, n_cols;    // row length of the output (= columns of X)
   int m_pad, n_mtiles, n_ntiles, vsplit;
@@ -555,35 +557,8 @@ __global__ void k_split_half(const float* __restrict__ src, int64_t rows, int co
   split_half(v, __ldg(scale), hi[i], lo[i]);
 }
 
-// longest CSR row (entries per source vertex), atomicMax'ed into *out
-__global__ void k_bw_max_row(const int32_t* __restrict__ row_ptr, int v_src, unsigned* __restrict__ out) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned m = v < v_src ? (unsigned)(row_ptr[v + 1] - row_ptr[v]) : 0u;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
-}
-
-// Power-of-two operand scales of the fp16 backward.  mx = {max|h|, max|w|, longest CSR row, max|Wcat|, max|X|};
-// |G| <= max|h| * max|w| * longest row - a loose bound only costs absolute resolution far below fp32's
-// (2^-25 of 2^14 / looseness).  scales = {sG, sW, sX, 1/(sG*sW), 1/(sG*sX)}, bound * s in [2^14, 2^15).
-__global__ void k_bw_scales(const unsigned* __restrict__ mx, int have_csr, float* __restrict__ scales) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  auto pow2_for = [](float bound) {
-    if (!(bound > 0.f) || !isfinite(bound)) return 0;
-    int e = 14 - ilogbf(bound);
-    return e < -60 ? -60 : (e > 60 ? 60 : e);
-  };
-  const float hm = __uint_as_float(mx[0]);
-  const float gm = have_csr ? fmaxf(hm * __uint_as_float(mx[1]) * (float)mx[2], hm) : hm;
-  const int eg = pow2_for(gm), ew = pow2_for(__uint_as_float(mx[3])), ex = pow2_for(__uint_as_float(mx[4]));
-  scales[0] = ldexpf(1.f, eg);
-  scales[1] = ldexpf(1.f, ew);
-  scales[2] = ldexpf(1.f, ex);
-  scales[3] = ldexpf(1.f, -(eg + ew));
-  scales[4] = ldexpf(1.f, -(eg + ex));
-}
-
+// Power-of-two operand scales of the fp16 backward (k_tc_maxima, mode 2): |G| <= max|h| * max|w| * longest CSR
+// row - a loose bound only costs absolute resolution far below fp32's (2^-25 of 2^14 / looseness).
 size_t tc_bwd_scales_bytes() { return 256; }
 
 // scratch: 8 unsigned maxima, then the 5 scales (the caller passes scratch + 8 words as `scales`)
@@ -591,22 +566,20 @@ int tc_bwd_scales(const float* h, const float* w, const int32_t* csr_row_ptr, co
                   const float* x, int v_out, int v_src, int R, int A, int F, int T, void* scratch, cudaStream_t st) {
   unsigned* mx = (unsigned*)scratch;
   GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 32, st));
-  int rc = tc_absmax(h, (int64_t)v_out * T, nullptr, 0, mx, st);
-  if (rc) return rc;
   const bool have_csr = csr_row_ptr && w_eff;
+  TcMaxJob job{};
+  job.mode = 2; job.have_csr = have_csr ? 1 : 0;
+  int n = 0;
+  job.seg[n++] = {h, (long long)v_out * T, 0, 0};
   if (have_csr) {
-    rc = tc_absmax(w, (int64_t)v_out * R * A * 3, nullptr, 0, mx + 1, st);
-    if (rc) return rc;
-    k_bw_max_row<<<(unsigned)ceil_div64(v_src, 256), 256, 0, st>>>(csr_row_ptr, v_src, mx + 2);
-    GCB_LAUNCH_OK();
+    job.seg[n++] = {w, (long long)v_out * R * A * 3, 0, 1};
+    job.seg[n++] = {csr_row_ptr, (long long)v_src, 1, 2};
+    job.seg[n++] = {w_eff, (long long)T * R * A * F, 0, 3};
   }
-  rc = tc_absmax(w_eff, w_eff ? (int64_t)T * R * A * F : 0, w_self, (int64_t)T * F, mx + 3, st);
-  if (rc) return rc;
-  rc = tc_absmax(x, (int64_t)v_src * F, nullptr, 0, mx + 4, st);
-  if (rc) return rc;
-  k_bw_scales<<<1, 32, 0, st>>>(mx, have_csr ? 1 : 0, (float*)(mx + 8));
-  GCB_LAUNCH_OK();
-  return GCB_OK;
+  job.seg[n++] = {w_self, (long long)T * F, 0, 3};
+  job.seg[n++] = {x, (long long)v_src * F, 0, 4};
+  job.n_seg = n;
+  return tc_maxima_scales(job, mx, (float*)(mx + 8), st);
 }
 
 // sums the vertex-split partials [vs][(s',t)][f] in a fixed order and scatters to d_w_eff[t][s'][f] / d_w_self[t][f]
@@ -810,7 +783,6 @@ int tc_dw_from_g(const float* g_hi, const float* g_lo, const float* x, int v_src
   }
   TcGemmTnParams p;
   p.inv_scale = half ? scales + 4 : nullptr;
-  p.kch = half ? 32 : TN_KCH;
   {
     static const int lbo_env = getenv("GCB_H_LBO") ? atoi(getenv("GCB_H_LBO")) : 0;   // experiments
     static const int sbo_env = getenv("GCB_H_SBO") ? atoi(getenv("GCB_H_SBO")) : 0;

@@ -366,20 +366,69 @@ __global__ void k_tc_absmax(const float* __restrict__ a, int64_t na, const float
   if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
-// power-of-two operand scales of the fp16 mode.  mx = {max|X|, max sum|w|, max|Wcat|} (fp32 bits);
-// scales = {sA, sB, 1 / (sA * sB)} with bound * s in [2^14, 2^15).
-__global__ void k_tc_scales(const unsigned* __restrict__ mx, float* __restrict__ scales) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const float xm = __uint_as_float(mx[0]), wm = fmaxf(__uint_as_float(mx[1]), 1.f), bm = __uint_as_float(mx[2]);
-  auto pow2_for = [](float bound) {
-    if (!(bound > 0.f) || !isfinite(bound)) return 0;
-    int e = 14 - ilogbf(bound);
-    return e < -60 ? -60 : (e > 60 ? 60 : e);
-  };
-  const int ea = pow2_for(xm * wm), eb = pow2_for(bm);
-  scales[0] = ldexpf(1.f, ea);
-  scales[1] = ldexpf(1.f, eb);
-  scales[2] = ldexpf(1.f, -(ea + eb));
+__device__ __forceinline__ int tc_pow2_for(float bound) {   // bound * 2^e in [2^14, 2^15); 0 for a zero / non-finite bound
+  if (!(bound > 0.f) || !isfinite(bound)) return 0;
+  const int e = 14 - ilogbf(bound);
+  return e < -60 ? -60 : (e > 60 ? 60 : e);
+}
+
+// Operand maxima and the power-of-two scales of the fp16 modes in ONE launch: every block strides over every
+// segment (max |a[i]|, or the longest CSR row for a row-pointer segment) and atomicMax'es its results into mx[slot];
+// the block that finishes last (ticket counter mx[7]) turns the maxima into scales.
+//   mode 1 (forward):  mx = {max|X|, max sum_j|w_j| (from k_tc_pack_recs), max|Wcat|}
+//                      scales = {sA, sB, 1 / (sA sB)},  sA from max|X| * max(sum|w|, 1)
+//   mode 2 (backward): mx = {max|h|, max|w|, longest CSR row, max|Wcat|, max|X|}
+//                      scales = {sG, sW, sX, 1 / (sG sW), 1 / (sG sX)},  |G| <= max|h| * max|w| * longest row
+// (maxima of non-negative floats are compared as bit patterns; a NaN compares above +inf and gives scale 1)
+__global__ void k_tc_maxima(const TcMaxJob job, unsigned* __restrict__ mx, float* __restrict__ scales) {
+  __shared__ unsigned s_max[TC_MAX_SEGS];
+  __shared__ bool s_last;
+  if (threadIdx.x < TC_MAX_SEGS) s_max[threadIdx.x] = 0u;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int sg = 0; sg < job.n_seg; ++sg) {
+    unsigned m = 0;
+    if (job.seg[sg].is_rowptr) {
+      const int32_t* rp = static_cast<const int32_t*>(job.seg[sg].ptr);
+      for (int64_t i = i0; i < job.seg[sg].n; i += stride) m = max(m, (unsigned)(rp[i + 1] - rp[i]));
+    } else {
+      const float* a = static_cast<const float*>(job.seg[sg].ptr);
+      for (int64_t i = i0; i < job.seg[sg].n; i += stride) m = max(m, __float_as_uint(fabsf(__ldg(a + i))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_max[sg], m);
+  }
+  __syncthreads();
+  if (threadIdx.x < job.n_seg && s_max[threadIdx.x]) {
+    atomicMax(mx + job.seg[threadIdx.x].slot, s_max[threadIdx.x]);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(mx + 7, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  volatile const unsigned* vm = mx;
+  if (job.mode == 1) {
+    const float xm = __uint_as_float(vm[0]), wm = fmaxf(__uint_as_float(vm[1]), 1.f), bm = __uint_as_float(vm[2]);
+    const int ea = tc_pow2_for(xm * wm), eb = tc_pow2_for(bm);
+    scales[0] = ldexpf(1.f, ea);
+    scales[1] = ldexpf(1.f, eb);
+    scales[2] = ldexpf(1.f, -(ea + eb));
+  } else {
+    const float hm = __uint_as_float(vm[0]);
+    const float gm = job.have_csr ? fmaxf(hm * __uint_as_float(vm[1]) * (float)vm[2], hm) : hm;
+    const int eg = tc_pow2_for(gm), ew = tc_pow2_for(__uint_as_float(vm[3])), ex = tc_pow2_for(__uint_as_float(vm[4]));
+    scales[0] = ldexpf(1.f, eg);
+    scales[1] = ldexpf(1.f, ew);
+    scales[2] = ldexpf(1.f, ex);
+    scales[3] = ldexpf(1.f, -(eg + ew));
+    scales[4] = ldexpf(1.f, -(eg + ex));
+  }
 }
 
 // fp16 variant of k_tc_wcat: Wcat * (*scales) = hi + lo (both fp16)
@@ -1430,6 +1479,12 @@ int tc_absmax(const float* a, int64_t na, const float* b, int64_t nb, unsigned* 
   return GCB_OK;
 }
 
+int tc_maxima_scales(const TcMaxJob& job, unsigned* mx, float* scales, cudaStream_t st) {
+  k_tc_maxima<<<148 * 2, 256, 0, st>>>(job, mx, scales);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
 static int tc_pack_recs_max(const int32_t* idx, const float* w, int v_out, int R, int A, uint4* recs,
                             unsigned* wsum_max, cudaStream_t st) {
   const int v_pad = (int)ceil_div64(v_out, TC_M) * TC_M;
@@ -1589,20 +1644,21 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   float* partial = (float*)ws;
   ws += tc_partial_bytes(v_out, n_rot, T, ksplit);
   unsigned* mx = (unsigned*)ws;                 // fp16 mode: operand maxima, then the scales
-  float* scales = half ? (float*)(mx + 4) : nullptr;
+  float* scales = half ? (float*)(mx + 8) : nullptr;
 
   int rc;
   CUtensorMap mh, ml;
   if (half) {
-    GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 16, st));
-    rc = tc_absmax(x, (int64_t)v_src * F, nullptr, 0, mx, st);
-    if (rc) return rc;
-    rc = tc_absmax(w_eff, (int64_t)T * RA * F, w_self, (int64_t)T * F, mx + 2, st);
-    if (rc) return rc;
+    GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 32, st));
     rc = tc_pack_recs_max(idx, w, v_out, R, A, recs, mx + 1, st);
     if (rc) return rc;
-    k_tc_scales<<<1, 32, 0, st>>>(mx, scales);
-    GCB_LAUNCH_OK();
+    TcMaxJob job{};
+    job.n_seg = 3; job.mode = 1;
+    job.seg[0] = {x, (long long)v_src * F, 0, 0};
+    job.seg[1] = {w_eff, (long long)T * RA * F, 0, 2};
+    job.seg[2] = {w_self, (long long)T * F, 0, 2};
+    rc = tc_maxima_scales(job, mx, scales, st);
+    if (rc) return rc;
     rc = tc_build_wcat_h(w_eff, w_self, T, R, A, F, scales + 1, (__half*)wc_hi, (__half*)wc_lo, st);
     if (rc) return rc;
     rc = make_weight_tmap_h(&mh, (const __half*)wc_hi, T, kcat, cfg.kc, cfg.n_t);

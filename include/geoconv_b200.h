@@ -168,7 +168,10 @@ int gcb_select_rot(const int32_t* argmax, const int32_t* rot_off_host, int32_t n
  * time); == 0 overwrites.  The AMP-sparse backward is a single call with rot_sel from
  * gcb_select_rot.  d_x uses the CSR from gcb_csr_build: fixed summation order, no atomics.
  * d_x == NULL skips the dSignal stages (signal does not require grad); w_eff == NULL as above
- * (then d_w_eff is zero-filled unless accumulating and the CSR pointers may be NULL).          */
+ * (then d_w_eff is zero-filled unless accumulating and the CSR pointers may be NULL).
+ * precision: GCB_PREC_F16X3 runs the route through the CSR on fp16 hi/lo splits and every other
+ * route (no CSR, w_eff == NULL) like GCB_PREC_TF32X3; shapes the tensor kernels cannot tile
+ * (F % 32 or T % 32 != 0) take the CUDA-core path whatever the precision.                       */
 size_t gcb_conv_bwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
                                     int32_t T, int precision);
 int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
