@@ -74,9 +74,10 @@ __global__ void k_bw_build_g(const float* __restrict__ h, const float* __restric
                              int kg /* (R*A+1)*T */, int kg_ld, const float* __restrict__ scales,
                              float* __restrict__ g_hi, float* __restrict__ g_lo) {
   extern __shared__ float s_acc[];                       // [RA][T]
-  __shared__ int s_k[G_CHUNK];
-  __shared__ int s_slot[G_CHUNK];
-  __shared__ float s_w[G_CHUNK];
+  // per staged entry {row offset of h[k], row offset of its rotated slot in s_acc, weight bits, -}: ONE broadcast
+  // 16-byte read per entry in the loop below (the kernel runs at the load/store-unit wavefront rate: with three
+  // separate arrays half of its shared-memory wavefronts were these metadata reads)
+  __shared__ int4 s_meta[G_CHUNK];
   const int v = blockIdx.x;
   const int RA = R * A;
   const int t = threadIdx.x;
@@ -109,26 +110,29 @@ __global__ void k_bw_build_g(const float* __restrict__ h, const float* __restric
       const int xr = slot / A, ya = slot - xr * A;
       int yr = ya + rot_sel[k];
       yr -= (yr >= A) ? A : 0;
-      s_k[i] = k;
-      s_slot[i] = xr * A + yr;
-      s_w[i] = w[s];
+      s_meta[i] = make_int4(k * T, (xr * A + yr) * T, __float_as_int(w[s]), 0);
     }
     __syncthreads();
     if (t < T) {
       int i = 0;
       for (; i + 8 <= n; i += 8) {
         float hv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) hv[u] = __ldg(h + (size_t)s_k[i + u] * T + t);
+        int4 m[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          float* a = s_acc + s_slot[i + u] * T + t;
-          *a = fmaf(s_w[i + u], hv[u], *a);
+          m[u] = s_meta[i + u];
+          hv[u] = __ldg(h + (size_t)m[u].x + t);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float* a = s_acc + m[u].y + t;
+          *a = fmaf(__int_as_float(m[u].z), hv[u], *a);
         }
       }
       for (; i < n; ++i) {
-        float* a = s_acc + s_slot[i] * T + t;
-        *a = fmaf(s_w[i], __ldg(h + (size_t)s_k[i] * T + t), *a);
+        const int4 m = s_meta[i];
+        float* a = s_acc + m.y + t;
+        *a = fmaf(__int_as_float(m.z), __ldg(h + (size_t)m.x + t), *a);
       }
     }
   }
