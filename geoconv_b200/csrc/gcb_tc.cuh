@@ -33,7 +33,7 @@ int tc_build_wcat_h(const float* w_eff, const float* w_self, int T, int R, int A
 // ticket), segments of floats (max |a[i]|) or of a CSR row pointer (longest row), each reduced into mx[slot]
 constexpr int TC_MAX_SEGS = 6;
 struct TcMaxSeg { const void* ptr; long long n; int is_rowptr; int slot; };
-struct TcMaxJob { TcMaxSeg seg[TC_MAX_SEGS]; int n_seg, mode, have_csr; };
+struct TcMaxJob { TcMaxSeg seg[TC_MAX_SEGS]; int blk0[TC_MAX_SEGS + 1]; int n_seg, mode, have_csr; };
 int tc_maxima_scales(const TcMaxJob& job, unsigned* mx, float* scales, cudaStream_t st);
 // max |a[i]| over up to two arrays as fp32 bits, atomicMax'ed into *out (zero it first)
 int tc_absmax(const float* a, int64_t na, const float* b, int64_t nb, unsigned* out, cudaStream_t st);

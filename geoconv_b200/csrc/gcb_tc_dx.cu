@@ -550,15 +550,26 @@ __global__ void k_split_tf32(const float4* __restrict__ src, int64_t n4, float4*
   if (lo) lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
 }
 
-// src[rows][cols] * (*scale) = hi + lo in fp16, rows of ld (>= cols, zero padded) halves
+// src[rows][cols] * (*scale) = hi + lo in fp16, rows of ld (>= cols, zero padded) halves; ld % 8 == 0 and
+// cols % 4 == 0, a thread converts 8 consecutive columns
 __global__ void k_split_half(const float* __restrict__ src, int64_t rows, int cols, int ld,
                              const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= rows * ld) return;
-  const int64_t r = i / ld;
-  const int c = (int)(i - r * ld);
-  const float v = c < cols ? __ldg(src + r * cols + c) : 0.f;
-  split_half(v, __ldg(scale), hi[i], lo[i]);
+  const int64_t i8 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int g = ld >> 3;
+  if (i8 >= rows * g) return;
+  const int64_t r = i8 / g;
+  const int c = (int)(i8 - r * g) << 3;
+  const float4* p = reinterpret_cast<const float4*>(src + r * cols + c);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 a = c + 4 <= cols ? __ldg(p) : z, b = c + 8 <= cols ? __ldg(p + 1) : z;
+  const float s = __ldg(scale);
+  __half h[8], l[8];
+  split_half(a.x, s, h[0], l[0]); split_half(a.y, s, h[1], l[1]);
+  split_half(a.z, s, h[2], l[2]); split_half(a.w, s, h[3], l[3]);
+  split_half(b.x, s, h[4], l[4]); split_half(b.y, s, h[5], l[5]);
+  split_half(b.z, s, h[6], l[6]); split_half(b.w, s, h[7], l[7]);
+  *reinterpret_cast<uint4*>(hi + i8 * 8) = *reinterpret_cast<const uint4*>(h);
+  *reinterpret_cast<uint4*>(lo + i8 * 8) = *reinterpret_cast<const uint4*>(l);
 }
 
 // Power-of-two operand scales of the fp16 backward (k_tc_maxima, mode 2): |G| <= max|h| * max|w| * longest CSR
@@ -758,7 +769,7 @@ int tc_dw_from_g(const float* g_hi, const float* g_lo, const float* x, int v_src
     const int x_ld = (int)ceil_div64(F, 64) * 64, kg_ld = (int)ceil_div64(L.kg, 64) * 64;
     __half* xh = (__half*)x_hi;
     __half* xl = xh + (size_t)v_src * x_ld;
-    const int64_t n = (int64_t)v_src * x_ld;
+    const int64_t n = (int64_t)v_src * (x_ld / 8);
     k_split_half<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(x, v_src, F, x_ld, scales + 2, xh, xl);
     GCB_LAUNCH_OK();
     rc = tc_make_tmap_mn_h(&ah, (const __half*)g_hi, (uint64_t)L.v_pad, (uint64_t)kg_ld, (uint64_t)kg_ld * 2, 32, 2);

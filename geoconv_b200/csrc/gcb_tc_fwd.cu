@@ -324,6 +324,16 @@ static int tc_pick_ksplit(const TcConfig& cfg, int v_out, int R, int A, int F, i
   return best;
 }
 
+// (a, b) * s = hi + lo with hi, lo fp16 pairs
+__device__ __forceinline__ void split_half2(float a, float b, float s, uint32_t& hi, uint32_t& lo) {
+  a *= s; b *= s;
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // ---- preparation kernels ---------------------------------------------------------------------
 // slot-major packed barycentric records, padded to a multiple of 128 vertices
 // (wsum_max, optional: max over slots of |w0| + |w1| + |w2| as fp32 bits - bounds |interpolation| / max|X|)
@@ -372,6 +382,11 @@ __device__ __forceinline__ int tc_pow2_for(float bound) {   // bound * 2^e in [2
   return e < -60 ? -60 : (e > 60 ? 60 : e);
 }
 
+// 0x7FC00000 if any component is a NaN (fmaxf would silently drop it), else 0
+__device__ __forceinline__ unsigned tc_nan_bits(const float4 v) {
+  return (v.x != v.x || v.y != v.y || v.z != v.z || v.w != v.w) ? 0x7FC00000u : 0u;
+}
+
 // Operand maxima and the power-of-two scales of the fp16 modes in ONE launch: every block strides over every
 // segment (max |a[i]|, or the longest CSR row for a row-pointer segment) and atomicMax'es its results into mx[slot];
 // the block that finishes last (ticket counter mx[7]) turns the maxima into scales.
@@ -381,27 +396,55 @@ __device__ __forceinline__ int tc_pow2_for(float bound) {   // bound * 2^e in [2
 //                      scales = {sG, sW, sX, 1 / (sG sW), 1 / (sG sX)},  |G| <= max|h| * max|w| * longest row
 // (maxima of non-negative floats are compared as bit patterns; a NaN compares above +inf and gives scale 1)
 __global__ void k_tc_maxima(const TcMaxJob job, unsigned* __restrict__ mx, float* __restrict__ scales) {
-  __shared__ unsigned s_max[TC_MAX_SEGS];
+  __shared__ unsigned s_max;
   __shared__ bool s_last;
-  if (threadIdx.x < TC_MAX_SEGS) s_max[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) s_max = 0u;
   __syncthreads();
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x, i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  for (int sg = 0; sg < job.n_seg; ++sg) {
-    unsigned m = 0;
-    if (job.seg[sg].is_rowptr) {
-      const int32_t* rp = static_cast<const int32_t*>(job.seg[sg].ptr);
-      for (int64_t i = i0; i < job.seg[sg].n; i += stride) m = max(m, (unsigned)(rp[i + 1] - rp[i]));
-    } else {
-      const float* a = static_cast<const float*>(job.seg[sg].ptr);
-      for (int64_t i = i0; i < job.seg[sg].n; i += stride) m = max(m, __float_as_uint(fabsf(__ldg(a + i))));
-    }
+  // blocks [blk0[sg], blk0[sg + 1]) work on segment sg (shares proportional to its size, set by the host): the
+  // inputs come cold from HBM, so every thread keeps four 16-byte loads in flight
+  int sg = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_max[sg], m);
+  for (int i = 1; i < TC_MAX_SEGS; ++i) sg += (i < job.n_seg && (int)blockIdx.x >= job.blk0[i]) ? 1 : 0;
+  const int nb = job.blk0[sg + 1] - job.blk0[sg], lb = (int)blockIdx.x - job.blk0[sg];
+  const int64_t n = job.seg[sg].n, stride = (int64_t)nb * blockDim.x, i0 = (int64_t)lb * blockDim.x + threadIdx.x;
+  unsigned m = 0;
+  if (job.seg[sg].is_rowptr) {
+    const int32_t* rp = static_cast<const int32_t*>(job.seg[sg].ptr);
+    for (int64_t i = i0; i < n; i += stride) m = max(m, (unsigned)(rp[i + 1] - rp[i]));
+  } else {
+    const float* a = static_cast<const float*>(job.seg[sg].ptr);
+    int64_t done = 0;
+    if ((reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+      const float4* a4 = reinterpret_cast<const float4*>(a);
+      const int64_t n4 = n >> 2;
+      int64_t i = i0;
+      for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 v0 = __ldg(a4 + i), v1 = __ldg(a4 + i + stride), v2 = __ldg(a4 + i + 2 * stride),
+                     v3 = __ldg(a4 + i + 3 * stride);
+        const float q0 = fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w)));
+        const float q1 = fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w)));
+        const float q2 = fmaxf(fmaxf(fabsf(v2.x), fabsf(v2.y)), fmaxf(fabsf(v2.z), fabsf(v2.w)));
+        const float q3 = fmaxf(fmaxf(fabsf(v3.x), fabsf(v3.y)), fmaxf(fabsf(v3.z), fabsf(v3.w)));
+        // (bit patterns, so that a NaN is not dropped the way fmaxf drops it)
+        m = max(m, max(max(__float_as_uint(fabsf(v0.x)), __float_as_uint(q0)), __float_as_uint(q1)));
+        m = max(m, max(__float_as_uint(q2), __float_as_uint(q3)));
+        m = max(m, tc_nan_bits(v0) | tc_nan_bits(v1) | tc_nan_bits(v2) | tc_nan_bits(v3));
+      }
+      for (; i < n4; i += stride) {
+        const float4 v = __ldg(a4 + i);
+        m = max(m, max(max(__float_as_uint(fabsf(v.x)), __float_as_uint(fabsf(v.y))),
+                       max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+      }
+      done = n4 << 2;
+    }
+    for (int64_t i = done + i0; i < n; i += stride) m = max(m, __float_as_uint(fabsf(__ldg(a + i))));
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_max, m);
   __syncthreads();
-  if (threadIdx.x < job.n_seg && s_max[threadIdx.x]) {
-    atomicMax(mx + job.seg[threadIdx.x].slot, s_max[threadIdx.x]);
+  if (threadIdx.x == 0 && s_max) {
+    atomicMax(mx + job.seg[sg].slot, s_max);
     __threadfence();
   }
   __syncthreads();
@@ -431,18 +474,33 @@ __global__ void k_tc_maxima(const TcMaxJob job, unsigned* __restrict__ mx, float
   }
 }
 
-// fp16 variant of k_tc_wcat: Wcat * (*scales) = hi + lo (both fp16)
+// fp16 variant of k_tc_wcat: Wcat * (*scales) = hi + lo (both fp16); a thread converts 8 consecutive elements of a
+// row (R*A*F and F are multiples of 8, so a group never straddles [Weff | Wself]) with 16-byte loads and stores
 __global__ void k_tc_wcat_h(const float* __restrict__ w_eff, const float* __restrict__ w_self, int T, int KRA,
                             int F, const float* __restrict__ scales, __half* __restrict__ hi,
                             __half* __restrict__ lo) {
-  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int kcat = KRA + F;
-  if (e >= (int64_t)T * kcat) return;
-  int t = (int)(e / kcat), k = (int)(e - (int64_t)t * kcat);
-  float v = (k < KRA ? w_eff[(size_t)t * KRA + k] : w_self[(size_t)t * F + (k - KRA)]) * __ldg(scales);
-  const __half h = __float2half_rn(v);
-  hi[e] = h;
-  lo[e] = __float2half_rn(v - __half2float(h));
+  const int64_t e8 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int kcat = KRA + F, k8n = kcat >> 3;
+  if (e8 >= (int64_t)T * k8n) return;
+  const int t = (int)(e8 / k8n), k = (int)(e8 - (int64_t)t * k8n) << 3;
+  const float* src = k < KRA ? w_eff + (size_t)t * KRA + k : w_self + (size_t)t * F + (k - KRA);
+  const float s = __ldg(scales);
+  float v[8];
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j);
+  }
+  uint4 h, l;
+  split_half2(v[0], v[1], s, h.x, l.x);
+  split_half2(v[2], v[3], s, h.y, l.y);
+  split_half2(v[4], v[5], s, h.z, l.z);
+  split_half2(v[6], v[7], s, h.w, l.w);
+  const size_t o = (size_t)t * kcat + k;   // multiple of 8 halves: 16-byte aligned
+  *reinterpret_cast<uint4*>(hi + o) = h;
+  *reinterpret_cast<uint4*>(lo + o) = l;
 }
 
 // Wcat[t, 0:KRA] = Weff[t], Wcat[t, KRA:KRA+F] = Wself[t], split into tf32 hi (+ lo for X3)
@@ -464,16 +522,6 @@ __device__ __forceinline__ uint32_t swz_chunk(int row, int c) {
   if (KC == 32) return (uint32_t)(c ^ (row & 7));
   if (KC == 16) return (uint32_t)(c ^ ((row >> 1) & 3));
   return (uint32_t)(c ^ ((row >> 2) & 1));
-}
-
-// (a, b) * s = hi + lo with hi, lo fp16 pairs
-__device__ __forceinline__ void split_half2(float a, float b, float s, uint32_t& hi, uint32_t& lo) {
-  a *= s; b *= s;
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 f = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // phase of the super-step after one with phase `phi`
@@ -1467,7 +1515,8 @@ static int make_weight_tmap_h(CUtensorMap* out, const __half* base, int T, int k
 int tc_build_wcat_h(const float* w_eff, const float* w_self, int T, int R, int A, int F, const float* scale,
                     __half* hi, __half* lo, cudaStream_t st) {
   const int KRA = R * A * F;
-  const int64_t wt = (int64_t)T * (KRA + F);
+  GCB_REQUIRE(F % 8 == 0, GCB_EINVAL, "tc_build_wcat_h: F must be a multiple of 8");
+  const int64_t wt = (int64_t)T * ((KRA + F) / 8);
   k_tc_wcat_h<<<(unsigned)ceil_div64(wt, 256), 256, 0, st>>>(w_eff, w_self, T, KRA, F, scale, hi, lo);
   GCB_LAUNCH_OK();
   return GCB_OK;
@@ -1479,8 +1528,27 @@ int tc_absmax(const float* a, int64_t na, const float* b, int64_t nb, unsigned* 
   return GCB_OK;
 }
 
-int tc_maxima_scales(const TcMaxJob& job, unsigned* mx, float* scales, cudaStream_t st) {
-  k_tc_maxima<<<148 * 2, 256, 0, st>>>(job, mx, scales);
+int tc_maxima_scales(const TcMaxJob& job_in, unsigned* mx, float* scales, cudaStream_t st) {
+  // blocks per segment: proportional to its bytes, at least one; empty segments are dropped
+  TcMaxJob job = job_in;
+  int n = 0;
+  for (int i = 0; i < job_in.n_seg; ++i)
+    if (job_in.seg[i].ptr && job_in.seg[i].n > 0) job.seg[n++] = job_in.seg[i];
+  job.n_seg = n;
+  GCB_REQUIRE(n > 0 && n <= TC_MAX_SEGS, GCB_EINVAL, "tc_maxima_scales: no input");
+  long long total = 0;
+  for (int i = 0; i < n; ++i) total += job.seg[i].n;
+  const int budget = 148 * 4;
+  int at = 0;
+  for (int i = 0; i < n; ++i) {
+    job.blk0[i] = at;
+    long long want = (job.seg[i].n * budget + total - 1) / total;
+    const long long cap = (job.seg[i].n + 1023) / 1024;   // no more blocks than 1024-element pieces
+    if (want > cap) want = cap;
+    at += want < 1 ? 1 : (int)want;
+  }
+  for (int i = n; i <= TC_MAX_SEGS; ++i) job.blk0[i] = at;
+  k_tc_maxima<<<at, 256, 0, st>>>(job, mx, scales);
   GCB_LAUNCH_OK();
   return GCB_OK;
 }

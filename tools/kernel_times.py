@@ -1,0 +1,50 @@
+"""Warm per-kernel durations of one S1 step (fwd + AMP + bwd) from torch.profiler (CUPTI activity records),
+L2 flushed between steps.  usage: kernel_times.py [precision ...]"""
+import collections, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import ProfilerActivity, profile
+from geoconv_b200 import synthetic as S
+from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
+from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
+
+v, f, r, a, t = 6890, 544, 5, 8, 96
+dev = "cuda:0"
+wn, ws, b = S.make_weights(t, r, a, f, seed=0)
+x = S.make_signal(v, f, seed=1).to(dev).requires_grad_(True)
+bary = S.make_bary(v, r, a, seed=1).to(dev)
+gz = torch.randn((v, t), generator=torch.Generator().manual_seed(2)).to(dev)
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+amp = AngularMaxPooling()
+STEPS = 10
+for prec in sys.argv[1:] or ["fp32"]:
+    layer = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.028, precision=prec)
+    layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
+    layer = layer.to(dev)
+
+    def step():
+        x.grad = None
+        for p in layer.parameters():
+            p.grad = None
+        amp(layer([x, bary])).backward(gz)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(STEPS):
+            flush.zero_()
+            step()
+        torch.cuda.synchronize()
+    agg = collections.OrderedDict()
+    for ev in prof.events():
+        if ev.device_type.name != "CUDA" or "FillFunctor" in ev.name and ev.device_time > 50:
+            continue
+        agg.setdefault(ev.name[:72], []).append(ev.device_time)
+    total = 0.0
+    print(f"== {prec}: per-kernel device time per step (us), {STEPS} steps")
+    for name, ts in agg.items():
+        per_step = sum(ts) / STEPS
+        total += per_step
+        print(f"{per_step:9.1f}  x{len(ts) / STEPS:4.1f}  {name}")
+    print(f"{total:9.1f}  sum of kernels per step")
