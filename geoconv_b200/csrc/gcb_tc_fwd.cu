@@ -119,7 +119,9 @@ struct TcFwdParams {
   const uint8_t* tabs;  // [n_groups][tab_bytes]
   const int* splits;    // [ksplit + 1] first super-step of every K split (tc_split_table)
   int drain_cw;         // accumulator columns staged per bulk store in the drain (0: registers -> global directly)
+  int split_reverse;    // 1: K splits are dispatched last-to-first
   long long* trace;     // GCB_TC_TRACE (investigation builds): clock64 stamps of CTA (1,0,0), [role][tile][8]
+  long long* cta_log;   // GCB_TC_TRACE=2: per CTA {globaltimer at entry, at exit, clock64 at entry, at exit, SM id}
   int debug;            // GCB_TC_DEBUG bits (timing experiments only): 1 = all gathers read row 0, 2 = no MMAs
   TcRing ring;
   RotTable rot;         // offsets in [0, A)
@@ -945,6 +947,15 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   long long* const life = p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 &&
                                   threadIdx.x == TC_WARP_PROD0 * 32 ? p.trace + ((size_t)3 * 128 + 127) * 8 : nullptr;
   if (life) life[0] = clock64();
+  long long* const clog = p.cta_log && threadIdx.x == TC_WARP_PROD0 * 32
+                              ? p.cta_log + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 5 : nullptr;
+  if (clog) {
+    unsigned sm;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    clog[0] = (long long)gt; clog[2] = clock64(); clog[4] = sm;
+  }
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_tile_bytes = p.n_t * ROW_BYTES;
   const uint32_t b_base = smem_base;                                        // [NPROD][n_pos][b_tile]
@@ -988,7 +999,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_M;
   const int grp = blockIdx.y;
-  const int tz = blockIdx.z / p.ksplit, sk = blockIdx.z - tz * p.ksplit;
+  // CTAs are dispatched in blockIdx order: the split that holds the centre super-steps (one tile each, so one
+  // weight-ring reload per tile) goes FIRST instead of forming the tail wave (GCB_TC_SPLIT_ORDER=0: index order)
+  const int tz = blockIdx.z / p.ksplit;
+  const int sk = p.split_reverse ? p.ksplit - 1 - (int)(blockIdx.z - tz * p.ksplit) : (int)(blockIdx.z - tz * p.ksplit);
   const int t0 = tz * p.n_t;
   const int rot0 = grp * p.g;
   const int g_cnt = min(p.g, p.n_rot - rot0);
@@ -1362,6 +1376,11 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
   }
   if (CL == 2) ptx::cluster_sync();   // neither CTA leaves while the peer may still write / arrive here
   if (life) life[5] = clock64();
+  if (clog) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    clog[1] = (long long)gt; clog[3] = clock64();
+  }
 }
 
 // ---- kernel 2: split reduction + bias + activation + angular max-pooling -------------------------
@@ -1752,6 +1771,10 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   p.phase_shift = phase_shift;
   p.phase_alt = cfg.ring.shift > 0 ? 1 : 0;
   p.bar_bytes = (int)tc_bar_bytes(cfg.ring.n_pos, cfg.ring.n_pos + cfg.ring.shift);
+  {
+    static const int order_env = getenv("GCB_TC_SPLIT_ORDER") ? atoi(getenv("GCB_TC_SPLIT_ORDER")) : 1;   // experiments
+    p.split_reverse = (order_env && x3) ? 1 : 0;   // (measured: +1 % with three products per k-step, -0.4 % in tf32 mode)
+  }
   p.tab_bytes = (int)tc_tab_bytes(A, cfg.ring.n_pos);
   p.tabs = (const uint8_t*)mx + TC_SCALES_BYTES;
   p.splits = (const int*)(p.tabs + TC_TABS_BYTES);
@@ -1770,7 +1793,17 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   p.debug = debug;
   p.ring = cfg.ring;
   p.trace = nullptr;
+  p.cta_log = nullptr;
   static long long* trace_dev = nullptr;
+  static long long* clog_dev = nullptr;
+  const size_t n_ctas = (size_t)m_tiles * cfg.n_groups * (T / cfg.n_t) * ksplit;
+  if (getenv("GCB_TC_TRACE") && atoi(getenv("GCB_TC_TRACE")) == 2) {
+    if (!clog_dev) GCB_CUDA_OK(cudaMalloc(&clog_dev, 16384 * 5 * sizeof(long long)));
+    if (n_ctas <= 16384) {
+      GCB_CUDA_OK(cudaMemsetAsync(clog_dev, 0, n_ctas * 5 * sizeof(long long), st));
+      p.cta_log = clog_dev;
+    }
+  }
   if (getenv("GCB_TC_TRACE")) {   // investigation aid only: the one place the library touches cudaMalloc
     if (!trace_dev) GCB_CUDA_OK(cudaMalloc(&trace_dev, 4 * 128 * 8 * sizeof(long long)));
     GCB_CUDA_OK(cudaMemsetAsync(trace_dev, 0, 4 * 128 * 8 * sizeof(long long), st));
@@ -1793,6 +1826,27 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   k_tc_finish<<<(unsigned)ceil_div64(v_out, warps_per_block), warps_per_block * 32, 0, st>>>(
       partial, bias, ksplit, v_out, v_pad, n_rot, T, act, scales, y, z, argmax);
   GCB_LAUNCH_OK();
+  if (p.cta_log) {
+    // per-CTA life times: printed by dispatch order in groups of 148 (one "wave" if all CTAs took equally long)
+    static long long hl[16384 * 5];
+    GCB_CUDA_OK(cudaMemcpyAsync(hl, p.cta_log, n_ctas * 5 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    GCB_CUDA_OK(cudaStreamSynchronize(st));
+    long long t_min = hl[0], t_max = 0;
+    for (size_t i = 0; i < n_ctas; ++i) { if (hl[i * 5] < t_min) t_min = hl[i * 5]; if (hl[i * 5 + 1] > t_max) t_max = hl[i * 5 + 1]; }
+    fprintf(stderr, "[cta log] %zu CTAs, kernel span %.1f us\n", n_ctas, (t_max - t_min) * 1e-3);
+    for (size_t g0 = 0; g0 < n_ctas; g0 += 148) {
+      const size_t g1 = g0 + 148 < n_ctas ? g0 + 148 : n_ctas;
+      double s_ns = 0, s_cy = 0, st0 = 0, en = 0; long long mx_ns = 0;
+      for (size_t i = g0; i < g1; ++i) {
+        const long long ns = hl[i * 5 + 1] - hl[i * 5], cy = hl[i * 5 + 3] - hl[i * 5 + 2];
+        s_ns += ns; s_cy += cy; st0 += hl[i * 5] - t_min; en += hl[i * 5 + 1] - t_min;
+        if (ns > mx_ns) mx_ns = ns;
+      }
+      const double n = (double)(g1 - g0);
+      fprintf(stderr, "  CTAs %5zu-%5zu: mean start %7.1f us, mean end %7.1f us, life %6.1f us (max %6.1f) = %7.0f cycles -> %.0f MHz\n",
+              g0, g1 - 1, st0 / n * 1e-3, en / n * 1e-3, s_ns / n * 1e-3, mx_ns * 1e-3, s_cy / n, s_cy / s_ns * 1e3);
+    }
+  }
   if (p.trace) {
     static long long host[4 * 128 * 8];
     GCB_CUDA_OK(cudaMemcpyAsync(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost, st));

@@ -14,5 +14,5 @@ with torch.no_grad():
     os.environ.pop("GCB_TC_TRACE", None)
     for _ in range(2): layer([x, bary])
     torch.cuda.synchronize()
-    os.environ["GCB_TC_TRACE"] = "1"
+    os.environ["GCB_TC_TRACE"] = os.environ.get("GCB_TRACE_MODE", "1")
     layer([x, bary]); torch.cuda.synchronize()
