@@ -46,6 +46,51 @@ def test_error_reporting_without_gpu():
         _native.check(rc, "gcb_prep_bary")
 
 
+def test_precision_resolution():
+    """'fp32' resolves to the fastest fp32-faithful arithmetic the shape allows: fp16 hi/lo splits (F % 16 == 0),
+    else tf32 splits, else CUDA cores; explicit modes degrade the same way (host-side tiling queries, no GPU)."""
+    from geoconv_b200 import ops
+    lib = _native.load()
+    assert lib.gcb_tc_supported(5, 8, 544, 96, 8) == 1 and lib.gcb_tc_half_supported(5, 8, 544, 96, 8) == 1
+    assert ops.resolve_precision("fp32", 5, 8, 544, 96, 8) == _native.PREC_F16X3
+    assert ops.resolve_precision("f16x3", 5, 8, 544, 96, 8) == _native.PREC_F16X3
+    assert ops.resolve_precision("tf32x3", 5, 8, 544, 96, 8) == _native.PREC_TF32X3
+    assert ops.resolve_precision("tf32", 5, 8, 544, 96, 8) == _native.PREC_TF32
+    assert ops.resolve_precision("ffma", 5, 8, 544, 96, 8) == _native.PREC_FP32
+    # F = 40: tensor tiling exists (F % 8 == 0) but no fp16 row of 16 features
+    assert lib.gcb_tc_supported(2, 6, 40, 48, 3) == 1 and lib.gcb_tc_half_supported(2, 6, 40, 48, 3) == 0
+    assert ops.resolve_precision("fp32", 2, 6, 40, 48, 3) == _native.PREC_TF32X3
+    assert ops.resolve_precision("f16x3", 2, 6, 40, 48, 3) == _native.PREC_TF32X3
+    # F = 3 (xyz signal): no tensor tiling at all
+    assert lib.gcb_tc_supported(5, 8, 3, 32, 8) == 0
+    assert ops.resolve_precision("fp32", 5, 8, 3, 32, 8) == _native.PREC_FP32
+    assert ops.resolve_precision("tf32", 5, 8, 3, 32, 8) == _native.PREC_FP32
+    with pytest.raises(ValueError):
+        ops.resolve_precision("bf16", 5, 8, 544, 96, 8)
+
+
+def test_fp16_split_shape_check_in_the_c_abi():
+    """gcb_conv_fwd refuses GCB_PREC_F16X3 for a shape without an fp16 tiling before any CUDA call, and the
+    workspace query covers the fp16 mode's extra buffers (scales, ring schedules, split table)."""
+    import ctypes as C
+    lib = _native.load()
+    v, r, a, f, t, n_rot = 256, 2, 6, 40, 48, 3
+    need = lib.gcb_conv_fwd_workspace_bytes(v, v, r, a, f, t, n_rot, _native.PREC_F16X3)
+    rot = (C.c_int32 * n_rot)(0, 2, 4)
+    fake = C.c_void_p(256)   # never dereferenced: the shape check comes first
+    rc = lib.gcb_conv_fwd(fake, fake, fake, fake, fake, fake, rot, n_rot, v, v, r, a, f, t, 0, _native.PREC_F16X3,
+                          fake, None, None, None, fake, C.c_size_t(max(need, 1) + (1 << 30)), None)
+    assert rc == 3, lib.gcb_last_error()
+    assert b"fp16 split" in lib.gcb_last_error()
+    # FAUST shape: the fp16 mode needs less workspace than 3xTF32 with its 12 K splits, more than nothing
+    w16 = lib.gcb_conv_fwd_workspace_bytes(6890, 6890, 5, 8, 544, 96, 8, _native.PREC_F16X3)
+    w32 = lib.gcb_conv_fwd_workspace_bytes(6890, 6890, 5, 8, 544, 96, 8, _native.PREC_TF32X3)
+    assert 0 < w16 < w32
+    b16 = lib.gcb_conv_bwd_workspace_bytes(6890, 6890, 5, 8, 544, 96, _native.PREC_F16X3)
+    b32 = lib.gcb_conv_bwd_workspace_bytes(6890, 6890, 5, 8, 544, 96, _native.PREC_TF32X3)
+    assert b16 == b32   # the fp16 buffers live inside the 3xTF32 layout
+
+
 def _make(g, **kw):
     v, r, a = g["bary"].shape[:3]
     f = g["signal"].shape[1]
