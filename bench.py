@@ -1,6 +1,6 @@
 """Benchmark of the ConvGeodesic + AngularMaxPooling forward+backward hot path (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|tf32] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|tf32|tf32x3|f16x3|ffma] [--impl ours|reference]
 
 Workload (config.workload = "S1"): one FAUST-shaped synthetic mesh per step and per GPU -
 V=6890 vertices, 544-dim SHOT-shaped signal, ConvGeodesic 544->96, R5xA8, rotation_delta 1, relu,
@@ -13,8 +13,10 @@ One JSON line is printed by rank 0:
   e2e       the same metric through the public layer API starting from pinned HOST buffers
             (signal, bary, upstream grad copied H2D and the pooled output copied D2H every step);
   roofline  the dominant kernel (forward tcgen05 contraction) timed live with CUDA events on its
-            launch stream, algorithmic FLOPs / duration against the TF32 tensor peak derived from
-            MEASURED_PEAKS.json (bf16/2; TF32 itself is not in that file);
+            launch stream, algorithmic FLOPs / duration against the tensor peak of MEASURED_PEAKS.json: the
+            measured bf16 figure for the fp32 mode (fp16 hi/lo operand splits, kind::f16 MMAs, three per
+            product: ceiling 1/3, `frac_of_ceiling` reported next to `frac`), bf16/2 (derived; TF32 itself is
+            not in that file) for the tf32 modes;
   cpu_baseline  the CPU oracle (a port of the reference algorithm in stock torch CPU ops) timed on
             this host's cores on the same workload.
 `--impl reference` times that CPU oracle only (rank 0), with all host threads.

@@ -44,7 +44,8 @@ def _need_cuda(t: torch.Tensor, name: str) -> None:
 
 
 def resolve_precision(mode: str, r: int, a: int, f: int, t: int, n_rot: int) -> int:
-    """'fp32' = fp32-faithful (3xTF32 tensor-core kernel when the shape allows, else CUDA cores)."""
+    """'fp32' = fp32-faithful: tensor cores on fp16 hi/lo splits (F % 16 == 0), else on tf32 splits (3xTF32),
+    else CUDA cores; explicit tensor modes fall back to the exact CUDA-core arithmetic for shapes they cannot tile."""
     if mode not in PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {mode!r}")
     lib = N.load()
