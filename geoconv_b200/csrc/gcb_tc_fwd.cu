@@ -1406,7 +1406,7 @@ __global__ void k_tc_finish(const float* __restrict__ partial, const float* __re
       const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + q);
       float4 acc = scales ? make_float4(0.f, 0.f, 0.f, 0.f) : bv;
       for (int sp = 0; sp < ksplit; ++sp) {
-        const float4 pv = __ldg(reinterpret_cast<const float4*>(src + sp * split_stride) + q);
+        const float4 pv = __ldcs(reinterpret_cast<const float4*>(src + sp * split_stride) + q);   // read once: streaming
         acc.x += pv.x; acc.y += pv.y; acc.z += pv.z; acc.w += pv.w;
       }
       if (scales) {
