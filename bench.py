@@ -172,16 +172,57 @@ def make_inputs(cfg, seed_offset=0):
     return signal, bary, grad_z
 
 
-def cpu_reference_step(cfg, weights, inputs):
-    """One fwd+bwd of the CPU oracle (reference algorithm restated in stock torch CPU ops)."""
+WORKLOAD = "S1: V=6890 F=544 T=96 R5xA8 delta1 relu, ConvGeodesic+AMP fwd+bwd, 1 mesh/step/GPU"
+
+
+def make_cpu_reference(cfg, weights):
+    """The CPU arm: a callable running one fwd+bwd of ConvGeodesic + AngularMaxPooling on the host cores.
+
+    Preferred: the UNMODIFIED reference package (`geoconv`, installed offline into baseline/_ref by
+    baseline/install_ref.sh, or an installed `geoconv` in site-packages) through its own public layer API
+    -> kind "reference".  If neither is importable: the oracle port (oracle/geoconv_oracle.py) -> kind "port".
+    Returns (step(inputs) -> seconds, kind, description)."""
     import torch
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    added = False
+    try:
+        if os.path.isdir(os.path.join(ref_dir, "geoconv")):
+            sys.path.insert(0, ref_dir)
+            added = True
+        from geoconv.pytorch.layers.angular_max_pooling import AngularMaxPooling as RefAMP
+        from geoconv.pytorch.layers.conv_geodesic import ConvGeodesic as RefConv
+        import geoconv as _g
+        layer = RefConv(input_shape=[(None, cfg["f"]), (None, cfg["r"], cfg["a"], 3, 2)], amt_templates=cfg["t"],
+                        template_radius=cfg["radius"], activation=cfg["act"], rotation_delta=cfg["delta"])
+        layer.load_state_dict({"_template_neighbor_weights": weights[0], "_template_self_weights": weights[1],
+                               "_bias": weights[2]})
+        amp = RefAMP()
+
+        def step(inputs):
+            signal, bary, grad_z = inputs
+            for p_ in layer.parameters():
+                p_.grad = None
+            xs = signal.clone().requires_grad_(True)
+            t0 = time.perf_counter()
+            z = amp(layer([xs, bary]))
+            z.backward(grad_z)
+            return time.perf_counter() - t0
+        where = os.path.relpath(os.path.dirname(_g.__file__), ROOT) if _g.__file__.startswith(ROOT) else "site-packages"
+        return step, "reference", f"geoconv {where} (unmodified reference layers, torch {torch.__version__} CPU autograd)"
+    except Exception as exc:  # noqa: BLE001 - the reference is not reachable: time the port
+        if added:
+            sys.path.remove(ref_dir)
+        sys.stderr.write(f"bench: reference package not importable ({exc}); timing the oracle port\n")
     from oracle import geoconv_oracle as O
     wn, ws, b = weights
-    signal, bary, grad_z = inputs
     prior = torch.from_numpy(O.geodesic_prior(O.template_matrix(cfg["r"], cfg["a"], cfg["radius"]))).float()
-    t0 = time.perf_counter()
-    O.conv_amp_forward_backward(signal, bary, wn, ws, b, prior, grad_z, cfg["act"], cfg["delta"])
-    return time.perf_counter() - t0
+
+    def step_port(inputs):
+        signal, bary, grad_z = inputs
+        t0 = time.perf_counter()
+        O.conv_amp_forward_backward(signal, bary, wn, ws, b, prior, grad_z, cfg["act"], cfg["delta"])
+        return time.perf_counter() - t0
+    return step_port, "port", f"oracle/geoconv_oracle.py (port of the reference algorithm, torch {torch.__version__} CPU)"
 
 
 def run_reference(args):
@@ -195,21 +236,21 @@ def run_reference(args):
     torch.set_num_threads(cores)
     weights = S.make_weights(cfg["t"], cfg["r"], cfg["a"], cfg["f"], seed=0)
     inputs = make_inputs(cfg)
+    step, kind, descr = make_cpu_reference(cfg, weights)
     for _ in range(args.warmup):
-        cpu_reference_step(cfg, weights, inputs)
+        step(inputs)
     total = 0.0
     for _ in range(args.steps):
-        total += cpu_reference_step(cfg, weights, inputs)
+        total += step(inputs)
     value = cfg["v"] * args.steps / total
     line = {
         "impl": "reference", "metric": "vertices/sec, ConvGeodesic+AMP fwd+bwd", "value": value,
         "unit": "vertices/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "S1: V=6890 F=544 T=96 R5xA8 delta1 relu, ConvGeodesic+AMP fwd+bwd, 1 mesh/step",
-                   "device": "cpu"},
-        "cpu_baseline": {"value": value, "unit": "vertices/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full S1 meshes (fwd+bwd), torch {torch.__version__} CPU"},
+        "config": {"workload": WORKLOAD, "device": "cpu", "implementation": descr},
+        "cpu_baseline": {"value": value, "unit": "vertices/s", "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} full S1 meshes (fwd+bwd) after {args.warmup} warm-ups; {descr}"},
         "e2e": {"value": value, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -475,15 +516,13 @@ def run_ours(args):
 
     # Host-to-host leg: the same public layer calls, with the H2D copies of this step's inputs, the
     # per-mesh preparation (bary split, CSR inversion) and the D2H of the result inside the timed
-    # region.  The user's step is captured in a CUDA graph (index validation, which needs a host
-    # sync, is switched off for the capture); eager launches if capture fails.
+    # region.  The user's step is captured in a CUDA graph with the layer's defaults (index validation is
+    # a device-side counter inside gcb_prep_bary, no host sync); eager launches if capture fails.
     e2e_mode = "eager"
     step_e2e_value = step_e2e
     if args.graph:
         try:
-            layer.check_indices = False
-
-            def e2e_body():
+            def e2e_body():   # (index validation stays on: it is a device-side counter, not a host sync)
                 for p_ in params:
                     p_.grad = None
                 sig_buf.copy_(signal_h, non_blocking=True)
@@ -582,10 +621,11 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         cpu_inputs = make_inputs(cfg)
-        cpu_reference_step(cfg, weights, cpu_inputs)
-        cpu_t = min(cpu_reference_step(cfg, weights, cpu_inputs) for _ in range(2))
-        cpu_baseline = {"value": v / cpu_t, "unit": "vertices/s", "cores": cores, "kind": "port",
-                        "sample": "best of 2 full S1 meshes (fwd+bwd) after 1 warm-up, torch CPU oracle"}
+        cpu_step, cpu_kind, cpu_descr = make_cpu_reference(cfg, weights)
+        cpu_step(cpu_inputs)
+        cpu_t = min(cpu_step(cpu_inputs) for _ in range(2))
+        cpu_baseline = {"value": v / cpu_t, "unit": "vertices/s", "cores": cores, "kind": cpu_kind,
+                        "sample": f"best of 2 full S1 meshes (fwd+bwd) after 1 warm-up; {cpu_descr}"}
 
     h2d = signal_h.numel() * 4 + bary_h.numel() * bary_h.element_size() + gz_h.numel() * 4
     d2h = z_host.numel() * 4
@@ -594,13 +634,17 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
-        "config": {"workload": "S1: V=6890 F=544 T=96 R5xA8 delta1 relu, ConvGeodesic+AMP fwd+bwd, 1 mesh/step/GPU",
+        "config": {"workload": WORKLOAD,
                    "precision": args.precision, "launch": launch_mode, "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)",
                    "parallelism": f"dp{world} (one mesh per rank per step" + (", NCCL all-reduce of weight gradients)" if world > 1 else ")")},
         "e2e": {"value": e2e_value, "unit": "vertices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "launch": e2e_mode,
                 "overlap": e2e_mode_p or "none (copies and compute serialised on one stream)",
                 "serial_ms_per_step": e2e_serial_ms / args.steps,
+                "derivation": ("pipelined figure = device time of the timed loop minus the separately timed loop of its L2 "
+                               "flushes (the flush is measurement apparatus, not part of a step); serial figure = per-step "
+                               "events, flush outside") if e2e_mode_p else "per-step events, flush outside",
+                "index_validation": "on (layer default: device-side counter, deferred report)",
                 "includes": "H2D signal+bary+upstream grad, bary split, CSR inversion, fwd, bwd, D2H pooled output"},
         "gpu_launches": int(launches),
         "roofline": roofline,

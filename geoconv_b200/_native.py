@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgeoconv_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_ROT = 32
 
 PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_F16X3 = 0, 1, 2, 3
@@ -48,8 +48,9 @@ SIGNATURES = {
     "gcb_apool_fwd": (_int, [_p, _i32, _i32, _i32, _int, _p, _p, _p]),
     "gcb_apool_bwd": (_int, [_p, _p, _i32, _i32, _i32, _int, _p, _p]),
     "gcb_act_grad": (_int, [_p, _p, _i64, _int, _p, _p]),
-    "gcb_select_rot": (_int, [_p, C.POINTER(_i32), _i32, _i32, _p, _p]),
+    "gcb_select_rot": (_int, [_p, C.POINTER(_i32), _i32, _i32, _i32, _p, _p]),
     "gcb_conv_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _int]),
+    "gcb_conv_bwd_workspace_selfcheck": (_int, [_i32, _i32, _i32, _i32, _i32, _i32, _int]),
     "gcb_conv_bwd": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _int,
                             _int, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gcb_pack_rows": (_int, [_p, _p, _i32, _i32, _p, _p]),

@@ -161,6 +161,15 @@ extern "C" size_t gcb_conv_bwd_workspace_bytes(int32_t v_out, int32_t v_src, int
   return ffma;
 }
 
+extern "C" int gcb_conv_bwd_workspace_selfcheck(int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
+                                                int32_t T, int precision) {
+  if (precision == GCB_PREC_FP32 || !tc_bwd_supported(R, A, F, T)) return 1;   // CUDA-core route: one fixed layout
+  return tc_bwd_layout_fits(v_out, v_src, R, A, F, T, precision) &&
+                 gcb_conv_bwd_workspace_bytes(v_out, v_src, R, A, F, T, precision) >=
+                     tc_bwd_workspace_bytes(v_out, v_src, R, A, F, T, precision)
+             ? 1 : 0;
+}
+
 extern "C" int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                             const float* w_self, const float* h, const int32_t* rot_sel,
                             const int32_t* csr_row_ptr, const int32_t* csr_entries, int32_t v_out,

@@ -282,13 +282,15 @@ extern "C" int gcb_act_grad(const float* grad, const float* out, int64_t n, int 
   return GCB_OK;
 }
 
-extern "C" int gcb_select_rot(const int32_t* argmax, const int32_t* rot_off_host, int32_t n_rot,
+extern "C" int gcb_select_rot(const int32_t* argmax, const int32_t* rot_off_host, int32_t n_rot, int32_t A,
                               int32_t v, int32_t* rot_sel, void* stream) {
   GCB_REQUIRE(argmax && rot_off_host && rot_sel, GCB_EINVAL, "gcb_select_rot: null pointer");
   GCB_REQUIRE(n_rot > 0 && n_rot <= GCB_MAX_ROT, GCB_EINVAL, "gcb_select_rot: n_rot=%d out of range", n_rot);
+  GCB_REQUIRE(A > 0, GCB_EINVAL, "gcb_select_rot: A must be positive");
   if (v <= 0) return GCB_OK;
   RotTable rot;
-  for (int i = 0; i < GCB_MAX_ROT; ++i) rot.off[i] = i < n_rot ? rot_off_host[i] : 0;
+  // any integer shift is legal for torch.roll (`orientations=`): the backward kernels expect it reduced to [0, A)
+  for (int i = 0; i < GCB_MAX_ROT; ++i) rot.off[i] = i < n_rot ? ((rot_off_host[i] % A) + A) % A : 0;
   k_select_rot<<<(unsigned)ceil_div64(v, 256), 256, 0, (cudaStream_t)stream>>>(argmax, rot, n_rot, v, rot_sel);
   GCB_LAUNCH_OK();
   return GCB_OK;

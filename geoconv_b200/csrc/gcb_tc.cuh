@@ -49,11 +49,14 @@ int tc_build_wcat(const float* w_eff, const float* w_self, int T, int R, int A, 
 
 // Backward through G[v, rotated slot, t] (gcb_tc_dx.cu): G is built once from the CSR inversion, then
 //   dSignal = G x [Weff | Wself]   and   d[Weff | Wself] = G^T x X   are two dense tcgen05 GEMMs.
+constexpr size_t TC_BUILD_G_SMEM_LIMIT = 200 * 1024;   // (R*A) x T fp32 accumulator of k_bw_build_g
 struct TcGLayout {
   size_t g_bytes, xsplit_bytes, partial_bytes, total;
   int v_pad, kg, m_pad, bn, n_ntiles, vsplit, n_kch;
 };
 TcGLayout tc_g_layout(int v_src, int R, int A, int F, int T, bool x3, bool half = false);
+// element-wise maximum of the buffer sizes over the tf32, fp16 and centre-only layouts (what the workspace provides)
+TcGLayout tc_g_layout_max(int v_src, int R, int A, int F, int T, bool x3);
 // fp16 route (half = true: `scales` = {sG, sW, sX, 1/(sG*sW), 1/(sG*sX)} on the device; g_hi / g_lo / wcat / x_hi /
 // x_lo are then __half buffers with row strides kg_ld = align(kg, 64), x_ld = align(F, 64))
 size_t tc_bwd_scales_bytes();
@@ -67,11 +70,12 @@ int tc_dx_from_g(const float* g_hi, const float* g_lo, const float* wcat_hi, con
                  const float* scales = nullptr);
 int tc_dw_from_g(const float* g_hi, const float* g_lo, const float* x, int v_src, int R, int A, int F, int T,
                  bool x3, int accumulate, float* d_w_eff, float* d_w_self, float* x_hi, float* x_lo, float* partial,
-                 cudaStream_t st, const float* scales = nullptr);
+                 size_t partial_bytes, cudaStream_t st, const float* scales = nullptr);
 
 // tensor-core backward (gcb_tc_bwd.cu)
 bool tc_bwd_supported(int R, int A, int F, int T);
 size_t tc_bwd_workspace_bytes(int v_out, int v_src, int R, int A, int F, int T, int precision);
+bool tc_bwd_layout_fits(int v_out, int v_src, int R, int A, int F, int T, int precision);
 int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
                 const float* h, const int32_t* rot_sel, const int32_t* csr_row_ptr, const int32_t* csr_entries,
                 int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,

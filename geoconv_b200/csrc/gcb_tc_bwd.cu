@@ -368,8 +368,9 @@ __global__ void k_bw_bias_final(const float* __restrict__ part, int nblocks, int
 // host side
 // =================================================================================================
 bool tc_bwd_supported(int R, int A, int F, int T) {
-  (void)R; (void)A;
   if (F % 32 != 0 || T % 32 != 0) return false;
+  // k_bw_build_g keeps the (R*A) x T accumulator of one source vertex in shared memory
+  if ((size_t)R * A * T * sizeof(float) > TC_BUILD_G_SMEM_LIMIT) return false;
   int n_t = T <= 256 ? T : 0;
   if (!n_t) {
     for (int c = 256; c >= 32; c -= 32)
@@ -421,7 +422,7 @@ static BwLayout bw_layout(int v_out, int v_src, int R, int A, int F, int T, bool
   const size_t bias_a = align_up((size_t)(L.v_pad / 32) * T * sizeof(float), 256);
   const size_t bias_b = align_up((size_t)L.bias_blocks * T * sizeof(float), 256);
   L.bias_part = bias_a > bias_b ? bias_a : bias_b;
-  L.via_g = tc_g_layout(v_src, R, A, F, T, x3).total;   // G, the split signal, the GEMM partials
+  L.via_g = tc_g_layout_max(v_src, R, A, F, T, x3).total;   // G, the split signal, the GEMM partials (any route)
   const size_t gather_route = L.recs + L.ht + L.partial;
   L.total = L.bias_part + L.wcat + (gather_route > L.via_g ? gather_route : L.via_g) + tc_bwd_scales_bytes() + 1024;
   return L;
@@ -429,6 +430,29 @@ static BwLayout bw_layout(int v_out, int v_src, int R, int A, int F, int T, bool
 
 size_t tc_bwd_workspace_bytes(int v_out, int v_src, int R, int A, int F, int T, int precision) {
   return bw_layout(v_out, v_src, R, A, F, T, precision == GCB_PREC_TF32X3 || precision == GCB_PREC_F16X3).total;
+}
+
+// Every buffer layout a backward call can choose for this shape (tf32 or fp16 operands, with or without the
+// neighbour term) against what the workspace query provides; the byte counts are recomputed here from the
+// layouts' own tile / split counts, independently of tc_g_layout_max.
+bool tc_bwd_layout_fits(int v_out, int v_src, int R, int A, int F, int T, int precision) {
+  const bool x3 = precision == GCB_PREC_TF32X3 || precision == GCB_PREC_F16X3;
+  const BwLayout L = bw_layout(v_out, v_src, R, A, F, T, x3);
+  const TcGLayout GM = tc_g_layout_max(v_src, R, A, F, T, x3);
+  const size_t fixed = L.bias_part + L.wcat + tc_bwd_scales_bytes() + 512 /* alignment of the base pointer */;
+  if (fixed + GM.g_bytes + GM.xsplit_bytes + GM.partial_bytes > L.total) return false;
+  for (int route = 0; route < 3; ++route) {
+    const bool half = route == 1;
+    if (half && !(precision == GCB_PREC_F16X3)) continue;
+    const TcGLayout G = route == 2 ? tc_g_layout(v_src, 0, 1, F, T, x3, false) : tc_g_layout(v_src, R, A, F, T, x3, half);
+    const int np = x3 ? 2 : 1;
+    const size_t g_need = half ? (size_t)2 * G.v_pad * (size_t)(ceil_div64(G.kg, 64) * 64) * 2
+                               : (size_t)np * G.v_pad * G.kg * 4;
+    const size_t x_need = half ? (size_t)2 * v_src * (size_t)(ceil_div64(F, 64) * 64) * 2 : (size_t)np * v_src * F * 4;
+    const size_t p_need = (size_t)G.vsplit * G.m_pad * F * 4;
+    if (g_need > GM.g_bytes || x_need > GM.xsplit_bytes || p_need > GM.partial_bytes) return false;
+  }
+  return true;
 }
 
 template <bool X3>
@@ -469,12 +493,13 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     // ---- centre-only layer (all-zero prior, ConvZero): G degenerates to its centre slab, h itself ----
     //   d_w_self = h^T X,  d_x = h Wself  (the same two tensor-core GEMMs with R*A = 0),  d_w_eff = 0
     const TcGLayout GL = tc_g_layout(v_src, 0, 1, F, T, x3);
+    const TcGLayout GM = tc_g_layout_max(v_src, R, A, F, T, x3);
     float* g_hi = (float*)ws;
     float* g_lo = x3 ? g_hi + (size_t)GL.v_pad * GL.kg : nullptr;
-    ws += tc_g_layout(v_src, R, A, F, T, x3).g_bytes;
+    ws += GM.g_bytes;
     float* x_hi = (float*)ws;
     float* x_lo = x3 ? x_hi + (size_t)v_src * F : nullptr;
-    ws += GL.xsplit_bytes;
+    ws += GM.xsplit_bytes;
     float* partial = (float*)ws;
     k_bw_bias_partial<<<dim3((unsigned)L.bias_blocks, (unsigned)ceil_div64(T, 32)), dim3(32, 8), 0, st>>>(
         h, v_out, T, L.bias_rows, bias_part);
@@ -484,7 +509,8 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     if (!accumulate) GCB_CUDA_OK(cudaMemsetAsync(d_w_eff, 0, (size_t)T * R * A * F * sizeof(float), st));
     k_bw_split_rows<<<(unsigned)ceil_div64((int64_t)GL.v_pad * T, 256), 256, 0, st>>>(h, v_out, GL.v_pad, T, g_hi, g_lo);
     GCB_LAUNCH_OK();
-    rc = tc_dw_from_g(g_hi, g_lo, x, v_src, 0, 1, F, T, x3, accumulate, nullptr, d_w_self, x_hi, x_lo, partial, st);
+    rc = tc_dw_from_g(g_hi, g_lo, x, v_src, 0, 1, F, T, x3, accumulate, nullptr, d_w_self, x_hi, x_lo, partial,
+                      GM.partial_bytes, st);
     if (rc || !d_x) return rc;
     rc = tc_build_wcat(nullptr, w_self, T, 0, 1, F, wc_hi, wc_lo, st);
     if (rc) return rc;
@@ -494,6 +520,7 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
   if (csr_row_ptr && csr_entries) {
     // ---- both gradients through G: dWcat = G^T X, dSignal = G Wcat (gcb_tc_dx.cu) ----
     const TcGLayout GL = tc_g_layout(v_src, R, A, F, T, x3);
+    const TcGLayout GM = tc_g_layout_max(v_src, R, A, F, T, x3);
     float* g_hi = (float*)ws;
     float* g_lo = x3 ? g_hi + (size_t)GL.v_pad * GL.kg : nullptr;
     const float* scales = nullptr;
@@ -503,10 +530,10 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
       if (rc) return rc;
       scales = (const float*)((const unsigned*)scale_scratch + 8);
     }
-    ws += GL.g_bytes;
+    ws += GM.g_bytes;
     float* x_hi = (float*)ws;
     float* x_lo = x3 ? x_hi + (size_t)v_src * F : nullptr;
-    ws += GL.xsplit_bytes;
+    ws += GM.xsplit_bytes;
     float* partial = (float*)ws;
     k_bw_bias_partial<<<dim3((unsigned)L.bias_blocks, (unsigned)ceil_div64(T, 32)), dim3(32, 8), 0, st>>>(
         h, v_out, T, L.bias_rows, bias_part);
@@ -515,8 +542,8 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     GCB_LAUNCH_OK();
     rc = tc_build_g(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, x3, g_hi, g_lo, st, scales);
     if (rc) return rc;
-    rc = tc_dw_from_g(g_hi, g_lo, x, v_src, R, A, F, T, x3, accumulate, d_w_eff, d_w_self, x_hi, x_lo, partial, st,
-                      scales);
+    rc = tc_dw_from_g(g_hi, g_lo, x, v_src, R, A, F, T, x3, accumulate, d_w_eff, d_w_self, x_hi, x_lo, partial,
+                      GM.partial_bytes, st, scales);
     if (rc || !d_x) return rc;
     rc = half ? tc_build_wcat_h(w_eff, w_self, T, R, A, F, scales + 1, (__half*)wc_hi, (__half*)wc_lo, st)
               : tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);

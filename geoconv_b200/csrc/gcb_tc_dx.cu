@@ -668,6 +668,29 @@ TcGLayout tc_g_layout(int v_src, int R, int A, int F, int T, bool x3, bool half)
   return L;
 }
 
+// Buffer sizes that serve every route tc_conv_bwd can take for this shape: the tf32 and the fp16 layouts differ in
+// their K chunking and N tile, hence in the vertex-split count of the G^T X partial sums, and the centre-only route
+// (R*A = 0) has a layout of its own.  The workspace is sized and carved with the element-wise maximum.
+TcGLayout tc_g_layout_max(int v_src, int R, int A, int F, int T, bool x3) {
+  TcGLayout L = tc_g_layout(v_src, R, A, F, T, x3, false);
+  auto widen = [&](const TcGLayout& o) {
+    if (o.g_bytes > L.g_bytes) L.g_bytes = o.g_bytes;
+    if (o.xsplit_bytes > L.xsplit_bytes) L.xsplit_bytes = o.xsplit_bytes;
+    if (o.partial_bytes > L.partial_bytes) L.partial_bytes = o.partial_bytes;
+  };
+  if (x3) {
+    TcGLayout H = tc_g_layout(v_src, R, A, F, T, true, true);
+    // fp16 G / X rows are padded to multiples of 64 halves
+    const size_t kg_ld = (size_t)ceil_div64(H.kg, 64) * 64, x_ld = (size_t)ceil_div64(F, 64) * 64;
+    H.g_bytes = align_up((size_t)2 * H.v_pad * kg_ld * sizeof(__half), 256);
+    H.xsplit_bytes = align_up((size_t)2 * v_src * x_ld * sizeof(__half), 256);
+    widen(H);
+  }
+  widen(tc_g_layout(v_src, 0, 1, F, T, x3, false));
+  L.total = L.g_bytes + L.xsplit_bytes + L.partial_bytes + 256;
+  return L;
+}
+
 int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int32_t* csr_row_ptr,
                const int32_t* csr_entries, int v_out, int v_src, int R, int A, int T, bool x3, float* g_hi,
                float* g_lo, cudaStream_t st, const float* scales) {
@@ -675,7 +698,7 @@ int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int
   const int kg = (RA + 1) * T;
   const int v_pad = (int)ceil_div64(v_src, 128) * 128;
   const size_t smem = (size_t)RA * T * sizeof(float);
-  GCB_REQUIRE(smem <= 200 * 1024, GCB_EUNSUPPORTED, "tc_build_g: R*A*T too large for the G accumulator");
+  GCB_REQUIRE(smem <= TC_BUILD_G_SMEM_LIMIT, GCB_EUNSUPPORTED, "tc_build_g: R*A*T too large for the G accumulator");
   const bool half = scales != nullptr;
   const int kg_ld = (int)ceil_div64(kg, 64) * 64;
   if (smem > 48 * 1024) {
@@ -757,12 +780,15 @@ int tc_dx_from_g(const float* g_hi, const float* g_lo, const float* wcat_hi, con
 // d_w_eff[T,R,A,F], d_w_self[T,F] (+)= G^T x X
 int tc_dw_from_g(const float* g_hi, const float* g_lo, const float* x, int v_src, int R, int A, int F, int T,
                  bool x3, int accumulate, float* d_w_eff, float* d_w_self, float* x_hi, float* x_lo, float* partial,
-                 cudaStream_t st, const float* scales) {
+                 size_t partial_bytes, cudaStream_t st, const float* scales) {
   const bool half = scales != nullptr;
   GCB_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)d_w_self % 16 == 0 && (uintptr_t)d_w_eff % 16 == 0 && F % 32 == 0 &&
                   T % 32 == 0,
               GCB_EINVAL, "tc_dw_from_g: operands must be 16-byte aligned, F and T multiples of 32");
   const TcGLayout L = tc_g_layout(v_src, R, A, F, T, x3, half);
+  GCB_REQUIRE((size_t)L.vsplit * L.m_pad * F * sizeof(float) <= partial_bytes, GCB_EWORKSPACE,
+              "tc_dw_from_g: %d vertex splits of the partial sums do not fit the %zu bytes provided", L.vsplit,
+              partial_bytes);
   CUtensorMap ah, al, bh, bl;
   int rc;
   if (half) {

@@ -43,6 +43,7 @@ def _need_cuda(t: torch.Tensor, name: str) -> None:
             "and has no CPU path - move the module and its inputs to a B200 device.")
 
 
+@torch.compiler.assume_constant_result
 def resolve_precision(mode: str, r: int, a: int, f: int, t: int, n_rot: int) -> int:
     """'fp32' = fp32-faithful: tensor cores on fp16 hi/lo splits (F % 16 == 0), else on tf32 splits (3xTF32),
     else CUDA cores; explicit tensor modes fall back to the exact CUDA-core arithmetic for shapes they cannot tile."""
@@ -66,7 +67,64 @@ def resolve_precision(mode: str, r: int, a: int, f: int, t: int, n_rot: int) -> 
 # ------------------------------------------------------------------------------------------------
 # bary -> packed (idx, w) [+ lazily the CSR inversion], cached per bary tensor object
 # ------------------------------------------------------------------------------------------------
-@dataclass
+class _IndexChecks:
+    """Deferred validation of barycentric vertex indices.
+
+    ``gcb_prep_bary`` counts the indices outside [0, V_src) on the device (and neutralises them, so the
+    kernels never read out of bounds).  Instead of reading that counter back with a blocking ``.item()``
+    per new barycentric tensor, the counter is copied to a pinned host slot behind an event; every later
+    layer call / backward polls the finished events (no host sync) and raises IndexError for a tensor that
+    held bad indices - the same deferred reporting CUDA itself uses for asynchronous errors.
+    ``BaryPack.validate()`` blocks until the answer is known."""
+
+    SLOTS = 512
+
+    def __init__(self):
+        self._host = None
+        self._next = 0
+        self._pending: list[tuple] = []   # (event, slot, v_src, weakref to the pack)
+
+    def submit(self, pack: "BaryPack", oob: torch.Tensor) -> None:
+        if torch.cuda.is_current_stream_capturing():
+            return                       # a captured step cannot report back to the host
+        if self._host is None:
+            self._host = torch.zeros(self.SLOTS, dtype=torch.int32).pin_memory()
+        if len(self._pending) >= self.SLOTS:
+            self.poll(block=True)
+        slot = self._next
+        self._next = (self._next + 1) % self.SLOTS
+        self._host[slot:slot + 1].copy_(oob, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(oob.device))
+        self._pending.append((ev, slot, pack.v_src, weakref.ref(pack)))
+
+    def poll(self, block: bool = False, only: "BaryPack | None" = None) -> None:
+        if not self._pending:
+            return
+        keep, bad = [], None
+        for item in self._pending:
+            ev, slot, v_src, ref = item
+            mine = only is None or ref() is only
+            if mine and block:
+                ev.synchronize()
+            if mine and ev.query():
+                n = int(self._host[slot])
+                pk = ref()
+                if pk is not None:
+                    pk.oob_count = n
+                if n and bad is None:
+                    bad = (n, v_src)
+            else:
+                keep.append(item)
+        self._pending = keep
+        if bad is not None:
+            raise IndexError(f"geoconv_b200: {bad[0]} barycentric vertex indices fall outside [0, {bad[1]})")
+
+
+INDEX_CHECKS = _IndexChecks()
+
+
+@dataclass(eq=False)
 class BaryPack:
     idx: torch.Tensor          # int32 [V_out,R,A,3]
     w: torch.Tensor            # fp32  [V_out,R,A,3]
@@ -74,7 +132,14 @@ class BaryPack:
     v_src: int
     r: int
     a: int
+    oob_count: int | None = None          # out-of-range indices found by gcb_prep_bary (None: not read back yet)
     _csr: tuple | None = field(default=None, repr=False)
+
+    def validate(self) -> None:
+        """Block until the index check of this tensor is known; raises IndexError if it failed."""
+        INDEX_CHECKS.poll(block=True, only=self)
+        if self.oob_count:
+            raise IndexError(f"geoconv_b200: {self.oob_count} barycentric vertex indices fall outside [0, {self.v_src})")
 
     def csr(self):
         """(row_ptr int32 [V_src+1], entries int32 [n_slots]) - built on first backward."""
@@ -94,34 +159,39 @@ class BaryPack:
         return self._csr
 
 
-def prep_bary(bary: torch.Tensor, v_src: int, check_indices: bool = True) -> BaryPack:
+def prep_bary(bary: torch.Tensor, v_src: int, check_indices: bool | str = True) -> BaryPack:
     """Split a (V,R,A,3,2) barycentric tensor (fp32 or fp64) into int32 indices and fp32 weights.
 
     Same arithmetic as the reference: cast to fp32, truncate the index column toward zero.
-    With ``check_indices`` an out-of-range index raises IndexError (one host sync per *new* bary
-    tensor; the reference's CPU gather raises too, its CUDA gather is undefined behaviour).
+    Out-of-range indices (the reference's CPU gather raises on them, its CUDA gather is undefined
+    behaviour) are counted on the device and neutralised (index 0, weight 0).  ``check_indices=True``
+    reports them WITHOUT a host sync: the counter travels to pinned host memory behind an event and the
+    next layer call / backward that finds the event finished raises IndexError (``BaryPack.validate()``
+    waits for it); ``check_indices="sync"`` raises here, at the price of one host sync per new tensor;
+    ``False`` skips the report.
     """
     _need_cuda(bary, "barycentric coordinates")
     if bary.dim() != 5 or bary.shape[3] != 3 or bary.shape[4] != 2:
         raise ValueError(f"barycentric coordinates must have shape (V,R,A,3,2), got {tuple(bary.shape)}")
     if bary.dtype not in (torch.float32, torch.float64):
         bary = bary.to(torch.float32)
-    bary = bary.contiguous()
     v, r, a = bary.shape[:3]
-    lib = N.load()
-    idx = torch.empty((v, r, a, 3), dtype=torch.int32, device=bary.device)
-    w = torch.empty((v, r, a, 3), dtype=torch.float32, device=bary.device)
-    oob = torch.zeros(1, dtype=torch.int32, device=bary.device)
-    if idx.numel():
-        with torch.cuda.device(bary.device):
-            N.check(lib.gcb_prep_bary(bary.data_ptr(), int(bary.dtype == torch.float64), idx.numel(), v_src,
-                                      idx.data_ptr(), w.data_ptr(), oob.data_ptr(), _stream(bary)),
-                    "gcb_prep_bary")
-        if check_indices:
-            bad = int(oob.item())
-            if bad:
-                raise IndexError(f"geoconv_b200: {bad} barycentric vertex indices fall outside [0, {v_src})")
-    return BaryPack(idx=idx, w=w, v_out=v, v_src=v_src, r=r, a=a)
+    idx, w, oob = prep_bary_op(bary, v_src)
+    pack = BaryPack(idx=idx, w=w, v_out=v, v_src=v_src, r=r, a=a)
+    _PACK_OF_IDX[idx.data_ptr()] = pack
+    if idx.numel() and check_indices:
+        INDEX_CHECKS.submit(pack, oob)
+        if check_indices == "sync":
+            pack.validate()
+    return pack
+
+
+def prep_bary_traced(bary: torch.Tensor, v_src: int) -> BaryPack:
+    """The split inside a torch.compile trace: one operator call, no cache, no host-side report."""
+    if bary.dtype not in (torch.float32, torch.float64):
+        bary = bary.to(torch.float32)
+    idx, w, _oob = prep_bary_op(bary, v_src)
+    return BaryPack(idx=idx, w=w, v_out=bary.shape[0], v_src=v_src, r=bary.shape[1], a=bary.shape[2])
 
 
 class BaryCache:
@@ -153,230 +223,371 @@ class BaryCache:
 GLOBAL_BARY_CACHE = BaryCache()
 
 
-# ------------------------------------------------------------------------------------------------
-# prior folding  W[T,R,A,F] x K[R,A,R,A] -> Weff
-# ------------------------------------------------------------------------------------------------
-def _fold(inp: torch.Tensor, prior: torch.Tensor, transpose: int) -> torch.Tensor:
+# ================================================================================================
+# torch.library operators (namespace ``geoconv_b200``)
+#
+# Every compute entry point of the C ABI is registered as a custom operator with a fake (meta) kernel
+# and an autograd formula, so a model that uses the drop-in layers traces under torch.compile with
+# ``fullgraph=True`` (the reference demo compiles its model, training_demo.py:126-127) and the eager
+# path and the compiled path run the same code.  The operator bodies only move pointers across the ABI.
+# ================================================================================================
+_LIB = "geoconv_b200"
+
+
+def _dev_guard(t: torch.Tensor):
+    return torch.cuda.device(t.device)
+
+
+@torch.library.custom_op(f"{_LIB}::prep_bary", mutates_args=(), device_types="cuda")
+def prep_bary_op(bary: torch.Tensor, v_src: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(V,R,A,3,2) fp32/fp64 -> idx int32 (V,R,A,3), w fp32 (V,R,A,3), out-of-range counter int32 (1,)."""
     lib = N.load()
+    bary = bary.contiguous()
+    v, r, a = bary.shape[:3]
+    idx = torch.empty((v, r, a, 3), dtype=torch.int32, device=bary.device)
+    w = torch.empty((v, r, a, 3), dtype=torch.float32, device=bary.device)
+    oob = torch.zeros(1, dtype=torch.int32, device=bary.device)
+    if idx.numel():
+        with _dev_guard(bary):
+            N.check(lib.gcb_prep_bary(bary.data_ptr(), int(bary.dtype == torch.float64), idx.numel(), v_src,
+                                      idx.data_ptr(), w.data_ptr(), oob.data_ptr(), _stream(bary)),
+                    "gcb_prep_bary")
+    return idx, w, oob
+
+
+@prep_bary_op.register_fake
+def _(bary, v_src):
+    v, r, a = bary.shape[:3]
+    return (bary.new_empty((v, r, a, 3), dtype=torch.int32), bary.new_empty((v, r, a, 3), dtype=torch.float32),
+            bary.new_empty((1,), dtype=torch.int32))
+
+
+@torch.library.custom_op(f"{_LIB}::csr_build", mutates_args=(), device_types="cuda")
+def csr_build_op(idx: torch.Tensor, w: torch.Tensor, v_src: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Neighbour -> vertex inversion: (row_ptr int32 [V_src+1], entries int32 [n_slots])."""
+    lib = N.load()
+    n_slots = idx.numel()
+    dev = idx.device
+    row_ptr = torch.empty(v_src + 1, dtype=torch.int32, device=dev)
+    entries = torch.empty(n_slots, dtype=torch.int32, device=dev)
+    ws_bytes = lib.gcb_csr_workspace_bytes(n_slots, v_src)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with _dev_guard(idx):
+        N.check(lib.gcb_csr_build(idx.data_ptr(), w.data_ptr(), n_slots, v_src, row_ptr.data_ptr(),
+                                  entries.data_ptr(), ws.data_ptr(), ws_bytes, _stream(idx)), "gcb_csr_build")
+    return row_ptr, entries
+
+
+@csr_build_op.register_fake
+def _(idx, w, v_src):
+    return idx.new_empty((v_src + 1,), dtype=torch.int32), idx.new_empty((idx.numel(),), dtype=torch.int32)
+
+
+# ---- prior folding  W[T,R,A,F] x K[R,A,R,A] -> Weff -------------------------------------------
+@torch.library.custom_op(f"{_LIB}::fold_prior", mutates_args=(), device_types="cuda")
+def fold_prior_op(inp: torch.Tensor, prior: torch.Tensor, transpose: int) -> torch.Tensor:
+    lib = N.load()
+    inp = inp.contiguous()
+    prior = prior.contiguous()
     t, r, a, f = inp.shape
     out = torch.empty_like(inp)
-    with torch.cuda.device(inp.device):
+    with _dev_guard(inp):
         N.check(lib.gcb_fold_prior(inp.data_ptr(), prior.data_ptr(), out.data_ptr(), t, r, a, f, transpose,
                                    _stream(inp)), "gcb_fold_prior")
     return out
 
 
-class FoldPrior(torch.autograd.Function):
+@fold_prior_op.register_fake
+def _(inp, prior, transpose):
+    return torch.empty_like(inp, memory_format=torch.contiguous_format)
+
+
+def _fold_setup(ctx, inputs, output):
+    _inp, prior, transpose = inputs
+    ctx.save_for_backward(prior)
+    ctx.transpose = transpose
+
+
+def _fold_backward(ctx, grad):
+    (prior,) = ctx.saved_tensors
+    return fold_prior_op(grad, prior, 1 - ctx.transpose), None, None
+
+
+fold_prior_op.register_autograd(_fold_backward, setup_context=_fold_setup)
+
+
+class FoldPrior:
+    """``FoldPrior.apply(W, K)`` -> Weff (differentiable in W)."""
+
     @staticmethod
-    def forward(ctx, w_neighbor, prior):
+    def apply(w_neighbor: torch.Tensor, prior: torch.Tensor) -> torch.Tensor:
         _need_cuda(w_neighbor, "template weights")
-        prior = prior.to(device=w_neighbor.device, dtype=torch.float32).contiguous()
-        ctx.save_for_backward(prior)
-        return _fold(w_neighbor.contiguous(), prior, 0)
-
-    @staticmethod
-    def backward(ctx, grad):
-        (prior,) = ctx.saved_tensors
-        return _fold(grad.contiguous(), prior, 1), None
+        return fold_prior_op(w_neighbor, prior.to(device=w_neighbor.device, dtype=torch.float32), 0)
 
 
-# ------------------------------------------------------------------------------------------------
-# the convolution (+ fused pooling outputs)
-# ------------------------------------------------------------------------------------------------
-class ConvIntrinsicFn(torch.autograd.Function):
-    """(signal, Weff|None, Wself, bias) -> (Y [V,n_rot,T], Z [V,T], argmax [V]).
+# ---- the convolution (+ fused pooling outputs) --------------------------------------------------
+@torch.library.custom_op(f"{_LIB}::conv_fwd", mutates_args=(), device_types="cuda")
+def conv_fwd_op(signal: torch.Tensor, w_eff: torch.Tensor | None, w_self: torch.Tensor, bias: torch.Tensor,
+                idx: torch.Tensor, w: torch.Tensor, w_anchor: torch.Tensor | None, rot: list[int], act_id: int,
+                prec_fwd: int, prec_bwd: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(signal, Weff|None, Wself, bias) -> (Y [V,n_rot,T], Z [V,T], argmax [V]): ConvIntrinsic.forward and the
+    AngularMaxPooling of its result in one pass (include/geoconv_b200.h: gcb_conv_fwd).  `w_anchor`: the
+    neighbour weights of an all-zero-prior layer (they take no part, but receive an all-zeros gradient)."""
+    lib = N.load()
+    x = signal.contiguous()
+    v_src, f = x.shape
+    v_out, r, a = idx.shape[:3]
+    t = w_self.shape[0]
+    n_rot = len(rot)
+    dev = x.device
+    w_self_c = w_self.reshape(t, f).contiguous()
+    bias_c = bias.reshape(t).contiguous()
+    w_eff_c = None if w_eff is None else w_eff.contiguous()
+    y = torch.empty((v_out, n_rot, t), dtype=torch.float32, device=dev)
+    z = torch.empty((v_out, t), dtype=torch.float32, device=dev)
+    arg = torch.empty((v_out,), dtype=torch.int32, device=dev)
+    ws_bytes = lib.gcb_conv_fwd_workspace_bytes(v_out, v_src, r, a, f, t, n_rot, prec_fwd)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with _dev_guard(x):
+        N.check(lib.gcb_conv_fwd(x.data_ptr(), idx.data_ptr(), w.data_ptr(), _ptr(w_eff_c), w_self_c.data_ptr(),
+                                 bias_c.data_ptr(), N.rot_array(rot), n_rot, v_out, v_src, r, a, f, t, act_id,
+                                 prec_fwd, y.data_ptr(), z.data_ptr(), arg.data_ptr(), None, ws.data_ptr(),
+                                 ws_bytes, _stream(x)), "gcb_conv_fwd")
+    return y, z, arg
 
-    Y is the layer output; Z/argmax are what AngularMaxPooling would produce from it.  In backward,
-    a gradient arriving only through Z takes the AMP-sparse route (one rotation per vertex); a
-    gradient arriving through Y is back-propagated one rotation at a time.
-    """
 
-    @staticmethod
-    def forward(ctx, signal, w_eff, w_self, bias, pack: BaryPack, rot_offsets, act_id, precision, w_anchor=None):
-        lib = N.load()
-        _need_cuda(signal, "signal")
-        # `precision` is one code for both directions or a (forward, backward) pair
-        precision, precision_bwd = precision if isinstance(precision, tuple) else (precision, precision)
-        x = signal.contiguous()
-        v_src, f = x.shape
-        t = w_self.shape[0]
-        n_rot = len(rot_offsets)
-        dev = x.device
-        w_self_c = w_self.reshape(t, f).contiguous()
-        bias_c = bias.reshape(t).contiguous()
-        w_eff_c = None if w_eff is None else w_eff.contiguous()
-        y = torch.empty((pack.v_out, n_rot, t), dtype=torch.float32, device=dev)
-        z = torch.empty((pack.v_out, t), dtype=torch.float32, device=dev)
-        arg = torch.empty((pack.v_out,), dtype=torch.int32, device=dev)
-        rot = N.rot_array(rot_offsets)
-        # Training: let the tensor-core forward keep the interpolations I [V,R,A,F] (the reference
-        # materialises the same tensor) so the backward's dW contraction reads them back instead of
-        # gathering three signal rows per template vertex again.
-        keep = (SAVE_INTERPOLATIONS and w_eff_c is not None and precision != N.PREC_FP32
-                and precision_bwd != N.PREC_FP32 and any(ctx.needs_input_grad[:4]))
-        interp = torch.empty((pack.v_out, pack.r * pack.a * f), dtype=torch.float32, device=dev) if keep else None
-        ws_bytes = lib.gcb_conv_fwd_workspace_bytes(pack.v_out, v_src, pack.r, pack.a, f, t, n_rot, precision)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
-            N.check(lib.gcb_conv_fwd(x.data_ptr(), pack.idx.data_ptr(), pack.w.data_ptr(), _ptr(w_eff_c),
-                                     w_self_c.data_ptr(), bias_c.data_ptr(), rot, n_rot, pack.v_out, v_src,
-                                     pack.r, pack.a, f, t, act_id, precision, y.data_ptr(), z.data_ptr(),
-                                     arg.data_ptr(), _ptr(interp), ws.data_ptr(), ws_bytes, _stream(x)),
-                    "gcb_conv_fwd")
-        ctx.pack = pack
-        ctx.rot_offsets = tuple(int(o) for o in rot_offsets)
-        ctx.act_id = act_id
-        ctx.precision = precision_bwd
-        ctx.has_neighbor = w_eff is not None
-        # all-zero prior: the neighbour weights still receive an all-zeros gradient, like the reference
-        ctx.anchor_shape = None if w_anchor is None else tuple(w_anchor.shape)
-        ctx.w_self_shape = tuple(w_self.shape)
-        ctx.bias_shape = tuple(bias.shape)
-        ctx.has_interp = interp is not None
-        ctx.save_for_backward(x, w_eff_c if w_eff_c is not None else x.new_empty(0), w_self_c, y, z, arg,
-                              interp if interp is not None else x.new_empty(0))
-        ctx.mark_non_differentiable(arg)
-        ctx.set_materialize_grads(False)
-        return y, z, arg
+@conv_fwd_op.register_fake
+def _(signal, w_eff, w_self, bias, idx, w, w_anchor, rot, act_id, prec_fwd, prec_bwd):
+    v_out, t = idx.shape[0], w_self.shape[0]
+    return (signal.new_empty((v_out, len(rot), t), dtype=torch.float32),
+            signal.new_empty((v_out, t), dtype=torch.float32), signal.new_empty((v_out,), dtype=torch.int32))
 
-    @staticmethod
-    def backward(ctx, grad_y, grad_z, _grad_arg):
-        lib = N.load()
-        x, w_eff, w_self, y, z, arg, interp = ctx.saved_tensors
-        interp_ptr = interp.data_ptr() if ctx.has_interp else None
-        pack: BaryPack = ctx.pack
-        has_nb = ctx.has_neighbor
-        v_src, f = x.shape
-        t = w_self.shape[0]
-        dev = x.device
-        n_rot = len(ctx.rot_offsets)
-        need_dx = ctx.needs_input_grad[0]
-        if grad_y is None and grad_z is None:
-            return (None,) * 9
-        d_x = torch.empty_like(x) if need_dx else None
-        d_w_eff = torch.empty((t, pack.r, pack.a, f), dtype=torch.float32, device=dev)
-        d_w_self = torch.empty((t, f), dtype=torch.float32, device=dev)
-        d_bias = torch.empty((t,), dtype=torch.float32, device=dev)
-        ws_bytes = lib.gcb_conv_bwd_workspace_bytes(pack.v_out, v_src, pack.r, pack.a, f, t, ctx.precision)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        # the CSR inversion also feeds the weight gradients (dW = G^T X on tensor cores), not only dSignal
-        row_ptr, entries = pack.csr() if has_nb else (None, None)
-        h = torch.empty((pack.v_out, t), dtype=torch.float32, device=dev)
-        rot_sel = torch.empty((pack.v_out,), dtype=torch.int32, device=dev)
-        st = _stream(x)
-        rot = N.rot_array(ctx.rot_offsets)
-        calls = 0
 
-        def run(accumulate):
-            N.check(lib.gcb_conv_bwd(x.data_ptr(), pack.idx.data_ptr(), pack.w.data_ptr(),
-                                     w_eff.data_ptr() if has_nb else None, w_self.data_ptr(), h.data_ptr(),
-                                     rot_sel.data_ptr(), _ptr(row_ptr), _ptr(entries), pack.v_out, v_src,
-                                     pack.r, pack.a, f, t, ctx.precision, accumulate, interp_ptr, _ptr(d_x),
-                                     d_w_eff.data_ptr(), d_w_self.data_ptr(), d_bias.data_ptr(),
-                                     ws.data_ptr(), ws_bytes, st), "gcb_conv_bwd")
+@torch.library.custom_op(f"{_LIB}::conv_bwd", mutates_args=(), device_types="cuda")
+def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: torch.Tensor,
+                w_eff: torch.Tensor | None, w_self: torch.Tensor, y: torch.Tensor, z: torch.Tensor,
+                arg: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, row_ptr: torch.Tensor | None,
+                entries: torch.Tensor | None, rot: list[int], act_id: int, precision: int,
+                need_dx: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Backward of conv_fwd: a gradient arriving through Z takes the AMP-sparse route (one rotation per
+    vertex), a gradient arriving through Y is back-propagated one rotation at a time.
+    Returns (dSignal [V_src,F] or an empty tensor, dWeff [T,R,A,F], dWself [T,F], dbias [T])."""
+    lib = N.load()
+    v_src, f = x.shape
+    v_out, r, a = idx.shape[:3]
+    t = w_self.shape[0]
+    dev = x.device
+    n_rot = len(rot)
+    has_nb = w_eff is not None
+    d_x = torch.empty_like(x) if need_dx else None
+    d_w_eff = torch.empty((t, r, a, f), dtype=torch.float32, device=dev)
+    d_w_self = torch.empty((t, f), dtype=torch.float32, device=dev)
+    d_bias = torch.empty((t,), dtype=torch.float32, device=dev)
+    ws_bytes = lib.gcb_conv_bwd_workspace_bytes(v_out, v_src, r, a, f, t, precision)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    h = torch.empty((v_out, t), dtype=torch.float32, device=dev)
+    rot_sel = torch.empty((v_out,), dtype=torch.int32, device=dev)
+    st = _stream(x)
+    rot_c = N.rot_array(rot)
+    calls = 0
 
-        with torch.cuda.device(dev):
-            if grad_z is not None:
-                gz = grad_z.contiguous().to(torch.float32)
-                N.check(lib.gcb_act_grad(gz.data_ptr(), z.data_ptr(), gz.numel(), ctx.act_id, h.data_ptr(), st),
+    def run(accumulate):
+        N.check(lib.gcb_conv_bwd(x.data_ptr(), idx.data_ptr(), w.data_ptr(), _ptr(w_eff) if has_nb else None,
+                                 w_self.data_ptr(), h.data_ptr(), rot_sel.data_ptr(), _ptr(row_ptr), _ptr(entries),
+                                 v_out, v_src, r, a, f, t, precision, accumulate, None, _ptr(d_x),
+                                 d_w_eff.data_ptr(), d_w_self.data_ptr(), d_bias.data_ptr(), ws.data_ptr(),
+                                 ws_bytes, st), "gcb_conv_bwd")
+
+    with _dev_guard(x):
+        if grad_z is not None:
+            gz = grad_z.contiguous().to(torch.float32)
+            N.check(lib.gcb_act_grad(gz.data_ptr(), z.data_ptr(), gz.numel(), act_id, h.data_ptr(), st), "gcb_act_grad")
+            N.check(lib.gcb_select_rot(arg.data_ptr(), rot_c, n_rot, a, v_out, rot_sel.data_ptr(), st),
+                    "gcb_select_rot")
+            run(0)
+            calls += 1
+        if grad_y is not None:
+            gy = grad_y.to(torch.float32)
+            for i, off in enumerate(rot):
+                gi = gy[:, i, :].contiguous()
+                yi = y[:, i, :].contiguous()
+                N.check(lib.gcb_act_grad(gi.data_ptr(), yi.data_ptr(), gi.numel(), act_id, h.data_ptr(), st),
                         "gcb_act_grad")
-                N.check(lib.gcb_select_rot(arg.data_ptr(), rot, n_rot, pack.v_out, rot_sel.data_ptr(), st),
-                        "gcb_select_rot")
-                run(0)
+                rot_sel.fill_(off % a)
+                run(1 if calls else 0)
                 calls += 1
-            if grad_y is not None:
-                gy = grad_y.to(torch.float32)
-                for i, off in enumerate(ctx.rot_offsets):
-                    gi = gy[:, i, :].contiguous()
-                    yi = y[:, i, :].contiguous()
-                    N.check(lib.gcb_act_grad(gi.data_ptr(), yi.data_ptr(), gi.numel(), ctx.act_id, h.data_ptr(),
-                                             st), "gcb_act_grad")
-                    rot_sel.fill_(off % pack.a)
-                    run(1 if calls else 0)
-                    calls += 1
-        g_w_eff = d_w_eff if has_nb else None
-        g_anchor = None if ctx.anchor_shape is None else torch.zeros(ctx.anchor_shape, dtype=torch.float32, device=dev)
-        return (d_x, g_w_eff, d_w_self.reshape(ctx.w_self_shape), d_bias.reshape(ctx.bias_shape),
-                None, None, None, None, g_anchor)
+    if d_x is None:
+        d_x = x.new_empty((0,))
+    return d_x, d_w_eff, d_w_self, d_bias
 
 
-# ------------------------------------------------------------------------------------------------
-# stand-alone AngularMaxPooling on a materialised tensor
-# ------------------------------------------------------------------------------------------------
-class AngularMaxPoolFn(torch.autograd.Function):
+@conv_bwd_op.register_fake
+def _(grad_y, grad_z, x, w_eff, w_self, y, z, arg, idx, w, row_ptr, entries, rot, act_id, precision, need_dx):
+    v_out, r, a = idx.shape[:3]
+    t, f = w_self.shape[0], x.shape[1]
+    return (torch.empty_like(x) if need_dx else x.new_empty((0,)), x.new_empty((t, r, a, f)), x.new_empty((t, f)),
+            x.new_empty((t,)))
+
+
+# idx tensor -> BaryPack that owns it (eager mode: the CSR inversion is built once per barycentric tensor)
+_PACK_OF_IDX: "weakref.WeakValueDictionary[int, BaryPack]" = weakref.WeakValueDictionary()
+
+
+def _csr_for(idx: torch.Tensor, w: torch.Tensor, v_src: int):
+    from torch._subclasses.fake_tensor import is_fake
+    if not is_fake(idx):
+        pack = _PACK_OF_IDX.get(idx.data_ptr())
+        if pack is not None and pack.v_src == v_src and pack.idx.data_ptr() == idx.data_ptr():
+            return pack.csr()
+    return csr_build_op(idx, w, v_src)
+
+
+def _conv_setup(ctx, inputs, output):
+    signal, w_eff, w_self, bias, idx, w, w_anchor, rot, act_id, _prec_fwd, prec_bwd = inputs
+    y, z, arg = output
+    ctx.rot = [int(o) for o in rot]
+    ctx.act_id = act_id
+    ctx.precision = prec_bwd
+    ctx.has_neighbor = w_eff is not None
+    ctx.has_anchor = w_anchor is not None
+    ctx.anchor_shape = None if w_anchor is None else tuple(w_anchor.shape)
+    ctx.w_self_shape = tuple(w_self.shape)
+    ctx.bias_shape = tuple(bias.shape)
+    t, f = w_self.shape[0], signal.shape[1]
+    ctx.save_for_backward(signal, w_eff if w_eff is not None else signal.new_empty((0,)),
+                          w_self.reshape(t, f), y, z, arg, idx, w)
+    ctx.set_materialize_grads(False)
+
+
+def _conv_backward(ctx, grad_y, grad_z, _grad_arg):
+    x, w_eff, w_self, y, z, arg, idx, w = ctx.saved_tensors
+    if grad_y is None and grad_z is None:
+        return (None,) * 11
+    INDEX_CHECKS.poll()
+    has_nb = ctx.has_neighbor
+    need_dx = bool(ctx.needs_input_grad[0])
+    # the CSR inversion also feeds the weight gradients (dW = G^T X on tensor cores), not only dSignal
+    row_ptr, entries = _csr_for(idx, w, x.shape[0]) if has_nb else (None, None)
+    d_x, d_w_eff, d_w_self, d_bias = conv_bwd_op(grad_y, grad_z, x.contiguous(), w_eff if has_nb else None, w_self, y, z,
+                                                 arg, idx, w, row_ptr, entries, ctx.rot, ctx.act_id, ctx.precision,
+                                                 need_dx)
+    g_anchor = torch.zeros(ctx.anchor_shape, dtype=torch.float32, device=x.device) if ctx.has_anchor else None
+    return (d_x if need_dx else None, d_w_eff if has_nb else None, d_w_self.reshape(ctx.w_self_shape),
+            d_bias.reshape(ctx.bias_shape), None, None, g_anchor, None, None, None, None)
+
+
+conv_fwd_op.register_autograd(_conv_backward, setup_context=_conv_setup)
+
+
+class ConvIntrinsicFn:
+    """``apply(signal, Weff|None, Wself, bias, pack, rot_offsets, act_id, precision, w_anchor=None)``
+    -> (Y, Z, argmax).  `precision` is one C-ABI code for both directions or a (forward, backward) pair."""
+
     @staticmethod
-    def forward(ctx, y):
-        lib = N.load()
-        _need_cuda(y, "inputs")
-        yc = y.contiguous().to(torch.float32)
-        v, n_rot, t = yc.shape
-        z = torch.empty((v, t), dtype=torch.float32, device=yc.device)
-        arg = torch.empty((v,), dtype=torch.int32, device=yc.device)
-        with torch.cuda.device(yc.device):
-            N.check(lib.gcb_amp_fwd(yc.data_ptr(), v, n_rot, t, z.data_ptr(), arg.data_ptr(), _stream(yc)),
-                    "gcb_amp_fwd")
-        ctx.save_for_backward(arg)
-        ctx.shape = (v, n_rot, t)
-        ctx.mark_non_differentiable(arg)
-        return z, arg
-
-    @staticmethod
-    def backward(ctx, grad_z, _):
-        lib = N.load()
-        (arg,) = ctx.saved_tensors
-        v, n_rot, t = ctx.shape
-        gz = grad_z.contiguous().to(torch.float32)
-        gy = torch.empty((v, n_rot, t), dtype=torch.float32, device=gz.device)
-        with torch.cuda.device(gz.device):
-            N.check(lib.gcb_amp_bwd(gz.data_ptr(), arg.data_ptr(), v, n_rot, t, gy.data_ptr(), _stream(gz)),
-                    "gcb_amp_bwd")
-        return gy
+    def apply(signal, w_eff, w_self, bias, pack: BaryPack, rot_offsets, act_id, precision, w_anchor=None):
+        _need_cuda(signal, "signal")
+        prec_fwd, prec_bwd = precision if isinstance(precision, tuple) else (precision, precision)
+        return conv_fwd_op(signal, w_eff, w_self, bias, pack.idx, pack.w, w_anchor, [int(o) for o in rot_offsets],
+                           act_id, prec_fwd, prec_bwd)
 
 
+# ---- angular poolings on a materialised tensor ---------------------------------------------------
 POOL_MAX, POOL_MIN, POOL_AVG = 0, 1, 2
 
 
-class AngularPoolFn(torch.autograd.Function):
-    """Angular max / min / average pooling of a materialised (V, n_rot, T) tensor."""
-
-    @staticmethod
-    def forward(ctx, y, mode):
-        lib = N.load()
-        _need_cuda(y, "inputs")
-        yc = y.contiguous().to(torch.float32)
-        v, n_rot, t = yc.shape
-        z = torch.empty((v, t), dtype=torch.float32, device=yc.device)
-        arg = torch.empty((v,), dtype=torch.int32, device=yc.device)
-        with torch.cuda.device(yc.device):
+@torch.library.custom_op(f"{_LIB}::apool_fwd", mutates_args=(), device_types="cuda")
+def apool_fwd_op(y: torch.Tensor, mode: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Angular max / min / average pooling of (V, n_rot, T): (Z (V,T), selected rotation int32 (V,))."""
+    lib = N.load()
+    yc = y.contiguous().to(torch.float32)
+    v, n_rot, t = yc.shape
+    z = torch.empty((v, t), dtype=torch.float32, device=yc.device)
+    arg = torch.empty((v,), dtype=torch.int32, device=yc.device)
+    with _dev_guard(yc):
+        if mode == POOL_MAX:
+            N.check(lib.gcb_amp_fwd(yc.data_ptr(), v, n_rot, t, z.data_ptr(), arg.data_ptr(), _stream(yc)), "gcb_amp_fwd")
+        else:
             N.check(lib.gcb_apool_fwd(yc.data_ptr(), v, n_rot, t, mode, z.data_ptr(), arg.data_ptr(), _stream(yc)),
                     "gcb_apool_fwd")
-        ctx.save_for_backward(arg)
-        ctx.shape = (v, n_rot, t)
-        ctx.mode = mode
-        ctx.mark_non_differentiable(arg)
-        return z, arg
+    return z, arg
+
+
+@apool_fwd_op.register_fake
+def _(y, mode):
+    v, _n_rot, t = y.shape
+    return y.new_empty((v, t), dtype=torch.float32), y.new_empty((v,), dtype=torch.int32)
+
+
+@torch.library.custom_op(f"{_LIB}::apool_bwd", mutates_args=(), device_types="cuda")
+def apool_bwd_op(grad_z: torch.Tensor, arg: torch.Tensor, n_rot: int, mode: int) -> torch.Tensor:
+    lib = N.load()
+    gz = grad_z.contiguous().to(torch.float32)
+    v, t = gz.shape
+    gy = torch.empty((v, n_rot, t), dtype=torch.float32, device=gz.device)
+    with _dev_guard(gz):
+        if mode == POOL_MAX:
+            N.check(lib.gcb_amp_bwd(gz.data_ptr(), arg.data_ptr(), v, n_rot, t, gy.data_ptr(), _stream(gz)), "gcb_amp_bwd")
+        else:
+            N.check(lib.gcb_apool_bwd(gz.data_ptr(), arg.data_ptr(), v, n_rot, t, mode, gy.data_ptr(), _stream(gz)),
+                    "gcb_apool_bwd")
+    return gy
+
+
+@apool_bwd_op.register_fake
+def _(grad_z, arg, n_rot, mode):
+    v, t = grad_z.shape
+    return grad_z.new_empty((v, n_rot, t), dtype=torch.float32)
+
+
+def _apool_setup(ctx, inputs, output):
+    y, mode = inputs
+    ctx.save_for_backward(output[1])
+    ctx.n_rot = y.shape[1]
+    ctx.mode = mode
+
+
+def _apool_backward(ctx, grad_z, _grad_arg):
+    (arg,) = ctx.saved_tensors
+    return apool_bwd_op(grad_z, arg, ctx.n_rot, ctx.mode), None
+
+
+apool_fwd_op.register_autograd(_apool_backward, setup_context=_apool_setup)
+
+
+class AngularPoolFn:
+    """``apply(y, mode)`` -> (Z, selected rotation); mode = POOL_MAX / POOL_MIN / POOL_AVG."""
 
     @staticmethod
-    def backward(ctx, grad_z, _):
-        lib = N.load()
-        (arg,) = ctx.saved_tensors
-        v, n_rot, t = ctx.shape
-        gz = grad_z.contiguous().to(torch.float32)
-        gy = torch.empty((v, n_rot, t), dtype=torch.float32, device=gz.device)
-        with torch.cuda.device(gz.device):
-            N.check(lib.gcb_apool_bwd(gz.data_ptr(), arg.data_ptr(), v, n_rot, t, ctx.mode, gy.data_ptr(),
-                                      _stream(gz)), "gcb_apool_bwd")
-        return gy, None
+    def apply(y, mode):
+        _need_cuda(y, "inputs")
+        return apool_fwd_op(y, mode)
+
+
+class AngularMaxPoolFn:
+    @staticmethod
+    def apply(y):
+        _need_cuda(y, "inputs")
+        return apool_fwd_op(y, POOL_MAX)
+
+
+@torch.library.custom_op(f"{_LIB}::pack_rows", mutates_args=(), device_types="cuda")
+def pack_rows_op(src: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    lib = N.load()
+    src = src.contiguous()
+    rows = rows.to(device=src.device, dtype=torch.int32).contiguous()
+    out = torch.empty((rows.numel(), src.shape[1]), dtype=torch.float32, device=src.device)
+    with _dev_guard(src):
+        N.check(lib.gcb_pack_rows(src.data_ptr(), rows.data_ptr(), rows.numel(), src.shape[1], out.data_ptr(),
+                                  _stream(src)), "gcb_pack_rows")
+    return out
+
+
+@pack_rows_op.register_fake
+def _(src, rows):
+    return src.new_empty((rows.numel(), src.shape[1]), dtype=torch.float32)
 
 
 def pack_rows(src: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
     """out[i] = src[rows[i]] (halo send-buffer packing)."""
-    lib = N.load()
     _need_cuda(src, "src")
-    src = src.contiguous()
-    rows = rows.to(device=src.device, dtype=torch.int32).contiguous()
-    out = torch.empty((rows.numel(), src.shape[1]), dtype=torch.float32, device=src.device)
-    with torch.cuda.device(src.device):
-        N.check(lib.gcb_pack_rows(src.data_ptr(), rows.data_ptr(), rows.numel(), src.shape[1], out.data_ptr(),
-                                  _stream(src)), "gcb_pack_rows")
-    return out
+    return pack_rows_op(src, rows)

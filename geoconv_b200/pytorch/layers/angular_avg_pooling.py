@@ -9,7 +9,6 @@ from geoconv_b200 import ops
 class AngularAvgPooling(nn.Module):
     """Mean over the rotations: (V, n_rotations, T) -> (V, T)."""
 
-    @torch.compiler.disable
     def forward(self, inputs):
         if inputs.dim() != 3:
             raise ValueError(f"expected (n_vertices, n_rotations, feature_dim), got {tuple(inputs.shape)}")

@@ -10,10 +10,9 @@ class AngularMaxPooling(nn.Module):
     """Per vertex, keep the rotation whose template-response vector has the largest Euclidean norm
     (first maximum wins): (V, n_rotations, T) -> (V, T)."""
 
-    @torch.compiler.disable
     def forward(self, inputs):
         fused = getattr(inputs, "_gcb_pooled", None)
-        if fused is not None and fused[2] == inputs._version:
+        if fused is not None and (fused[2] is None or fused[2] == inputs._version):
             # produced by a geoconv_b200 ConvIntrinsic in the same kernel pass as `inputs`
             return fused[0]
         if inputs.dim() != 3:

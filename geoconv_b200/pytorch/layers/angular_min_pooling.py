@@ -10,7 +10,6 @@ class AngularMinPooling(nn.Module):
     """Per vertex, keep the rotation whose template-response vector has the SMALLEST Euclidean norm
     (first minimum wins): (V, n_rotations, T) -> (V, T)."""
 
-    @torch.compiler.disable
     def forward(self, inputs):
         if inputs.dim() != 3:
             raise ValueError(f"expected (n_vertices, n_rotations, feature_dim), got {tuple(inputs.shape)}")

@@ -138,6 +138,8 @@ class ConvIntrinsic(ABC, nn.Module):
         self._prior_is_zero = bool(self.include_prior and not np.any(values))
         steps = range(0, self._all_rotations, max(int(self.rotation_delta), 1))
         self._prior_is_symmetric = _rotation_symmetric(values, steps) if self.include_prior else True
+        # the layer's own rotation set is answered here, so a traced forward only looks the result up
+        self._symmetry_checked[tuple(sorted(set(steps)))] = self._prior_is_symmetric
 
     def _rotation_offsets(self, orientations):
         if orientations is None:
@@ -169,7 +171,14 @@ class ConvIntrinsic(ABC, nn.Module):
         through one rotation per vertex only.
         """
         y, z, arg = self._run(inputs, orientations)
-        y._gcb_pooled = (z, arg, y._version)
+        if torch.compiler.is_compiling():
+            # Dynamo tracks attributes only on tensors made by a traced torch call (an operator's tuple output is
+            # not one), and cannot read the version counter: inside a trace the tuple rides on an alias of Y and
+            # lives and dies with that trace
+            y = y.view_as(y)
+            y._gcb_pooled = (z, arg, None)
+        else:
+            y._gcb_pooled = (z, arg, y._version)
         return y
 
     def forward_pooled(self, inputs, orientations=None):
@@ -177,11 +186,9 @@ class ConvIntrinsic(ABC, nn.Module):
         _, z, arg = self._run(inputs, orientations)
         return z, arg
 
-    @torch.compiler.disable
     def _run(self, inputs, orientations):
-        # Opaque to torch.compile (the reference demo compiles its model, training_demo.py:127): the body
-        # hands raw device pointers to libgeoconv_b200.so through ctypes, which Dynamo cannot trace; the
-        # surrounding modules still compile, this call runs as a graph break.
+        # Traceable by torch.compile (the reference demo compiles its model, training_demo.py:126-127): every
+        # device-side step is a `geoconv_b200::*` torch.library operator with a fake kernel, the rest is shape logic.
         mesh_signal, bary_coordinates = inputs
         ops._need_cuda(mesh_signal, "signal")
         ops._need_cuda(bary_coordinates, "barycentric coordinates")
@@ -194,7 +201,12 @@ class ConvIntrinsic(ABC, nn.Module):
         if bary_coordinates.shape[0] > mesh_signal.shape[0]:
             raise ValueError("more barycentric rows than signal rows")
         signal = mesh_signal.to(torch.float32)
-        pack = ops.GLOBAL_BARY_CACHE.get(bary_coordinates, signal.shape[0], self.check_indices)
+        if torch.compiler.is_compiling():
+            # no Python-side cache inside a traced graph: the split is one more operator of the graph
+            pack = ops.prep_bary_traced(bary_coordinates, signal.shape[0])
+        else:
+            ops.INDEX_CHECKS.poll()       # deferred index validation of earlier tensors (no host sync)
+            pack = ops.GLOBAL_BARY_CACHE.get(bary_coordinates, signal.shape[0], self.check_indices)
         offsets = self._rotation_offsets(orientations)
         w_eff = self._effective_weights(offsets)
         r, a = self._template_size

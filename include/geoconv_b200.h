@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GCB_ABI_VERSION 5
+#define GCB_ABI_VERSION 6
 #define GCB_MAX_ROT 32
 
 /* error codes */
@@ -152,8 +152,9 @@ int gcb_apool_bwd(const float* grad_z, const int32_t* arg, int32_t v, int32_t n_
 /* h = grad * act'(.) with act' written in terms of the activation OUTPUT `out` (n elements). */
 int gcb_act_grad(const float* grad, const float* out, int64_t n, int act, float* h, void* stream);
 
-/* rot_sel[k] = rot_off_host[argmax[k]]  (int32, device) */
-int gcb_select_rot(const int32_t* argmax, const int32_t* rot_off_host, int32_t n_rot, int32_t v,
+/* rot_sel[k] = rot_off_host[argmax[k]] mod A, in [0, A)  (int32, device; torch.roll accepts any integer shift,
+ * conv_intrinsic.py:163, so `orientations` may hold negative values or values >= A) */
+int gcb_select_rot(const int32_t* argmax, const int32_t* rot_off_host, int32_t n_rot, int32_t A, int32_t v,
                    int32_t* rot_sel, void* stream);
 
 /* ---- backward --------------------------------------------------------------------------
@@ -174,6 +175,10 @@ int gcb_select_rot(const int32_t* argmax, const int32_t* rot_off_host, int32_t n
  * (F % 32 or T % 32 != 0) take the CUDA-core path whatever the precision.                       */
 size_t gcb_conv_bwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
                                     int32_t T, int precision);
+/* Host-only self-check (no device work): 1 if every internal buffer layout gcb_conv_bwd can choose for this shape
+ * and precision (tf32 / fp16 operand routes, centre-only route) fits inside gcb_conv_bwd_workspace_bytes. */
+int gcb_conv_bwd_workspace_selfcheck(int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F, int32_t T,
+                                     int precision);
 int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                  const float* w_self, const float* h, const int32_t* rot_sel,
                  const int32_t* csr_row_ptr, const int32_t* csr_entries, int32_t v_out,

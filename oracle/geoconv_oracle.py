@@ -234,7 +234,10 @@ def conv_forward(signal, bary, w_neighbor, w_self, bias, prior, act="relu", rota
     ``prior`` is the (R,A,R,A) coefficient tensor or ``None`` for include_prior=False.
     """
     a = bary.shape[2]
-    centre = torch.einsum("tef,kf->ket", w_self, signal)
+    # (the reference has as many barycentric rows as signal rows; a row SUBSET of the barycentric tensor against
+    # the full signal - a vertex-row shard, or a test that evaluates a few rows of a large mesh - produces those
+    # rows of the full result, the centre term reading the subset's own signal rows)
+    centre = torch.einsum("tef,kf->ket", w_self, signal[: bary.shape[0]])
     patches = patch_operator(signal_retrieval(signal, bary), prior)
     shifts = rotation_offsets(a, rotation_delta) if orientations is None else [int(o) for o in orientations]
     per_rot = [
@@ -310,7 +313,7 @@ def prior_is_rotation_symmetric(prior: np.ndarray, rotation_delta: int = 1, tol:
 def conv_forward_folded(signal, bary, w_eff, w_self, bias, act="relu", offsets=(0,)):
     """Y[k,i,t] = act(X[k]·Wself[t] + sum_{x,y,f} Weff[t,x,(y+o_i)%A,f] * I[k,x,y,f] + b[t])."""
     interp = signal_retrieval(signal, bary).to(w_eff.dtype)
-    centre = signal.to(w_eff.dtype) @ w_self[:, 0, :].T
+    centre = signal[: bary.shape[0]].to(w_eff.dtype) @ w_self[:, 0, :].T
     outs = []
     for o in offsets:
         outs.append(torch.einsum("txyf,kxyf->kt", torch.roll(w_eff, shifts=-int(o), dims=2), interp))
@@ -340,10 +343,11 @@ def conv_amp_backward_closed_form(signal, bary, w_eff, w_self, z, rot_offset, gr
     d_full = torch.einsum("kt,txyf->kxyf", h, w_eff)
     dst = (ar[None, :] + rot_offset[:, None].long()) % a
     d_interp = torch.gather(d_full, 2, dst[:, None, :, None].expand(v, r, a, f))
-    d_signal = h @ w_self[:, 0, :]
+    d_signal = torch.zeros((signal.shape[0], f), dtype=dt)
+    d_signal[:v] = h @ w_self[:, 0, :]          # (v < signal rows: a row subset against the full signal)
     contrib = (d_interp.unsqueeze(3) * w.unsqueeze(-1)).reshape(-1, f)
     d_signal = d_signal.index_add(0, idx.reshape(-1), contrib)
-    d_w_self = (h.T @ signal.to(dt)).unsqueeze(1)
+    d_w_self = (h.T @ signal[:v].to(dt)).unsqueeze(1)
     d_bias = h.sum(dim=0, keepdim=True)
     return d_signal, d_w_eff, d_w_self, d_bias
 

@@ -158,3 +158,51 @@ def test_product_does_not_import_oracle():
         for fn in files:
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 assert "oracle" not in open(os.path.join(dirpath, fn)).read(), fn
+
+
+def test_backward_workspace_covers_every_internal_layout():
+    """the fp16 route of the backward picks its own vertex-split count for the G^T X partial sums; the
+    workspace query must cover the tf32, fp16 and centre-only layouts for every shape (host-only self-check)."""
+    import itertools
+    from geoconv_b200 import _native
+    lib = _native.load()
+    for v, r, a, f, t in itertools.product([100, 6890, 14000, 20000, 50000, 250000], [1, 3, 4, 5, 8], [6, 8, 12, 16],
+                                           [32, 64, 128, 384, 544], [32, 96, 128, 384]):
+        for prec in (_native.PREC_TF32, _native.PREC_TF32X3, _native.PREC_F16X3):
+            assert lib.gcb_conv_bwd_workspace_selfcheck(v, v, r, a, f, t, prec) == 1, (v, r, a, f, t, prec)
+
+
+def test_check_gradients_helper_both_branches():
+    """tests/helpers.py::check_gradients on CPU data: the autograd branch when the decisions agree, the closed
+    form (row subset against the full signal included) when a pooling decision differs."""
+    import types
+    import torch
+    from oracle import geoconv_oracle as O
+    from tests.helpers import check_gradients
+    v_src, v, f, r, a, t = 90, 40, 8, 2, 4, 8
+    wn, ws, b = O.make_weights(t, r, a, f, seed=0)
+    signal = O.make_signal(v_src, f, seed=1, kind="randn")
+    bary = O.make_bary(v, r, a, seed=1, v_src=v_src)
+    gz = torch.randn((v, t), generator=torch.Generator().manual_seed(2))
+    prior = torch.from_numpy(O.geodesic_prior(O.template_matrix(r, a, 0.1))).float()
+    ref = O.conv_amp_forward_backward(signal, bary, wn, ws, b, prior, gz, "relu", 1)
+
+    def fake_layer(gr):
+        ns = types.SimpleNamespace
+        return ns(_template_neighbor_weights=ns(grad=gr["d_w_neighbor"]), _template_self_weights=ns(grad=gr["d_w_self"]),
+                  _bias=ns(grad=gr["d_bias"]))
+    how = check_gradients(fake_layer(ref), ref["d_signal"], ref["z"], ref["argmax"], ref, signal, bary, wn, ws, prior, gz,
+                          "relu", range(a), 1e-5)
+    assert how == "autograd"
+    # force another rotation for one vertex: the "kernel" result is then the closed form at that decision
+    arg2 = ref["argmax"].clone()
+    arg2[3] = (arg2[3] + 1) % a
+    z2 = ref["y"][torch.arange(v), arg2.long()]
+    xs = signal.clone().requires_grad_(True)
+    ps = [p_.clone().requires_grad_(True) for p_ in (wn, ws, b)]
+    y = O.conv_forward(xs, bary, ps[0], ps[1], ps[2], prior, "relu", 1)
+    g2 = torch.autograd.grad(y[torch.arange(v), arg2.long()], [xs] + ps, grad_outputs=gz)
+    got = {"d_signal": g2[0], "d_w_neighbor": g2[1], "d_w_self": g2[2], "d_bias": g2[3]}
+    how = check_gradients(fake_layer(got), got["d_signal"], z2, arg2, ref, signal, bary, wn, ws, prior, gz, "relu",
+                          range(a), 1e-5)
+    assert how == "closed-form"
