@@ -112,8 +112,8 @@ extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, 
                             const float* w_self, const float* bias, const int32_t* rot_off_host,
                             int32_t n_rot, int32_t v_out, int32_t v_src, int32_t R, int32_t A,
                             int32_t F, int32_t T, int act, int precision, float* y, float* z,
-                            int32_t* argmax, float* interp_out, void* workspace, size_t workspace_bytes,
-                            void* stream) {
+                            int32_t* argmax, float* interp_out, const void* records, const void* tables,
+                            uint32_t* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
   GCB_REQUIRE(x && idx && w && w_self && bias, GCB_EINVAL, "gcb_conv_fwd: null input pointer");
   GCB_REQUIRE(y || z, GCB_EINVAL, "gcb_conv_fwd: need y and/or z");
   GCB_REQUIRE((z == nullptr) == (argmax == nullptr), GCB_EINVAL, "gcb_conv_fwd: z and argmax go together");
@@ -132,6 +132,7 @@ extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, 
   float* y_out = y ? y : (float*)ws;
   ws += y_tmp;
   workspace_bytes -= y_tmp;
+  if (stats_out && (precision != GCB_PREC_F16X3 || !w_eff)) GCB_CUDA_OK(cudaMemsetAsync(stats_out, 0, 32, st));
   if (precision == GCB_PREC_FP32 || !w_eff) {  // centre-only (w_eff == NULL) is a tiny GEMM: CUDA cores
     rc = ffma_conv_fwd(x, idx, w, w_eff, w_self, bias, rot, n_rot, v_out, v_src, R, A, F, T, act, y_out, ws, st);
   } else if (precision == GCB_PREC_TF32 || precision == GCB_PREC_TF32X3 || precision == GCB_PREC_F16X3) {
@@ -141,13 +142,35 @@ extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, 
                 "gcb_conv_fwd: the fp16 split does not support R=%d A=%d F=%d T=%d n_rot=%d", R, A, F, T, n_rot);
     // the tensor-core path pools in its own finishing kernel
     return tc_conv_fwd(x, idx, w, w_eff, w_self, bias, rot, n_rot, v_out, v_src, R, A, F, T, act, precision,
-                       y_out, z, argmax, interp_out, ws, workspace_bytes, st);
+                       y_out, z, argmax, interp_out, records, tables, stats_out, ws, workspace_bytes, st);
   } else {
     GCB_REQUIRE(false, GCB_EINVAL, "gcb_conv_fwd: unknown precision %d", precision);
   }
   if (rc) return rc;
   if (z) rc = amp_fwd(y_out, v_out, n_rot, T, z, argmax, st);
   return rc;
+}
+
+extern "C" size_t gcb_fwd_records_bytes(int32_t v_out, int32_t R, int32_t A) { return tc_fwd_records_bytes(v_out, R, A); }
+
+extern "C" int gcb_fwd_pack_records(const int32_t* idx, const float* w, int32_t v_out, int32_t R, int32_t A,
+                                    void* records, void* stream) {
+  GCB_REQUIRE(idx && w && records, GCB_EINVAL, "gcb_fwd_pack_records: null pointer");
+  GCB_REQUIRE(v_out > 0 && R > 0 && A > 0, GCB_EINVAL, "gcb_fwd_pack_records: bad sizes");
+  return tc_fwd_pack_records(idx, w, v_out, R, A, records, (cudaStream_t)stream);
+}
+
+extern "C" size_t gcb_fwd_tables_bytes(void) { return tc_fwd_tables_bytes(); }
+
+extern "C" int gcb_fwd_build_tables(const int32_t* rot_off_host, int32_t n_rot, int32_t v_out, int32_t R, int32_t A,
+                                    int32_t F, int32_t T, int precision, void* tables, void* stream) {
+  GCB_REQUIRE(tables, GCB_EINVAL, "gcb_fwd_build_tables: null pointer");
+  GCB_REQUIRE(precision != GCB_PREC_FP32 && tc_supported(R, A, F, T, n_rot), GCB_EUNSUPPORTED,
+              "gcb_fwd_build_tables: only the tcgen05 forward uses tables");
+  RotTable rot;
+  int rc = make_rot_table(rot_off_host, n_rot, A, &rot);
+  if (rc) return rc;
+  return tc_fwd_build_tables(rot, n_rot, v_out, R, A, F, T, precision, tables, (cudaStream_t)stream);
 }
 
 extern "C" size_t gcb_conv_bwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A,
@@ -196,4 +219,57 @@ extern "C" int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, 
   if (rc || !d_x) return rc;
   return csr_reduce_dx(w_eff ? d_full : nullptr, w, h, w_self, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T,
                        accumulate, d_x, st);
+}
+
+// ---- AMP-sparse backward from (dZ, Z, argmax): one call, one preparation kernel ---------------------------------
+extern "C" size_t gcb_conv_amp_bwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
+                                                   int32_t T, int precision) {
+  return gcb_conv_bwd_workspace_bytes(v_out, v_src, R, A, F, T, precision) +
+         align_up((size_t)v_out * T * sizeof(float), 256) + align_up((size_t)v_out * sizeof(int32_t), 256) + 512;
+}
+
+namespace gcb {
+int act_grad_launch(const float* grad, const float* out, int64_t n, int act, float* h, cudaStream_t st);
+int select_rot_launch(const int32_t* argmax, const RotTable& rot, int n_rot, int v, int32_t* rot_sel, cudaStream_t st);
+}  // namespace gcb
+
+extern "C" int gcb_conv_amp_bwd(const float* grad_z, const float* z, const int32_t* argmax,
+                                const int32_t* rot_off_host, int32_t n_rot, int act, const float* x,
+                                const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
+                                const int32_t* csr_row_ptr, const int32_t* csr_entries, const uint32_t* csr_stats,
+                                const uint32_t* fwd_stats, int32_t v_out, int32_t v_src, int32_t R, int32_t A,
+                                int32_t F, int32_t T, int precision, float* d_x, float* d_w_eff, float* d_w_self,
+                                float* d_bias, void* workspace, size_t workspace_bytes, void* stream) {
+  GCB_REQUIRE(grad_z && z && argmax && x && idx && w && w_self, GCB_EINVAL, "gcb_conv_amp_bwd: null input pointer");
+  GCB_REQUIRE(!d_x || !w_eff || (csr_row_ptr && csr_entries), GCB_EINVAL, "gcb_conv_amp_bwd: d_x needs the CSR");
+  GCB_REQUIRE(d_w_eff && d_w_self && d_bias, GCB_EINVAL, "gcb_conv_amp_bwd: null output pointer");
+  GCB_REQUIRE(act >= 0 && act <= GCB_ACT_TANH, GCB_EINVAL, "gcb_conv_amp_bwd: unknown activation %d", act);
+  int rc = check_shape(v_out, v_src, R, A, F, T);
+  if (rc) return rc;
+  GCB_REQUIRE(v_out > 0, GCB_EINVAL, "gcb_conv_amp_bwd: empty input");
+  GCB_REQUIRE(workspace && workspace_bytes >= gcb_conv_amp_bwd_workspace_bytes(v_out, v_src, R, A, F, T, precision),
+              GCB_EWORKSPACE, "gcb_conv_amp_bwd: workspace too small");
+  TcBwdAmp amp;
+  rc = make_rot_table(rot_off_host, n_rot, A, &amp.rot);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)align_up((size_t)workspace, 256);
+  amp.h = (float*)ws;
+  ws += align_up((size_t)v_out * T * sizeof(float), 256);
+  amp.rot_sel = (int32_t*)ws;
+  ws += align_up((size_t)v_out * sizeof(int32_t), 256);
+  const size_t rest = workspace_bytes - (size_t)(ws - (char*)workspace);
+  amp.grad_z = grad_z; amp.z = z; amp.argmax = argmax; amp.n_rot = n_rot; amp.act = act;
+  amp.csr_stats = csr_stats; amp.fwd_stats = fwd_stats;
+  const bool aligned = ((uintptr_t)grad_z % 16 == 0) && ((uintptr_t)z % 16 == 0) && T % 4 == 0 && T <= 1024;
+  if (precision != GCB_PREC_FP32 && tc_bwd_supported(R, A, F, T) && aligned)
+    return tc_conv_bwd(x, idx, w, w_eff, w_self, amp.h, amp.rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T,
+                       precision, 0, nullptr, d_x, d_w_eff, d_w_self, d_bias, ws, rest, st, &amp);
+  // CUDA-core route (or a shape the preparation kernel does not tile): the separate small kernels, then gcb_conv_bwd
+  rc = act_grad_launch(grad_z, z, (int64_t)v_out * T, act, amp.h, st);
+  if (rc) return rc;
+  rc = select_rot_launch(argmax, amp.rot, n_rot, v_out, amp.rot_sel, st);
+  if (rc) return rc;
+  return gcb_conv_bwd(x, idx, w, w_eff, w_self, amp.h, amp.rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T,
+                      precision, 0, nullptr, d_x, d_w_eff, d_w_self, d_bias, ws, rest, stream);
 }

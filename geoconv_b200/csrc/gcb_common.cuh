@@ -100,7 +100,9 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
                 const float* w_self, const float* bias, const RotTable& rot, int n_rot, int v_out,
                 int v_src, int R, int A, int F, int T, int act, int precision, float* y,
                 float* z /* nullable: fused AngularMaxPooling */, int32_t* argmax,
-                float* interp_out /* nullable: keep I[v_out,R,A,F] for the backward */, void* workspace,
+                float* interp_out /* nullable: keep I[v_out,R,A,F] for the backward */,
+                const void* records /* nullable: gcb_fwd_pack_records */, const void* tables /* nullable: gcb_fwd_build_tables */,
+                uint32_t* stats_out /* nullable: 8 words of operand maxima for the backward */, void* workspace,
                 size_t workspace_bytes, cudaStream_t st);
 
 // shared small kernels (gcb_pool.cu)

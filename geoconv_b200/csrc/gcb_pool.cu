@@ -218,6 +218,20 @@ int csr_reduce_dx(const float* d_full, const float* w, const float* h, const flo
   return GCB_OK;
 }
 
+int act_grad_launch(const float* grad, const float* out, int64_t n, int act, float* h, cudaStream_t st) {
+  if (n <= 0) return GCB_OK;
+  k_act_grad<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(grad, out, n, act, h);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+int select_rot_launch(const int32_t* argmax, const RotTable& rot, int n_rot, int v, int32_t* rot_sel, cudaStream_t st) {
+  if (v <= 0) return GCB_OK;
+  k_select_rot<<<(unsigned)ceil_div64(v, 256), 256, 0, st>>>(argmax, rot, n_rot, v, rot_sel);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
 }  // namespace gcb
 
 using namespace gcb;

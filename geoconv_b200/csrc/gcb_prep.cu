@@ -2,6 +2,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "gcb_common.cuh"
+#include "gcb_tc.cuh"
 
 namespace gcb {
 
@@ -153,7 +154,7 @@ extern "C" size_t gcb_csr_workspace_bytes(int64_t n_slots, int32_t v_src) {
 }
 
 extern "C" int gcb_csr_build(const int32_t* idx, const float* w, int64_t n_slots, int32_t v_src,
-                             int32_t* row_ptr, int32_t* entries, void* workspace,
+                             int32_t* row_ptr, int32_t* entries, uint32_t* stats, void* workspace,
                              size_t workspace_bytes, void* stream) {
   GCB_REQUIRE(idx && w && row_ptr && entries && workspace, GCB_EINVAL, "gcb_csr_build: null pointer");
   GCB_REQUIRE(n_slots > 0 && n_slots < (1ll << 31) && v_src > 0, GCB_EINVAL, "gcb_csr_build: bad sizes");
@@ -176,6 +177,17 @@ extern "C" int gcb_csr_build(const int32_t* idx, const float* w, int64_t n_slots
                                               entries, (int)n_slots, 0, bits, st));
   k_csr_row_ptr<<<(unsigned)ceil_div64((int64_t)v_src + 1, 256), 256, 0, st>>>(keys_out, n_slots, v_src, row_ptr);
   GCB_LAUNCH_OK();
+  if (stats) {
+    // what the fp16 backward needs to bound |G| (gcb_conv_amp_bwd): largest |weight| and longest row - properties of
+    // the barycentric tensor, computed here once instead of in every backward
+    GCB_CUDA_OK(cudaMemsetAsync(stats, 0, 32, st));
+    TcMaxJob job{};
+    job.mode = 0;
+    job.n_seg = 2;
+    job.seg[0] = {w, (long long)n_slots, 0, 1};
+    job.seg[1] = {row_ptr, (long long)v_src, 1, 2};
+    return tc_maxima_scales(job, stats, nullptr, st);
+  }
   return GCB_OK;
 }
 

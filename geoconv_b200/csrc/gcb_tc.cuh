@@ -33,10 +33,19 @@ int tc_build_wcat_h(const float* w_eff, const float* w_self, int T, int R, int A
 // ticket), segments of floats (max |a[i]|) or of a CSR row pointer (longest row), each reduced into mx[slot]
 constexpr int TC_MAX_SEGS = 6;
 struct TcMaxSeg { const void* ptr; long long n; int is_rowptr; int slot; };
-struct TcMaxJob { TcMaxSeg seg[TC_MAX_SEGS]; int blk0[TC_MAX_SEGS + 1]; int n_seg, mode, have_csr; };
+// mode 0: maxima only; 1: forward scales; 2: backward scales.  ext_wsum (mode 1, nullable): max sum_j |w_j| of a cached
+// record packing, used instead of mx[1]
+struct TcMaxJob { TcMaxSeg seg[TC_MAX_SEGS]; int blk0[TC_MAX_SEGS + 1]; int n_seg, mode, have_csr; const unsigned* ext_wsum; };
 int tc_maxima_scales(const TcMaxJob& job, unsigned* mx, float* scales, cudaStream_t st);
 // max |a[i]| over up to two arrays as fp32 bits, atomicMax'ed into *out (zero it first)
 int tc_absmax(const float* a, int64_t na, const float* b, int64_t nb, unsigned* out, cudaStream_t st);
+
+// what a caller may prepare once and hand to every forward (gcb_fwd_pack_records / gcb_fwd_build_tables)
+size_t tc_fwd_records_bytes(int v_out, int R, int A);
+int tc_fwd_pack_records(const int32_t* idx, const float* w, int v_out, int R, int A, void* records, cudaStream_t st);
+size_t tc_fwd_tables_bytes();
+int tc_fwd_build_tables(const RotTable& rot, int n_rot, int v_out, int R, int A, int F, int T, int precision, void* tables,
+                        cudaStream_t st);
 
 // slot-major packed barycentric records [R*A][v_pad][2 x uint4], v_pad = multiple of 128
 size_t tc_recs_bytes(int v_out, int R, int A);
@@ -70,16 +79,30 @@ int tc_dx_from_g(const float* g_hi, const float* g_lo, const float* wcat_hi, con
                  const float* scales = nullptr);
 int tc_dw_from_g(const float* g_hi, const float* g_lo, const float* x, int v_src, int R, int A, int F, int T,
                  bool x3, int accumulate, float* d_w_eff, float* d_w_self, float* x_hi, float* x_lo, float* partial,
-                 size_t partial_bytes, cudaStream_t st, const float* scales = nullptr);
+                 size_t partial_bytes, cudaStream_t st, const float* scales = nullptr, bool x_is_split = false);
 
 // tensor-core backward (gcb_tc_bwd.cu)
 bool tc_bwd_supported(int R, int A, int F, int T);
 size_t tc_bwd_workspace_bytes(int v_out, int v_src, int R, int A, int F, int T, int precision);
 bool tc_bwd_layout_fits(int v_out, int v_src, int R, int A, int F, int T, int precision);
+// AMP-sparse entry: the backward starts from dZ, Z and the pooling decisions instead of h / rot_sel, which it then
+// produces itself into `h` [v_out,T] and `rot_sel` [v_out] (caller-provided scratch)
+struct TcBwdAmp {
+  const float* grad_z;
+  const float* z;
+  const int32_t* argmax;
+  RotTable rot;                 // offsets reduced to [0, A)
+  int n_rot, act;
+  const uint32_t* csr_stats;    // nullable: [1] max|w| bits, [2] longest CSR row (gcb_csr_build)
+  const uint32_t* fwd_stats;    // nullable: [0] max|X| bits, [2] max|Wcat| bits (gcb_conv_fwd)
+  float* h;
+  int32_t* rot_sel;
+};
 int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
                 const float* h, const int32_t* rot_sel, const int32_t* csr_row_ptr, const int32_t* csr_entries,
                 int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,
                 const float* interp /* nullable: I saved by the forward */, float* d_x, float* d_w_eff,
-                float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                const TcBwdAmp* amp = nullptr);
 
 }  // namespace gcb

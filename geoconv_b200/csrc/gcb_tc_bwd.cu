@@ -364,6 +364,170 @@ __global__ void k_bw_bias_final(const float* __restrict__ part, int nblocks, int
   d_bias[t] = accumulate ? d_bias[t] + acc : acc;
 }
 
+
+// =================================================================================================
+// k_bw_prepare: everything the AMP-sparse backward needs before its first big kernel, in ONE launch
+//   role A (blocks [0, nb_h)):  h = dZ * act'(Z), rot_sel[k] = rot[argmax[k]], per-block column sums of h (first
+//           stage of d_bias), max|h|; the block that finishes last (ticket) adds the column sums in block order
+//           (fixed order: bit-reproducible) into d_bias and, in the fp16 mode, turns the operand maxima into the
+//           five power-of-two scales {sG, sW, sX, 1/(sG sW), 1/(sG sX)}
+//   role B (fp16 mode with the forward's maxima at hand):  X * sX = hi + lo (fp16)   - the B operand of G^T X
+//   role C (same condition):  [Weff | Wself] * sW = hi + lo (fp16)                   - the B operand of G Wcat
+// It replaces six launches (activation gradient, rotation select, maxima, two bias reductions, a memset) and runs
+// the two operand splits, which depend on nothing computed here, beside them.
+// =================================================================================================
+struct BwPrepParams {
+  const float* grad_z;
+  const float* z;
+  const int32_t* argmax;
+  RotTable rot;              // offsets in [0, A)
+  int n_rot, act, v_out, T;
+  float* h;
+  int32_t* rot_sel;
+  float* bias_part;          // [nb_h][T]
+  int rows_per_block, nb_h, accumulate;
+  float* d_bias;
+  unsigned* mx;              // 8 zeroed words: [0] max|h| bits, [6] ticket; [1..4] maxima when the stats are absent ([7]: k_tc_maxima's ticket)
+  const unsigned* csr_stats; // nullable: [1] max|w| bits, [2] longest CSR row
+  const unsigned* fwd_stats; // nullable: [0] max|X| bits, [2] max|Wcat| bits
+  float* scales;             // nullable (tf32 modes): the five scales
+  int have_csr;
+  // roles B / C
+  const float* x; long long x_rows; int F, x_ld; __half* xh; __half* xl; int nb_x;
+  const float* w_eff; const float* w_self; int KRA; __half* wh; __half* wl; int nb_w;
+};
+
+__device__ __forceinline__ int bw_pow2_for(float bound) {   // bound * 2^e in [2^14, 2^15); 0 for a zero / non-finite bound
+  if (!(bound > 0.f) || !isfinite(bound)) return 0;
+  const int e = 14 - ilogbf(bound);
+  return e < -60 ? -60 : (e > 60 ? 60 : e);
+}
+
+__device__ __forceinline__ void bw_split_half2(float a, float b, float s, uint32_t& hi, uint32_t& lo) {
+  a *= s; b *= s;
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+constexpr int BWP_THREADS = 256;
+
+__global__ void __launch_bounds__(BWP_THREADS) k_bw_prepare(const __grid_constant__ BwPrepParams p) {
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x >= p.nb_h) {
+    // ---------------- roles B / C: fp16 operand splits (8 consecutive elements per thread) ----------------
+    int b = (int)blockIdx.x - p.nb_h;
+    if (b < p.nb_x) {
+      const float s = ldexpf(1.f, bw_pow2_for(__uint_as_float(__ldg(p.fwd_stats + 0))));
+      const int g8 = p.x_ld >> 3;
+      const long long n = p.x_rows * g8;
+      for (long long i8 = (long long)b * BWP_THREADS + tid; i8 < n; i8 += (long long)p.nb_x * BWP_THREADS) {
+        const long long r = i8 / g8;
+        const int c = (int)(i8 - r * g8) << 3;
+        const float4* src = reinterpret_cast<const float4*>(p.x + r * p.F + c);
+        const float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 a = c + 4 <= p.F ? __ldg(src) : zz, bq = c + 8 <= p.F ? __ldg(src + 1) : zz;
+        uint4 hi, lo;
+        bw_split_half2(a.x, a.y, s, hi.x, lo.x); bw_split_half2(a.z, a.w, s, hi.y, lo.y);
+        bw_split_half2(bq.x, bq.y, s, hi.z, lo.z); bw_split_half2(bq.z, bq.w, s, hi.w, lo.w);
+        *reinterpret_cast<uint4*>(p.xh + i8 * 8) = hi;
+        *reinterpret_cast<uint4*>(p.xl + i8 * 8) = lo;
+      }
+      return;
+    }
+    b -= p.nb_x;
+    const float s = ldexpf(1.f, bw_pow2_for(__uint_as_float(__ldg(p.fwd_stats + 2))));
+    const int kcat = p.KRA + p.F, k8n = kcat >> 3;
+    const long long n = (long long)p.T * k8n;
+    for (long long e8 = (long long)b * BWP_THREADS + tid; e8 < n; e8 += (long long)p.nb_w * BWP_THREADS) {
+      const int t = (int)(e8 / k8n), k = (int)(e8 - (long long)t * k8n) << 3;
+      const float* src = k < p.KRA ? p.w_eff + (size_t)t * p.KRA + k : p.w_self + (size_t)t * p.F + (k - p.KRA);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), bq = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      uint4 hi, lo;
+      bw_split_half2(a.x, a.y, s, hi.x, lo.x); bw_split_half2(a.z, a.w, s, hi.y, lo.y);
+      bw_split_half2(bq.x, bq.y, s, hi.z, lo.z); bw_split_half2(bq.z, bq.w, s, hi.w, lo.w);
+      const size_t o = (size_t)t * kcat + k;
+      *reinterpret_cast<uint4*>(p.wh + o) = hi;
+      *reinterpret_cast<uint4*>(p.wl + o) = lo;
+    }
+    return;
+  }
+  // ---------------- role A ----------------
+  extern __shared__ float4 s_col[];            // [row lanes][T / 4]
+  __shared__ unsigned s_max;
+  __shared__ bool s_last;
+  if (tid == 0) s_max = 0u;
+  const int T4 = p.T >> 2;
+  const int n_lanes = BWP_THREADS / T4;        // row lanes (>= 1: T <= 1024)
+  const int c4 = tid % T4, rl = tid / T4;
+  const int r0 = (int)blockIdx.x * p.rows_per_block, r1 = min(p.v_out, r0 + p.rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned m = 0;
+  if (rl < n_lanes) {
+    for (int r = r0 + rl; r < r1; r += n_lanes) {
+      const size_t o = (size_t)r * T4 + c4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.grad_z) + o);
+      const float4 zo = __ldg(reinterpret_cast<const float4*>(p.z) + o);
+      float4 hv;
+      hv.x = g.x * act_grad_from_out(p.act, zo.x); hv.y = g.y * act_grad_from_out(p.act, zo.y);
+      hv.z = g.z * act_grad_from_out(p.act, zo.z); hv.w = g.w * act_grad_from_out(p.act, zo.w);
+      reinterpret_cast<float4*>(p.h)[o] = hv;
+      acc.x += hv.x; acc.y += hv.y; acc.z += hv.z; acc.w += hv.w;
+      m = max(m, max(max(__float_as_uint(fabsf(hv.x)), __float_as_uint(fabsf(hv.y))),
+                     max(__float_as_uint(fabsf(hv.z)), __float_as_uint(fabsf(hv.w)))));
+      if (c4 == 0) {
+        const int a = __ldg(p.argmax + r);
+        p.rot_sel[r] = p.rot.off[a < 0 ? 0 : (a >= p.n_rot ? p.n_rot - 1 : a)];
+      }
+    }
+    s_col[rl * T4 + c4] = acc;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __syncthreads();
+  if ((tid & 31) == 0 && m) atomicMax(&s_max, m);
+  if (tid < T4) {      // fixed-order sum over the row lanes
+    float4 sum = s_col[tid];
+    for (int l = 1; l < n_lanes; ++l) {
+      const float4 v = s_col[l * T4 + tid];
+      sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+    }
+    reinterpret_cast<float4*>(p.bias_part)[(size_t)blockIdx.x * T4 + tid] = sum;
+    __threadfence();   // visible to the block that finishes last before this block's ticket is
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (s_max) atomicMax(p.mx + 0, s_max);
+    __threadfence();
+    s_last = atomicAdd(p.mx + 6, 1u) == (unsigned)p.nb_h - 1u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int t = tid; t < p.T; t += BWP_THREADS) {
+    float sum = 0.f;
+    for (int b = 0; b < p.nb_h; ++b) sum += __ldcg(p.bias_part + (size_t)b * p.T + t);
+    p.d_bias[t] = p.accumulate ? p.d_bias[t] + sum : sum;
+  }
+  if (tid == 0 && p.scales) {
+    volatile const unsigned* vm = p.mx;
+    const float hm = __uint_as_float(vm[0]);
+    const unsigned wbits = p.csr_stats ? __ldg(p.csr_stats + 1) : vm[1];
+    const unsigned longest = p.csr_stats ? __ldg(p.csr_stats + 2) : vm[2];
+    const unsigned wcbits = p.fwd_stats ? __ldg(p.fwd_stats + 2) : vm[3];
+    const unsigned xbits = p.fwd_stats ? __ldg(p.fwd_stats + 0) : vm[4];
+    const float gm = p.have_csr ? fmaxf(hm * __uint_as_float(wbits) * (float)longest, hm) : hm;
+    const int eg = bw_pow2_for(gm), ew = bw_pow2_for(__uint_as_float(wcbits)), ex = bw_pow2_for(__uint_as_float(xbits));
+    p.scales[0] = ldexpf(1.f, eg);
+    p.scales[1] = ldexpf(1.f, ew);
+    p.scales[2] = ldexpf(1.f, ex);
+    p.scales[3] = ldexpf(1.f, -(eg + ew));
+    p.scales[4] = ldexpf(1.f, -(eg + ex));
+  }
+}
+
 // =================================================================================================
 // host side
 // =================================================================================================
@@ -421,7 +585,9 @@ static BwLayout bw_layout(int v_out, int v_src, int R, int A, int F, int T, bool
   L.partial = align_up((size_t)L.vsplit * T * L.kcat_pad * sizeof(float), 256);
   const size_t bias_a = align_up((size_t)(L.v_pad / 32) * T * sizeof(float), 256);
   const size_t bias_b = align_up((size_t)L.bias_blocks * T * sizeof(float), 256);
+  const size_t bias_c = align_up((size_t)296 * T * sizeof(float), 256);   // k_bw_prepare: at most 296 row blocks
   L.bias_part = bias_a > bias_b ? bias_a : bias_b;
+  if (bias_c > L.bias_part) L.bias_part = bias_c;
   L.via_g = tc_g_layout_max(v_src, R, A, F, T, x3).total;   // G, the split signal, the GEMM partials (any route)
   const size_t gather_route = L.recs + L.ht + L.partial;
   L.total = L.bias_part + L.wcat + (gather_route > L.via_g ? gather_route : L.via_g) + tc_bwd_scales_bytes() + 1024;
@@ -470,7 +636,7 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
                 const float* h, const int32_t* rot_sel, const int32_t* csr_row_ptr, const int32_t* csr_entries,
                 int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,
                 const float* interp, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias, void* workspace,
-                size_t workspace_bytes, cudaStream_t st) {
+                size_t workspace_bytes, cudaStream_t st, const TcBwdAmp* amp) {
   // fp16 operand splits (GCB_PREC_F16X3) serve the route through G; the centre-only and gather-fed routes run
   // the same precision request as 3xTF32
   static const bool no_half = getenv("GCB_BWD_NO_HALF") && atoi(getenv("GCB_BWD_NO_HALF")) != 0;   // A/B measurements
@@ -488,6 +654,75 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
   void* scale_scratch = ws;
   ws += tc_bwd_scales_bytes();
   int rc;
+  // AMP-sparse entry (gcb_conv_amp_bwd): h, rot_sel, d_bias, the fp16 scales and - when the forward's operand maxima
+  // came along - both operand splits are produced by ONE launch (k_bw_prepare)
+  bool bias_done = false, scales_done = false, x_split_done = false, w_split_done = false;
+  const TcGLayout GMX = tc_g_layout_max(v_src, R, A, F, T, x3);
+  if (amp) {
+    GCB_REQUIRE(T % 4 == 0 && T <= 1024 && ((uintptr_t)amp->grad_z % 16 == 0) && ((uintptr_t)amp->z % 16 == 0), GCB_EINVAL,
+                "tc_conv_bwd: grad_z / z must be 16-byte aligned and T a multiple of 4");
+    unsigned* mx = (unsigned*)scale_scratch;
+    GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 32, st));
+    const bool have_csr = csr_row_ptr && w_eff;
+    const bool stats = half && amp->fwd_stats && (!have_csr || amp->csr_stats);
+    if (half && !stats) {   // the maxima the caller did not bring along (mode 0: no scales yet)
+      TcMaxJob job{};
+      job.mode = 0;
+      int n = 0;
+      if (have_csr && !amp->csr_stats) {
+        job.seg[n++] = {w, (long long)v_out * R * A * 3, 0, 1};
+        job.seg[n++] = {csr_row_ptr, (long long)v_src, 1, 2};
+      }
+      if (!amp->fwd_stats) {
+        if (w_eff) job.seg[n++] = {w_eff, (long long)T * R * A * F, 0, 3};
+        job.seg[n++] = {w_self, (long long)T * F, 0, 3};
+        job.seg[n++] = {x, (long long)v_src * F, 0, 4};
+      }
+      job.n_seg = n;
+      if (n) {
+        rc = tc_maxima_scales(job, mx, nullptr, st);   // (slots 1..4; its ticket is word 7, k_bw_prepare's word 6)
+        if (rc) return rc;
+      }
+    }
+    BwPrepParams pp{};
+    pp.grad_z = amp->grad_z; pp.z = amp->z; pp.argmax = amp->argmax; pp.rot = amp->rot; pp.n_rot = amp->n_rot;
+    pp.act = amp->act; pp.v_out = v_out; pp.T = T; pp.h = amp->h; pp.rot_sel = amp->rot_sel;
+    pp.nb_h = (int)ceil_div64(v_out, 24);
+    if (pp.nb_h > 296) pp.nb_h = 296;
+    pp.rows_per_block = (int)ceil_div64(v_out, pp.nb_h);
+    pp.nb_h = (int)ceil_div64(v_out, pp.rows_per_block);
+    GCB_REQUIRE((size_t)pp.nb_h * T * sizeof(float) <= L.bias_part, GCB_EWORKSPACE, "tc_conv_bwd: bias partial sums do not fit");
+    pp.bias_part = bias_part; pp.accumulate = accumulate; pp.d_bias = d_bias;
+    pp.mx = mx;
+    pp.have_csr = have_csr ? 1 : 0;
+    pp.scales = half ? (float*)(mx + 8) : nullptr;
+    pp.csr_stats = amp->csr_stats;   // (a null pointer: the maxima are in mx[1..4], from the job above)
+    pp.fwd_stats = amp->fwd_stats;
+    if (stats && F % 8 == 0) {
+      const int x_ld = (int)ceil_div64(F, 64) * 64;
+      char* wsx = ws + GMX.g_bytes;   // where the routes below place the split signal
+      pp.x = x; pp.x_rows = v_src; pp.F = F; pp.x_ld = x_ld;
+      pp.xh = (__half*)wsx; pp.xl = pp.xh + (size_t)v_src * x_ld;
+      pp.nb_x = (int)ceil_div64((int64_t)v_src * (x_ld / 8), (int64_t)BWP_THREADS * 4);
+      if (pp.nb_x > 148) pp.nb_x = 148;
+      x_split_done = true;
+      if (w_eff && d_x) {
+        pp.w_eff = w_eff; pp.w_self = w_self; pp.KRA = KRA;
+        pp.wh = (__half*)wc_hi; pp.wl = (__half*)wc_lo;
+        pp.nb_w = (int)ceil_div64((int64_t)T * ((KRA + F) / 8), (int64_t)BWP_THREADS * 4);
+        if (pp.nb_w > 148) pp.nb_w = 148;
+        w_split_done = true;
+      }
+    }
+    const int T4 = T / 4;
+    const size_t smem = (size_t)(BWP_THREADS / T4) * T4 * sizeof(float4);
+    k_bw_prepare<<<pp.nb_h + pp.nb_x + pp.nb_w, BWP_THREADS, smem, st>>>(pp);
+    GCB_LAUNCH_OK();
+    h = amp->h;
+    rot_sel = amp->rot_sel;
+    bias_done = true;
+    scales_done = half;
+  }
 
   if (!w_eff) {
     // ---- centre-only layer (all-zero prior, ConvZero): G degenerates to its centre slab, h itself ----
@@ -501,11 +736,13 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     float* x_lo = x3 ? x_hi + (size_t)v_src * F : nullptr;
     ws += GM.xsplit_bytes;
     float* partial = (float*)ws;
-    k_bw_bias_partial<<<dim3((unsigned)L.bias_blocks, (unsigned)ceil_div64(T, 32)), dim3(32, 8), 0, st>>>(
-        h, v_out, T, L.bias_rows, bias_part);
-    GCB_LAUNCH_OK();
-    k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.bias_blocks, T, accumulate, d_bias);
-    GCB_LAUNCH_OK();
+    if (!bias_done) {
+      k_bw_bias_partial<<<dim3((unsigned)L.bias_blocks, (unsigned)ceil_div64(T, 32)), dim3(32, 8), 0, st>>>(
+          h, v_out, T, L.bias_rows, bias_part);
+      GCB_LAUNCH_OK();
+      k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.bias_blocks, T, accumulate, d_bias);
+      GCB_LAUNCH_OK();
+    }
     if (!accumulate) GCB_CUDA_OK(cudaMemsetAsync(d_w_eff, 0, (size_t)T * R * A * F * sizeof(float), st));
     k_bw_split_rows<<<(unsigned)ceil_div64((int64_t)GL.v_pad * T, 256), 256, 0, st>>>(h, v_out, GL.v_pad, T, g_hi, g_lo);
     GCB_LAUNCH_OK();
@@ -526,8 +763,10 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     const float* scales = nullptr;
     if (half) {   // fp16 buffers: rows of kg_ld halves (they fit in the 3xTF32 sizes)
       g_lo = (float*)((__half*)g_hi + (size_t)GL.v_pad * (ceil_div64(GL.kg, 64) * 64));
-      rc = tc_bwd_scales(h, w, csr_row_ptr, w_eff, w_self, x, v_out, v_src, R, A, F, T, scale_scratch, st);
-      if (rc) return rc;
+      if (!scales_done) {
+        rc = tc_bwd_scales(h, w, csr_row_ptr, w_eff, w_self, x, v_out, v_src, R, A, F, T, scale_scratch, st);
+        if (rc) return rc;
+      }
       scales = (const float*)((const unsigned*)scale_scratch + 8);
     }
     ws += GM.g_bytes;
@@ -535,19 +774,23 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     float* x_lo = x3 ? x_hi + (size_t)v_src * F : nullptr;
     ws += GM.xsplit_bytes;
     float* partial = (float*)ws;
-    k_bw_bias_partial<<<dim3((unsigned)L.bias_blocks, (unsigned)ceil_div64(T, 32)), dim3(32, 8), 0, st>>>(
-        h, v_out, T, L.bias_rows, bias_part);
-    GCB_LAUNCH_OK();
-    k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.bias_blocks, T, accumulate, d_bias);
-    GCB_LAUNCH_OK();
+    if (!bias_done) {
+      k_bw_bias_partial<<<dim3((unsigned)L.bias_blocks, (unsigned)ceil_div64(T, 32)), dim3(32, 8), 0, st>>>(
+          h, v_out, T, L.bias_rows, bias_part);
+      GCB_LAUNCH_OK();
+      k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.bias_blocks, T, accumulate, d_bias);
+      GCB_LAUNCH_OK();
+    }
     rc = tc_build_g(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, x3, g_hi, g_lo, st, scales);
     if (rc) return rc;
     rc = tc_dw_from_g(g_hi, g_lo, x, v_src, R, A, F, T, x3, accumulate, d_w_eff, d_w_self, x_hi, x_lo, partial,
-                      GM.partial_bytes, st, scales);
+                      GM.partial_bytes, st, scales, half && x_split_done);
     if (rc || !d_x) return rc;
-    rc = half ? tc_build_wcat_h(w_eff, w_self, T, R, A, F, scales + 1, (__half*)wc_hi, (__half*)wc_lo, st)
-              : tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);
-    if (rc) return rc;
+    if (!(half && w_split_done)) {
+      rc = half ? tc_build_wcat_h(w_eff, w_self, T, R, A, F, scales + 1, (__half*)wc_hi, (__half*)wc_lo, st)
+                : tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);
+      if (rc) return rc;
+    }
     return tc_dx_from_g(g_hi, g_lo, wc_hi, wc_lo, v_src, R, A, F, T, x3, accumulate, d_x, st, scales);
   }
 
@@ -564,8 +807,10 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     dim3 grid((unsigned)(L.v_pad / 32), (unsigned)ceil_div64(T, 32));
     k_bw_transpose_h<<<grid, dim3(32, 8), 0, st>>>(h, v_out, L.v_pad, T, ht_hi, ht_lo, bias_part);
     GCB_LAUNCH_OK();
-    k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.v_pad / 32, T, accumulate, d_bias);
-    GCB_LAUNCH_OK();
+    if (!bias_done) {
+      k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.v_pad / 32, T, accumulate, d_bias);
+      GCB_LAUNCH_OK();
+    }
   }
   CUtensorMap mh, ml;
   rc = tc_make_tmap_2d(&mh, ht_hi, (uint64_t)L.v_pad, (uint64_t)T, (uint64_t)L.v_pad * 4, 32, (uint32_t)L.n_t);

@@ -167,6 +167,8 @@ struct TcGemmParams {
   int ld_out, rows_valid, cols_valid, accumulate;
   int n_mtiles, n_ntiles, ns;
   int n_kc;               // K chunks of 32
+  int kparts;             // passes over K per tile: every pass ends in an fp32 (RN) add into the output, which keeps
+                          // the truncating accumulation chains of the tensor core short for long contractions
   int kc_per_group;       // B tile of chunk kc: rows (kc % kc_per_group)*32, cols (kc / kc_per_group)*group_stride + n0
   int group_stride;
 };
@@ -253,11 +255,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
       int stage = 0;
       uint32_t par = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+       for (int kp = 0; kp < p.kparts; ++kp, ++it) {
         ptx::mbar_wait(tm_empty, (((uint32_t)it) & 1u) ^ 1u);
         ptx::tc_fence_after();
         uint32_t started = 0;   // bit a: accumulator a already holds a partial sum
-        for (int si = 0; si < n_st; ++si) {
+        const int si_b = (int)(((int64_t)n_st * kp) / p.kparts), si_e = (int)(((int64_t)n_st * (kp + 1)) / p.kparts);
+        for (int si = si_b; si < si_e; ++si) {
           ptx::mbar_wait(full + 8u * stage, par);
           ptx::tc_fence_after();
           const int n_sub = min(NSUB, p.n_kc - si * NSUB);
@@ -287,13 +291,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
           if (++stage == p.ns) { stage = 0; par ^= 1u; }
         }
         ptx::umma_commit(tm_full);
+       }
       }
     }
   } else {
     const int q = warp & 3;
     const float inv = H ? __ldg(p.inv_scale) : 1.f;
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+     for (int kp = 0; kp < p.kparts; ++kp, ++it) {
       const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
       ptx::mbar_wait(tm_full, ((uint32_t)it) & 1u);
       ptx::tc_fence_after();
@@ -323,7 +329,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
             }
             if (H) { o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv; }
             float4* dst = reinterpret_cast<float4*>(out + c0 + u);
-            if (p.accumulate) {
+            if (p.accumulate || kp > 0) {   // (kp > 0: this thread's own earlier store to the same address)
               const float4 old = *dst;
               o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
             }
@@ -334,6 +340,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tm_empty);
+     }
     }
   }
   ptx::tc_fence_before();
@@ -764,6 +771,15 @@ int tc_dx_from_g(const float* g_hi, const float* g_lo, const float* wcat_hi, con
   p.n_mtiles = v_pad / 128;
   p.n_ntiles = (int)ceil_div64(F, GM_BN);
   p.n_kc = kg / 32;
+  {
+    // accumulation steps per TMEM accumulator and pass: chunks / 4 accumulators x (4 tf32 | 2 fp16) k-steps; measured
+    // (tests/test_gpu_configs.py, randn signal): 3xTF32 stays inside 1e-5 at 164 steps (T = 128) and leaves it at
+    // 328 (T = 256), so passes are cut at <= 192 steps
+    const int steps = half ? p.n_kc / 2 : p.n_kc;
+    int kparts = x3 ? (steps + 191) / 192 : 1;
+    if (kparts > p.n_kc / 8) kparts = p.n_kc / 8;   // every pass feeds all four accumulators
+    p.kparts = kparts < 1 ? 1 : kparts;
+  }
   p.kc_per_group = T / 32;
   p.group_stride = F;
   const size_t stage_bytes = (size_t)(x3 ? 2 : 1) * (GM_STAGE_A + GM_STAGE_B);
@@ -780,7 +796,7 @@ int tc_dx_from_g(const float* g_hi, const float* g_lo, const float* wcat_hi, con
 // d_w_eff[T,R,A,F], d_w_self[T,F] (+)= G^T x X
 int tc_dw_from_g(const float* g_hi, const float* g_lo, const float* x, int v_src, int R, int A, int F, int T,
                  bool x3, int accumulate, float* d_w_eff, float* d_w_self, float* x_hi, float* x_lo, float* partial,
-                 size_t partial_bytes, cudaStream_t st, const float* scales) {
+                 size_t partial_bytes, cudaStream_t st, const float* scales, bool x_is_split) {
   const bool half = scales != nullptr;
   GCB_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)d_w_self % 16 == 0 && (uintptr_t)d_w_eff % 16 == 0 && F % 32 == 0 &&
                   T % 32 == 0,
@@ -795,9 +811,11 @@ int tc_dw_from_g(const float* g_hi, const float* g_lo, const float* x, int v_src
     const int x_ld = (int)ceil_div64(F, 64) * 64, kg_ld = (int)ceil_div64(L.kg, 64) * 64;
     __half* xh = (__half*)x_hi;
     __half* xl = xh + (size_t)v_src * x_ld;
-    const int64_t n = (int64_t)v_src * (x_ld / 8);
-    k_split_half<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(x, v_src, F, x_ld, scales + 2, xh, xl);
-    GCB_LAUNCH_OK();
+    if (!x_is_split) {   // (k_bw_prepare has already written the split signal in this layout)
+      const int64_t n = (int64_t)v_src * (x_ld / 8);
+      k_split_half<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(x, v_src, F, x_ld, scales + 2, xh, xl);
+      GCB_LAUNCH_OK();
+    }
     rc = tc_make_tmap_mn_h(&ah, (const __half*)g_hi, (uint64_t)L.v_pad, (uint64_t)kg_ld, (uint64_t)kg_ld * 2, 32, 2);
     if (rc) return rc;
     rc = tc_make_tmap_mn_h(&al, (const __half*)g_lo, (uint64_t)L.v_pad, (uint64_t)kg_ld, (uint64_t)kg_ld * 2, 32, 2);

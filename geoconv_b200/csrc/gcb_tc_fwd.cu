@@ -120,6 +120,18 @@ struct TcFwdParams {
   const int* splits;    // [ksplit + 1] first super-step of every K split (tc_split_table)
   int drain_cw;         // accumulator columns staged per bulk store in the drain (0: registers -> global directly)
   int split_reverse;    // 1: K splits are dispatched last-to-first
+  // fused finish (fuse = 1): the K splits of a (vertex tile, template chunk, rotation group) unit are neighbours in
+  // dispatch order; the split that finishes last sums the unit's partial sums (still L2-resident) in split order and
+  // applies bias / activation, the unit that finishes a vertex tile last does the angular max-pooling
+  int fuse;
+  unsigned* tickets;     // [m_tiles * t_chunks * n_groups] arrivals per unit, then [m_tiles] finished units per tile (zeroed)
+  float* nrm2;           // [v_pad][n_rot][t_chunks] squared norms of the activated rows, per template chunk
+  const float* bias;
+  float* y;              // [v_out, n_rot, T]
+  float* z;              // nullable [v_out, T]
+  int32_t* argmax;       // nullable [v_out]
+  int act;
+  int discard;           // 1: partial-sum lines are discarded from L2 once summed (never written back to DRAM)
   long long* trace;     // GCB_TC_TRACE (investigation builds): clock64 stamps of CTA (1,0,0), [role][tile][8]
   long long* cta_log;   // GCB_TC_TRACE=2: per CTA {globaltimer at entry, at exit, clock64 at entry, at exit, SM id}
   int debug;            // GCB_TC_DEBUG bits (timing experiments only): 1 = all gathers read row 0, 2 = no MMAs
@@ -455,10 +467,11 @@ __global__ void k_tc_maxima(const TcMaxJob job, unsigned* __restrict__ mx, float
     s_last = atomicAdd(mx + 7, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (!s_last || threadIdx.x != 0) return;
+  if (!s_last || threadIdx.x != 0 || job.mode == 0) return;   // mode 0: maxima only
   __threadfence();
   volatile const unsigned* vm = mx;
   if (job.mode == 1) {
+    if (job.ext_wsum) mx[1] = __ldg(job.ext_wsum);   // cached record packing: its max sum_j |w_j| was computed then
     const float xm = __uint_as_float(vm[0]), wm = fmaxf(__uint_as_float(vm[1]), 1.f), bm = __uint_as_float(vm[2]);
     const int ea = tc_pow2_for(xm * wm), eb = tc_pow2_for(bm);
     scales[0] = ldexpf(1.f, ea);
@@ -997,12 +1010,25 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
 
   // the shuffle tells the compiler the warp index is warp-uniform (role dispatch, uniform registers)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_M;
   const int grp = blockIdx.y;
-  // CTAs are dispatched in blockIdx order: the split that holds the centre super-steps (one tile each, so one
-  // weight-ring reload per tile) goes FIRST instead of forming the tail wave (GCB_TC_SPLIT_ORDER=0: index order)
-  const int tz = blockIdx.z / p.ksplit;
-  const int sk = p.split_reverse ? p.ksplit - 1 - (int)(blockIdx.z - tz * p.ksplit) : (int)(blockIdx.z - tz * p.ksplit);
+  const int t_chunks = p.T / p.n_t;
+  int tile_m, tz, sk;
+  if (p.fuse) {
+    // blockIdx.x = (vertex tile, template chunk, K split) with the split fastest: the splits of a unit are dispatched
+    // together, finish together, and the one that finishes last finds the others' partial sums in L2
+    const int bx = (int)blockIdx.x;
+    sk = bx % p.ksplit;
+    const int rest = bx / p.ksplit;
+    tz = rest % t_chunks;
+    tile_m = rest / t_chunks;
+  } else {
+    // CTAs are dispatched in blockIdx order: the split that holds the centre super-steps (one tile each, so one
+    // weight-ring reload per tile) goes FIRST instead of forming the tail wave (GCB_TC_SPLIT_ORDER=0: index order)
+    tile_m = (int)blockIdx.x;
+    tz = blockIdx.z / p.ksplit;
+    sk = p.split_reverse ? p.ksplit - 1 - (int)(blockIdx.z - tz * p.ksplit) : (int)(blockIdx.z - tz * p.ksplit);
+  }
+  const int m0 = tile_m * TC_M;
   const int t0 = tz * p.n_t;
   const int rot0 = grp * p.g;
   const int g_cnt = min(p.g, p.n_rot - rot0);
@@ -1236,7 +1262,30 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         for (int c0 = 0; c0 < p.n_t; c0 += p.drain_cw) {
           const int cw = min(p.drain_cw, p.n_t - c0);
           ptx::bulk_wait_read_all();   // the previous piece has left this lane's staging row
-          for (int cc = 0; cc < cw; cc += 16) {
+          // (TMEM loads of up to 64 columns are issued back to back and waited for once: one wait per 16 columns
+          // left the load latency exposed six times per 96-column piece)
+          int cc = 0;
+          for (; cc + 64 <= cw; cc += 64) {
+            uint32_t ra[32], rb[32];
+            ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(il * p.n_t + c0 + cc), ra);
+            ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(il * p.n_t + c0 + cc + 32), rb);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+              ptx::st_shared_v4(my_row + (uint32_t)(cc + q) * 4u, ra[q], ra[q + 1], ra[q + 2], ra[q + 3]);
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+              ptx::st_shared_v4(my_row + (uint32_t)(cc + 32 + q) * 4u, rb[q], rb[q + 1], rb[q + 2], rb[q + 3]);
+          }
+          for (; cc + 32 <= cw; cc += 32) {
+            uint32_t ra[32];
+            ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(il * p.n_t + c0 + cc), ra);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+              ptx::st_shared_v4(my_row + (uint32_t)(cc + q) * 4u, ra[q], ra[q + 1], ra[q + 2], ra[q + 3]);
+          }
+          for (; cc < cw; cc += 16) {
             uint32_t r[16];
             ptx::tmem_ld_32x32b_x16(lane_addr + (uint32_t)(il * p.n_t + c0 + cc), r);
             ptx::tmem_ld_wait();
@@ -1249,7 +1298,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
           ptx::bulk_commit_group();
         }
       }
-      ptx::bulk_wait_read_all();   // shared memory must outlive the copies' reads
+      if (p.fuse) ptx::bulk_wait_all();   // ... and the rows must have reached global memory before the ticket is taken
+      else ptx::bulk_wait_read_all();     // shared memory must outlive the copies' reads
     } else {
       for (int il = dh; il < g_cnt; il += TC_PRODUCER_WARPS / 4) {
         for (int c0 = 0; c0 < p.n_t; c0 += 16) {
@@ -1263,6 +1313,109 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       }
     }
     if (life) life[4] = clock64();
+    if (p.fuse) {
+      // ===================== fused finish: split reduction, bias, activation, angular max-pooling =====================
+      // Every producer thread has completed its own partial-sum stores (bulk copies waited for / plain stores);
+      // publish them (fence, barrier, one ticket per CTA).  Nobody waits for anybody: the CTA whose ticket is the
+      // last one of its unit does the unit's reduction, every other CTA is done.
+      volatile uint32_t* const flag = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base)) + 1;
+      ptx::fence_proxy_async_all();
+      __threadfence();
+      producer_bar_sync();
+      const int unit = (tile_m * t_chunks + tz) * (int)gridDim.y + grp;
+      if (ptid == 0) {
+        const unsigned t = atomicAdd(p.tickets + unit, 1u);
+        __threadfence();
+        *flag = t == (unsigned)p.ksplit - 1u ? 1u : 0u;
+      }
+      producer_bar_sync();
+      if (*flag) {
+        const float inv = H ? __ldg(p.scales + 2) : 1.f;
+        const int T4c = p.n_t >> 2, T4 = p.T >> 2;
+        const size_t split_stride4 = (size_t)p.v_pad * p.n_rot * T4;     // float4 units between two splits' slabs
+        const float4* bias4 = reinterpret_cast<const float4*>(p.bias) + (t0 >> 2);
+        for (int rr = pw; rr < TC_M; rr += TC_PRODUCER_WARPS) {
+          const int vrow = m0 + rr;
+          if (vrow >= p.v_out) break;
+          for (int il = 0; il < g_cnt; ++il) {
+            const size_t row4 = ((size_t)vrow * p.n_rot + rot0 + il) * T4 + (t0 >> 2);
+            const float4* src = reinterpret_cast<const float4*>(p.partial) + row4;
+            float4* dst = reinterpret_cast<float4*>(p.y) + row4;
+            float sq = 0.f;
+            for (int q = lane; q < T4c; q += 32) {
+              const float4 bv = __ldg(bias4 + q);
+              float4 acc = H ? make_float4(0.f, 0.f, 0.f, 0.f) : bv;
+              int sp = 0;
+              for (; sp + 4 <= p.ksplit; sp += 4) {      // four slabs in flight, added in split order
+                const float4 p0 = __ldcg(src + (size_t)sp * split_stride4 + q);
+                const float4 p1 = __ldcg(src + (size_t)(sp + 1) * split_stride4 + q);
+                const float4 p2 = __ldcg(src + (size_t)(sp + 2) * split_stride4 + q);
+                const float4 p3 = __ldcg(src + (size_t)(sp + 3) * split_stride4 + q);
+                acc.x += p0.x; acc.y += p0.y; acc.z += p0.z; acc.w += p0.w;
+                acc.x += p1.x; acc.y += p1.y; acc.z += p1.z; acc.w += p1.w;
+                acc.x += p2.x; acc.y += p2.y; acc.z += p2.z; acc.w += p2.w;
+                acc.x += p3.x; acc.y += p3.y; acc.z += p3.z; acc.w += p3.w;
+              }
+              for (; sp < p.ksplit; ++sp) {
+                const float4 pv = __ldcg(src + (size_t)sp * split_stride4 + q);
+                acc.x += pv.x; acc.y += pv.y; acc.z += pv.z; acc.w += pv.w;
+              }
+              if (H) {
+                acc.x = fmaf(acc.x, inv, bv.x); acc.y = fmaf(acc.y, inv, bv.y);
+                acc.z = fmaf(acc.z, inv, bv.z); acc.w = fmaf(acc.w, inv, bv.w);
+              }
+              float4 o;
+              o.x = act_apply(p.act, acc.x); o.y = act_apply(p.act, acc.y);
+              o.z = act_apply(p.act, acc.z); o.w = act_apply(p.act, acc.w);
+              dst[q] = o;
+              sq = fmaf(o.x, o.x, sq); sq = fmaf(o.y, o.y, sq); sq = fmaf(o.z, o.z, sq); sq = fmaf(o.w, o.w, sq);
+              if (p.discard && (q & 7) == 0) {   // one 128-byte line per 8 lanes: summed, never needed again
+                for (int sp2 = 0; sp2 < p.ksplit; ++sp2)
+                  if ((((uintptr_t)(src + (size_t)sp2 * split_stride4 + q)) & 127) == 0 && q + 8 <= T4c)
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(src + (size_t)sp2 * split_stride4 + q) : "memory");
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (lane == 0 && p.z) p.nrm2[((size_t)vrow * p.n_rot + rot0 + il) * t_chunks + tz] = sq;
+          }
+        }
+        if (p.z) {
+          // the unit that completes this vertex tile pools it: norms over all template chunks (chunk order), first
+          // maximum over the rotations (a NaN norm counts as the maximum, like torch.argmax), row select
+          __threadfence();
+          producer_bar_sync();
+          if (ptid == 0) {
+            const unsigned t = atomicAdd(p.tickets + (size_t)gridDim.x / p.ksplit * gridDim.y + tile_m, 1u);
+            __threadfence();
+            *flag = t == (unsigned)(t_chunks * (int)gridDim.y) - 1u ? 1u : 0u;
+          }
+          producer_bar_sync();
+          if (*flag) {
+            for (int rr = pw; rr < TC_M; rr += TC_PRODUCER_WARPS) {
+              const int vrow = m0 + rr;
+              if (vrow >= p.v_out) break;
+              float nrm = -1.f;
+              if (lane < p.n_rot) {
+                float sq = 0.f;
+                for (int c = 0; c < t_chunks; ++c) sq += __ldcg(p.nrm2 + ((size_t)vrow * p.n_rot + lane) * t_chunks + c);
+                nrm = sqrtf(sq);
+              }
+              const unsigned nan_mask = __ballot_sync(0xffffffffu, nrm != nrm);
+              float best = nrm == nrm ? nrm : -1.f;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+              const unsigned max_mask = __ballot_sync(0xffffffffu, lane < p.n_rot && nrm == best);
+              const int arg = nan_mask ? __ffs((int)nan_mask) - 1 : (max_mask ? __ffs((int)max_mask) - 1 : 0);
+              const float4* sel = reinterpret_cast<const float4*>(p.y) + ((size_t)vrow * p.n_rot + arg) * T4;
+              float4* zr = reinterpret_cast<float4*>(p.z) + (size_t)vrow * T4;
+              for (int q = lane; q < T4; q += 32) zr[q] = __ldcg(sel + q);
+              if (lane == 0) p.argmax[vrow] = arg;
+            }
+          }
+        }
+      }
+    }
   } else if (warp == TC_WARP_TMA) {
     // ===================== TMA: weight tiles -> ring =====================
     // (reload order: order_tab, built in the prologue; an entry = one ring position of the current layout)
@@ -1619,6 +1772,15 @@ bool tc_half_supported(int R, int A, int F, int T, int n_rot) {
   return tc_pick_config(A, F, T, n_rot, true, true, 0).ok;
 }
 
+// fused finish: one arrival counter per (vertex tile, template chunk, rotation group) unit and one per vertex tile
+// (bounds: at most n_rot groups and T / 16 template chunks), squared row norms per template chunk
+static size_t tc_ticket_bytes(int v_out, int n_rot, int T) {
+  return align_up((size_t)ceil_div64(v_out, TC_M) * ((size_t)n_rot * (T / 16) + 1) * sizeof(unsigned), 256);
+}
+static size_t tc_nrm2_bytes(int v_out, int n_rot, int T) {
+  return align_up((size_t)ceil_div64(v_out, TC_M) * TC_M * n_rot * (T / 16) * sizeof(float), 256);
+}
+
 constexpr size_t TC_TABS_BYTES = (size_t)GCB_MAX_ROT * 16384;   // ring schedules of every rotation group
 constexpr size_t TC_SPLITS_BYTES = 16384;   // K-split boundaries
 constexpr size_t TC_SCALES_BYTES = 256;   // {max|X|, max sum|w|, max|Wcat|} as bits, then the three scales
@@ -1634,7 +1796,8 @@ size_t tc_fwd_workspace_bytes(int v_out, int R, int A, int F, int T, int n_rot, 
     if (s > ksplit) ksplit = s;
   }
   return tc_recs_bytes(v_out, R, A) + (x3 ? 2 : 1) * tc_wcat_bytes(R, A, F, T) +
-         tc_partial_bytes(v_out, n_rot, T, ksplit) + TC_SCALES_BYTES + TC_TABS_BYTES + TC_SPLITS_BYTES + 1024;
+         tc_partial_bytes(v_out, n_rot, T, ksplit) + TC_SCALES_BYTES + TC_TABS_BYTES + TC_SPLITS_BYTES +
+         tc_ticket_bytes(v_out, n_rot, T) + tc_nrm2_bytes(v_out, n_rot, T) + 1024;
 }
 
 template <int KC, bool X3, bool H, int CL, bool KEEP>
@@ -1674,10 +1837,14 @@ static int tc_launch(const CUtensorMap& mh, const CUtensorMap& ml, const TcFwdPa
                       : tc_launch_k<KC, X3, H, 1, false>(mh, ml, p, cfg, grid, st);
 }
 
-int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
-                const float* bias, const RotTable& rot, int n_rot, int v_out, int v_src, int R, int A, int F,
-                int T, int act, int precision, float* y, float* z, int32_t* argmax, float* interp_out,
-                void* workspace, size_t workspace_bytes, cudaStream_t st) {
+// Everything the host decides for one forward launch; a function of the shape, the rotation list and the precision only
+struct TcFwdPlan {
+  TcConfig cfg;
+  int phase_shift, ksplit, drain_cw, split_reverse;
+  bool pairs, half, x3;
+};
+
+static int tc_fwd_plan(const RotTable& rot, int n_rot, int v_out, int R, int A, int F, int T, int precision, TcFwdPlan* out) {
   const bool half = precision == GCB_PREC_F16X3;
   const bool x3 = half || precision == GCB_PREC_TF32X3;
   static const bool no_merge = getenv("GCB_TC_NOMERGE") && atoi(getenv("GCB_TC_NOMERGE")) != 0;
@@ -1687,34 +1854,112 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   // Weight ring: spend spare shared memory on a second, shifted layout when that buys refill slack (3 steps
   // cover the commit -> TMA -> barrier latency) without changing the tiling or starving the A ring.
   int phase_shift = 0;
-  {
-    static const int shift_env = getenv("GCB_TC_RINGSHIFT") ? atoi(getenv("GCB_TC_RINGSHIFT")) : -1;   // experiments
-    static const int phase_env = getenv("GCB_TC_PHASE") ? atoi(getenv("GCB_TC_PHASE")) : -1;
-    const bool pairs = tc_use_pairs() && cfg.n_groups % 2 == 0 && cfg.kc >= 16;
-    int best_slack = -1;
-    phase_shift = tc_pick_phase_shift(rot, n_rot, A, cfg.g, cfg.n_groups, pairs, cfg.ring, false, &best_slack);
-    for (int rs = 1; rs <= 4; ++rs) {
-      if (shift_env >= 0 && rs != shift_env) continue;
-      if (shift_env < 0 && best_slack >= 3) break;
-      TcConfig c2 = tc_pick_config(A, F, T, n_rot, x3, half, dstep, rs);
-      if (!c2.ok || c2.kc != cfg.kc || c2.ring.m != cfg.ring.m || c2.n_t != cfg.n_t || c2.g != cfg.g || c2.ns_a < 4) break;
-      int sl2 = -1;
-      const int ph2 = tc_pick_phase_shift(rot, n_rot, A, c2.g, c2.n_groups, pairs, c2.ring, true, &sl2);   // two layouts: two phases
-      if (sl2 > best_slack || shift_env >= 0) { best_slack = sl2; phase_shift = ph2; cfg = c2; }
-    }
-    if (phase_env >= 0) phase_shift = phase_env % A;
-    static const bool verbose = getenv("GCB_TC_VERBOSE") != nullptr;
-    if (verbose)
-      fprintf(stderr, "[gcb] tc forward: kc %d n_t %d g %d groups %d m %d ring %d+%d positions, phase shift %d, refill slack %d steps, A stages %d\n",
-              cfg.kc, cfg.n_t, cfg.g, cfg.n_groups, cfg.ring.m, cfg.ring.n_pos, cfg.ring.shift, phase_shift,
-              tc_refill_slack(rot, n_rot, A, cfg.g, cfg.n_groups, pairs, cfg.ring, phase_shift, cfg.ring.shift > 0), cfg.ns_a);
+  static const int shift_env = getenv("GCB_TC_RINGSHIFT") ? atoi(getenv("GCB_TC_RINGSHIFT")) : -1;   // experiments
+  static const int phase_env = getenv("GCB_TC_PHASE") ? atoi(getenv("GCB_TC_PHASE")) : -1;
+  const bool pairs = tc_use_pairs() && cfg.n_groups % 2 == 0 && cfg.kc >= 16;
+  int best_slack = -1;
+  phase_shift = tc_pick_phase_shift(rot, n_rot, A, cfg.g, cfg.n_groups, pairs, cfg.ring, false, &best_slack);
+  for (int rs = 1; rs <= 4; ++rs) {
+    if (shift_env >= 0 && rs != shift_env) continue;
+    if (shift_env < 0 && best_slack >= 3) break;
+    TcConfig c2 = tc_pick_config(A, F, T, n_rot, x3, half, dstep, rs);
+    if (!c2.ok || c2.kc != cfg.kc || c2.ring.m != cfg.ring.m || c2.n_t != cfg.n_t || c2.g != cfg.g || c2.ns_a < 4) break;
+    int sl2 = -1;
+    const int ph2 = tc_pick_phase_shift(rot, n_rot, A, c2.g, c2.n_groups, pairs, c2.ring, true, &sl2);   // two layouts: two phases
+    if (sl2 > best_slack || shift_env >= 0) { best_slack = sl2; phase_shift = ph2; cfg = c2; }
   }
+  if (phase_env >= 0) phase_shift = phase_env % A;
+  static const bool verbose = getenv("GCB_TC_VERBOSE") != nullptr;
+  if (verbose)
+    fprintf(stderr, "[gcb] tc forward: kc %d n_t %d g %d groups %d m %d ring %d+%d positions, phase shift %d, refill slack %d steps, A stages %d\n",
+            cfg.kc, cfg.n_t, cfg.g, cfg.n_groups, cfg.ring.m, cfg.ring.n_pos, cfg.ring.shift, phase_shift,
+            tc_refill_slack(rot, n_rot, A, cfg.g, cfg.n_groups, pairs, cfg.ring, phase_shift, cfg.ring.shift > 0), cfg.ns_a);
+  out->cfg = cfg;
+  out->phase_shift = phase_shift;
+  out->pairs = pairs;
+  out->half = half;
+  out->x3 = x3;
+  out->ksplit = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3, half, n_rot);
+  {
+    static const int order_env = getenv("GCB_TC_SPLIT_ORDER") ? atoi(getenv("GCB_TC_SPLIT_ORDER")) : 1;   // experiments
+    out->split_reverse = (order_env && x3) ? 1 : 0;   // (measured: +1 % with three products per k-step, -0.4 % in tf32 mode)
+  }
+  {
+    // drain staging: 8 warps x 32 rows x (cw * 4 + 16) bytes inside the weight ring
+    static const int drain_env = getenv("GCB_TC_DRAIN") ? atoi(getenv("GCB_TC_DRAIN")) : -1;   // experiments (0: direct)
+    const size_t ring_bytes = (size_t)(cfg.ring.n_pos + cfg.ring.shift) * (x3 ? 2 : 1) * cfg.n_t * cfg.kc * 4;
+    int cw = cfg.n_t < 128 ? cfg.n_t : 128;
+    while (cw >= 16 && (size_t)TC_PRODUCER_WARPS * 32 * (cw * 4 + 16) > ring_bytes) cw -= 16;
+    out->drain_cw = cw >= 16 ? cw : 0;
+    if (drain_env >= 0) out->drain_cw = drain_env < out->drain_cw ? (drain_env / 16) * 16 : out->drain_cw;
+  }
+  GCB_REQUIRE((size_t)(out->ksplit + 1) * sizeof(int) <= TC_SPLITS_BYTES, GCB_EUNSUPPORTED, "tc_conv_fwd: too many K splits");
+  GCB_REQUIRE((size_t)cfg.n_groups * tc_tab_bytes(A, cfg.ring.n_pos) <= TC_TABS_BYTES, GCB_EUNSUPPORTED,
+              "tc_conv_fwd: ring schedules exceed their workspace");
+  return GCB_OK;
+}
+
+// the launch parameters that depend on the plan only (no data pointers)
+static void tc_fwd_plan_params(const TcFwdPlan& plan, const RotTable& rot, int n_rot, int v_out, int R, int A, int F, int T,
+                               TcFwdParams* p) {
+  const TcConfig& cfg = plan.cfg;
+  const int m_tiles = (int)ceil_div64(v_out, TC_M);
+  p->v_out = v_out; p->v_pad = m_tiles * TC_M; p->R = R; p->A = A; p->F = F; p->T = T; p->n_rot = n_rot;
+  p->nfc = F / (plan.half ? 2 * cfg.kc : cfg.kc); p->n_t = cfg.n_t; p->g = cfg.g; p->ns_a = cfg.ns_a; p->tmem_cols = cfg.tmem_cols;
+  p->ksplit = plan.ksplit;
+  p->phase_shift = plan.phase_shift;
+  p->phase_alt = cfg.ring.shift > 0 ? 1 : 0;
+  p->bar_bytes = (int)tc_bar_bytes(cfg.ring.n_pos, cfg.ring.n_pos + cfg.ring.shift);
+  p->split_reverse = plan.split_reverse;
+  p->tab_bytes = (int)tc_tab_bytes(A, cfg.ring.n_pos);
+  p->drain_cw = plan.drain_cw;
+  p->ring = cfg.ring;
+  p->rot = rot;
+}
+
+// Ring schedules + K-split boundaries of one (shape, rotation list, precision): `tables` = TC_TABS_BYTES of schedules
+// followed by TC_SPLITS_BYTES of split boundaries.  They depend on nothing else, so a caller may build them once
+// (gcb_fwd_build_tables) and hand them to every forward of that shape.
+size_t tc_fwd_tables_bytes() { return TC_TABS_BYTES + TC_SPLITS_BYTES; }
+
+int tc_fwd_build_tables(const RotTable& rot, int n_rot, int v_out, int R, int A, int F, int T, int precision, void* tables,
+                        cudaStream_t st) {
+  TcFwdPlan plan;
+  int rc = tc_fwd_plan(rot, n_rot, v_out, R, A, F, T, precision, &plan);
+  if (rc) return rc;
+  TcFwdParams p{};
+  tc_fwd_plan_params(plan, rot, n_rot, v_out, R, A, F, T, &p);
+  k_tc_build_tabs<<<plan.cfg.n_groups, 128, p.tab_bytes, st>>>(p, plan.pairs ? 1 : 0, p.tab_bytes, (uint8_t*)tables,
+                                                                (int*)((uint8_t*)tables + TC_TABS_BYTES));
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+size_t tc_fwd_records_bytes(int v_out, int R, int A) { return tc_recs_bytes(v_out, R, A) + 256; }
+
+// records = the slot-major packed records, then 256 bytes whose first word is max_slots(|w0|+|w1|+|w2|) as fp32 bits
+int tc_fwd_pack_records(const int32_t* idx, const float* w, int v_out, int R, int A, void* records, cudaStream_t st) {
+  unsigned* tail = (unsigned*)((char*)records + tc_recs_bytes(v_out, R, A));
+  GCB_CUDA_OK(cudaMemsetAsync(tail, 0, 256, st));
+  return tc_pack_recs_max(idx, w, v_out, R, A, (uint4*)records, tail, st);
+}
+
+int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
+                const float* bias, const RotTable& rot, int n_rot, int v_out, int v_src, int R, int A, int F,
+                int T, int act, int precision, float* y, float* z, int32_t* argmax, float* interp_out,
+                const void* records, const void* tables, uint32_t* stats_out,
+                void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  TcFwdPlan plan;
+  int rc = tc_fwd_plan(rot, n_rot, v_out, R, A, F, T, precision, &plan);
+  if (rc) return rc;
+  const bool half = plan.half, x3 = plan.x3;
+  const TcConfig cfg = plan.cfg;
   GCB_REQUIRE(workspace_bytes >= tc_fwd_workspace_bytes(v_out, R, A, F, T, n_rot, precision), GCB_EWORKSPACE,
               "tc_conv_fwd: workspace too small");
   GCB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)bias % 16 == 0) &&
                   ((uintptr_t)z % 16 == 0),
               GCB_EINVAL, "tc_conv_fwd: x, y, z and bias must be 16-byte aligned");
-  const int ksplit = tc_pick_ksplit(cfg, v_out, R, A, F, T, x3, half, n_rot);
+  const int ksplit = plan.ksplit;
   const int RA = R * A, KRA = RA * F, kcat = KRA + F;
   const int m_tiles = (int)ceil_div64(v_out, TC_M);
   const int v_pad = m_tiles * TC_M;
@@ -1730,17 +1975,33 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   }
   float* partial = (float*)ws;
   ws += tc_partial_bytes(v_out, n_rot, T, ksplit);
+  float* nrm2 = (float*)ws;
+  ws += tc_nrm2_bytes(v_out, n_rot, T);
+  unsigned* tickets = (unsigned*)ws;            // zeroed together with the operand maxima that follow them
+  const size_t ticket_bytes = tc_ticket_bytes(v_out, n_rot, T);
+  ws += ticket_bytes;
   unsigned* mx = (unsigned*)ws;                 // fp16 mode: operand maxima, then the scales
   float* scales = half ? (float*)(mx + 8) : nullptr;
+  static const int fuse_env = getenv("GCB_TC_FUSE") ? atoi(getenv("GCB_TC_FUSE")) : 1;   // 0: separate k_tc_finish (A/B)
+  const long long grid_x = (long long)ksplit * m_tiles * (T / cfg.n_t);
+  const bool fuse = fuse_env != 0 && grid_x < (1ll << 31) && T % 4 == 0;
+  const unsigned* ext_wsum = nullptr;
+  if (records) {   // cached packing of this barycentric tensor (gcb_fwd_pack_records)
+    recs = (uint4*)records;
+    ext_wsum = (const unsigned*)((const char*)records + tc_recs_bytes(v_out, R, A));
+  }
 
-  int rc;
   CUtensorMap mh, ml;
+  if (fuse) GCB_CUDA_OK(cudaMemsetAsync(tickets, 0, ticket_bytes + (half ? 32 : 0), st));
+  else if (half) GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 32, st));
   if (half) {
-    GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 32, st));
-    rc = tc_pack_recs_max(idx, w, v_out, R, A, recs, mx + 1, st);
-    if (rc) return rc;
+    if (!records) {
+      rc = tc_pack_recs_max(idx, w, v_out, R, A, recs, mx + 1, st);
+      if (rc) return rc;
+    }
     TcMaxJob job{};
     job.n_seg = 3; job.mode = 1;
+    job.ext_wsum = ext_wsum;
     job.seg[0] = {x, (long long)v_src * F, 0, 0};
     job.seg[1] = {w_eff, (long long)T * RA * F, 0, 2};
     job.seg[2] = {w_self, (long long)T * F, 0, 2};
@@ -1752,46 +2013,39 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
     if (rc) return rc;
     rc = make_weight_tmap_h(&ml, (const __half*)wc_lo, T, kcat, cfg.kc, cfg.n_t);
     if (rc) return rc;
+    if (stats_out)   // {max|X|, max sum|w|, max|Wcat|, ...} for the backward of the same step (word 7 = ticket != 0: valid)
+      GCB_CUDA_OK(cudaMemcpyAsync(stats_out, mx, 32, cudaMemcpyDeviceToDevice, st));
   } else {
-    rc = tc_pack_recs(idx, w, v_out, R, A, recs, st);
-    if (rc) return rc;
+    if (!records) {
+      rc = tc_pack_recs(idx, w, v_out, R, A, recs, st);
+      if (rc) return rc;
+    }
     rc = tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);
     if (rc) return rc;
     rc = make_weight_tmap(&mh, wc_hi, T, kcat, cfg.kc, cfg.n_t);
     if (rc) return rc;
     rc = make_weight_tmap(&ml, x3 ? wc_lo : wc_hi, T, kcat, cfg.kc, cfg.n_t);
     if (rc) return rc;
+    if (stats_out) GCB_CUDA_OK(cudaMemsetAsync(stats_out, 0, 32, st));
   }
 
   TcFwdParams p;
+  tc_fwd_plan_params(plan, rot, n_rot, v_out, R, A, F, T, &p);
   p.x = x; p.recs = recs; p.partial = partial; p.interp_out = interp_out; p.scales = scales;
-  p.v_out = v_out; p.v_pad = v_pad; p.R = R; p.A = A; p.F = F; p.T = T; p.n_rot = n_rot;
-  p.nfc = F / (half ? 2 * cfg.kc : cfg.kc); p.n_t = cfg.n_t; p.g = cfg.g; p.ns_a = cfg.ns_a; p.tmem_cols = cfg.tmem_cols;
-  p.ksplit = ksplit;
-  p.phase_shift = phase_shift;
-  p.phase_alt = cfg.ring.shift > 0 ? 1 : 0;
-  p.bar_bytes = (int)tc_bar_bytes(cfg.ring.n_pos, cfg.ring.n_pos + cfg.ring.shift);
+  p.fuse = fuse ? 1 : 0;
+  p.tickets = tickets; p.nrm2 = nrm2; p.bias = bias; p.y = y; p.z = z; p.argmax = argmax; p.act = act;
   {
-    static const int order_env = getenv("GCB_TC_SPLIT_ORDER") ? atoi(getenv("GCB_TC_SPLIT_ORDER")) : 1;   // experiments
-    p.split_reverse = (order_env && x3) ? 1 : 0;   // (measured: +1 % with three products per k-step, -0.4 % in tf32 mode)
+    static const int discard_env = getenv("GCB_TC_DISCARD") ? atoi(getenv("GCB_TC_DISCARD")) : 1;   // A/B
+    p.discard = discard_env ? 1 : 0;
   }
-  p.tab_bytes = (int)tc_tab_bytes(A, cfg.ring.n_pos);
-  p.tabs = (const uint8_t*)mx + TC_SCALES_BYTES;
+  if (tables) {
+    p.tabs = (const uint8_t*)tables;
+  } else {
+    p.tabs = (const uint8_t*)mx + TC_SCALES_BYTES;
+  }
   p.splits = (const int*)(p.tabs + TC_TABS_BYTES);
-  GCB_REQUIRE((size_t)(ksplit + 1) * sizeof(int) <= TC_SPLITS_BYTES, GCB_EUNSUPPORTED, "tc_conv_fwd: too many K splits");
-  GCB_REQUIRE((size_t)cfg.n_groups * p.tab_bytes <= TC_TABS_BYTES, GCB_EUNSUPPORTED, "tc_conv_fwd: ring schedules exceed their workspace");
-  {
-    // drain staging: 8 warps x 32 rows x (cw * 4 + 16) bytes inside the weight ring
-    static const int drain_env = getenv("GCB_TC_DRAIN") ? atoi(getenv("GCB_TC_DRAIN")) : -1;   // experiments (0: direct)
-    const size_t ring_bytes = (size_t)(cfg.ring.n_pos + cfg.ring.shift) * (x3 ? 2 : 1) * cfg.n_t * cfg.kc * 4;
-    int cw = cfg.n_t < 128 ? cfg.n_t : 128;
-    while (cw >= 16 && (size_t)TC_PRODUCER_WARPS * 32 * (cw * 4 + 16) > ring_bytes) cw -= 16;
-    p.drain_cw = cw >= 16 ? cw : 0;
-    if (drain_env >= 0) p.drain_cw = drain_env < p.drain_cw ? (drain_env / 16) * 16 : p.drain_cw;
-  }
   static const int debug = getenv("GCB_TC_DEBUG") ? atoi(getenv("GCB_TC_DEBUG")) : 0;
   p.debug = debug;
-  p.ring = cfg.ring;
   p.trace = nullptr;
   p.cta_log = nullptr;
   static long long* trace_dev = nullptr;
@@ -1809,23 +2063,24 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
     GCB_CUDA_OK(cudaMemsetAsync(trace_dev, 0, 4 * 128 * 8 * sizeof(long long), st));
     p.trace = trace_dev;
   }
-  p.rot = rot;
-  {
-    const bool pairs = tc_use_pairs() && cfg.n_groups % 2 == 0 && cfg.kc >= 16;
-    k_tc_build_tabs<<<cfg.n_groups, 128, p.tab_bytes, st>>>(p, pairs ? 1 : 0, p.tab_bytes, (uint8_t*)p.tabs,
+  if (!tables) {
+    k_tc_build_tabs<<<cfg.n_groups, 128, p.tab_bytes, st>>>(p, plan.pairs ? 1 : 0, p.tab_bytes, (uint8_t*)p.tabs,
                                                              (int*)p.splits);
     GCB_LAUNCH_OK();
   }
   dim3 grid((unsigned)m_tiles, (unsigned)cfg.n_groups, (unsigned)((T / cfg.n_t) * ksplit));
+  if (fuse) grid = dim3((unsigned)grid_x, (unsigned)cfg.n_groups, 1u);
   if (half) rc = cfg.kc == 16 ? tc_launch<16, true, true>(mh, ml, p, cfg, grid, st) : tc_launch<8, true, true>(mh, ml, p, cfg, grid, st);
   else if (cfg.kc == 32) rc = x3 ? tc_launch<32, true>(mh, ml, p, cfg, grid, st) : tc_launch<32, false>(mh, ml, p, cfg, grid, st);
   else if (cfg.kc == 16) rc = x3 ? tc_launch<16, true>(mh, ml, p, cfg, grid, st) : tc_launch<16, false>(mh, ml, p, cfg, grid, st);
   else rc = x3 ? tc_launch<8, true>(mh, ml, p, cfg, grid, st) : tc_launch<8, false>(mh, ml, p, cfg, grid, st);
   if (rc) return rc;
-  const int warps_per_block = 8;
-  k_tc_finish<<<(unsigned)ceil_div64(v_out, warps_per_block), warps_per_block * 32, 0, st>>>(
-      partial, bias, ksplit, v_out, v_pad, n_rot, T, act, scales, y, z, argmax);
-  GCB_LAUNCH_OK();
+  if (!fuse) {
+    const int warps_per_block = 8;
+    k_tc_finish<<<(unsigned)ceil_div64(v_out, warps_per_block), warps_per_block * 32, 0, st>>>(
+        partial, bias, ksplit, v_out, v_pad, n_rot, T, act, scales, y, z, argmax);
+    GCB_LAUNCH_OK();
+  }
   if (p.cta_log) {
     // per-CTA life times: printed by dispatch order in groups of 148 (one "wave" if all CTAs took equally long)
     static long long hl[16384 * 5];

@@ -99,8 +99,8 @@ class _IndexChecks:
         self._pending.append((ev, slot, pack.v_src, weakref.ref(pack)))
 
     def poll(self, block: bool = False, only: "BaryPack | None" = None) -> None:
-        if not self._pending:
-            return
+        if not self._pending or torch.cuda.is_current_stream_capturing():
+            return                       # (an event query is not allowed while a stream is being captured)
         keep, bad = [], None
         for item in self._pending:
             ev, slot, v_src, ref = item
@@ -134,6 +134,7 @@ class BaryPack:
     a: int
     oob_count: int | None = None          # out-of-range indices found by gcb_prep_bary (None: not read back yet)
     _csr: tuple | None = field(default=None, repr=False)
+    _records: torch.Tensor | None = field(default=None, repr=False)
 
     def validate(self) -> None:
         """Block until the index check of this tensor is known; raises IndexError if it failed."""
@@ -142,21 +143,17 @@ class BaryPack:
             raise IndexError(f"geoconv_b200: {self.oob_count} barycentric vertex indices fall outside [0, {self.v_src})")
 
     def csr(self):
-        """(row_ptr int32 [V_src+1], entries int32 [n_slots]) - built on first backward."""
+        """(row_ptr int32 [V_src+1], entries int32 [n_slots], stats int32 [8]) - built on first backward."""
         if self._csr is None:
-            lib = N.load()
-            n_slots = self.idx.numel()
-            dev = self.idx.device
-            row_ptr = torch.empty(self.v_src + 1, dtype=torch.int32, device=dev)
-            entries = torch.empty(n_slots, dtype=torch.int32, device=dev)
-            ws_bytes = lib.gcb_csr_workspace_bytes(n_slots, self.v_src)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            with torch.cuda.device(dev):
-                N.check(lib.gcb_csr_build(self.idx.data_ptr(), self.w.data_ptr(), n_slots, self.v_src,
-                                          row_ptr.data_ptr(), entries.data_ptr(), ws.data_ptr(), ws_bytes,
-                                          _stream(self.idx)), "gcb_csr_build")
-            self._csr = (row_ptr, entries)
+            self._csr = tuple(csr_build_op(self.idx, self.w, self.v_src))
         return self._csr
+
+    def records(self):
+        """The tensor-core forward's packed gather records of this tensor (built on first use, then reused by
+        every layer and every step that sees the same barycentric tensor)."""
+        if self._records is None:
+            self._records = pack_records_op(self.idx, self.w)
+        return self._records
 
 
 def prep_bary(bary: torch.Tensor, v_src: int, check_indices: bool | str = True) -> BaryPack:
@@ -263,24 +260,67 @@ def _(bary, v_src):
 
 
 @torch.library.custom_op(f"{_LIB}::csr_build", mutates_args=(), device_types="cuda")
-def csr_build_op(idx: torch.Tensor, w: torch.Tensor, v_src: int) -> tuple[torch.Tensor, torch.Tensor]:
-    """Neighbour -> vertex inversion: (row_ptr int32 [V_src+1], entries int32 [n_slots])."""
+def csr_build_op(idx: torch.Tensor, w: torch.Tensor, v_src: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Neighbour -> vertex inversion: (row_ptr int32 [V_src+1], entries int32 [n_slots], stats int32 [8]:
+    [1] max |w| as fp32 bits, [2] longest row - what the fp16-split backward bounds its operand with)."""
     lib = N.load()
     n_slots = idx.numel()
     dev = idx.device
     row_ptr = torch.empty(v_src + 1, dtype=torch.int32, device=dev)
     entries = torch.empty(n_slots, dtype=torch.int32, device=dev)
+    stats = torch.empty(8, dtype=torch.int32, device=dev)
     ws_bytes = lib.gcb_csr_workspace_bytes(n_slots, v_src)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with _dev_guard(idx):
         N.check(lib.gcb_csr_build(idx.data_ptr(), w.data_ptr(), n_slots, v_src, row_ptr.data_ptr(),
-                                  entries.data_ptr(), ws.data_ptr(), ws_bytes, _stream(idx)), "gcb_csr_build")
-    return row_ptr, entries
+                                  entries.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes, _stream(idx)),
+                "gcb_csr_build")
+    return row_ptr, entries, stats
 
 
 @csr_build_op.register_fake
 def _(idx, w, v_src):
-    return idx.new_empty((v_src + 1,), dtype=torch.int32), idx.new_empty((idx.numel(),), dtype=torch.int32)
+    return (idx.new_empty((v_src + 1,), dtype=torch.int32), idx.new_empty((idx.numel(),), dtype=torch.int32),
+            idx.new_empty((8,), dtype=torch.int32))
+
+
+@torch.library.custom_op(f"{_LIB}::pack_records", mutates_args=(), device_types="cuda")
+def pack_records_op(idx: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """(idx, w) -> the slot-major, tile-padded gather records of the tensor-core forward (gcb_fwd_pack_records)."""
+    lib = N.load()
+    v_out, r, a = idx.shape[:3]
+    out = torch.empty(lib.gcb_fwd_records_bytes(v_out, r, a), dtype=torch.uint8, device=idx.device)
+    with _dev_guard(idx):
+        N.check(lib.gcb_fwd_pack_records(idx.data_ptr(), w.data_ptr(), v_out, r, a, out.data_ptr(), _stream(idx)),
+                "gcb_fwd_pack_records")
+    return out
+
+
+@pack_records_op.register_fake
+def _(idx, w):
+    v_out, r, a = idx.shape[:3]
+    v_pad = (v_out + 127) // 128 * 128
+    return idx.new_empty(((r * a * v_pad * 32 + 255) // 256 * 256 + 256,), dtype=torch.uint8)
+
+
+# weight-ring schedules + K-split boundaries per (device, shape, rotation list, precision): built once
+_FWD_TABLES: dict[tuple, torch.Tensor] = {}
+
+
+def forward_tables(device, v_out, r, a, f, t, rot, precision):
+    key = (device.index, v_out, r, a, f, t, tuple(rot), precision)
+    tab = _FWD_TABLES.get(key)
+    if tab is None:
+        lib = N.load()
+        tab = torch.empty(lib.gcb_fwd_tables_bytes(), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            N.check(lib.gcb_fwd_build_tables(N.rot_array(rot), len(rot), v_out, r, a, f, t, precision, tab.data_ptr(),
+                                             torch.cuda.current_stream(device).cuda_stream), "gcb_fwd_build_tables")
+        if len(_FWD_TABLES) > 64:
+            _FWD_TABLES.clear()
+        if not torch.cuda.is_current_stream_capturing():   # (a table built inside a capture belongs to that graph)
+            _FWD_TABLES[key] = tab
+    return tab
 
 
 # ---- prior folding  W[T,R,A,F] x K[R,A,R,A] -> Weff -------------------------------------------
@@ -328,11 +368,13 @@ class FoldPrior:
 # ---- the convolution (+ fused pooling outputs) --------------------------------------------------
 @torch.library.custom_op(f"{_LIB}::conv_fwd", mutates_args=(), device_types="cuda")
 def conv_fwd_op(signal: torch.Tensor, w_eff: torch.Tensor | None, w_self: torch.Tensor, bias: torch.Tensor,
-                idx: torch.Tensor, w: torch.Tensor, w_anchor: torch.Tensor | None, rot: list[int], act_id: int,
-                prec_fwd: int, prec_bwd: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """(signal, Weff|None, Wself, bias) -> (Y [V,n_rot,T], Z [V,T], argmax [V]): ConvIntrinsic.forward and the
-    AngularMaxPooling of its result in one pass (include/geoconv_b200.h: gcb_conv_fwd).  `w_anchor`: the
-    neighbour weights of an all-zero-prior layer (they take no part, but receive an all-zeros gradient)."""
+                idx: torch.Tensor, w: torch.Tensor, w_anchor: torch.Tensor | None, records: torch.Tensor | None,
+                rot: list[int], act_id: int, prec_fwd: int,
+                prec_bwd: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(signal, Weff|None, Wself, bias) -> (Y [V,n_rot,T], Z [V,T], argmax [V], stats int32 [8]): ConvIntrinsic.forward
+    and the AngularMaxPooling of its result in one pass (include/geoconv_b200.h: gcb_conv_fwd).  `w_anchor`: the
+    neighbour weights of an all-zero-prior layer (they take no part, but receive an all-zeros gradient);
+    `records`: cached gather records of the barycentric tensor; `stats`: operand maxima for the backward."""
     lib = N.load()
     x = signal.contiguous()
     v_src, f = x.shape
@@ -346,28 +388,34 @@ def conv_fwd_op(signal: torch.Tensor, w_eff: torch.Tensor | None, w_self: torch.
     y = torch.empty((v_out, n_rot, t), dtype=torch.float32, device=dev)
     z = torch.empty((v_out, t), dtype=torch.float32, device=dev)
     arg = torch.empty((v_out,), dtype=torch.int32, device=dev)
+    stats = torch.empty((8,), dtype=torch.int32, device=dev)
     ws_bytes = lib.gcb_conv_fwd_workspace_bytes(v_out, v_src, r, a, f, t, n_rot, prec_fwd)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    tensor_path = prec_fwd != N.PREC_FP32 and w_eff_c is not None and v_out > 0
+    tables = forward_tables(dev, v_out, r, a, f, t, rot, prec_fwd) if tensor_path else None
     with _dev_guard(x):
         N.check(lib.gcb_conv_fwd(x.data_ptr(), idx.data_ptr(), w.data_ptr(), _ptr(w_eff_c), w_self_c.data_ptr(),
                                  bias_c.data_ptr(), N.rot_array(rot), n_rot, v_out, v_src, r, a, f, t, act_id,
-                                 prec_fwd, y.data_ptr(), z.data_ptr(), arg.data_ptr(), None, ws.data_ptr(),
-                                 ws_bytes, _stream(x)), "gcb_conv_fwd")
-    return y, z, arg
+                                 prec_fwd, y.data_ptr(), z.data_ptr(), arg.data_ptr(), None,
+                                 _ptr(records) if tensor_path else None, _ptr(tables), stats.data_ptr(),
+                                 ws.data_ptr(), ws_bytes, _stream(x)), "gcb_conv_fwd")
+    return y, z, arg, stats
 
 
 @conv_fwd_op.register_fake
-def _(signal, w_eff, w_self, bias, idx, w, w_anchor, rot, act_id, prec_fwd, prec_bwd):
+def _(signal, w_eff, w_self, bias, idx, w, w_anchor, records, rot, act_id, prec_fwd, prec_bwd):
     v_out, t = idx.shape[0], w_self.shape[0]
     return (signal.new_empty((v_out, len(rot), t), dtype=torch.float32),
-            signal.new_empty((v_out, t), dtype=torch.float32), signal.new_empty((v_out,), dtype=torch.int32))
+            signal.new_empty((v_out, t), dtype=torch.float32), signal.new_empty((v_out,), dtype=torch.int32),
+            signal.new_empty((8,), dtype=torch.int32))
 
 
 @torch.library.custom_op(f"{_LIB}::conv_bwd", mutates_args=(), device_types="cuda")
 def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: torch.Tensor,
                 w_eff: torch.Tensor | None, w_self: torch.Tensor, y: torch.Tensor, z: torch.Tensor,
                 arg: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, row_ptr: torch.Tensor | None,
-                entries: torch.Tensor | None, rot: list[int], act_id: int, precision: int,
+                entries: torch.Tensor | None, csr_stats: torch.Tensor | None, fwd_stats: torch.Tensor | None,
+                rot: list[int], act_id: int, precision: int,
                 need_dx: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Backward of conv_fwd: a gradient arriving through Z takes the AMP-sparse route (one rotation per
     vertex), a gradient arriving through Y is back-propagated one rotation at a time.
@@ -383,13 +431,14 @@ def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: tor
     d_w_eff = torch.empty((t, r, a, f), dtype=torch.float32, device=dev)
     d_w_self = torch.empty((t, f), dtype=torch.float32, device=dev)
     d_bias = torch.empty((t,), dtype=torch.float32, device=dev)
-    ws_bytes = lib.gcb_conv_bwd_workspace_bytes(v_out, v_src, r, a, f, t, precision)
+    ws_bytes = lib.gcb_conv_amp_bwd_workspace_bytes(v_out, v_src, r, a, f, t, precision)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    h = torch.empty((v_out, t), dtype=torch.float32, device=dev)
-    rot_sel = torch.empty((v_out,), dtype=torch.int32, device=dev)
     st = _stream(x)
     rot_c = N.rot_array(rot)
     calls = 0
+    if grad_y is not None:
+        h = torch.empty((v_out, t), dtype=torch.float32, device=dev)
+        rot_sel = torch.empty((v_out,), dtype=torch.int32, device=dev)
 
     def run(accumulate):
         N.check(lib.gcb_conv_bwd(x.data_ptr(), idx.data_ptr(), w.data_ptr(), _ptr(w_eff) if has_nb else None,
@@ -400,11 +449,15 @@ def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: tor
 
     with _dev_guard(x):
         if grad_z is not None:
+            # AMP-sparse route: one rotation per vertex, one call (activation gradient, rotation select, bias
+            # reduction, operand scales and splits ride in its single preparation kernel)
             gz = grad_z.contiguous().to(torch.float32)
-            N.check(lib.gcb_act_grad(gz.data_ptr(), z.data_ptr(), gz.numel(), act_id, h.data_ptr(), st), "gcb_act_grad")
-            N.check(lib.gcb_select_rot(arg.data_ptr(), rot_c, n_rot, a, v_out, rot_sel.data_ptr(), st),
-                    "gcb_select_rot")
-            run(0)
+            N.check(lib.gcb_conv_amp_bwd(gz.data_ptr(), z.data_ptr(), arg.data_ptr(), rot_c, n_rot, act_id, x.data_ptr(),
+                                         idx.data_ptr(), w.data_ptr(), _ptr(w_eff) if has_nb else None,
+                                         w_self.data_ptr(), _ptr(row_ptr), _ptr(entries), _ptr(csr_stats),
+                                         _ptr(fwd_stats), v_out, v_src, r, a, f, t, precision, _ptr(d_x),
+                                         d_w_eff.data_ptr(), d_w_self.data_ptr(), d_bias.data_ptr(), ws.data_ptr(),
+                                         ws_bytes, st), "gcb_conv_amp_bwd")
             calls += 1
         if grad_y is not None:
             gy = grad_y.to(torch.float32)
@@ -422,7 +475,8 @@ def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: tor
 
 
 @conv_bwd_op.register_fake
-def _(grad_y, grad_z, x, w_eff, w_self, y, z, arg, idx, w, row_ptr, entries, rot, act_id, precision, need_dx):
+def _(grad_y, grad_z, x, w_eff, w_self, y, z, arg, idx, w, row_ptr, entries, csr_stats, fwd_stats, rot, act_id,
+      precision, need_dx):
     v_out, r, a = idx.shape[:3]
     t, f = w_self.shape[0], x.shape[1]
     return (torch.empty_like(x) if need_dx else x.new_empty((0,)), x.new_empty((t, r, a, f)), x.new_empty((t, f)),
@@ -439,12 +493,14 @@ def _csr_for(idx: torch.Tensor, w: torch.Tensor, v_src: int):
         pack = _PACK_OF_IDX.get(idx.data_ptr())
         if pack is not None and pack.v_src == v_src and pack.idx.data_ptr() == idx.data_ptr():
             return pack.csr()
-    return csr_build_op(idx, w, v_src)
+    return tuple(csr_build_op(idx, w, v_src))
 
 
 def _conv_setup(ctx, inputs, output):
-    signal, w_eff, w_self, bias, idx, w, w_anchor, rot, act_id, _prec_fwd, prec_bwd = inputs
-    y, z, arg = output
+    signal, w_eff, w_self, bias, idx, w, w_anchor, _records, rot, act_id, prec_fwd, prec_bwd = inputs
+    y, z, arg, stats = output
+    # the forward's operand maxima serve the backward when both run the fp16-split kernels on the same operands
+    ctx.use_fwd_stats = prec_fwd == N.PREC_F16X3 and prec_bwd == N.PREC_F16X3 and w_eff is not None
     ctx.rot = [int(o) for o in rot]
     ctx.act_id = act_id
     ctx.precision = prec_bwd
@@ -455,25 +511,26 @@ def _conv_setup(ctx, inputs, output):
     ctx.bias_shape = tuple(bias.shape)
     t, f = w_self.shape[0], signal.shape[1]
     ctx.save_for_backward(signal, w_eff if w_eff is not None else signal.new_empty((0,)),
-                          w_self.reshape(t, f), y, z, arg, idx, w)
+                          w_self.reshape(t, f), y, z, arg, idx, w, stats)
     ctx.set_materialize_grads(False)
 
 
-def _conv_backward(ctx, grad_y, grad_z, _grad_arg):
-    x, w_eff, w_self, y, z, arg, idx, w = ctx.saved_tensors
+def _conv_backward(ctx, grad_y, grad_z, _grad_arg, _grad_stats):
+    x, w_eff, w_self, y, z, arg, idx, w, stats = ctx.saved_tensors
     if grad_y is None and grad_z is None:
-        return (None,) * 11
+        return (None,) * 12
     INDEX_CHECKS.poll()
     has_nb = ctx.has_neighbor
     need_dx = bool(ctx.needs_input_grad[0])
     # the CSR inversion also feeds the weight gradients (dW = G^T X on tensor cores), not only dSignal
-    row_ptr, entries = _csr_for(idx, w, x.shape[0]) if has_nb else (None, None)
+    row_ptr, entries, csr_stats = _csr_for(idx, w, x.shape[0]) if has_nb else (None, None, None)
     d_x, d_w_eff, d_w_self, d_bias = conv_bwd_op(grad_y, grad_z, x.contiguous(), w_eff if has_nb else None, w_self, y, z,
-                                                 arg, idx, w, row_ptr, entries, ctx.rot, ctx.act_id, ctx.precision,
-                                                 need_dx)
+                                                 arg, idx, w, row_ptr, entries, csr_stats,
+                                                 stats if ctx.use_fwd_stats else None, ctx.rot, ctx.act_id,
+                                                 ctx.precision, need_dx)
     g_anchor = torch.zeros(ctx.anchor_shape, dtype=torch.float32, device=x.device) if ctx.has_anchor else None
     return (d_x if need_dx else None, d_w_eff if has_nb else None, d_w_self.reshape(ctx.w_self_shape),
-            d_bias.reshape(ctx.bias_shape), None, None, g_anchor, None, None, None, None)
+            d_bias.reshape(ctx.bias_shape), None, None, g_anchor, None, None, None, None, None)
 
 
 conv_fwd_op.register_autograd(_conv_backward, setup_context=_conv_setup)
@@ -487,8 +544,12 @@ class ConvIntrinsicFn:
     def apply(signal, w_eff, w_self, bias, pack: BaryPack, rot_offsets, act_id, precision, w_anchor=None):
         _need_cuda(signal, "signal")
         prec_fwd, prec_bwd = precision if isinstance(precision, tuple) else (precision, precision)
-        return conv_fwd_op(signal, w_eff, w_self, bias, pack.idx, pack.w, w_anchor, [int(o) for o in rot_offsets],
-                           act_id, prec_fwd, prec_bwd)
+        records = None
+        if prec_fwd != N.PREC_FP32 and w_eff is not None and not torch.compiler.is_compiling() and pack.v_out > 0:
+            records = pack.records()
+        y, z, arg, _stats = conv_fwd_op(signal, w_eff, w_self, bias, pack.idx, pack.w, w_anchor, records,
+                                        [int(o) for o in rot_offsets], act_id, prec_fwd, prec_bwd)
+        return y, z, arg
 
 
 # ---- angular poolings on a materialised tensor ---------------------------------------------------

@@ -94,11 +94,13 @@ int gcb_prep_bary(const void* bary, int bary_is_f64, int64_t n_slots, int32_t v_
  * Replaces the atomic scatter_add_ that autograd runs for torch.gather (conv_intrinsic.py:237).
  * row_ptr [v_src+1], entries [n_slots]: slot ids grouped by source vertex, ascending inside a
  * group (stable => bit-reproducible).  Zero-weight slots (the (0,0,0) fallback,
- * barycentric_coordinates.py:69) are dropped; row_ptr[v_src] = number kept.                   */
+ * barycentric_coordinates.py:69) are dropped; row_ptr[v_src] = number kept.
+ * stats (nullable, 8 uint32): [1] = max |w| as fp32 bits, [2] = longest row - the properties of the tensor from
+ * which the fp16-split backward bounds its operand G; pass them to gcb_conv_amp_bwd.           */
 size_t gcb_csr_workspace_bytes(int64_t n_slots, int32_t v_src);
 int gcb_csr_build(const int32_t* idx, const float* w, int64_t n_slots, int32_t v_src,
-                  int32_t* row_ptr, int32_t* entries, void* workspace, size_t workspace_bytes,
-                  void* stream);
+                  int32_t* row_ptr, int32_t* entries, uint32_t* stats, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* ---- prior folding ---------------------------------------------------------------------
  * Replaces the per-call einsum "raxy,kxyf->kraf" (conv_intrinsic.py:194) by folding the
@@ -121,14 +123,33 @@ int gcb_fold_prior(const float* in, const float* prior, float* out, int32_t T, i
  * term is skipped and only the centre term is computed.
  * interp_out (nullable) [V_out,R,A,F]: the tensor-core path stores the interpolations I there
  * (the reference materialises the same tensor, conv_intrinsic.py:240); handing it to
- * gcb_conv_bwd saves the backward one full gather pass.  Ignored by the CUDA-core path.        */
+ * gcb_conv_bwd saves the backward one full gather pass.  Ignored by the CUDA-core path.
+ * records / tables (nullable): preparation that depends only on the barycentric tensor / on the shape and rotation
+ * list (see below); when NULL the tensor-core path redoes it in the workspace on every call.
+ * stats_out (nullable, 8 uint32): operand maxima the fp16-split forward computes anyway ([0] max|X|, [2]
+ * max|[Weff|Wself]| as fp32 bits; all zero from the other paths) - gcb_conv_amp_bwd of the same step reuses them. */
 size_t gcb_conv_fwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
                                     int32_t T, int32_t n_rot, int precision);
 int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                  const float* w_self, const float* bias, const int32_t* rot_off_host,
                  int32_t n_rot, int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
                  int32_t T, int act, int precision, float* y, float* z, int32_t* argmax,
-                 float* interp_out, void* workspace, size_t workspace_bytes, void* stream);
+                 float* interp_out, const void* records, const void* tables, uint32_t* stats_out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- forward preparation a caller may cache ----------------------------------------------------
+ * The reference rebuilds everything per call (conv_intrinsic.py:198-240).  Two pieces of the tensor-core
+ * forward's preparation do not depend on the signal or the weights:
+ *   records: the (idx, w) pairs repacked slot-major and padded to 128-vertex tiles (what the gather producers
+ *            stage in shared memory) plus max_slots(|w0|+|w1|+|w2|) - a function of the barycentric tensor;
+ *   tables:  weight-ring schedules and K-split boundaries - a function of (v_out, R, A, F, T, rotations, precision).
+ * Build them once and pass them to gcb_conv_fwd.                                                 */
+size_t gcb_fwd_records_bytes(int32_t v_out, int32_t R, int32_t A);
+int gcb_fwd_pack_records(const int32_t* idx, const float* w, int32_t v_out, int32_t R, int32_t A, void* records,
+                         void* stream);
+size_t gcb_fwd_tables_bytes(void);
+int gcb_fwd_build_tables(const int32_t* rot_off_host, int32_t n_rot, int32_t v_out, int32_t R, int32_t A, int32_t F,
+                         int32_t T, int precision, void* tables, void* stream);
 
 /* ---- AngularMaxPooling on a materialised Y -----------------------------------------------
  * Replaces angular_max_pooling.py:27-29 and its autograd (index_put).                        */
@@ -186,6 +207,22 @@ int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, const float
                  int accumulate, const float* interp /* nullable: interp_out of the forward */, float* d_x,
                  float* d_w_eff, float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes,
                  void* stream);
+
+/* ---- backward of conv + AngularMaxPooling in one call -----------------------------------------
+ * Replaces autograd of angular_max_pooling.py:27-29 followed by conv_intrinsic.py:144-171/:226-240: starts from
+ * grad_z [V_out,T] (gradient of the pooled output), z [V_out,T] (the pooled output itself: the activation
+ * derivative is taken from it) and argmax [V_out]; equivalent to gcb_act_grad + gcb_select_rot + gcb_conv_bwd
+ * with accumulate = 0, but ONE preparation kernel produces h, the selected shifts, d_bias and - in the fp16-split
+ * mode - the operand scales and both operand splits.  csr_stats (gcb_csr_build) and fwd_stats (gcb_conv_fwd's
+ * stats_out, same signal and weights) are optional: without them the maxima are recomputed.       */
+size_t gcb_conv_amp_bwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F, int32_t T,
+                                        int precision);
+int gcb_conv_amp_bwd(const float* grad_z, const float* z, const int32_t* argmax, const int32_t* rot_off_host,
+                     int32_t n_rot, int act, const float* x, const int32_t* idx, const float* w, const float* w_eff,
+                     const float* w_self, const int32_t* csr_row_ptr, const int32_t* csr_entries,
+                     const uint32_t* csr_stats, const uint32_t* fwd_stats, int32_t v_out, int32_t v_src, int32_t R,
+                     int32_t A, int32_t F, int32_t T, int precision, float* d_x, float* d_w_eff, float* d_w_self,
+                     float* d_bias, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- vertex-row sharding helper (halo exchange) ---------------------------
  * out[i,:] = src[rows[i],:]  (packs the signal rows a peer asked for into a send buffer). */
