@@ -18,6 +18,7 @@ ABI_VERSION = 6
 MAX_ROT = 32
 
 PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_F16X3 = 0, 1, 2, 3
+CSR_RING_GROUPED = 1
 ACT_IDS = {"relu": 0, "elu": 1, "leaky_relu": 2, "selu": 3, "sigmoid": 4, "tanh": 5}
 
 _p = C.c_void_p
@@ -37,7 +38,7 @@ SIGNATURES = {
     "gcb_tc_half_supported": (_int, [_i32, _i32, _i32, _i32, _i32]),
     "gcb_prep_bary": (_int, [_p, _int, _i64, _i32, _p, _p, _p, _p]),
     "gcb_csr_workspace_bytes": (_sz, [_i64, _i32]),
-    "gcb_csr_build": (_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
+    "gcb_csr_build": (_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
     "gcb_fold_prior": (_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _int, _p]),
     "gcb_conv_fwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _int]),
     "gcb_conv_fwd": (_int, [_p, _p, _p, _p, _p, _p, C.POINTER(_i32), _i32, _i32, _i32, _i32, _i32, _i32,
@@ -47,7 +48,7 @@ SIGNATURES = {
     "gcb_fwd_tables_bytes": (_sz, []),
     "gcb_fwd_build_tables": (_int, [C.POINTER(_i32), _i32, _i32, _i32, _i32, _i32, _i32, _int, _p, _p]),
     "gcb_conv_amp_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _int]),
-    "gcb_conv_amp_bwd": (_int, [_p, _p, _p, C.POINTER(_i32), _i32, _int, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+    "gcb_conv_amp_bwd": (_int, [_p, _p, _p, C.POINTER(_i32), _i32, _int, _p, _p, _p, _p, _p, _p, _p, _int, _p, _p,
                                 _i32, _i32, _i32, _i32, _i32, _i32, _int, _p, _p, _p, _p, _p, _sz, _p]),
     "gcb_amp_fwd": (_int, [_p, _i32, _i32, _i32, _p, _p, _p]),
     "gcb_amp_bwd": (_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
@@ -58,7 +59,7 @@ SIGNATURES = {
     "gcb_select_rot": (_int, [_p, C.POINTER(_i32), _i32, _i32, _i32, _p, _p]),
     "gcb_conv_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _int]),
     "gcb_conv_bwd_workspace_selfcheck": (_int, [_i32, _i32, _i32, _i32, _i32, _i32, _int]),
-    "gcb_conv_bwd": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _int,
+    "gcb_conv_bwd": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _int, _i32, _i32, _i32, _i32, _i32, _i32, _int,
                             _int, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gcb_pack_rows": (_int, [_p, _p, _i32, _i32, _p, _p]),
 }

@@ -195,7 +195,7 @@ extern "C" int gcb_conv_bwd_workspace_selfcheck(int32_t v_out, int32_t v_src, in
 
 extern "C" int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                             const float* w_self, const float* h, const int32_t* rot_sel,
-                            const int32_t* csr_row_ptr, const int32_t* csr_entries, int32_t v_out,
+                            const int32_t* csr_row_ptr, const int32_t* csr_entries, int csr_flags, int32_t v_out,
                             int32_t v_src, int32_t R, int32_t A, int32_t F, int32_t T, int precision,
                             int accumulate, const float* interp, float* d_x, float* d_w_eff, float* d_w_self,
                             float* d_bias, void* workspace, size_t workspace_bytes, void* stream) {
@@ -213,7 +213,8 @@ extern "C" int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, 
   ws += align_up((size_t)v_out * R * A * F * sizeof(float), 256);
   if (precision != GCB_PREC_FP32 && tc_bwd_supported(R, A, F, T))   // (w_eff == NULL: centre-only GEMMs, no CSR needed)
     return tc_conv_bwd(x, idx, w, w_eff, w_self, h, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T,
-                       precision, accumulate, interp, d_x, d_w_eff, d_w_self, d_bias, workspace, workspace_bytes, st);
+                       precision, accumulate, interp, d_x, d_w_eff, d_w_self, d_bias, workspace, workspace_bytes, st,
+                       nullptr, (csr_flags & GCB_CSR_RING_GROUPED) != 0);
   rc = ffma_conv_bwd(x, idx, w, w_eff, h, rot_sel, v_out, v_src, R, A, F, T, accumulate, d_w_eff, d_w_self,
                      d_bias, d_x ? d_full : nullptr, ws, st);
   if (rc || !d_x) return rc;
@@ -236,8 +237,8 @@ int select_rot_launch(const int32_t* argmax, const RotTable& rot, int n_rot, int
 extern "C" int gcb_conv_amp_bwd(const float* grad_z, const float* z, const int32_t* argmax,
                                 const int32_t* rot_off_host, int32_t n_rot, int act, const float* x,
                                 const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
-                                const int32_t* csr_row_ptr, const int32_t* csr_entries, const uint32_t* csr_stats,
-                                const uint32_t* fwd_stats, int32_t v_out, int32_t v_src, int32_t R, int32_t A,
+                                const int32_t* csr_row_ptr, const int32_t* csr_entries, int csr_flags,
+                                const uint32_t* csr_stats, const uint32_t* fwd_stats, int32_t v_out, int32_t v_src, int32_t R, int32_t A,
                                 int32_t F, int32_t T, int precision, float* d_x, float* d_w_eff, float* d_w_self,
                                 float* d_bias, void* workspace, size_t workspace_bytes, void* stream) {
   GCB_REQUIRE(grad_z && z && argmax && x && idx && w && w_self, GCB_EINVAL, "gcb_conv_amp_bwd: null input pointer");
@@ -261,15 +262,16 @@ extern "C" int gcb_conv_amp_bwd(const float* grad_z, const float* z, const int32
   const size_t rest = workspace_bytes - (size_t)(ws - (char*)workspace);
   amp.grad_z = grad_z; amp.z = z; amp.argmax = argmax; amp.n_rot = n_rot; amp.act = act;
   amp.csr_stats = csr_stats; amp.fwd_stats = fwd_stats;
-  const bool aligned = ((uintptr_t)grad_z % 16 == 0) && ((uintptr_t)z % 16 == 0) && T % 4 == 0 && T <= 1024;
+  const bool aligned = ((uintptr_t)grad_z % 16 == 0) && ((uintptr_t)z % 16 == 0) && ((uintptr_t)d_bias % 16 == 0) && T % 4 == 0 && T <= 1024;
   if (precision != GCB_PREC_FP32 && tc_bwd_supported(R, A, F, T) && aligned)
     return tc_conv_bwd(x, idx, w, w_eff, w_self, amp.h, amp.rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T,
-                       precision, 0, nullptr, d_x, d_w_eff, d_w_self, d_bias, ws, rest, st, &amp);
+                       precision, 0, nullptr, d_x, d_w_eff, d_w_self, d_bias, ws, rest, st, &amp,
+                       (csr_flags & GCB_CSR_RING_GROUPED) != 0);
   // CUDA-core route (or a shape the preparation kernel does not tile): the separate small kernels, then gcb_conv_bwd
   rc = act_grad_launch(grad_z, z, (int64_t)v_out * T, act, amp.h, st);
   if (rc) return rc;
   rc = select_rot_launch(argmax, amp.rot, n_rot, v_out, amp.rot_sel, st);
   if (rc) return rc;
-  return gcb_conv_bwd(x, idx, w, w_eff, w_self, amp.h, amp.rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T,
-                      precision, 0, nullptr, d_x, d_w_eff, d_w_self, d_bias, ws, rest, stream);
+  return gcb_conv_bwd(x, idx, w, w_eff, w_self, amp.h, amp.rot_sel, csr_row_ptr, csr_entries, csr_flags, v_out, v_src, R,
+                      A, F, T, precision, 0, nullptr, d_x, d_w_eff, d_w_self, d_bias, ws, rest, stream);
 }

@@ -28,24 +28,30 @@ __global__ void k_prep_bary(const TIn* __restrict__ bary, int64_t n_slots, int32
 }
 
 // ---- CSR inversion ---------------------------------------------------------------------------
+// key = source vertex * rings + radial ring of the slot (rings = R when the caller gives the template size, else 1):
+// inside a vertex's row the entries are then grouped by radial ring, ascending slot id inside a ring - what lets
+// k_bw_build_g2 keep a ring's accumulators in registers (the rotation only moves a slot inside its ring)
 __global__ void k_csr_keys(const int32_t* __restrict__ idx, const float* __restrict__ w,
-                           int64_t n_slots, int32_t v_src, int32_t* __restrict__ keys,
+                           int64_t n_slots, int32_t v_src, int32_t rings, int32_t A, int32_t* __restrict__ keys,
                            int32_t* __restrict__ vals) {
   int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (s >= n_slots) return;
-  keys[s] = (w[s] == 0.f) ? v_src : idx[s];  // zero-weight slots sort to the tail and are dropped
+  int32_t ring = 0;
+  if (rings > 1) ring = (int32_t)(((s / 3) % ((int64_t)rings * A)) / A);
+  keys[s] = (w[s] == 0.f) ? v_src * rings : idx[s] * rings + ring;  // zero-weight slots sort to the tail and are dropped
   vals[s] = (int32_t)s;
 }
 
 __global__ void k_csr_row_ptr(const int32_t* __restrict__ sorted_keys, int64_t n_slots,
-                              int32_t v_src, int32_t* __restrict__ row_ptr) {
+                              int32_t v_src, int32_t rings, int32_t* __restrict__ row_ptr) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v > v_src) return;
-  // lower_bound(sorted_keys, v)
+  // lower_bound(sorted_keys, v * rings)
+  const int32_t key = v * rings;
   int64_t lo = 0, hi = n_slots;
   while (lo < hi) {
     int64_t mid = (lo + hi) >> 1;
-    if (sorted_keys[mid] < v) lo = mid + 1; else hi = mid;
+    if (sorted_keys[mid] < key) lo = mid + 1; else hi = mid;
   }
   row_ptr[v] = (int32_t)lo;
 }
@@ -58,9 +64,9 @@ static size_t cub_sort_temp_bytes(int64_t n_slots, int end_bit) {
   return bytes;
 }
 
-static int key_bits(int32_t v_src) {
+static int key_bits(int64_t max_key) {
   int bits = 1;
-  while ((1ll << bits) <= (long long)v_src) ++bits;
+  while ((1ll << bits) <= (long long)max_key) ++bits;
   return bits;
 }
 
@@ -150,13 +156,17 @@ extern "C" int gcb_prep_bary(const void* bary, int bary_is_f64, int64_t n_slots,
 
 extern "C" size_t gcb_csr_workspace_bytes(int64_t n_slots, int32_t v_src) {
   size_t arr = align_up((size_t)n_slots * sizeof(int32_t), 256);
-  return 3 * arr + align_up(cub_sort_temp_bytes(n_slots, key_bits(v_src)), 256) + 256;
+  return 3 * arr + align_up(cub_sort_temp_bytes(n_slots, 31), 256) + 256;   // (any key width)
 }
 
 extern "C" int gcb_csr_build(const int32_t* idx, const float* w, int64_t n_slots, int32_t v_src,
-                             int32_t* row_ptr, int32_t* entries, uint32_t* stats, void* workspace,
-                             size_t workspace_bytes, void* stream) {
+                             int32_t R, int32_t A, int32_t* row_ptr, int32_t* entries, uint32_t* stats,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   GCB_REQUIRE(idx && w && row_ptr && entries && workspace, GCB_EINVAL, "gcb_csr_build: null pointer");
+  GCB_REQUIRE(R >= 0 && A >= 0 && (R == 0) == (A == 0), GCB_EINVAL, "gcb_csr_build: R and A go together");
+  const int32_t rings = R > 0 ? R : 1;
+  GCB_REQUIRE((int64_t)v_src * rings + rings < (1ll << 31), GCB_EUNSUPPORTED, "gcb_csr_build: V_src * R exceeds int32 keys");
+  GCB_REQUIRE(R == 0 || n_slots % ((int64_t)R * A * 3) == 0, GCB_EINVAL, "gcb_csr_build: n_slots is not a multiple of R*A*3");
   GCB_REQUIRE(n_slots > 0 && n_slots < (1ll << 31) && v_src > 0, GCB_EINVAL, "gcb_csr_build: bad sizes");
   GCB_REQUIRE(workspace_bytes >= gcb_csr_workspace_bytes(n_slots, v_src), GCB_EWORKSPACE,
               "gcb_csr_build: workspace too small");
@@ -167,15 +177,15 @@ extern "C" int gcb_csr_build(const int32_t* idx, const float* w, int64_t n_slots
   int32_t* keys_out = (int32_t*)(base + arr);
   int32_t* vals_in = (int32_t*)(base + 2 * arr);
   void* cub_tmp = base + 3 * arr;
-  int bits = key_bits(v_src);
+  int bits = key_bits((int64_t)v_src * rings);
   size_t cub_bytes = cub_sort_temp_bytes(n_slots, bits);
   unsigned grid = (unsigned)ceil_div64(n_slots, 256);
-  k_csr_keys<<<grid, 256, 0, st>>>(idx, w, n_slots, v_src, keys_in, vals_in);
+  k_csr_keys<<<grid, 256, 0, st>>>(idx, w, n_slots, v_src, rings, A > 0 ? A : 1, keys_in, vals_in);
   GCB_LAUNCH_OK();
   // LSD radix sort is stable: slots of one source vertex stay in ascending slot order.
   GCB_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, vals_in,
                                               entries, (int)n_slots, 0, bits, st));
-  k_csr_row_ptr<<<(unsigned)ceil_div64((int64_t)v_src + 1, 256), 256, 0, st>>>(keys_out, n_slots, v_src, row_ptr);
+  k_csr_row_ptr<<<(unsigned)ceil_div64((int64_t)v_src + 1, 256), 256, 0, st>>>(keys_out, n_slots, v_src, rings, row_ptr);
   GCB_LAUNCH_OK();
   if (stats) {
     // what the fp16 backward needs to bound |G| (gcb_conv_amp_bwd): largest |weight| and longest row - properties of

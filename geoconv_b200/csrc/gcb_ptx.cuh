@@ -106,6 +106,12 @@ __device__ __forceinline__ void bulk_store_global(void* dst_global, uint32_t src
                "r"(bytes)
                : "memory");
 }
+// global -> this CTA's shared memory, completion (bytes) signalled on an mbarrier of this CTA
+__device__ __forceinline__ void bulk_load_global(uint32_t dst_cta, const void* src_global, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cta),
+               "l"(src_global), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // every bulk async-group of this thread has finished READING its shared-memory source
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

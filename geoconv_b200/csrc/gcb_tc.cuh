@@ -73,7 +73,7 @@ int tc_bwd_scales(const float* h, const float* w, const int32_t* csr_row_ptr, co
                   const float* x, int v_out, int v_src, int R, int A, int F, int T, void* scratch, cudaStream_t st);
 int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int32_t* csr_row_ptr,
                const int32_t* csr_entries, int v_out, int v_src, int R, int A, int T, bool x3, float* g_hi,
-               float* g_lo, cudaStream_t st, const float* scales = nullptr);
+               float* g_lo, cudaStream_t st, const float* scales = nullptr, bool ring_sorted = false);
 int tc_dx_from_g(const float* g_hi, const float* g_lo, const float* wcat_hi, const float* wcat_lo, int v_src, int R,
                  int A, int F, int T, bool x3, int accumulate, float* d_x, cudaStream_t st,
                  const float* scales = nullptr);
@@ -103,6 +103,6 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
                 int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,
                 const float* interp /* nullable: I saved by the forward */, float* d_x, float* d_w_eff,
                 float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                const TcBwdAmp* amp = nullptr);
+                const TcBwdAmp* amp = nullptr, bool csr_ring_grouped = false);
 
 }  // namespace gcb

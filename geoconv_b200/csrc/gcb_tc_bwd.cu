@@ -506,10 +506,29 @@ __global__ void __launch_bounds__(BWP_THREADS) k_bw_prepare(const __grid_constan
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int t = tid; t < p.T; t += BWP_THREADS) {
-    float sum = 0.f;
-    for (int b = 0; b < p.nb_h; ++b) sum += __ldcg(p.bias_part + (size_t)b * p.T + t);
-    p.d_bias[t] = p.accumulate ? p.d_bias[t] + sum : sum;
+  // d_bias: block partial sums added in a fixed order - row lane l takes blocks l, l + n_lanes, ... (independent
+  // loads in flight instead of one dependent chain of nb_h L2 round trips), then the lanes in order
+  if (rl < n_lanes) {
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = rl; b < p.nb_h; b += n_lanes) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(p.bias_part) + (size_t)b * T4 + c4);
+      sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+    }
+    s_col[rl * T4 + c4] = sum;
+  }
+  __syncthreads();
+  if (tid < T4) {
+    float4 sum = s_col[tid];
+    for (int l = 1; l < n_lanes; ++l) {
+      const float4 v = s_col[l * T4 + tid];
+      sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+    }
+    float4* out = reinterpret_cast<float4*>(p.d_bias) + tid;
+    if (p.accumulate) {
+      const float4 old = *out;
+      sum.x += old.x; sum.y += old.y; sum.z += old.z; sum.w += old.w;
+    }
+    *out = sum;
   }
   if (tid == 0 && p.scales) {
     volatile const unsigned* vm = p.mx;
@@ -636,7 +655,7 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
                 const float* h, const int32_t* rot_sel, const int32_t* csr_row_ptr, const int32_t* csr_entries,
                 int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,
                 const float* interp, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias, void* workspace,
-                size_t workspace_bytes, cudaStream_t st, const TcBwdAmp* amp) {
+                size_t workspace_bytes, cudaStream_t st, const TcBwdAmp* amp, bool csr_ring_grouped) {
   // fp16 operand splits (GCB_PREC_F16X3) serve the route through G; the centre-only and gather-fed routes run
   // the same precision request as 3xTF32
   static const bool no_half = getenv("GCB_BWD_NO_HALF") && atoi(getenv("GCB_BWD_NO_HALF")) != 0;   // A/B measurements
@@ -659,8 +678,9 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
   bool bias_done = false, scales_done = false, x_split_done = false, w_split_done = false;
   const TcGLayout GMX = tc_g_layout_max(v_src, R, A, F, T, x3);
   if (amp) {
-    GCB_REQUIRE(T % 4 == 0 && T <= 1024 && ((uintptr_t)amp->grad_z % 16 == 0) && ((uintptr_t)amp->z % 16 == 0), GCB_EINVAL,
-                "tc_conv_bwd: grad_z / z must be 16-byte aligned and T a multiple of 4");
+    GCB_REQUIRE(T % 4 == 0 && T <= 1024 && ((uintptr_t)amp->grad_z % 16 == 0) && ((uintptr_t)amp->z % 16 == 0) &&
+                    ((uintptr_t)d_bias % 16 == 0), GCB_EINVAL,
+                "tc_conv_bwd: grad_z / z / d_bias must be 16-byte aligned and T a multiple of 4");
     unsigned* mx = (unsigned*)scale_scratch;
     GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 32, st));
     const bool have_csr = csr_row_ptr && w_eff;
@@ -706,7 +726,8 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
       pp.nb_x = (int)ceil_div64((int64_t)v_src * (x_ld / 8), (int64_t)BWP_THREADS * 4);
       if (pp.nb_x > 148) pp.nb_x = 148;
       x_split_done = true;
-      if (w_eff && d_x) {
+      static const bool wsplit_here = !(getenv("GCB_BW_WSPLIT") && atoi(getenv("GCB_BW_WSPLIT")) == 0);   // A/B
+      if (w_eff && d_x && wsplit_here) {
         pp.w_eff = w_eff; pp.w_self = w_self; pp.KRA = KRA;
         pp.wh = (__half*)wc_hi; pp.wl = (__half*)wc_lo;
         pp.nb_w = (int)ceil_div64((int64_t)T * ((KRA + F) / 8), (int64_t)BWP_THREADS * 4);
@@ -781,7 +802,7 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
       k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.bias_blocks, T, accumulate, d_bias);
       GCB_LAUNCH_OK();
     }
-    rc = tc_build_g(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, x3, g_hi, g_lo, st, scales);
+    rc = tc_build_g(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, x3, g_hi, g_lo, st, scales, csr_ring_grouped);
     if (rc) return rc;
     rc = tc_dw_from_g(g_hi, g_lo, x, v_src, R, A, F, T, x3, accumulate, d_w_eff, d_w_self, x_hi, x_lo, partial,
                       GM.partial_bytes, st, scales, half && x_split_done);

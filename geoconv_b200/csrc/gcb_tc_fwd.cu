@@ -194,7 +194,7 @@ static size_t tc_tab_bytes(int A, int n_pos) {
 // mbarriers: A-stage full/empty (<= 8 stages), per (parity, position) full, per absolute position empty,
 // accumulators; TMEM slot
 static size_t tc_bar_bytes(int n_pos, int n_ring) {
-  return align_up((size_t)8 * (16 + 2 * n_pos + n_ring + 1 + TC_READY_RING) + 16, 64);
+  return align_up((size_t)8 * (16 + 2 * n_pos + n_ring + 1 + TC_READY_RING) + 16 + 16 /* fused finish */, 64);
 }
 
 // Refill slack of the weight ring for a visiting order that advances `phase_shift` steps per super-step and a
@@ -1062,6 +1062,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
     for (int s = 0; s < n_ring; ++s) ptx::mbar_init(b_empty + 8u * s, (uint32_t)n_mma);
     ptx::mbar_init(acc_full, (uint32_t)n_mma);
     for (int s = 0; s < TC_READY_RING; ++s) ptx::mbar_init(ready + 8u * s, 1);
+    ptx::mbar_init(tmem_slot + 16u, 1);   // fused finish: two staging buffers
+    ptx::mbar_init(tmem_slot + 24u, 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tensormap(&tmap_hi);
     if (X3) ptx::prefetch_tensormap(&tmap_lo);
@@ -1330,54 +1332,114 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       }
       producer_bar_sync();
       if (*flag) {
+        // The unit's partial sums - ksplit slabs x (rows of this tile) x (g_cnt rotations x n_t templates) - are
+        // fetched by the bulk-copy engine into the now idle operand rings, a batch of rows at a time, double
+        // buffered: plain loads (one row per warp, a few 16-byte loads per lane in flight) left this CTA waiting on
+        // L2 latency for ~100 us; the copy engine keeps ~100 KB in flight.
         const float inv = H ? __ldg(p.scales + 2) : 1.f;
         const int T4c = p.n_t >> 2, T4 = p.T >> 2;
-        const size_t split_stride4 = (size_t)p.v_pad * p.n_rot * T4;     // float4 units between two splits' slabs
         const float4* bias4 = reinterpret_cast<const float4*>(p.bias) + (t0 >> 2);
-        for (int rr = pw; rr < TC_M; rr += TC_PRODUCER_WARPS) {
-          const int vrow = m0 + rr;
-          if (vrow >= p.v_out) break;
-          for (int il = 0; il < g_cnt; ++il) {
-            const size_t row4 = ((size_t)vrow * p.n_rot + rot0 + il) * T4 + (t0 >> 2);
-            const float4* src = reinterpret_cast<const float4*>(p.partial) + row4;
-            float4* dst = reinterpret_cast<float4*>(p.y) + row4;
-            float sq = 0.f;
-            for (int q = lane; q < T4c; q += 32) {
-              const float4 bv = __ldg(bias4 + q);
-              float4 acc = H ? make_float4(0.f, 0.f, 0.f, 0.f) : bv;
-              int sp = 0;
-              for (; sp + 4 <= p.ksplit; sp += 4) {      // four slabs in flight, added in split order
-                const float4 p0 = __ldcg(src + (size_t)sp * split_stride4 + q);
-                const float4 p1 = __ldcg(src + (size_t)(sp + 1) * split_stride4 + q);
-                const float4 p2 = __ldcg(src + (size_t)(sp + 2) * split_stride4 + q);
-                const float4 p3 = __ldcg(src + (size_t)(sp + 3) * split_stride4 + q);
-                acc.x += p0.x; acc.y += p0.y; acc.z += p0.z; acc.w += p0.w;
-                acc.x += p1.x; acc.y += p1.y; acc.z += p1.z; acc.w += p1.w;
-                acc.x += p2.x; acc.y += p2.y; acc.z += p2.z; acc.w += p2.w;
-                acc.x += p3.x; acc.y += p3.y; acc.z += p3.z; acc.w += p3.w;
+        const int rows_valid = min(TC_M, p.v_out - m0);
+        const uint32_t seg_floats = (uint32_t)(g_cnt * p.n_t);              // one (row, split): g_cnt rotations x n_t
+        const uint32_t row_bytes = (uint32_t)p.ksplit * seg_floats * 4u;    // one row: every split
+        const uint32_t region = rec_base - b_base;
+        int nb = (int)(region / (2u * row_bytes));
+        nb = nb > TC_PRODUCER_WARPS ? TC_PRODUCER_WARPS : nb;               // one row per warp and batch
+        const bool contiguous = t_chunks == 1;                              // the g_cnt rotations of a row are adjacent
+        const int pieces = contiguous ? 1 : g_cnt;                          // copies per (row, split)
+        const uint32_t piece_bytes = (contiguous ? seg_floats : (uint32_t)p.n_t) * 4u;
+        const uint32_t fin_bar = tmem_slot + 16u;
+        const int n_batches = nb > 0 ? (rows_valid + nb - 1) / nb : 0;
+        ptx::fence_proxy_async_all();
+        auto issue = [&](int b, int buf) {
+          const int r_lo = b * nb, r_n = min(nb, rows_valid - r_lo);
+          if (ptid == 0) ptx::mbar_arrive_expect_tx(fin_bar + 8u * (uint32_t)buf, (uint32_t)r_n * row_bytes);
+          for (int i = ptid; i < r_n * p.ksplit * pieces; i += TC_PRODUCER_WARPS * 32) {
+            const int pc = i % pieces, sp = (i / pieces) % p.ksplit, rr = i / (pieces * p.ksplit);
+            const float* src = p.partial + (((size_t)sp * p.v_pad + m0 + r_lo + rr) * p.n_rot + rot0 + pc) * p.T + t0;
+            const uint32_t dst = b_base + (uint32_t)buf * (uint32_t)nb * row_bytes +
+                                 ((uint32_t)(rr * p.ksplit + sp) * seg_floats + (uint32_t)(pc * p.n_t)) * 4u;
+            ptx::bulk_load_global(dst, src, piece_bytes, fin_bar + 8u * (uint32_t)buf);
+          }
+        };
+        if (n_batches > 0) issue(0, 0);
+        if (n_batches > 1) issue(1, 1);
+        for (int b = 0; b < n_batches; ++b) {
+          const int buf = b & 1;
+          ptx::mbar_wait(fin_bar + 8u * (uint32_t)buf, (uint32_t)(b >> 1) & 1u);
+          const int rr = pw, vrow = m0 + b * nb + rr;
+          if (rr < nb && b * nb + rr < rows_valid) {
+            const float4* sm = reinterpret_cast<const float4*>(
+                smem_gen + (b_base - smem_base) + (size_t)buf * nb * row_bytes + (size_t)rr * row_bytes);
+            const uint32_t seg4 = seg_floats >> 2;
+            for (int il = 0; il < g_cnt; ++il) {
+              float4* dst = reinterpret_cast<float4*>(p.y) + ((size_t)vrow * p.n_rot + rot0 + il) * T4 + (t0 >> 2);
+              float sq = 0.f;
+              for (int q = lane; q < T4c; q += 32) {
+                const float4 bv = __ldg(bias4 + q);
+                float4 acc = H ? make_float4(0.f, 0.f, 0.f, 0.f) : bv;
+                for (int sp = 0; sp < p.ksplit; ++sp) {          // split order: the order k_tc_finish adds in
+                  const float4 pv = sm[(size_t)sp * seg4 + (size_t)il * T4c + q];
+                  acc.x += pv.x; acc.y += pv.y; acc.z += pv.z; acc.w += pv.w;
+                }
+                if (H) {
+                  acc.x = fmaf(acc.x, inv, bv.x); acc.y = fmaf(acc.y, inv, bv.y);
+                  acc.z = fmaf(acc.z, inv, bv.z); acc.w = fmaf(acc.w, inv, bv.w);
+                }
+                float4 o;
+                o.x = act_apply(p.act, acc.x); o.y = act_apply(p.act, acc.y);
+                o.z = act_apply(p.act, acc.z); o.w = act_apply(p.act, acc.w);
+                dst[q] = o;
+                sq = fmaf(o.x, o.x, sq); sq = fmaf(o.y, o.y, sq); sq = fmaf(o.z, o.z, sq); sq = fmaf(o.w, o.w, sq);
               }
-              for (; sp < p.ksplit; ++sp) {
-                const float4 pv = __ldcg(src + (size_t)sp * split_stride4 + q);
-                acc.x += pv.x; acc.y += pv.y; acc.z += pv.z; acc.w += pv.w;
-              }
-              if (H) {
-                acc.x = fmaf(acc.x, inv, bv.x); acc.y = fmaf(acc.y, inv, bv.y);
-                acc.z = fmaf(acc.z, inv, bv.z); acc.w = fmaf(acc.w, inv, bv.w);
-              }
-              float4 o;
-              o.x = act_apply(p.act, acc.x); o.y = act_apply(p.act, acc.y);
-              o.z = act_apply(p.act, acc.z); o.w = act_apply(p.act, acc.w);
-              dst[q] = o;
-              sq = fmaf(o.x, o.x, sq); sq = fmaf(o.y, o.y, sq); sq = fmaf(o.z, o.z, sq); sq = fmaf(o.w, o.w, sq);
-              if (p.discard && (q & 7) == 0) {   // one 128-byte line per 8 lanes: summed, never needed again
-                for (int sp2 = 0; sp2 < p.ksplit; ++sp2)
-                  if ((((uintptr_t)(src + (size_t)sp2 * split_stride4 + q)) & 127) == 0 && q + 8 <= T4c)
-                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(src + (size_t)sp2 * split_stride4 + q) : "memory");
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+              if (lane == 0 && p.z) p.nrm2[((size_t)vrow * p.n_rot + rot0 + il) * t_chunks + tz] = sq;
+            }
+            if (p.discard && contiguous && (p.T & 31) == 0) {
+              // the row's partial sums are dead: drop their (dirty) L2 lines instead of writing them back to DRAM
+              const int lines = (int)(seg_floats >> 5);           // 128-byte lines per (row, split)
+              for (int i = lane; i < p.ksplit * lines; i += 32) {
+                const int sp = i / lines, ln = i - sp * lines;
+                const float* a = p.partial + (((size_t)sp * p.v_pad + vrow) * p.n_rot + rot0) * p.T + t0 + ln * 32;
+                if ((reinterpret_cast<uintptr_t>(a) & 127) == 0) asm volatile("discard.global.L2 [%0], 128;" ::"l"(a) : "memory");
               }
             }
+          }
+          producer_bar_sync();                                   // everybody is done with this buffer
+          if (b + 2 < n_batches) issue(b + 2, buf);
+        }
+        if (n_batches == 0) {
+          // (a row does not fit the staging area twice: plain loads)
+          const size_t split_stride4 = (size_t)p.v_pad * p.n_rot * T4;
+          for (int rr = pw; rr < rows_valid; rr += TC_PRODUCER_WARPS) {
+            const int vrow = m0 + rr;
+            for (int il = 0; il < g_cnt; ++il) {
+              const size_t row4 = ((size_t)vrow * p.n_rot + rot0 + il) * T4 + (t0 >> 2);
+              const float4* src = reinterpret_cast<const float4*>(p.partial) + row4;
+              float4* dst = reinterpret_cast<float4*>(p.y) + row4;
+              float sq = 0.f;
+              for (int q = lane; q < T4c; q += 32) {
+                const float4 bv = __ldg(bias4 + q);
+                float4 acc = H ? make_float4(0.f, 0.f, 0.f, 0.f) : bv;
+                for (int sp = 0; sp < p.ksplit; ++sp) {
+                  const float4 pv = __ldcg(src + (size_t)sp * split_stride4 + q);
+                  acc.x += pv.x; acc.y += pv.y; acc.z += pv.z; acc.w += pv.w;
+                }
+                if (H) {
+                  acc.x = fmaf(acc.x, inv, bv.x); acc.y = fmaf(acc.y, inv, bv.y);
+                  acc.z = fmaf(acc.z, inv, bv.z); acc.w = fmaf(acc.w, inv, bv.w);
+                }
+                float4 o;
+                o.x = act_apply(p.act, acc.x); o.y = act_apply(p.act, acc.y);
+                o.z = act_apply(p.act, acc.z); o.w = act_apply(p.act, acc.w);
+                dst[q] = o;
+                sq = fmaf(o.x, o.x, sq); sq = fmaf(o.y, o.y, sq); sq = fmaf(o.z, o.z, sq); sq = fmaf(o.w, o.w, sq);
+              }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-            if (lane == 0 && p.z) p.nrm2[((size_t)vrow * p.n_rot + rot0 + il) * t_chunks + tz] = sq;
+              for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+              if (lane == 0 && p.z) p.nrm2[((size_t)vrow * p.n_rot + rot0 + il) * t_chunks + tz] = sq;
+            }
           }
         }
         if (p.z) {

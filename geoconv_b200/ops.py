@@ -266,13 +266,15 @@ def csr_build_op(idx: torch.Tensor, w: torch.Tensor, v_src: int) -> tuple[torch.
     lib = N.load()
     n_slots = idx.numel()
     dev = idx.device
+    r, a = idx.shape[1], idx.shape[2]
     row_ptr = torch.empty(v_src + 1, dtype=torch.int32, device=dev)
     entries = torch.empty(n_slots, dtype=torch.int32, device=dev)
     stats = torch.empty(8, dtype=torch.int32, device=dev)
     ws_bytes = lib.gcb_csr_workspace_bytes(n_slots, v_src)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with _dev_guard(idx):
-        N.check(lib.gcb_csr_build(idx.data_ptr(), w.data_ptr(), n_slots, v_src, row_ptr.data_ptr(),
+        # (template size given: rows grouped by radial ring - _native.CSR_RING_GROUPED goes to the backward)
+        N.check(lib.gcb_csr_build(idx.data_ptr(), w.data_ptr(), n_slots, v_src, r, a, row_ptr.data_ptr(),
                                   entries.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes, _stream(idx)),
                 "gcb_csr_build")
     return row_ptr, entries, stats
@@ -443,7 +445,7 @@ def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: tor
     def run(accumulate):
         N.check(lib.gcb_conv_bwd(x.data_ptr(), idx.data_ptr(), w.data_ptr(), _ptr(w_eff) if has_nb else None,
                                  w_self.data_ptr(), h.data_ptr(), rot_sel.data_ptr(), _ptr(row_ptr), _ptr(entries),
-                                 v_out, v_src, r, a, f, t, precision, accumulate, None, _ptr(d_x),
+                                 N.CSR_RING_GROUPED, v_out, v_src, r, a, f, t, precision, accumulate, None, _ptr(d_x),
                                  d_w_eff.data_ptr(), d_w_self.data_ptr(), d_bias.data_ptr(), ws.data_ptr(),
                                  ws_bytes, st), "gcb_conv_bwd")
 
@@ -454,8 +456,8 @@ def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: tor
             gz = grad_z.contiguous().to(torch.float32)
             N.check(lib.gcb_conv_amp_bwd(gz.data_ptr(), z.data_ptr(), arg.data_ptr(), rot_c, n_rot, act_id, x.data_ptr(),
                                          idx.data_ptr(), w.data_ptr(), _ptr(w_eff) if has_nb else None,
-                                         w_self.data_ptr(), _ptr(row_ptr), _ptr(entries), _ptr(csr_stats),
-                                         _ptr(fwd_stats), v_out, v_src, r, a, f, t, precision, _ptr(d_x),
+                                         w_self.data_ptr(), _ptr(row_ptr), _ptr(entries), N.CSR_RING_GROUPED,
+                                         _ptr(csr_stats), _ptr(fwd_stats), v_out, v_src, r, a, f, t, precision, _ptr(d_x),
                                          d_w_eff.data_ptr(), d_w_self.data_ptr(), d_bias.data_ptr(), ws.data_ptr(),
                                          ws_bytes, st), "gcb_conv_amp_bwd")
             calls += 1

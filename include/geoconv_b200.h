@@ -95,12 +95,17 @@ int gcb_prep_bary(const void* bary, int bary_is_f64, int64_t n_slots, int32_t v_
  * row_ptr [v_src+1], entries [n_slots]: slot ids grouped by source vertex, ascending inside a
  * group (stable => bit-reproducible).  Zero-weight slots (the (0,0,0) fallback,
  * barycentric_coordinates.py:69) are dropped; row_ptr[v_src] = number kept.
+ * R, A: the template size, or 0, 0.  With the template size the entries of a row are additionally grouped by the
+ * radial ring of their slot (ascending slot id inside a ring) - the order the tensor-core backward wants, because a
+ * rotation moves a template vertex only inside its ring; pass GCB_CSR_RING_GROUPED to the backward then.
  * stats (nullable, 8 uint32): [1] = max |w| as fp32 bits, [2] = longest row - the properties of the tensor from
  * which the fp16-split backward bounds its operand G; pass them to gcb_conv_amp_bwd.           */
 size_t gcb_csr_workspace_bytes(int64_t n_slots, int32_t v_src);
-int gcb_csr_build(const int32_t* idx, const float* w, int64_t n_slots, int32_t v_src,
+int gcb_csr_build(const int32_t* idx, const float* w, int64_t n_slots, int32_t v_src, int32_t R, int32_t A,
                   int32_t* row_ptr, int32_t* entries, uint32_t* stats, void* workspace,
                   size_t workspace_bytes, void* stream);
+/* csr_flags of gcb_conv_bwd / gcb_conv_amp_bwd: how the entries of a row are ordered */
+#define GCB_CSR_RING_GROUPED 1 /* built with R, A > 0: grouped by radial ring, ascending slot id inside a ring */
 
 /* ---- prior folding ---------------------------------------------------------------------
  * Replaces the per-call einsum "raxy,kxyf->kraf" (conv_intrinsic.py:194) by folding the
@@ -202,7 +207,7 @@ int gcb_conv_bwd_workspace_selfcheck(int32_t v_out, int32_t v_src, int32_t R, in
                                      int precision);
 int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                  const float* w_self, const float* h, const int32_t* rot_sel,
-                 const int32_t* csr_row_ptr, const int32_t* csr_entries, int32_t v_out,
+                 const int32_t* csr_row_ptr, const int32_t* csr_entries, int csr_flags, int32_t v_out,
                  int32_t v_src, int32_t R, int32_t A, int32_t F, int32_t T, int precision,
                  int accumulate, const float* interp /* nullable: interp_out of the forward */, float* d_x,
                  float* d_w_eff, float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes,
@@ -219,7 +224,7 @@ size_t gcb_conv_amp_bwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R,
                                         int precision);
 int gcb_conv_amp_bwd(const float* grad_z, const float* z, const int32_t* argmax, const int32_t* rot_off_host,
                      int32_t n_rot, int act, const float* x, const int32_t* idx, const float* w, const float* w_eff,
-                     const float* w_self, const int32_t* csr_row_ptr, const int32_t* csr_entries,
+                     const float* w_self, const int32_t* csr_row_ptr, const int32_t* csr_entries, int csr_flags,
                      const uint32_t* csr_stats, const uint32_t* fwd_stats, int32_t v_out, int32_t v_src, int32_t R,
                      int32_t A, int32_t F, int32_t T, int precision, float* d_x, float* d_w_eff, float* d_w_self,
                      float* d_bias, void* workspace, size_t workspace_bytes, void* stream);

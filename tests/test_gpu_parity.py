@@ -141,12 +141,14 @@ def test_prep_bary_and_csr_bit_exact():
         idx, w = O.split_bary(bary)
         assert torch.equal(pack.idx.cpu().long(), idx)
         assert torch.equal(pack.w.cpu(), w)
-        row_ptr, entries = pack.csr()
+        row_ptr, entries, _stats = pack.csr()
         row_ptr, entries = row_ptr.cpu().long(), entries.cpu().long()
         flat_idx, flat_w = idx.reshape(-1), w.reshape(-1)
         keep = (flat_w != 0).nonzero().flatten()
         assert row_ptr[0] == 0 and row_ptr[-1] == keep.numel()
-        order = torch.argsort(flat_idx[keep], stable=True)
+        # rows grouped by source vertex, inside a row by the radial ring of the slot, inside a ring by slot id
+        ring = (keep // 3) % (r * a) // a
+        order = torch.argsort(flat_idx[keep] * r + ring, stable=True)
         assert torch.equal(entries[: keep.numel()], keep[order])       # stable => unique answer
         counts = torch.bincount(flat_idx[keep], minlength=v)
         assert torch.equal(row_ptr[1:] - row_ptr[:-1], counts)
