@@ -257,11 +257,211 @@ def run_reference(args):
     emit(json.dumps(line))
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# Extras (BASELINE.json configs beyond the headline line): TF32 mode at S1, config 4 (64 meshes, 3-layer net, data
+# parallel), config 5 (row-sharded large mesh with halo exchange).  Reported under "extra"; the headline stays S1 fp32.
+# ------------------------------------------------------------------------------------------------------------------
+def _max_over_ranks(x, world, dev):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return float(x)
+    t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def extra_tf32(cfg, weights, inputs_dev, flush, lib, steps, warmup, peaks):
+    """S1 in the TF32 mode (<= 2e-3): device-resident step from a CUDA graph, forward kernel timed with events."""
+    import ctypes
+    import torch
+    from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
+    from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
+    signal_d, bary_d, gz_d = inputs_dev
+    dev = signal_d.device
+    v, f, r, a, t = cfg["v"], cfg["f"], cfg["r"], cfg["a"], cfg["t"]
+    layer = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=cfg["radius"],
+                         activation=cfg["act"], rotation_delta=cfg["delta"], precision="tf32")
+    layer.load_state_dict({"_template_neighbor_weights": weights[0], "_template_self_weights": weights[1],
+                           "_bias": weights[2]})
+    layer = layer.to(dev)
+    amp = AngularMaxPooling()
+    xs = signal_d.detach().clone().requires_grad_(True)
+
+    def body():
+        for p_ in layer.parameters():
+            p_.grad = None
+        xs.grad = None
+        amp(layer([xs, bary_d])).backward(gz_d)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            body()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        body()
+    for _ in range(warmup):
+        flush.zero_()
+        graph.replay()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = sum(a_.elapsed_time(b_) for a_, b_ in evs) / steps
+    lib.gcb_profile_enable(1)
+    for _ in range(min(steps, 10)):
+        flush.zero_()
+        body()
+    torch.cuda.synchronize()
+    k_ms, k_cnt = ctypes.c_double(0.0), ctypes.c_int64(0)
+    lib.gcb_profile_read(0, ctypes.byref(k_ms), ctypes.byref(k_cnt))
+    lib.gcb_profile_enable(0)
+    fwd_flops, _bwd = algorithmic_flops(cfg)
+    peak = peaks["bf16_tflops"] / 2.0
+    achieved = fwd_flops * k_cnt.value / (k_ms.value * 1e-3) / 1e12 if k_ms.value > 0 else None
+    return {"workload": WORKLOAD, "precision": "tf32 (single pass, <= 2e-3 normalised error)", "ms_per_step": ms,
+            "value": v / (ms * 1e-3), "unit": "vertices/s", "launch": "cuda-graph replay",
+            "roofline": {"bound": "tensor", "kernel": "k_tc_conv", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if achieved else None,
+                         "kernel_ms_avg": k_ms.value / k_cnt.value if k_cnt.value else None,
+                         "peak_source": f"{peaks['source']} bf16_tflops/2 (TF32 dense peak is derived, not measured)"}}
+
+
+def extra_s3(rank, world, dev, steps=3, warmup=1, n_meshes=64):
+    """BASELINE config 4: 3-layer ConvGeodesic + AngularMaxPooling segmentation net (64 -> 96 -> 256 -> 384, Linear head,
+    cross entropy) on a batch of 64 FAUST-shaped meshes, meshes dealt round-robin to the ranks, one all-reduce of the
+    accumulated weight gradients per step.  Also: the data-parallel gradients against the same batch on one rank."""
+    import torch
+    import torch.distributed as dist
+    from geoconv_b200 import synthetic as S
+    from geoconv_b200.distributed import allreduce_gradients
+    from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
+    from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
+    v, r, a, n_cls = 6890, 5, 8, 32
+    dims = [64, 96, 256, 384]
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.convs = torch.nn.ModuleList(
+                ConvGeodesic(input_shape=[(None, fi), (None, r, a, 3, 2)], amt_templates=fo, template_radius=0.028)
+                for fi, fo in zip(dims[:-1], dims[1:]))
+            self.amp = AngularMaxPooling()
+            self.head = torch.nn.Linear(dims[-1], n_cls)
+
+        def forward(self, x, bary):
+            for conv in self.convs:
+                x = self.amp(conv([x, bary]))
+            return self.head(x)
+    torch.manual_seed(0)
+    net = Net().to(dev)
+    params = list(net.parameters())
+    loss_fn = torch.nn.CrossEntropyLoss(reduction="sum")
+    mine = list(range(rank, n_meshes, world))
+    meshes = {}
+    for m in (range(n_meshes) if world > 1 and n_meshes <= 64 else mine):
+        g = torch.Generator().manual_seed(1000 + m)
+        meshes[m] = (S.make_signal(v, dims[0], seed=100 + m).to(dev), S.make_bary(v, r, a, seed=100 + m).to(dev),
+                     torch.randint(0, n_cls, (v,), generator=g).to(dev))
+
+    def run(ids):
+        for p_ in params:
+            p_.grad = None
+        for m in ids:
+            x, bary, y = meshes[m]
+            loss_fn(net(x, bary), y).backward()
+
+    def step():
+        run(mine)
+        if world > 1:
+            allreduce_gradients(params)
+    grad_err = None
+    step()
+    if world > 1:
+        dp = [p_.grad.clone() for p_ in params]
+        run(range(n_meshes))                   # the whole batch on this rank
+        err = max(((x_.double() - p_.grad.double()).abs().max() / p_.grad.double().abs().max().clamp_min(1e-30)).item()
+                  for x_, p_ in zip(dp, params))
+        grad_err = _max_over_ranks(err, world, dev)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1) / steps, world, dev)
+    return {"workload": f"S3 (BASELINE config 4): {n_meshes} FAUST-shaped meshes (V=6890, R5xA8), net 64->96->256->384 + "
+                        f"Linear->{n_cls}, cross entropy, fwd+bwd, fp32 mode, meshes round-robin over {world} rank(s), "
+                        "one all-reduce of the accumulated weight gradients per step",
+            "ms_per_step": ms, "value": n_meshes * v / (ms * 1e-3), "unit": "vertices/s", "steps": steps, "launch": "eager",
+            "grad_max_normalised_err_vs_one_rank": grad_err}
+
+
+def extra_s4(rank, world, dev, rows_per_rank=250_000, iters=5):
+    """BASELINE config 5 (at N = 8: one mesh of 2 M vertices): ConvGeodesic 128 -> 128 forward on a mesh partitioned by
+    vertex rows, 250 k rows per rank, halo exchange of neighbour signal rows over NCCL, with and without overlapping
+    the exchange with the interior rows.  Every rank generates its own rows only (locality-preserving indices)."""
+    import torch
+    import torch.distributed as dist
+    from geoconv_b200 import synthetic as S
+    from geoconv_b200.distributed import ShardedForward, build_local_shard_plan, row_ranges
+    from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
+    f = t = 128
+    r, a = 5, 8
+    v_total = rows_per_rank * world
+    lo, hi = row_ranges(v_total, world)[rank]
+    bary_rows = S.make_bary_local_rows(v_total, lo, hi, r, a, window=2048, seed=5)
+    plan = build_local_shard_plan(bary_rows, v_total)
+    torch.manual_seed(1)
+    layer = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.028).to(dev)
+    sf = ShardedForward(layer, plan, f, dev)
+    sf.load(S.make_signal(hi - lo, f, seed=50 + rank, kind="randn").to(dev))
+    out = {}
+    with torch.no_grad():
+        ys = {}
+        for overlap in (True, False):
+            for _ in range(2):
+                sf(overlap=overlap)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                blocks = sf(overlap=overlap)
+            e1.record()
+            torch.cuda.synchronize()
+            out[overlap] = _max_over_ranks(e0.elapsed_time(e1) / iters, world, dev)
+            ys[overlap] = [b_ for b_ in blocks if b_ is not None]
+        same = all(torch.equal(x_, y_) for x_, y_ in zip(ys[True], ys[False]))
+    ok = _max_over_ranks(0.0 if same else 1.0, world, dev) == 0.0
+    return {"workload": f"S4 (BASELINE config 5 at N = 8): one mesh of {v_total} vertices, ConvGeodesic 128->128 R5xA8 forward, "
+                        f"fp32 mode, {rows_per_rank} rows per rank, halo exchange (all_to_all of packed signal rows) over NCCL",
+            "ms_forward_overlapped": out[True], "ms_forward_serial": out[False],
+            "value": v_total / (out[True] * 1e-3), "unit": "vertices/s",
+            "rows_interior": sf.hi - sf.lo, "rows_boundary": plan.n_local - (sf.hi - sf.lo), "halo_rows": plan.n_halo,
+            "halo_bytes_per_rank": sf.halo_bytes, "overlap_equals_serial": ok}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from geoconv_b200 import _native, ops
-    from geoconv_b200.distributed import allreduce_gradients
+    from geoconv_b200.distributed import allreduce_gradients, overlapped_grad_sync
     from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
     from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
     from geoconv_b200 import synthetic as S   # the oracle is imported by the cpu_baseline leg only
@@ -295,14 +495,35 @@ def run_ours(args):
     sampler.start()
     params = [layer._template_neighbor_weights, layer._template_self_weights, layer._bias]
 
+    # Data parallel over meshes (N > 1): the weight gradients are summed over the ranks.  Preferred: the all-reduce
+    # is started INSIDE the layer's backward, right after the weight-gradient stage, and runs beside the dSignal
+    # GEMM (geoconv_b200.distributed.overlapped_grad_sync); it is then part of the captured step.  If that cannot
+    # be captured in a CUDA graph the step is replayed without it and the gradients are reduced after the replay.
+    grad_sync = {"ctx": None, "mode": "none"}
+    if world > 1 and args.overlap_allreduce:
+        grad_sync["ctx"] = overlapped_grad_sync()
+        grad_sync["ctx"].__enter__()
+        grad_sync["mode"] = "all-reduce inside the backward (after the weight-gradient stage, beside the dSignal GEMM)"
+    elif world > 1:
+        grad_sync["mode"] = "all-reduce after the step"
+
+    def reduce_after_step():
+        if world > 1 and grad_sync["ctx"] is None:
+            allreduce_gradients(params)
+
+    def drop_in_backward_sync(why):
+        if grad_sync["ctx"] is not None:
+            grad_sync["ctx"].__exit__(None, None, None)
+            grad_sync["ctx"] = None
+            grad_sync["mode"] = f"all-reduce after the step ({why})"
+
     def step_resident():
         for p_ in params:
             p_.grad = None
         signal_d.grad = None
         z = amp(layer([signal_d, bary_d]))
         z.backward(gz_d)
-        if world > 1:                      # data parallel over meshes: sum the weight gradients
-            allreduce_gradients(params)
+        reduce_after_step()
         return z
 
     # buffers for the host-to-host leg
@@ -320,8 +541,7 @@ def run_ours(args):
         xs = sig_buf.detach().requires_grad_(True)
         z = amp(layer([xs, bary_buf]))
         z.backward(gz_buf)
-        if world > 1:
-            allreduce_gradients(params)
+        reduce_after_step()
         z_host.copy_(z.detach(), non_blocking=True)
 
     def barrier():
@@ -389,13 +609,30 @@ def run_ours(args):
 
             def step_graph():
                 graph.replay()
-                if world > 1:
-                    allreduce_gradients(params)
+                reduce_after_step()
             step_value = step_graph
             launch_mode = "cuda-graph replay"
         except Exception as exc:  # noqa: BLE001 - measurement falls back, it never hides a compute error
             sys.stderr.write(f"bench: CUDA graph capture failed ({exc}); timing eager launches\n")
             torch.cuda.synchronize()
+            if grad_sync["ctx"] is not None:
+                # the collective inside the backward could not be captured: same capture without it
+                drop_in_backward_sync("a collective inside the backward could not be captured")
+                try:
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        fwd_bwd()
+                    graph.replay()
+                    torch.cuda.synchronize()
+
+                    def step_graph2():
+                        graph.replay()
+                        reduce_after_step()
+                    step_value = step_graph2
+                    launch_mode = "cuda-graph replay"
+                except Exception as exc2:  # noqa: BLE001
+                    sys.stderr.write(f"bench: second capture failed too ({exc2}); eager launches\n")
+                    torch.cuda.synchronize()
 
     total_ms, launches = timed(step_value, args.steps, args.warmup, sampler=sampler)
     if launches_per_step is not None:
@@ -482,8 +719,7 @@ def run_ours(args):
                 cur["graph"].replay()
                 for p_, g_ in zip(params, cur["grads"]):
                     p_.grad = g_
-                if world > 1:
-                    allreduce_gradients(params)
+                reduce_after_step()
                 fin = torch.cuda.Event()
                 fin.record(main)
                 done[i & 1] = fin
@@ -547,8 +783,7 @@ def run_ours(args):
 
             def step_e2e_graph():
                 graph2.replay()
-                if world > 1:
-                    allreduce_gradients(params)
+                reduce_after_step()
             step_e2e_value = step_e2e_graph
             e2e_mode = "cuda-graph replay"
         except Exception as exc:  # noqa: BLE001
@@ -571,6 +806,22 @@ def run_ours(args):
             sys.stderr.write(f"bench: pipelined e2e failed ({exc}); reporting the serial number\n")
             torch.cuda.synchronize()
             e2e_ms = e2e_serial_ms
+
+    extra = {}
+    if args.extras:
+        if grad_sync["ctx"] is not None:       # the extras synchronise their gradients themselves
+            grad_sync["ctx"].__exit__(None, None, None)
+        for name, fn in (("tf32", (lambda: extra_tf32(cfg, weights, (signal_d, bary_d, gz_d), flush, lib, args.steps,
+                                                        args.warmup, load_peaks())) if world == 1 else None),
+                         ("s3", lambda: extra_s3(rank, world, dev)),
+                         ("s4", (lambda: extra_s4(rank, world, dev)) if world > 1 else None)):
+            if fn is None:
+                continue
+            try:
+                extra[name] = fn()
+            except Exception as exc:  # noqa: BLE001 - an extra never takes the headline line down
+                extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                torch.cuda.synchronize()
 
     if rank != 0:
         if world > 1:
@@ -636,7 +887,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD,
                    "precision": args.precision, "launch": launch_mode, "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)",
-                   "parallelism": f"dp{world} (one mesh per rank per step" + (", NCCL all-reduce of weight gradients)" if world > 1 else ")")},
+                   "parallelism": f"dp{world} (one mesh per rank per step" + (f", NCCL {grad_sync['mode']})" if world > 1 else ")")},
         "e2e": {"value": e2e_value, "unit": "vertices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "launch": e2e_mode,
                 "overlap": e2e_mode_p or "none (copies and compute serialised on one stream)",
@@ -651,6 +902,7 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
         "clocks": clocks,
         "flops_per_step": {"fwd": fwd_flops, "bwd": bwd_flops},
+        "extra": extra,
     }
     emit(json.dumps(line))
     if world > 1:
@@ -685,6 +937,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "ffma", "tf32x3", "f16x3"])
     ap.add_argument("--graph", type=int, default=1, help="1: replay the resident step from a CUDA graph (default)")
+    ap.add_argument("--overlap-allreduce", type=int, default=1,
+                    help="1: N > 1 starts the weight-gradient all-reduce inside the backward (default); 0: after the step")
+    ap.add_argument("--extras", type=int, default=1, help="1: also measure the TF32 mode (N = 1) and configs 4 / 5 (default)")
     ap.add_argument("--e2e-pipeline", type=int, default=1,
                     help="1: overlap the H2D of step n+1 with the compute of step n in the host-to-host leg (default)")
     args = ap.parse_args()

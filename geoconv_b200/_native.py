@@ -42,14 +42,15 @@ SIGNATURES = {
     "gcb_fold_prior": (_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _int, _p]),
     "gcb_conv_fwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _int]),
     "gcb_conv_fwd": (_int, [_p, _p, _p, _p, _p, _p, C.POINTER(_i32), _i32, _i32, _i32, _i32, _i32, _i32,
-                            _i32, _int, _int, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+                            _i32, _int, _int, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _sz, _p]),
     "gcb_fwd_records_bytes": (_sz, [_i32, _i32, _i32]),
     "gcb_fwd_pack_records": (_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
     "gcb_fwd_tables_bytes": (_sz, []),
     "gcb_fwd_build_tables": (_int, [C.POINTER(_i32), _i32, _i32, _i32, _i32, _i32, _i32, _int, _p, _p]),
     "gcb_conv_amp_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _int]),
     "gcb_conv_amp_bwd": (_int, [_p, _p, _p, C.POINTER(_i32), _i32, _int, _p, _p, _p, _p, _p, _p, _p, _int, _p, _p,
-                                _i32, _i32, _i32, _i32, _i32, _i32, _int, _p, _p, _p, _p, _p, _sz, _p]),
+                                _i32, _i32, _i32, _i32, _i32, _i32, _int, _int, _p, _p, _p, _p, _p, _sz, _p]),
+    "gcb_conv_amp_bwd_can_split": (_int, [_i32, _i32, _i32, _i32, _int, _int]),
     "gcb_amp_fwd": (_int, [_p, _i32, _i32, _i32, _p, _p, _p]),
     "gcb_amp_bwd": (_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
     "gcb_bary_from_gpc": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _p]),

@@ -113,11 +113,15 @@ extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, 
                             int32_t n_rot, int32_t v_out, int32_t v_src, int32_t R, int32_t A,
                             int32_t F, int32_t T, int act, int precision, float* y, float* z,
                             int32_t* argmax, float* interp_out, const void* records, const void* tables,
-                            uint32_t* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+                            uint32_t* stats_out, int32_t row0, void* workspace, size_t workspace_bytes,
+                            void* stream) {
   GCB_REQUIRE(x && idx && w && w_self && bias, GCB_EINVAL, "gcb_conv_fwd: null input pointer");
   GCB_REQUIRE(y || z, GCB_EINVAL, "gcb_conv_fwd: need y and/or z");
   GCB_REQUIRE((z == nullptr) == (argmax == nullptr), GCB_EINVAL, "gcb_conv_fwd: z and argmax go together");
   GCB_REQUIRE(act >= 0 && act <= GCB_ACT_TANH, GCB_EINVAL, "gcb_conv_fwd: unknown activation %d", act);
+  GCB_REQUIRE(row0 >= 0 && (int64_t)row0 + v_out <= v_src, GCB_EINVAL,
+              "gcb_conv_fwd: rows [row0, row0 + v_out) = [%d, %lld) must lie inside the signal (%d rows)", row0,
+              (long long)row0 + v_out, v_src);
   int rc = check_shape(v_out, v_src, R, A, F, T);
   if (rc) return rc;
   RotTable rot;
@@ -134,7 +138,7 @@ extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, 
   workspace_bytes -= y_tmp;
   if (stats_out && (precision != GCB_PREC_F16X3 || !w_eff)) GCB_CUDA_OK(cudaMemsetAsync(stats_out, 0, 32, st));
   if (precision == GCB_PREC_FP32 || !w_eff) {  // centre-only (w_eff == NULL) is a tiny GEMM: CUDA cores
-    rc = ffma_conv_fwd(x, idx, w, w_eff, w_self, bias, rot, n_rot, v_out, v_src, R, A, F, T, act, y_out, ws, st);
+    rc = ffma_conv_fwd(x, idx, w, w_eff, w_self, bias, rot, n_rot, v_out, v_src, R, A, F, T, act, y_out, ws, st, row0);
   } else if (precision == GCB_PREC_TF32 || precision == GCB_PREC_TF32X3 || precision == GCB_PREC_F16X3) {
     GCB_REQUIRE(tc_supported(R, A, F, T, n_rot), GCB_EUNSUPPORTED,
                 "gcb_conv_fwd: tcgen05 path does not support R=%d A=%d F=%d T=%d n_rot=%d", R, A, F, T, n_rot);
@@ -142,7 +146,7 @@ extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, 
                 "gcb_conv_fwd: the fp16 split does not support R=%d A=%d F=%d T=%d n_rot=%d", R, A, F, T, n_rot);
     // the tensor-core path pools in its own finishing kernel
     return tc_conv_fwd(x, idx, w, w_eff, w_self, bias, rot, n_rot, v_out, v_src, R, A, F, T, act, precision,
-                       y_out, z, argmax, interp_out, records, tables, stats_out, ws, workspace_bytes, st);
+                       y_out, z, argmax, interp_out, records, tables, stats_out, row0, ws, workspace_bytes, st);
   } else {
     GCB_REQUIRE(false, GCB_EINVAL, "gcb_conv_fwd: unknown precision %d", precision);
   }
@@ -229,6 +233,10 @@ extern "C" size_t gcb_conv_amp_bwd_workspace_bytes(int32_t v_out, int32_t v_src,
          align_up((size_t)v_out * T * sizeof(float), 256) + align_up((size_t)v_out * sizeof(int32_t), 256) + 512;
 }
 
+extern "C" int gcb_conv_amp_bwd_can_split(int32_t R, int32_t A, int32_t F, int32_t T, int precision, int has_neighbor) {
+  return precision != GCB_PREC_FP32 && tc_bwd_supported(R, A, F, T) && has_neighbor && T % 4 == 0 && T <= 1024 ? 1 : 0;
+}
+
 namespace gcb {
 int act_grad_launch(const float* grad, const float* out, int64_t n, int act, float* h, cudaStream_t st);
 int select_rot_launch(const int32_t* argmax, const RotTable& rot, int n_rot, int v, int32_t* rot_sel, cudaStream_t st);
@@ -239,8 +247,12 @@ extern "C" int gcb_conv_amp_bwd(const float* grad_z, const float* z, const int32
                                 const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
                                 const int32_t* csr_row_ptr, const int32_t* csr_entries, int csr_flags,
                                 const uint32_t* csr_stats, const uint32_t* fwd_stats, int32_t v_out, int32_t v_src, int32_t R, int32_t A,
-                                int32_t F, int32_t T, int precision, float* d_x, float* d_w_eff, float* d_w_self,
-                                float* d_bias, void* workspace, size_t workspace_bytes, void* stream) {
+                                int32_t F, int32_t T, int precision, int stages, float* d_x, float* d_w_eff,
+                                float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  GCB_REQUIRE(stages >= 1 && stages <= 3, GCB_EINVAL, "gcb_conv_amp_bwd: stages must be 1, 2 or 3");
+  GCB_REQUIRE(stages == 3 || gcb_conv_amp_bwd_can_split(R, A, F, T, precision, w_eff != nullptr), GCB_EUNSUPPORTED,
+              "gcb_conv_amp_bwd: this shape / precision runs in one stage only");
   GCB_REQUIRE(grad_z && z && argmax && x && idx && w && w_self, GCB_EINVAL, "gcb_conv_amp_bwd: null input pointer");
   GCB_REQUIRE(!d_x || !w_eff || (csr_row_ptr && csr_entries), GCB_EINVAL, "gcb_conv_amp_bwd: d_x needs the CSR");
   GCB_REQUIRE(d_w_eff && d_w_self && d_bias, GCB_EINVAL, "gcb_conv_amp_bwd: null output pointer");
@@ -266,7 +278,7 @@ extern "C" int gcb_conv_amp_bwd(const float* grad_z, const float* z, const int32
   if (precision != GCB_PREC_FP32 && tc_bwd_supported(R, A, F, T) && aligned)
     return tc_conv_bwd(x, idx, w, w_eff, w_self, amp.h, amp.rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T,
                        precision, 0, nullptr, d_x, d_w_eff, d_w_self, d_bias, ws, rest, st, &amp,
-                       (csr_flags & GCB_CSR_RING_GROUPED) != 0);
+                       (csr_flags & GCB_CSR_RING_GROUPED) != 0, stages);
   // CUDA-core route (or a shape the preparation kernel does not tile): the separate small kernels, then gcb_conv_bwd
   rc = act_grad_launch(grad_z, z, (int64_t)v_out * T, act, amp.h, st);
   if (rc) return rc;

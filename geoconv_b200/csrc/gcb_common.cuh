@@ -84,7 +84,7 @@ size_t ffma_fwd_workspace_bytes(int v_out, int R, int A, int F);
 int ffma_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                   const float* w_self, const float* bias, const RotTable& rot, int n_rot,
                   int v_out, int v_src, int R, int A, int F, int T, int act, float* y,
-                  void* workspace, cudaStream_t st);
+                  void* workspace, cudaStream_t st, int row0 = 0);
 size_t ffma_bwd_workspace_bytes(int v_out, int R, int A, int F);
 int ffma_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                   const float* h, const int32_t* rot_sel, int v_out, int v_src, int R, int A,
@@ -102,7 +102,8 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
                 float* z /* nullable: fused AngularMaxPooling */, int32_t* argmax,
                 float* interp_out /* nullable: keep I[v_out,R,A,F] for the backward */,
                 const void* records /* nullable: gcb_fwd_pack_records */, const void* tables /* nullable: gcb_fwd_build_tables */,
-                uint32_t* stats_out /* nullable: 8 words of operand maxima for the backward */, void* workspace,
+                uint32_t* stats_out /* nullable: 8 words of operand maxima for the backward */,
+                int row0 /* output row k is vertex row0 + k of the signal (centre term) */, void* workspace,
                 size_t workspace_bytes, cudaStream_t st);
 
 // shared small kernels (gcb_pool.cu)

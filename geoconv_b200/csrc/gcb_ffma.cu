@@ -178,7 +178,7 @@ size_t ffma_fwd_workspace_bytes(int v_out, int R, int A, int F) {
 int ffma_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                   const float* w_self, const float* bias, const RotTable& rot, int n_rot,
                   int v_out, int v_src, int R, int A, int F, int T, int act, float* y,
-                  void* workspace, cudaStream_t st) {
+                  void* workspace, cudaStream_t st, int row0) {
   (void)v_src;
   float* interp = (float*)workspace;
   int64_t rows = (int64_t)v_out * R * A;
@@ -192,7 +192,7 @@ int ffma_conv_fwd(const float* x, const int32_t* idx, const float* w, const floa
   op.M = v_out; op.N = w_eff ? n_rot * T : T; op.KRA = w_eff ? R * A * F : 0; op.K = op.KRA + F;
   op.n_bcast = w_eff ? 1 : n_rot;
   op.A = A; op.F = F; op.T = T; op.act = act;
-  op.interp = interp; op.x = x; op.w_eff = w_eff; op.w_self = w_self; op.bias = bias; op.y = y;
+  op.interp = interp; op.x = x + (size_t)row0 * F /* centre term: output row k is vertex row0 + k */; op.w_eff = w_eff; op.w_self = w_self; op.bias = bias; op.y = y;
   op.rot = rot;
   return launch_sgemm(op, st);
 }

@@ -103,6 +103,6 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
                 int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,
                 const float* interp /* nullable: I saved by the forward */, float* d_x, float* d_w_eff,
                 float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                const TcBwdAmp* amp = nullptr, bool csr_ring_grouped = false);
+                const TcBwdAmp* amp = nullptr, bool csr_ring_grouped = false, int stages = 3);
 
 }  // namespace gcb

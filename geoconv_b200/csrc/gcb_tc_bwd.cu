@@ -655,7 +655,7 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
                 const float* h, const int32_t* rot_sel, const int32_t* csr_row_ptr, const int32_t* csr_entries,
                 int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,
                 const float* interp, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias, void* workspace,
-                size_t workspace_bytes, cudaStream_t st, const TcBwdAmp* amp, bool csr_ring_grouped) {
+                size_t workspace_bytes, cudaStream_t st, const TcBwdAmp* amp, bool csr_ring_grouped, int stages) {
   // fp16 operand splits (GCB_PREC_F16X3) serve the route through G; the centre-only and gather-fed routes run
   // the same precision request as 3xTF32
   static const bool no_half = getenv("GCB_BWD_NO_HALF") && atoi(getenv("GCB_BWD_NO_HALF")) != 0;   // A/B measurements
@@ -677,15 +677,20 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
   // came along - both operand splits are produced by ONE launch (k_bw_prepare)
   bool bias_done = false, scales_done = false, x_split_done = false, w_split_done = false;
   const TcGLayout GMX = tc_g_layout_max(v_src, R, A, F, T, x3);
+  // stages (route through G only): 1 = everything up to the weight gradients, 2 = the signal gradient from the G, the
+  // scales and the weight split a stage-1 call left in the SAME workspace; 3 = both.  A caller that reduces weight
+  // gradients over ranks starts its collective between the two calls, beside the dSignal GEMM.
+  const bool can_split = w_eff && csr_row_ptr && csr_entries;
+  const bool do_w = !can_split || (stages & 1), do_x = !can_split || (stages & 2);
   if (amp) {
     GCB_REQUIRE(T % 4 == 0 && T <= 1024 && ((uintptr_t)amp->grad_z % 16 == 0) && ((uintptr_t)amp->z % 16 == 0) &&
                     ((uintptr_t)d_bias % 16 == 0), GCB_EINVAL,
                 "tc_conv_bwd: grad_z / z / d_bias must be 16-byte aligned and T a multiple of 4");
     unsigned* mx = (unsigned*)scale_scratch;
-    GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 32, st));
+    if (do_w) GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 32, st));
     const bool have_csr = csr_row_ptr && w_eff;
     const bool stats = half && amp->fwd_stats && (!have_csr || amp->csr_stats);
-    if (half && !stats) {   // the maxima the caller did not bring along (mode 0: no scales yet)
+    if (half && !stats && do_w) {   // the maxima the caller did not bring along (mode 0: no scales yet)
       TcMaxJob job{};
       job.mode = 0;
       int n = 0;
@@ -737,8 +742,10 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     }
     const int T4 = T / 4;
     const size_t smem = (size_t)(BWP_THREADS / T4) * T4 * sizeof(float4);
-    k_bw_prepare<<<pp.nb_h + pp.nb_x + pp.nb_w, BWP_THREADS, smem, st>>>(pp);
-    GCB_LAUNCH_OK();
+    if (do_w) {
+      k_bw_prepare<<<pp.nb_h + pp.nb_x + pp.nb_w, BWP_THREADS, smem, st>>>(pp);
+      GCB_LAUNCH_OK();
+    }
     h = amp->h;
     rot_sel = amp->rot_sel;
     bias_done = true;
@@ -784,7 +791,7 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     const float* scales = nullptr;
     if (half) {   // fp16 buffers: rows of kg_ld halves (they fit in the 3xTF32 sizes)
       g_lo = (float*)((__half*)g_hi + (size_t)GL.v_pad * (ceil_div64(GL.kg, 64) * 64));
-      if (!scales_done) {
+      if (!scales_done && do_w) {
         rc = tc_bwd_scales(h, w, csr_row_ptr, w_eff, w_self, x, v_out, v_src, R, A, F, T, scale_scratch, st);
         if (rc) return rc;
       }
@@ -795,18 +802,21 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     float* x_lo = x3 ? x_hi + (size_t)v_src * F : nullptr;
     ws += GM.xsplit_bytes;
     float* partial = (float*)ws;
-    if (!bias_done) {
-      k_bw_bias_partial<<<dim3((unsigned)L.bias_blocks, (unsigned)ceil_div64(T, 32)), dim3(32, 8), 0, st>>>(
-          h, v_out, T, L.bias_rows, bias_part);
-      GCB_LAUNCH_OK();
-      k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.bias_blocks, T, accumulate, d_bias);
-      GCB_LAUNCH_OK();
+    if (do_w) {
+      if (!bias_done) {
+        k_bw_bias_partial<<<dim3((unsigned)L.bias_blocks, (unsigned)ceil_div64(T, 32)), dim3(32, 8), 0, st>>>(
+            h, v_out, T, L.bias_rows, bias_part);
+        GCB_LAUNCH_OK();
+        k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.bias_blocks, T, accumulate, d_bias);
+        GCB_LAUNCH_OK();
+      }
+      rc = tc_build_g(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, x3, g_hi, g_lo, st, scales, csr_ring_grouped);
+      if (rc) return rc;
+      rc = tc_dw_from_g(g_hi, g_lo, x, v_src, R, A, F, T, x3, accumulate, d_w_eff, d_w_self, x_hi, x_lo, partial,
+                        GM.partial_bytes, st, scales, half && x_split_done);
+      if (rc) return rc;
     }
-    rc = tc_build_g(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, x3, g_hi, g_lo, st, scales, csr_ring_grouped);
-    if (rc) return rc;
-    rc = tc_dw_from_g(g_hi, g_lo, x, v_src, R, A, F, T, x3, accumulate, d_w_eff, d_w_self, x_hi, x_lo, partial,
-                      GM.partial_bytes, st, scales, half && x_split_done);
-    if (rc || !d_x) return rc;
+    if (!d_x || !do_x) return GCB_OK;
     if (!(half && w_split_done)) {
       rc = half ? tc_build_wcat_h(w_eff, w_self, T, R, A, F, scales + 1, (__half*)wc_hi, (__half*)wc_lo, st)
                 : tc_build_wcat(w_eff, w_self, T, R, A, F, wc_hi, wc_lo, st);

@@ -154,43 +154,37 @@ __global__ void k_bw_build_g(const float* __restrict__ h, const float* __restric
 }
 
 
-// ---- G[v, s', t], ring-grouped CSR: accumulators in registers ----------------------------------------
+// ---- G[v, s', t], ring-grouped CSR: one register accumulator per lane and template --------------------
 // The rotation moves a template vertex only INSIDE its radial ring: s' = (x, (y + rot_k) % A).  With the CSR
-// entries of a source vertex grouped by ring x (gcb_csr_build with the template size), the A accumulators of the
-// current ring live in registers and shared memory is only used to broadcast the decoded entries:
+// entries of a source vertex grouped by ring x (gcb_csr_build with the template size) the kernel needs no
+// accumulator array at all:
 //   one warp per source vertex, lane l owns templates l, l + 32, ... (TPL per pass, passes over T for wide layers);
-//   per 32 entries the lanes decode one entry each ({h row, rotated angular index, weight}) into a per-warp staging
-//   row; then per entry: one broadcast read, TPL coalesced loads of h, TPL FMAs into the accumulator the (warp-
-//   uniform) angular index selects; at a ring boundary the A accumulators are converted and stored, rings without
-//   entries are written as zeros.
+//   per 32 entries the lanes decode one entry each ({h row, ring, rotated angular index y', weight}) into a per-warp
+//   staging row and keep (ring, y') in registers;
+//   for every ring segment of the chunk and every y' a ballot gives the segment's entries with that y'; their h
+//   rows are summed (CSR order: the order of k_bw_build_g, same bits) into TPL registers and stored - converted -
+//   straight to G.  Rings without entries are written as zeros.
+//   A ring that straddles a 32-entry chunk parks its running sums in a per-warp shared-memory tile and continues
+//   from them (rare: a ring has ~24 entries at the FAUST shape).
 // Against k_bw_build_g (an (R*A) x T accumulator in shared memory, read-modify-written per entry: 4 load/store-unit
-// wavefronts per (entry, warp), 84 us at the FAUST shape) this leaves 1 + TPL wavefronts per (entry, vertex).
-// The order of additions inside every (v, s') is the CSR order in both kernels: same bits.
+// wavefronts per (entry, warp), 84 us at the FAUST shape) an entry costs one broadcast read and TPL loads.
+// Two earlier variants are recorded in profiles/r02_notes.md: A accumulators per template selected by a switch on y'
+// (187 us: three indirect branches per entry) and the same with 8 entries' loads in flight (178 us).
 constexpr int G2_WARPS = 8;
 
-template <int AMAX>
-__device__ __forceinline__ void g2_add(float (&acc)[AMAX], int yr, float wgt, float hv) {
-  // yr is warp-uniform: a jump table, no divergence
-  switch (yr) {
-#define GCB_G2_CASE(i) case i: if (i < AMAX) acc[i < AMAX ? i : 0] = fmaf(wgt, hv, acc[i < AMAX ? i : 0]); break;
-    GCB_G2_CASE(0) GCB_G2_CASE(1) GCB_G2_CASE(2) GCB_G2_CASE(3) GCB_G2_CASE(4) GCB_G2_CASE(5) GCB_G2_CASE(6) GCB_G2_CASE(7)
-    GCB_G2_CASE(8) GCB_G2_CASE(9) GCB_G2_CASE(10) GCB_G2_CASE(11) GCB_G2_CASE(12) GCB_G2_CASE(13) GCB_G2_CASE(14) GCB_G2_CASE(15)
-#undef GCB_G2_CASE
-    default: break;
-  }
-}
-
-template <bool H, int AMAX, int TPL>
+template <bool H, int TPL>
 __global__ void __launch_bounds__(G2_WARPS * 32)
 k_bw_build_g2(const float* __restrict__ h, const float* __restrict__ w, const int32_t* __restrict__ rot_sel,
               const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ entries, int v_out, int v_src, int v_pad,
               int R, int A, int T, int kg, int kg_ld, const float* __restrict__ scales, float* __restrict__ g_hi,
               float* __restrict__ g_lo) {
-  __shared__ int4 s_meta[G2_WARPS][32];
+  extern __shared__ float s_carry_all[];               // [G2_WARPS][A][32 * TPL]: running sums of a straddling ring
+  __shared__ int2 s_meta[G2_WARPS][32];                // {h row offset, weight bits}
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int v = blockIdx.x * G2_WARPS + warp;
   if (v >= v_pad) return;
   const int RA = R * A;
+  float* s_carry = s_carry_all + (size_t)warp * A * 32 * TPL;
   float* out_hi = g_hi + (size_t)v * kg;
   float* out_lo = g_lo ? g_lo + (size_t)v * kg : nullptr;
   __half* hh = reinterpret_cast<__half*>(g_hi) + (size_t)v * kg_ld;
@@ -213,61 +207,105 @@ k_bw_build_g2(const float* __restrict__ h, const float* __restrict__ w, const in
   }
   const int beg = row_ptr[v], end = row_ptr[v + 1];
   for (int t_base = 0; t_base < T; t_base += 32 * TPL) {
-    float acc[TPL][AMAX];
-#pragma unroll
-    for (int j = 0; j < TPL; ++j)
-#pragma unroll
-      for (int y = 0; y < AMAX; ++y) acc[j][y] = 0.f;
-    int cur_x = 0;          // ring whose sums the accumulators hold; rings below it are written
-    auto flush = [&](int x_next) {
-      // store ring cur_x, zero rings cur_x + 1 .. x_next - 1, start ring x_next
-#pragma unroll
-      for (int y = 0; y < AMAX; ++y) {
-        if (y < A) {
-#pragma unroll
-          for (int j = 0; j < TPL; ++j) {
-            const int t = t_base + 32 * j + lane;
-            if (t < T) put((cur_x * A + y) * T + t, acc[j][y]);
-            acc[j][y] = 0.f;
-          }
-        }
-      }
-      for (int x = cur_x + 1; x < x_next; ++x)
+    int next_x = 0;           // rings below it are written
+    bool open = false;        // ring `next_x` has running sums parked in s_carry (it may continue in the next chunk)
+    auto zero_rings = [&](int x0, int x1) {
+      for (int x = x0; x < x1; ++x)
         for (int y = 0; y < A; ++y)
 #pragma unroll
           for (int j = 0; j < TPL; ++j) {
             const int t = t_base + 32 * j + lane;
             if (t < T) put((x * A + y) * T + t, 0.f);
           }
-      cur_x = x_next;
+    };
+    auto close_ring = [&]() {   // the parked ring is complete: convert and store it
+      for (int y = 0; y < A; ++y)
+#pragma unroll
+        for (int j = 0; j < TPL; ++j) {
+          const int t = t_base + 32 * j + lane;
+          if (t < T) put((next_x * A + y) * T + t, s_carry[(y * TPL + j) * 32 + lane]);
+        }
+      open = false;
+      ++next_x;
     };
     for (int base = beg; base < end; base += 32) {
       const int n = min(32, end - base);
       __syncwarp();
+      int my_x = -1, my_y = -1;
       if (lane < n) {
         const int s = __ldg(entries + base + lane);
         const int cell = s / 3;
         const int k = cell / RA;
         const int slot = cell - k * RA;
-        const int xr = slot / A, ya = slot - xr * A;
-        int yr = ya + __ldg(rot_sel + k);
-        yr -= (yr >= A) ? A : 0;
-        s_meta[warp][lane] = make_int4(k * T, xr, yr, __float_as_int(__ldg(w + s)));
+        my_x = slot / A;
+        my_y = slot - my_x * A + __ldg(rot_sel + k);
+        my_y -= (my_y >= A) ? A : 0;
+        s_meta[warp][lane] = make_int2(k * T, __float_as_int(__ldg(w + s)));
       }
       __syncwarp();
-      for (int i = 0; i < n; ++i) {
-        const int4 m = s_meta[warp][i];
-        if (m.y != cur_x) flush(m.y);     // (warp-uniform)
-        const float wgt = __int_as_float(m.w);
-        const float* hrow = h + (size_t)m.x + t_base + lane;
+      int pos = 0;
+      while (pos < n) {
+        const int x = __shfl_sync(0xffffffffu, my_x, pos);
+        const unsigned seg = __ballot_sync(0xffffffffu, my_x == x);          // (entries of a ring are adjacent)
+        const int seg_end = pos + __popc(seg);
+        if (open && x != next_x) close_ring();
+        const bool cont = open;                                               // this segment continues the parked ring
+        if (!cont) { zero_rings(next_x, x); next_x = x; }
+        const bool more = seg_end == n && base + n < end;                     // the ring may go on in the next chunk
+        for (int y = 0; y < A; ++y) {
+          unsigned bits = seg & __ballot_sync(0xffffffffu, my_y == y);
+          float acc[TPL];
 #pragma unroll
-        for (int j = 0; j < TPL; ++j) {
-          const float hv = (t_base + 32 * j + lane < T) ? __ldg(hrow + 32 * j) : 0.f;
-          g2_add<AMAX>(acc[j], m.z, wgt, hv);   // (the same fused multiply-add as k_bw_build_g: same bits)
+          for (int j = 0; j < TPL; ++j) acc[j] = cont ? s_carry[(y * TPL + j) * 32 + lane] : 0.f;
+          while (bits) {
+            // up to four entries' rows are requested before the first is added (CSR order kept)
+            int e[4];
+            float wg[4], hv[4][TPL];
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              e[u] = bits ? __ffs((int)bits) - 1 : -1;
+              if (bits) { bits &= bits - 1; ++cnt; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (u < cnt) {
+                const int2 m = s_meta[warp][e[u]];
+                wg[u] = __int_as_float(m.y);
+                const float* hrow = h + (size_t)m.x + t_base + lane;
+#pragma unroll
+                for (int j = 0; j < TPL; ++j) hv[u][j] = (t_base + 32 * j + lane < T) ? __ldg(hrow + 32 * j) : 0.f;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (u < cnt) {
+#pragma unroll
+                for (int j = 0; j < TPL; ++j) acc[j] = fmaf(wg[u], hv[u][j], acc[j]);
+              }
+          }
+          if (cont || more) {
+#pragma unroll
+            for (int j = 0; j < TPL; ++j) s_carry[(y * TPL + j) * 32 + lane] = acc[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < TPL; ++j) {
+              const int t = t_base + 32 * j + lane;
+              if (t < T) put((x * A + y) * T + t, acc[j]);
+            }
+          }
         }
+        if (cont || more) {
+          open = true;
+          if (!more) close_ring();
+        } else {
+          ++next_x;
+        }
+        pos = seg_end;
       }
     }
-    flush(R);                              // the last ring that had entries, and empty rings after it
+    if (open) close_ring();
+    zero_rings(next_x, R);                 // empty rings after the last one that had entries
   }
   for (int i = lane; i < T; i += 32)       // centre slab: h[v] itself (zero for halo rows)
     put(RA * T + i, v < v_out ? h[(size_t)v * T + i] : 0.f);
@@ -818,12 +856,16 @@ TcGLayout tc_g_layout_max(int v_src, int R, int A, int F, int T, bool x3) {
   return L;
 }
 
-template <bool H, int AMAX, int TPL>
-static void launch_build_g2(const float* h, const float* w, const int32_t* rot_sel, const int32_t* row_ptr,
-                            const int32_t* entries, int v_out, int v_src, int v_pad, int R, int A, int T, int kg, int kg_ld,
-                            const float* scales, float* g_hi, float* g_lo, cudaStream_t st) {
-  k_bw_build_g2<H, AMAX, TPL><<<(unsigned)ceil_div64(v_pad, G2_WARPS), G2_WARPS * 32, 0, st>>>(
+template <bool H, int TPL>
+static int launch_build_g2(const float* h, const float* w, const int32_t* rot_sel, const int32_t* row_ptr,
+                           const int32_t* entries, int v_out, int v_src, int v_pad, int R, int A, int T, int kg, int kg_ld,
+                           const float* scales, float* g_hi, float* g_lo, cudaStream_t st) {
+  const size_t smem = (size_t)G2_WARPS * A * 32 * TPL * sizeof(float);
+  if (smem > 40 * 1024)
+    GCB_CUDA_OK(cudaFuncSetAttribute(k_bw_build_g2<H, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_bw_build_g2<H, TPL><<<(unsigned)ceil_div64(v_pad, G2_WARPS), G2_WARPS * 32, smem, st>>>(
       h, w, rot_sel, row_ptr, entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, g_lo);
+  return GCB_OK;
 }
 
 int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int32_t* csr_row_ptr,
@@ -832,20 +874,21 @@ int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int
   const int RA = R * A;
   const int kg = (RA + 1) * T;
   const int v_pad = (int)ceil_div64(v_src, 128) * 128;
-  static const bool g2_off = getenv("GCB_BUILD_G2") && atoi(getenv("GCB_BUILD_G2")) == 0;   // A/B measurements
-  if (ring_sorted && A <= 16 && T % 32 == 0 && !g2_off) {
+  // GCB_BUILD_G2=0 (read per call): the shared-memory kernel k_bw_build_g, for A/B measurements
+  const bool g2_off = getenv("GCB_BUILD_G2") && atoi(getenv("GCB_BUILD_G2")) == 0;
+  if (ring_sorted && A <= GCB_MAX_ROT && T % 32 == 0 && !g2_off) {
     const bool half = scales != nullptr;
     const int kg_ld = half ? (int)ceil_div64(kg, 64) * 64 : kg;
     float* lo = half || x3 ? g_lo : nullptr;
     const int tpl = T % 128 == 0 ? 4 : (T % 96 == 0 ? 3 : (T % 64 == 0 ? 2 : 1));
+    int rc;
     profile_begin(GCB_PROF_BWD_CSR, st);
-#define GCB_G2_LAUNCH(HH, AM, TP) launch_build_g2<HH, AM, TP>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, lo, st)
-#define GCB_G2_TPL(HH, AM) (tpl == 4 ? GCB_G2_LAUNCH(HH, AM, 4) : tpl == 3 ? GCB_G2_LAUNCH(HH, AM, 3) : tpl == 2 ? GCB_G2_LAUNCH(HH, AM, 2) : GCB_G2_LAUNCH(HH, AM, 1))
-    if (half) { if (A <= 8) GCB_G2_TPL(true, 8); else GCB_G2_TPL(true, 16); }
-    else { if (A <= 8) GCB_G2_TPL(false, 8); else GCB_G2_TPL(false, 16); }
-#undef GCB_G2_TPL
+#define GCB_G2_LAUNCH(HH, TP) launch_build_g2<HH, TP>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, lo, st)
+    if (half) rc = tpl == 4 ? GCB_G2_LAUNCH(true, 4) : tpl == 3 ? GCB_G2_LAUNCH(true, 3) : tpl == 2 ? GCB_G2_LAUNCH(true, 2) : GCB_G2_LAUNCH(true, 1);
+    else rc = tpl == 4 ? GCB_G2_LAUNCH(false, 4) : tpl == 3 ? GCB_G2_LAUNCH(false, 3) : tpl == 2 ? GCB_G2_LAUNCH(false, 2) : GCB_G2_LAUNCH(false, 1);
 #undef GCB_G2_LAUNCH
     profile_end(GCB_PROF_BWD_CSR, st);
+    if (rc) return rc;
     GCB_LAUNCH_OK();
     return GCB_OK;
   }

@@ -101,6 +101,7 @@ struct TcRing {
 
 struct TcFwdParams {
   const float* x;       // [v_src, F]
+  const float* x_centre;  // row 0 of the centre term: output row k multiplies Wself with x_centre[k] (= x + row0 * F)
   const uint4* recs;    // [R*A, v_pad, 2]: {i0,i1,i2,-} {w0,w1,w2,-}
   float* partial;       // [ksplit, v_pad, n_rot, T] raw accumulators
   float* interp_out;    // optional [v_out, R*A*F]: the interpolations, kept for the backward's dW
@@ -123,7 +124,7 @@ struct TcFwdParams {
   // fused finish (fuse = 1): the K splits of a (vertex tile, template chunk, rotation group) unit are neighbours in
   // dispatch order; the split that finishes last sums the unit's partial sums (still L2-resident) in split order and
   // applies bias / activation, the unit that finishes a vertex tile last does the angular max-pooling
-  int fuse;
+  int fuse;              // 1: fused finish; 2: the same dispatch order, reduction left to k_tc_finish (A/B of the order)
   unsigned* tickets;     // [m_tiles * t_chunks * n_groups] arrivals per unit, then [m_tiles] finished units per tile (zeroed)
   float* nrm2;           // [v_pad][n_rot][t_chunks] squared norms of the activated rows, per template chunk
   const float* bias;
@@ -961,7 +962,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
                                   threadIdx.x == TC_WARP_PROD0 * 32 ? p.trace + ((size_t)3 * 128 + 127) * 8 : nullptr;
   if (life) life[0] = clock64();
   long long* const clog = p.cta_log && threadIdx.x == TC_WARP_PROD0 * 32
-                              ? p.cta_log + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 5 : nullptr;
+                              ? p.cta_log + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (clog) {
     unsigned sm;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
@@ -1174,7 +1175,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
             const int row = m0 + row_w + row_l + j * ROWS_PER_PASS;
 #pragma unroll
             for (int q = 0; q < NV; ++q)
-              v[j * NV + q] = row < p.v_out ? __ldg(reinterpret_cast<const float4*>(xcol + (size_t)row * p.F) + q)
+              v[j * NV + q] = row < p.v_out ? __ldg(reinterpret_cast<const float4*>(xcol + (p.x_centre - p.x) + (size_t)row * p.F) + q)
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
@@ -1300,7 +1301,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
           ptx::bulk_commit_group();
         }
       }
-      if (p.fuse) ptx::bulk_wait_all();   // ... and the rows must have reached global memory before the ticket is taken
+      if (p.fuse == 1) ptx::bulk_wait_all();   // ... and the rows must have reached global memory before the ticket is taken
       else ptx::bulk_wait_read_all();     // shared memory must outlive the copies' reads
     } else {
       for (int il = dh; il < g_cnt; il += TC_PRODUCER_WARPS / 4) {
@@ -1315,7 +1316,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       }
     }
     if (life) life[4] = clock64();
-    if (p.fuse) {
+    if (p.fuse == 1) {
       // ===================== fused finish: split reduction, bias, activation, angular max-pooling =====================
       // Every producer thread has completed its own partial-sum stores (bulk copies waited for / plain stores);
       // publish them (fence, barrier, one ticket per CTA).  Nobody waits for anybody: the CTA whose ticket is the
@@ -1325,6 +1326,11 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
       __threadfence();
       producer_bar_sync();
       const int unit = (tile_m * t_chunks + tz) * (int)gridDim.y + grp;
+      if (clog) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        clog[5] = (long long)gt;
+      }
       if (ptid == 0) {
         const unsigned t = atomicAdd(p.tickets + unit, 1u);
         __threadfence();
@@ -1353,6 +1359,10 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
         ptx::fence_proxy_async_all();
         auto issue = [&](int b, int buf) {
           const int r_lo = b * nb, r_n = min(nb, rows_valid - r_lo);
+          if (p.debug & 16) {   // timing experiment: no copies (the sums are garbage)
+            if (ptid == 0) ptx::mbar_arrive(fin_bar + 8u * (uint32_t)buf);
+            return;
+          }
           if (ptid == 0) ptx::mbar_arrive_expect_tx(fin_bar + 8u * (uint32_t)buf, (uint32_t)r_n * row_bytes);
           for (int i = ptid; i < r_n * p.ksplit * pieces; i += TC_PRODUCER_WARPS * 32) {
             const int pc = i % pieces, sp = (i / pieces) % p.ksplit, rr = i / (pieces * p.ksplit);
@@ -1368,7 +1378,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
           const int buf = b & 1;
           ptx::mbar_wait(fin_bar + 8u * (uint32_t)buf, (uint32_t)(b >> 1) & 1u);
           const int rr = pw, vrow = m0 + b * nb + rr;
-          if (rr < nb && b * nb + rr < rows_valid) {
+          if (rr < nb && b * nb + rr < rows_valid && !(p.debug & 32)) {   // (32: timing experiment, copies only)
             const float4* sm = reinterpret_cast<const float4*>(
                 smem_gen + (b_base - smem_base) + (size_t)buf * nb * row_bytes + (size_t)rr * row_bytes);
             const uint32_t seg4 = seg_floats >> 2;
@@ -1441,6 +1451,11 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ C
               if (lane == 0 && p.z) p.nrm2[((size_t)vrow * p.n_rot + rot0 + il) * t_chunks + tz] = sq;
             }
           }
+        }
+        if (clog) {
+          unsigned long long gt;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+          clog[6] = 1; clog[7] = (long long)gt;
         }
         if (p.z) {
           // the unit that completes this vertex tile pools it: norms over all template chunks (chunk order), first
@@ -2009,7 +2024,7 @@ int tc_fwd_pack_records(const int32_t* idx, const float* w, int v_out, int R, in
 int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
                 const float* bias, const RotTable& rot, int n_rot, int v_out, int v_src, int R, int A, int F,
                 int T, int act, int precision, float* y, float* z, int32_t* argmax, float* interp_out,
-                const void* records, const void* tables, uint32_t* stats_out,
+                const void* records, const void* tables, uint32_t* stats_out, int row0,
                 void* workspace, size_t workspace_bytes, cudaStream_t st) {
   TcFwdPlan plan;
   int rc = tc_fwd_plan(rot, n_rot, v_out, R, A, F, T, precision, &plan);
@@ -2044,7 +2059,12 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   ws += ticket_bytes;
   unsigned* mx = (unsigned*)ws;                 // fp16 mode: operand maxima, then the scales
   float* scales = half ? (float*)(mx + 8) : nullptr;
-  static const int fuse_env = getenv("GCB_TC_FUSE") ? atoi(getenv("GCB_TC_FUSE")) : 1;   // 0: separate k_tc_finish (A/B)
+  // GCB_TC_FUSE (read per call, so one process can run both): 0 (default) = k_tc_finish reduces the K splits in a
+  // launch of its own; 1 = the reduction, bias, activation and pooling run inside k_tc_conv (last-arriving split of a
+  // unit); 2 = the fused mode's dispatch order with the separate finish.  Measured at the FAUST shape (profiles/
+  // r02_notes.md): 1 removes the launch and 4/5 of the DRAM traffic but a finishing CTA needs ~75 us for its 1.5 MB
+  // of partial sums (one SM pulls ~13 B/cycle from L2) while its SM issues no MMAs: 640 us against 499 + 38.
+  const int fuse_env = getenv("GCB_TC_FUSE") ? atoi(getenv("GCB_TC_FUSE")) : 0;
   const long long grid_x = (long long)ksplit * m_tiles * (T / cfg.n_t);
   const bool fuse = fuse_env != 0 && grid_x < (1ll << 31) && T % 4 == 0;
   const unsigned* ext_wsum = nullptr;
@@ -2094,7 +2114,8 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   TcFwdParams p;
   tc_fwd_plan_params(plan, rot, n_rot, v_out, R, A, F, T, &p);
   p.x = x; p.recs = recs; p.partial = partial; p.interp_out = interp_out; p.scales = scales;
-  p.fuse = fuse ? 1 : 0;
+  p.x_centre = x + (size_t)row0 * F;
+  p.fuse = fuse ? (fuse_env == 2 ? 2 : 1) : 0;
   p.tickets = tickets; p.nrm2 = nrm2; p.bias = bias; p.y = y; p.z = z; p.argmax = argmax; p.act = act;
   {
     static const int discard_env = getenv("GCB_TC_DISCARD") ? atoi(getenv("GCB_TC_DISCARD")) : 1;   // A/B
@@ -2114,9 +2135,9 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   static long long* clog_dev = nullptr;
   const size_t n_ctas = (size_t)m_tiles * cfg.n_groups * (T / cfg.n_t) * ksplit;
   if (getenv("GCB_TC_TRACE") && atoi(getenv("GCB_TC_TRACE")) == 2) {
-    if (!clog_dev) GCB_CUDA_OK(cudaMalloc(&clog_dev, 16384 * 5 * sizeof(long long)));
+    if (!clog_dev) GCB_CUDA_OK(cudaMalloc(&clog_dev, 16384 * 8 * sizeof(long long)));
     if (n_ctas <= 16384) {
-      GCB_CUDA_OK(cudaMemsetAsync(clog_dev, 0, n_ctas * 5 * sizeof(long long), st));
+      GCB_CUDA_OK(cudaMemsetAsync(clog_dev, 0, n_ctas * 8 * sizeof(long long), st));
       p.cta_log = clog_dev;
     }
   }
@@ -2137,7 +2158,7 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   else if (cfg.kc == 16) rc = x3 ? tc_launch<16, true>(mh, ml, p, cfg, grid, st) : tc_launch<16, false>(mh, ml, p, cfg, grid, st);
   else rc = x3 ? tc_launch<8, true>(mh, ml, p, cfg, grid, st) : tc_launch<8, false>(mh, ml, p, cfg, grid, st);
   if (rc) return rc;
-  if (!fuse) {
+  if (p.fuse != 1) {
     const int warps_per_block = 8;
     k_tc_finish<<<(unsigned)ceil_div64(v_out, warps_per_block), warps_per_block * 32, 0, st>>>(
         partial, bias, ksplit, v_out, v_pad, n_rot, T, act, scales, y, z, argmax);
@@ -2145,23 +2166,38 @@ int tc_conv_fwd(const float* x, const int32_t* idx, const float* w, const float*
   }
   if (p.cta_log) {
     // per-CTA life times: printed by dispatch order in groups of 148 (one "wave" if all CTAs took equally long)
-    static long long hl[16384 * 5];
-    GCB_CUDA_OK(cudaMemcpyAsync(hl, p.cta_log, n_ctas * 5 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    static long long hl[16384 * 8];
+    GCB_CUDA_OK(cudaMemcpyAsync(hl, p.cta_log, n_ctas * 8 * sizeof(long long), cudaMemcpyDeviceToHost, st));
     GCB_CUDA_OK(cudaStreamSynchronize(st));
     long long t_min = hl[0], t_max = 0;
-    for (size_t i = 0; i < n_ctas; ++i) { if (hl[i * 5] < t_min) t_min = hl[i * 5]; if (hl[i * 5 + 1] > t_max) t_max = hl[i * 5 + 1]; }
+    for (size_t i = 0; i < n_ctas; ++i) { if (hl[i * 8] < t_min) t_min = hl[i * 8]; if (hl[i * 8 + 1] > t_max) t_max = hl[i * 8 + 1]; }
     fprintf(stderr, "[cta log] %zu CTAs, kernel span %.1f us\n", n_ctas, (t_max - t_min) * 1e-3);
-    for (size_t g0 = 0; g0 < n_ctas; g0 += 148) {
-      const size_t g1 = g0 + 148 < n_ctas ? g0 + 148 : n_ctas;
-      double s_ns = 0, s_cy = 0, st0 = 0, en = 0; long long mx_ns = 0;
-      for (size_t i = g0; i < g1; ++i) {
-        const long long ns = hl[i * 5 + 1] - hl[i * 5], cy = hl[i * 5 + 3] - hl[i * 5 + 2];
-        s_ns += ns; s_cy += cy; st0 += hl[i * 5] - t_min; en += hl[i * 5 + 1] - t_min;
-        if (ns > mx_ns) mx_ns = ns;
+    {
+      // dispatch order = ascending start time
+      static size_t order[16384];
+      for (size_t i = 0; i < n_ctas; ++i) order[i] = i;
+      for (size_t i = 1; i < n_ctas; ++i) {   // insertion sort (nearly sorted already)
+        const size_t o = order[i];
+        size_t j = i;
+        while (j > 0 && hl[order[j - 1] * 8] > hl[o * 8]) { order[j] = order[j - 1]; --j; }
+        order[j] = o;
       }
-      const double n = (double)(g1 - g0);
-      fprintf(stderr, "  CTAs %5zu-%5zu: mean start %7.1f us, mean end %7.1f us, life %6.1f us (max %6.1f) = %7.0f cycles -> %.0f MHz\n",
-              g0, g1 - 1, st0 / n * 1e-3, en / n * 1e-3, s_ns / n * 1e-3, mx_ns * 1e-3, s_cy / n, s_cy / s_ns * 1e3);
+      for (size_t g0 = 0; g0 < n_ctas; g0 += 148) {
+        const size_t g1 = g0 + 148 < n_ctas ? g0 + 148 : n_ctas;
+        double s_ns = 0, s_cy = 0, st0 = 0, en = 0, s_main = 0, s_fin = 0; long long mx_ns = 0; int n_fin = 0;
+        for (size_t q = g0; q < g1; ++q) {
+          const size_t i = order[q];
+          const long long ns = hl[i * 8 + 1] - hl[i * 8], cy = hl[i * 8 + 3] - hl[i * 8 + 2];
+          s_ns += ns; s_cy += cy; st0 += hl[i * 8] - t_min; en += hl[i * 8 + 1] - t_min;
+          if (hl[i * 8 + 5]) s_main += hl[i * 8 + 5] - hl[i * 8];
+          if (hl[i * 8 + 6]) { ++n_fin; s_fin += hl[i * 8 + 7] - hl[i * 8 + 5]; }
+          if (ns > mx_ns) mx_ns = ns;
+        }
+        const double n = (double)(g1 - g0);
+        fprintf(stderr, "  CTAs %5zu-%5zu (by start): mean start %7.1f us, mean end %7.1f us, life %6.1f us (max %6.1f) = %7.0f cycles -> %.0f MHz; to ticket %6.1f us; %d finishers, %6.1f us each\n",
+                g0, g1 - 1, st0 / n * 1e-3, en / n * 1e-3, s_ns / n * 1e-3, mx_ns * 1e-3, s_cy / n, s_cy / s_ns * 1e3,
+                s_main / n * 1e-3, n_fin, n_fin ? s_fin / n_fin * 1e-3 : 0.0);
+      }
     }
   }
   if (p.trace) {

@@ -23,19 +23,56 @@ import torch.distributed as dist
 # data parallel over meshes
 # ------------------------------------------------------------------------------------------------
 def allreduce_gradients(params, group=None, average: bool = False) -> None:
-    """Sum (or average) `.grad` of `params` over the process group with a single flat all-reduce."""
+    """Sum (or average) `.grad` of `params` over the process group: gradients above 1 MiB are reduced in place
+    (no staging copy), the small ones travel together in one flat buffer; the collectives of one call are issued
+    back to back and complete asynchronously on the collective stream (the compute stream waits, not the host)."""
     params = [p for p in params if p.grad is not None]
     if not params or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    flat = torch.cat([p.grad.reshape(-1) for p in params])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    world = dist.get_world_size(group)
+    big = [p for p in params if p.grad.numel() * p.grad.element_size() >= (1 << 20) and p.grad.is_contiguous()]
+    small = [p for p in params if not any(p is q for q in big)]
+    works = [dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group, async_op=True) for p in big]
+    flat = None
+    if small:
+        flat = torch.cat([p.grad.reshape(-1) for p in small])
+        works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for w in works:
+        w.wait()
+    if flat is not None:
+        off = 0
+        for p in small:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
     if average:
-        flat /= dist.get_world_size(group)
-    off = 0
-    for p in params:
-        n = p.grad.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
-        off += n
+        for p in params:
+            p.grad /= world
+
+
+class overlapped_grad_sync:
+    """Context manager: inside it, every geoconv_b200 convolution whose backward takes the AMP-sparse route
+    all-reduces its weight gradients from INSIDE the backward, between the weight-gradient stage and the dSignal GEMM
+    (ops.GradSync), so the collective runs beside that GEMM instead of after the step.  Valid when every rank runs
+    ONE backward per step and layer (the sum of per-rank gradients is what is reduced); with several meshes per rank
+    accumulate locally and call `allreduce_gradients` once instead.  `synced(params)` tells which parameters need no
+    further reduction."""
+
+    def __init__(self, group=None):
+        from . import ops
+        self._ops = ops
+        self.sync = ops.GradSync(group)
+        self._prev = None
+
+    def __enter__(self):
+        self._prev = self._ops.GRAD_SYNC
+        self._ops.GRAD_SYNC = self.sync
+        return self.sync
+
+    def __exit__(self, *exc):
+        self.sync.join()
+        self._ops.GRAD_SYNC = self._prev
+        return False
 
 
 # ------------------------------------------------------------------------------------------------
@@ -73,10 +110,15 @@ def build_shard_plans(bary: torch.Tensor, world: int) -> list[VertexShardPlan]:
     v = bary.shape[0]
     ranges = row_ranges(v, world)
     idx_all = bary[..., 0].to(torch.float32).long()
+    # Zero-weight entries (the (0, 0) fallback of barycentric_coordinates.py:69 and anything else with weight 0)
+    # contribute nothing to a finite signal: they are pointed at the shard's own first row instead of pulling global
+    # row 0 into every rank's halo.  (With a non-finite signal 0 * inf differs from the unpartitioned result.)
+    dead = bary[..., 1] == 0
     owner_bounds = torch.tensor([hi for _, hi in ranges])
     plans = []
     needs = []  # needs[p][q] = sorted global rows p needs from q
     for p, (lo, hi) in enumerate(ranges):
+        idx_all[lo:hi][dead[lo:hi]] = lo
         idx = idx_all[lo:hi]
         uniq = torch.unique(idx)
         remote = uniq[(uniq < lo) | (uniq >= hi)]
@@ -96,6 +138,44 @@ def build_shard_plans(bary: torch.Tensor, world: int) -> list[VertexShardPlan]:
         plans.append(VertexShardPlan(rank=p, world=world, ranges=ranges, bary_local=local, recv_rows=recv,
                                      send_rows=send, n_local=n_local, n_halo=int(halo.numel())))
     return plans
+
+
+def build_local_shard_plan(bary_rows: torch.Tensor, v_total: int, group=None) -> VertexShardPlan:
+    """The plan of THIS rank only, from this rank's own rows of the barycentric tensor (global indices): every rank
+    finds the remote rows it references and the ranks exchange those lists (one all_gather of index lists), so no
+    rank ever holds the whole mesh.  Same result as `build_shard_plans(whole, world)[rank]`."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    ranges = row_ranges(v_total, world)
+    lo, hi = ranges[rank]
+    if bary_rows.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} owns rows [{lo}, {hi}) but was given {bary_rows.shape[0]} barycentric rows")
+    idx = bary_rows[..., 0].to(torch.float32).long()
+    idx[bary_rows[..., 1] == 0] = lo                       # zero-weight entries stay local (see build_shard_plans)
+    uniq = torch.unique(idx)
+    remote = uniq[(uniq < lo) | (uniq >= hi)]
+    owner = torch.bucketize(remote, torch.tensor([h_ for _, h_ in ranges]), right=True)
+    recv = [remote[owner == q] for q in range(world)]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [r_.tolist() for r_ in recv], group=group)
+        send = [torch.tensor(gathered[q][rank], dtype=torch.long) - lo for q in range(world)]
+    else:
+        send = [torch.empty(0, dtype=torch.long)]
+    halo = torch.cat(recv) if world > 1 else torch.empty(0, dtype=torch.long)
+    n_local = hi - lo
+    # global row -> position in (local rows ++ halo rows): local rows by offset, halo rows by search in the sorted list
+    local = bary_rows.clone()
+    is_local = (idx >= lo) & (idx < hi)
+    pos = torch.where(is_local, idx - lo, torch.zeros_like(idx))
+    if halo.numel():
+        order = torch.argsort(halo)
+        where = torch.searchsorted(halo[order], idx.clamp(min=0))
+        where = where.clamp(max=halo.numel() - 1)
+        pos = torch.where(is_local, pos, n_local + order[where])
+    local[..., 0] = pos.to(bary_rows.dtype)
+    return VertexShardPlan(rank=rank, world=world, ranges=ranges, bary_local=local, recv_rows=recv, send_rows=send,
+                           n_local=n_local, n_halo=int(halo.numel()))
 
 
 def _pack(src: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
@@ -139,6 +219,76 @@ class _HaloExchange(torch.autograd.Function):
                 grad_local.index_add_(0, ctx.send_idx[off:off + cnt], back[off:off + cnt])
                 off += cnt
         return grad_local, None, None
+
+
+def interior_rows(plan: VertexShardPlan) -> tuple[int, int]:
+    """[lo, hi): the longest run of consecutive local rows whose template vertices only reference LOCAL signal rows.
+    With a locality-preserving vertex order these are all rows but a thin band at either end of the shard; they can be
+    convolved while the halo rows are still in flight."""
+    idx = plan.bary_local[..., 0].reshape(plan.n_local, -1)
+    local_only = (idx.max(dim=1).values < plan.n_local)
+    if not bool(local_only.any()):
+        return 0, 0
+    # longest run of True
+    z = torch.cat([torch.tensor([False]), local_only, torch.tensor([False])]).to(torch.int8)
+    d = z[1:] - z[:-1]
+    starts = (d == 1).nonzero().flatten()
+    ends = (d == -1).nonzero().flatten()
+    k = int(torch.argmax(ends - starts))
+    return int(starts[k]), int(ends[k])
+
+
+class ShardedForward:
+    """Forward of one geoconv_b200 convolution on this rank's rows of a row-partitioned mesh with the halo exchange
+    OVERLAPPED with the interior rows:
+
+      1. the rows peers asked for are packed and the all-to-all is started asynchronously; it writes the halo rows
+         straight behind the local rows of one preallocated signal buffer (no concatenation);
+      2. meanwhile the layer runs on the interior rows - those whose template vertices reference local rows only -
+         against the local part of the buffer;
+      3. when the collective has finished the layer runs on the remaining boundary rows against the whole buffer.
+
+    `__call__` returns the row blocks (Y_head, Y_interior, Y_tail) in local row order; `assemble` concatenates them
+    (a copy; a consumer that accepts row blocks does not need it).  The layer is called with `row_offset`, so that
+    a block's centre term reads its own vertices.  Forward only: training uses `sharded_layer_forward`."""
+
+    def __init__(self, layer, plan: VertexShardPlan, n_features: int, device, group=None):
+        self.layer, self.plan, self.group = layer, plan, group
+        self.lo, self.hi = interior_rows(plan)
+        bl = plan.bary_local
+        self.bary_int = bl[self.lo:self.hi].contiguous().to(device)
+        self.bary_head = bl[:self.lo].contiguous().to(device)       # boundary rows: they reference halo rows
+        self.bary_tail = bl[self.hi:].contiguous().to(device)
+        self.full = torch.empty((plan.n_local + plan.n_halo, n_features), dtype=torch.float32, device=device)
+        self.send_counts = [int(r.numel()) for r in plan.send_rows]
+        self.recv_counts = [int(r.numel()) for r in plan.recv_rows]
+        self.send_idx = torch.cat(plan.send_rows).to(device) if sum(self.send_counts) else None
+        self.halo_bytes = plan.n_halo * n_features * 4
+
+    def load(self, signal_local: torch.Tensor) -> None:
+        self.full[:self.plan.n_local].copy_(signal_local)
+
+    def __call__(self, overlap: bool = True):
+        p = self.plan
+        local = self.full[:p.n_local]
+        work = None
+        if p.world > 1 and (p.n_halo or sum(self.send_counts)):
+            send = _pack(local, self.send_idx) if self.send_idx is not None else local.new_empty((0, local.shape[1]))
+            work = dist.all_to_all_single(self.full[p.n_local:], send, output_split_sizes=self.recv_counts,
+                                          input_split_sizes=self.send_counts, group=self.group, async_op=True)
+            if not overlap:
+                work.wait()
+                work = None
+        # (row_offset: the block's rows are vertices lo .. hi of the buffer - its centre term reads those rows)
+        y_int = self.layer([local, self.bary_int], row_offset=self.lo) if self.hi > self.lo else None
+        if work is not None:
+            work.wait()                      # the compute stream waits for the collective, the host does not
+        y_head = self.layer([self.full, self.bary_head], row_offset=0) if self.lo else None
+        y_tail = self.layer([self.full, self.bary_tail], row_offset=self.hi) if self.hi < p.n_local else None
+        return y_head, y_int, y_tail
+
+    def assemble(self, y_head, y_int, y_tail):
+        return torch.cat([y_ for y_ in (y_head, y_int, y_tail) if y_ is not None])
 
 
 def halo_exchange(signal_local: torch.Tensor, plan: VertexShardPlan, group=None) -> torch.Tensor:

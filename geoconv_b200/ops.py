@@ -371,8 +371,8 @@ class FoldPrior:
 @torch.library.custom_op(f"{_LIB}::conv_fwd", mutates_args=(), device_types="cuda")
 def conv_fwd_op(signal: torch.Tensor, w_eff: torch.Tensor | None, w_self: torch.Tensor, bias: torch.Tensor,
                 idx: torch.Tensor, w: torch.Tensor, w_anchor: torch.Tensor | None, records: torch.Tensor | None,
-                rot: list[int], act_id: int, prec_fwd: int,
-                prec_bwd: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+                rot: list[int], act_id: int, prec_fwd: int, prec_bwd: int,
+                row0: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """(signal, Weff|None, Wself, bias) -> (Y [V,n_rot,T], Z [V,T], argmax [V], stats int32 [8]): ConvIntrinsic.forward
     and the AngularMaxPooling of its result in one pass (include/geoconv_b200.h: gcb_conv_fwd).  `w_anchor`: the
     neighbour weights of an all-zero-prior layer (they take no part, but receive an all-zeros gradient);
@@ -399,13 +399,13 @@ def conv_fwd_op(signal: torch.Tensor, w_eff: torch.Tensor | None, w_self: torch.
         N.check(lib.gcb_conv_fwd(x.data_ptr(), idx.data_ptr(), w.data_ptr(), _ptr(w_eff_c), w_self_c.data_ptr(),
                                  bias_c.data_ptr(), N.rot_array(rot), n_rot, v_out, v_src, r, a, f, t, act_id,
                                  prec_fwd, y.data_ptr(), z.data_ptr(), arg.data_ptr(), None,
-                                 _ptr(records) if tensor_path else None, _ptr(tables), stats.data_ptr(),
+                                 _ptr(records) if tensor_path else None, _ptr(tables), stats.data_ptr(), row0,
                                  ws.data_ptr(), ws_bytes, _stream(x)), "gcb_conv_fwd")
     return y, z, arg, stats
 
 
 @conv_fwd_op.register_fake
-def _(signal, w_eff, w_self, bias, idx, w, w_anchor, records, rot, act_id, prec_fwd, prec_bwd):
+def _(signal, w_eff, w_self, bias, idx, w, w_anchor, records, rot, act_id, prec_fwd, prec_bwd, row0):
     v_out, t = idx.shape[0], w_self.shape[0]
     return (signal.new_empty((v_out, len(rot), t), dtype=torch.float32),
             signal.new_empty((v_out, t), dtype=torch.float32), signal.new_empty((v_out,), dtype=torch.int32),
@@ -417,11 +417,14 @@ def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: tor
                 w_eff: torch.Tensor | None, w_self: torch.Tensor, y: torch.Tensor, z: torch.Tensor,
                 arg: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, row_ptr: torch.Tensor | None,
                 entries: torch.Tensor | None, csr_stats: torch.Tensor | None, fwd_stats: torch.Tensor | None,
-                rot: list[int], act_id: int, precision: int,
-                need_dx: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+                rot: list[int], act_id: int, precision: int, need_dx: bool, stages: int,
+                ws_in: torch.Tensor | None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """Backward of conv_fwd: a gradient arriving through Z takes the AMP-sparse route (one rotation per
     vertex), a gradient arriving through Y is back-propagated one rotation at a time.
-    Returns (dSignal [V_src,F] or an empty tensor, dWeff [T,R,A,F], dWself [T,F], dbias [T])."""
+    Returns (dSignal [V_src,F] or an empty tensor, dWeff [T,R,A,F], dWself [T,F], dbias [T], workspace).
+    stages (AMP-sparse route only): 3 = everything; 1 = up to the weight gradients, the returned workspace then goes
+    into a stages = 2 call (`ws_in`) that produces dSignal - a data-parallel caller starts the all-reduce of the
+    weight gradients in between (see `GradSync`)."""
     lib = N.load()
     v_src, f = x.shape
     v_out, r, a = idx.shape[:3]
@@ -429,12 +432,13 @@ def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: tor
     dev = x.device
     n_rot = len(rot)
     has_nb = w_eff is not None
-    d_x = torch.empty_like(x) if need_dx else None
-    d_w_eff = torch.empty((t, r, a, f), dtype=torch.float32, device=dev)
-    d_w_self = torch.empty((t, f), dtype=torch.float32, device=dev)
-    d_bias = torch.empty((t,), dtype=torch.float32, device=dev)
+    d_x = torch.empty_like(x) if need_dx and stages != 1 else None
+    w_stage = stages != 2
+    d_w_eff = torch.empty((t, r, a, f) if w_stage else (0,), dtype=torch.float32, device=dev)
+    d_w_self = torch.empty((t, f) if w_stage else (0,), dtype=torch.float32, device=dev)
+    d_bias = torch.empty((t,) if w_stage else (0,), dtype=torch.float32, device=dev)
     ws_bytes = lib.gcb_conv_amp_bwd_workspace_bytes(v_out, v_src, r, a, f, t, precision)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ws = ws_in if ws_in is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     st = _stream(x)
     rot_c = N.rot_array(rot)
     calls = 0
@@ -457,9 +461,10 @@ def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: tor
             N.check(lib.gcb_conv_amp_bwd(gz.data_ptr(), z.data_ptr(), arg.data_ptr(), rot_c, n_rot, act_id, x.data_ptr(),
                                          idx.data_ptr(), w.data_ptr(), _ptr(w_eff) if has_nb else None,
                                          w_self.data_ptr(), _ptr(row_ptr), _ptr(entries), N.CSR_RING_GROUPED,
-                                         _ptr(csr_stats), _ptr(fwd_stats), v_out, v_src, r, a, f, t, precision, _ptr(d_x),
-                                         d_w_eff.data_ptr(), d_w_self.data_ptr(), d_bias.data_ptr(), ws.data_ptr(),
-                                         ws_bytes, st), "gcb_conv_amp_bwd")
+                                         _ptr(csr_stats), _ptr(fwd_stats), v_out, v_src, r, a, f, t, precision, stages,
+                                         _ptr(d_x), d_w_eff.data_ptr() if w_stage else 256,
+                                         d_w_self.data_ptr() if w_stage else 256, d_bias.data_ptr() if w_stage else 256,
+                                         ws.data_ptr(), ws_bytes, st), "gcb_conv_amp_bwd")
             calls += 1
         if grad_y is not None:
             gy = grad_y.to(torch.float32)
@@ -473,16 +478,52 @@ def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: tor
                 calls += 1
     if d_x is None:
         d_x = x.new_empty((0,))
-    return d_x, d_w_eff, d_w_self, d_bias
+    return d_x, d_w_eff, d_w_self, d_bias, (ws if stages == 1 else x.new_empty((0,), dtype=torch.uint8))
 
 
 @conv_bwd_op.register_fake
 def _(grad_y, grad_z, x, w_eff, w_self, y, z, arg, idx, w, row_ptr, entries, csr_stats, fwd_stats, rot, act_id,
-      precision, need_dx):
+      precision, need_dx, stages, ws_in):
     v_out, r, a = idx.shape[:3]
     t, f = w_self.shape[0], x.shape[1]
     return (torch.empty_like(x) if need_dx else x.new_empty((0,)), x.new_empty((t, r, a, f)), x.new_empty((t, f)),
-            x.new_empty((t,)))
+            x.new_empty((t,)), x.new_empty((0,), dtype=torch.uint8))
+
+
+def _is_fake(t: torch.Tensor) -> bool:
+    from torch._subclasses.fake_tensor import is_fake
+    return is_fake(t)
+
+
+class GradSync:
+    """Data-parallel weight-gradient reduction started INSIDE the layer's backward (geoconv_b200/distributed.py installs
+    one): the backward runs in two stages; after the first (weight gradients final) `reduce_early` launches their
+    all-reduce asynchronously - the collective's stream waits for what has been enqueued so far, i.e. for stage one -
+    and the dSignal GEMM of stage two runs beside it; `join` makes the compute stream wait for the collective."""
+
+    def __init__(self, group=None, average: bool = False):
+        self.group = group
+        self.average = average
+        self.active = True
+        self._works = []
+        self.early_reductions = 0
+
+    def reduce_early(self, tensors):
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        for t_ in tensors:
+            if t_.numel():
+                self._works.append(dist.all_reduce(t_, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.early_reductions += 1
+
+    def join(self):
+        for w_ in self._works:
+            w_.wait()          # (stream-level wait: the host does not block)
+        self._works = []
+
+
+GRAD_SYNC: GradSync | None = None
 
 
 # idx tensor -> BaryPack that owns it (eager mode: the CSR inversion is built once per barycentric tensor)
@@ -499,7 +540,8 @@ def _csr_for(idx: torch.Tensor, w: torch.Tensor, v_src: int):
 
 
 def _conv_setup(ctx, inputs, output):
-    signal, w_eff, w_self, bias, idx, w, w_anchor, _records, rot, act_id, prec_fwd, prec_bwd = inputs
+    signal, w_eff, w_self, bias, idx, w, w_anchor, _records, rot, act_id, prec_fwd, prec_bwd, row0 = inputs
+    ctx.row0 = row0
     y, z, arg, stats = output
     # the forward's operand maxima serve the backward when both run the fp16-split kernels on the same operands
     ctx.use_fwd_stats = prec_fwd == N.PREC_F16X3 and prec_bwd == N.PREC_F16X3 and w_eff is not None
@@ -520,19 +562,29 @@ def _conv_setup(ctx, inputs, output):
 def _conv_backward(ctx, grad_y, grad_z, _grad_arg, _grad_stats):
     x, w_eff, w_self, y, z, arg, idx, w, stats = ctx.saved_tensors
     if grad_y is None and grad_z is None:
-        return (None,) * 12
+        return (None,) * 13
+    if ctx.row0:
+        raise NotImplementedError("geoconv_b200: a convolution over a row block (row_offset > 0) is forward-only")
     INDEX_CHECKS.poll()
     has_nb = ctx.has_neighbor
     need_dx = bool(ctx.needs_input_grad[0])
     # the CSR inversion also feeds the weight gradients (dW = G^T X on tensor cores), not only dSignal
     row_ptr, entries, csr_stats = _csr_for(idx, w, x.shape[0]) if has_nb else (None, None, None)
-    d_x, d_w_eff, d_w_self, d_bias = conv_bwd_op(grad_y, grad_z, x.contiguous(), w_eff if has_nb else None, w_self, y, z,
-                                                 arg, idx, w, row_ptr, entries, csr_stats,
-                                                 stats if ctx.use_fwd_stats else None, ctx.rot, ctx.act_id,
-                                                 ctx.precision, need_dx)
+    args = (grad_y, grad_z, x.contiguous(), w_eff if has_nb else None, w_self, y, z, arg, idx, w, row_ptr, entries,
+            csr_stats, stats if ctx.use_fwd_stats else None, ctx.rot, ctx.act_id, ctx.precision, need_dx)
+    sync = GRAD_SYNC
+    if (sync is not None and sync.active and grad_y is None and need_dx and has_nb and not _is_fake(x) and
+            N.load().gcb_conv_amp_bwd_can_split(idx.shape[1], idx.shape[2], x.shape[1], w_self.shape[0], ctx.precision, 1)):
+        # data parallel: weight gradients first, their all-reduce (collective stream) beside the dSignal GEMM
+        _none, d_w_eff, d_w_self, d_bias, ws = conv_bwd_op(*args, 1, None)
+        sync.reduce_early([d_w_eff, d_w_self, d_bias])
+        d_x = conv_bwd_op(*args, 2, ws)[0]
+        sync.join()
+    else:
+        d_x, d_w_eff, d_w_self, d_bias, _ws = conv_bwd_op(*args, 3, None)
     g_anchor = torch.zeros(ctx.anchor_shape, dtype=torch.float32, device=x.device) if ctx.has_anchor else None
     return (d_x if need_dx else None, d_w_eff if has_nb else None, d_w_self.reshape(ctx.w_self_shape),
-            d_bias.reshape(ctx.bias_shape), None, None, g_anchor, None, None, None, None, None)
+            d_bias.reshape(ctx.bias_shape), None, None, g_anchor, None, None, None, None, None, None)
 
 
 conv_fwd_op.register_autograd(_conv_backward, setup_context=_conv_setup)
@@ -543,14 +595,14 @@ class ConvIntrinsicFn:
     -> (Y, Z, argmax).  `precision` is one C-ABI code for both directions or a (forward, backward) pair."""
 
     @staticmethod
-    def apply(signal, w_eff, w_self, bias, pack: BaryPack, rot_offsets, act_id, precision, w_anchor=None):
+    def apply(signal, w_eff, w_self, bias, pack: BaryPack, rot_offsets, act_id, precision, w_anchor=None, row0=0):
         _need_cuda(signal, "signal")
         prec_fwd, prec_bwd = precision if isinstance(precision, tuple) else (precision, precision)
         records = None
         if prec_fwd != N.PREC_FP32 and w_eff is not None and not torch.compiler.is_compiling() and pack.v_out > 0:
             records = pack.records()
         y, z, arg, _stats = conv_fwd_op(signal, w_eff, w_self, bias, pack.idx, pack.w, w_anchor, records,
-                                        [int(o) for o in rot_offsets], act_id, prec_fwd, prec_bwd)
+                                        [int(o) for o in rot_offsets], act_id, prec_fwd, prec_bwd, int(row0))
         return y, z, arg
 
 

@@ -163,14 +163,17 @@ class ConvIntrinsic(ABC, nn.Module):
                 "shipped by geoconv: functions of the radial and angular distance) are supported.")
         return ops.FoldPrior.apply(self._template_neighbor_weights, self._kernel)
 
-    def forward(self, inputs, orientations=None):
+    def forward(self, inputs, orientations=None, row_offset=0):
         """inputs = [signal (V, F), barycentric (V, R, A, 3, 2)] -> (V, n_rotations, templates).
+
+        ``row_offset`` (extension, forward only): the barycentric tensor holds the rows of vertices
+        ``row_offset .. row_offset + len(barycentric)`` of the signal (its indices still address the whole signal).
 
         The result also carries the fused AngularMaxPooling outputs so that a following
         ``AngularMaxPooling`` module returns them without re-reading the tensor and back-propagates
         through one rotation per vertex only.
         """
-        y, z, arg = self._run(inputs, orientations)
+        y, z, arg = self._run(inputs, orientations, row_offset)
         if torch.compiler.is_compiling():
             # Dynamo tracks attributes only on tensors made by a traced torch call (an operator's tuple output is
             # not one), and cannot read the version counter: inside a trace the tuple rides on an alias of Y and
@@ -186,7 +189,7 @@ class ConvIntrinsic(ABC, nn.Module):
         _, z, arg = self._run(inputs, orientations)
         return z, arg
 
-    def _run(self, inputs, orientations):
+    def _run(self, inputs, orientations, row_offset=0):
         # Traceable by torch.compile (the reference demo compiles its model, training_demo.py:126-127): every
         # device-side step is a `geoconv_b200::*` torch.library operator with a fake kernel, the rest is shape logic.
         mesh_signal, bary_coordinates = inputs
@@ -198,7 +201,7 @@ class ConvIntrinsic(ABC, nn.Module):
         if tuple(bary_coordinates.shape[1:3]) != tuple(self._template_size):
             raise ValueError(f"barycentric coordinates must have shape (V, {self._template_size[0]}, "
                              f"{self._template_size[1]}, 3, 2), got {tuple(bary_coordinates.shape)}")
-        if bary_coordinates.shape[0] > mesh_signal.shape[0]:
+        if row_offset < 0 or row_offset + bary_coordinates.shape[0] > mesh_signal.shape[0]:
             raise ValueError("more barycentric rows than signal rows")
         signal = mesh_signal.to(torch.float32)
         if torch.compiler.is_compiling():
@@ -216,7 +219,7 @@ class ConvIntrinsic(ABC, nn.Module):
                                                 self.amt_templates, len(offsets)))
         anchor = self._template_neighbor_weights if w_eff is None else None
         return ops.ConvIntrinsicFn.apply(signal, w_eff, self._template_self_weights, self._bias, pack,
-                                         tuple(offsets), self._act_id, prec, anchor)
+                                         tuple(offsets), self._act_id, prec, anchor, row_offset)
 
     @abstractmethod
     def define_kernel_values(self, template_matrix):

@@ -68,3 +68,20 @@ def make_bary_local(v, r, a, window=512, seed=1, fallback_frac=0.02, dtype=torch
         idx[dead] = 0
         w[dead] = 0.0
     return torch.stack([idx.to(dtype), w.to(dtype)], dim=-1)
+
+
+def make_bary_local_rows(v_total, lo, hi, r, a, window=512, seed=1, fallback_frac=0.02, dtype=torch.float32):
+    """Rows [lo, hi) of a locality-preserving barycentric tensor of a `v_total`-vertex mesh (global indices within
+    `window` rows of the vertex, wrapping around), generated without the other rows: what one rank of a
+    row-partitioned mesh holds.  Seeded per row block, so different partitions give different (equally valid) meshes."""
+    g = torch.Generator().manual_seed(seed * 1_000_003 + lo)
+    n = hi - lo
+    own = torch.arange(lo, hi).view(n, 1, 1, 1)
+    idx = (own + torch.randint(-window, window + 1, (n, r, a, 3), generator=g)) % v_total
+    w = torch.rand((n, r, a, 3), generator=g)
+    w = w / w.sum(dim=-1, keepdim=True)
+    if fallback_frac > 0:
+        dead = torch.rand((n, r, a), generator=g) < fallback_frac
+        idx[dead] = 0
+        w[dead] = 0.0
+    return torch.stack([idx.to(dtype), w.to(dtype)], dim=-1)

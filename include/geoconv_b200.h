@@ -132,14 +132,17 @@ int gcb_fold_prior(const float* in, const float* prior, float* out, int32_t T, i
  * records / tables (nullable): preparation that depends only on the barycentric tensor / on the shape and rotation
  * list (see below); when NULL the tensor-core path redoes it in the workspace on every call.
  * stats_out (nullable, 8 uint32): operand maxima the fp16-split forward computes anyway ([0] max|X|, [2]
- * max|[Weff|Wself]| as fp32 bits; all zero from the other paths) - gcb_conv_amp_bwd of the same step reuses them. */
+ * max|[Weff|Wself]| as fp32 bits; all zero from the other paths) - gcb_conv_amp_bwd of the same step reuses them.
+ * row0: output row k is vertex row0 + k, i.e. its centre term reads x[row0 + k] (0 for a whole mesh or a shard whose
+ * rows lead the signal; > 0 lets a caller convolve a block of rows in the middle of the signal, e.g. the boundary
+ * rows of a vertex-row shard after its interior rows - geoconv_b200/distributed.py).  Forward only.               */
 size_t gcb_conv_fwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
                                     int32_t T, int32_t n_rot, int precision);
 int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
                  const float* w_self, const float* bias, const int32_t* rot_off_host,
                  int32_t n_rot, int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
                  int32_t T, int act, int precision, float* y, float* z, int32_t* argmax,
-                 float* interp_out, const void* records, const void* tables, uint32_t* stats_out,
+                 float* interp_out, const void* records, const void* tables, uint32_t* stats_out, int32_t row0,
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- forward preparation a caller may cache ----------------------------------------------------
@@ -226,8 +229,13 @@ int gcb_conv_amp_bwd(const float* grad_z, const float* z, const int32_t* argmax,
                      int32_t n_rot, int act, const float* x, const int32_t* idx, const float* w, const float* w_eff,
                      const float* w_self, const int32_t* csr_row_ptr, const int32_t* csr_entries, int csr_flags,
                      const uint32_t* csr_stats, const uint32_t* fwd_stats, int32_t v_out, int32_t v_src, int32_t R,
-                     int32_t A, int32_t F, int32_t T, int precision, float* d_x, float* d_w_eff, float* d_w_self,
-                     float* d_bias, void* workspace, size_t workspace_bytes, void* stream);
+                     int32_t A, int32_t F, int32_t T, int precision, int stages, float* d_x, float* d_w_eff,
+                     float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes, void* stream);
+/* stages: 3 = the whole backward.  1 = everything up to the weight gradients (d_w_eff, d_w_self, d_bias), 2 = the
+ * signal gradient from what a stages = 1 call with the same arguments left in the SAME workspace.  Data-parallel
+ * callers start the all-reduce of the weight gradients between the two calls, so that it runs beside the dSignal
+ * GEMM (geoconv_b200/distributed.py).  Only where gcb_conv_amp_bwd_can_split() returns 1. */
+int gcb_conv_amp_bwd_can_split(int32_t R, int32_t A, int32_t F, int32_t T, int precision, int has_neighbor);
 
 /* ---- vertex-row sharding helper (halo exchange) ---------------------------
  * out[i,:] = src[rows[i],:]  (packs the signal rows a peer asked for into a send buffer). */

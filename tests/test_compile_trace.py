@@ -79,19 +79,19 @@ def test_autograd_formulas_on_fake_tensors():
         w = torch.empty(V, R, A, 3, device=dev)
         rot = list(range(n_rot))
         y, z, arg, stats = ops.conv_fwd_op(x, w_eff, w_self, bias, idx, w, None, None, rot, 0, _native.PREC_F16X3,
-                                           _native.PREC_F16X3)
+                                           _native.PREC_F16X3, 0)
         assert tuple(y.shape) == (V, n_rot, T) and tuple(z.shape) == (V, T) and arg.dtype == torch.int32
-        ctx = types.SimpleNamespace(needs_input_grad=[True] * 12, set_materialize_grads=lambda _f: None, saved=None)
+        ctx = types.SimpleNamespace(needs_input_grad=[True] * 13, set_materialize_grads=lambda _f: None, saved=None)
         ctx.save_for_backward = lambda *ts: setattr(ctx, "saved_tensors", ts)
-        ops._conv_setup(ctx, (x, w_eff, w_self, bias, idx, w, None, None, rot, 0, 3, 3), (y, z, arg, stats))
+        ops._conv_setup(ctx, (x, w_eff, w_self, bias, idx, w, None, None, rot, 0, 3, 3, 0), (y, z, arg, stats))
         grads = ops._conv_backward(ctx, None, torch.empty_like(z), None, None)
-        assert len(grads) == 12
+        assert len(grads) == 13
         assert tuple(grads[0].shape) == (V, F) and tuple(grads[1].shape) == (T, R, A, F)
         assert tuple(grads[2].shape) == (T, 1, F) and tuple(grads[3].shape) == (1, T)
         assert all(g is None for g in grads[4:])
         # dense gradient through Y, no signal gradient, all-zero prior (anchor receives zeros)
-        ctx.needs_input_grad = [False] + [True] * 11
-        ops._conv_setup(ctx, (x, None, w_self, bias, idx, w, w_eff, None, rot, 0, 3, 3), (y, z, arg, stats))
+        ctx.needs_input_grad = [False] + [True] * 12
+        ops._conv_setup(ctx, (x, None, w_self, bias, idx, w, w_eff, None, rot, 0, 3, 3, 0), (y, z, arg, stats))
         grads = ops._conv_backward(ctx, torch.empty_like(y), None, None, None)
         assert grads[0] is None and grads[1] is None and tuple(grads[6].shape) == (T, R, A, F)
         # pooling and prior folding

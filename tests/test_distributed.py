@@ -47,8 +47,11 @@ def test_sharded_oracle_equals_unsharded(world):
         full = torch.cat([signal[lo:hi], signal[halo_rows]])
         idx_local = p.bary_local[..., 0].long()
         assert idx_local.min() >= 0 and idx_local.max() < full.shape[0]
-        # every remapped index points at the same signal row as before
-        assert torch.equal(full[idx_local.reshape(-1)], signal[bary[lo:hi, ..., 0].long().reshape(-1)])
+        # every remapped index of a live entry points at the same signal row as before (zero-weight entries are
+        # kept local: they contribute nothing and must not drag global row 0 into every halo)
+        live = (bary[lo:hi, ..., 1] != 0).reshape(-1)
+        assert torch.equal(full[idx_local.reshape(-1)][live], signal[bary[lo:hi, ..., 0].long().reshape(-1)][live])
+        assert bool((idx_local.reshape(-1)[~live] == 0).all())
         # interpolation + contraction see identical operands => identical output rows
         interp = O.signal_retrieval(full, p.bary_local)
         assert torch.equal(interp, O.signal_retrieval(signal, bary)[lo:hi])
@@ -56,6 +59,20 @@ def test_sharded_oracle_equals_unsharded(world):
         for q in range(world):
             assert torch.equal(plans[q].send_rows[p.rank] + p.ranges[q][0], p.recv_rows[q])
     assert y_ref.shape[0] == v
+
+
+def test_interior_rows_of_a_local_mesh():
+    from geoconv_b200 import synthetic as S
+    bary = S.make_bary_local(1000, 2, 4, window=40, seed=1)
+    for p_ in D.build_shard_plans(bary, 4):
+        lo, hi = D.interior_rows(p_)
+        idx = p_.bary_local[..., 0].reshape(p_.n_local, -1)
+        assert hi - lo >= p_.n_local - 2 * 40 - 2
+        assert int(idx[lo:hi].max()) < p_.n_local                         # interior rows reference local rows only
+        if lo > 0:
+            assert int(idx[lo - 1].max()) >= p_.n_local                    # the run cannot be extended
+    one = D.build_shard_plans(bary, 1)[0]
+    assert D.interior_rows(one) == (0, 1000)
 
 
 def _worker(rank, world, port, v, f):
@@ -93,6 +110,47 @@ def _worker(rank, world, port, v, f):
         tot = sum(range(1, world + 1))
         assert torch.equal(p1.grad, torch.full((3, 4), float(tot)))
         assert torch.equal(p2.grad, torch.arange(5.0) * tot)
+        # a gradient above 1 MiB is reduced in place, beside the flat buffer of the small ones
+        p3 = torch.nn.Parameter(torch.zeros(600, 512))
+        p3.grad = torch.full((600, 512), float(rank + 1))
+        p2.grad = torch.arange(5.0) * (rank + 1)
+        D.allreduce_gradients([p3, p2], average=True)
+        assert torch.equal(p3.grad, torch.full((600, 512), tot / world))
+        assert torch.allclose(p2.grad, torch.arange(5.0) * tot / world)
+        # the in-backward reduction object (ops.GradSync): asynchronous all-reduce, joined later
+        from geoconv_b200 import ops
+        with D.overlapped_grad_sync() as sync:
+            assert ops.GRAD_SYNC is sync
+            g1, g2 = torch.full((7,), float(rank + 1)), torch.full((2, 3), 2.0 * (rank + 1))
+            sync.reduce_early([g1, g2, torch.empty(0)])
+            sync.join()
+            assert torch.equal(g1, torch.full((7,), float(tot))) and torch.equal(g2, torch.full((2, 3), 2.0 * tot))
+        assert ops.GRAD_SYNC is None
+        # forward of a row-sharded mesh with the halo exchange overlapped with the interior rows
+        vb, fb, rb, ab, tb = 400, 6, 2, 4, 5
+        from geoconv_b200 import synthetic as S
+        sig_b = O.make_signal(vb, fb, kind="randn")
+        bary_b = S.make_bary_local(vb, rb, ab, window=30, seed=3)
+        wn, ws, b = O.make_weights(tb, rb, ab, fb, seed=1)
+        y_ref = O.conv_forward(sig_b, bary_b, wn, ws, b, None, "relu", 1)
+        plan_b = D.build_shard_plans(bary_b, world)[rank]
+        lo_b, hi_b = plan_b.ranges[rank]
+        def layer(inp, row_offset=0):      # the oracle on a row block: the block's own rows lead the centre term
+            x_, b_ = inp
+            return O.conv_forward(torch.cat([x_[row_offset:row_offset + b_.shape[0]], x_]),
+                                  torch.stack([b_[..., 0] + b_.shape[0], b_[..., 1]], dim=-1), wn, ws, b, None, "relu", 1)
+        # the plan built from this rank's rows alone (ranks exchange their needs) equals the whole-mesh plan
+        mine = D.build_local_shard_plan(bary_b[lo_b:hi_b], vb)
+        assert mine.n_halo == plan_b.n_halo and torch.equal(mine.bary_local, plan_b.bary_local)
+        assert all(torch.equal(x_, y_) for x_, y_ in zip(mine.recv_rows, plan_b.recv_rows))
+        assert all(torch.equal(x_, y_) for x_, y_ in zip(mine.send_rows, plan_b.send_rows))
+        sf = D.ShardedForward(layer, plan_b, fb, torch.device("cpu"))
+        assert 0 < sf.hi - sf.lo < plan_b.n_local
+        assert sf.bary_int.shape[0] + sf.bary_head.shape[0] + sf.bary_tail.shape[0] == plan_b.n_local
+        assert int(sf.bary_int[..., 0].max()) < plan_b.n_local
+        sf.load(sig_b[lo_b:hi_b])
+        for overlap in (True, False):
+            assert torch.equal(sf.assemble(*sf(overlap=overlap)), y_ref[lo_b:hi_b])
     finally:
         dist.destroy_process_group()
 

@@ -346,3 +346,33 @@ def test_faust_shape_randn_signal_stays_inside_fp32_tolerance():
     with torch.no_grad():
         y = layer([signal.to("cuda:0"), bary.to("cuda:0")])
     assert nerr(y, ref64) < TOL_FP32
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["ffma", "fp32", "tf32"])
+def test_row_block_with_row_offset(precision):
+    """`row_offset` (extension): a block of rows from the middle of the mesh, indices addressing the whole signal,
+    reproduces those rows of the whole-mesh result - centre term included - and of the oracle."""
+    v, f, r, a, t = 700, 64, 3, 8, 32
+    wn, ws, b = O.make_weights(t, r, a, f, seed=4)
+    signal = O.make_signal(v, f, seed=4, kind="randn")
+    bary = O.make_bary(v, r, a, seed=4, fallback_frac=0.05)
+    prior = torch.from_numpy(O.geodesic_prior(O.template_matrix(r, a, 0.03))).float()
+    y_ref = O.conv_forward(signal, bary, wn, ws, b, prior, "relu", 1)
+    layer = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.03,
+                         precision=precision)
+    layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
+    layer = layer.to(DEV)
+    tol = TOL_TF32 if precision == "tf32" else TOL_FP32
+    xd, bd = signal.to(DEV), bary.to(DEV)
+    with torch.no_grad():
+        for lo, hi in ((0, 130), (130, 517), (517, 700)):
+            y = layer([xd, bd[lo:hi].contiguous()], row_offset=lo)
+            assert nerr(y, y_ref[lo:hi]) < tol
+            z = AngularMaxPooling()(y)
+            assert torch.equal(z, y[torch.arange(hi - lo, device=DEV), y._gcb_pooled[1].long()])
+    with pytest.raises(ValueError):
+        layer([xd, bd[600:].contiguous()], row_offset=650)
+    y = layer([xd.clone().requires_grad_(True), bd[100:200].contiguous()], row_offset=100)
+    with pytest.raises(NotImplementedError):
+        AngularMaxPooling()(y).sum().backward()

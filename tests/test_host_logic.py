@@ -79,7 +79,7 @@ def test_fp16_split_shape_check_in_the_c_abi():
     rot = (C.c_int32 * n_rot)(0, 2, 4)
     fake = C.c_void_p(256)   # never dereferenced: the shape check comes first
     rc = lib.gcb_conv_fwd(fake, fake, fake, fake, fake, fake, rot, n_rot, v, v, r, a, f, t, 0, _native.PREC_F16X3,
-                          fake, None, None, None, None, None, None, fake, C.c_size_t(max(need, 1) + (1 << 30)), None)
+                          fake, None, None, None, None, None, None, 0, fake, C.c_size_t(max(need, 1) + (1 << 30)), None)
     assert rc == 3, lib.gcb_last_error()
     assert b"fp16 split" in lib.gcb_last_error()
     # FAUST shape: the fp16 mode needs less workspace than 3xTF32 with its 12 K splits, more than nothing
