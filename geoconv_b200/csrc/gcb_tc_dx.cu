@@ -172,59 +172,72 @@ __global__ void k_bw_build_g(const float* __restrict__ h, const float* __restric
 // (187 us: three indirect branches per entry) and the same with 8 entries' loads in flight (178 us).
 constexpr int G2_WARPS = 8;
 
-template <bool H, int TPL>
+// (a, b, c, d) * s = hi + lo as two packed fp16 quadruples
+__device__ __forceinline__ void g2_split4(const float4 v, float s, uint2& hi, uint2& lo) {
+  const float a = v.x * s, b = v.y * s, c = v.z * s, d = v.w * s;
+  const __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(c, d);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(a - f0.x, b - f0.y), l1 = __floats2half2_rn(c - f1.x, d - f1.y);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+
+// Lane l owns the four templates t_base + 4 l .. + 3 of a 128-template pass: one 16-byte load of an h row, four
+// FMAs and no per-template address arithmetic per entry (the variant with one template per lane and load was
+// instruction-issue bound at 94 us: ~25 instructions per entry and ~56 per (ring, y') group).
+template <bool H>
 __global__ void __launch_bounds__(G2_WARPS * 32)
 k_bw_build_g2(const float* __restrict__ h, const float* __restrict__ w, const int32_t* __restrict__ rot_sel,
               const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ entries, int v_out, int v_src, int v_pad,
               int R, int A, int T, int kg, int kg_ld, const float* __restrict__ scales, float* __restrict__ g_hi,
               float* __restrict__ g_lo) {
-  extern __shared__ float s_carry_all[];               // [G2_WARPS][A][32 * TPL]: running sums of a straddling ring
+  extern __shared__ float4 s_carry_all[];              // [G2_WARPS][A][32]: running sums of a straddling ring
   __shared__ int2 s_meta[G2_WARPS][32];                // {h row offset, weight bits}
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int v = blockIdx.x * G2_WARPS + warp;
   if (v >= v_pad) return;
   const int RA = R * A;
-  float* s_carry = s_carry_all + (size_t)warp * A * 32 * TPL;
+  float4* s_carry = s_carry_all + (size_t)warp * A * 32;
   float* out_hi = g_hi + (size_t)v * kg;
   float* out_lo = g_lo ? g_lo + (size_t)v * kg : nullptr;
   __half* hh = reinterpret_cast<__half*>(g_hi) + (size_t)v * kg_ld;
   __half* hl = reinterpret_cast<__half*>(g_lo) + (size_t)v * kg_ld;
   const float sg = H ? __ldg(scales) : 1.f;
-  auto put = [&](int col, float val) {
+  auto put4 = [&](int col, const float4 val) {          // col % 4 == 0
     if (H) {
-      split_half(val, sg, hh[col], hl[col]);
+      uint2 hi, lo;
+      g2_split4(val, sg, hi, lo);
+      *reinterpret_cast<uint2*>(hh + col) = hi;
+      *reinterpret_cast<uint2*>(hl + col) = lo;
     } else {
-      const float hi = ptx::to_tf32(val);
-      out_hi[col] = hi;
-      if (out_lo) out_lo[col] = val - hi;
+      float4 hi;
+      hi.x = ptx::to_tf32(val.x); hi.y = ptx::to_tf32(val.y); hi.z = ptx::to_tf32(val.z); hi.w = ptx::to_tf32(val.w);
+      *reinterpret_cast<float4*>(out_hi + col) = hi;
+      if (out_lo)
+        *reinterpret_cast<float4*>(out_lo + col) = make_float4(val.x - hi.x, val.y - hi.y, val.z - hi.z, val.w - hi.w);
     }
   };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (H)
     for (int i = kg + lane; i < kg_ld; i += 32) { hh[i] = __float2half_rn(0.f); hl[i] = __float2half_rn(0.f); }
   if (v >= v_src) {                                      // padding rows of the GEMM's A operand
-    for (int i = lane; i < kg; i += 32) put(i, 0.f);
+    for (int i = 4 * lane; i < kg; i += 128) put4(i, zero4);
     return;
   }
   const int beg = row_ptr[v], end = row_ptr[v + 1];
-  for (int t_base = 0; t_base < T; t_base += 32 * TPL) {
+  for (int t_base = 0; t_base < T; t_base += 128) {
+    const int t = t_base + 4 * lane;
+    const bool t_on = t < T;
     int next_x = 0;           // rings below it are written
     bool open = false;        // ring `next_x` has running sums parked in s_carry (it may continue in the next chunk)
     auto zero_rings = [&](int x0, int x1) {
-      for (int x = x0; x < x1; ++x)
-        for (int y = 0; y < A; ++y)
-#pragma unroll
-          for (int j = 0; j < TPL; ++j) {
-            const int t = t_base + 32 * j + lane;
-            if (t < T) put((x * A + y) * T + t, 0.f);
-          }
+      if (t_on)
+        for (int x = x0; x < x1; ++x)
+          for (int y = 0; y < A; ++y) put4((x * A + y) * T + t, zero4);
     };
     auto close_ring = [&]() {   // the parked ring is complete: convert and store it
-      for (int y = 0; y < A; ++y)
-#pragma unroll
-        for (int j = 0; j < TPL; ++j) {
-          const int t = t_base + 32 * j + lane;
-          if (t < T) put((next_x * A + y) * T + t, s_carry[(y * TPL + j) * 32 + lane]);
-        }
+      if (t_on)
+        for (int y = 0; y < A; ++y) put4((next_x * A + y) * T + t, s_carry[y * 32 + lane]);
       open = false;
       ++next_x;
     };
@@ -254,46 +267,32 @@ k_bw_build_g2(const float* __restrict__ h, const float* __restrict__ w, const in
         const bool more = seg_end == n && base + n < end;                     // the ring may go on in the next chunk
         for (int y = 0; y < A; ++y) {
           unsigned bits = seg & __ballot_sync(0xffffffffu, my_y == y);
-          float acc[TPL];
-#pragma unroll
-          for (int j = 0; j < TPL; ++j) acc[j] = cont ? s_carry[(y * TPL + j) * 32 + lane] : 0.f;
+          float4 acc = cont ? s_carry[y * 32 + lane] : zero4;
           while (bits) {
             // up to four entries' rows are requested before the first is added (CSR order kept)
-            int e[4];
-            float wg[4], hv[4][TPL];
+            float wg[4];
+            float4 hv[4];
             int cnt = 0;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              e[u] = bits ? __ffs((int)bits) - 1 : -1;
-              if (bits) { bits &= bits - 1; ++cnt; }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (u < cnt) {
-                const int2 m = s_meta[warp][e[u]];
+              if (bits) {
+                const int e = __ffs((int)bits) - 1;
+                bits &= bits - 1;
+                const int2 m = s_meta[warp][e];
                 wg[u] = __int_as_float(m.y);
-                const float* hrow = h + (size_t)m.x + t_base + lane;
-#pragma unroll
-                for (int j = 0; j < TPL; ++j) hv[u][j] = (t_base + 32 * j + lane < T) ? __ldg(hrow + 32 * j) : 0.f;
+                hv[u] = t_on ? __ldg(reinterpret_cast<const float4*>(h + (size_t)m.x + t)) : zero4;
+                ++cnt;
               }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
               if (u < cnt) {
-#pragma unroll
-                for (int j = 0; j < TPL; ++j) acc[j] = fmaf(wg[u], hv[u][j], acc[j]);
+                acc.x = fmaf(wg[u], hv[u].x, acc.x); acc.y = fmaf(wg[u], hv[u].y, acc.y);
+                acc.z = fmaf(wg[u], hv[u].z, acc.z); acc.w = fmaf(wg[u], hv[u].w, acc.w);
               }
           }
-          if (cont || more) {
-#pragma unroll
-            for (int j = 0; j < TPL; ++j) s_carry[(y * TPL + j) * 32 + lane] = acc[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < TPL; ++j) {
-              const int t = t_base + 32 * j + lane;
-              if (t < T) put((x * A + y) * T + t, acc[j]);
-            }
-          }
+          if (cont || more) s_carry[y * 32 + lane] = acc;
+          else if (t_on) put4((x * A + y) * T + t, acc);
         }
         if (cont || more) {
           open = true;
@@ -307,8 +306,8 @@ k_bw_build_g2(const float* __restrict__ h, const float* __restrict__ w, const in
     if (open) close_ring();
     zero_rings(next_x, R);                 // empty rings after the last one that had entries
   }
-  for (int i = lane; i < T; i += 32)       // centre slab: h[v] itself (zero for halo rows)
-    put(RA * T + i, v < v_out ? h[(size_t)v * T + i] : 0.f);
+  for (int i = 4 * lane; i < T; i += 128)  // centre slab: h[v] itself (zero for halo rows)
+    put4(RA * T + i, v < v_out ? __ldg(reinterpret_cast<const float4*>(h + (size_t)v * T + i)) : zero4);
 }
 
 // ---- persistent TMA-fed tcgen05 GEMM ---------------------------------------------------------------
@@ -856,14 +855,14 @@ TcGLayout tc_g_layout_max(int v_src, int R, int A, int F, int T, bool x3) {
   return L;
 }
 
-template <bool H, int TPL>
+template <bool H>
 static int launch_build_g2(const float* h, const float* w, const int32_t* rot_sel, const int32_t* row_ptr,
                            const int32_t* entries, int v_out, int v_src, int v_pad, int R, int A, int T, int kg, int kg_ld,
                            const float* scales, float* g_hi, float* g_lo, cudaStream_t st) {
-  const size_t smem = (size_t)G2_WARPS * A * 32 * TPL * sizeof(float);
+  const size_t smem = (size_t)G2_WARPS * A * 32 * sizeof(float4);
   if (smem > 40 * 1024)
-    GCB_CUDA_OK(cudaFuncSetAttribute(k_bw_build_g2<H, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_bw_build_g2<H, TPL><<<(unsigned)ceil_div64(v_pad, G2_WARPS), G2_WARPS * 32, smem, st>>>(
+    GCB_CUDA_OK(cudaFuncSetAttribute(k_bw_build_g2<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_bw_build_g2<H><<<(unsigned)ceil_div64(v_pad, G2_WARPS), G2_WARPS * 32, smem, st>>>(
       h, w, rot_sel, row_ptr, entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, g_lo);
   return GCB_OK;
 }
@@ -876,17 +875,14 @@ int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int
   const int v_pad = (int)ceil_div64(v_src, 128) * 128;
   // GCB_BUILD_G2=0 (read per call): the shared-memory kernel k_bw_build_g, for A/B measurements
   const bool g2_off = getenv("GCB_BUILD_G2") && atoi(getenv("GCB_BUILD_G2")) == 0;
-  if (ring_sorted && A <= GCB_MAX_ROT && T % 32 == 0 && !g2_off) {
+  if (ring_sorted && A <= GCB_MAX_ROT && T % 32 == 0 && !g2_off && ((uintptr_t)h % 16 == 0)) {
     const bool half = scales != nullptr;
     const int kg_ld = half ? (int)ceil_div64(kg, 64) * 64 : kg;
     float* lo = half || x3 ? g_lo : nullptr;
-    const int tpl = T % 128 == 0 ? 4 : (T % 96 == 0 ? 3 : (T % 64 == 0 ? 2 : 1));
     int rc;
     profile_begin(GCB_PROF_BWD_CSR, st);
-#define GCB_G2_LAUNCH(HH, TP) launch_build_g2<HH, TP>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, lo, st)
-    if (half) rc = tpl == 4 ? GCB_G2_LAUNCH(true, 4) : tpl == 3 ? GCB_G2_LAUNCH(true, 3) : tpl == 2 ? GCB_G2_LAUNCH(true, 2) : GCB_G2_LAUNCH(true, 1);
-    else rc = tpl == 4 ? GCB_G2_LAUNCH(false, 4) : tpl == 3 ? GCB_G2_LAUNCH(false, 3) : tpl == 2 ? GCB_G2_LAUNCH(false, 2) : GCB_G2_LAUNCH(false, 1);
-#undef GCB_G2_LAUNCH
+    rc = half ? launch_build_g2<true>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, lo, st)
+              : launch_build_g2<false>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, lo, st);
     profile_end(GCB_PROF_BWD_CSR, st);
     if (rc) return rc;
     GCB_LAUNCH_OK();

@@ -104,10 +104,18 @@ class DeviceFaustCache(IterableDataset):
 
     Iterating yields ``((signal, bc), gt)`` device tensors in the reference's order (training split shuffled per
     epoch).  For the training split the barycentric tensor handed out is ``bc + noise`` with
-    noise = |N(0, 1e-5)| on the weight column, drawn on the device from ``generator`` - a new tensor every epoch."""
+    noise = |N(0, 1e-5)| on the weight column, drawn on the device from ``generator`` - a new tensor every epoch.
 
-    def __init__(self, path_to_zip, set_type=0, device="cuda", set_indices=None, generator=None):
+    Every mesh is also PACKED once: the int32 indices and the CSR inversion the backward needs
+    depend on the index column only, which the noise never touches, so they are computed when the mesh is loaded
+    and every tensor handed out carries them (`ops.attach_pack`): the layers then skip gcb_prep_bary and the radix
+    sort of gcb_csr_build in every step; only the fp32 weights of the epoch are new.  ``pack=False`` hands out
+    plain tensors (the layers pack them on the fly)."""
+
+    def __init__(self, path_to_zip, set_type=0, device="cuda", set_indices=None, generator=None, pack=True):
         self.set_type = set_type
+        self.pack = bool(pack) and torch.device(device).type == "cuda"
+        self.packs = {}
         self.device = torch.device(device)
         self.generator = generator
         dataset = np.load(path_to_zip, allow_pickle=True)
@@ -119,6 +127,11 @@ class DeviceFaustCache(IterableDataset):
             bc = torch.tensor(dataset[bc_names[idx]], dtype=torch.float32).to(self.device)
             gt = torch.tensor(dataset[gt_names[idx]], dtype=torch.int64).view(-1,).to(self.device)
             self.meshes[idx] = (signal, bc, gt)
+            if self.pack:
+                from geoconv_b200 import ops
+                base = ops.prep_bary(bc, signal.shape[0], keep_zero_weight_slots=True)
+                base.csr()                      # the inversion is paid here, once per mesh
+                self.packs[idx] = base
 
     def __len__(self):
         return len(self.indices)
@@ -137,6 +150,12 @@ class DeviceFaustCache(IterableDataset):
                                     dtype=torch.float32).abs_().mul_(NOISE_SCALE)
                 noisy = bc.clone()
                 noisy[..., 1] += noise
+                if self.pack:
+                    from geoconv_b200 import ops
+                    ops.attach_pack(noisy, ops.pack_with_weights(self.packs[idx], noisy[..., 1]))
                 yield (signal, noisy), gt
             else:
+                if self.pack:
+                    from geoconv_b200 import ops
+                    ops.attach_pack(bc, self.packs[idx])
                 yield (signal, bc), gt

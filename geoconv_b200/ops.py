@@ -133,6 +133,7 @@ class BaryPack:
     r: int
     a: int
     oob_count: int | None = None          # out-of-range indices found by gcb_prep_bary (None: not read back yet)
+    keeps_all_slots: bool = False         # the CSR inversion keeps zero-weight slots (shared between weight variants)
     _csr: tuple | None = field(default=None, repr=False)
     _records: torch.Tensor | None = field(default=None, repr=False)
 
@@ -145,7 +146,9 @@ class BaryPack:
     def csr(self):
         """(row_ptr int32 [V_src+1], entries int32 [n_slots], stats int32 [8]) - built on first backward."""
         if self._csr is None:
-            self._csr = tuple(csr_build_op(self.idx, self.w, self.v_src))
+            # (all-ones weights: nothing is dropped and the stats bound |w| by 1, which barycentric weights respect)
+            w = torch.ones_like(self.w) if self.keeps_all_slots else self.w
+            self._csr = tuple(csr_build_op(self.idx, w, self.v_src))
         return self._csr
 
     def records(self):
@@ -156,7 +159,8 @@ class BaryPack:
         return self._records
 
 
-def prep_bary(bary: torch.Tensor, v_src: int, check_indices: bool | str = True) -> BaryPack:
+def prep_bary(bary: torch.Tensor, v_src: int, check_indices: bool | str = True,
+              keep_zero_weight_slots: bool = False) -> BaryPack:
     """Split a (V,R,A,3,2) barycentric tensor (fp32 or fp64) into int32 indices and fp32 weights.
 
     Same arithmetic as the reference: cast to fp32, truncate the index column toward zero.
@@ -174,7 +178,7 @@ def prep_bary(bary: torch.Tensor, v_src: int, check_indices: bool | str = True) 
         bary = bary.to(torch.float32)
     v, r, a = bary.shape[:3]
     idx, w, oob = prep_bary_op(bary, v_src)
-    pack = BaryPack(idx=idx, w=w, v_out=v, v_src=v_src, r=r, a=a)
+    pack = BaryPack(idx=idx, w=w, v_out=v, v_src=v_src, r=r, a=a, keeps_all_slots=keep_zero_weight_slots)
     _PACK_OF_IDX[idx.data_ptr()] = pack
     if idx.numel() and check_indices:
         INDEX_CHECKS.submit(pack, oob)
@@ -202,6 +206,9 @@ class BaryCache:
         self._items: dict[int, tuple] = {}
 
     def get(self, bary: torch.Tensor, v_src: int, check_indices: bool = True) -> BaryPack:
+        attached = getattr(bary, "_gcb_pack", None)      # a loader that packed the tensor itself (attach_pack)
+        if attached is not None and attached[1] == bary._version and attached[0].v_src == v_src:
+            return attached[0]
         key = id(bary)
         hit = self._items.get(key)
         if hit is not None:
@@ -218,6 +225,28 @@ class BaryCache:
 
 
 GLOBAL_BARY_CACHE = BaryCache()
+
+
+def attach_pack(bary: torch.Tensor, pack: BaryPack) -> torch.Tensor:
+    """Tell the layers that `bary` has already been split / inverted: they use `pack` instead of running
+    gcb_prep_bary and gcb_csr_build again (valid until `bary` is modified in place).  A data loader that keeps the
+    meshes of a dataset on the device packs each of them once (data/faust_data_set.py::DeviceFaustCache)."""
+    bary._gcb_pack = (pack, bary._version)
+    return bary
+
+
+def pack_with_weights(base: BaryPack, w: torch.Tensor) -> BaryPack:
+    """A pack that shares `base`'s indices and CSR inversion but carries other weights (training-time noise on the
+    barycentric weights: preprocess / faust_data_set.py:82-94 perturb the weight column only).  `base` must have been
+    inverted WITHOUT dropping zero-weight slots (`prep_bary(..., keep_zero_weight_slots=True)`), because a weight that
+    is zero in one epoch need not be in the next."""
+    if not base.keeps_all_slots:
+        raise ValueError("pack_with_weights needs a base pack built with keep_zero_weight_slots=True")
+    out = BaryPack(idx=base.idx, w=w.contiguous(), v_out=base.v_out, v_src=base.v_src, r=base.r, a=base.a,
+                   oob_count=base.oob_count, keeps_all_slots=True)
+    out._csr = base.csr()
+    _PACK_OF_IDX[out.idx.data_ptr()] = out
+    return out
 
 
 # ================================================================================================

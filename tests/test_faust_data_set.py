@@ -91,3 +91,36 @@ def test_device_cache_feeds_the_layer(archive):
     assert torch.equal(b1[..., 0], clean[..., 0])
     d = (b1[..., 1] - clean[..., 1])
     assert (d >= 0).all() and d.max() < 1e-3
+
+
+@pytest.mark.gpu
+def test_device_cache_packs_every_mesh_once(archive):
+    """the cache hands out tensors that carry their int32 indices and CSR inversion (computed when
+    the mesh was loaded); a training step through them equals a step through a plain tensor with the same values."""
+    from geoconv_b200 import ops
+    from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
+    from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    train = DeviceFaustCache(archive, set_type=0, set_indices=[0, 1, 2], generator=gen)
+    layer = ConvGeodesic(input_shape=[(None, 6), (None, 2, 4, 3, 2)], amt_templates=4, template_radius=0.03).cuda()
+    packs_seen = set()
+    for epoch in range(2):
+        for (signal, bc), _gt in train:
+            pack, version = bc._gcb_pack
+            assert version == bc._version and pack.keeps_all_slots
+            assert torch.equal(pack.idx.long().cpu(), bc[..., 0].long().cpu())
+            assert torch.equal(pack.w, bc[..., 1])
+            assert ops.GLOBAL_BARY_CACHE.get(bc, signal.shape[0]) is pack          # the layers take it as is
+            packs_seen.add(pack.csr()[1].data_ptr())                               # inversion shared across epochs
+            grads = []
+            for tensor in (bc, bc.clone()):                                        # packed by the cache / by the layer
+                xs = signal.clone().requires_grad_(True)
+                layer.zero_grad()
+                AngularMaxPooling()(layer([xs, tensor])).sum().backward()
+                grads.append((xs.grad.clone(), layer._template_neighbor_weights.grad.clone()))
+            assert torch.allclose(grads[0][0], grads[1][0], rtol=1e-5, atol=1e-7)
+            assert torch.allclose(grads[0][1], grads[1][1], rtol=1e-5, atol=1e-7)
+    assert len(packs_seen) == 3                                                    # one inversion per mesh, not per epoch
+    plain = DeviceFaustCache(archive, set_type=1, pack=False)
+    (_s, bc), _ = next(iter(plain))
+    assert not hasattr(bc, "_gcb_pack")
