@@ -823,9 +823,17 @@ def run_ours(args):
                 extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
                 torch.cuda.synchronize()
 
+    def leave_multi_rank():
+        # CUDA graphs that hold NCCL kernels are still alive here; tearing the communicator down under them made
+        # rank 0 hang in destroy_process_group (N = 2, r02).  Nothing is left to do collectively: flush and leave.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            leave_multi_rank()
         return
 
     value = world * v * args.steps / (total_ms * 1e-3)
@@ -906,7 +914,7 @@ def run_ours(args):
     }
     emit(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        leave_multi_rank()
 
 
 _RESULT_FD = None

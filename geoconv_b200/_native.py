@@ -32,6 +32,7 @@ SIGNATURES = {
     "gcb_abi_version": (_int, []),
     "gcb_last_error": (C.c_char_p, []),
     "gcb_launch_count": (_i64, []),
+    "gcb_yield_sms": (None, [_int]),
     "gcb_profile_enable": (None, [_int]),
     "gcb_profile_read": (_int, [_int, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "gcb_tc_supported": (_int, [_i32, _i32, _i32, _i32, _i32]),

@@ -22,6 +22,9 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static std::atomic<int> g_yield_sms{0};
+int yield_sms() { return g_yield_sms.load(std::memory_order_relaxed); }
+
 // ---- optional kernel timing (one host thread per process drives the library) ----
 struct ProfSlot {
   std::vector<cudaEvent_t> start, stop;
@@ -70,6 +73,7 @@ static int check_shape(int v_out, int v_src, int R, int A, int F, int T) {
 using namespace gcb;
 
 extern "C" int gcb_abi_version(void) { return GCB_ABI_VERSION; }
+extern "C" void gcb_yield_sms(int on) { g_yield_sms.store(on ? 1 : 0, std::memory_order_relaxed); }
 extern "C" int64_t gcb_launch_count(void) { return (int64_t)g_launches.load(); }
 extern "C" void gcb_profile_enable(int on) {
   g_prof_on = on != 0;

@@ -30,6 +30,8 @@ void set_error(const char* fmt, ...);
 
 // every kernel launch of the library goes through this: error check + launch accounting
 void count_launch();
+// gcb_yield_sms(): persistent GEMMs size their grid to the tile rounds they need instead of to the SM count
+int yield_sms();
 #define GCB_LAUNCH_OK()              \
   do {                               \
     gcb::count_launch();             \

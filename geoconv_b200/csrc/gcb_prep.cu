@@ -77,53 +77,65 @@ static int key_bits(int64_t max_key) {
 // input slot p a thread reads its own value once and the 8 prior elements as two broadcast
 // 128-bit loads, so the loop runs at 8 FMAs per 3 shared-memory instructions (the first version did
 // 1 FMA per 2 and was shared-memory-issue bound at 31 us for 8.4 MB).
+constexpr int FOLD_TB = 4;   // templates per block: the prior is staged once for all of them, their tiles fly together
+
 __global__ void __launch_bounds__(1024) k_fold_prior(const float* __restrict__ in, const float* __restrict__ prior,
-                                                    float* __restrict__ out, int RA, int RAp, int F, int transpose) {
+                                                    float* __restrict__ out, int T, int RA, int RAp, int F, int transpose) {
   extern __shared__ float4 s_mem4[];
   float* s_prior = reinterpret_cast<float*>(s_mem4);   // [RA][RAp]: s_prior[p*RAp + q] multiplies in[p] into out[q]
-  float* s_in = s_prior + RA * RAp;                    // [RA][32]
-  const int t = blockIdx.y, f0 = blockIdx.x * 32;
+  float* s_in = s_prior + RA * RAp;                    // [FOLD_TB][RA][32]
+  const int t0 = blockIdx.y * FOLD_TB, f0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // The input tile comes cold from HBM, the prior from L2: the tile's loads are issued first and parked in
-  // registers (blockDim = 4 * RAp threads, so a thread owns at most 8 of the RA * 32 tile elements), the prior is
-  // staged while they fly - one exposed round trip instead of two (ncu: half of the stall samples sat on the
-  // shared-memory stores waiting for these loads).  blockDim = 4 * RAp also gives (row, column) of a prior
-  // element without a division per element.
-  float xin[8];
+  // The input tiles come cold from HBM, the prior from L2: the loads of all FOLD_TB tiles are issued first and
+  // parked in registers (blockDim = 4 * RAp threads, so a thread owns at most 8 of the RA * 32 elements of a tile),
+  // the prior is staged while they fly - one exposed round trip per block (ncu, r01: half of the stall samples sat
+  // on the shared-memory stores waiting for these loads; one template per block paid that round trip and the prior
+  // staging 4x as often: 14 us per call).  blockDim = 4 * RAp also gives (row, column) of a prior element without
+  // a division per element.
+  float xin[FOLD_TB][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int i = threadIdx.x + j * blockDim.x;
-    const int p = i >> 5, fl = i & 31;
-    xin[j] = (i < RA * 32 && f0 + fl < F) ? __ldg(in + ((size_t)t * RA + p) * F + f0 + fl) : 0.f;
-  }
+  for (int b = 0; b < FOLD_TB; ++b)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = threadIdx.x + j * blockDim.x;
+      const int p = i >> 5, fl = i & 31;
+      xin[b][j] = (i < RA * 32 && f0 + fl < F && t0 + b < T) ? __ldg(in + ((size_t)(t0 + b) * RA + p) * F + f0 + fl) : 0.f;
+    }
   {
     const int p0 = threadIdx.x / RAp, q = threadIdx.x - p0 * RAp;
     for (int p = p0; p < RA; p += 4)
       s_prior[p * RAp + q] = q < RA ? __ldg(transpose ? prior + q * RA + p : prior + p * RA + q) : 0.f;
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int i = threadIdx.x + j * blockDim.x;
-    if (i < RA * 32) s_in[i] = xin[j];
-  }
+  for (int b = 0; b < FOLD_TB; ++b)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = threadIdx.x + j * blockDim.x;
+      if (i < RA * 32) s_in[b * RA * 32 + i] = xin[b][j];
+    }
   __syncthreads();
   const int q0 = warp * 8;
   if (q0 >= RA || f0 + lane >= F) return;
-  float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int p = 0; p < RA; ++p) {
-    const float x = s_in[p * 32 + lane];
-    const float4 k0 = *reinterpret_cast<const float4*>(s_prior + p * RAp + q0);
-    const float4 k1 = *reinterpret_cast<const float4*>(s_prior + p * RAp + q0 + 4);
-    acc[0] = fmaf(x, k0.x, acc[0]); acc[1] = fmaf(x, k0.y, acc[1]);
-    acc[2] = fmaf(x, k0.z, acc[2]); acc[3] = fmaf(x, k0.w, acc[3]);
-    acc[4] = fmaf(x, k1.x, acc[4]); acc[5] = fmaf(x, k1.y, acc[5]);
-    acc[6] = fmaf(x, k1.z, acc[6]); acc[7] = fmaf(x, k1.w, acc[7]);
+  for (int b = 0; b < FOLD_TB; ++b) {
+    if (t0 + b >= T) break;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const float* sx = s_in + b * RA * 32;
+    for (int p = 0; p < RA; ++p) {
+      const float x = sx[p * 32 + lane];
+      const float4 k0 = *reinterpret_cast<const float4*>(s_prior + p * RAp + q0);
+      const float4 k1 = *reinterpret_cast<const float4*>(s_prior + p * RAp + q0 + 4);
+      acc[0] = fmaf(x, k0.x, acc[0]); acc[1] = fmaf(x, k0.y, acc[1]);
+      acc[2] = fmaf(x, k0.z, acc[2]); acc[3] = fmaf(x, k0.w, acc[3]);
+      acc[4] = fmaf(x, k1.x, acc[4]); acc[5] = fmaf(x, k1.y, acc[5]);
+      acc[6] = fmaf(x, k1.z, acc[6]); acc[7] = fmaf(x, k1.w, acc[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (q0 + j < RA) out[((size_t)(t0 + b) * RA + q0 + j) * F + f0 + lane] = acc[j];
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (q0 + j < RA) out[((size_t)t * RA + q0 + j) * F + f0 + lane] = acc[j];
 }
 
 __global__ void k_pack_rows(const float* __restrict__ src, const int32_t* __restrict__ rows,
@@ -207,12 +219,12 @@ extern "C" int gcb_fold_prior(const float* in, const float* prior, float* out, i
   GCB_REQUIRE(T > 0 && R > 0 && A > 0 && F > 0, GCB_EINVAL, "gcb_fold_prior: bad sizes");
   int RA = R * A;
   const int RAp = (RA + 7) / 8 * 8;
-  size_t smem = ((size_t)RA * RAp + (size_t)RA * 32) * sizeof(float);
+  size_t smem = ((size_t)RA * RAp + (size_t)FOLD_TB * RA * 32) * sizeof(float);
   GCB_REQUIRE(smem <= 160 * 1024 && RAp / 8 <= 32, GCB_EUNSUPPORTED, "gcb_fold_prior: R*A=%d too large", RA);
   if (smem > 48 * 1024)
     GCB_CUDA_OK(cudaFuncSetAttribute(k_fold_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div64(F, 32), (unsigned)T);
-  k_fold_prior<<<grid, (unsigned)(RAp / 8 * 32), smem, (cudaStream_t)stream>>>(in, prior, out, RA, RAp, F, transpose);
+  dim3 grid((unsigned)ceil_div64(F, 32), (unsigned)ceil_div64(T, FOLD_TB));
+  k_fold_prior<<<grid, (unsigned)(RAp / 8 * 32), smem, (cudaStream_t)stream>>>(in, prior, out, T, RA, RAp, F, transpose);
   GCB_LAUNCH_OK();
   return GCB_OK;
 }

@@ -982,7 +982,13 @@ int tc_dx_from_g(const float* g_hi, const float* g_lo, const float* wcat_hi, con
   p.ns = ns;
   const size_t smem = 2048 + (size_t)ns * stage_bytes;
   const int n_tiles = p.n_mtiles * p.n_ntiles;
-  const int grid = n_tiles < 148 ? n_tiles : 148;
+  int grid = n_tiles < 148 ? n_tiles : 148;
+  if (yield_sms() && n_tiles > 148) {
+    // a collective runs beside this GEMM (gcb_yield_sms): 270 tiles take two rounds on 148 CTAs and on 135 - the
+    // smaller grid costs nothing and leaves whole SMs (227 KB of shared memory each) to the collective's CTAs
+    const int rounds = (n_tiles + 147) / 148;
+    grid = (n_tiles + rounds - 1) / rounds;
+  }
   if (half) return launch_gemm<true, true>(ah, al, bh, bl, p, grid, smem, st);
   return x3 ? launch_gemm<true>(ah, al, bh, bl, p, grid, smem, st) : launch_gemm<false>(ah, al, bh, bl, p, grid, smem, st);
 }

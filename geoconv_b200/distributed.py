@@ -58,21 +58,52 @@ class overlapped_grad_sync:
     accumulate locally and call `allreduce_gradients` once instead.  `synced(params)` tells which parameters need no
     further reduction."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, max_ctas: int | None = 8):
         from . import ops
         self._ops = ops
+        if group is None and max_ctas and dist.is_initialized() and dist.get_backend() == "nccl":
+            group = _low_cta_group(max_ctas)
         self.sync = ops.GradSync(group)
         self._prev = None
 
     def __enter__(self):
         self._prev = self._ops.GRAD_SYNC
         self._ops.GRAD_SYNC = self.sync
+        self._yield(1)
         return self.sync
 
     def __exit__(self, *exc):
         self.sync.join()
         self._ops.GRAD_SYNC = self._prev
+        self._yield(0)
         return False
+
+    @staticmethod
+    def _yield(on):
+        try:
+            from . import _native
+            _native.load().gcb_yield_sms(on)     # the dSignal GEMM leaves SMs to the collective
+        except Exception:  # noqa: BLE001 - CPU-only process (gloo tests): nothing to tell
+            pass
+
+
+_LOW_CTA_GROUPS: dict = {}
+
+
+def _low_cta_group(max_ctas: int):
+    """A process group over all ranks whose NCCL kernels use at most `max_ctas` CTAs: the collective that runs beside
+    the dSignal GEMM has to fit on the SMs that GEMM leaves free (13 of 148 at the FAUST shape)."""
+    if max_ctas not in _LOW_CTA_GROUPS:
+        group = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = int(max_ctas)
+            opts.config.min_ctas = 1
+            group = dist.new_group(backend="nccl", pg_options=opts)
+        except Exception:  # noqa: BLE001 - option not available in this build: the default group
+            group = None
+        _LOW_CTA_GROUPS[max_ctas] = group
+    return _LOW_CTA_GROUPS[max_ctas]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -541,8 +541,19 @@ class GradSync:
         import torch.distributed as dist
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
-        for t_ in tensors:
-            if t_.numel():
+        tensors = [t_ for t_ in tensors if t_.numel()]
+        done = False
+        if len(tensors) > 1 and tensors[0].is_cuda:
+            try:     # one NCCL launch for all of them (coalesced group)
+                with dist._coalescing_manager(group=self.group, device=tensors[0].device, async_ops=True) as cm:
+                    for t_ in tensors:
+                        dist.all_reduce(t_, op=dist.ReduceOp.SUM, group=self.group)
+                self._works.append(cm)
+                done = True
+            except Exception:  # noqa: BLE001 - private API: fall back to one collective per tensor
+                done = False
+        if not done:
+            for t_ in tensors:
                 self._works.append(dist.all_reduce(t_, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self.early_reductions += 1
 

@@ -58,6 +58,10 @@ extern "C" {
 
 int gcb_abi_version(void);
 const char* gcb_last_error(void);
+/* on != 0: a collective is going to run beside the library's persistent GEMMs (data-parallel all-reduce started inside
+ * the backward): they size their grids to the tile rounds they need (e.g. 135 CTAs for 270 tiles) instead of one CTA
+ * per SM, which costs nothing and leaves whole SMs to the collective.  Process-wide, off by default. */
+void gcb_yield_sms(int on);
 /* Kernel launches issued by this library in this process so far (bench.py's gpu_launches). */
 int64_t gcb_launch_count(void);
 /* Measurement hooks (bench.py's roofline leg): while enabled, CUDA events bracket the dominant
