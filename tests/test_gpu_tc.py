@@ -167,3 +167,30 @@ def test_f16x3_zero_and_constant_inputs():
     layer.load_state_dict({"_template_neighbor_weights": wn * 0, "_template_self_weights": ws * 0, "_bias": b})
     y1 = layer([O.make_signal(v, f, seed=9, kind="randn").to(DEV), bary])
     assert torch.equal(y1, expect)
+
+
+@pytest.mark.parametrize("shape", [(1000, 96, 5, 8, 96, 1), (700, 64, 3, 8, 32, 1), (517, 128, 2, 6, 256, 2), (300, 32, 2, 8, 384, 4)],
+                         ids=lambda s: "-".join(map(str, s)))
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_fused_finish_equals_separate_finish(shape, precision, monkeypatch):
+    """GCB_TC_FUSE=1: the split reduction, bias, activation and pooling run inside k_tc_conv (last-arriving split of
+    a unit).  Same additions in the same order as k_tc_finish: Y, Z and argmax are bit-identical.  (Not the default:
+    slower at the FAUST shape, profiles/r02_notes.md.)"""
+    v, f, r, a, t, delta = shape
+    wn, ws, b = O.make_weights(t, r, a, f, seed=0)
+    signal = O.make_signal(v, f, seed=1, kind="randn").to(DEV)
+    bary = O.make_bary(v, r, a, seed=1, fallback_frac=0.05).to(DEV)
+    layer = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.03,
+                         rotation_delta=delta, activation="elu", precision=precision)
+    layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
+    layer = layer.to(DEV)
+    outs = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("GCB_TC_FUSE", mode)
+        with torch.no_grad():
+            y = layer([signal, bary])
+        outs[mode] = (y.clone(), y._gcb_pooled[0].clone(), y._gcb_pooled[1].clone())
+    monkeypatch.delenv("GCB_TC_FUSE")
+    for mode in ("1", "2"):
+        for got, want in zip(outs[mode], outs["0"]):
+            assert torch.equal(got, want), f"GCB_TC_FUSE={mode}"
