@@ -501,7 +501,7 @@ def run_ours(args):
     # be captured in a CUDA graph the step is replayed without it and the gradients are reduced after the replay.
     grad_sync = {"ctx": None, "mode": "none"}
     if world > 1 and args.overlap_allreduce:
-        grad_sync["ctx"] = overlapped_grad_sync()
+        grad_sync["ctx"] = overlapped_grad_sync(max_ctas=args.allreduce_ctas)
         grad_sync["ctx"].__enter__()
         grad_sync["mode"] = "all-reduce inside the backward (after the weight-gradient stage, beside the dSignal GEMM)"
     elif world > 1:
@@ -900,6 +900,8 @@ def run_ours(args):
                 "ms_per_step": e2e_ms / args.steps, "launch": e2e_mode,
                 "overlap": e2e_mode_p or "none (copies and compute serialised on one stream)",
                 "serial_ms_per_step": e2e_serial_ms / args.steps,
+                "h2d_gbs_per_rank": h2d / (e2e_ms / args.steps * 1e-3) / 1e9,
+                "h2d_gbs_all_ranks": world * h2d / (e2e_ms / args.steps * 1e-3) / 1e9,
                 "derivation": ("pipelined figure = device time of the timed loop minus the separately timed loop of its L2 "
                                "flushes (the flush is measurement apparatus, not part of a step); serial figure = per-step "
                                "events, flush outside") if e2e_mode_p else "per-step events, flush outside",
@@ -947,6 +949,7 @@ def main():
     ap.add_argument("--graph", type=int, default=1, help="1: replay the resident step from a CUDA graph (default)")
     ap.add_argument("--overlap-allreduce", type=int, default=1,
                     help="1: N > 1 starts the weight-gradient all-reduce inside the backward (default); 0: after the step")
+    ap.add_argument("--allreduce-ctas", type=int, default=8, help="CTA cap of the in-backward all-reduce's NCCL communicator")
     ap.add_argument("--extras", type=int, default=1, help="1: also measure the TF32 mode (N = 1) and configs 4 / 5 (default)")
     ap.add_argument("--e2e-pipeline", type=int, default=1,
                     help="1: overlap the H2D of step n+1 with the compute of step n in the host-to-host leg (default)")

@@ -96,7 +96,9 @@ def _low_cta_group(max_ctas: int):
     if max_ctas not in _LOW_CTA_GROUPS:
         group = None
         try:
-            opts = dist.ProcessGroupNCCL.Options()
+            # high-priority stream: the collective's few CTAs are placed as soon as an SM has room instead of
+            # queueing behind the compute grid that was launched beside it
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
             opts.config.max_ctas = int(max_ctas)
             opts.config.min_ctas = 1
             group = dist.new_group(backend="nccl", pg_options=opts)
@@ -283,7 +285,12 @@ class ShardedForward:
     (a copy; a consumer that accepts row blocks does not need it).  The layer is called with `row_offset`, so that
     a block's centre term reads its own vertices.  Forward only: training uses `sharded_layer_forward`."""
 
-    def __init__(self, layer, plan: VertexShardPlan, n_features: int, device, group=None):
+    def __init__(self, layer, plan: VertexShardPlan, n_features: int, device, group=None, max_ctas: int | None = 4):
+        if group is None and max_ctas and plan.world > 1 and dist.is_initialized() and dist.get_backend() == "nccl":
+            # the exchange runs BESIDE the interior rows' kernels: few CTAs on a high-priority stream, or its CTAs
+            # queue behind the compute grid while their peers spin (N = 8: 11.1 ms overlapped against 7.3 ms serial
+            # with the default communicator, profiles/r02_notes.md)
+            group = _low_cta_group(max_ctas)
         self.layer, self.plan, self.group = layer, plan, group
         self.lo, self.hi = interior_rows(plan)
         bl = plan.bary_local
