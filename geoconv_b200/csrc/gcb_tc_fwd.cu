@@ -519,17 +519,24 @@ __global__ void k_tc_wcat_h(const float* __restrict__ w_eff, const float* __rest
   *reinterpret_cast<uint4*>(lo + o) = l;
 }
 
-// Wcat[t, 0:KRA] = Weff[t], Wcat[t, KRA:KRA+F] = Wself[t], split into tf32 hi (+ lo for X3)
+// Wcat[t, 0:KRA] = Weff[t], Wcat[t, KRA:KRA+F] = Wself[t], split into tf32 hi (+ lo for X3); a thread converts 4
+// consecutive elements of a row (R*A*F and F are multiples of 4 on the tensor path, so a group never straddles
+// [Weff | Wself]) with 16-byte accesses (one element per thread and a division per element took 9 us per call)
 __global__ void k_tc_wcat(const float* __restrict__ w_eff, const float* __restrict__ w_self, int T, int KRA,
                           int F, float* __restrict__ hi, float* __restrict__ lo) {
-  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int kcat = KRA + F;
-  if (e >= (int64_t)T * kcat) return;
-  int t = (int)(e / kcat), k = (int)(e - (int64_t)t * kcat);
-  float v = k < KRA ? w_eff[(size_t)t * KRA + k] : w_self[(size_t)t * F + (k - KRA)];
-  float h = ptx::to_tf32(v);
-  hi[e] = h;
-  if (lo) lo[e] = v - h;
+  const int64_t e4 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int kcat = KRA + F, k4n = kcat >> 2;
+  if (e4 >= (int64_t)T * k4n) return;
+  const int t = (int)(e4 / k4n), k = (int)(e4 - (int64_t)t * k4n) << 2;
+  const float* src = k < KRA ? w_eff + (size_t)t * KRA + k : w_self + (size_t)t * F + (k - KRA);
+  float4 v;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) v = __ldg(reinterpret_cast<const float4*>(src));
+  else v = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+  float4 h;
+  h.x = ptx::to_tf32(v.x); h.y = ptx::to_tf32(v.y); h.z = ptx::to_tf32(v.z); h.w = ptx::to_tf32(v.w);
+  const size_t o = (size_t)t * kcat + k;   // multiple of 4 floats: 16-byte aligned
+  *reinterpret_cast<float4*>(hi + o) = h;
+  if (lo) *reinterpret_cast<float4*>(lo + o) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
 }
 
 // ---- kernel 1: the contraction ---------------------------------------------------------------
@@ -1818,7 +1825,8 @@ int tc_pack_recs(const int32_t* idx, const float* w, int v_out, int R, int A, ui
 int tc_build_wcat(const float* w_eff, const float* w_self, int T, int R, int A, int F, float* hi, float* lo,
                   cudaStream_t st) {
   const int KRA = R * A * F;
-  int64_t wt = (int64_t)T * (KRA + F);
+  GCB_REQUIRE(F % 4 == 0, GCB_EINVAL, "tc_build_wcat: F must be a multiple of 4");
+  int64_t wt = (int64_t)T * ((KRA + F) / 4);
   k_tc_wcat<<<(unsigned)ceil_div64(wt, 256), 256, 0, st>>>(w_eff, w_self, T, KRA, F, hi, lo);
   GCB_LAUNCH_OK();
   return GCB_OK;

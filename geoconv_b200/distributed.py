@@ -50,6 +50,71 @@ def allreduce_gradients(params, group=None, average: bool = False) -> None:
             p.grad /= world
 
 
+class PeerAllReduce:
+    """In-place sum of a few gradient tensors over the ranks with libgeoconv_b200's own NVLink kernel
+    (`gcb_peer_allreduce`: two-shot all-reduce on directly mapped peer buffers, include/geoconv_b200.h) instead of
+    NCCL.  The peer-mapped staging buffers come from torch's symmetric memory; one buffer per total element count,
+    allocated (collectively - every rank must reach the first call together) on first use."""
+
+    def __init__(self, group=None, n_ctas: int = 12):
+        self.group = group if group is not None else dist.group.WORLD
+        self.n_ctas = n_ctas
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self._bufs: dict[int, tuple] = {}
+        self.stream = None
+        self.calls = 0
+
+    def _buffer(self, n: int, device):
+        hit = self._bufs.get(n)
+        if hit is None:
+            import torch.distributed._symmetric_memory as symm
+            from . import _native
+            lib = _native.load()
+            nbytes = lib.gcb_peer_allreduce_bytes(n, self.world)
+            buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, self.group)
+            torch.cuda.synchronize(device)
+            hdl.barrier()                       # every rank's flags are zero before anybody writes one
+            torch.cuda.synchronize(device)
+            hit = (buf, hdl, nbytes)
+            self._bufs[n] = hit
+        return hit
+
+    def error_word(self, n: int) -> int:
+        buf, _hdl, nbytes = self._bufs[n]
+        n_pad = (n + 3) // 4 * 4
+        off = (2 * n_pad * 4 + 255) // 256 * 256 + (2 * self.world + 4) * 4
+        return int(buf[off:off + 4].view(torch.int32).item())
+
+    def __call__(self, tensors, stream=None):
+        """Sum `tensors` (<= 3 contiguous fp32 CUDA tensors, each a multiple of 4 elements) over the ranks in place,
+        on `stream` (default: the current stream)."""
+        from . import _native
+        lib = _native.load()
+        ts = [t for t in tensors if t.numel()]
+        if not 1 <= len(ts) <= 3:
+            raise ValueError("PeerAllReduce takes one to three non-empty tensors")
+        for t in ts:
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and t.numel() % 4 == 0):
+                raise ValueError("PeerAllReduce needs contiguous fp32 CUDA tensors whose sizes are multiples of 4")
+        n = sum(t.numel() for t in ts)
+        dev = ts[0].device
+        _buf, hdl, _nbytes = self._buffer(n, dev)
+        ts = ts + [None] * (3 - len(ts))
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            _native.check(lib.gcb_peer_allreduce(ts[0].data_ptr(), ts[0].numel(),
+                                                 ts[1].data_ptr() if ts[1] is not None else None,
+                                                 ts[1].numel() if ts[1] is not None else 0,
+                                                 ts[2].data_ptr() if ts[2] is not None else None,
+                                                 ts[2].numel() if ts[2] is not None else 0,
+                                                 hdl.buffer_ptrs_dev, self.rank, self.world, self.n_ctas, st.cuda_stream),
+                          "gcb_peer_allreduce")
+        self.calls += 1
+
+
 class overlapped_grad_sync:
     """Context manager: inside it, every geoconv_b200 convolution whose backward takes the AMP-sparse route
     all-reduces its weight gradients from INSIDE the backward, between the weight-gradient stage and the dSignal GEMM
@@ -58,12 +123,19 @@ class overlapped_grad_sync:
     accumulate locally and call `allreduce_gradients` once instead.  `synced(params)` tells which parameters need no
     further reduction."""
 
-    def __init__(self, group=None, max_ctas: int | None = 8):
+    def __init__(self, group=None, max_ctas: int | None = 8, peer: bool = True):
         from . import ops
         self._ops = ops
+        reducer = None
+        if peer and dist.is_initialized() and dist.get_backend(group) == "nccl" and dist.get_world_size(group) > 1:
+            # the library's own all-reduce kernel over NVLink peer memory; NCCL remains the fallback
+            try:
+                reducer = PeerAllReduce(group, n_ctas=12)
+            except Exception:  # noqa: BLE001 - no symmetric memory in this build / on this machine
+                reducer = None
         if group is None and max_ctas and dist.is_initialized() and dist.get_backend() == "nccl":
             group = _low_cta_group(max_ctas)
-        self.sync = ops.GradSync(group)
+        self.sync = ops.GradSync(group, peer_reducer=reducer)
         self._prev = None
 
     def __enter__(self):

@@ -530,18 +530,36 @@ class GradSync:
     all-reduce asynchronously - the collective's stream waits for what has been enqueued so far, i.e. for stage one -
     and the dSignal GEMM of stage two runs beside it; `join` makes the compute stream wait for the collective."""
 
-    def __init__(self, group=None, average: bool = False):
+    def __init__(self, group=None, average: bool = False, peer_reducer=None):
         self.group = group
         self.average = average
         self.active = True
         self._works = []
         self.early_reductions = 0
+        self.peer_reducer = peer_reducer      # distributed.PeerAllReduce: the library's own NVLink all-reduce kernel
+        self.peer_failed = None
+        self._side = None
+        self._joined = True
 
     def reduce_early(self, tensors):
         import torch.distributed as dist
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
         tensors = [t_ for t_ in tensors if t_.numel()]
+        if self.peer_reducer is not None and tensors and tensors[0].is_cuda and len(tensors) <= 3 and \
+                all(t_.numel() % 4 == 0 and t_.is_contiguous() for t_ in tensors):
+            try:
+                dev = tensors[0].device
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=dev, priority=-1)
+                self._side.wait_stream(torch.cuda.current_stream(dev))      # stage one (weight gradients) is enqueued
+                self.peer_reducer(tensors, stream=self._side)
+                self._joined = False
+                self.early_reductions += 1
+                return
+            except Exception as exc:  # noqa: BLE001 - e.g. symmetric memory unavailable: NCCL from now on
+                self.peer_failed = f"{type(exc).__name__}: {exc}"
+                self.peer_reducer = None
         done = False
         if len(tensors) > 1 and tensors[0].is_cuda:
             try:     # one NCCL launch for all of them (coalesced group)
@@ -561,6 +579,9 @@ class GradSync:
         for w_ in self._works:
             w_.wait()          # (stream-level wait: the host does not block)
         self._works = []
+        if not self._joined:
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+            self._joined = True
 
 
 GRAD_SYNC: GradSync | None = None

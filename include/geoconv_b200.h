@@ -241,6 +241,22 @@ int gcb_conv_amp_bwd(const float* grad_z, const float* z, const int32_t* argmax,
  * GEMM (geoconv_b200/distributed.py).  Only where gcb_conv_amp_bwd_can_split() returns 1. */
 int gcb_conv_amp_bwd_can_split(int32_t R, int32_t A, int32_t F, int32_t T, int precision, int has_neighbor);
 
+/* ---- data-parallel weight-gradient all-reduce over NVLink peer memory ------------
+ * The reference has no multi-GPU mode; this is the one exchange step of the batch-of-meshes mode.  Up to three
+ * gradient tensors (d_w_eff, d_w_self, d_bias; g1 / g2 may be NULL) are summed over `world` ranks IN PLACE by one
+ * kernel working on directly mapped peer buffers (two-shot: every rank reduces its slice of the flattened
+ * gradients over all ranks in rank order - fixed order, bit-identical on every rank - and delivers it to all).
+ * peer_bufs_dev: device array of `world` addresses, entry q = rank q's symmetric buffer of
+ * gcb_peer_allreduce_bytes() bytes mapped into this process (e.g. torch.distributed._symmetric_memory), zeroed
+ * once before first use; the same buffers serve every later call (the epoch lives in them, so the launch can be
+ * replayed from a CUDA graph).  Every rank must make the same calls in the same order.  n_ctas (default 12): the
+ * kernel is meant to run beside the dSignal GEMM on the SMs gcb_yield_sms leaves free.  A peer that never arrives
+ * raises an error word after ~2 s instead of hanging: the uint32 at byte offset
+ * align256(2 * n_pad * 4) + (2 * world + 4) * 4 of this rank's buffer, n_pad = n_elements rounded up to 4.  */
+size_t gcb_peer_allreduce_bytes(int64_t n_elements, int32_t world);
+int gcb_peer_allreduce(float* g0, int64_t n0, float* g1, int64_t n1, float* g2, int64_t n2,
+                       const uint64_t* peer_bufs_dev, int32_t rank, int32_t world, int32_t n_ctas, void* stream);
+
 /* ---- vertex-row sharding helper (halo exchange) ---------------------------
  * out[i,:] = src[rows[i],:]  (packs the signal rows a peer asked for into a send buffer). */
 int gcb_pack_rows(const float* src, const int32_t* rows, int32_t n_rows, int32_t F, float* out,
