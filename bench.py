@@ -501,7 +501,7 @@ def run_ours(args):
     # be captured in a CUDA graph the step is replayed without it and the gradients are reduced after the replay.
     grad_sync = {"ctx": None, "mode": "none"}
     if world > 1 and args.overlap_allreduce:
-        grad_sync["ctx"] = overlapped_grad_sync(max_ctas=args.allreduce_ctas)
+        grad_sync["ctx"] = overlapped_grad_sync(max_ctas=args.allreduce_ctas, peer=bool(args.peer_allreduce))
         grad_sync["ctx"].__enter__()
         grad_sync["mode"] = "all-reduce inside the backward (after the weight-gradient stage, beside the dSignal GEMM)"
     elif world > 1:
@@ -807,6 +807,13 @@ def run_ours(args):
             torch.cuda.synchronize()
             e2e_ms = e2e_serial_ms
 
+    if grad_sync["ctx"] is not None:
+        sync_obj = grad_sync["ctx"].sync
+        if sync_obj.peer_reducer is not None and sync_obj.peer_reducer.calls:
+            grad_sync["mode"] += ("; collective = gcb_peer_allreduce_staged, the library's own two-shot all-reduce kernel on "
+                                  "NVLink peer memory (12 CTAs beside the dSignal GEMM)")
+        else:
+            grad_sync["mode"] += f"; collective = NCCL on a low-CTA high-priority communicator ({sync_obj.peer_failed or 'peer kernel not used'})"
     extra = {}
     if args.extras:
         if grad_sync["ctx"] is not None:       # the extras synchronise their gradients themselves
@@ -949,6 +956,8 @@ def main():
     ap.add_argument("--graph", type=int, default=1, help="1: replay the resident step from a CUDA graph (default)")
     ap.add_argument("--overlap-allreduce", type=int, default=1,
                     help="1: N > 1 starts the weight-gradient all-reduce inside the backward (default); 0: after the step")
+    ap.add_argument("--peer-allreduce", type=int, default=1,
+                    help="1: the in-backward all-reduce is the library's own NVLink peer-memory kernel (default); 0: NCCL")
     ap.add_argument("--allreduce-ctas", type=int, default=8, help="CTA cap of the in-backward all-reduce's NCCL communicator")
     ap.add_argument("--extras", type=int, default=1, help="1: also measure the TF32 mode (N = 1) and configs 4 / 5 (default)")
     ap.add_argument("--e2e-pipeline", type=int, default=1,

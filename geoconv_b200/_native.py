@@ -66,6 +66,7 @@ SIGNATURES = {
     "gcb_pack_rows": (_int, [_p, _p, _i32, _i32, _p, _p]),
     "gcb_peer_allreduce_bytes": (_sz, [_i64, _i32]),
     "gcb_peer_allreduce": (_int, [_p, _i64, _p, _i64, _p, _i64, _p, _i32, _i32, _i32, _p]),
+    "gcb_peer_allreduce_staged": (_int, [_i64, _p, _i32, _i32, _i32, _p]),
 }
 
 _lib = None

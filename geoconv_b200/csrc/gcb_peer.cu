@@ -34,6 +34,8 @@ struct PeerParams {
   long long out_off;          // float offset of OUT inside a symmetric buffer (S starts at 0)
   long long flag_off;         // byte offset of the flag block: uint32 ready[world], delivered[world], then
                               // {epoch, ticket0, ticket1, ticket2, error} (local words, never written by peers)
+  int staged;                 // 1: the caller has already written its gradients into S_r and takes the sums from OUT_r
+                              // (no copies in this kernel: the backward writes its weight gradients straight into S_r)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
@@ -65,7 +67,12 @@ __device__ __forceinline__ bool peer_wait_all(const unsigned* flags, int world, 
   return true;
 }
 
+// WC = compile-time cap of the world size; U = 16 / WC slice elements per thread and iteration, so that 16 loads of
+// 16 bytes are in flight per thread whatever the world size (NVLink round trips are ~2 us: with one element per
+// iteration the first version needed 187 us for 8.6 MB on 12 CTAs at 2 ranks)
+template <int WC>
 __global__ void __launch_bounds__(PEER_THREADS) k_peer_allreduce(const PeerParams p) {
+  constexpr int U = 16 / WC;
   float* const seg[3] = {p.seg_ptr[0], p.seg_ptr[1], p.seg_ptr[2]};
   char* const mine = reinterpret_cast<char*>(p.bufs[p.rank]);
   unsigned* const ready = reinterpret_cast<unsigned*>(mine + p.flag_off);
@@ -76,10 +83,20 @@ __global__ void __launch_bounds__(PEER_THREADS) k_peer_allreduce(const PeerParam
   const long long n4 = p.n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x, tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 
-  // ---- phase 0: local gradients -> S_r ----
+  // ---- phase 0: local gradients -> S_r (skipped when the caller staged them itself) ----
   float4* const s_me = reinterpret_cast<float4*>(mine);
-  for (long long i = tid0; i < n4; i += stride) s_me[i] = *peer_seg_addr(p, i << 2, seg);
-  __threadfence_system();
+  if (!p.staged) {
+    for (long long i0 = tid0; i0 < n4; i0 += 8 * stride) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u * stride < n4) v[u] = *peer_seg_addr(p, (i0 + u * stride) << 2, seg);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u * stride < n4) s_me[i0 + u * stride] = v[u];
+    }
+    __threadfence_system();
+  }
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(state + 1, 1u) == gridDim.x - 1;
   __syncthreads();
@@ -92,19 +109,26 @@ __global__ void __launch_bounds__(PEER_THREADS) k_peer_allreduce(const PeerParam
   // ---- phase 1: reduce this rank's slice over all ranks, deliver it to everybody ----
   peer_wait_all(ready, p.world, epoch, state + 4);
   const long long lo4 = n4 * p.rank / p.world, hi4 = n4 * (p.rank + 1) / p.world;
-  for (long long i = lo4 + tid0; i < hi4; i += stride) {
-    float4 v[PEER_MAX_WORLD];
+  for (long long i0 = lo4 + tid0; i0 < hi4; i0 += U * stride) {
+    float4 v[U][WC];
 #pragma unroll
-    for (int q = 0; q < PEER_MAX_WORLD; ++q)
-      if (q < p.world) v[q] = __ldcg(reinterpret_cast<const float4*>(p.bufs[q]) + i);
-    float4 acc = v[0];
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-    for (int q = 1; q < PEER_MAX_WORLD; ++q)
-      if (q < p.world) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+      for (int q = 0; q < WC; ++q)
+        if (q < p.world && i0 + u * stride < hi4) v[u][q] = __ldcg(reinterpret_cast<const float4*>(p.bufs[q]) + i0 + u * stride);
 #pragma unroll
-    for (int q = 0; q < PEER_MAX_WORLD; ++q)
-      if (q < p.world && q != p.rank) (reinterpret_cast<float4*>(p.bufs[q]) + (p.out_off >> 2))[i] = acc;
-    *peer_seg_addr(p, i << 2, seg) = acc;
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= hi4) break;
+      float4 acc = v[u][0];
+#pragma unroll
+      for (int q = 1; q < WC; ++q)
+        if (q < p.world) { acc.x += v[u][q].x; acc.y += v[u][q].y; acc.z += v[u][q].z; acc.w += v[u][q].w; }
+#pragma unroll
+      for (int q = 0; q < WC; ++q)
+        if (q < p.world && (p.staged || q != p.rank)) (reinterpret_cast<float4*>(p.bufs[q]) + (p.out_off >> 2))[i] = acc;
+      if (!p.staged) *peer_seg_addr(p, i << 2, seg) = acc;
+    }
   }
   __threadfence_system();
   __syncthreads();
@@ -116,11 +140,24 @@ __global__ void __launch_bounds__(PEER_THREADS) k_peer_allreduce(const PeerParam
     if (threadIdx.x == 0) state[2] = 0u;
   }
 
-  // ---- phase 2: the other ranks' slices -> local gradient tensors ----
+  // ---- phase 2: all slices have arrived in OUT_r; unless staged, copy the other ranks' slices into the local tensors ----
   peer_wait_all(delivered, p.world, epoch, state + 4);
-  const float4* const out_me = reinterpret_cast<const float4*>(mine) + (p.out_off >> 2);
-  for (long long i = tid0; i < n4; i += stride)
-    if (i < lo4 || i >= hi4) *peer_seg_addr(p, i << 2, seg) = __ldcg(out_me + i);
+  if (!p.staged) {
+    const float4* const out_me = reinterpret_cast<const float4*>(mine) + (p.out_off >> 2);
+    for (long long i0 = tid0; i0 < n4; i0 += 8 * stride) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < n4 && (i < lo4 || i >= hi4)) v[u] = __ldcg(out_me + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < n4 && (i < lo4 || i >= hi4)) *peer_seg_addr(p, i << 2, seg) = v[u];
+      }
+    }
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -141,6 +178,33 @@ extern "C" size_t gcb_peer_allreduce_bytes(int64_t n_elements, int32_t world) {
   return align_up(2 * n * sizeof(float), 256) + align_up((size_t)(2 * world + 8) * sizeof(unsigned), 256);
 }
 
+static int peer_launch(const PeerParams& p, int n_ctas, cudaStream_t st) {
+  if (n_ctas < 1) n_ctas = 12;
+  if (n_ctas > 64) n_ctas = 64;   // all CTAs must be resident together: the phases hand over through tickets and flags
+  if (p.world <= 2) k_peer_allreduce<2><<<n_ctas, PEER_THREADS, 0, st>>>(p);
+  else if (p.world <= 4) k_peer_allreduce<4><<<n_ctas, PEER_THREADS, 0, st>>>(p);
+  else if (p.world <= 8) k_peer_allreduce<8><<<n_ctas, PEER_THREADS, 0, st>>>(p);
+  else k_peer_allreduce<16><<<n_ctas, PEER_THREADS, 0, st>>>(p);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
+extern "C" int gcb_peer_allreduce_staged(int64_t n_elements, const uint64_t* peer_bufs_dev, int32_t rank, int32_t world,
+                                         int32_t n_ctas, void* stream) {
+  GCB_REQUIRE(n_elements > 0 && n_elements % 4 == 0 && peer_bufs_dev, GCB_EINVAL, "gcb_peer_allreduce_staged: bad argument");
+  GCB_REQUIRE(world >= 1 && world <= PEER_MAX_WORLD && rank >= 0 && rank < world, GCB_EINVAL,
+              "gcb_peer_allreduce_staged: rank %d / world %d out of range (at most %d ranks)", rank, world, PEER_MAX_WORLD);
+  PeerParams p{};
+  p.n = n_elements;
+  p.seg_end[0] = p.seg_end[1] = p.seg_end[2] = n_elements;
+  p.bufs = reinterpret_cast<const unsigned long long*>(peer_bufs_dev);
+  p.rank = rank; p.world = world;
+  p.out_off = p.n;
+  p.flag_off = (long long)align_up(2 * (size_t)p.n * sizeof(float), 256);
+  p.staged = 1;
+  return peer_launch(p, n_ctas, (cudaStream_t)stream);
+}
+
 extern "C" int gcb_peer_allreduce(float* g0, int64_t n0, float* g1, int64_t n1, float* g2, int64_t n2,
                                   const uint64_t* peer_bufs_dev, int32_t rank, int32_t world, int32_t n_ctas,
                                   void* stream) {
@@ -158,9 +222,6 @@ extern "C" int gcb_peer_allreduce(float* g0, int64_t n0, float* g1, int64_t n1, 
   p.rank = rank; p.world = world;
   p.out_off = p.n;
   p.flag_off = (long long)align_up(2 * (size_t)p.n * sizeof(float), 256);
-  if (n_ctas < 1) n_ctas = 12;
-  if (n_ctas > 64) n_ctas = 64;   // all CTAs must be resident together: the phases hand over through tickets and flags
-  k_peer_allreduce<<<n_ctas, PEER_THREADS, 0, (cudaStream_t)stream>>>(p);
-  GCB_LAUNCH_OK();
-  return GCB_OK;
+  p.staged = 0;
+  return peer_launch(p, n_ctas, (cudaStream_t)stream);
 }

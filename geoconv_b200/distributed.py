@@ -88,6 +88,33 @@ class PeerAllReduce:
         off = (2 * n_pad * 4 + 255) // 256 * 256 + (2 * self.world + 4) * 4
         return int(buf[off:off + 4].view(torch.int32).item())
 
+    def staging(self, sizes, device):
+        """Views of this rank's peer-readable staging area, one per size: a producer that writes its gradients there
+        (instead of into private tensors) saves the all-reduce kernel both of its local copies (`reduce_staged`)."""
+        n = sum(sizes)
+        buf, _hdl, _nbytes = self._buffer(n, device)
+        flat = buf[:n * 4].view(torch.float32)
+        out, off = [], 0
+        for k in sizes:
+            out.append(flat[off:off + k])
+            off += k
+        return out
+
+    def reduce_staged(self, n: int, device, stream=None):
+        """All-reduce what `staging` views hold; the sums are in `result(n)` once `stream` has passed the kernel."""
+        from . import _native
+        lib = _native.load()
+        _buf, hdl, _nbytes = self._buffer(n, device)
+        st = stream if stream is not None else torch.cuda.current_stream(device)
+        with torch.cuda.device(device):
+            _native.check(lib.gcb_peer_allreduce_staged(n, hdl.buffer_ptrs_dev, self.rank, self.world, self.n_ctas,
+                                                        st.cuda_stream), "gcb_peer_allreduce_staged")
+        self.calls += 1
+
+    def result(self, n: int, device):
+        buf, _hdl, _nbytes = self._buffer(n, device)
+        return buf[n * 4:2 * n * 4].view(torch.float32)
+
     def __call__(self, tensors, stream=None):
         """Sum `tensors` (<= 3 contiguous fp32 CUDA tensors, each a multiple of 4 elements) over the ranks in place,
         on `stream` (default: the current stream)."""

@@ -463,9 +463,17 @@ def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: tor
     has_nb = w_eff is not None
     d_x = torch.empty_like(x) if need_dx and stages != 1 else None
     w_stage = stages != 2
-    d_w_eff = torch.empty((t, r, a, f) if w_stage else (0,), dtype=torch.float32, device=dev)
-    d_w_self = torch.empty((t, f) if w_stage else (0,), dtype=torch.float32, device=dev)
-    d_bias = torch.empty((t,) if w_stage else (0,), dtype=torch.float32, device=dev)
+    staged = None
+    if stages == 1 and GRAD_SYNC is not None and GRAD_SYNC.wants_staging(t % 4 == 0):
+        # data parallel, peer-memory all-reduce: the weight gradients are written straight into this rank's
+        # peer-readable staging area (no copy on either side of the collective)
+        staged = GRAD_SYNC.peer_reducer.staging([t * r * a * f, t * f, t], dev)
+    if staged is not None:
+        d_w_eff, d_w_self, d_bias = staged[0].view(t, r, a, f), staged[1].view(t, f), staged[2]
+    else:
+        d_w_eff = torch.empty((t, r, a, f) if w_stage else (0,), dtype=torch.float32, device=dev)
+        d_w_self = torch.empty((t, f) if w_stage else (0,), dtype=torch.float32, device=dev)
+        d_bias = torch.empty((t,) if w_stage else (0,), dtype=torch.float32, device=dev)
     ws_bytes = lib.gcb_conv_amp_bwd_workspace_bytes(v_out, v_src, r, a, f, t, precision)
     ws = ws_in if ws_in is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     st = _stream(x)
@@ -541,10 +549,16 @@ class GradSync:
         self._side = None
         self._joined = True
 
+    def wants_staging(self, sizes_ok: bool) -> bool:
+        return bool(self.active and self.peer_reducer is not None and sizes_ok)
+
     def reduce_early(self, tensors):
+        """Start the sum of `tensors` over the ranks; returns None (reduced in place once `join` has run) or, when
+        the tensors are views of the peer reducer's staging area, a callable that returns private copies of the sums
+        (call it after `join`)."""
         import torch.distributed as dist
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
-            return
+            return None
         tensors = [t_ for t_ in tensors if t_.numel()]
         if self.peer_reducer is not None and tensors and tensors[0].is_cuda and len(tensors) <= 3 and \
                 all(t_.numel() % 4 == 0 and t_.is_contiguous() for t_ in tensors):
@@ -553,10 +567,27 @@ class GradSync:
                 if self._side is None:
                     self._side = torch.cuda.Stream(device=dev, priority=-1)
                 self._side.wait_stream(torch.cuda.current_stream(dev))      # stage one (weight gradients) is enqueued
+                sizes = [t_.numel() for t_ in tensors]
+                n = sum(sizes)
+                stage = self.peer_reducer.staging(sizes, dev)
+                if all(t_.data_ptr() == s_.data_ptr() for t_, s_ in zip(tensors, stage)):
+                    self.peer_reducer.reduce_staged(n, dev, stream=self._side)
+                    shapes = [tuple(t_.shape) for t_ in tensors]
+
+                    def take():
+                        flat = self.peer_reducer.result(n, dev).clone()
+                        out, off = [], 0
+                        for k, shp in zip(sizes, shapes):
+                            out.append(flat[off:off + k].view(shp))
+                            off += k
+                        return out
+                    self._joined = False
+                    self.early_reductions += 1
+                    return take
                 self.peer_reducer(tensors, stream=self._side)
                 self._joined = False
                 self.early_reductions += 1
-                return
+                return None
             except Exception as exc:  # noqa: BLE001 - e.g. symmetric memory unavailable: NCCL from now on
                 self.peer_failed = f"{type(exc).__name__}: {exc}"
                 self.peer_reducer = None
@@ -574,6 +605,7 @@ class GradSync:
             for t_ in tensors:
                 self._works.append(dist.all_reduce(t_, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self.early_reductions += 1
+        return None
 
     def join(self):
         for w_ in self._works:
@@ -638,9 +670,11 @@ def _conv_backward(ctx, grad_y, grad_z, _grad_arg, _grad_stats):
             N.load().gcb_conv_amp_bwd_can_split(idx.shape[1], idx.shape[2], x.shape[1], w_self.shape[0], ctx.precision, 1)):
         # data parallel: weight gradients first, their all-reduce (collective stream) beside the dSignal GEMM
         _none, d_w_eff, d_w_self, d_bias, ws = conv_bwd_op(*args, 1, None)
-        sync.reduce_early([d_w_eff, d_w_self, d_bias])
+        staged = sync.reduce_early([d_w_eff, d_w_self, d_bias])
         d_x = conv_bwd_op(*args, 2, ws)[0]
         sync.join()
+        if staged is not None:       # the sums sit in the collective's result area: private copies for autograd
+            d_w_eff, d_w_self, d_bias = staged()
     else:
         d_x, d_w_eff, d_w_self, d_bias, _ws = conv_bwd_op(*args, 3, None)
     g_anchor = torch.zeros(ctx.anchor_shape, dtype=torch.float32, device=x.device) if ctx.has_anchor else None

@@ -256,6 +256,11 @@ int gcb_conv_amp_bwd_can_split(int32_t R, int32_t A, int32_t F, int32_t T, int p
 size_t gcb_peer_allreduce_bytes(int64_t n_elements, int32_t world);
 int gcb_peer_allreduce(float* g0, int64_t n0, float* g1, int64_t n1, float* g2, int64_t n2,
                        const uint64_t* peer_bufs_dev, int32_t rank, int32_t world, int32_t n_ctas, void* stream);
+/* The same without the two local copies: the caller has written its n_elements (multiple of 4) gradient values to
+ * the first n_elements floats of ITS buffer (e.g. by passing pointers into it as d_w_eff / d_w_self / d_bias of
+ * gcb_conv_amp_bwd) and finds the sums in the following n_elements floats when the kernel has finished.        */
+int gcb_peer_allreduce_staged(int64_t n_elements, const uint64_t* peer_bufs_dev, int32_t rank, int32_t world,
+                              int32_t n_ctas, void* stream);
 
 /* ---- vertex-row sharding helper (halo exchange) ---------------------------
  * out[i,:] = src[rows[i],:]  (packs the signal rows a peer asked for into a send buffer). */
