@@ -515,6 +515,10 @@ def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: tor
                 calls += 1
     if d_x is None:
         d_x = x.new_empty((0,))
+    if staged is not None:
+        # (an operator's outputs may not share storage: the gradients stay where they were written - the caller
+        # takes the views from the reducer - and empty placeholders are returned)
+        d_w_eff, d_w_self, d_bias = x.new_empty((0,)), x.new_empty((0,)), x.new_empty((0,))
     return d_x, d_w_eff, d_w_self, d_bias, (ws if stages == 1 else x.new_empty((0,), dtype=torch.uint8))
 
 
@@ -670,6 +674,10 @@ def _conv_backward(ctx, grad_y, grad_z, _grad_arg, _grad_stats):
             N.load().gcb_conv_amp_bwd_can_split(idx.shape[1], idx.shape[2], x.shape[1], w_self.shape[0], ctx.precision, 1)):
         # data parallel: weight gradients first, their all-reduce (collective stream) beside the dSignal GEMM
         _none, d_w_eff, d_w_self, d_bias, ws = conv_bwd_op(*args, 1, None)
+        if d_w_eff.numel() == 0:     # written into the peer reducer's staging area (see conv_bwd_op)
+            t_, r_, a_, f_ = w_self.shape[0], idx.shape[1], idx.shape[2], x.shape[1]
+            st_ = sync.peer_reducer.staging([t_ * r_ * a_ * f_, t_ * f_, t_], x.device)
+            d_w_eff, d_w_self, d_bias = st_[0].view(t_, r_, a_, f_), st_[1].view(t_, f_), st_[2]
         staged = sync.reduce_early([d_w_eff, d_w_self, d_bias])
         d_x = conv_bwd_op(*args, 2, ws)[0]
         sync.join()

@@ -192,3 +192,49 @@ def test_sharded_layer_matches_unsharded_on_gpu():
         dx[halo_rows.to(dev)] += full.grad[hi - lo:]
     assert nerr(dx, ref_dx) < TOL_FP32
     assert nerr(layer._template_neighbor_weights.grad, ref_dw) < TOL_FP32     # accumulated over shards
+
+
+@pytest.mark.gpu
+def test_peer_allreduce_kernel_single_rank():
+    """gcb_peer_allreduce / gcb_peer_allreduce_staged with world = 1 on an ordinary buffer: the kernel's phases, flags
+    and device-side epoch run (three calls, then three CUDA-graph replays) and the sum over one rank is the identity.
+    The multi-rank behaviour is checked over real NVLink by tools/peer_allreduce_check.py (profiles/)."""
+    from geoconv_b200 import _native
+    lib = _native.load()
+    dev = torch.device("cuda:0")
+    sizes = [4096 * 12, 512, 96]
+    n = sum(sizes)
+    buf = torch.zeros(lib.gcb_peer_allreduce_bytes(n, 1), dtype=torch.uint8, device=dev)
+    ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for rep in range(3):
+        g = [torch.randn(k, device=dev) for k in sizes]
+        want = [t.clone() for t in g]
+        _native.check(lib.gcb_peer_allreduce(g[0].data_ptr(), sizes[0], g[1].data_ptr(), sizes[1], g[2].data_ptr(), sizes[2],
+                                             ptrs.data_ptr(), 0, 1, 4, st), "gcb_peer_allreduce")
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(g, want))
+    flat = buf[:n * 4].view(torch.float32)
+    out = buf[n * 4:2 * n * 4].view(torch.float32)
+    src = torch.randn(n, device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        flat.copy_(src)
+        _native.check(lib.gcb_peer_allreduce_staged(n, ptrs.data_ptr(), 0, 1, 4, side.cuda_stream), "staged")
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert torch.equal(out, src)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        flat.mul_(2.0)
+        _native.check(lib.gcb_peer_allreduce_staged(n, ptrs.data_ptr(), 0, 1, 4, torch.cuda.current_stream().cuda_stream),
+                      "staged (captured)")
+    for rep in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, flat)
+    n_pad = (n + 3) // 4 * 4
+    off = (2 * n_pad * 4 + 255) // 256 * 256 + (2 * 1 + 4) * 4
+    assert int(buf[off:off + 4].view(torch.int32).item()) == 0          # error word clear
+    assert int(buf[off - 16:off - 12].view(torch.int32).item()) == 7      # epoch: 3 + 1 + 3 calls completed
