@@ -21,7 +21,8 @@ import torch
 import torch.distributed as dist
 
 from geoconv_b200 import synthetic as S
-from geoconv_b200.distributed import allreduce_gradients, build_shard_plans, sharded_layer_forward
+from geoconv_b200.distributed import (ShardedForward, allreduce_gradients, build_shard_plans, overlapped_grad_sync,
+                                      sharded_layer_forward)
 from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
 from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
 
@@ -105,6 +106,41 @@ def main():
     out.append({"check": "S3 data-parallel weight gradients vs one rank", "world": world, "meshes": args.meshes,
                 "max_normalised_err": err, "ok": err < 1e-5, "ms_per_step": ms,
                 "vertices_per_s": args.meshes * v / (ms * 1e-3)})
+
+    # ---------------- S1: weight-gradient all-reduce started inside the backward ----------------
+    # (the library's own NVLink peer-memory kernel when symmetric memory is available, else NCCL on a low-CTA group)
+    from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling as AMP
+    f1, t1 = 544, 96
+    torch.manual_seed(3)
+    layer1 = ConvGeodesic(input_shape=[(None, f1), (None, r, a, 3, 2)], amt_templates=t1, template_radius=0.028).to(dev)
+    x1 = S.make_signal(v, f1, seed=200 + rank).to(dev)
+    b1 = S.make_bary(v, r, a, seed=200 + rank).to(dev)
+    gz1 = torch.randn((v, t1), generator=torch.Generator().manual_seed(300 + rank)).to(dev)
+
+    def one_step():
+        for p in layer1.parameters():
+            p.grad = None
+        xs = x1.clone().requires_grad_(True)
+        AMP()(layer1([xs, b1])).backward(gz1)
+        return xs.grad
+    dx_plain = one_step()
+    want = [p.grad.clone() for p in layer1.parameters()]
+    for g_ in want:
+        dist.all_reduce(g_)
+    with overlapped_grad_sync() as sync:
+        for _ in range(3):                     # repeated steps reuse the peer buffers (device-side epoch)
+            dx_sync = one_step()
+        torch.cuda.synchronize()
+        got = [p.grad.clone() for p in layer1.parameters()]
+        used_peer = sync.peer_reducer is not None and sync.peer_reducer.calls > 0
+        peer_failed = sync.peer_failed
+    err = max(nerr(x_, y_) for x_, y_ in zip(got, want))
+    flags = torch.tensor([err, nerr(dx_sync, dx_plain)], device=dev, dtype=torch.float64)
+    dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+    out.append({"check": "S1 weight gradients reduced inside the backward vs NCCL all-reduce of the local gradients",
+                "world": world, "peer_memory_kernel": used_peer, "peer_fallback_reason": peer_failed,
+                "max_normalised_err": flags[0].item(), "d_signal_unchanged_err": flags[1].item(),
+                "ok": flags[0].item() < 1e-6 and flags[1].item() == 0.0})
 
     # ---------------- S4: vertex-row shards + halo exchange ----------------
     f = t = 128
