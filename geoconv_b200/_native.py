@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgeoconv_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_ROT = 32
 
 PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_F16X3 = 0, 1, 2, 3
@@ -55,6 +55,9 @@ SIGNATURES = {
     "gcb_amp_fwd": (_int, [_p, _i32, _i32, _i32, _p, _p, _p]),
     "gcb_amp_bwd": (_int, [_p, _p, _i32, _i32, _i32, _p, _p]),
     "gcb_bary_from_gpc": (_int, [_p, _p, _p, _i32, _p, _i32, _p, _p]),
+    "gcb_gpc_smem_per_system": (_i64, [_i32]),
+    "gcb_gpc_wavefront": (_int, [_p, _p, _p, _p, _p, _i32, _p, _i32, C.c_double, C.c_double, _i32, _p, _p, _p, _p,
+                                 _p, _p, _p, _p, _p]),
     "gcb_apool_fwd": (_int, [_p, _i32, _i32, _i32, _int, _p, _p, _p]),
     "gcb_apool_bwd": (_int, [_p, _p, _i32, _i32, _i32, _int, _p, _p]),
     "gcb_act_grad": (_int, [_p, _p, _i64, _int, _p, _p]),

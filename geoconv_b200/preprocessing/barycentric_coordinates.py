@@ -75,5 +75,7 @@ def compute_barycentric_coordinates(gpc_systems, n_radial=2, n_angular=4, radius
     """Same call and same result layout as the reference (barycentric_coordinates.py:127-175): a float64 numpy
     array B[v, r, a, :, 0] = vertex indices, B[v, r, a, :, 1] = barycentric weights of the first triangle of
     GPC system v that contains template vertex (r, a); zeros if none does."""
-    packed = pack_gpc_triangles(gpc_systems)
+    packed = getattr(gpc_systems, "packed", None)   # geoconv_b200's GPCSystemGroup: already packed, on the device
+    if packed is None:
+        packed = pack_gpc_triangles(gpc_systems)
     return barycentric_from_packed(*packed, n_radial, n_angular, radius, device=device).cpu().numpy()

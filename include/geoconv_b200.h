@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GCB_ABI_VERSION 6
+#define GCB_ABI_VERSION 7
 #define GCB_MAX_ROT 32
 
 /* error codes */
@@ -86,6 +86,34 @@ int gcb_tc_half_supported(int32_t R, int32_t A, int32_t F, int32_t T, int32_t n_
  * zeros where no triangle contains the template vertex.                                     */
 int gcb_bary_from_gpc(const double* tri_xy, const int32_t* tri_idx, const int64_t* tri_ptr, int32_t V,
                       const double* template_xy, int32_t RA, double* bary_out, void* stream);
+
+/* ---- mesh -> GPC systems (the wavefront; the step before gcb_bary_from_gpc) ----------------
+ * Replaces, for all source vertices in one launch, GPCSystemGroup.compute_gpc_system
+ * (geoconv/preprocessing/gpc_system_group.py:42-122) with GPCSystem (gpc_system.py:12-337),
+ * compute_distance_and_angle (gpc_system_utils.py:150-212) and the reference's C extension
+ * (preprocessing/c_extension/c_extension.c:11-145).  One warp per source vertex, float64.
+ * Mesh tables: vertices / normals [n_vertices,3] f64; nbr_ptr [n_vertices+1], nbr [nnz] i32 = the
+ * neighbours of every vertex in ASCENDING vertex id (the first one is a system's reference
+ * direction); opposite [nnz,2] i32 = for the edge {v, nbr} the third vertex of its first / second
+ * incident face in ascending face index, -1 where there is none (boundary edge).
+ * sources [n_sources] i32 (NULL = vertices 0 .. n_sources-1).  u_max / eps as in the reference
+ * (GPCSystemGroup(eps=1e-6).compute(u_max=0.04)).  max_patch in [8, 1023] = capacity of a system's
+ * vertex table; a system owns max_patch rows of out_vid / out_rho / out_theta and 3*max_patch rows
+ * of out_tri [.,3] i32 (vertex ids, sorted) / out_xy [.,3,2] f64 (cartesian GPC coordinates), filled
+ * in the order the reference inserts them; out_nv / out_nf [n_sources] i32 say how many.  Vertices
+ * the wavefront touched but never accepted keep rho = inf, theta = -1 (the reference's fill
+ * values).  out_flags [n_sources] i32: GCB_GPC_* bits.                                         */
+#define GCB_GPC_OVERFLOW 1    /* a table was too small: raise max_patch (results of that system are partial) */
+#define GCB_GPC_NONMANIFOLD 2 /* an edge with more than two faces                                */
+#define GCB_GPC_FRAGILE 4     /* the crossing guard judged collinear segments: a verdict that is rounding
+                                 noise in the reference as well (gpc_system.py:322-337)           */
+int64_t gcb_gpc_smem_per_system(int32_t max_patch);
+int gcb_gpc_wavefront(const double* vertices, const double* normals, const int32_t* nbr_ptr,
+                      const int32_t* nbr, const int32_t* opposite, int32_t n_vertices,
+                      const int32_t* sources, int32_t n_sources, double u_max, double eps,
+                      int32_t max_patch, int32_t* out_nv, int32_t* out_vid, double* out_rho,
+                      double* out_theta, int32_t* out_nf, int32_t* out_tri, double* out_xy,
+                      int32_t* out_flags, void* stream);
 
 /* ---- bary -> (idx, w) ------------------------------------------------------------------
  * Replaces conv_intrinsic.py:213-221 (cast to fp32, `[...,0].long()`, `[...,1]`).

@@ -17,7 +17,9 @@ def golden_cases(which="path"):
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
     if which == "gpc":     # §8(f-1) fixtures: GPC systems -> barycentric coordinates
         return [n for n in names if n.startswith("gpc_")]
-    names = [n for n in names if not n.startswith("gpc_")]
+    if which == "wave":    # §8(f-1) fixtures: mesh -> GPC systems (the wavefront)
+        return [n for n in names if n.startswith("wave_")]
+    names = [n for n in names if not n.startswith(("gpc_", "wave_"))]
     is_next = lambda n: n.split("_")[0] in NEXT_PREFIXES  # noqa: E731
     if which == "all":
         return names
