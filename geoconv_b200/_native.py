@@ -58,6 +58,11 @@ SIGNATURES = {
     "gcb_gpc_smem_per_system": (_i64, [_i32]),
     "gcb_gpc_wavefront": (_int, [_p, _p, _p, _p, _p, _i32, _p, _i32, C.c_double, C.c_double, _i32, _p, _p, _p, _p,
                                  _p, _p, _p, _p, _p]),
+    "gcb_bn_workspace_bytes": (_sz, [_i32, _i32]),
+    "gcb_bn_stats": (_int, [_p, _i32, _i32, C.c_float, _p, _p, _p, _p, C.c_float, _p, _sz, _p]),
+    "gcb_bn_dropout_fwd": (_int, [_p, _i32, _i32, _p, _p, _p, _p, C.c_float, C.c_uint64, C.c_uint64, _p, _p]),
+    "gcb_bn_dropout_bwd": (_int, [_p, _p, _i32, _i32, _p, _p, _p, _int, C.c_float, C.c_uint64, C.c_uint64, _p, _p, _p,
+                                  _p, _sz, _p]),
     "gcb_apool_fwd": (_int, [_p, _i32, _i32, _i32, _int, _p, _p, _p]),
     "gcb_apool_bwd": (_int, [_p, _p, _i32, _i32, _i32, _int, _p, _p]),
     "gcb_act_grad": (_int, [_p, _p, _i64, _int, _p, _p]),

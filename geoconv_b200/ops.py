@@ -809,3 +809,101 @@ def pack_rows(src: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
     """out[i] = src[rows[i]] (halo send-buffer packing)."""
     _need_cuda(src, "src")
     return pack_rows_op(src, rows)
+
+
+# ---- between two convolutions: BatchNorm1d -> Dropout (SURVEY.md §8 f-2) --------------------------
+_BN_WS: dict = {}
+
+
+def _bn_workspace(v: int, t: int, dev: torch.device) -> torch.Tensor:
+    """Column-reduction scratch; zeroed once (the kernels leave the ticket zero), grown on demand, per device."""
+    need = N.load().gcb_bn_workspace_bytes(v, t)
+    ws = _BN_WS.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+        if not torch.cuda.is_current_stream_capturing():
+            _BN_WS[dev] = ws
+    return ws
+
+
+@torch.library.custom_op(f"{_LIB}::bn_stats", mutates_args=("running_mean", "running_var"), device_types="cuda")
+def bn_stats_op(z: torch.Tensor, eps: float, running_mean: torch.Tensor | None, running_var: torch.Tensor | None,
+                momentum: float) -> tuple[torch.Tensor, torch.Tensor]:
+    """Per-feature (mean, 1/sqrt(biased var + eps)) of z (V, T), fixed summation order; the running estimates, when
+    given, are updated in place by the same kernel (torch's rule, unbiased variance)."""
+    lib = N.load()
+    z = z.contiguous()
+    v, t = z.shape
+    mean, invstd = (torch.empty(t, dtype=torch.float32, device=z.device) for _ in range(2))
+    ws = _bn_workspace(v, t, z.device)
+    with _dev_guard(z):
+        N.check(lib.gcb_bn_stats(z.data_ptr(), v, t, float(eps), mean.data_ptr(), invstd.data_ptr(),
+                                 _ptr(running_mean), _ptr(running_var), float(momentum), ws.data_ptr(), ws.numel(),
+                                 _stream(z)), "gcb_bn_stats")
+    return mean, invstd
+
+
+@bn_stats_op.register_fake
+def _(z, eps, running_mean, running_var, momentum):
+    t = z.shape[1]
+    return z.new_empty((t,)), z.new_empty((t,))
+
+
+@torch.library.custom_op(f"{_LIB}::bn_dropout", mutates_args=(), device_types="cuda")
+def bn_dropout_op(z: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                  training: bool, p: float, seed: int, stream_id: int) -> torch.Tensor:
+    """dropout_p(gamma * (z - mean) * invstd + beta) in one pass; the mask is a function of (seed, stream_id, element)."""
+    lib = N.load()
+    z = z.contiguous()
+    v, t = z.shape
+    out = torch.empty_like(z)
+    with _dev_guard(z):
+        N.check(lib.gcb_bn_dropout_fwd(z.data_ptr(), v, t, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                       beta.data_ptr(), float(p), seed, stream_id, out.data_ptr(), _stream(z)),
+                "gcb_bn_dropout_fwd")
+    return out
+
+
+@bn_dropout_op.register_fake
+def _(z, mean, invstd, gamma, beta, training, p, seed, stream_id):
+    return torch.empty_like(z)
+
+
+@torch.library.custom_op(f"{_LIB}::bn_dropout_bwd", mutates_args=(), device_types="cuda")
+def bn_dropout_bwd_op(d_out: torch.Tensor, z: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, gamma: torch.Tensor,
+                      training: bool, p: float, seed: int, stream_id: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    lib = N.load()
+    d_out, z = d_out.contiguous(), z.contiguous()
+    v, t = z.shape
+    d_z = torch.empty_like(z)
+    d_gamma, d_beta = (torch.empty(t, dtype=torch.float32, device=z.device) for _ in range(2))
+    ws = _bn_workspace(v, t, z.device)
+    with _dev_guard(z):
+        N.check(lib.gcb_bn_dropout_bwd(d_out.data_ptr(), z.data_ptr(), v, t, mean.data_ptr(), invstd.data_ptr(),
+                                       gamma.data_ptr(), int(training), float(p), seed, stream_id, d_z.data_ptr(),
+                                       d_gamma.data_ptr(), d_beta.data_ptr(), ws.data_ptr(), ws.numel(), _stream(z)),
+                "gcb_bn_dropout_bwd")
+    return d_z, d_gamma, d_beta
+
+
+@bn_dropout_bwd_op.register_fake
+def _(d_out, z, mean, invstd, gamma, training, p, seed, stream_id):
+    t = z.shape[1]
+    return torch.empty_like(z), z.new_empty((t,)), z.new_empty((t,))
+
+
+def _bn_dropout_setup(ctx, inputs, output):
+    z, mean, invstd, gamma, _beta, training, p, seed, stream_id = inputs
+    ctx.save_for_backward(z, mean, invstd, gamma)
+    ctx.cfg = (bool(training), float(p), int(seed), int(stream_id))
+
+
+def _bn_dropout_backward(ctx, d_out):
+    z, mean, invstd, gamma = ctx.saved_tensors
+    training, p, seed, stream_id = ctx.cfg
+    # in training mode mean / invstd are functions of z: the kernel's d_z is the full derivative, so they get none
+    d_z, d_gamma, d_beta = bn_dropout_bwd_op(d_out, z, mean, invstd, gamma, training, p, seed, stream_id)
+    return d_z, None, None, d_gamma, d_beta, None, None, None, None
+
+
+bn_dropout_op.register_autograd(_bn_dropout_backward, setup_context=_bn_dropout_setup)

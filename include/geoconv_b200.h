@@ -115,6 +115,33 @@ int gcb_gpc_wavefront(const double* vertices, const double* normals, const int32
                       double* out_theta, int32_t* out_nf, int32_t* out_tri, double* out_xy,
                       int32_t* out_flags, void* stream);
 
+/* ---- between two convolutions: BatchNorm1d -> Dropout ------------------------------------------
+ * The chain the reference's network runs between the pooled output of one block and the next
+ * convolution (geoconv_examples/mpi_faust/pytorch/model.py:93-105, :128-132: do -> isc -> amp -> bn).
+ * z, out, d_out, d_z [V,T] fp32 (T % 4 == 0, 16-byte aligned); mean, invstd, gamma, beta, d_gamma, d_beta [T].
+ * gcb_bn_stats: training-mode statistics of z (biased variance inside invstd = 1/sqrt(var + eps)), fixed
+ *   summation order; running_mean / running_var (both or neither, nullable) are updated in place as
+ *   torch does: new = (1 - momentum) * old + momentum * (mean | unbiased variance).
+ * gcb_bn_dropout_fwd: out = dropout_p(gamma * (z - mean) * invstd + beta); element e is kept (and scaled
+ *   by 1/(1-p)) iff word e%4 of Philox4x32-10(counter = (e/4, stream_id), key = seed) < (1-p) * 2^32.
+ *   The mask is never stored: gcb_bn_dropout_bwd regenerates it from (seed, stream_id).  p = 0: no dropout.
+ * gcb_bn_dropout_bwd: d_beta = sum dY, d_gamma = sum dY * xhat, and (training != 0)
+ *   d_z = gamma * invstd * (dY - d_beta/V - xhat * d_gamma/V), else d_z = gamma * invstd * dY, with
+ *   dY = mask * d_out / (1-p).
+ * workspace: gcb_bn_workspace_bytes(V, T); its first 256 bytes must be zero before the first use (the
+ * kernels leave them zero).                                                                      */
+size_t gcb_bn_workspace_bytes(int32_t V, int32_t T);
+int gcb_bn_stats(const float* z, int32_t V, int32_t T, float eps, float* mean, float* invstd,
+                 float* running_mean, float* running_var, float momentum, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int gcb_bn_dropout_fwd(const float* z, int32_t V, int32_t T, const float* mean, const float* invstd,
+                       const float* gamma, const float* beta, float p, uint64_t seed, uint64_t stream_id,
+                       float* out, void* stream);
+int gcb_bn_dropout_bwd(const float* d_out, const float* z, int32_t V, int32_t T, const float* mean,
+                       const float* invstd, const float* gamma, int training, float p, uint64_t seed,
+                       uint64_t stream_id, float* d_z, float* d_gamma, float* d_beta, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* ---- bary -> (idx, w) ------------------------------------------------------------------
  * Replaces conv_intrinsic.py:213-221 (cast to fp32, `[...,0].long()`, `[...,1]`).
  * bary: [n_slots, 2] fp32 or fp64 (n_slots = V_out*R*A*3).  idx = trunc-toward-zero of the fp32
