@@ -71,6 +71,9 @@ SIGNATURES = {
     "gcb_conv_bwd_workspace_selfcheck": (_int, [_i32, _i32, _i32, _i32, _i32, _i32, _int]),
     "gcb_conv_bwd": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _int, _i32, _i32, _i32, _i32, _i32, _i32, _int,
                             _int, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "gcb_conv_bwd_dense_supported": (_int, [_i32, _i32, _i32, _i32, _int]),
+    "gcb_conv_bwd_dense": (_int, [_p, _p, _p, _p, _p, _p, C.POINTER(_i32), _i32, _p, _p, _int, _i32, _i32, _i32, _i32, _i32,
+                                  _i32, _int, _int, _p, _p, _p, _p, _p, _sz, _p]),
     "gcb_pack_rows": (_int, [_p, _p, _i32, _i32, _p, _p]),
     "gcb_peer_allreduce_bytes": (_sz, [_i64, _i32]),
     "gcb_peer_allreduce": (_int, [_p, _i64, _p, _i64, _p, _i64, _p, _i32, _i32, _i32, _p]),

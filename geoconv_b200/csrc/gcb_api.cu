@@ -230,6 +230,33 @@ extern "C" int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, 
                        accumulate, d_x, st);
 }
 
+// ---- dense backward: a gradient for EVERY rotation (the layer used without AngularMaxPooling, or under min /
+// average pooling) in ONE pass through G instead of n_rot sparse backward calls --------------------------------
+extern "C" int gcb_conv_bwd_dense_supported(int32_t R, int32_t A, int32_t F, int32_t T, int precision) {
+  return precision != GCB_PREC_FP32 && tc_bwd_supported(R, A, F, T) && A <= GCB_MAX_ROT && T % 32 == 0 ? 1 : 0;
+}
+
+extern "C" int gcb_conv_bwd_dense(const float* x, const int32_t* idx, const float* w, const float* w_eff,
+                                  const float* w_self, const float* h_all, const int32_t* rot_off_host, int32_t n_rot,
+                                  const int32_t* csr_row_ptr, const int32_t* csr_entries, int csr_flags, int32_t v_out,
+                                  int32_t v_src, int32_t R, int32_t A, int32_t F, int32_t T, int precision,
+                                  int accumulate, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  GCB_REQUIRE(x && idx && w && w_eff && w_self && h_all && rot_off_host && csr_row_ptr && csr_entries, GCB_EINVAL,
+              "gcb_conv_bwd_dense: null input pointer");
+  GCB_REQUIRE(d_w_eff && d_w_self && d_bias, GCB_EINVAL, "gcb_conv_bwd_dense: null output pointer");
+  int rc = check_shape(v_out, v_src, R, A, F, T);
+  if (rc) return rc;
+  GCB_REQUIRE(v_out > 0 && n_rot > 0 && n_rot <= GCB_MAX_ROT, GCB_EINVAL, "gcb_conv_bwd_dense: bad sizes");
+  GCB_REQUIRE(gcb_conv_bwd_dense_supported(R, A, F, T, precision) && (csr_flags & GCB_CSR_RING_GROUPED), GCB_EUNSUPPORTED,
+              "gcb_conv_bwd_dense: needs the tensor-core backward, a ring-grouped CSR, A <= %d and T %% 32 == 0", GCB_MAX_ROT);
+  GCB_REQUIRE(workspace && workspace_bytes >= gcb_conv_bwd_workspace_bytes(v_out, v_src, R, A, F, T, precision),
+              GCB_EWORKSPACE, "gcb_conv_bwd_dense: workspace too small");
+  return tc_conv_bwd(x, idx, w, w_eff, w_self, h_all, nullptr, csr_row_ptr, csr_entries, v_out, v_src, R, A, F, T, precision,
+                     accumulate, nullptr, d_x, d_w_eff, d_w_self, d_bias, workspace, workspace_bytes, (cudaStream_t)stream,
+                     nullptr, true, 3, n_rot, rot_off_host);
+}
+
 // ---- AMP-sparse backward from (dZ, Z, argmax): one call, one preparation kernel ---------------------------------
 extern "C" size_t gcb_conv_amp_bwd_workspace_bytes(int32_t v_out, int32_t v_src, int32_t R, int32_t A, int32_t F,
                                                    int32_t T, int precision) {

@@ -70,10 +70,14 @@ TcGLayout tc_g_layout_max(int v_src, int R, int A, int F, int T, bool x3);
 // x_lo are then __half buffers with row strides kg_ld = align(kg, 64), x_ld = align(F, 64))
 size_t tc_bwd_scales_bytes();
 int tc_bwd_scales(const float* h, const float* w, const int32_t* csr_row_ptr, const float* w_eff, const float* w_self,
-                  const float* x, int v_out, int v_src, int R, int A, int F, int T, void* scratch, cudaStream_t st);
+                  const float* x, int v_out, int v_src, int R, int A, int F, int T, void* scratch, cudaStream_t st,
+                  int h_rows_per_vertex = 1);
+// dense_n_rot > 0: h = [v_out][dense_n_rot][T] (a gradient for every rotation, offsets dense_offsets on the host),
+// rot_sel unused
 int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int32_t* csr_row_ptr,
                const int32_t* csr_entries, int v_out, int v_src, int R, int A, int T, bool x3, float* g_hi,
-               float* g_lo, cudaStream_t st, const float* scales = nullptr, bool ring_sorted = false);
+               float* g_lo, cudaStream_t st, const float* scales = nullptr, bool ring_sorted = false,
+               int dense_n_rot = 0, const int32_t* dense_offsets = nullptr);
 int tc_dx_from_g(const float* g_hi, const float* g_lo, const float* wcat_hi, const float* wcat_lo, int v_src, int R,
                  int A, int F, int T, bool x3, int accumulate, float* d_x, cudaStream_t st,
                  const float* scales = nullptr);
@@ -103,6 +107,7 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
                 int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,
                 const float* interp /* nullable: I saved by the forward */, float* d_x, float* d_w_eff,
                 float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                const TcBwdAmp* amp = nullptr, bool csr_ring_grouped = false, int stages = 3);
+                const TcBwdAmp* amp = nullptr, bool csr_ring_grouped = false, int stages = 3, int dense_n_rot = 0,
+                const int32_t* dense_offsets = nullptr);
 
 }  // namespace gcb

@@ -655,7 +655,12 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
                 const float* h, const int32_t* rot_sel, const int32_t* csr_row_ptr, const int32_t* csr_entries,
                 int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,
                 const float* interp, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias, void* workspace,
-                size_t workspace_bytes, cudaStream_t st, const TcBwdAmp* amp, bool csr_ring_grouped, int stages) {
+                size_t workspace_bytes, cudaStream_t st, const TcBwdAmp* amp, bool csr_ring_grouped, int stages,
+                int dense_n_rot, const int32_t* dense_offsets) {
+  // dense_n_rot > 0: a gradient for every rotation, h = [v_out][dense_n_rot][T]; only the route through G serves it
+  GCB_REQUIRE(dense_n_rot == 0 || (!amp && w_eff && csr_row_ptr && csr_entries), GCB_EUNSUPPORTED,
+              "tc_conv_bwd: the dense backward runs through G (neighbour weights and the CSR inversion required)");
+  const int h_rows = dense_n_rot > 0 ? dense_n_rot : 1;   // rows of h per output vertex
   // fp16 operand splits (GCB_PREC_F16X3) serve the route through G; the centre-only and gather-fed routes run
   // the same precision request as 3xTF32
   static const bool no_half = getenv("GCB_BWD_NO_HALF") && atoi(getenv("GCB_BWD_NO_HALF")) != 0;   // A/B measurements
@@ -792,7 +797,7 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     if (half) {   // fp16 buffers: rows of kg_ld halves (they fit in the 3xTF32 sizes)
       g_lo = (float*)((__half*)g_hi + (size_t)GL.v_pad * (ceil_div64(GL.kg, 64) * 64));
       if (!scales_done && do_w) {
-        rc = tc_bwd_scales(h, w, csr_row_ptr, w_eff, w_self, x, v_out, v_src, R, A, F, T, scale_scratch, st);
+        rc = tc_bwd_scales(h, w, csr_row_ptr, w_eff, w_self, x, v_out, v_src, R, A, F, T, scale_scratch, st, h_rows);
         if (rc) return rc;
       }
       scales = (const float*)((const unsigned*)scale_scratch + 8);
@@ -803,14 +808,15 @@ int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float*
     ws += GM.xsplit_bytes;
     float* partial = (float*)ws;
     if (do_w) {
-      if (!bias_done) {
+      if (!bias_done) {   // (dense: the same strips, h_rows times as long)
         k_bw_bias_partial<<<dim3((unsigned)L.bias_blocks, (unsigned)ceil_div64(T, 32)), dim3(32, 8), 0, st>>>(
-            h, v_out, T, L.bias_rows, bias_part);
+            h, v_out * h_rows, T, L.bias_rows * h_rows, bias_part);
         GCB_LAUNCH_OK();
         k_bw_bias_final<<<(unsigned)ceil_div64(T, 128), 128, 0, st>>>(bias_part, L.bias_blocks, T, accumulate, d_bias);
         GCB_LAUNCH_OK();
       }
-      rc = tc_build_g(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, x3, g_hi, g_lo, st, scales, csr_ring_grouped);
+      rc = tc_build_g(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, R, A, T, x3, g_hi, g_lo, st, scales, csr_ring_grouped,
+                      dense_n_rot, dense_offsets);
       if (rc) return rc;
       rc = tc_dw_from_g(g_hi, g_lo, x, v_src, R, A, F, T, x3, accumulate, d_w_eff, d_w_self, x_hi, x_lo, partial,
                         GM.partial_bytes, st, scales, half && x_split_done);

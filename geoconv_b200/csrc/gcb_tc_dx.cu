@@ -185,12 +185,18 @@ __device__ __forceinline__ void g2_split4(const float4 v, float s, uint2& hi, ui
 // Lane l owns the four templates t_base + 4 l .. + 3 of a 128-template pass: one 16-byte load of an h row, four
 // FMAs and no per-template address arithmetic per entry (the variant with one template per lane and load was
 // instruction-issue bound at 94 us: ~25 instructions per entry and ~56 per (ring, y') group).
-template <bool H>
+// DENSE (a gradient for EVERY rotation, h = [v_out][n_rot][T]): an entry with angular index y feeds the rotated slot
+// y' from rotation i with offset o_i = (y' - y) mod A (`inv` maps an offset to its rotation, -1: not in the list),
+// so every entry of a ring takes part in every y' group - n_rot times the gather of the sparse case, but the two
+// GEMMs behind G stay the size of ONE rotation instead of running n_rot times.
+struct RotInv { int8_t of_offset[GCB_MAX_ROT]; };
+
+template <bool H, bool DENSE>
 __global__ void __launch_bounds__(G2_WARPS * 32)
 k_bw_build_g2(const float* __restrict__ h, const float* __restrict__ w, const int32_t* __restrict__ rot_sel,
               const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ entries, int v_out, int v_src, int v_pad,
               int R, int A, int T, int kg, int kg_ld, const float* __restrict__ scales, float* __restrict__ g_hi,
-              float* __restrict__ g_lo) {
+              float* __restrict__ g_lo, int n_rot, const RotInv inv) {
   extern __shared__ float4 s_carry_all[];              // [G2_WARPS][A][32]: running sums of a straddling ring
   __shared__ int2 s_meta[G2_WARPS][32];                // {h row offset, weight bits}
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -251,9 +257,12 @@ k_bw_build_g2(const float* __restrict__ h, const float* __restrict__ w, const in
         const int k = cell / RA;
         const int slot = cell - k * RA;
         my_x = slot / A;
-        my_y = slot - my_x * A + __ldg(rot_sel + k);
-        my_y -= (my_y >= A) ? A : 0;
-        s_meta[warp][lane] = make_int2(k * T, __float_as_int(__ldg(w + s)));
+        my_y = slot - my_x * A;
+        if (!DENSE) {
+          my_y += __ldg(rot_sel + k);
+          my_y -= (my_y >= A) ? A : 0;
+        }
+        s_meta[warp][lane] = make_int2(DENSE ? k * n_rot * T : k * T, __float_as_int(__ldg(w + s)));
       }
       __syncwarp();
       int pos = 0;
@@ -266,7 +275,13 @@ k_bw_build_g2(const float* __restrict__ h, const float* __restrict__ w, const in
         if (!cont) { zero_rings(next_x, x); next_x = x; }
         const bool more = seg_end == n && base + n < end;                     // the ring may go on in the next chunk
         for (int y = 0; y < A; ++y) {
-          unsigned bits = seg & __ballot_sync(0xffffffffu, my_y == y);
+          int my_i = 0;   // DENSE: the rotation through which this lane's entry reaches slot y
+          if (DENSE) {
+            int d = y - my_y;
+            d += d < 0 ? A : 0;
+            my_i = my_y >= 0 ? inv.of_offset[d] : -1;
+          }
+          unsigned bits = seg & __ballot_sync(0xffffffffu, DENSE ? my_i >= 0 : my_y == y);
           float4 acc = cont ? s_carry[y * 32 + lane] : zero4;
           while (bits) {
             // up to four entries' rows are requested before the first is added (CSR order kept)
@@ -280,7 +295,8 @@ k_bw_build_g2(const float* __restrict__ h, const float* __restrict__ w, const in
                 bits &= bits - 1;
                 const int2 m = s_meta[warp][e];
                 wg[u] = __int_as_float(m.y);
-                hv[u] = t_on ? __ldg(reinterpret_cast<const float4*>(h + (size_t)m.x + t)) : zero4;
+                const int roff = DENSE ? __shfl_sync(0xffffffffu, my_i, e) * T : 0;
+                hv[u] = t_on ? __ldg(reinterpret_cast<const float4*>(h + (size_t)m.x + roff + t)) : zero4;
                 ++cnt;
               }
             }
@@ -306,8 +322,20 @@ k_bw_build_g2(const float* __restrict__ h, const float* __restrict__ w, const in
     if (open) close_ring();
     zero_rings(next_x, R);                 // empty rings after the last one that had entries
   }
-  for (int i = 4 * lane; i < T; i += 128)  // centre slab: h[v] itself (zero for halo rows)
-    put4(RA * T + i, v < v_out ? __ldg(reinterpret_cast<const float4*>(h + (size_t)v * T + i)) : zero4);
+  for (int i = 4 * lane; i < T; i += 128) {  // centre slab: h[v] itself (zero for halo rows); DENSE: summed over rotations
+    float4 c = zero4;
+    if (v < v_out) {
+      if (DENSE) {
+        for (int r = 0; r < n_rot; ++r) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(h + ((size_t)v * n_rot + r) * T + i));
+          c.x += a.x; c.y += a.y; c.z += a.z; c.w += a.w;
+        }
+      } else {
+        c = __ldg(reinterpret_cast<const float4*>(h + (size_t)v * T + i));
+      }
+    }
+    put4(RA * T + i, c);
+  }
 }
 
 // ---- persistent TMA-fed tcgen05 GEMM ---------------------------------------------------------------
@@ -752,14 +780,15 @@ size_t tc_bwd_scales_bytes() { return 256; }
 
 // scratch: 8 unsigned maxima, then the 5 scales (the caller passes scratch + 8 words as `scales`)
 int tc_bwd_scales(const float* h, const float* w, const int32_t* csr_row_ptr, const float* w_eff, const float* w_self,
-                  const float* x, int v_out, int v_src, int R, int A, int F, int T, void* scratch, cudaStream_t st) {
+                  const float* x, int v_out, int v_src, int R, int A, int F, int T, void* scratch, cudaStream_t st,
+                  int h_rows_per_vertex) {
   unsigned* mx = (unsigned*)scratch;
   GCB_CUDA_OK(cudaMemsetAsync(mx, 0, 32, st));
   const bool have_csr = csr_row_ptr && w_eff;
   TcMaxJob job{};
   job.mode = 2; job.have_csr = have_csr ? 1 : 0;
   int n = 0;
-  job.seg[n++] = {h, (long long)v_out * T, 0, 0};
+  job.seg[n++] = {h, (long long)v_out * h_rows_per_vertex * T, 0, 0};
   if (have_csr) {
     job.seg[n++] = {w, (long long)v_out * R * A * 3, 0, 1};
     job.seg[n++] = {csr_row_ptr, (long long)v_src, 1, 2};
@@ -865,22 +894,34 @@ TcGLayout tc_g_layout_max(int v_src, int R, int A, int F, int T, bool x3) {
   return L;
 }
 
-template <bool H>
+template <bool H, bool DENSE>
 static int launch_build_g2(const float* h, const float* w, const int32_t* rot_sel, const int32_t* row_ptr,
                            const int32_t* entries, int v_out, int v_src, int v_pad, int R, int A, int T, int kg, int kg_ld,
-                           const float* scales, float* g_hi, float* g_lo, cudaStream_t st) {
+                           const float* scales, float* g_hi, float* g_lo, cudaStream_t st, int n_rot, const RotInv& inv) {
   const size_t smem = (size_t)G2_WARPS * A * 32 * sizeof(float4);
   if (smem > 40 * 1024)
-    GCB_CUDA_OK(cudaFuncSetAttribute(k_bw_build_g2<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_bw_build_g2<H><<<(unsigned)ceil_div64(v_pad, G2_WARPS), G2_WARPS * 32, smem, st>>>(
-      h, w, rot_sel, row_ptr, entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, g_lo);
+    GCB_CUDA_OK(cudaFuncSetAttribute(k_bw_build_g2<H, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_bw_build_g2<H, DENSE><<<(unsigned)ceil_div64(v_pad, G2_WARPS), G2_WARPS * 32, smem, st>>>(
+      h, w, rot_sel, row_ptr, entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, g_lo, n_rot, inv);
   return GCB_OK;
 }
 
 int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int32_t* csr_row_ptr,
                const int32_t* csr_entries, int v_out, int v_src, int R, int A, int T, bool x3, float* g_hi,
-               float* g_lo, cudaStream_t st, const float* scales, bool ring_sorted) {
+               float* g_lo, cudaStream_t st, const float* scales, bool ring_sorted, int dense_n_rot,
+               const int32_t* dense_offsets) {
   const int RA = R * A;
+  RotInv inv;
+  for (int i = 0; i < GCB_MAX_ROT; ++i) inv.of_offset[i] = -1;
+  if (dense_n_rot > 0) {
+    GCB_REQUIRE(ring_sorted && A <= GCB_MAX_ROT && T % 32 == 0 && ((uintptr_t)h % 16 == 0) && dense_offsets, GCB_EUNSUPPORTED,
+                "tc_build_g: the dense route needs a ring-grouped CSR, A <= %d and T %% 32 == 0", GCB_MAX_ROT);
+    for (int i = 0; i < dense_n_rot; ++i) {
+      const int o = ((dense_offsets[i] % A) + A) % A;
+      GCB_REQUIRE(inv.of_offset[o] < 0, GCB_EUNSUPPORTED, "tc_build_g: the dense route needs distinct rotation offsets");
+      inv.of_offset[o] = (int8_t)i;
+    }
+  }
   const int kg = (RA + 1) * T;
   const int v_pad = (int)ceil_div64(v_src, 128) * 128;
   // GCB_BUILD_G2=0 (read per call): the shared-memory kernel k_bw_build_g, for A/B measurements
@@ -891,13 +932,18 @@ int tc_build_g(const float* h, const float* w, const int32_t* rot_sel, const int
     float* lo = half || x3 ? g_lo : nullptr;
     int rc;
     profile_begin(GCB_PROF_BWD_CSR, st);
-    rc = half ? launch_build_g2<true>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, lo, st)
-              : launch_build_g2<false>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, lo, st);
+    if (dense_n_rot > 0)
+      rc = half ? launch_build_g2<true, true>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, lo, st, dense_n_rot, inv)
+                : launch_build_g2<false, true>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, lo, st, dense_n_rot, inv);
+    else
+      rc = half ? launch_build_g2<true, false>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, lo, st, 0, inv)
+                : launch_build_g2<false, false>(h, w, rot_sel, csr_row_ptr, csr_entries, v_out, v_src, v_pad, R, A, T, kg, kg_ld, scales, g_hi, lo, st, 0, inv);
     profile_end(GCB_PROF_BWD_CSR, st);
     if (rc) return rc;
     GCB_LAUNCH_OK();
     return GCB_OK;
   }
+  GCB_REQUIRE(dense_n_rot == 0, GCB_EUNSUPPORTED, "tc_build_g: the dense route is served by k_bw_build_g2 only");
   const size_t smem = (size_t)RA * T * sizeof(float);
   GCB_REQUIRE(smem <= TC_BUILD_G_SMEM_LIMIT, GCB_EUNSUPPORTED, "tc_build_g: R*A*T too large for the G accumulator");
   const bool half = scales != nullptr;

@@ -504,15 +504,31 @@ def conv_bwd_op(grad_y: torch.Tensor | None, grad_z: torch.Tensor | None, x: tor
                                          ws.data_ptr(), ws_bytes, st), "gcb_conv_amp_bwd")
             calls += 1
         if grad_y is not None:
-            gy = grad_y.to(torch.float32)
-            for i, off in enumerate(rot):
-                gi = gy[:, i, :].contiguous()
-                yi = y[:, i, :].contiguous()
-                N.check(lib.gcb_act_grad(gi.data_ptr(), yi.data_ptr(), gi.numel(), act_id, h.data_ptr(), st),
+            gy = grad_y.contiguous().to(torch.float32)
+            offs = [int(o) % a for o in rot]
+            if (has_nb and row_ptr is not None and len(set(offs)) == n_rot and os.environ.get("GCB_DENSE_BWD", "1") != "0"
+                    and lib.gcb_conv_bwd_dense_supported(r, a, f, t, precision)):
+                # every rotation in ONE pass: h for the whole (V, n_rot, T) tensor, one G, one pair of GEMMs
+                yc = y.contiguous()
+                h_all = torch.empty_like(gy)
+                N.check(lib.gcb_act_grad(gy.data_ptr(), yc.data_ptr(), gy.numel(), act_id, h_all.data_ptr(), st),
                         "gcb_act_grad")
-                rot_sel.fill_(off % a)
-                run(1 if calls else 0)
+                N.check(lib.gcb_conv_bwd_dense(x.data_ptr(), idx.data_ptr(), w.data_ptr(), w_eff.data_ptr(),
+                                               w_self.data_ptr(), h_all.data_ptr(), N.rot_array(offs), n_rot,
+                                               row_ptr.data_ptr(), entries.data_ptr(), N.CSR_RING_GROUPED, v_out, v_src, r, a,
+                                               f, t, precision, 1 if calls else 0, _ptr(d_x), d_w_eff.data_ptr(),
+                                               d_w_self.data_ptr(), d_bias.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                        "gcb_conv_bwd_dense")
                 calls += 1
+            else:
+                for i, off in enumerate(rot):   # shapes the dense kernel does not tile: one sparse backward per rotation
+                    gi = gy[:, i, :].contiguous()
+                    yi = y[:, i, :].contiguous()
+                    N.check(lib.gcb_act_grad(gi.data_ptr(), yi.data_ptr(), gi.numel(), act_id, h.data_ptr(), st),
+                            "gcb_act_grad")
+                    rot_sel.fill_(off % a)
+                    run(1 if calls else 0)
+                    calls += 1
     if d_x is None:
         d_x = x.new_empty((0,))
     if staged is not None:

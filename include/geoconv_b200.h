@@ -275,6 +275,21 @@ int gcb_conv_bwd(const float* x, const int32_t* idx, const float* w, const float
                  float* d_w_eff, float* d_w_self, float* d_bias, void* workspace, size_t workspace_bytes,
                  void* stream);
 
+/* Dense backward: a gradient for EVERY rotation (the layer used without AngularMaxPooling, or under
+ * AngularMinPooling / AngularAvgPooling - autograd of conv_intrinsic.py:144-171 over all n_rot rotations) in ONE pass:
+ * h_all [V_out, n_rot, T] = dY * act'(Y) (gcb_act_grad on the whole tensor); the operand G collects, per source vertex
+ * and rotated slot, the contributions of all rotations, and the two GEMMs behind it are the size of one rotation.
+ * rot_off_host: the n_rot DISTINCT rotation offsets (mod A) on the host.  Needs gcb_conv_bwd_dense_supported() and a
+ * CSR built with the template size (GCB_CSR_RING_GROUPED); otherwise call gcb_conv_bwd once per rotation.
+ * Workspace: gcb_conv_bwd_workspace_bytes.                                                              */
+int gcb_conv_bwd_dense_supported(int32_t R, int32_t A, int32_t F, int32_t T, int precision);
+int gcb_conv_bwd_dense(const float* x, const int32_t* idx, const float* w, const float* w_eff,
+                       const float* w_self, const float* h_all, const int32_t* rot_off_host, int32_t n_rot,
+                       const int32_t* csr_row_ptr, const int32_t* csr_entries, int csr_flags, int32_t v_out,
+                       int32_t v_src, int32_t R, int32_t A, int32_t F, int32_t T, int precision,
+                       int accumulate, float* d_x, float* d_w_eff, float* d_w_self, float* d_bias,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- backward of conv + AngularMaxPooling in one call -----------------------------------------
  * Replaces autograd of angular_max_pooling.py:27-29 followed by conv_intrinsic.py:144-171/:226-240: starts from
  * grad_z [V_out,T] (gradient of the pooled output), z [V_out,T] (the pooled output itself: the activation

@@ -194,3 +194,76 @@ def test_fused_finish_equals_separate_finish(shape, precision, monkeypatch):
     for mode in ("1", "2"):
         for got, want in zip(outs[mode], outs["0"]):
             assert torch.equal(got, want), f"GCB_TC_FUSE={mode}"
+
+
+DENSE_SHAPES = [
+    # kind, V, F, R, A, T, delta, act
+    ("geodesic", 700, 64, 5, 8, 96, 1, "relu"),
+    ("geodesic", 450, 96, 3, 6, 64, 2, "elu"),
+    ("dirac", 333, 64, 2, 8, 32, 1, "tanh"),
+]
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x3"])
+@pytest.mark.parametrize("shape", DENSE_SHAPES, ids=lambda s: "-".join(map(str, s)))
+def test_dense_backward_one_pass(shape, precision, monkeypatch):
+    """A loss on Y itself (the layer used without angular max-pooling): the gradient for every rotation goes through ONE
+    operand G and one pair of GEMMs (gcb_conv_bwd_dense) - against float64 autograd over the oracle, and against the
+    per-rotation route it replaces."""
+    kind, v, f, r, a, t, delta, act = shape
+    assert _native.load().gcb_conv_bwd_dense_supported(r, a, f, t, _native.PREC_TF32X3)
+    wn, ws, b = O.make_weights(t, r, a, f, seed=0)
+    signal = O.make_signal(v, f, seed=1, kind="randn")
+    bary = O.make_bary(v, r, a, seed=1, fallback_frac=0.05)
+    prior = torch.from_numpy(O.geodesic_prior(O.template_matrix(r, a, 0.03))).float() if kind == "geodesic" else None
+    n_rot = len(range(0, a, delta))
+    gy = torch.randn((v, n_rot, t), generator=torch.Generator().manual_seed(5))
+    xs = signal.double().requires_grad_(True)
+    ps = [p.double().requires_grad_(True) for p in (wn, ws, b)]
+    yo = O.conv_forward(xs, bary, ps[0], ps[1], ps[2], None if prior is None else prior.double(), act, delta)
+    ref = torch.autograd.grad((yo * gy.double()).sum(), [xs] + ps)
+    cls = ConvGeodesic if kind == "geodesic" else ConvDirac
+    got = {}
+    for route in ("dense", "loop"):
+        monkeypatch.setenv("GCB_DENSE_BWD", "1" if route == "dense" else "0")
+        layer = cls(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.03,
+                    activation=act, rotation_delta=delta, precision=precision)
+        layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
+        layer = layer.to(DEV)
+        x = signal.to(DEV).requires_grad_(True)
+        launches = _native.load().gcb_launch_count()
+        y = layer([x, bary.to(DEV)])
+        (y * gy.to(DEV)).sum().backward()
+        got[route] = (x.grad, layer._template_neighbor_weights.grad, layer._template_self_weights.grad, layer._bias.grad,
+                      _native.load().gcb_launch_count() - launches)
+    # activations with a kink flip a derivative bit where the pre-activation is within rounding of zero
+    tol = TOL_FP32 if act != "relu" else 3 * TOL_FP32
+    for i, name in enumerate(("d_signal", "d_w_neighbor", "d_w_self", "d_bias")):
+        assert nerr(got["dense"][i], ref[i]) < tol, (name, nerr(got["dense"][i], ref[i]))
+        assert nerr(got["dense"][i], got["loop"][i]) < TOL_FP32, name
+    assert got["dense"][4] < got["loop"][4]          # fewer launches than n_rot sparse backward calls
+
+
+def test_dense_backward_under_min_and_avg_pooling():
+    from geoconv_b200.pytorch.layers.angular_avg_pooling import AngularAvgPooling
+    from geoconv_b200.pytorch.layers.angular_min_pooling import AngularMinPooling
+    v, f, r, a, t = 500, 64, 5, 8, 64
+    wn, ws, b = O.make_weights(t, r, a, f, seed=0)
+    signal = O.make_signal(v, f, seed=1, kind="randn")
+    bary = O.make_bary(v, r, a, seed=1)
+    prior = torch.from_numpy(O.geodesic_prior(O.template_matrix(r, a, 0.03))).float()
+    gz = torch.randn((v, t), generator=torch.Generator().manual_seed(7))
+    for pool, ref_pool in ((AngularAvgPooling(), O.aavg_forward), (AngularMinPooling(), lambda y: O.amin_forward(y)[0])):
+        xs = signal.double().requires_grad_(True)
+        ps = [p.double().requires_grad_(True) for p in (wn, ws, b)]
+        yo = O.conv_forward(xs, bary, ps[0], ps[1], ps[2], prior.double(), "tanh", 1)
+        ref = torch.autograd.grad((ref_pool(yo) * gz.double()).sum(), [xs] + ps)
+        layer = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.03,
+                             activation="tanh", precision="fp32")
+        layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
+        layer = layer.to(DEV)
+        x = signal.to(DEV).requires_grad_(True)
+        pool(layer([x, bary.to(DEV)])).backward(gz.to(DEV))
+        assert nerr(x.grad, ref[0]) < TOL_FP32
+        assert nerr(layer._template_neighbor_weights.grad, ref[1]) < TOL_FP32
+        assert nerr(layer._bias.grad, ref[3]) < TOL_FP32
