@@ -109,7 +109,9 @@ extern "C" size_t gcb_conv_fwd_workspace_bytes(int32_t v_out, int32_t v_src, int
   (void)v_src;
   size_t y_tmp = align_up((size_t)v_out * n_rot * T * sizeof(float), 256);  // when caller passes y == NULL
   if (precision == GCB_PREC_FP32) return y_tmp + ffma_fwd_workspace_bytes(v_out, R, A, F) + 256;
-  return y_tmp + tc_fwd_workspace_bytes(v_out, R, A, F, T, n_rot, precision) + 256;
+  size_t tc = tc_fwd_workspace_bytes(v_out, R, A, F, T, n_rot, precision);
+  if (tc_centre_fwd_supported(F, T) && tc_centre_fwd_bytes(v_out, F, T) > tc) tc = tc_centre_fwd_bytes(v_out, F, T);
+  return y_tmp + tc + 256;   // (a centre-only layer on the CUDA-core path uses no workspace)
 }
 
 extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, const float* w_eff,
@@ -141,7 +143,12 @@ extern "C" int gcb_conv_fwd(const float* x, const int32_t* idx, const float* w, 
   ws += y_tmp;
   workspace_bytes -= y_tmp;
   if (stats_out && (precision != GCB_PREC_F16X3 || !w_eff)) GCB_CUDA_OK(cudaMemsetAsync(stats_out, 0, 32, st));
-  if (precision == GCB_PREC_FP32 || !w_eff) {  // centre-only (w_eff == NULL) is a tiny GEMM: CUDA cores
+  if (!w_eff && precision != GCB_PREC_FP32 && tc_centre_fwd_supported(F, T) && ((uintptr_t)x % 16 == 0)) {
+    // centre-only (all-zero prior): one tensor-core GEMM, bias / activation / pooling in its epilogue kernel
+    return tc_centre_fwd(x + (size_t)row0 * F, w_self, bias, n_rot, v_out, F, T, act, precision, y, z, argmax, ws,
+                         workspace_bytes, st);
+  }
+  if (precision == GCB_PREC_FP32 || !w_eff) {
     rc = ffma_conv_fwd(x, idx, w, w_eff, w_self, bias, rot, n_rot, v_out, v_src, R, A, F, T, act, y_out, ws, st, row0);
   } else if (precision == GCB_PREC_TF32 || precision == GCB_PREC_TF32X3 || precision == GCB_PREC_F16X3) {
     GCB_REQUIRE(tc_supported(R, A, F, T, n_rot), GCB_EUNSUPPORTED,

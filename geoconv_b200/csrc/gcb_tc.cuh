@@ -87,6 +87,12 @@ int tc_dw_from_g(const float* g_hi, const float* g_lo, const float* x, int v_src
 
 // tensor-core backward (gcb_tc_bwd.cu)
 bool tc_bwd_supported(int R, int A, int F, int T);
+// centre-only forward (ConvZero) as one tensor-core GEMM
+bool tc_centre_fwd_supported(int F, int T);
+size_t tc_centre_fwd_bytes(int v_out, int F, int T);
+int tc_centre_fwd(const float* x_rows, const float* w_self, const float* bias, int n_rot, int v_out, int F, int T, int act,
+                  int precision, float* y, float* z, int32_t* argmax, void* workspace, size_t workspace_bytes,
+                  cudaStream_t st);
 size_t tc_bwd_workspace_bytes(int v_out, int v_src, int R, int A, int F, int T, int precision);
 bool tc_bwd_layout_fits(int v_out, int v_src, int R, int A, int F, int T, int precision);
 // AMP-sparse entry: the backward starts from dZ, Z and the pooling decisions instead of h / rot_sel, which it then

@@ -651,6 +651,75 @@ static int launch_dw(const CUtensorMap& mh, const CUtensorMap& ml, const TcDwPar
   return GCB_OK;
 }
 
+// ---- centre-only forward (all-zero prior, ConvZero: conv_zero.py:12-15) on tensor cores ---------------------------
+// Y[k, i, :] = act(X[k] Wself^T + b) for every rotation i; the pooling picks rotation 0.  The contraction is the
+// persistent TMA-fed GEMM of the signal gradient (tc_dx_from_g) with the roles swapped: A = the signal rows (K-major,
+// tf32 hi / lo), B = Wself^T [F x T] (MN-major).  The CUDA-core GEMM this replaces took 190 us at the FAUST shape.
+__global__ void k_centre_wt(const float* __restrict__ w_self, int T, int F, float* __restrict__ hi, float* __restrict__ lo) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // over [F][T]
+  if (e >= F * T) return;
+  const int f = e / T, t = e - f * T;
+  const float v = w_self[(size_t)t * F + f];
+  const float hv = ptx::to_tf32(v);
+  hi[e] = hv;
+  if (lo) lo[e] = v - hv;
+}
+
+__global__ void k_centre_epilogue(const float4* __restrict__ acc, const float4* __restrict__ bias, int v_out, int T4,
+                                  int n_rot, int act, float4* __restrict__ y, float4* __restrict__ z,
+                                  int32_t* __restrict__ argmax) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= (int64_t)v_out * T4) return;
+  const int k = (int)(e / T4), q = (int)(e - (int64_t)k * T4);
+  const float4 a = acc[e], b = __ldg(bias + q);
+  float4 o;
+  o.x = act_apply(act, a.x + b.x); o.y = act_apply(act, a.y + b.y);
+  o.z = act_apply(act, a.z + b.z); o.w = act_apply(act, a.w + b.w);
+  if (y)
+    for (int i = 0; i < n_rot; ++i) y[((size_t)k * n_rot + i) * T4 + q] = o;
+  if (z) {
+    z[e] = o;
+    if (q == 0) argmax[k] = 0;   // equal norms: the first rotation (torch.argmax)
+  }
+}
+
+size_t tc_centre_fwd_bytes(int v_out, int F, int T) {
+  const size_t v_pad = (size_t)ceil_div64(v_out, 128) * 128;
+  return align_up(2 * v_pad * F * sizeof(float), 256) + align_up((size_t)2 * F * T * sizeof(float), 256) +
+         align_up((size_t)v_out * T * sizeof(float), 256) + 512;
+}
+
+bool tc_centre_fwd_supported(int F, int T) { return tc_bwd_supported(0, 1, T, F); }
+
+int tc_centre_fwd(const float* x_rows, const float* w_self, const float* bias, int n_rot, int v_out, int F, int T, int act,
+                  int precision, float* y, float* z, int32_t* argmax, void* workspace, size_t workspace_bytes,
+                  cudaStream_t st) {
+  GCB_REQUIRE(workspace_bytes >= tc_centre_fwd_bytes(v_out, F, T), GCB_EWORKSPACE, "tc_centre_fwd: workspace too small");
+  GCB_REQUIRE(((uintptr_t)bias % 16 == 0) && (!y || (uintptr_t)y % 16 == 0) && (!z || (uintptr_t)z % 16 == 0), GCB_EINVAL,
+              "tc_centre_fwd: bias, y and z must be 16-byte aligned");
+  const bool x3 = precision != GCB_PREC_TF32;
+  const int v_pad = (int)ceil_div64(v_out, 128) * 128;
+  char* ws = (char*)align_up((size_t)workspace, 256);
+  float* a_hi = (float*)ws;
+  float* a_lo = x3 ? a_hi + (size_t)v_pad * F : nullptr;
+  ws += align_up((size_t)2 * v_pad * F * sizeof(float), 256);
+  float* b_hi = (float*)ws;
+  float* b_lo = x3 ? b_hi + (size_t)F * T : nullptr;
+  ws += align_up((size_t)2 * F * T * sizeof(float), 256);
+  float* acc = (float*)ws;
+  k_bw_split_rows<<<(unsigned)ceil_div64((int64_t)v_pad * F, 256), 256, 0, st>>>(x_rows, v_out, v_pad, F, a_hi, a_lo);
+  GCB_LAUNCH_OK();
+  k_centre_wt<<<(unsigned)ceil_div64((int64_t)F * T, 256), 256, 0, st>>>(w_self, T, F, b_hi, b_lo);
+  GCB_LAUNCH_OK();
+  // out[v, T] = A[v, F] x B[F, T]: the dSignal GEMM with (contraction, columns) = (F, T)
+  int rc = tc_dx_from_g(a_hi, a_lo, b_hi, b_lo, v_out, 0, 1, /*columns*/ T, /*contraction*/ F, x3, 0, acc, st);
+  if (rc) return rc;
+  k_centre_epilogue<<<(unsigned)ceil_div64((int64_t)v_out * (T / 4), 256), 256, 0, st>>>(
+      (const float4*)acc, (const float4*)bias, v_out, T / 4, n_rot, act, (float4*)y, (float4*)z, argmax);
+  GCB_LAUNCH_OK();
+  return GCB_OK;
+}
+
 int tc_conv_bwd(const float* x, const int32_t* idx, const float* w, const float* w_eff, const float* w_self,
                 const float* h, const int32_t* rot_sel, const int32_t* csr_row_ptr, const int32_t* csr_entries,
                 int v_out, int v_src, int R, int A, int F, int T, int precision, int accumulate,

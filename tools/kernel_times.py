@@ -1,5 +1,5 @@
 """Warm per-kernel durations of one S1 step (fwd + AMP + bwd) from torch.profiler (CUPTI activity records),
-L2 flushed between steps.  usage: kernel_times.py [precision ...]"""
+L2 flushed between steps.  usage: [GCB_KT_CLASS=geodesic|dirac|zero] kernel_times.py [precision ...]"""
 import collections, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,6 +7,9 @@ from torch.profiler import ProfilerActivity, profile
 from geoconv_b200 import synthetic as S
 from geoconv_b200.pytorch.layers.angular_max_pooling import AngularMaxPooling
 from geoconv_b200.pytorch.layers.conv_geodesic import ConvGeodesic
+from geoconv_b200.pytorch.layers.conv_dirac import ConvDirac
+from geoconv_b200.pytorch.layers.conv_zero import ConvZero
+CLS = {"geodesic": ConvGeodesic, "dirac": ConvDirac, "zero": ConvZero}[os.environ.get("GCB_KT_CLASS", "geodesic")]
 
 v, f, r, a, t = 6890, 544, 5, 8, 96
 dev = "cuda:0"
@@ -18,7 +21,7 @@ flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 amp = AngularMaxPooling()
 STEPS = 10
 for prec in sys.argv[1:] or ["fp32"]:
-    layer = ConvGeodesic(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.028, precision=prec)
+    layer = CLS(input_shape=[(None, f), (None, r, a, 3, 2)], amt_templates=t, template_radius=0.028, precision=prec)
     layer.load_state_dict({"_template_neighbor_weights": wn, "_template_self_weights": ws, "_bias": b})
     layer = layer.to(dev)
 
@@ -42,7 +45,7 @@ for prec in sys.argv[1:] or ["fp32"]:
             continue
         agg.setdefault(ev.name[:72], []).append(ev.device_time)
     total = 0.0
-    print(f"== {prec}: per-kernel device time per step (us), {STEPS} steps")
+    print(f"== {CLS.__name__} {prec}: per-kernel device time per step (us), {STEPS} steps")
     for name, ts in agg.items():
         per_step = sum(ts) / STEPS
         total += per_step
