@@ -486,7 +486,23 @@ def run_ours(args):
                            "_bias": weights[2]})
     layer = layer.to(dev)
     amp = AngularMaxPooling()
-    signal_h, bary_h, gz_h = [x.pin_memory() for x in make_inputs(cfg, seed_offset=rank)]
+    # The step's three inputs live in ONE pinned host arena and travel in ONE copy: on this box a pinned H2D copy
+    # costs ~0.28 ms before the first byte moves (tools/h2d_probe.py: 24 MB at 35 GB/s, 256 MB at 56 GB/s), so three
+    # separate copies of 15 + 6.6 + 2.6 MB reached 25 GB/s together.
+    def arena(tensors, device=None, pin=False):
+        sizes = [(x.numel() * x.element_size() + 255) // 256 * 256 for x in tensors]
+        buf = torch.empty(sum(sizes), dtype=torch.uint8, device=device)
+        if pin:
+            buf = buf.pin_memory()
+        views, off = [], 0
+        for x, n in zip(tensors, sizes):
+            views.append(buf[off:off + x.numel() * x.element_size()].view(x.dtype).view(x.shape))
+            off += n
+        return buf, views
+    inputs = make_inputs(cfg, seed_offset=rank)
+    arena_h, (signal_h, bary_h, gz_h) = arena(inputs, pin=True)
+    for dst_, src_ in zip((signal_h, bary_h, gz_h), inputs):
+        dst_.copy_(src_)
     signal_d = signal_h.to(dev).requires_grad_(True)
     bary_d = bary_h.to(dev)
     gz_d = gz_h.to(dev)
@@ -526,18 +542,14 @@ def run_ours(args):
         reduce_after_step()
         return z
 
-    # buffers for the host-to-host leg
-    sig_buf = torch.empty_like(signal_d)
-    bary_buf = torch.empty_like(bary_d)
-    gz_buf = torch.empty_like(gz_d)
+    # buffers for the host-to-host leg (one device arena, the three tensors are views of it)
+    arena_buf, (sig_buf, bary_buf, gz_buf) = arena(inputs, device=dev)
     z_host = torch.empty((v, t), dtype=torch.float32).pin_memory()
 
     def step_e2e():
         for p_ in params:
             p_.grad = None
-        sig_buf.copy_(signal_h, non_blocking=True)
-        bary_buf.copy_(bary_h, non_blocking=True)     # bumps the version: bary is re-packed, CSR rebuilt
-        gz_buf.copy_(gz_h, non_blocking=True)
+        arena_buf.copy_(arena_h, non_blocking=True)   # bumps the views' version: bary is re-packed, CSR rebuilt
         xs = sig_buf.detach().requires_grad_(True)
         z = amp(layer([xs, bary_buf]))
         z.backward(gz_buf)
@@ -655,14 +667,16 @@ def run_ours(args):
         Returns the total time of `steps` steps with the time of the `steps` L2 flushes subtracted."""
         main = torch.cuda.current_stream()
         copy = torch.cuda.Stream()
+        back = torch.cuda.Stream()   # results go home on their own stream (and copy engine): a D2H queued between two
+                                     # H2D copies made the next step's inputs wait for this step's result
         quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
         if quiet is not None:
             quiet(False)   # the parameters' AccumulateGrad nodes were created on another stream by the earlier legs
         sets = []
         for _ in range(2):
-            bufs = dict(sig=torch.empty_like(signal_d), bary=torch.empty_like(bary_d), gz=torch.empty_like(gz_d))
-            for key, src in (("sig", signal_h), ("bary", bary_h), ("gz", gz_h)):
-                bufs[key].copy_(src)
+            a_, (s_, b_, g_) = arena(inputs, device=dev)
+            bufs = dict(arena=a_, sig=s_, bary=b_, gz=g_)
+            bufs["arena"].copy_(arena_h)
 
             def body(bufs=bufs):
                 for p_ in params:
@@ -675,11 +689,11 @@ def run_ours(args):
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    bufs["bary"].copy_(bary_h)          # new version: the step re-packs the barycentric tensor
+                    bufs["arena"].copy_(arena_h)        # new version: the step re-packs the barycentric tensor
                     body()
             main.wait_stream(side)
             torch.cuda.synchronize()
-            bufs["bary"].copy_(bary_h)
+            bufs["arena"].copy_(arena_h)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -690,9 +704,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
         def h2d(bufs):
-            bufs["sig"].copy_(signal_h, non_blocking=True)
-            bufs["bary"].copy_(bary_h, non_blocking=True)
-            bufs["gz"].copy_(gz_h, non_blocking=True)
+            bufs["arena"].copy_(arena_h, non_blocking=True)
 
         def run(n):
             done = [None, None]                      # compute-finished event of the last step on each set
@@ -723,11 +735,15 @@ def run_ours(args):
                 fin = torch.cuda.Event()
                 fin.record(main)
                 done[i & 1] = fin
-                with torch.cuda.stream(copy):
-                    copy.wait_event(fin)
+                with torch.cuda.stream(back):
+                    back.wait_event(fin)
                     z_host.copy_(cur["z"].detach(), non_blocking=True)
+                    read = torch.cuda.Event()
+                    read.record(back)
+                done[i & 1] = read                   # the set (its z included) is free once the result has left
                 copied = copied_next
             main.wait_stream(copy)
+            main.wait_stream(back)
 
         run(warmup)
         barrier()
@@ -761,9 +777,7 @@ def run_ours(args):
             def e2e_body():   # (index validation stays on: it is a device-side counter, not a host sync)
                 for p_ in params:
                     p_.grad = None
-                sig_buf.copy_(signal_h, non_blocking=True)
-                bary_buf.copy_(bary_h, non_blocking=True)
-                gz_buf.copy_(gz_h, non_blocking=True)
+                arena_buf.copy_(arena_h, non_blocking=True)
                 xs = sig_buf.detach().requires_grad_(True)
                 z = amp(layer([xs, bary_buf]))
                 z.backward(gz_buf)
@@ -893,7 +907,7 @@ def run_ours(args):
         cpu_baseline = {"value": v / cpu_t, "unit": "vertices/s", "cores": cores, "kind": cpu_kind,
                         "sample": f"best of 2 full S1 meshes (fwd+bwd) after 1 warm-up; {cpu_descr}"}
 
-    h2d = signal_h.numel() * 4 + bary_h.numel() * bary_h.element_size() + gz_h.numel() * 4
+    h2d = arena_h.numel()   # signal + barycentric tensor + upstream gradient, padded to 256 bytes each: one copy
     d2h = z_host.numel() * 4
     line = {
         "metric": "vertices/sec, ConvGeodesic+AMP fwd+bwd", "value": value, "unit": "vertices/s",
@@ -913,7 +927,7 @@ def run_ours(args):
                                "flushes (the flush is measurement apparatus, not part of a step); serial figure = per-step "
                                "events, flush outside") if e2e_mode_p else "per-step events, flush outside",
                 "index_validation": "on (layer default: device-side counter, deferred report)",
-                "includes": "H2D signal+bary+upstream grad, bary split, CSR inversion, fwd, bwd, D2H pooled output"},
+                "includes": "H2D signal+bary+upstream grad (one pinned arena, one copy per step), bary split, CSR inversion, fwd, bwd, D2H pooled output"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
