@@ -486,23 +486,17 @@ def run_ours(args):
                            "_bias": weights[2]})
     layer = layer.to(dev)
     amp = AngularMaxPooling()
-    # The step's three inputs live in ONE pinned host arena and travel in ONE copy: on this box a pinned H2D copy
-    # costs ~0.28 ms before the first byte moves (tools/h2d_probe.py: 24 MB at 35 GB/s, 256 MB at 56 GB/s), so three
-    # separate copies of 15 + 6.6 + 2.6 MB reached 25 GB/s together.
-    def arena(tensors, device=None, pin=False):
-        sizes = [(x.numel() * x.element_size() + 255) // 256 * 256 for x in tensors]
-        buf = torch.empty(sum(sizes), dtype=torch.uint8, device=device)
-        if pin:
-            buf = buf.pin_memory()
-        views, off = [], 0
-        for x, n in zip(tensors, sizes):
-            views.append(buf[off:off + x.numel() * x.element_size()].view(x.dtype).view(x.shape))
-            off += n
-        return buf, views
+    # The step's three inputs live in ONE pinned, write-combined host arena and travel in ONE copy
+    # (geoconv_b200/data/staging.py: a pinned buffer the CPU has just written is copied at ~25 GB/s on this box - every
+    # DMA read snoops the dirty cache lines - write-combined pinned memory at ~45 GB/s).
+    from geoconv_b200.data.staging import PinnedArena, device_arena
     inputs = make_inputs(cfg, seed_offset=rank)
-    arena_h, (signal_h, bary_h, gz_h) = arena(inputs, pin=True)
-    for dst_, src_ in zip((signal_h, bary_h, gz_h), inputs):
-        dst_.copy_(src_)
+    host_arena = PinnedArena(inputs).fill(inputs)
+    arena_h = host_arena.buffer
+    signal_h, bary_h, gz_h = inputs          # (CPU copies for the resident leg; the arena is write-only for the CPU)
+
+    def arena(tensors, device=None):
+        return device_arena(tensors, device)
     signal_d = signal_h.to(dev).requires_grad_(True)
     bary_d = bary_h.to(dev)
     gz_d = gz_h.to(dev)
@@ -927,7 +921,7 @@ def run_ours(args):
                                "flushes (the flush is measurement apparatus, not part of a step); serial figure = per-step "
                                "events, flush outside") if e2e_mode_p else "per-step events, flush outside",
                 "index_validation": "on (layer default: device-side counter, deferred report)",
-                "includes": "H2D signal+bary+upstream grad (one pinned arena, one copy per step), bary split, CSR inversion, fwd, bwd, D2H pooled output"},
+                "includes": "H2D signal+bary+upstream grad (one pinned write-combined arena, one copy per step), bary split, CSR inversion, fwd, bwd, D2H pooled output"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
