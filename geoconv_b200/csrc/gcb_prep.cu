@@ -116,25 +116,31 @@ __global__ void __launch_bounds__(1024) k_fold_prior(const float* __restrict__ i
   __syncthreads();
   const int q0 = warp * 8;
   if (q0 >= RA || f0 + lane >= F) return;
+  // p outermost: the eight prior values of this warp's columns are read once per p for all FOLD_TB templates
+  // (32 FMAs per 2 + FOLD_TB shared-memory loads; one template at a time was 8 per 3 and load-issue bound)
+  float acc[FOLD_TB][8];
+#pragma unroll
+  for (int b = 0; b < FOLD_TB; ++b)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[b][j] = 0.f;
+  for (int p = 0; p < RA; ++p) {
+    const float4 k0 = *reinterpret_cast<const float4*>(s_prior + p * RAp + q0);
+    const float4 k1 = *reinterpret_cast<const float4*>(s_prior + p * RAp + q0 + 4);
+#pragma unroll
+    for (int b = 0; b < FOLD_TB; ++b) {
+      const float x = s_in[(b * RA + p) * 32 + lane];
+      acc[b][0] = fmaf(x, k0.x, acc[b][0]); acc[b][1] = fmaf(x, k0.y, acc[b][1]);
+      acc[b][2] = fmaf(x, k0.z, acc[b][2]); acc[b][3] = fmaf(x, k0.w, acc[b][3]);
+      acc[b][4] = fmaf(x, k1.x, acc[b][4]); acc[b][5] = fmaf(x, k1.y, acc[b][5]);
+      acc[b][6] = fmaf(x, k1.z, acc[b][6]); acc[b][7] = fmaf(x, k1.w, acc[b][7]);
+    }
+  }
 #pragma unroll
   for (int b = 0; b < FOLD_TB; ++b) {
     if (t0 + b >= T) break;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const float* sx = s_in + b * RA * 32;
-    for (int p = 0; p < RA; ++p) {
-      const float x = sx[p * 32 + lane];
-      const float4 k0 = *reinterpret_cast<const float4*>(s_prior + p * RAp + q0);
-      const float4 k1 = *reinterpret_cast<const float4*>(s_prior + p * RAp + q0 + 4);
-      acc[0] = fmaf(x, k0.x, acc[0]); acc[1] = fmaf(x, k0.y, acc[1]);
-      acc[2] = fmaf(x, k0.z, acc[2]); acc[3] = fmaf(x, k0.w, acc[3]);
-      acc[4] = fmaf(x, k1.x, acc[4]); acc[5] = fmaf(x, k1.y, acc[5]);
-      acc[6] = fmaf(x, k1.z, acc[6]); acc[7] = fmaf(x, k1.w, acc[7]);
-    }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (q0 + j < RA) out[((size_t)(t0 + b) * RA + q0 + j) * F + f0 + lane] = acc[j];
+      if (q0 + j < RA) out[((size_t)(t0 + b) * RA + q0 + j) * F + f0 + lane] = acc[b][j];
   }
 }
 
