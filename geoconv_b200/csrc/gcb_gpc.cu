@@ -41,8 +41,12 @@ namespace gcb {
 constexpr double kTwoPi = 6.283185307179586476925286766559;   // 2 * M_PI
 constexpr double kPi = 3.14159265358979323846;
 
+#ifndef GCB_GPC_HEAP_MULT
+#define GCB_GPC_HEAP_MULT 2   // candidate-list capacity in units of the vertex capacity (measured peak: below 1)
+#endif
+
 __host__ __device__ inline int64_t gpc_smem_per_system(int P) {
-  const int64_t EC = 4 * (int64_t)P, FC = 3 * (int64_t)P, HC = 8 * (int64_t)P, SC = 3 * (int64_t)P;
+  const int64_t EC = 4 * (int64_t)P, FC = 3 * (int64_t)P, HC = GCB_GPC_HEAP_MULT * (int64_t)P, SC = 3 * (int64_t)P;
   const int64_t b = 8 * (4 * P + HC) + 4 * (P + HC) + 4 * (EC + FC + SC) + 2 * 2 * EC + EC + EC;
   return (b + 15) / 16 * 16;
 }
@@ -493,7 +497,7 @@ __global__ void k_gpc_wavefront(const double* __restrict__ pos, const double* __
   const int sys = blockIdx.x * warps_per_block + wib;
   if (sys >= n_sources) return;
   Wave w;
-  w.P = P; w.EC = 4 * P; w.FC = 3 * P; w.HC = 8 * P; w.SC = 3 * P; w.lane = threadIdx.x % GCB_WARP;
+  w.P = P; w.EC = 4 * P; w.FC = 3 * P; w.HC = GCB_GPC_HEAP_MULT * P; w.SC = 3 * P; w.lane = threadIdx.x % GCB_WARP;
   w.pos = pos; w.nrm = nrm; w.nptr = nptr; w.nbr = nbr; w.opp = opp;
   const size_t per_warp = (size_t)gpc_smem_per_system(P);
   unsigned char* base = smem + per_warp * wib;
