@@ -26,13 +26,10 @@
 #include <float.h>
 #include <math.h>
 
-#ifdef GCB_GPC_HOST_EMULATION
-// tests/emul/: the algorithm text below compiled for the HOST with a one-lane "warp", so that the CPU test suite
-// can run it against the fixtures before any GPU time is spent.  Test infrastructure; never part of the library.
-#include "gpc_emul_shim.h"
-#else
 #include "gcb_common.cuh"
-#define GCB_WARP 32
+
+#ifndef GCB_WARP
+#define GCB_WARP 32   // lanes that share one system (the CPU test suite compiles the text below with 1, tests/emul/)
 #endif
 
 namespace gcb {
@@ -585,7 +582,6 @@ __global__ void k_gpc_wavefront(const double* __restrict__ pos, const double* __
 
 }  // namespace gcb
 
-#ifndef GCB_GPC_HOST_EMULATION
 using namespace gcb;
 
 extern "C" int64_t gcb_gpc_smem_per_system(int32_t max_patch) { return gpc_smem_per_system(max_patch); }
@@ -618,4 +614,3 @@ extern "C" int gcb_gpc_wavefront(const double* vertices, const double* normals, 
   GCB_LAUNCH_OK();
   return GCB_OK;
 }
-#endif  // !GCB_GPC_HOST_EMULATION

@@ -1,7 +1,10 @@
-// TEST INFRASTRUCTURE.  Host build of the GPC wavefront kernel's algorithm text (see gpc_emul_shim.h):
-//   g++ -O1 -shared -fPIC -DGCB_GPC_HOST_EMULATION -I tests/emul tests/emul/gpc_emul.cpp -o tests/emul/_build/libgpc_emul.so
-// exports gpc_emul_run(), which calls the kernel body once per source vertex.
-#include "../../geoconv_b200/csrc/gcb_gpc.cu"
+// TEST INFRASTRUCTURE.  Host build of the GPC wavefront kernel's algorithm text (see gpc_emul_shim.h).
+// tests/test_gpc_wavefront.py::emul copies the DEVICE section of geoconv_b200/csrc/gcb_gpc.cu - everything between its
+// #include "gcb_common.cuh" and the end of namespace gcb, verbatim - into _build/gcb_gpc_device_section.inc and compiles
+//   g++ -O1 -shared -fPIC -I tests/emul -x c++ tests/emul/gpc_emul.cpp -o tests/emul/_build/libgpc_emul.so
+// This file exports gpc_emul_run(), which calls the kernel body once per source vertex.
+#include "gpc_emul_shim.h"
+#include "_build/gcb_gpc_device_section.inc"
 
 extern "C" int64_t gpc_emul_smem_per_system(int32_t P) { return gcb::gpc_smem_per_system(P); }
 

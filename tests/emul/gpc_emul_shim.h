@@ -1,7 +1,9 @@
 // TEST INFRASTRUCTURE.  Lets g++ compile geoconv_b200/csrc/gcb_gpc.cu's algorithm text for the host with a
 // one-lane "warp" (GCB_WARP = 1): every warp-wide primitive degenerates to its single-lane meaning.  Used by
-// tests/test_gpc_wavefront.py (CPU suite) to run the kernel's logic against the reference fixtures without a GPU.
+// tests/test_gpc_wavefront.py (CPU suite) to run the kernel's logic against the reference fixtures without a GPU.  The harness (test_gpc_wavefront.py::emul) places the
+// device section of the product source behind this header, unchanged.
 #pragma once
+#include <float.h>
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>

@@ -113,8 +113,15 @@ def emul():
     out = os.path.join(HERE, "emul", "_build")
     os.makedirs(out, exist_ok=True)
     lib = os.path.join(out, "libgpc_emul.so")
-    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-DGCB_GPC_HOST_EMULATION", "-I", os.path.join(HERE, "emul"),
-                           "-x", "c++", os.path.join(HERE, "emul", "gpc_emul.cpp"), "-o", lib])
+    # the device section of the product source, verbatim: from below its #include of the CUDA helpers to the end of
+    # namespace gcb (what follows is the host launch code)
+    src = open(os.path.join(HERE, "..", "geoconv_b200", "csrc", "gcb_gpc.cu")).read()
+    begin = src.index('#include "gcb_common.cuh"') + len('#include "gcb_common.cuh"')
+    end = src.index("}  // namespace gcb") + len("}  // namespace gcb")
+    with open(os.path.join(out, "gcb_gpc_device_section.inc"), "w") as fh:
+        fh.write(src[begin:end] + "\n")
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-I", os.path.join(HERE, "emul"), "-x", "c++",
+                           os.path.join(HERE, "emul", "gpc_emul.cpp"), "-o", lib])
     h = ctypes.CDLL(lib)
     h.gpc_emul_run.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int32, ctypes.c_double, ctypes.c_double, ctypes.c_int32] + [ctypes.c_void_p] * 8
     return h
