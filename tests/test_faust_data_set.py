@@ -124,3 +124,40 @@ def test_device_cache_packs_every_mesh_once(archive):
     plain = DeviceFaustCache(archive, set_type=1, pack=False)
     (_s, bc), _ = next(iter(plain))
     assert not hasattr(bc, "_gcb_pack")
+
+
+def test_reader_matches_the_executed_reference():
+    """tests/golden/faust_reader_expected.npz holds what the reference's own faust_generator / FaustDataset yield on
+    tests/golden/faust_reader_archive.npz (make_golden_faust_reader.py): same order, values, noise and dtypes, bit for
+    bit - the reader draws from `random` / `numpy.random` exactly like the reference."""
+    import os
+    import random
+
+    import numpy as np
+    import torch
+
+    from geoconv_b200.data.faust_data_set import FaustDataset, faust_generator
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    archive = os.path.join(here, "faust_reader_archive.npz")
+    want = np.load(os.path.join(here, "faust_reader_expected.npz"))
+    for set_type in (0, 1, 2, 3):
+        random.seed(5)
+        np.random.seed(6)
+        got = list(faust_generator(archive, set_type=set_type))
+        assert len(got) == int(want[f"n_{set_type}"]) == {0: 70, 1: 10, 2: 20, 3: 100}[set_type]
+        assert [str(got[0][0][0].dtype), str(got[0][0][1].dtype), str(got[0][1].dtype)] == list(want[f"dtypes_{set_type}"])
+        assert np.array_equal(np.stack([s.numpy() for (s, _), _ in got]), want[f"signal_{set_type}"])
+        assert np.array_equal(np.stack([b.numpy() for (_, b), _ in got]), want[f"bc_{set_type}"])
+        assert np.array_equal(np.stack([g.numpy() for _, g in got]), want[f"gt_{set_type}"])
+    random.seed(8)
+    np.random.seed(9)
+    got = list(faust_generator(archive, set_type=0, set_indices=[4, 99, 0], return_coordinates=True))
+    assert np.array_equal(np.stack([c.numpy() for (_, _, c), _ in got]), want["coord_sel"])
+    assert np.array_equal(np.stack([b.numpy() for (_, b, _), _ in got]), want["bc_sel"])
+    only = np.stack([s.numpy() for s in faust_generator(archive, set_type=1, only_signal=True)])
+    assert np.array_equal(only, want["signal_only"])
+    ds = FaustDataset(archive, set_type=2)
+    first = next(iter(ds))
+    assert np.array_equal(first[1].numpy(), want["dataset_first_gt"])
+    ds.reset()
+    assert torch.equal(next(iter(ds))[0][0], first[0][0])
