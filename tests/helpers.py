@@ -19,7 +19,7 @@ def golden_cases(which="path"):
         return [n for n in names if n.startswith("gpc_")]
     if which == "wave":    # §8(f-1) fixtures: mesh -> GPC systems (the wavefront)
         return [n for n in names if n.startswith("wave_")]
-    names = [n for n in names if not n.startswith(("gpc_", "wave_"))]
+    names = [n for n in names if not n.startswith(("gpc_", "wave_", "faust_reader_"))]   # (§8 f-3 reader fixtures)
     is_next = lambda n: n.split("_")[0] in NEXT_PREFIXES  # noqa: E731
     if which == "all":
         return names
