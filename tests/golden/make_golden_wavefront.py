@@ -65,7 +65,7 @@ def reference_gpc_systems(mesh, u_max, eps=1e-6):
 
 
 def cases():
-    from oracle.mesh_stub import bumpy_grid, icosphere
+    from oracle.mesh_stub import blob, bumpy_grid, icosphere, torus
     v, f = icosphere(2, jitter=0.05, seed=3)
     yield "wave_ico2_jitter", v, f, 0.75, 3, 6, 0.5
     v, f = bumpy_grid(11, 9, seed=5)
@@ -74,13 +74,20 @@ def cases():
     yield "wave_ico1_wide", v, f, 1.6, 2, 4, 1.0
     v, f = icosphere(3, jitter=0.1, seed=11)
     yield "wave_ico3_patch60", v, f, 0.62, 5, 8, 0.45
+    v, f = torus(16, 9, seed=2)
+    yield "wave_torus", v, f, 0.75, 3, 8, 0.5
+    v, f = blob(2, seed=4)
+    yield "wave_blob", v, f, 0.8, 4, 6, 0.55
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])      # optional: regenerate the named cases only
     install_stub_modules()
     from geoconv.preprocessing.barycentric_coordinates import compute_barycentric_coordinates
     from oracle.mesh_stub import StubMesh
     for name, vertices, faces, u_max, n_radial, n_angular, radius in cases():
+        if only and name not in only:
+            continue
         mesh = StubMesh(vertices, faces)
         rho, theta, tri_idx, tri_ptr, group = reference_gpc_systems(mesh, u_max)
         bary = compute_barycentric_coordinates(group, n_radial=n_radial, n_angular=n_angular, radius=radius)
