@@ -940,6 +940,8 @@ def run_ours(args):
                 "serial_ms_per_step": e2e_serial_ms / args.steps,
                 "h2d_gbs_per_rank": h2d / (e2e_ms / args.steps * 1e-3) / 1e9,
                 "h2d_gbs_all_ranks": world * h2d / (e2e_ms / args.steps * 1e-3) / 1e9,
+                "h2d_gbs_note": "input bytes per step / step time = the rate the host has to sustain, not the speed of the copy "
+                                "(one 24 MB copy from the write-combined arena runs at ~45 GB/s and is hidden behind compute)",
                 "derivation": ("pipelined figure = device time of the timed loop minus the separately timed loop of its L2 "
                                "flushes (the flush is measurement apparatus, not part of a step); serial figure = per-step "
                                "events, flush outside") if e2e_mode_p else "per-step events, flush outside",
