@@ -832,7 +832,9 @@ _BN_WS: dict = {}
 
 
 def _bn_workspace(v: int, t: int, dev: torch.device) -> torch.Tensor:
-    """Column-reduction scratch; zeroed once (the kernels leave the ticket zero), grown on demand, per device."""
+    """Column-reduction scratch; zeroed once (the kernels leave the ticket zero), grown on demand, per device.
+    One scratch per device: calls on the same device are expected on ONE stream at a time (like the layers'
+    workspaces, which come from the caching allocator of the current stream)."""
     need = N.load().gcb_bn_workspace_bytes(v, t)
     ws = _BN_WS.get(dev)
     if ws is None or ws.numel() < need:
