@@ -1,6 +1,8 @@
 // One-time / per-step preparation kernels: bary split, CSR inversion, prior folding, row packing.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <stdlib.h>
+
 #include "gcb_common.cuh"
 #include "gcb_tc.cuh"
 
@@ -77,9 +79,11 @@ static int key_bits(int64_t max_key) {
 // input slot p a thread reads its own value once and the 8 prior elements as two broadcast
 // 128-bit loads, so the loop runs at 8 FMAs per 3 shared-memory instructions (the first version did
 // 1 FMA per 2 and was shared-memory-issue bound at 31 us for 8.4 MB).
-constexpr int FOLD_TB = 4;   // templates per block: the prior is staged once for all of them, their tiles fly together
-
-__global__ void __launch_bounds__(1024) k_fold_prior(const float* __restrict__ in, const float* __restrict__ prior,
+// FOLD_TB templates per block: the prior is staged once for all of them, their tiles fly together.  MAXT = the block
+// size bound (4 * RAp threads): 256 covers R*A <= 64 and leaves the compiler 255 registers instead of the 64 a bound of
+// 1024 allows (the 32 accumulators + 32 parked loads did not fit in 64).
+template <int MAXT, int FOLD_TB>
+__global__ void __launch_bounds__(MAXT) k_fold_prior(const float* __restrict__ in, const float* __restrict__ prior,
                                                     float* __restrict__ out, int T, int RA, int RAp, int F, int transpose) {
   extern __shared__ float4 s_mem4[];
   float* s_prior = reinterpret_cast<float*>(s_mem4);   // [RA][RAp]: s_prior[p*RAp + q] multiplies in[p] into out[q]
@@ -225,14 +229,19 @@ extern "C" int gcb_fold_prior(const float* in, const float* prior, float* out, i
   GCB_REQUIRE(T > 0 && R > 0 && A > 0 && F > 0, GCB_EINVAL, "gcb_fold_prior: bad sizes");
   int RA = R * A;
   const int RAp = (RA + 7) / 8 * 8;
-  size_t smem = ((size_t)RA * RAp + (size_t)FOLD_TB * RA * 32) * sizeof(float);
+  const int threads = RAp / 8 * 32;
+  const int tb = 4;   // templates per block (two per block, i.e. twice the blocks: 25.4 us against 23.9 for fold + unfold)
+  size_t smem = ((size_t)RA * RAp + (size_t)tb * RA * 32) * sizeof(float);
   GCB_REQUIRE(smem <= 160 * 1024 && RAp / 8 <= 32, GCB_EUNSUPPORTED, "gcb_fold_prior: R*A=%d too large", RA);
-  if (smem > 48 * 1024)
-    GCB_CUDA_OK(cudaFuncSetAttribute(k_fold_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div64(F, 32), (unsigned)ceil_div64(T, FOLD_TB));
-  k_fold_prior<<<grid, (unsigned)(RAp / 8 * 32), smem, (cudaStream_t)stream>>>(in, prior, out, T, RA, RAp, F, transpose);
-  GCB_LAUNCH_OK();
-  return GCB_OK;
+  dim3 grid((unsigned)ceil_div64(F, 32), (unsigned)ceil_div64(T, tb));
+  auto launch = [&](auto kernel) -> int {
+    if (smem > 48 * 1024)
+      GCB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, (unsigned)threads, smem, (cudaStream_t)stream>>>(in, prior, out, T, RA, RAp, F, transpose);
+    GCB_LAUNCH_OK();
+    return GCB_OK;
+  };
+  return threads > 256 ? launch(k_fold_prior<1024, 4>) : launch(k_fold_prior<256, 4>);
 }
 
 extern "C" int gcb_pack_rows(const float* src, const int32_t* rows, int32_t n_rows, int32_t F,
