@@ -261,51 +261,82 @@ static int tc_pick_phase_shift(const RotTable& rot, int n_rot, int A, int g, int
 }
 
 // dstep = 0: every rotation on its own (works for any rotation list)
+// One candidate (template chunk n_t, tile row width kc): the rotation grouping, the widest rotation merge whose
+// weight ring fits, the number of A stages.  ok = false if nothing fits in shared memory.
+static TcConfig tc_try_config(int A, int T, int n_rot, bool x3, int dstep, int ring_shift, int n_t, int kc) {
+  TcConfig c{};
+  c.ok = false;
+  const int nprod = x3 ? 2 : 1;
+  int g_max = 512 / n_t;
+  if (g_max > TC_G_MAX) g_max = TC_G_MAX;
+  if (g_max > n_rot) g_max = n_rot;
+  const int n_groups = (n_rot + g_max - 1) / g_max;
+  const int g = (n_rot + n_groups - 1) / n_groups;
+  int m_top = 1;
+  if (dstep > 0) {
+    const int L = A / gcd_int(dstep, A);
+    while (m_top * 2 <= g && m_top * 2 * n_t <= 256 && m_top * 2 - 1 < L) m_top *= 2;
+  }
+  for (int m = m_top; m >= 1; m >>= 1) {
+    TcRing ring = tc_ring_layout(A, dstep, m);
+    if (ring.n_pos > 32) continue;   // position masks are 32-bit
+    ring.shift = ring_shift;
+    const bool pairs = tc_use_pairs() && n_groups % 2 == 0 && kc >= 16;   // a pair member stages half of the records
+    size_t b_bytes = (size_t)(ring.n_pos + ring_shift) * nprod * n_t * kc * 4;
+    size_t a_stage = (size_t)nprod * TC_M * kc * 4;
+    size_t fixed = b_bytes + (size_t)A * TC_REC_BYTES / (pairs ? 2 : 1) + tc_bar_bytes(ring.n_pos, ring.n_pos + ring_shift) +
+                   tc_tab_bytes(A, ring.n_pos) + 1024 /* alignment slack */;
+    if (fixed + 4 * a_stage > (size_t)TC_SMEM_LIMIT) continue;
+    int ns_a = (int)(((size_t)TC_SMEM_LIMIT - fixed) / a_stage);
+    if (ns_a > 8) ns_a = 8;
+    static const int ns_cap = getenv("GCB_TC_NSA") ? atoi(getenv("GCB_TC_NSA")) : 0;   // experiments
+    if (ns_cap >= 3 && ns_a > ns_cap) ns_a = ns_cap;
+    int cols = 32;
+    while (cols < g * n_t) cols <<= 1;
+    c.kc = kc; c.n_t = n_t; c.g = g; c.n_groups = n_groups; c.ns_a = ns_a; c.tmem_cols = cols;
+    c.ring = ring;
+    c.smem_bytes = fixed + (size_t)ns_a * a_stage;
+    c.ok = true;
+    return c;
+  }
+  return c;
+}
+
+// Tile row width FIRST, template chunk second: a wide layer (T = 256, 384) does not fit its weight ring with the widest
+// rows AND the largest template chunk, and giving up the row width costs far more than giving up chunk width -
+// measured at V = 6890, 256 -> 384: 1428 us with kc = 8 (n_t as large as possible) against 925 us with kc = 16 in
+// the fp16-split mode, 963 against 714 us (kc = 16 / 32) in the TF32 mode (profiles/r02_notes.md, section 14).  Narrow
+// rows halve the work per tile, so twice as many barrier rounds, ring entries and staging fences per FLOP.
+// Chunks below 64 templates are only taken when nothing else fits (an MMA of N < 64 wastes the A operand reads).
 static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, bool half, int dstep, int ring_shift = 0) {
   TcConfig c{};
   c.ok = false;
   if (T % 16 != 0 || F % 8 != 0 || A > GCB_MAX_ROT || n_rot > GCB_MAX_ROT) return c;
-  const int nprod = x3 ? 2 : 1;
-  for (int n_t = (T < 256 ? T : 256); n_t >= 16; n_t -= 16) {
-    if (T % n_t != 0) continue;
-    int g_max = 512 / n_t;
-    if (g_max > TC_G_MAX) g_max = TC_G_MAX;
-    if (g_max > n_rot) g_max = n_rot;
-    const int n_groups = (n_rot + g_max - 1) / g_max;
-    const int g = (n_rot + n_groups - 1) / n_groups;
-    int m_top = 1;
-    if (dstep > 0) {
-      const int L = A / gcd_int(dstep, A);
-      while (m_top * 2 <= g && m_top * 2 * n_t <= 256 && m_top * 2 - 1 < L) m_top *= 2;
-    }
-    static const int kc_env = getenv("GCB_TC_KC") ? atoi(getenv("GCB_TC_KC")) : 0;   // experiments
-    // kc = 4-byte units per tile row; fp16 rows hold 2 * kc features and stay <= 64 bytes so that a producer
-    // lane keeps the same number of gathered float4 in flight as in the tf32 layouts
-    for (int kc = half ? 16 : 32; kc >= 8; kc >>= 1) {
+  static const int kc_env = getenv("GCB_TC_KC") ? atoi(getenv("GCB_TC_KC")) : 0;   // experiments
+  static const bool old_order = getenv("GCB_TC_NT_FIRST") && atoi(getenv("GCB_TC_NT_FIRST")) != 0;   // A/B: round-1 order
+  const int nt_top = T < 256 ? T : 256;
+  // kc = 4-byte units per tile row; fp16 rows hold 2 * kc features and stay <= 64 bytes so that a producer
+  // lane keeps the same number of gathered float4 in flight as in the tf32 layouts
+  const int kc_top = half ? 16 : 32;
+  if (!old_order) {
+    const int nt_floor = T < 64 ? T : 64;
+    for (int kc = kc_top; kc >= 8; kc >>= 1) {
       if (F % (half ? 2 * kc : kc) != 0) continue;
       if (kc_env > 0 && kc != kc_env) continue;
-      for (int m = m_top; m >= 1; m >>= 1) {
-        TcRing ring = tc_ring_layout(A, dstep, m);
-        if (ring.n_pos > 32) continue;   // position masks are 32-bit
-        ring.shift = ring_shift;
-        const bool pairs = tc_use_pairs() && n_groups % 2 == 0 && kc >= 16;   // a pair member stages half of the records
-        size_t b_bytes = (size_t)(ring.n_pos + ring_shift) * nprod * n_t * kc * 4;
-        size_t a_stage = (size_t)nprod * TC_M * kc * 4;
-        size_t fixed = b_bytes + (size_t)A * TC_REC_BYTES / (pairs ? 2 : 1) + tc_bar_bytes(ring.n_pos, ring.n_pos + ring_shift) +
-                       tc_tab_bytes(A, ring.n_pos) + 1024 /* alignment slack */;
-        if (fixed + 4 * a_stage > (size_t)TC_SMEM_LIMIT) continue;
-        int ns_a = (int)(((size_t)TC_SMEM_LIMIT - fixed) / a_stage);
-        if (ns_a > 8) ns_a = 8;
-        static const int ns_cap = getenv("GCB_TC_NSA") ? atoi(getenv("GCB_TC_NSA")) : 0;   // experiments
-        if (ns_cap >= 3 && ns_a > ns_cap) ns_a = ns_cap;
-        int cols = 32;
-        while (cols < g * n_t) cols <<= 1;
-        c.kc = kc; c.n_t = n_t; c.g = g; c.n_groups = n_groups; c.ns_a = ns_a; c.tmem_cols = cols;
-        c.ring = ring;
-        c.smem_bytes = fixed + (size_t)ns_a * a_stage;
-        c.ok = true;
-        return c;
+      for (int n_t = nt_top; n_t >= nt_floor; n_t -= 16) {
+        if (T % n_t != 0) continue;
+        c = tc_try_config(A, T, n_rot, x3, dstep, ring_shift, n_t, kc);
+        if (c.ok) return c;
       }
+    }
+  }
+  for (int n_t = nt_top; n_t >= 16; n_t -= 16) {
+    if (T % n_t != 0) continue;
+    for (int kc = kc_top; kc >= 8; kc >>= 1) {
+      if (F % (half ? 2 * kc : kc) != 0) continue;
+      if (kc_env > 0 && kc != kc_env) continue;
+      c = tc_try_config(A, T, n_rot, x3, dstep, ring_shift, n_t, kc);
+      if (c.ok) return c;
     }
   }
   return c;
