@@ -307,7 +307,8 @@ static TcConfig tc_try_config(int A, int T, int n_rot, bool x3, int dstep, int r
 // measured at V = 6890, 256 -> 384: 1428 us with kc = 8 (n_t as large as possible) against 925 us with kc = 16 in
 // the fp16-split mode, 963 against 714 us (kc = 16 / 32) in the TF32 mode (profiles/r02_notes.md, section 14).  Narrow
 // rows halve the work per tile, so twice as many barrier rounds, ring entries and staging fences per FLOP.
-// Chunks below 64 templates are only taken when nothing else fits (an MMA of N < 64 wastes the A operand reads).
+// The same holds for A = 12 at T = 96 (n_t = 48 with kc = 16: forward 1356 us, n_t = 96 with kc = 8: 1635 us at R = 5).
+// Chunks below 48 templates are only taken when nothing else fits.
 static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, bool half, int dstep, int ring_shift = 0) {
   TcConfig c{};
   c.ok = false;
@@ -319,7 +320,7 @@ static TcConfig tc_pick_config(int A, int F, int T, int n_rot, bool x3, bool hal
   // lane keeps the same number of gathered float4 in flight as in the tf32 layouts
   const int kc_top = half ? 16 : 32;
   if (!old_order) {
-    const int nt_floor = T < 64 ? T : 64;
+    const int nt_floor = T < 48 ? T : 48;
     for (int kc = kc_top; kc >= 8; kc >>= 1) {
       if (F % (half ? 2 * kc : kc) != 0) continue;
       if (kc_env > 0 && kc != kc_env) continue;

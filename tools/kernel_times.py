@@ -1,5 +1,5 @@
 """Warm per-kernel durations of one S1 step (fwd + AMP + bwd) from torch.profiler (CUPTI activity records),
-L2 flushed between steps.  usage: [GCB_KT_CLASS=geodesic|dirac|zero] [GCB_KT_V= GCB_KT_F= GCB_KT_T=] kernel_times.py [precision ...]"""
+L2 flushed between steps.  usage: [GCB_KT_CLASS=geodesic|dirac|zero] [GCB_KT_V= GCB_KT_F= GCB_KT_T= GCB_KT_R= GCB_KT_A=] kernel_times.py [precision ...]"""
 import collections, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,7 +11,7 @@ from geoconv_b200.pytorch.layers.conv_dirac import ConvDirac
 from geoconv_b200.pytorch.layers.conv_zero import ConvZero
 CLS = {"geodesic": ConvGeodesic, "dirac": ConvDirac, "zero": ConvZero}[os.environ.get("GCB_KT_CLASS", "geodesic")]
 
-v, f, r, a, t = int(os.environ.get("GCB_KT_V", 6890)), int(os.environ.get("GCB_KT_F", 544)), 5, 8, int(os.environ.get("GCB_KT_T", 96))
+v, f, r, a, t = int(os.environ.get("GCB_KT_V", 6890)), int(os.environ.get("GCB_KT_F", 544)), int(os.environ.get("GCB_KT_R", 5)), int(os.environ.get("GCB_KT_A", 8)), int(os.environ.get("GCB_KT_T", 96))
 dev = "cuda:0"
 wn, ws, b = S.make_weights(t, r, a, f, seed=0)
 x = S.make_signal(v, f, seed=1).to(dev).requires_grad_(True)
