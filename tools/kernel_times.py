@@ -51,3 +51,27 @@ for prec in sys.argv[1:] or ["fp32"]:
         total += per_step
         print(f"{per_step:9.1f}  x{len(ts) / STEPS:4.1f}  {name}")
     print(f"{total:9.1f}  sum of kernels per step")
+    # the same steps without the profiler, CUDA events around each (L2 flush outside): kernels + launch gaps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(STEPS)]
+    for e0, e1 in ev:
+        flush.zero_()
+        e0.record()
+        step()
+        e1.record()
+    torch.cuda.synchronize()
+    print(f"{sum(a.elapsed_time(b) for a, b in ev) / STEPS * 1e3:9.1f}  step by CUDA events (eager launches)")
+    # ... and with a host sync after every step (a loop that reads the loss each step): the GPU starts every step idle
+    import time
+    tot, host = 0.0, 0.0
+    for _ in range(STEPS):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        step()
+        e1.record()
+        host += time.perf_counter() - t0
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    print(f"{tot / STEPS * 1e3:9.1f}  step by CUDA events, host sync after every step (host time to enqueue a step: {host / STEPS * 1e6:.0f} us)")

@@ -52,8 +52,13 @@ def run(tag, kind, v, f, t, r, a, delta, iters=5):
     print(json.dumps(rec), flush=True)
 
 
+only_a = int(os.environ.get("GCB_SWEEP_ONLY_A", "0"))   # restrict the sweep to one angular size (A/B runs)
 for kind, r, a, delta in itertools.product(("geodesic", "dirac", "zero"), (3, 5, 8), (6, 8, 12), (1, 2)):
+    if only_a and (a != only_a or kind == "zero"):
+        continue
     run("S2 sweep", kind, 6890, 544, 96, r, a, delta)
+if only_a:
+    sys.exit(0)
 for fi, fo in ((64, 96), (96, 256), (256, 384)):
     run("S3 layer", "geodesic", 6890, fi, fo, 5, 8, 1)
 run("S4 layer", "geodesic", 250000, 128, 128, 5, 8, 1, iters=3)
