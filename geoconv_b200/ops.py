@@ -260,6 +260,16 @@ def pack_with_weights(base: BaryPack, w: torch.Tensor) -> BaryPack:
 _LIB = "geoconv_b200"
 
 
+def _direct(op, probe=None):
+    """The Python body behind a custom operator.  Outside a torch.compile trace (and off fake tensors) the layers call
+    the bodies directly (under a plain autograd.Function where a gradient is needed): the dispatcher adds 20-40 us of
+    host time per operator call, which a step that is read back every iteration pays in full
+    (profiles/r02_notes.md, section 15)."""
+    if torch.compiler.is_compiling() or (probe is not None and _is_fake(probe)):
+        return op
+    return op._init_fn
+
+
 def _dev_guard(t: torch.Tensor):
     return torch.cuda.device(t.device)
 
@@ -381,7 +391,7 @@ def _fold_setup(ctx, inputs, output):
 
 def _fold_backward(ctx, grad):
     (prior,) = ctx.saved_tensors
-    return fold_prior_op(grad, prior, 1 - ctx.transpose), None, None
+    return _direct(fold_prior_op, grad)(grad, prior, 1 - ctx.transpose), None, None
 
 
 fold_prior_op.register_autograd(_fold_backward, setup_context=_fold_setup)
@@ -393,7 +403,24 @@ class FoldPrior:
     @staticmethod
     def apply(w_neighbor: torch.Tensor, prior: torch.Tensor) -> torch.Tensor:
         _need_cuda(w_neighbor, "template weights")
-        return fold_prior_op(w_neighbor, prior.to(device=w_neighbor.device, dtype=torch.float32), 0)
+        prior = prior.to(device=w_neighbor.device, dtype=torch.float32)
+        if torch.compiler.is_compiling() or _is_fake(w_neighbor):
+            return fold_prior_op(w_neighbor, prior, 0)
+        return _EagerFold.apply(w_neighbor, prior, 0)
+
+
+class _EagerFold(torch.autograd.Function):
+    """fold_prior_op's body and autograd formula without the operator dispatcher (eager mode)."""
+
+    @staticmethod
+    def forward(ctx, inp, prior, transpose):
+        out = fold_prior_op._init_fn(inp, prior, transpose)
+        _fold_setup(ctx, (inp, prior, transpose), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        return _fold_backward(ctx, grad)
 
 
 # ---- the convolution (+ fused pooling outputs) --------------------------------------------------
@@ -689,18 +716,18 @@ def _conv_backward(ctx, grad_y, grad_z, _grad_arg, _grad_stats):
     if (sync is not None and sync.active and grad_y is None and need_dx and has_nb and not _is_fake(x) and
             N.load().gcb_conv_amp_bwd_can_split(idx.shape[1], idx.shape[2], x.shape[1], w_self.shape[0], ctx.precision, 1)):
         # data parallel: weight gradients first, their all-reduce (collective stream) beside the dSignal GEMM
-        _none, d_w_eff, d_w_self, d_bias, ws = conv_bwd_op(*args, 1, None)
+        _none, d_w_eff, d_w_self, d_bias, ws = _direct(conv_bwd_op, x)(*args, 1, None)
         if d_w_eff.numel() == 0:     # written into the peer reducer's staging area (see conv_bwd_op)
             t_, r_, a_, f_ = w_self.shape[0], idx.shape[1], idx.shape[2], x.shape[1]
             st_ = sync.peer_reducer.staging([t_ * r_ * a_ * f_, t_ * f_, t_], x.device)
             d_w_eff, d_w_self, d_bias = st_[0].view(t_, r_, a_, f_), st_[1].view(t_, f_), st_[2]
         staged = sync.reduce_early([d_w_eff, d_w_self, d_bias])
-        d_x = conv_bwd_op(*args, 2, ws)[0]
+        d_x = _direct(conv_bwd_op, x)(*args, 2, ws)[0]
         sync.join()
         if staged is not None:       # the sums sit in the collective's result area: private copies for autograd
             d_w_eff, d_w_self, d_bias = staged()
     else:
-        d_x, d_w_eff, d_w_self, d_bias, _ws = conv_bwd_op(*args, 3, None)
+        d_x, d_w_eff, d_w_self, d_bias, _ws = _direct(conv_bwd_op, x)(*args, 3, None)
     g_anchor = torch.zeros(ctx.anchor_shape, dtype=torch.float32, device=x.device) if ctx.has_anchor else None
     return (d_x if need_dx else None, d_w_eff if has_nb else None, d_w_self.reshape(ctx.w_self_shape),
             d_bias.reshape(ctx.bias_shape), None, None, g_anchor, None, None, None, None, None, None)
@@ -720,9 +747,26 @@ class ConvIntrinsicFn:
         records = None
         if prec_fwd != N.PREC_FP32 and w_eff is not None and not torch.compiler.is_compiling() and pack.v_out > 0:
             records = pack.records()
-        y, z, arg, _stats = conv_fwd_op(signal, w_eff, w_self, bias, pack.idx, pack.w, w_anchor, records,
-                                        [int(o) for o in rot_offsets], act_id, prec_fwd, prec_bwd, int(row0))
+        args = (signal, w_eff, w_self, bias, pack.idx, pack.w, w_anchor, records, [int(o) for o in rot_offsets], act_id,
+                prec_fwd, prec_bwd, int(row0))
+        traced = torch.compiler.is_compiling() or _is_fake(signal)
+        y, z, arg, _stats = conv_fwd_op(*args) if traced else _EagerConv.apply(*args)
         return y, z, arg
+
+
+class _EagerConv(torch.autograd.Function):
+    """conv_fwd_op's body and autograd formula without the operator dispatcher (eager mode)."""
+
+    @staticmethod
+    def forward(ctx, *inputs):
+        out = conv_fwd_op._init_fn(*inputs)
+        _conv_setup(ctx, inputs, out)
+        ctx.mark_non_differentiable(out[2], out[3])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_y, grad_z, _grad_arg, _grad_stats):
+        return _conv_backward(ctx, grad_y, grad_z, _grad_arg, _grad_stats)
 
 
 # ---- angular poolings on a materialised tensor ---------------------------------------------------
